@@ -1,0 +1,176 @@
+/*
+ * vtree_b200.h -- C ABI of the B200-native vocabulary-tree hot path.
+ *
+ * The reference (epignatelli/scalable-recognition-with-a-vocabulary-tree) is pure Python and
+ * has no FFI of its own; its "plugin API" is two duck-typed protocols (encoder:
+ * cbir/encoders/new_encoder_example.py:1-4, descriptor: cbir/descriptors/descriptor_base.py:14-21).
+ * The entry points below are what a binding for that path binds: one per hot function of
+ * cbir/encoders/vocabulary.py and cbir/database.py (cited on each declaration).  The Python
+ * package in this repo calls them through ctypes; INTEGRATION.md shows the stub a maintainer
+ * of the reference would add.
+ *
+ * Conventions
+ *   - every pointer named d_* is DEVICE memory owned by the caller (nothing is allocated or
+ *     freed behind the ABI except by the vt_pipe_* / vt_host_* helpers, which say so);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - every function returns 0 on success, a negative VT_E* code otherwise, and
+ *     vt_last_error() then returns a human-readable message (thread-local);
+ *   - descriptors are row-major [n, dp] with dp in {32, 64, 128} (rows zero padded up to dp),
+ *     dtype VT_U8 (bytes, what SIFT/ORB emit) or VT_F32;
+ *   - trees are implicit complete k-ary heaps: node h has children h*k+1 .. h*k+k, level l
+ *     starts at (k^l - 1)/(k - 1); d_centroids is float32 [n_heap, dp]; d_internal[h] != 0
+ *     iff node h has children; d_ref_id[h] is the id the reference gives that node (DFS
+ *     pre-order, vocabulary.py:70-75) or -1 when the node does not exist.
+ *   - distances follow the canonical contract in DESIGN.md section 3: the result always equals
+ *     the first-wins argmin of the binary64 evaluation of sum (c - x)^2 (fast float32 pass,
+ *     provable-margin check, binary64 re-evaluation of contested rows).
+ */
+#ifndef VTREE_B200_H
+#define VTREE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VT_ABI_VERSION 1
+
+enum { VT_U8 = 0, VT_F32 = 1 };
+enum { VT_OK = 0, VT_EINVAL = -1, VT_ECUDA = -2, VT_EUNSUPPORTED = -3, VT_ENOMEM = -4 };
+/* scoring modes: integer tf dot product (reference semantics), float dot product (tf-idf,
+ * L2-normalised weights), float L1 form of Nister & Stewenius eq. (5) */
+enum { VT_SCORE_TF_L2 = 0, VT_SCORE_W_L2 = 1, VT_SCORE_W_L1 = 2 };
+
+int         vt_abi_version(void);
+const char *vt_last_error(void);
+/* sm_count, cc_major, cc_minor of the current device; fails when no sm_100 device is present */
+int vt_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---- descriptor staging (input side of vocabulary.py:29-34 extract_features) ------------- */
+/* float32 [n, d] -> bytes [n, dp] zero padded.  *d_flag (device int, caller zeroes it) is set
+ * to 1 when some value is not an integer in 0..255 (the conversion would be lossy). */
+int vt_stage_f32_to_u8(const float *d_src, int64_t n, int d, uint8_t *d_dst, int dp,
+                       int *d_flag, void *stream);
+/* generic row padder: [n, d] elements of elem_size bytes -> [n, dp], zero filled */
+int vt_stage_pad(const void *d_src, int64_t n, int d, void *d_dst, int dp, int elem_size,
+                 void *stream);
+
+/* ---- greedy descent: VocabularyTree.propagate_feature, vocabulary.py:104-124 ------------- */
+/* For each descriptor, walks from heap node `start` while the node is internal, picking the
+ * child with the smallest L2 distance (first child wins exact ties, vocabulary.py:119).
+ *   d_leaf_heap [n]  (nullable) heap index of the stop node
+ *   d_word      [n]  (nullable) d_ref_id[stop node] -- the reference's node id
+ *   d_stats     [4]  (nullable, uint64, caller zeroes) [0] += rows re-evaluated in binary64 */
+int vt_quantize(const void *d_desc, int dtype, int64_t n, int dp,
+                const float *d_centroids, const uint8_t *d_internal, const int32_t *d_ref_id,
+                int k, int depth, int32_t start,
+                int32_t *d_leaf_heap, int32_t *d_word, uint64_t *d_stats, void *stream);
+
+/* Host-buffer convenience used for end-to-end timing: descriptors in (preferably pinned) host
+ * memory are streamed to the device in chunks on internal streams (copy/compute overlap), word
+ * ids are copied back to h_word.  The tree stays device resident.  `chunk_rows` <= 0 picks a
+ * default.  Blocks until h_word is complete. */
+int vt_quantize_host(const void *h_desc, int dtype, int64_t n, int dp,
+                     const float *d_centroids, const uint8_t *d_internal, const int32_t *d_ref_id,
+                     int k, int depth, int32_t *h_word, int64_t chunk_rows);
+
+/* ---- tree build: VocabularyTree.fit, vocabulary.py:36-76, one LEVEL per call -------------
+ * Members of all nodes of a level are processed in one launch.  d_perm[p] is the descriptor
+ * row of member p, d_parent[p] the index (within its level) of the node it belongs to; members
+ * are grouped by node in stable (original) order.  Child c of level-node j is level-node
+ * j*k + c of the next level; d_child_centroids points at the next level's first row. */
+/* initial centres: child c of node j <- member floor(c*m_j/k) of node j, for nodes with
+ * d_seg_count[j] >= k (others are leaves, vocabulary.py:55).  d_seg_begin/d_seg_count: [n_nodes].
+ * Multi-GPU: pass the GLOBAL member count in d_seg_count_global and this rank's global starting
+ * rank inside each node in d_seg_rank0 (both nullable => single GPU); rows this rank does not
+ * own are left untouched (caller zeroes and all-reduces). */
+int vt_kmeans_init(const void *d_desc, int dtype, int dp, const int32_t *d_perm,
+                   const int64_t *d_seg_begin, const int64_t *d_seg_count,
+                   const int64_t *d_seg_count_global, const int64_t *d_seg_rank0,
+                   int64_t n_nodes, int k, float *d_child_centroids, void *stream);
+/* assignment + exact accumulation (replaces sklearn's E and M step sums, _kmeans.py:1566-1684):
+ *   d_label [n_members] in/out uint8 -- previous labels in, new labels out
+ *   d_sums  [n_nodes*k, dp] uint64, d_counts [n_nodes*k] uint64 -- caller zeroes; integer sums
+ *            are exact, hence identical on any number of GPUs after an all-reduce
+ *   d_changed (uint64) += number of members whose label changed
+ *   d_stats as in vt_quantize.  Members whose node is a leaf (d_node_internal[j]==0) are skipped. */
+int vt_kmeans_assign(const void *d_desc, int dtype, int dp, const int32_t *d_perm,
+                     const int32_t *d_parent, int64_t n_members, const uint8_t *d_node_internal,
+                     int64_t n_nodes, int k, const float *d_child_centroids, uint8_t *d_label,
+                     uint64_t *d_sums, uint64_t *d_counts, uint64_t *d_changed,
+                     uint64_t *d_stats, void *stream);
+/* centre = (float)((double)sum / (double)count) where count > 0; empty clusters keep their centre */
+int vt_kmeans_update(const uint64_t *d_sums, const uint64_t *d_counts, int64_t n_rows, int dp,
+                     float *d_child_centroids, void *stream);
+/* exact column sums of all rows (root value = mean of all features, vocabulary.py:48-49) */
+int vt_column_sums(const void *d_desc, int dtype, int64_t n, int dp, uint64_t *d_sums, void *stream);
+/* keys for the stable partition at the end of a level (vocabulary.py:64-66):
+ * key[p] = d_parent[p]*k + d_label[p] for members of internal nodes, `sentinel` otherwise */
+int vt_partition_keys(const int32_t *d_parent, const uint8_t *d_label, int64_t n_members,
+                      const uint8_t *d_node_internal, int k, uint32_t sentinel, uint32_t *d_keys,
+                      void *stream);
+
+/* ---- stable LSD radix sort of (uint32 key, uint32 value) pairs on bits [0, n_bits) --------
+ * d_tmp_* are scratch of the same size; d_hist is scratch of vt_sort_scratch_bytes(n) bytes.
+ * *result_in_tmp tells which buffer pair holds the sorted output. */
+int64_t vt_sort_scratch_bytes(int64_t n);
+int vt_sort_pairs(uint32_t *d_keys, uint32_t *d_vals, uint32_t *d_tmp_keys, uint32_t *d_tmp_vals,
+                  int64_t n, int n_bits, void *d_hist, int *result_in_tmp, void *stream);
+
+/* ---- bag-of-words encoding: VocabularyTree.propagate + embedding, vocabulary.py:78-137 ----
+ * d_word [n_desc] reference node ids of the stop nodes, grouped by image (d_img_off [n_img+1]);
+ * max_words = largest number of descriptors in one image (<= vt_encode_max_words()).
+ * all_nodes != 0 counts every node on the path (reference semantics, vocabulary.py:92-100) using
+ * d_parent_ref/d_level_ref ([n_ref] parent id / depth of each reference node); 0 counts stop
+ * nodes only ("leaf words").  Two-pass CSR: call with d_out_node == NULL to get d_nnz [n_img]
+ * (entries per image), prefix-sum it into d_row_off [n_img+1], call again to fill.
+ *   d_out_node/d_out_count : CSR columns (reference node id) and term frequencies
+ *   d_sumsq [n_img] uint64 : sum of squared counts (exact squared L2 norm), written in pass 2
+ *   d_df    [n_ref] uint32 : (nullable) document frequency, += 1 per (image, node), pass 2 */
+int vt_encode(const int32_t *d_word, const int64_t *d_img_off, int64_t n_img, int32_t max_words,
+              int all_nodes, const int32_t *d_parent_ref, const uint8_t *d_level_ref, int depth,
+              int32_t *d_nnz, const int64_t *d_row_off, int32_t *d_out_node, int32_t *d_out_count,
+              uint64_t *d_sumsq, uint32_t *d_df, void *stream);
+int vt_encode_max_words(void);
+
+/* ---- inverted file: the dict-per-node postings of vocabulary.py:96-100 as CSR, sharded by image
+ * range (vt_score_shard_size() images per shard).  Row key = (img / shard_size) * n_ref + node.
+ * vt_posting_keys writes, for every forward-CSR entry e, its key, e itself and its image;
+ * sort (key, e) with vt_sort_pairs (stable => postings stay in image order); vt_posting_fill then
+ * gathers the postings (uint32 local image id, uint32 payload = tf count, or float weight bits
+ * when d_weight is given) and derives the row pointers d_post_off [n_keys + 1] (uint32). */
+int vt_posting_keys(const int64_t *d_row_off, const int32_t *d_node, int64_t n_img,
+                    int32_t shard_size, int64_t n_ref, uint32_t *d_keys, uint32_t *d_entry,
+                    int32_t *d_entry_img, void *stream);
+int vt_posting_fill(const uint32_t *d_sorted_keys, const uint32_t *d_sorted_entry, int64_t nnz,
+                    const int32_t *d_entry_img, const int32_t *d_count, const float *d_weight,
+                    int32_t shard_size, int64_t n_keys, uint32_t *d_post_off, void *d_postings,
+                    void *stream);
+
+/* ---- scoring + top-k: Database.score / Database.retrieve, database.py:59-81 -----------------
+ * Queries are a CSR batch (d_q_off [n_query+1], d_q_node, d_q_val = tf as float or weight).
+ * vt_score_topk writes, per (query, shard), the topk best (rank key, global image id) pairs:
+ * d_shard_key / d_shard_id [n_query, n_shards, topk] (id -1 = no candidate); optionally every
+ * image's rank key in d_all_key [n_query, n_img].  vt_topk_merge merges n_cand candidates per
+ * query (shards of one GPU, or the all-gathered lists of several GPUs) into the final topk and
+ * converts keys to the reference's score.  Order: key descending == score ascending, ties by
+ * ascending image index (the reference's stable sort, database.py:79-80).
+ *   d_img_rnorm [n_img]: 1/||tf_d||_2 as double, -1 for images without descriptors (vt_rnorm)
+ *   d_q_rnorm / d_q_sumsq [n_query], d_img_sumsq [n_img]: norms for the final score (tf mode) */
+int vt_score_shard_size(void);
+int vt_score_max_topk(void);
+int vt_rnorm(const uint64_t *d_sumsq, int64_t n, double *d_rnorm, void *stream);
+int vt_score_topk(const uint32_t *d_post_off, const void *d_postings, const double *d_img_rnorm,
+                  int64_t n_img, int64_t n_ref, const int64_t *d_q_off, const int32_t *d_q_node,
+                  const float *d_q_val, int64_t n_query, int mode, int topk, double *d_shard_key,
+                  int32_t *d_shard_id, double *d_all_key, void *stream);
+int vt_topk_merge(const double *d_in_key, const int32_t *d_in_id, int64_t n_query, int n_cand,
+                  int topk, int mode, const double *d_q_rnorm, const uint64_t *d_q_sumsq,
+                  const uint64_t *d_img_sumsq, double *d_out_key, int32_t *d_out_id,
+                  double *d_out_score, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VTREE_B200_H */

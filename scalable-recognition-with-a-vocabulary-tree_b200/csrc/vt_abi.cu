@@ -1,0 +1,106 @@
+// vt_abi.cu -- error plumbing, device info and descriptor staging kernels of the C ABI.
+#include "vt_common.cuh"
+#include <stdarg.h>
+#include <string.h>
+
+static thread_local char g_err[512] = "";
+
+void vt_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+extern "C" int vt_abi_version(void) { return VT_ABI_VERSION; }
+extern "C" const char *vt_last_error(void) { return g_err; }
+
+int vt_sm_count()
+{
+    static int cached = 0;
+    if (!cached) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            cached = n;
+        else
+            return 148;
+    }
+    return cached;
+}
+
+extern "C" int vt_device_info(int *sm_count, int *cc_major, int *cc_minor)
+{
+    int dev = 0, n = 0, ma = 0, mi = 0;
+    VT_CUDA(cudaGetDevice(&dev));
+    VT_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    VT_CUDA(cudaDeviceGetAttribute(&ma, cudaDevAttrComputeCapabilityMajor, dev));
+    VT_CUDA(cudaDeviceGetAttribute(&mi, cudaDevAttrComputeCapabilityMinor, dev));
+    if (sm_count) *sm_count = n;
+    if (cc_major) *cc_major = ma;
+    if (cc_minor) *cc_minor = mi;
+    if (ma != 10) {
+        vt_set_error("vt_device_info: device is sm_%d%d; this library only carries sm_100a code", ma, mi);
+        return VT_EUNSUPPORTED;
+    }
+    return VT_OK;
+}
+
+// ---- staging ------------------------------------------------------------------------------------
+__global__ void stage_f32_to_u8_kernel(const float *__restrict__ src, int64_t n, int d, uint8_t *__restrict__ dst,
+                                       int dp, int *__restrict__ flag)
+{
+    const int64_t total = n * (int64_t)dp;
+    bool bad = false;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / dp;
+        const int c = (int)(t - r * dp);
+        uint8_t out = 0;
+        if (c < d) {
+            const float v = src[r * d + c];
+            const float q = rintf(v);
+            if (!(q == v) || v < 0.f || v > 255.f) bad = true;
+            out = (uint8_t)fminf(fmaxf(q, 0.f), 255.f);
+        }
+        dst[t] = out;
+    }
+    if (__any_sync(VT_FULL, bad) && (threadIdx.x & 31) == 0) atomicExch(flag, 1);
+}
+
+extern "C" int vt_stage_f32_to_u8(const float *d_src, int64_t n, int d, uint8_t *d_dst, int dp, int *d_flag, void *stream)
+{
+    VT_CHECK_ARG(n >= 0 && d > 0 && dp >= d, "bad shape");
+    if (n == 0) return VT_OK;
+    const int64_t total = n * (int64_t)dp;
+    const int blocks = (int)((total + 255) / 256 < (int64_t)vt_sm_count() * 16 ? (total + 255) / 256 : (int64_t)vt_sm_count() * 16);
+    stage_f32_to_u8_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_src, n, d, d_dst, dp, d_flag);
+    VT_LAUNCH_CHECK();
+    return VT_OK;
+}
+
+template <typename E>
+__global__ void stage_pad_kernel(const E *__restrict__ src, int64_t n, int d, E *__restrict__ dst, int dp)
+{
+    const int64_t total = n * (int64_t)dp;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / dp;
+        const int c = (int)(t - r * dp);
+        dst[t] = c < d ? src[r * d + c] : (E)0;
+    }
+}
+
+extern "C" int vt_stage_pad(const void *d_src, int64_t n, int d, void *d_dst, int dp, int elem_size, void *stream)
+{
+    VT_CHECK_ARG(n >= 0 && d > 0 && dp >= d, "bad shape");
+    VT_CHECK_ARG(elem_size == 1 || elem_size == 4, "elem_size must be 1 or 4");
+    if (n == 0) return VT_OK;
+    const int64_t total = n * (int64_t)dp;
+    const int blocks = (int)((total + 255) / 256 < (int64_t)vt_sm_count() * 16 ? (total + 255) / 256 : (int64_t)vt_sm_count() * 16);
+    if (elem_size == 1)
+        stage_pad_kernel<uint8_t><<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint8_t *)d_src, n, d, (uint8_t *)d_dst, dp);
+    else
+        stage_pad_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float *)d_src, n, d, (float *)d_dst, dp);
+    VT_LAUNCH_CHECK();
+    return VT_OK;
+}

@@ -1,0 +1,285 @@
+// vt_encode.cu -- bag-of-words encoding of a batch of images (VocabularyTree.propagate +
+// embedding, cbir/encoders/vocabulary.py:78-137) and inverted-file construction.
+//
+// One CTA per image: the image's stop-node ids (reference DFS ids) are sorted in shared memory
+// (bitonic), run-length encoded into (node, tf) pairs, and -- in the reference's "all nodes"
+// semantics (vocabulary.py:92-100 counts every node on the path) -- lifted level by level:
+// because reference ids are DFS pre-order, the parents of an id-sorted list are still sorted, so
+// every level is one parent lookup + one adjacent-merge.  HBM traffic per image is the 4 B/word
+// read plus the 8 B/entry CSR write; everything else stays in shared memory.
+#include "vt_common.cuh"
+
+namespace {
+constexpr int ENC_THREADS = 256;
+constexpr int ENC_WARPS = ENC_THREADS / 32;
+constexpr int ENC_MAX = 8192;
+
+struct ScanScratch { uint32_t wsum[ENC_WARPS]; };
+
+// in-place exclusive scan of a[0..len) (uint32, shared memory); returns the total to every thread
+__device__ uint32_t block_excl_scan(uint32_t *a, int len, ScanScratch &sc)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t carry = 0;
+    for (int base = 0; base < len; base += ENC_THREADS) {
+        const int idx = base + threadIdx.x;
+        const uint32_t v = idx < len ? a[idx] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(VT_FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) sc.wsum[warp] = incl;
+        __syncthreads();
+        uint32_t woff = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < ENC_WARPS; ++w) {
+            const uint32_t t = sc.wsum[w];
+            if (w < warp) woff += t;
+            total += t;
+        }
+        if (idx < len) a[idx] = carry + woff + incl - v;
+        carry += total;
+        __syncthreads();
+    }
+    return carry;
+}
+
+__device__ void bitonic_sort(uint32_t *key, int p2)
+{
+    for (int size = 2; size <= p2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < (p2 >> 1); t += ENC_THREADS) {
+                const int lo = 2 * t - (t & (stride - 1));        // index with bit `stride` clear
+                const int hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const uint32_t a = key[lo], b = key[hi];
+                if ((a > b) == up) { key[lo] = b; key[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// CAP: shared-memory capacity in words per array (power of two)
+template <int CAP>
+__global__ void __launch_bounds__(ENC_THREADS)
+encode_kernel(const int32_t *__restrict__ word, const int64_t *__restrict__ img_off, int64_t n_img, int all_nodes,
+              const int32_t *__restrict__ parent_ref, const uint8_t *__restrict__ level_ref, int depth,
+              int32_t *__restrict__ nnz_out, const int64_t *__restrict__ row_off, int32_t *__restrict__ out_node,
+              int32_t *__restrict__ out_count, unsigned long long *__restrict__ sumsq, uint32_t *__restrict__ df)
+{
+    extern __shared__ uint32_t smem[];
+    uint32_t *A = smem;                 // ids
+    uint32_t *C = smem + CAP;           // counts
+    uint32_t *A2 = smem + 2 * CAP;      // scratch: flags / positions / merged ids
+    uint32_t *C2 = smem + 3 * CAP;      // scratch: merged counts
+    __shared__ ScanScratch sc;
+    __shared__ unsigned long long s_sq;
+    const bool fill = out_node != nullptr;
+
+    for (int64_t img = blockIdx.x; img < n_img; img += gridDim.x) {
+        const int64_t beg = img_off[img];
+        const int n = (int)(img_off[img + 1] - beg);
+        int64_t out_base = fill ? row_off[img] : 0;
+        uint32_t emitted = 0;
+        if (threadIdx.x == 0) s_sq = 0ull;
+        if (n == 0) {
+            if (threadIdx.x == 0) { if (!fill) nnz_out[img] = 0; else if (sumsq) sumsq[img] = 0ull; }
+            __syncthreads();
+            continue;
+        }
+        int p2 = 32;
+        while (p2 < n) p2 <<= 1;
+        for (int t = threadIdx.x; t < p2; t += ENC_THREADS) A[t] = t < n ? (uint32_t)word[beg + t] : 0xffffffffu;
+        __syncthreads();
+        bitonic_sort(A, p2);
+        // run-length encode A[0..n) -> (A2 ids, C counts), m distinct
+        for (int t = threadIdx.x; t < n; t += ENC_THREADS) C2[t] = (t == 0 || A[t] != A[t - 1]) ? 1u : 0u;
+        __syncthreads();
+        int m = (int)block_excl_scan(C2, n, sc);                       // C2[t] = output slot of t if head
+        for (int t = threadIdx.x; t < n; t += ENC_THREADS)
+            if (t == 0 || A[t] != A[t - 1]) { A2[C2[t]] = A[t]; C[C2[t]] = (uint32_t)t; }   // C = run start
+        __syncthreads();
+        for (int t = threadIdx.x; t < m; t += ENC_THREADS) {
+            const uint32_t start = C[t];
+            const uint32_t end = t + 1 < m ? C[t + 1] : (uint32_t)n;
+            C2[t] = end - start;
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < m; t += ENC_THREADS) { A[t] = A2[t]; C[t] = C2[t]; }
+        __syncthreads();
+
+        // emit levels from the deepest up; without all_nodes emit everything at once
+        unsigned long long sq = 0ull;
+        const int first_level = all_nodes ? depth : 0;
+        for (int dd = first_level; dd >= 0; --dd) {
+            // flag entries that leave the working list at this step
+            for (int t = threadIdx.x; t < m; t += ENC_THREADS)
+                A2[t] = (!all_nodes || level_ref[A[t]] == dd) ? 1u : 0u;
+            __syncthreads();
+            const uint32_t n_emit = block_excl_scan(A2, m, sc);
+            for (int t = threadIdx.x; t < m; t += ENC_THREADS) {
+                const bool mine = !all_nodes || level_ref[A[t]] == dd;
+                if (mine) {
+                    const uint32_t cnt = C[t];
+                    sq += (unsigned long long)cnt * cnt;
+                    if (fill) {
+                        const int64_t o = out_base + emitted + A2[t];
+                        out_node[o] = (int32_t)A[t];
+                        out_count[o] = (int32_t)cnt;
+                        if (df) atomicAdd(&df[A[t]], 1u);
+                    }
+                }
+            }
+            emitted += n_emit;
+            __syncthreads();
+            if (!all_nodes || dd == 0) break;
+            // lift: entries of level dd move to their parent, then merge adjacent equal ids
+            for (int t = threadIdx.x; t < m; t += ENC_THREADS)
+                if (level_ref[A[t]] == dd) A[t] = (uint32_t)parent_ref[A[t]];
+            __syncthreads();
+            for (int t = threadIdx.x; t < m; t += ENC_THREADS) A2[t] = (t == 0 || A[t] != A[t - 1]) ? 1u : 0u;
+            __syncthreads();
+            const int m2 = (int)block_excl_scan(A2, m, sc);            // A2[t]: slot of the run t starts
+            for (int t = threadIdx.x; t < m2; t += ENC_THREADS) C2[t] = 0u;
+            __syncthreads();
+            for (int t = threadIdx.x; t < m; t += ENC_THREADS) {
+                const bool head = (t == 0 || A[t] != A[t - 1]);
+                const uint32_t slot = head ? A2[t] : A2[t] - 1u;       // exclusive scan: non-heads see slot+1
+                atomicAdd(&C2[slot], C[t]);
+            }
+            __syncthreads();
+            // C is consumed: reuse it to stage the merged id list, then swap both lists in
+            for (int t = threadIdx.x; t < m; t += ENC_THREADS)
+                if (t == 0 || A[t] != A[t - 1]) C[A2[t]] = A[t];
+            __syncthreads();
+            for (int t = threadIdx.x; t < m2; t += ENC_THREADS) { A[t] = C[t]; C[t] = C2[t]; }
+            __syncthreads();
+            m = m2;
+        }
+        // per-image statistics
+        atomicAdd(&s_sq, sq);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (!fill) nnz_out[img] = (int32_t)emitted;
+            else if (sumsq) sumsq[img] = s_sq;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- inverted file ------------------------------------------------------------------------------
+__global__ void posting_keys_kernel(const int64_t *__restrict__ row_off, const int32_t *__restrict__ node, int64_t n_img,
+                                    int32_t shard_size, int64_t n_ref, uint32_t *__restrict__ keys,
+                                    uint32_t *__restrict__ entry, int32_t *__restrict__ entry_img)
+{
+    for (int64_t img = blockIdx.x; img < n_img; img += gridDim.x) {
+        const int64_t b = row_off[img], e = row_off[img + 1];
+        const uint32_t shard_base = (uint32_t)((img / shard_size) * n_ref);
+        for (int64_t t = b + threadIdx.x; t < e; t += blockDim.x) {
+            keys[t] = shard_base + (uint32_t)node[t];
+            entry[t] = (uint32_t)t;
+            entry_img[t] = (int32_t)img;
+        }
+    }
+}
+
+__global__ void posting_fill_kernel(const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ sentry, int64_t nnz,
+                                    const int32_t *__restrict__ entry_img, const int32_t *__restrict__ count,
+                                    const float *__restrict__ weight, int32_t shard_size, int64_t n_keys,
+                                    uint32_t *__restrict__ post_off, uint2 *__restrict__ postings)
+{
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t key = skeys[p];
+        const uint32_t e = sentry[p];
+        const uint32_t local = (uint32_t)(entry_img[e] % shard_size);
+        postings[p] = make_uint2(local, weight ? __float_as_uint(weight[e]) : (uint32_t)count[e]);
+        // row pointers: every key in (previous key, key] starts at p
+        const int64_t prev = p == 0 ? -1 : (int64_t)skeys[p - 1];
+        for (int64_t kk = prev + 1; kk <= (int64_t)key; ++kk) post_off[kk] = (uint32_t)p;
+        if (p == nnz - 1)
+            for (int64_t kk = (int64_t)key + 1; kk <= n_keys; ++kk) post_off[kk] = (uint32_t)nnz;
+    }
+}
+
+__global__ void fill_u32_kernel(uint32_t *a, int64_t n, uint32_t v)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) a[t] = v;
+}
+}  // namespace
+
+extern "C" int vt_encode_max_words(void) { return ENC_MAX; }
+
+template <int CAP>
+static int launch_encode(const int32_t *word, const int64_t *img_off, int64_t n_img, int all_nodes,
+                         const int32_t *parent_ref, const uint8_t *level_ref, int depth, int32_t *nnz,
+                         const int64_t *row_off, int32_t *out_node, int32_t *out_count, uint64_t *sumsq, uint32_t *df,
+                         cudaStream_t s)
+{
+    auto kern = encode_kernel<CAP>;
+    const size_t smem = (size_t)4 * CAP * sizeof(uint32_t);
+    VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t cap = (int64_t)vt_sm_count() * (CAP <= 2048 ? 6 : 1);
+    const int blocks = (int)(n_img < cap ? n_img : cap);
+    kern<<<blocks, ENC_THREADS, smem, s>>>(word, img_off, n_img, all_nodes, parent_ref, level_ref, depth, nnz, row_off,
+                                           out_node, out_count, (unsigned long long *)sumsq, df);
+    VT_LAUNCH_CHECK();
+    return VT_OK;
+}
+
+extern "C" int vt_encode(const int32_t *d_word, const int64_t *d_img_off, int64_t n_img, int32_t max_words,
+                         int all_nodes, const int32_t *d_parent_ref, const uint8_t *d_level_ref, int depth,
+                         int32_t *d_nnz, const int64_t *d_row_off, int32_t *d_out_node, int32_t *d_out_count,
+                         uint64_t *d_sumsq, uint32_t *d_df, void *stream)
+{
+    VT_CHECK_ARG(n_img >= 0 && d_img_off, "bad image offsets");
+    VT_CHECK_ARG(max_words >= 0 && max_words <= ENC_MAX, "an image has more descriptors than vt_encode_max_words()");
+    VT_CHECK_ARG(!all_nodes || (d_parent_ref && d_level_ref), "all_nodes needs parent/level tables");
+    VT_CHECK_ARG((d_out_node == nullptr) == (d_out_count == nullptr), "out_node/out_count must come together");
+    VT_CHECK_ARG(d_out_node != nullptr || d_nnz != nullptr, "count pass needs d_nnz");
+    VT_CHECK_ARG(d_out_node == nullptr || d_row_off != nullptr, "fill pass needs d_row_off");
+    if (n_img == 0) return VT_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+#define VT_E(CAPV) return launch_encode<CAPV>(d_word, d_img_off, n_img, all_nodes, d_parent_ref, d_level_ref, depth, d_nnz, d_row_off, d_out_node, d_out_count, d_sumsq, d_df, s)
+    if (max_words <= 1024) VT_E(1024);
+    if (max_words <= 2048) VT_E(2048);
+    VT_E(8192);
+#undef VT_E
+}
+
+extern "C" int vt_posting_keys(const int64_t *d_row_off, const int32_t *d_node, int64_t n_img, int32_t shard_size,
+                               int64_t n_ref, uint32_t *d_keys, uint32_t *d_entry, int32_t *d_entry_img, void *stream)
+{
+    VT_CHECK_ARG(n_img >= 0 && shard_size > 0 && n_ref > 0, "bad sizes");
+    const int64_t n_shards = (n_img + shard_size - 1) / shard_size;
+    VT_CHECK_ARG(n_shards * n_ref < ((int64_t)1 << 32), "shards * nodes must fit 32 bits");
+    if (n_img == 0) return VT_OK;
+    const int64_t cap = (int64_t)vt_sm_count() * 16;
+    posting_keys_kernel<<<(int)(n_img < cap ? n_img : cap), 128, 0, (cudaStream_t)stream>>>(
+        d_row_off, d_node, n_img, shard_size, n_ref, d_keys, d_entry, d_entry_img);
+    VT_LAUNCH_CHECK();
+    return VT_OK;
+}
+
+extern "C" int vt_posting_fill(const uint32_t *d_sorted_keys, const uint32_t *d_sorted_entry, int64_t nnz,
+                               const int32_t *d_entry_img, const int32_t *d_count, const float *d_weight,
+                               int32_t shard_size, int64_t n_keys, uint32_t *d_post_off, void *d_postings, void *stream)
+{
+    VT_CHECK_ARG(nnz >= 0 && nnz < ((int64_t)1 << 32) && n_keys >= 0 && shard_size > 0, "bad sizes");
+    VT_CHECK_ARG(d_count || d_weight, "need counts or weights");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (nnz == 0) {
+        const int64_t cap = (int64_t)vt_sm_count() * 16, want = (n_keys + 1 + 255) / 256;
+        fill_u32_kernel<<<(int)(want < cap ? want : cap), 256, 0, s>>>(d_post_off, n_keys + 1, 0u);
+        VT_LAUNCH_CHECK();
+        return VT_OK;
+    }
+    const int64_t cap = (int64_t)vt_sm_count() * 16, want = (nnz + 255) / 256;
+    posting_fill_kernel<<<(int)(want < cap ? want : cap), 256, 0, s>>>(d_sorted_keys, d_sorted_entry, nnz, d_entry_img,
+                                                                       d_count, d_weight, shard_size, n_keys, d_post_off,
+                                                                       (uint2 *)d_postings);
+    VT_LAUNCH_CHECK();
+    return VT_OK;
+}

@@ -1,0 +1,167 @@
+// vt_quantize.cu -- fused L-level greedy tree descent (VocabularyTree.propagate_feature,
+// cbir/encoders/vocabulary.py:104-124) for a whole batch of descriptors.
+//
+// Mapping: 8 lanes per descriptor (4 descriptors per warp); a lane keeps DP/8 dimensions of its
+// descriptor in registers for the whole descent, so the descriptor is read from HBM exactly once
+// (DP bytes for u8 input) and only the 4-byte word id is written.  Child centroids are streamed
+// through L1/L2 as coalesced 128 B rows.  Algorithmic work per descriptor: 2*k*DP*L float32
+// lane-slots (sub + fma), DP*sizeof(T) + 4 bytes.
+#include "vt_common.cuh"
+
+template <typename T, int DP>
+__global__ void __launch_bounds__(256, 3)
+quantize_kernel(const T *__restrict__ desc, int64_t n, const float *__restrict__ cent,
+                const uint8_t *__restrict__ internal, const int32_t *__restrict__ ref_id, int k, int depth,
+                int64_t n_heap, int32_t start, int32_t *__restrict__ leaf, int32_t *__restrict__ word,
+                unsigned long long *__restrict__ stats)
+{
+    constexpr int VEC = DP / 32;
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 3, j = lane & 7;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    unsigned int rechecks = 0;
+
+    for (int64_t base = warp * 4; base < n; base += nwarps * 4) {       // warp-uniform trip count
+        const int64_t i = base + g;
+        const bool valid = i < n;
+        const T *xrow = desc + (size_t)(valid ? i : 0) * DP;
+        float4 x[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) x[v] = Elem<T>::load4(xrow, j + 8 * v);
+
+        int64_t node = start;
+        bool active = valid && (node * k + k < n_heap) && internal[node];
+        for (int lvl = 0; lvl < depth; ++lvl) {
+            if (!__any_sync(VT_FULL, active)) break;
+            const float *children = cent + (size_t)(node * k + 1) * DP;
+            const int c = descend_one_level<T, DP>(x, xrow, children, k, active, lane, rechecks);
+            if (active) {
+                node = node * k + 1 + c;
+                active = (node * k + k < n_heap) && internal[node];
+            }
+        }
+        if (valid && j == 0) {
+            if (leaf) leaf[i] = (int32_t)node;
+            if (word) word[i] = ref_id[node];
+        }
+    }
+    if (stats && rechecks) atomicAdd(stats, (unsigned long long)rechecks);
+}
+
+static int64_t heap_nodes(int k, int depth)
+{
+    int64_t n = 0, p = 1;
+    for (int l = 0; l <= depth; ++l) { n += p; p *= k; }
+    return n;
+}
+
+template <typename T, int DP>
+static int launch_quantize(const void *d_desc, int64_t n, const float *cent, const uint8_t *internal,
+                           const int32_t *ref_id, int k, int depth, int32_t start, int32_t *leaf, int32_t *word,
+                           uint64_t *stats, cudaStream_t s)
+{
+    const int64_t want = (n + 31) / 32;                       // 32 descriptors per 256-thread block pass
+    const int64_t cap = (int64_t)vt_sm_count() * 8;
+    const int blocks = (int)(want < cap ? want : cap);
+    quantize_kernel<T, DP><<<blocks, 256, 0, s>>>((const T *)d_desc, n, cent, internal, ref_id, k, depth,
+                                                  heap_nodes(k, depth), start, leaf, word,
+                                                  (unsigned long long *)stats);
+    VT_LAUNCH_CHECK();
+    return VT_OK;
+}
+
+int vt_quantize_dispatch(const void *d_desc, int dtype, int64_t n, int dp, const float *cent, const uint8_t *internal,
+                         const int32_t *ref_id, int k, int depth, int32_t start, int32_t *leaf, int32_t *word,
+                         uint64_t *stats, cudaStream_t s)
+{
+#define VT_Q(T, DPV) return launch_quantize<T, DPV>(d_desc, n, cent, internal, ref_id, k, depth, start, leaf, word, stats, s)
+    if (dtype == VT_U8) {
+        if (dp == 32) VT_Q(uint8_t, 32);
+        if (dp == 64) VT_Q(uint8_t, 64);
+        if (dp == 128) VT_Q(uint8_t, 128);
+    } else if (dtype == VT_F32) {
+        if (dp == 32) VT_Q(float, 32);
+        if (dp == 64) VT_Q(float, 64);
+        if (dp == 128) VT_Q(float, 128);
+    }
+#undef VT_Q
+    vt_set_error("vt_quantize: unsupported dtype %d / dp %d (dp must be 32, 64 or 128)", dtype, dp);
+    return VT_EUNSUPPORTED;
+}
+
+extern "C" int vt_quantize(const void *d_desc, int dtype, int64_t n, int dp, const float *d_centroids,
+                           const uint8_t *d_internal, const int32_t *d_ref_id, int k, int depth, int32_t start,
+                           int32_t *d_leaf_heap, int32_t *d_word, uint64_t *d_stats, void *stream)
+{
+    VT_CHECK_ARG(n >= 0, "n < 0");
+    VT_CHECK_ARG(k >= 1 && k <= 255, "k out of range");
+    VT_CHECK_ARG(depth >= 0 && depth <= 16, "depth out of range");
+    VT_CHECK_ARG(d_centroids && d_internal, "null tree");
+    VT_CHECK_ARG(d_word == nullptr || d_ref_id != nullptr, "d_word needs d_ref_id");
+    VT_CHECK_ARG(start >= 0 && start < heap_nodes(k, depth), "start node outside the heap");
+    if (n == 0) return VT_OK;
+    return vt_quantize_dispatch(d_desc, dtype, n, dp, d_centroids, d_internal, d_ref_id, k, depth, start,
+                                d_leaf_heap, d_word, d_stats, (cudaStream_t)stream);
+}
+
+// ---- host-buffer pipeline (end-to-end path) ---------------------------------------------------------
+extern "C" int vt_quantize_host(const void *h_desc, int dtype, int64_t n, int dp, const float *d_centroids,
+                                const uint8_t *d_internal, const int32_t *d_ref_id, int k, int depth,
+                                int32_t *h_word, int64_t chunk_rows)
+{
+    VT_CHECK_ARG(n >= 0 && h_desc && h_word, "bad host buffers");
+    VT_CHECK_ARG(dtype == VT_U8 || dtype == VT_F32, "bad dtype");
+    VT_CHECK_ARG(d_ref_id != nullptr, "d_ref_id required");
+    if (n == 0) return VT_OK;
+    const size_t esz = dtype == VT_U8 ? 1 : 4;
+    if (chunk_rows <= 0) chunk_rows = (int64_t)1 << 20;
+    if (chunk_rows > n) chunk_rows = n;
+    constexpr int NS = 3;
+    cudaStream_t st[NS] = {};
+    void *dbuf[NS] = {};
+    int32_t *wbuf[NS] = {};
+    int rc = VT_OK;
+    auto cleanup = [&]() {
+        for (int s = 0; s < NS; ++s) {
+            if (st[s]) { cudaStreamSynchronize(st[s]); cudaStreamDestroy(st[s]); }
+            if (dbuf[s]) cudaFree(dbuf[s]);
+            if (wbuf[s]) cudaFree(wbuf[s]);
+        }
+    };
+    for (int s = 0; s < NS; ++s) {
+        if (cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaMalloc(&dbuf[s], (size_t)chunk_rows * dp * esz) != cudaSuccess ||
+            cudaMalloc((void **)&wbuf[s], (size_t)chunk_rows * sizeof(int32_t)) != cudaSuccess) {
+            vt_set_error("vt_quantize_host: staging allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+            cleanup();
+            return VT_ENOMEM;
+        }
+    }
+    int64_t done = 0;
+    for (int c = 0; done < n && rc == VT_OK; ++c, done += chunk_rows) {
+        const int s = c % NS;
+        const int64_t rows = (n - done) < chunk_rows ? (n - done) : chunk_rows;
+        const char *src = (const char *)h_desc + (size_t)done * dp * esz;
+        if (cudaMemcpyAsync(dbuf[s], src, (size_t)rows * dp * esz, cudaMemcpyHostToDevice, st[s]) != cudaSuccess) {
+            vt_set_error("vt_quantize_host: H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = VT_ECUDA;
+            break;
+        }
+        rc = vt_quantize_dispatch(dbuf[s], dtype, rows, dp, d_centroids, d_internal, d_ref_id, k, depth, 0, nullptr,
+                                  wbuf[s], nullptr, st[s]);
+        if (rc != VT_OK) break;
+        if (cudaMemcpyAsync(h_word + done, wbuf[s], (size_t)rows * sizeof(int32_t), cudaMemcpyDeviceToHost, st[s]) !=
+            cudaSuccess) {
+            vt_set_error("vt_quantize_host: D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = VT_ECUDA;
+        }
+    }
+    for (int s = 0; s < NS; ++s)
+        if (st[s] && cudaStreamSynchronize(st[s]) != cudaSuccess && rc == VT_OK) {
+            vt_set_error("vt_quantize_host: stream sync failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = VT_ECUDA;
+        }
+    cleanup();
+    return rc;
+}

@@ -1,0 +1,297 @@
+// vt_score.cu -- inverted-file scoring + top-k (Database.score / Database.retrieve,
+// cbir/database.py:59-81), batched over queries.
+//
+// The database is sharded by image range (shard_size images, the same rule that shards it across
+// GPUs).  One CTA scores one (query, shard) pair: it walks the posting list of every query word
+// inside that shard (CSR, 8 B per posting: local image id + tf or weight), accumulates the sparse
+// dot products of all shard images in shared memory, converts them to rank keys and selects the
+// shard's top-k.  A second kernel merges the per-shard lists of a query and turns keys into the
+// reference's score (database.py:66-70: L2 distance of the L2-normalised vectors, NaN -> 1e6).
+// HBM traffic per query: 8 B x (sum of the posting lengths of its words) + 8 B per (word, shard)
+// row-pointer pair.
+//
+// Rank key (larger is better), ties broken by smaller image index like the reference's stable
+// ascending sort (database.py:79-80):
+//   VT_SCORE_TF_L2 : dot(tf_q, tf_d) / ||tf_d||   (integer dot, exact)   score = sqrt(2 - 2 key/||tf_q||)
+//   VT_SCORE_W_L2  : dot(w_q, w_d)   (weights pre-normalised)            score = sqrt(2 - 2 key)
+//   VT_SCORE_W_L1  : -sum_common(|q-d| - q - d)                          score = 2 - key
+// An image with no descriptors has key -1 (score 1e6).
+#include "vt_common.cuh"
+
+namespace {
+constexpr int SC_THREADS = 256;
+constexpr int SC_WARPS = SC_THREADS / 32;
+constexpr int SC_MAXK = 64;
+
+struct Cand { double key; int32_t id; };
+
+__device__ __forceinline__ bool better(double ka, int32_t ia, double kb, int32_t ib)
+{
+    return ka > kb || (ka == kb && ia < ib);
+}
+
+// block-wide argmax of (key, id) over one candidate per thread; result broadcast to all threads
+__device__ __forceinline__ void block_best(double &key, int32_t &id, int &owner, double *s_key, int32_t *s_id, int *s_owner)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    owner = threadIdx.x;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const double k2 = __shfl_xor_sync(VT_FULL, key, o);
+        const int32_t i2 = __shfl_xor_sync(VT_FULL, id, o);
+        const int o2 = __shfl_xor_sync(VT_FULL, owner, o);
+        if (better(k2, i2, key, id)) { key = k2; id = i2; owner = o2; }
+    }
+    if (lane == 0) { s_key[warp] = key; s_id[warp] = id; s_owner[warp] = owner; }
+    __syncthreads();
+    key = s_key[0]; id = s_id[0]; owner = s_owner[0];
+#pragma unroll
+    for (int w = 1; w < SC_WARPS; ++w)
+        if (better(s_key[w], s_id[w], key, id)) { key = s_key[w]; id = s_id[w]; owner = s_owner[w]; }
+    __syncthreads();
+}
+
+// MODE: VT_SCORE_*.  R: images per shard.
+template <int MODE, int R>
+__global__ void __launch_bounds__(SC_THREADS)
+score_shard_kernel(const uint32_t *__restrict__ post_off, const uint2 *__restrict__ postings,
+                   const double *__restrict__ img_rnorm, int64_t n_img, int64_t n_ref, int n_shards,
+                   const int64_t *__restrict__ q_off, const int32_t *__restrict__ q_node,
+                   const float *__restrict__ q_val, int64_t n_query, int topk, double *__restrict__ out_key,
+                   int32_t *__restrict__ out_id, double *__restrict__ all_key)
+{
+    constexpr int PER = R / SC_THREADS;
+    extern __shared__ unsigned char s_raw[];
+    double *s_keys = reinterpret_cast<double *>(s_raw);                        // [R]
+    float *s_accf = reinterpret_cast<float *>(s_raw + (size_t)R * 8);          // [R] (aliased int/float)
+    int *s_acci = reinterpret_cast<int *>(s_accf);
+    __shared__ double r_key[SC_WARPS];
+    __shared__ int32_t r_id[SC_WARPS];
+    __shared__ int r_owner[SC_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    for (int64_t pair = blockIdx.x; pair < n_query * n_shards; pair += gridDim.x) {
+        const int64_t q = pair / n_shards;
+        const int shard = (int)(pair - q * n_shards);
+        const int64_t img0 = (int64_t)shard * R;
+        const int n_here = (int)((n_img - img0) < R ? (n_img - img0) : R);
+        for (int t = threadIdx.x; t < R; t += SC_THREADS) s_acci[t] = 0;
+        __syncthreads();
+        // accumulate: one warp per query word, lanes over its postings in this shard
+        const int64_t qb = q_off[q], qe = q_off[q + 1];
+        const uint32_t *off = post_off + (size_t)shard * n_ref;
+        for (int64_t w = qb + warp; w < qe; w += SC_WARPS) {
+            const int32_t node = q_node[w];
+            const float qv = q_val[w];
+            const uint32_t b = off[node], e = off[node + 1];
+            for (uint32_t p = b + lane; p < e; p += 32) {
+                const uint2 pe = postings[p];
+                if (MODE == VT_SCORE_TF_L2) {
+                    atomicAdd(&s_acci[pe.x], (int)qv * (int)pe.y);
+                } else if (MODE == VT_SCORE_W_L2) {
+                    atomicAdd(&s_accf[pe.x], qv * __uint_as_float(pe.y));
+                } else {
+                    const float dv = __uint_as_float(pe.y);
+                    atomicAdd(&s_accf[pe.x], qv + dv - fabsf(qv - dv));
+                }
+            }
+        }
+        __syncthreads();
+        // rank keys + per-thread best
+        double bkey = -2.0; int32_t bid = 0x7fffffff;
+#pragma unroll 4
+        for (int u = 0; u < PER; ++u) {
+            const int t = u * SC_THREADS + threadIdx.x;
+            double key = -2.0;                                                  // padding slots never win
+            if (t < n_here) {
+                if (MODE == VT_SCORE_TF_L2) {
+                    const double rn = img_rnorm[img0 + t];
+                    key = rn < 0.0 ? -1.0 : (double)s_acci[t] * rn;
+                } else {
+                    const double rn = img_rnorm ? img_rnorm[img0 + t] : 1.0;
+                    key = rn < 0.0 ? -1.0 : (double)s_accf[t];
+                }
+                if (all_key) all_key[q * n_img + img0 + t] = key;
+            }
+            s_keys[t] = key;
+            if (better(key, (int32_t)(img0 + t), bkey, bid)) { bkey = key; bid = (int32_t)(img0 + t); }
+        }
+        __syncthreads();
+        // k rounds of block argmax; only the winning thread rescans its slice
+        for (int r = 0; r < topk; ++r) {
+            double key = bkey; int32_t id = bid; int owner;
+            block_best(key, id, owner, r_key, r_id, r_owner);
+            if (threadIdx.x == 0) {
+                const size_t o = ((size_t)q * n_shards + shard) * topk + r;
+                out_key[o] = key;
+                out_id[o] = key > -2.0 ? id : -1;
+            }
+            if (threadIdx.x == owner) {
+                if (key > -2.0) s_keys[id - img0] = -2.0;
+                bkey = -2.0; bid = 0x7fffffff;
+                for (int u = 0; u < PER; ++u) {
+                    const int t = u * SC_THREADS + threadIdx.x;
+                    const double k2 = s_keys[t];
+                    if (better(k2, (int32_t)(img0 + t), bkey, bid)) { bkey = k2; bid = (int32_t)(img0 + t); }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// merge n_lists sorted-or-not candidate lists of a query into its top-k, compute final scores
+template <int MODE>
+__global__ void __launch_bounds__(SC_THREADS)
+topk_merge_kernel(const double *__restrict__ in_key, const int32_t *__restrict__ in_id, int64_t n_query, int n_cand,
+                  int topk, const double *__restrict__ q_rnorm, const unsigned long long *__restrict__ q_sumsq,
+                  const unsigned long long *__restrict__ img_sumsq, double *__restrict__ out_key,
+                  int32_t *__restrict__ out_id, double *__restrict__ out_score)
+{
+    extern __shared__ unsigned char s_raw[];
+    double *s_keys = reinterpret_cast<double *>(s_raw);                      // [n_cand]
+    int32_t *s_ids = reinterpret_cast<int32_t *>(s_raw + (size_t)n_cand * 8);
+    __shared__ double r_key[SC_WARPS];
+    __shared__ int32_t r_id[SC_WARPS];
+    __shared__ int r_owner[SC_WARPS];
+    for (int64_t q = blockIdx.x; q < n_query; q += gridDim.x) {
+        for (int t = threadIdx.x; t < n_cand; t += SC_THREADS) {
+            const int32_t id = in_id[q * n_cand + t];
+            s_ids[t] = id;
+            s_keys[t] = id >= 0 ? in_key[q * n_cand + t] : -2.0;
+        }
+        __syncthreads();
+        for (int r = 0; r < topk; ++r) {
+            double bkey = -2.0; int32_t bid = 0x7fffffff; int bslot = -1;
+            for (int t = threadIdx.x; t < n_cand; t += SC_THREADS) {
+                const double k2 = s_keys[t];
+                const int32_t i2 = k2 > -2.0 ? s_ids[t] : 0x7fffffff;
+                if (better(k2, i2, bkey, bid)) { bkey = k2; bid = i2; bslot = t; }
+            }
+            double key = bkey; int32_t id = bid; int owner;
+            block_best(key, id, owner, r_key, r_id, r_owner);
+            if (threadIdx.x == owner && key > -2.0) s_keys[bslot] = -2.0;
+            if (threadIdx.x == 0) {
+                const bool ok = key > -2.0;
+                out_key[q * topk + r] = key;
+                out_id[q * topk + r] = ok ? id : -1;
+                if (out_score) {
+                    double s = 1e6;                                         // database.py:70
+                    if (ok && key >= 0.0) {
+                        if (MODE == VT_SCORE_TF_L2) {
+                            const double rq = q_rnorm[q];
+                            if (rq >= 0.0) {
+                                const double c = key * rq;
+                                s = sqrt(fmax(0.0, 2.0 - 2.0 * c));
+                                // identical count vectors: dot == |d|^2 == |q|^2 -> exactly 0 like the
+                                // reference's d/|d| - q/|q| (Cauchy-Schwarz equality)
+                                if (q_sumsq && img_sumsq && img_sumsq[id] == q_sumsq[q]) {
+                                    const double dot = key * sqrt((double)img_sumsq[id]);
+                                    if (fabs(dot - (double)q_sumsq[q]) < 0.5) s = 0.0;
+                                }
+                            }
+                        } else if (MODE == VT_SCORE_W_L2) {
+                            s = sqrt(fmax(0.0, 2.0 - 2.0 * key));
+                        } else {
+                            s = fmax(0.0, 2.0 - key);
+                        }
+                    }
+                    out_score[q * topk + r] = s;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void rnorm_kernel(const unsigned long long *__restrict__ sumsq, int64_t n, double *__restrict__ rnorm)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long s = sumsq[t];
+        rnorm[t] = s ? 1.0 / sqrt((double)s) : -1.0;
+    }
+}
+}  // namespace
+
+extern "C" int vt_score_shard_size(void) { return 8192; }
+extern "C" int vt_score_max_topk(void) { return SC_MAXK; }
+
+extern "C" int vt_rnorm(const uint64_t *d_sumsq, int64_t n, double *d_rnorm, void *stream)
+{
+    if (n <= 0) return VT_OK;
+    const int64_t cap = (int64_t)vt_sm_count() * 8, want = (n + 255) / 256;
+    rnorm_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>((const unsigned long long *)d_sumsq, n, d_rnorm);
+    VT_LAUNCH_CHECK();
+    return VT_OK;
+}
+
+template <int MODE>
+static int launch_score(const uint32_t *post_off, const void *postings, const double *img_rnorm, int64_t n_img,
+                        int64_t n_ref, const int64_t *q_off, const int32_t *q_node, const float *q_val, int64_t n_query,
+                        int topk, double *out_key, int32_t *out_id, double *all_key, cudaStream_t s)
+{
+    constexpr int R = 8192;
+    const int n_shards = (int)((n_img + R - 1) / R);
+    auto kern = score_shard_kernel<MODE, R>;
+    const size_t smem = (size_t)R * 12;
+    VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t pairs = n_query * n_shards;
+    const int64_t cap = (int64_t)vt_sm_count() * 2 * 8;
+    kern<<<(int)(pairs < cap ? pairs : cap), SC_THREADS, smem, s>>>(post_off, (const uint2 *)postings, img_rnorm, n_img, n_ref,
+                                                                    n_shards, q_off, q_node, q_val, n_query, topk, out_key,
+                                                                    out_id, all_key);
+    VT_LAUNCH_CHECK();
+    return VT_OK;
+}
+
+extern "C" int vt_score_topk(const uint32_t *d_post_off, const void *d_postings, const double *d_img_rnorm, int64_t n_img,
+                             int64_t n_ref, const int64_t *d_q_off, const int32_t *d_q_node, const float *d_q_val,
+                             int64_t n_query, int mode, int topk, double *d_shard_key, int32_t *d_shard_id,
+                             double *d_all_key, void *stream)
+{
+    VT_CHECK_ARG(n_img > 0 && n_ref > 0 && n_query >= 0, "bad sizes");
+    VT_CHECK_ARG(topk >= 1 && topk <= SC_MAXK, "topk out of range");
+    VT_CHECK_ARG(mode != VT_SCORE_TF_L2 || d_img_rnorm != nullptr, "tf mode needs image norms");
+    if (n_query == 0) return VT_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (mode) {
+    case VT_SCORE_TF_L2: return launch_score<VT_SCORE_TF_L2>(d_post_off, d_postings, d_img_rnorm, n_img, n_ref, d_q_off, d_q_node, d_q_val, n_query, topk, d_shard_key, d_shard_id, d_all_key, s);
+    case VT_SCORE_W_L2: return launch_score<VT_SCORE_W_L2>(d_post_off, d_postings, d_img_rnorm, n_img, n_ref, d_q_off, d_q_node, d_q_val, n_query, topk, d_shard_key, d_shard_id, d_all_key, s);
+    case VT_SCORE_W_L1: return launch_score<VT_SCORE_W_L1>(d_post_off, d_postings, d_img_rnorm, n_img, n_ref, d_q_off, d_q_node, d_q_val, n_query, topk, d_shard_key, d_shard_id, d_all_key, s);
+    }
+    vt_set_error("vt_score_topk: unknown mode %d", mode);
+    return VT_EINVAL;
+}
+
+extern "C" int vt_topk_merge(const double *d_in_key, const int32_t *d_in_id, int64_t n_query, int n_cand, int topk,
+                             int mode, const double *d_q_rnorm, const uint64_t *d_q_sumsq, const uint64_t *d_img_sumsq,
+                             double *d_out_key, int32_t *d_out_id, double *d_out_score, void *stream)
+{
+    VT_CHECK_ARG(n_query >= 0 && n_cand >= 1 && topk >= 1 && topk <= SC_MAXK, "bad sizes");
+    VT_CHECK_ARG((size_t)n_cand * 12 <= 200 * 1024, "too many candidates per query for one merge");
+    VT_CHECK_ARG(mode != VT_SCORE_TF_L2 || d_out_score == nullptr || d_q_rnorm != nullptr, "tf scores need query norms");
+    if (n_query == 0) return VT_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t smem = (size_t)n_cand * 12;
+    const int64_t cap = (int64_t)vt_sm_count() * 8;
+    const int blocks = (int)(n_query < cap ? n_query : cap);
+#define VT_M(MODEV)                                                                                              \
+    {                                                                                                            \
+        auto kern = topk_merge_kernel<MODEV>;                                                                    \
+        VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+        kern<<<blocks, SC_THREADS, smem, s>>>(d_in_key, d_in_id, n_query, n_cand, topk, d_q_rnorm,               \
+                                              (const unsigned long long *)d_q_sumsq,                             \
+                                              (const unsigned long long *)d_img_sumsq, d_out_key, d_out_id,      \
+                                              d_out_score);                                                      \
+        VT_LAUNCH_CHECK();                                                                                       \
+        return VT_OK;                                                                                            \
+    }
+    switch (mode) {
+    case VT_SCORE_TF_L2: VT_M(VT_SCORE_TF_L2)
+    case VT_SCORE_W_L2: VT_M(VT_SCORE_W_L2)
+    case VT_SCORE_W_L1: VT_M(VT_SCORE_W_L1)
+    }
+#undef VT_M
+    vt_set_error("vt_topk_merge: unknown mode %d", mode);
+    return VT_EINVAL;
+}

@@ -1,0 +1,171 @@
+// vt_sort.cu -- stable LSD radix sort of (uint32 key, uint32 value) pairs, 8 bits per pass.
+//
+// Used for (a) the stable partition of node members at the end of every tree level (the Python
+// append loop at cbir/encoders/vocabulary.py:64-66) and (b) turning the forward bag-of-words CSR
+// into image-ordered posting lists (the per-node dicts of vocabulary.py:96-100).
+// HBM-bound: per pass one read of the keys (histogram) + one read and one scattered write of the
+// pairs = 20 B per element per pass.
+//
+// Per pass:  hist (per-tile digit counts, digit-major)  ->  scan (one block per digit, exclusive
+// over tiles)  ->  scatter (per-warp stable ranking with match_any, tile = 8 warps x 512 items).
+#include "vt_common.cuh"
+
+namespace {
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_ROUNDS = 16;                          // items per thread
+constexpr int SORT_WARP_ITEMS = 32 * SORT_ROUNDS;        // 512 contiguous items per warp
+constexpr int SORT_TILE = SORT_WARP_ITEMS * SORT_WARPS;  // 4096 items per block
+
+__global__ void __launch_bounds__(SORT_THREADS)
+sort_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift, uint32_t *__restrict__ hist, int nblocks)
+{
+    __shared__ uint32_t cnt[256];
+    cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t start = (int64_t)blockIdx.x * SORT_TILE;
+#pragma unroll 4
+    for (int r = 0; r < SORT_ROUNDS; ++r) {
+        const int64_t idx = start + r * SORT_THREADS + threadIdx.x;
+        if (idx < n) atomicAdd(&cnt[(keys[idx] >> shift) & 0xffu], 1u);
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = cnt[threadIdx.x];
+}
+
+// one block per digit: exclusive scan of that digit's per-tile counts, in place; total -> digit_total
+__global__ void __launch_bounds__(SORT_THREADS)
+sort_scan_kernel(uint32_t *__restrict__ hist, int nblocks, uint32_t *__restrict__ digit_total)
+{
+    __shared__ uint32_t wsum[SORT_WARPS];
+    uint32_t *row = hist + (size_t)blockIdx.x * nblocks;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t carry = 0;
+    for (int base = 0; base < nblocks; base += SORT_THREADS) {
+        const int idx = base + threadIdx.x;
+        const uint32_t v = idx < nblocks ? row[idx] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(VT_FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        uint32_t woff = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w) {
+            const uint32_t t = wsum[w];
+            if (w < warp) woff += t;
+            total += t;
+        }
+        if (idx < nblocks) row[idx] = carry + woff + incl - v;
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) digit_total[blockIdx.x] = carry;
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+sort_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                    uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n, int shift,
+                    const uint32_t *__restrict__ hist, const uint32_t *__restrict__ digit_total, int nblocks)
+{
+    __shared__ uint32_t wcnt[SORT_WARPS][256];
+    __shared__ uint32_t dbase[256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; ++w) wcnt[w][threadIdx.x] = 0;
+    // exclusive scan of the 256 digit totals (Hillis-Steele)
+    uint32_t mine = digit_total[threadIdx.x];
+    dbase[threadIdx.x] = mine;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+        const uint32_t t = threadIdx.x >= o ? dbase[threadIdx.x - o] : 0u;
+        __syncthreads();
+        dbase[threadIdx.x] += t;
+        __syncthreads();
+    }
+    const uint32_t excl = dbase[threadIdx.x] - mine;
+    __syncthreads();
+    dbase[threadIdx.x] = excl + hist[(size_t)threadIdx.x * nblocks + blockIdx.x];
+    __syncthreads();
+
+    const int64_t wstart = (int64_t)blockIdx.x * SORT_TILE + (int64_t)warp * SORT_WARP_ITEMS;
+    uint32_t key[SORT_ROUNDS], val[SORT_ROUNDS], lrank[SORT_ROUNDS];
+#pragma unroll
+    for (int r = 0; r < SORT_ROUNDS; ++r) {
+        const int64_t idx = wstart + r * 32 + lane;
+        const bool valid = idx < n;
+        key[r] = valid ? keys_in[idx] : 0u;
+        val[r] = valid ? vals_in[idx] : 0u;
+        const uint32_t d = (key[r] >> shift) & 0xffu;
+        const uint32_t tag = valid ? d : (0x100u | (uint32_t)lane);        // invalid lanes match nobody
+        const uint32_t peers = __match_any_sync(VT_FULL, tag);
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        const uint32_t base = valid ? wcnt[warp][d] : 0u;
+        __syncwarp();
+        if (valid && rank == 0) wcnt[warp][d] = base + __popc(peers);
+        __syncwarp();
+        lrank[r] = base + rank;
+    }
+    __syncthreads();
+    {   // thread d: turn per-warp counts into per-warp global offsets for digit d
+        uint32_t run = dbase[threadIdx.x];
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w) {
+            const uint32_t t = wcnt[w][threadIdx.x];
+            wcnt[w][threadIdx.x] = run;
+            run += t;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SORT_ROUNDS; ++r) {
+        const int64_t idx = wstart + r * 32 + lane;
+        if (idx < n) {
+            const uint32_t d = (key[r] >> shift) & 0xffu;
+            const uint32_t pos = wcnt[warp][d] + lrank[r];
+            keys_out[pos] = key[r];
+            vals_out[pos] = val[r];
+        }
+    }
+}
+}  // namespace
+
+extern "C" int64_t vt_sort_scratch_bytes(int64_t n)
+{
+    const int64_t nblocks = (n + SORT_TILE - 1) / SORT_TILE;
+    return (256 * (nblocks > 0 ? nblocks : 1) + 256) * (int64_t)sizeof(uint32_t);
+}
+
+extern "C" int vt_sort_pairs(uint32_t *d_keys, uint32_t *d_vals, uint32_t *d_tmp_keys, uint32_t *d_tmp_vals, int64_t n,
+                             int n_bits, void *d_hist, int *result_in_tmp, void *stream)
+{
+    VT_CHECK_ARG(n >= 0 && n < ((int64_t)1 << 31), "n must be below 2^31");
+    VT_CHECK_ARG(n_bits >= 0 && n_bits <= 32, "n_bits out of range");
+    VT_CHECK_ARG(result_in_tmp != nullptr, "result_in_tmp is null");
+    *result_in_tmp = 0;
+    if (n == 0 || n_bits == 0) return VT_OK;
+    VT_CHECK_ARG(d_keys && d_vals && d_tmp_keys && d_tmp_vals && d_hist, "null buffer");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nblocks = (int)((n + SORT_TILE - 1) / SORT_TILE);
+    uint32_t *hist = (uint32_t *)d_hist;
+    uint32_t *digit_total = hist + (size_t)256 * nblocks;
+    uint32_t *kin = d_keys, *vin = d_vals, *kout = d_tmp_keys, *vout = d_tmp_vals;
+    int flips = 0;
+    for (int shift = 0; shift < n_bits; shift += 8) {
+        sort_hist_kernel<<<nblocks, SORT_THREADS, 0, s>>>(kin, n, shift, hist, nblocks);
+        VT_LAUNCH_CHECK();
+        sort_scan_kernel<<<256, SORT_THREADS, 0, s>>>(hist, nblocks, digit_total);
+        VT_LAUNCH_CHECK();
+        sort_scatter_kernel<<<nblocks, SORT_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, hist, digit_total, nblocks);
+        VT_LAUNCH_CHECK();
+        uint32_t *t;
+        t = kin; kin = kout; kout = t;
+        t = vin; vin = vout; vout = t;
+        ++flips;
+    }
+    *result_in_tmp = flips & 1;
+    return VT_OK;
+}

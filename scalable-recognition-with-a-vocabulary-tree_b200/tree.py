@@ -1,0 +1,181 @@
+"""Flat vocabulary tree: the array form of the reference's ``VocabularyTree.tree`` /
+``.nodes`` / ``.graph`` (cbir/encoders/vocabulary.py:16-18).
+
+Layout.  The tree is an implicit complete k-ary heap: node ``h`` has children
+``h*k+1 .. h*k+k``; level ``l`` starts at ``(k**l - 1)/(k - 1)``.  Per heap slot we keep the
+centroid (float32, zero padded to ``DP``), ``exists`` (the reference created this node),
+``internal`` (it has children; the reference's ``graph.out_degree(node) > 0``,
+vocabulary.py:113) and ``ref_id`` -- the id the reference assigns, i.e. the DFS pre-order
+counter of ``fit`` (vocabulary.py:70-75).  Ragged trees (a node with fewer than ``k`` members is
+a leaf at any depth, vocabulary.py:55) simply leave heap slots unused.
+
+Only host-side index arithmetic lives here (numpy); device copies are plain torch tensors.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def pad_dim(d: int) -> int:
+    dp = 32
+    while dp < d:
+        dp *= 2
+    if dp > 128:
+        raise ValueError("descriptor dimension %d is not supported (max 128)" % d)
+    return dp
+
+
+def heap_size(k: int, depth: int) -> int:
+    return sum(k ** l for l in range(depth + 1))
+
+
+def level_offset(k: int, level: int) -> int:
+    return sum(k ** l for l in range(level))
+
+
+def reference_ids(exists: np.ndarray, internal: np.ndarray, k: int, depth: int):
+    """DFS pre-order numbering of the existing nodes (vocabulary.py:70-75), vectorised per level.
+
+    id(child c of n) = id(n) + 1 + sum of the subtree sizes of the children before c.
+    Returns (ref_id [n_heap] int32 with -1 for unused slots, n_ref)."""
+    n_heap = exists.shape[0]
+    size = exists.astype(np.int64).copy()                     # subtree sizes, bottom-up
+    for level in range(depth - 1, -1, -1):
+        o, n_l = level_offset(k, level), k ** level
+        co = level_offset(k, level + 1)
+        child = size[co: co + n_l * k].reshape(n_l, k)
+        size[o: o + n_l] += np.where(internal[o: o + n_l] != 0, child.sum(axis=1), 0)
+    ref = np.full(n_heap, -1, np.int64)
+    if n_heap and exists[0]:
+        ref[0] = 0
+    for level in range(depth):
+        o, n_l = level_offset(k, level), k ** level
+        co = level_offset(k, level + 1)
+        child = size[co: co + n_l * k].reshape(n_l, k)
+        before = np.cumsum(child, axis=1) - child             # exclusive prefix over siblings
+        cid = ref[o: o + n_l, None] + 1 + before
+        ok = (internal[o: o + n_l, None] != 0) & (exists[co: co + n_l * k].reshape(n_l, k) != 0)
+        ref[co: co + n_l * k] = np.where(ok, cid, -1).reshape(-1)
+    return ref.astype(np.int32), int(size[0]) if n_heap else 0
+
+
+class FlatTree:
+    """Host mirror of a built tree plus lazily created device tensors."""
+
+    def __init__(self, k: int, depth: int, d: int, centroids: np.ndarray, exists: np.ndarray,
+                 internal: np.ndarray, count=None):
+        self.k, self.depth, self.D = int(k), int(depth), int(d)
+        self.DP = int(centroids.shape[1])
+        self.n_heap = heap_size(k, depth)
+        assert centroids.shape[0] == self.n_heap
+        self.centroids = np.ascontiguousarray(centroids, np.float32)
+        self.exists = np.ascontiguousarray(exists, np.uint8)
+        self.internal = np.ascontiguousarray(internal, np.uint8)
+        self.count = None if count is None else np.ascontiguousarray(count, np.int64)
+        self.ref_id, self.n_ref = reference_ids(self.exists, self.internal, self.k, self.depth)
+        ex = np.nonzero(self.exists)[0]
+        self.heap_of_ref = np.full(self.n_ref, -1, np.int64)
+        self.heap_of_ref[self.ref_id[ex]] = ex
+        # per reference id: parent id and depth (used by the bag-of-words encoder)
+        heap = self.heap_of_ref
+        parent_heap = np.maximum(heap - 1, 0) // self.k
+        self.parent_ref = np.where(heap > 0, self.ref_id[parent_heap], -1).astype(np.int32)
+        lvl = np.zeros(self.n_heap, np.uint8)
+        for level in range(1, self.depth + 1):
+            o = level_offset(self.k, level)
+            lvl[o: o + self.k ** level] = level
+        self.level_ref = lvl[heap].astype(np.uint8)
+        self._dev = {}
+
+    # ------------------------------------------------------------------ device copies
+    def device(self, device=None):
+        """dict of torch tensors on ``device`` (cached): centroids, internal, ref_id,
+        parent_ref, level_ref."""
+        import torch
+        device = torch.device(device if device is not None else "cuda")
+        key = str(device)
+        if key not in self._dev:
+            self._dev[key] = dict(
+                centroids=torch.from_numpy(self.centroids).to(device),
+                internal=torch.from_numpy(self.internal).to(device),
+                ref_id=torch.from_numpy(self.ref_id).to(device),
+                parent_ref=torch.from_numpy(self.parent_ref).to(device),
+                level_ref=torch.from_numpy(self.level_ref).to(device),
+            )
+        return self._dev[key]
+
+    def adopt_device(self, device, centroids, internal):
+        """Reuse tensors the build already holds on the device instead of re-uploading."""
+        import torch
+        key = str(torch.device(device))
+        self._dev[key] = dict(
+            centroids=centroids, internal=internal,
+            ref_id=torch.from_numpy(self.ref_id).to(device),
+            parent_ref=torch.from_numpy(self.parent_ref).to(device),
+            level_ref=torch.from_numpy(self.level_ref).to(device),
+        )
+
+    # ------------------------------------------------------------------ reference views
+    def nodes_dict(self) -> dict:
+        """``VocabularyTree.nodes``: reference id -> centre (float32 [D]) (vocabulary.py:51)."""
+        return {int(r): self.centroids[h, :self.D].copy() for r, h in enumerate(self.heap_of_ref)}
+
+    def tree_dict(self) -> dict:
+        """``VocabularyTree.tree``: reference id -> list of child ids (vocabulary.py:69-72)."""
+        out = {}
+        for h in np.nonzero(self.internal)[0]:
+            out[int(self.ref_id[h])] = [int(x) for x in self.ref_id[h * self.k + 1: h * self.k + 1 + self.k]]
+        return dict(sorted(out.items()))
+
+    def to_networkx(self):
+        """``VocabularyTree.graph`` (vocabulary.py:18,52,73) for small trees / visualisation."""
+        import networkx as nx
+        g = nx.DiGraph()
+        g.add_nodes_from(range(self.n_ref))
+        for node, kids in self.tree_dict().items():
+            for c in kids:
+                g.add_edge(node, c)
+        return g
+
+    def path_of(self, heap_leaf: int) -> list:
+        """reference-id path root..stop node, what ``propagate_feature`` returns (vocabulary.py:111-124)."""
+        path = []
+        h = int(heap_leaf)
+        while True:
+            path.append(int(self.ref_id[h]))
+            if h == 0:
+                break
+            h = (h - 1) // self.k
+        return path[::-1]
+
+    # ------------------------------------------------------------------ persistence
+    def state(self) -> dict:
+        return dict(k=self.k, depth=self.depth, D=self.D, centroids=self.centroids, exists=self.exists,
+                    internal=self.internal, count=self.count if self.count is not None else np.zeros(0, np.int64))
+
+    @classmethod
+    def from_state(cls, st) -> "FlatTree":
+        count = st["count"] if len(st["count"]) else None
+        return cls(int(st["k"]), int(st["depth"]), int(st["D"]), st["centroids"], st["exists"], st["internal"], count)
+
+    @classmethod
+    def from_reference_dicts(cls, nodes: dict, tree: dict, k: int, depth: int) -> "FlatTree":
+        """Import a tree built by the reference (its ``nodes`` / ``tree`` dicts, e.g. from
+        ``nodes.pickle``, vocabulary.py:148-159)."""
+        d = int(np.asarray(nodes[0]).shape[0])
+        dp = pad_dim(d)
+        nh = heap_size(k, depth)
+        cent = np.zeros((nh, dp), np.float32)
+        exists = np.zeros(nh, np.uint8)
+        internal = np.zeros(nh, np.uint8)
+        stack = [(0, 0)]
+        while stack:
+            rid, h = stack.pop()
+            exists[h] = 1
+            cent[h, :d] = np.asarray(nodes[rid], np.float32)
+            kids = tree.get(rid, [])
+            if kids:
+                internal[h] = 1
+                for j, c in enumerate(kids):
+                    stack.append((c, h * k + 1 + j))
+        return cls(k, depth, d, cent, exists, internal)
