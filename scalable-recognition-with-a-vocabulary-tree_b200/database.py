@@ -1,0 +1,220 @@
+"""``Database`` with the reference's API (cbir/database.py) on top of the sm_100a inverted-file
+scorer.
+
+Same constructor / method names (database.py:9-115): ``index / embedding / score / retrieve /
+is_indexed / save / load / show_results``.  ``retrieve`` returns the reference's dict
+``image_path -> score`` ordered best first over ALL images (its ``n`` argument is ignored there
+too, database.py:72-81).  ``retrieve_batch`` is the batched top-k entry point.
+
+Any object with ``embedding(image)`` works as encoder for the reference; the accelerated path
+needs the encoder protocol extended by ``encode_batch`` (``VocabularyTree`` has it).  Image
+identity is the position in ``dataset.image_paths`` (the reference keys by a salted
+``hash(abspath)``, database.py:25-34, which cannot cross processes).
+"""
+from __future__ import annotations
+
+import os
+import pickle
+
+import numpy as np
+
+from . import _native as nat
+from . import engine
+from .dataset import Dataset
+
+
+class Database(object):
+    def __init__(self, dataset, encoder, *, weighting="tf", norm="l2"):
+        # public:
+        if isinstance(dataset, Dataset):
+            self.dataset = dataset
+        elif isinstance(dataset, str):
+            self.dataset = Dataset(dataset)
+        else:
+            raise TypeError("Invalid dataset of type %s" % type(dataset))
+        self.encoder = encoder
+        if weighting not in ("tf", "tfidf") or norm not in ("l2", "l1"):
+            raise ValueError("weighting must be 'tf' or 'tfidf', norm 'l2' or 'l1'")
+        if weighting == "tf" and norm != "l2":
+            raise ValueError("the reference's tf scoring is L2 only; use weighting='tfidf' for L1")
+        self.weighting, self.norm = weighting, norm
+
+        # private:
+        self._rows = {}           # image path -> row in the indexed CSR
+        self._host = None         # host copy of the forward CSR (row_off, node, count)
+        self._csr = None          # device forward CSR of the indexed images
+        self._index = None        # device inverted file
+        self._idf = None
+        self._extra = {}          # path -> (nodes, counts) of non-indexed images (queries)
+        return
+
+    # ------------------------------------------------------------------ indexing
+    def _mode(self):
+        if self.weighting == "tf":
+            return nat.SCORE_TF_L2
+        return nat.SCORE_W_L2 if self.norm == "l2" else nat.SCORE_W_L1
+
+    def _descriptors(self, image_path):
+        return np.asarray(self.encoder.descriptor(self.dataset.read_image(image_path)))
+
+    def index(self):
+        """Encode every dataset image (in ``image_paths`` order) and build the inverted file
+        (database.py:36-44)."""
+        import torch
+        paths = list(self.dataset.image_paths)
+        feats = [self._descriptors(p) for p in paths]
+        csr = self.encoder.encode_batch(feats, want_df=True)
+        n_ref = self.encoder.flat.n_ref
+        weight = None
+        if self.weighting == "tfidf":
+            n = max(len(paths), 1)
+            df = csr["df"].to(torch.float64)
+            self._idf = torch.where(df > 0, torch.log(n / df.clamp(min=1)), torch.zeros_like(df)).to(torch.float32)
+            weight = engine.tfidf_weights(csr, self._idf, self.norm)
+        self._csr = csr
+        self._index = engine.build_index(csr, n_ref, weight)
+        self._rows = {p: i for i, p in enumerate(paths)}
+        self._host = (csr["row_off"].cpu().numpy(), csr["node"].cpu().numpy(), csr["count"].cpu().numpy())
+        self._extra = {}
+        return
+
+    def is_indexed(self, image_path):
+        return image_path in self._rows
+
+    def _sparse(self, image_path):
+        if image_path in self._rows:
+            ro, node, count = self._host
+            i = self._rows[image_path]
+            return node[ro[i]:ro[i + 1]], count[ro[i]:ro[i + 1]]
+        if image_path not in self._extra:
+            csr = self.encoder.encode_batch([self._descriptors(image_path)])
+            self._extra[image_path] = (csr["node"].cpu().numpy(), csr["count"].cpu().numpy())
+        return self._extra[image_path]
+
+    def embedding(self, image_path):
+        """Dense L2-normalised visit-count vector of an image (database.py:50-57)."""
+        nodes, counts = self._sparse(image_path)
+        return self.encoder.dense_embedding(nodes, counts)
+
+    def score(self, db_image_path, query_image_path):
+        """database.py:59-70 for one pair (not the hot path: two dense vectors on the host)."""
+        d = self.embedding(db_image_path)
+        q = self.embedding(query_image_path)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            d = d / np.linalg.norm(d, ord=2)
+            q = q / np.linalg.norm(q, ord=2)
+            score = np.linalg.norm(d - q, ord=2)
+        return score if not np.isnan(score) else 1e6
+
+    # ------------------------------------------------------------------ retrieval
+    def _query_csr(self, query_paths):
+        """CSR batch (device) for a list of image paths; indexed images reuse their rows."""
+        import torch
+        dev = self._csr["row_off"].device
+        rows = [self._sparse(p) for p in query_paths]
+        sizes = torch.tensor([len(r[0]) for r in rows], dtype=torch.int64)
+        off = torch.zeros(len(rows) + 1, dtype=torch.int64)
+        off[1:] = torch.cumsum(sizes, 0)
+        node = np.concatenate([r[0] for r in rows]) if rows else np.zeros(0, np.int32)
+        count = np.concatenate([r[1] for r in rows]) if rows else np.zeros(0, np.int32)
+        sumsq = torch.tensor([int((r[1].astype(np.int64) ** 2).sum()) for r in rows], dtype=torch.int64)
+        q = dict(row_off=off.to(dev), node=torch.from_numpy(node.astype(np.int32)).to(dev),
+                 count=torch.from_numpy(count.astype(np.int32)).to(dev), sumsq=sumsq.to(dev),
+                 n_img=len(rows), nnz=int(off[-1]))
+        q_val = None
+        if self.weighting == "tfidf":
+            q_val = engine.tfidf_weights(q, self._idf, self.norm)
+        return q, q_val
+
+    def retrieve_batch(self, query_paths, k=10, return_all=False):
+        """Top-k image indices (positions in ``dataset.image_paths``) and scores per query.
+        Returns (ids [Q, k] int32, scores [Q, k] float64[, all_keys [Q, n_img]])."""
+        if self._index is None:
+            self.index()
+        q, q_val = self._query_csr(list(query_paths))
+        out = engine.score(self._index, q, k, self._mode(), q_val=q_val, want_all=return_all)
+        ids, sc = out["id"].cpu().numpy(), out["score"].cpu().numpy()
+        if return_all:
+            return ids, sc, out["all_key"].cpu().numpy()
+        return ids, sc
+
+    def _scores_from_keys(self, keys, q_sumsq):
+        """rank keys of every image -> reference scores (host, float64)."""
+        mode = self._mode()
+        with np.errstate(invalid="ignore", divide="ignore"):
+            if mode == nat.SCORE_TF_L2:
+                if q_sumsq == 0:
+                    return np.full(keys.shape, 1e6)
+                s = np.sqrt(np.maximum(0.0, 2.0 - 2.0 * keys / np.sqrt(float(q_sumsq))))
+                sumsq = self._index["sumsq"].cpu().numpy()
+                dot = keys * np.sqrt(sumsq.astype(np.float64))
+                s[(sumsq == q_sumsq) & (np.abs(dot - q_sumsq) < 0.5)] = 0.0
+            elif mode == nat.SCORE_W_L2:
+                s = np.sqrt(np.maximum(0.0, 2.0 - 2.0 * keys))
+            else:
+                s = np.maximum(0.0, 2.0 - keys)
+        s[keys < 0] = 1e6                                        # images without descriptors: NaN -> 1e6
+        return s
+
+    def retrieve(self, query_image_path, n=4):
+        """All dataset images ordered by ascending score, as a dict path -> score
+        (database.py:72-81; ties keep ``image_paths`` order like Python's stable sort)."""
+        if self._index is None:
+            self.index()
+        paths = list(self.dataset.image_paths)
+        q, q_val = self._query_csr([query_image_path])
+        out = engine.score(self._index, q, 1, self._mode(), q_val=q_val, want_all=True)
+        keys = out["all_key"][0].cpu().numpy()
+        scores = self._scores_from_keys(keys, int(q["sumsq"][0].item()))
+        order = np.argsort(scores, kind="stable")
+        return {paths[i]: float(scores[i]) for i in order}
+
+    # ------------------------------------------------------------------ persistence
+    def save(self, path=None):
+        """``index.pickle`` (database.py:83-91): here the forward CSR of the indexed images."""
+        if path is None:
+            path = "data"
+        os.makedirs(path, exist_ok=True)
+        with open(os.path.join(path, "index.pickle"), "wb") as f:
+            pickle.dump(dict(rows=self._rows, host=self._host, weighting=self.weighting, norm=self.norm), f)
+        return True
+
+    def load(self, path="data"):
+        try:
+            import torch
+            with open(os.path.join(path, "index.pickle"), "rb") as f:
+                st = pickle.load(f)
+            ro, node, count = st["host"]
+            dev = torch.device(self.encoder.device)
+            n_img = len(ro) - 1
+            sumsq = np.add.reduceat(count.astype(np.int64) ** 2, ro[:-1]) if len(count) else np.zeros(n_img, np.int64)
+            sumsq = np.where(ro[1:] > ro[:-1], sumsq, 0)
+            csr = dict(row_off=torch.from_numpy(ro).to(dev), node=torch.from_numpy(node).to(dev),
+                       count=torch.from_numpy(count).to(dev), sumsq=torch.from_numpy(sumsq).to(dev),
+                       n_img=n_img, nnz=len(node), df=None)
+            self._rows, self._host, self._csr = st["rows"], st["host"], csr
+            self.weighting, self.norm = st["weighting"], st["norm"]
+            weight = None
+            if self.weighting == "tfidf":
+                df = torch.bincount(csr["node"].long(), minlength=self.encoder.flat.n_ref).to(torch.float64)
+                self._idf = torch.where(df > 0, torch.log(max(n_img, 1) / df.clamp(min=1)),
+                                        torch.zeros_like(df)).to(torch.float32)
+                weight = engine.tfidf_weights(csr, self._idf, self.norm)
+            self._index = engine.build_index(csr, self.encoder.flat.n_ref, weight)
+        except (OSError, KeyError, pickle.UnpicklingError):
+            print("Cannot load index file from %s/index.pickle" % path)
+        return True
+
+    def show_results(self, query_path, scores_dict, n=4, figsize=(10, 4)):
+        """Plot the query next to its n best matches; entry 0 of ``scores_dict`` is the query
+        itself when it is a database image, so matches start at entry 1 (database.py:103-115)."""
+        import matplotlib.pyplot as plt          # optional dependency, plotting only
+        ranked = list(scores_dict.items())[1:n + 1]
+        panels = [("Query image", query_path)] + [
+            ("#%d. %s Score:%.3f" % (r + 1, p, s), p) for r, (p, s) in enumerate(ranked)]
+        _, axes = plt.subplots(1, len(panels), figsize=figsize)
+        for axis, (title, path) in zip(np.atleast_1d(axes), panels):
+            axis.imshow(self.dataset.read_image(path))
+            axis.set_title(title)
+            axis.axis("off")
+        return

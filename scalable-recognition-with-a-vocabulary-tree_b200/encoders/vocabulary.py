@@ -1,0 +1,203 @@
+"""``VocabularyTree`` with the reference's API (cbir/encoders/vocabulary.py) on top of the
+sm_100a kernels.
+
+Same constructor and method names as the reference class (vocabulary.py:10-159):
+``fit / learn / extract_features / propagate / propagate_feature / embedding / save`` and the
+attributes ``n_branches, depth, descriptor, tree, nodes, graph``.  Additions are batched entry
+points (``quantize``, ``encode_batch``) and ``load``; new options are keyword-only and default to
+the reference's behaviour (all-node visit counts, no idf, L2 normalisation).
+
+Differences that are deliberate and documented in DESIGN.md:
+* the per-node k-means is the seeded exact Lloyd (the reference's MiniBatchKMeans is unseeded);
+* distances are decided in binary64 on near-ties (the reference's float32 result depends on
+  OpenBLAS' summation order there);
+* querying does not add the query's counts to the postings (vocabulary.py:126-127 does).
+"""
+from __future__ import annotations
+
+import os
+import pickle
+
+import numpy as np
+
+from .. import utils
+from .. import engine
+from ..tree import FlatTree
+
+
+class VocabularyTree(object):
+    def __init__(self, n_branches, depth, descriptor, *, n_iter=10, all_nodes=True, device="cuda"):
+        self.n_branches = n_branches
+        self.depth = depth
+        self.descriptor = descriptor
+        # keyword-only additions
+        self.n_iter = n_iter
+        self.all_nodes = all_nodes          # reference semantics: count every node on the path
+        self.device = device
+        # private
+        self._flat = None                   # FlatTree
+        self._propagated = {}               # image sha1 -> (node ids int32, counts int32)
+        self._views = {}
+        self.build_log = []
+
+    # ------------------------------------------------------------------ reference-shaped views
+    @property
+    def flat(self) -> FlatTree:
+        if self._flat is None:
+            raise RuntimeError("the vocabulary tree has not been fitted")
+        return self._flat
+
+    @property
+    def tree(self) -> dict:
+        """node id -> child ids (vocabulary.py:16,69-72)."""
+        if self._flat is None:
+            return {}
+        if "tree" not in self._views:
+            self._views["tree"] = self._flat.tree_dict()
+        return self._views["tree"]
+
+    @property
+    def nodes(self) -> dict:
+        """node id -> centre (vocabulary.py:17,51)."""
+        if self._flat is None:
+            return {}
+        if "nodes" not in self._views:
+            self._views["nodes"] = self._flat.nodes_dict()
+        return self._views["nodes"]
+
+    @property
+    def graph(self):
+        """networkx view (vocabulary.py:18) including the per-node {image_id: count} postings
+        the reference keeps as node attributes (vocabulary.py:96-100).  Small trees only."""
+        g = self._flat.to_networkx() if self._flat is not None else __import__("networkx").DiGraph()
+        for image_id, (nodes, counts) in self._propagated.items():
+            for n_, c in zip(nodes.tolist(), counts.tolist()):
+                g.nodes[n_][image_id] = c
+        return g
+
+    def postings(self) -> dict:
+        """node id -> {image sha1: count}: the inverted file as the reference stores it."""
+        out = {}
+        for image_id, (nodes, counts) in self._propagated.items():
+            for n_, c in zip(nodes.tolist(), counts.tolist()):
+                out.setdefault(n_, {})[image_id] = c
+        return out
+
+    # ------------------------------------------------------------------ build
+    def learn(self, dataset):
+        features = self.extract_features(dataset)
+        self.fit(features)
+        return self
+
+    def extract_features(self, dataset):
+        print("Extracting features...")
+        func = lambda path: self.descriptor(dataset.read_image(path))  # noqa: E731
+        features = utils.show_progress(func, dataset)
+        print("\n%d features extracted" % len(features))
+        return np.array(features)
+
+    def fit(self, features, node=0, root=None, current_depth=0):
+        """Hierarchical k-means over ``features`` [N, D] (vocabulary.py:36-76), all nodes of a
+        level per launch.  Only whole-tree builds (node=0) are offered."""
+        if node != 0 or root is not None or current_depth != 0:
+            raise NotImplementedError("only whole-tree builds (node=0) are supported")
+        features = np.asarray(features) if not hasattr(features, "device") else features
+        desc, d = engine.stage(features, self.device, prefer_bytes=True)
+        self.build_log = []
+        self._flat = engine.build_tree(desc, d, self.n_branches, self.depth, n_iter=self.n_iter,
+                                       log=lambda **kw: self.build_log.append(kw))
+        self._views = {}
+        self._propagated = {}
+        return self
+
+    def set_tree(self, flat: FlatTree):
+        self._flat = flat
+        self._views = {}
+        self._propagated = {}
+        return self
+
+    # ------------------------------------------------------------------ descent
+    def quantize(self, features, return_heap=False):
+        """Batched ``propagate_feature``: reference node id of the stop node per descriptor."""
+        desc, _ = engine.stage(features, self.device)
+        t = self.flat
+        out = engine.quantize(t.device(self.device), t.k, t.depth, desc, want_heap=return_heap)
+        if return_heap:
+            return out[0].cpu().numpy(), out[1].cpu().numpy()
+        return out.cpu().numpy()
+
+    def propagate_feature(self, feature, node=0):
+        """Path of node ids from ``node`` down to a leaf (vocabulary.py:104-124)."""
+        t = self.flat
+        desc, _ = engine.stage(np.asarray(feature)[None, :], self.device)
+        start = int(t.heap_of_ref[node])
+        _, heap = engine.quantize(t.device(self.device), t.k, t.depth, desc, want_heap=True, start=start)
+        path = t.path_of(int(heap[0].item()))
+        return path[path.index(node):]
+
+    # ------------------------------------------------------------------ encoding
+    def encode_batch(self, images, want_df=False, all_nodes=None):
+        """Bag-of-words CSR (device tensors) for a list of descriptor arrays."""
+        import torch
+        t = self.flat
+        sizes = [int(np.asarray(a).shape[0]) for a in images]
+        d = t.D
+        nonempty = [np.asarray(a).reshape(-1, d) for a in images if np.asarray(a).shape[0] > 0]
+        off = torch.zeros(len(images) + 1, dtype=torch.int64)
+        off[1:] = torch.cumsum(torch.tensor(sizes, dtype=torch.int64), 0)
+        dev = torch.device(self.device)
+        if nonempty:
+            allrows = np.concatenate(nonempty, axis=0)
+            desc, _ = engine.stage(allrows, dev)
+            words = engine.quantize(t.device(dev), t.k, t.depth, desc)
+        else:
+            words = torch.zeros(1, dtype=torch.int32, device=dev)
+        return engine.encode(words, off.to(dev), t.device(dev), t.depth, t.n_ref,
+                             all_nodes=self.all_nodes if all_nodes is None else all_nodes, want_df=want_df)
+
+    def propagate(self, image):
+        """Send an image's features down the tree and record its visit counts
+        (vocabulary.py:78-102).  Idempotent per image content (sha1 key)."""
+        image_id = utils.get_image_id(image)
+        if image_id in self._propagated:
+            return
+        features = self.descriptor(image)
+        csr = self.encode_batch([features])
+        self._propagated[image_id] = (csr["node"].cpu().numpy(), csr["count"].cpu().numpy())
+        return
+
+    def embedding(self, image):
+        """Dense visit-count vector over ALL nodes in node-id order, L2 normalised
+        (vocabulary.py:126-137).  float64 [n_nodes]; 0/0 -> NaN like the reference."""
+        self.propagate(image)
+        nodes, counts = self._propagated[utils.get_image_id(image)]
+        return self.dense_embedding(nodes, counts)
+
+    encode = embedding      # name used by the notebook skeleton / BASELINE north_star
+
+    def dense_embedding(self, nodes, counts):
+        e = np.zeros(self.flat.n_ref, dtype=np.int64)
+        e[nodes] = counts
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return e / np.linalg.norm(e, ord=2)
+
+    # ------------------------------------------------------------------ persistence
+    def save(self, path=None):
+        """Flat-array checkpoint ``tree.npz`` plus the reference's ``nodes.pickle`` dict
+        (vocabulary.py:148-159; its graph.pickle needs networkx<3 and is not written)."""
+        if path is None:
+            path = "data"
+        os.makedirs(path, exist_ok=True)
+        np.savez_compressed(os.path.join(path, "tree.npz"), **self.flat.state())
+        with open(os.path.join(path, "nodes.pickle"), "wb") as f:
+            pickle.dump(self.nodes, f)
+        return True
+
+    def load(self, path="data"):
+        st = np.load(os.path.join(path, "tree.npz"))
+        self.set_tree(FlatTree.from_state(st))
+        self.n_branches, self.depth = self.flat.k, self.flat.depth
+        return True
+
+    def draw(self, *args, **kwargs):
+        raise NotImplementedError("plotting is outside the accelerated path; use .graph with networkx")

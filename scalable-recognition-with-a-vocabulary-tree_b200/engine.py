@@ -1,0 +1,374 @@
+"""Device-side orchestration of the hot path: thin torch-tensor wrappers over the C ABI
+(``include/vtree_b200.h``).  torch only owns memory and streams here; every compute step is one
+of the hand-written sm_100a kernels.  Nothing in this module runs on the CPU -- without the
+native library and a B200-class device every entry point raises ``NativeError``.
+
+Reference functions covered (cbir/encoders/vocabulary.py, cbir/database.py):
+``stage``      input side of ``extract_features`` (:29-34)        -> byte / float rows on device
+``build_tree`` ``VocabularyTree.fit`` (:36-76), level synchronous  -> FlatTree
+``quantize``   ``propagate_feature`` (:104-124), batched           -> reference node ids
+``encode``     ``propagate`` + ``embedding`` (:78-137), batched    -> CSR (node, tf), norms
+``build_index``the per-node posting dicts (:96-100)                -> sharded inverted CSR
+``score``      ``Database.score`` / ``retrieve`` (database.py:59-81) -> top-k ids and scores
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .tree import FlatTree, heap_size, level_offset, pad_dim
+
+VT_U8, VT_F32 = nat.VT_U8, nat.VT_F32
+
+
+def _lib():
+    return nat.load()
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.uint8:
+        return VT_U8
+    if t.dtype == torch.float32:
+        return VT_F32
+    raise TypeError("descriptors must be uint8 or float32 on the device, got %s" % t.dtype)
+
+
+# --------------------------------------------------------------------------------------- staging
+def stage(x, device="cuda", prefer_bytes: bool = True):
+    """[n, D] descriptors (numpy or torch; uint8, any int, float32/64) -> (rows [n, DP] on the
+    device, D).  Integer-valued data in 0..255 is kept as bytes (lossless, 4x less HBM traffic);
+    anything else stays float32."""
+    nat.require_device()
+    lib = _lib()
+    if isinstance(x, np.ndarray):
+        if x.dtype not in (np.uint8, np.float32):
+            x = x.astype(np.float32)
+        t = torch.from_numpy(np.ascontiguousarray(x))
+    else:
+        t = x
+        if t.dtype not in (torch.uint8, torch.float32):
+            t = t.to(torch.float32)
+    if t.dim() == 1:
+        t = t[None, :]
+    t = t.to(device, non_blocking=True).contiguous()
+    n, d = t.shape
+    dp = pad_dim(d)
+    s = nat.stream_ptr()
+    if t.dtype == torch.uint8:
+        if d == dp:
+            return t, d
+        out = torch.empty((n, dp), dtype=torch.uint8, device=t.device)
+        nat.check(lib.vt_stage_pad(nat.ptr(t), n, d, nat.ptr(out), dp, 1, s), "vt_stage_pad")
+        return out, d
+    if prefer_bytes:
+        out = torch.empty((n, dp), dtype=torch.uint8, device=t.device)
+        flag = torch.zeros(1, dtype=torch.int32, device=t.device)
+        nat.check(lib.vt_stage_f32_to_u8(nat.ptr(t), n, d, nat.ptr(out), dp, nat.ptr(flag), s), "vt_stage_f32_to_u8")
+        if int(flag.item()) == 0:
+            return out, d
+    if d == dp:
+        return t, d
+    out = torch.empty((n, dp), dtype=torch.float32, device=t.device)
+    nat.check(lib.vt_stage_pad(nat.ptr(t), n, d, nat.ptr(out), dp, 4, s), "vt_stage_pad")
+    return out, d
+
+
+# --------------------------------------------------------------------------------------- descent
+def quantize(tree_dev: dict, k: int, depth: int, desc: torch.Tensor, want_heap: bool = False,
+             stats: torch.Tensor = None, start: int = 0):
+    """Reference node id of the stop node of every descriptor (int32 [n]); optionally also the
+    heap index.  ``stats`` (int64 [4], zeroed by the caller) receives the binary64 recheck count."""
+    lib = _lib()
+    n, dp = desc.shape
+    word = torch.empty(n, dtype=torch.int32, device=desc.device)
+    leaf = torch.empty(n, dtype=torch.int32, device=desc.device) if want_heap else None
+    nat.check(lib.vt_quantize(nat.ptr(desc), _dtype_code(desc), n, dp, nat.ptr(tree_dev["centroids"]),
+                              nat.ptr(tree_dev["internal"]), nat.ptr(tree_dev["ref_id"]), k, depth, start,
+                              nat.ptr(leaf), nat.ptr(word), nat.ptr(stats), nat.stream_ptr()), "vt_quantize")
+    return (word, leaf) if want_heap else word
+
+
+def quantize_host(tree_dev: dict, k: int, depth: int, h_desc, h_word, chunk_rows: int = 0):
+    """End-to-end variant: host (pinned) descriptor rows in, host word ids out, chunked and
+    overlapped inside the native library (``vt_quantize_host``)."""
+    lib = _lib()
+    n, dp = h_desc.shape
+    code = VT_U8 if h_desc.dtype in (torch.uint8, np.uint8) else VT_F32
+    nat.check(lib.vt_quantize_host(nat.ptr(h_desc), code, n, dp, nat.ptr(tree_dev["centroids"]),
+                                   nat.ptr(tree_dev["internal"]), nat.ptr(tree_dev["ref_id"]), k, depth,
+                                   nat.ptr(h_word), chunk_rows), "vt_quantize_host")
+    return h_word
+
+
+# --------------------------------------------------------------------------------------- sort
+def sort_pairs(keys: torch.Tensor, vals: torch.Tensor, n_bits: int):
+    """Stable radix sort of (uint32 key, uint32 value) pairs held in int32 tensors."""
+    lib = _lib()
+    n = keys.numel()
+    if n == 0 or n_bits == 0:
+        return keys, vals
+    tk, tv = torch.empty_like(keys), torch.empty_like(vals)
+    hist = torch.empty(int(lib.vt_sort_scratch_bytes(n)), dtype=torch.uint8, device=keys.device)
+    flip = C.c_int(0)
+    nat.check(lib.vt_sort_pairs(nat.ptr(keys), nat.ptr(vals), nat.ptr(tk), nat.ptr(tv), n, n_bits, nat.ptr(hist),
+                                C.byref(flip), nat.stream_ptr()), "vt_sort_pairs")
+    return (tk, tv) if flip.value else (keys, vals)
+
+
+# --------------------------------------------------------------------------------------- build
+class _NoComm:
+    """Single-GPU stand-in for the collective hooks ``build_tree`` uses."""
+    world = 1
+    rank = 0
+
+    def all_reduce(self, t):
+        return t
+
+    def all_gather_counts(self, t):
+        return t[None]
+
+
+def build_tree(desc: torch.Tensor, d: int, k: int, depth: int, n_iter: int = 10, comm=None,
+               stats: torch.Tensor = None, log=None) -> FlatTree:
+    """Level-synchronous hierarchical k-means over byte descriptors [N, DP] (this rank's shard).
+
+    Per level: seeded initial centres (member floor(j*m/k) of every node), ``n_iter`` exact Lloyd
+    steps over ALL nodes of the level at once (early exit when no label changes), stable
+    partition of the members into the children.  With ``comm`` (see ``dist.Comm``) the integer
+    sums/counts are all-reduced, so every rank ends with the same tree, bit for bit."""
+    lib = _lib()
+    if desc.dtype != torch.uint8:
+        raise TypeError("build_tree needs byte descriptors (integer valued 0..255); stage() keeps float rows only "
+                        "when the data is not byte-exact, which the exact-sum k-means does not support")
+    comm = comm or _NoComm()
+    dev = desc.device
+    n, dp = desc.shape
+    s = nat.stream_ptr()
+    n_heap = heap_size(k, depth)
+    cent = torch.zeros((n_heap, dp), dtype=torch.float32, device=dev)
+    internal = torch.zeros(n_heap, dtype=torch.uint8, device=dev)
+    exists = torch.zeros(n_heap, dtype=torch.uint8, device=dev)
+    count_heap = torch.zeros(n_heap, dtype=torch.int64, device=dev)
+    exists[0] = 1
+
+    # root = mean of all features (vocabulary.py:48-49), exact
+    col = torch.zeros(dp + 1, dtype=torch.int64, device=dev)
+    nat.check(lib.vt_column_sums(nat.ptr(desc), VT_U8, n, dp, nat.ptr(col), s), "vt_column_sums")
+    col[dp] = n
+    col = comm.all_reduce(col)
+    n_total = int(col[dp].item())
+    if n_total > 0:
+        cent[0] = (col[:dp].to(torch.float64) / float(n_total)).to(torch.float32)
+    count_heap[0] = n_total
+
+    perm = torch.arange(n, dtype=torch.int32, device=dev)
+    parent = torch.zeros(n, dtype=torch.int32, device=dev)
+    seg_local = torch.tensor([n], dtype=torch.int64, device=dev)
+    seg_global = torch.tensor([n_total], dtype=torch.int64, device=dev)
+
+    for level in range(depth):
+        n_nodes = k ** level
+        n_rows = n_nodes * k
+        n_active = perm.numel()
+        node_internal = (seg_global >= k).to(torch.uint8)                 # vocabulary.py:55
+        if int(node_internal.sum().item()) == 0:
+            break
+        o, co = level_offset(k, level), level_offset(k, level + 1)
+        internal[o:o + n_nodes] = node_internal
+        child_cent = cent[co:co + n_rows]
+        seg_begin = torch.cumsum(seg_local, 0) - seg_local
+        if comm.world > 1:
+            allc = comm.all_gather_counts(seg_local)                      # [world, n_nodes]
+            rank0 = allc[:comm.rank].sum(0) if comm.rank > 0 else torch.zeros_like(seg_local)
+            nat.check(lib.vt_kmeans_init(nat.ptr(desc), VT_U8, dp, nat.ptr(perm), nat.ptr(seg_begin),
+                                         nat.ptr(seg_local), nat.ptr(seg_global), nat.ptr(rank0.contiguous()),
+                                         n_nodes, k, nat.ptr(child_cent), s), "vt_kmeans_init")
+            comm.all_reduce(child_cent)                                    # one owner per row: exact
+        else:
+            nat.check(lib.vt_kmeans_init(nat.ptr(desc), VT_U8, dp, nat.ptr(perm), nat.ptr(seg_begin),
+                                         nat.ptr(seg_local), None, None, n_nodes, k, nat.ptr(child_cent), s),
+                      "vt_kmeans_init")
+
+        label = torch.full((max(n_active, 1),), 255, dtype=torch.uint8, device=dev)
+        acc = torch.zeros(n_rows * dp + n_rows + 1, dtype=torch.int64, device=dev)   # sums | counts | changed
+        sums, counts, changed = acc[:n_rows * dp], acc[n_rows * dp:n_rows * dp + n_rows], acc[n_rows * dp + n_rows:]
+        local_counts = None
+
+        def assign():
+            nonlocal local_counts
+            acc.zero_()
+            nat.check(lib.vt_kmeans_assign(nat.ptr(desc), VT_U8, dp, nat.ptr(perm), nat.ptr(parent), n_active,
+                                           nat.ptr(node_internal), n_nodes, k, nat.ptr(child_cent), nat.ptr(label),
+                                           nat.ptr(sums), nat.ptr(counts), nat.ptr(changed), nat.ptr(stats), s),
+                      "vt_kmeans_assign")
+            if comm.world > 1:
+                local_counts = counts.clone()
+                comm.all_reduce(acc)                                       # sums, counts and changed in one go
+            else:
+                local_counts = counts
+
+        converged = False
+        iters = 0
+        for it in range(n_iter):
+            assign()
+            if it > 0 and int(changed.item()) == 0:
+                converged = True                                           # labels repeat: fixed point
+                break
+            nat.check(lib.vt_kmeans_update(nat.ptr(sums), nat.ptr(counts), n_rows, dp, nat.ptr(child_cent), s),
+                      "vt_kmeans_update")
+            iters += 1
+        if not converged:
+            assign()                                                       # labels_ against the final centres
+        if log is not None:
+            log(level=level, nodes=n_nodes, members=n_active, iters=iters, converged=converged)
+
+        kid_exists = node_internal.repeat_interleave(k)
+        exists[co:co + n_rows] = kid_exists
+        count_heap[co:co + n_rows] = counts * kid_exists
+        seg_global = (counts * kid_exists).clone()
+        seg_local = (local_counts * kid_exists).clone()
+        if level + 1 >= depth:
+            break
+        # stable partition of every node's members into its children (vocabulary.py:64-66)
+        keys = torch.empty(max(n_active, 1), dtype=torch.int32, device=dev)
+        nat.check(lib.vt_partition_keys(nat.ptr(parent), nat.ptr(label), n_active, nat.ptr(node_internal), k,
+                                        n_rows, nat.ptr(keys), s), "vt_partition_keys")
+        skeys, svals = sort_pairs(keys[:n_active], perm, int(n_rows).bit_length())
+        n_next = int(seg_local.sum().item())
+        perm = svals[:n_next].contiguous()
+        parent = skeys[:n_next].contiguous()
+
+    tree = FlatTree(k, depth, d, cent.cpu().numpy(), exists.cpu().numpy(), internal.cpu().numpy(),
+                    count_heap.cpu().numpy())
+    tree.adopt_device(dev, cent, internal)
+    return tree
+
+
+# --------------------------------------------------------------------------------------- encode
+def encode(words: torch.Tensor, img_off: torch.Tensor, tree_dev: dict, depth: int, n_ref: int,
+           all_nodes: bool = True, want_df: bool = False) -> dict:
+    """Bag-of-words CSR of a batch of images.  ``words`` int32 [n_desc] (reference ids of the
+    stop nodes) grouped by image, ``img_off`` int64 [n_img+1] on the device."""
+    lib = _lib()
+    dev = words.device
+    n_img = img_off.numel() - 1
+    s = nat.stream_ptr()
+    sizes = img_off[1:] - img_off[:-1]
+    max_words = int(sizes.max().item()) if n_img > 0 else 0
+    if max_words > lib.vt_encode_max_words():
+        raise ValueError("an image has %d descriptors; vt_encode handles at most %d per image"
+                         % (max_words, lib.vt_encode_max_words()))
+    nnz = torch.zeros(max(n_img, 1), dtype=torch.int32, device=dev)
+    args = (nat.ptr(words), nat.ptr(img_off), n_img, max_words, 1 if all_nodes else 0,
+            nat.ptr(tree_dev["parent_ref"]), nat.ptr(tree_dev["level_ref"]), depth)
+    nat.check(lib.vt_encode(*args, nat.ptr(nnz), None, None, None, None, None, s), "vt_encode(count)")
+    row_off = torch.zeros(n_img + 1, dtype=torch.int64, device=dev)
+    row_off[1:] = torch.cumsum(nnz[:n_img].to(torch.int64), 0)
+    total = int(row_off[-1].item())
+    node = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    count = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    sumsq = torch.zeros(max(n_img, 1), dtype=torch.int64, device=dev)
+    df = torch.zeros(n_ref, dtype=torch.int32, device=dev) if want_df else None
+    nat.check(lib.vt_encode(*args, None, nat.ptr(row_off), nat.ptr(node), nat.ptr(count), nat.ptr(sumsq),
+                            nat.ptr(df), s), "vt_encode(fill)")
+    return dict(row_off=row_off, node=node[:total], count=count[:total], sumsq=sumsq[:n_img], df=df,
+                n_img=n_img, nnz=total)
+
+
+def entry_rows(csr: dict) -> torch.Tensor:
+    """image index of every CSR entry (int64 [nnz])."""
+    n_img = csr["n_img"]
+    sizes = csr["row_off"][1:] - csr["row_off"][:-1]
+    return torch.repeat_interleave(torch.arange(n_img, device=sizes.device), sizes)
+
+
+def tfidf_weights(csr: dict, idf: torch.Tensor, norm: str = "l2"):
+    """Opt-in Nister & Stewenius weighting (what vocabulary.py:131,137 leaves commented out):
+    w = tf * idf[node], normalised per image in L2 or L1.  Returns float32 [nnz]."""
+    w = csr["count"].to(torch.float32) * idf[csr["node"].long()]
+    rows = entry_rows(csr)
+    tot = torch.zeros(csr["n_img"], dtype=torch.float64, device=w.device)
+    if norm == "l2":
+        tot.index_add_(0, rows, (w.double() ** 2))
+        tot = tot.sqrt()
+    else:
+        tot.index_add_(0, rows, w.double().abs())
+    scale = torch.where(tot > 0, 1.0 / tot, torch.zeros_like(tot))
+    return (w.double() * scale[rows]).to(torch.float32)
+
+
+# --------------------------------------------------------------------------------------- index
+def build_index(csr: dict, n_ref: int, weight: torch.Tensor = None) -> dict:
+    """Forward CSR -> inverted file sharded by image range (postings in image order)."""
+    lib = _lib()
+    dev = csr["row_off"].device
+    s = nat.stream_ptr()
+    n_img, nnz = csr["n_img"], csr["nnz"]
+    shard = lib.vt_score_shard_size()
+    n_shards = max(1, (n_img + shard - 1) // shard)
+    n_keys = n_shards * n_ref
+    keys = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+    entry = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+    entry_img = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+    nat.check(lib.vt_posting_keys(nat.ptr(csr["row_off"]), nat.ptr(csr["node"]), n_img, shard, n_ref, nat.ptr(keys),
+                                  nat.ptr(entry), nat.ptr(entry_img), s), "vt_posting_keys")
+    skeys, sentry = sort_pairs(keys[:nnz], entry[:nnz], int(n_keys).bit_length())
+    post_off = torch.empty(n_keys + 1, dtype=torch.int32, device=dev)
+    postings = torch.empty((max(nnz, 1), 2), dtype=torch.int32, device=dev)
+    nat.check(lib.vt_posting_fill(nat.ptr(skeys), nat.ptr(sentry), nnz, nat.ptr(entry_img), nat.ptr(csr["count"]),
+                                  nat.ptr(weight), shard, n_keys, nat.ptr(post_off), nat.ptr(postings), s),
+              "vt_posting_fill")
+    rnorm = torch.empty(max(n_img, 1), dtype=torch.float64, device=dev)
+    nat.check(lib.vt_rnorm(nat.ptr(csr["sumsq"]), n_img, nat.ptr(rnorm), s), "vt_rnorm")
+    return dict(post_off=post_off, postings=postings[:nnz], rnorm=rnorm[:n_img], sumsq=csr["sumsq"], n_img=n_img,
+                n_ref=n_ref, shard=shard, n_shards=n_shards, nnz=nnz, weighted=weight is not None)
+
+
+# --------------------------------------------------------------------------------------- score
+def score(index: dict, q: dict, topk: int, mode: int = nat.SCORE_TF_L2, q_val: torch.Tensor = None,
+          want_all: bool = False, merge: bool = True) -> dict:
+    """Score a CSR batch of queries against the inverted file and select the top-k per query.
+
+    Returns dict(key [Q, topk] f64, id [Q, topk] i32, score [Q, topk] f64, all_key [Q, n_img] | None,
+    shard_key/shard_id when ``merge`` is False)."""
+    lib = _lib()
+    dev = index["post_off"].device
+    s = nat.stream_ptr()
+    nq = q["n_img"]
+    n_img, n_shards = index["n_img"], index["n_shards"]
+    topk = int(min(topk, lib.vt_score_max_topk()))
+    if q_val is None:
+        q_val = q["count"].to(torch.float32)
+    shard_key = torch.empty((max(nq, 1), n_shards, topk), dtype=torch.float64, device=dev)
+    shard_id = torch.empty((max(nq, 1), n_shards, topk), dtype=torch.int32, device=dev)
+    all_key = torch.empty((max(nq, 1), n_img), dtype=torch.float64, device=dev) if want_all else None
+    nat.check(lib.vt_score_topk(nat.ptr(index["post_off"]), nat.ptr(index["postings"]), nat.ptr(index["rnorm"]),
+                                n_img, index["n_ref"], nat.ptr(q["row_off"]), nat.ptr(q["node"]), nat.ptr(q_val),
+                                nq, mode, topk, nat.ptr(shard_key), nat.ptr(shard_id), nat.ptr(all_key), s),
+              "vt_score_topk")
+    out = dict(all_key=all_key, shard_key=shard_key, shard_id=shard_id, topk=topk)
+    if merge:
+        out.update(merge_topk(shard_key.view(max(nq, 1), -1), shard_id.view(max(nq, 1), -1), nq, topk, mode,
+                              q["sumsq"], index["sumsq"]))
+    return out
+
+
+def merge_topk(cand_key: torch.Tensor, cand_id: torch.Tensor, nq: int, topk: int, mode: int,
+               q_sumsq: torch.Tensor, img_sumsq: torch.Tensor) -> dict:
+    """Merge ``n_cand`` (key, id) candidates per query into the final top-k + reference scores."""
+    lib = _lib()
+    dev = cand_key.device
+    s = nat.stream_ptr()
+    n_cand = cand_key.shape[1]
+    q_rnorm = torch.empty(max(nq, 1), dtype=torch.float64, device=dev)
+    nat.check(lib.vt_rnorm(nat.ptr(q_sumsq), nq, nat.ptr(q_rnorm), s), "vt_rnorm")
+    key = torch.empty((max(nq, 1), topk), dtype=torch.float64, device=dev)
+    ids = torch.empty((max(nq, 1), topk), dtype=torch.int32, device=dev)
+    sc = torch.empty((max(nq, 1), topk), dtype=torch.float64, device=dev)
+    nat.check(lib.vt_topk_merge(nat.ptr(cand_key.contiguous()), nat.ptr(cand_id.contiguous()), nq, n_cand, topk, mode,
+                                nat.ptr(q_rnorm), nat.ptr(q_sumsq), nat.ptr(img_sumsq), nat.ptr(key), nat.ptr(ids),
+                                nat.ptr(sc), s), "vt_topk_merge")
+    return dict(key=key[:nq], id=ids[:nq], score=sc[:nq])

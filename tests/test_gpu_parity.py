@@ -1,0 +1,383 @@
+"""GPU parity tests: every CUDA entry point (through the C ABI) against the CPU oracle and the
+reference's golden vectors.  Integer / index results are compared bit-exactly; float64 scores
+within 1e-5 relative (BASELINE.json north_star).  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+from oracle import vt_oracle as vo
+from helpers import (csr_to_dense, golden_inputs, golden_tree_dicts, load_golden, oracle_tree_from_flat)
+
+pytestmark = pytest.mark.gpu
+CASES = ["toy", "small", "orb", "adversarial"]
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _flat_from_golden(vt, name):
+    g, meta = load_golden(name)
+    images, k, depth, n_iter = golden_inputs(name)
+    nodes, tree = golden_tree_dicts(g, k)
+    return vt.FlatTree.from_reference_dicts(nodes, tree, k, depth), g, meta, images
+
+
+# ------------------------------------------------------------------------------------------ sort
+@pytest.mark.parametrize("n,bits", [(1, 8), (31, 3), (1000, 8), (4097, 13), (100003, 20), (3_000_001, 32)])
+def test_sort_pairs_is_a_stable_sort(vt, cuda, n, bits):
+    torch = _torch()
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 1 << bits, n, dtype=np.uint64).astype(np.uint32)
+    vals = np.arange(n, dtype=np.uint32)
+    k_d = torch.from_numpy(keys.view(np.int32)).to(cuda)
+    v_d = torch.from_numpy(vals.view(np.int32)).to(cuda)
+    sk, sv = vt.engine.sort_pairs(k_d, v_d, bits)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(sk.cpu().numpy().view(np.uint32), keys[order])
+    assert np.array_equal(sv.cpu().numpy().view(np.uint32), vals[order])
+
+
+# ------------------------------------------------------------------------------------------ descent
+@pytest.mark.parametrize("name", CASES + ["c1"])
+@pytest.mark.parametrize("as_float", [False, True])
+def test_quantize_matches_oracle_and_reference(vt, cuda, name, as_float):
+    torch = _torch()
+    ft, g, meta, images = _flat_from_golden(vt, name)
+    x = np.concatenate(images)
+    if name == "c1":
+        x = x[:400_000] if as_float else x
+    ot = oracle_tree_from_flat(ft)
+    want_heap, gap = vo.descend(ot, x, want_gap=True)
+    desc, d = vt.engine.stage(x.astype(np.float32) if as_float else x, cuda, prefer_bytes=not as_float)
+    assert desc.dtype == (torch.float32 if as_float else torch.uint8)
+    stats = torch.zeros(4, dtype=torch.int64, device=cuda)
+    word, heap = vt.engine.quantize(ft.device(cuda), ft.k, ft.depth, desc, want_heap=True, stats=stats)
+    heap, word = heap.cpu().numpy(), word.cpu().numpy()
+    assert np.array_equal(heap, want_heap), "%d rows differ from the binary64 oracle" % (heap != want_heap).sum()
+    assert np.array_equal(word, ft.ref_id[want_heap])
+    # against the reference's own float32 propagate_feature: only near-ties may differ
+    ref_leaf = g["ref_leaf"].astype(np.int32)[:len(x)]
+    mism = np.nonzero(word != ref_leaf)[0]
+    assert np.all(gap[mism] < 1e-5)
+    assert len(mism) <= max(2, int(3e-5 * len(x)))
+    print("%s: %d/%d near-tie rows differ from the float32 reference; %d binary64 rechecks"
+          % (name, len(mism), len(x), int(stats[0].item())))
+
+
+def _random_tree(vt, rng, k, depth, d, ragged, tie_heavy):
+    dp = vt.tree.pad_dim(d)
+    nh = vt.tree.heap_size(k, depth)
+    cent = np.zeros((nh, dp), np.float32)
+    if tie_heavy:      # small integer centres + duplicated siblings: exact and near ties everywhere
+        cent[:, :d] = rng.integers(0, 4, (nh, d)).astype(np.float32)
+        dup = rng.random(nh) < 0.3
+        cent[1:][dup[1:]] = cent[:-1][dup[1:]]
+    else:
+        cent[:, :d] = rng.random((nh, d), dtype=np.float32) * 255.0
+    exists = np.zeros(nh, np.uint8)
+    internal = np.zeros(nh, np.uint8)
+    exists[0] = 1
+    for h in range(nh):
+        if exists[h] and h * k + k < nh and (not ragged or h == 0 or rng.random() < 0.8):
+            internal[h] = 1
+            exists[h * k + 1:h * k + 1 + k] = 1
+    return vt.FlatTree(k, depth, d, cent, exists, internal)
+
+
+@pytest.mark.parametrize("k,depth,d", [(2, 6, 1), (3, 5, 20), (4, 4, 32), (10, 3, 64), (10, 4, 128), (16, 3, 100),
+                                       (31, 2, 128), (1, 3, 32)])
+@pytest.mark.parametrize("tie_heavy", [False, True])
+def test_quantize_random_trees(vt, cuda, k, depth, d, tie_heavy):
+    torch = _torch()
+    rng = np.random.default_rng(1000 * k + 10 * depth + d + tie_heavy)
+    ft = _random_tree(vt, rng, k, depth, d, ragged=True, tie_heavy=tie_heavy)
+    n = 20011
+    x = rng.integers(0, 4 if tie_heavy else 256, (n, d)).astype(np.uint8)
+    want, gap = vo.descend(oracle_tree_from_flat(ft), x, want_gap=True)
+    for arr in (x, x.astype(np.float32) + (0.0 if tie_heavy else 0.25)):
+        exp = want if arr.dtype == np.uint8 or tie_heavy else vo.descend(oracle_tree_from_flat(ft), arr)
+        desc, _ = vt.engine.stage(arr, cuda)
+        stats = torch.zeros(4, dtype=torch.int64, device=cuda)
+        _, heap = vt.engine.quantize(ft.device(cuda), k, depth, desc, want_heap=True, stats=stats)
+        assert np.array_equal(heap.cpu().numpy(), exp)
+        if tie_heavy and k > 1:
+            assert int(stats[0].item()) > 0            # the binary64 path really ran
+    if tie_heavy and k > 1:
+        assert (gap == 0).any()                        # exact ties were present (first child must win)
+
+
+def test_quantize_start_node_and_empty_batch(vt, cuda):
+    torch = _torch()
+    ft, g, meta, images = _flat_from_golden(vt, "small")
+    x = np.concatenate(images)[:100]
+    desc, _ = vt.engine.stage(x, cuda)
+    kids = ft.tree_dict()[0]
+    node = kids[3]
+    start = int(ft.heap_of_ref[node])
+    w = vt.engine.quantize(ft.device(cuda), ft.k, ft.depth, desc, start=start).cpu().numpy()
+    ot = oracle_tree_from_flat(ft)
+    # oracle: descend a subtree by re-rooting through explicit loops
+    for i in range(len(x)):
+        h = start
+        while ft.internal[h]:
+            c = vo.assign(vo.padded(x[i:i + 1]), ft.centroids[h * ft.k + 1:h * ft.k + 1 + ft.k])[0]
+            h = h * ft.k + 1 + c
+        assert w[i] == ft.ref_id[h]
+    empty = torch.empty((0, ft.DP), dtype=torch.uint8, device=cuda)
+    assert vt.engine.quantize(ft.device(cuda), ft.k, ft.depth, empty).numel() == 0
+    del ot
+
+
+def test_quantize_host_pipeline_equals_device_path(vt, cuda):
+    torch = _torch()
+    ft, g, meta, images = _flat_from_golden(vt, "c1")
+    x = np.concatenate(images)[:300_001]
+    desc, _ = vt.engine.stage(x, cuda)
+    want = vt.engine.quantize(ft.device(cuda), ft.k, ft.depth, desc).cpu().numpy()
+    h_desc = torch.from_numpy(x).pin_memory()
+    h_word = torch.empty(len(x), dtype=torch.int32).pin_memory()
+    vt.engine.quantize_host(ft.device(cuda), ft.k, ft.depth, h_desc, h_word, chunk_rows=70_000)
+    assert np.array_equal(h_word.numpy(), want)
+
+
+# ------------------------------------------------------------------------------------------ build
+@pytest.mark.parametrize("name", CASES)
+def test_build_matches_reference_fit(vt, cuda, name):
+    g, meta = load_golden(name)
+    images, k, depth, n_iter = golden_inputs(name)
+    x = np.concatenate(images)
+    desc, d = vt.engine.stage(x, cuda)
+    ft = vt.engine.build_tree(desc, d, k, depth, n_iter=n_iter)
+    t = vo.build_tree(x, k, depth, n_iter)
+    assert np.array_equal(ft.exists, t["exists"]) and np.array_equal(ft.internal, t["internal"])
+    assert np.array_equal(ft.ref_id, t["ref_id"]) and ft.n_ref == meta["n_ref"]
+    assert np.array_equal(ft.centroids, t["centroids"]), "centroids are not bit-identical to the oracle"
+    assert np.array_equal(ft.count, t["count"])
+    nodes = ft.nodes_dict()
+    assert all(np.array_equal(nodes[i], g["ref_nodes"][i]) for i in range(1, ft.n_ref))
+    assert ft.tree_dict() == golden_tree_dicts(g, k)[1]
+
+
+def test_build_medium_tree_bit_exact(vt, cuda):
+    """200 k descriptors, k=10, L=4 (deep levels use the global-atomic accumulation path)."""
+    x = vt.synth.sift_like(200_000, 128, n_centres=3000, seed=77)
+    desc, d = vt.engine.stage(x, cuda)
+    log = []
+    ft = vt.engine.build_tree(desc, d, 10, 4, n_iter=6, log=lambda **kw: log.append(kw))
+    t = vo.build_tree(x, 10, 4, 6)
+    assert np.array_equal(ft.internal, t["internal"]) and np.array_equal(ft.count, t["count"])
+    assert np.array_equal(ft.centroids, t["centroids"])
+    assert len(log) == 4
+
+
+def test_build_degenerate_inputs(vt, cuda):
+    # fewer points than branches: the root is a leaf (vocabulary.py:55)
+    x = np.array([[3, 4], [5, 6]], np.uint8)
+    desc, d = vt.engine.stage(x, cuda)
+    ft = vt.engine.build_tree(desc, d, 4, 3)
+    assert ft.n_ref == 1 and not ft.internal.any() and ft.centroids[0, 0] == 4.0
+    # all points identical: one full cluster, k-1 empty leaves that keep the initial centre
+    x = np.full((50, 8), 7, np.uint8)
+    desc, d = vt.engine.stage(x, cuda)
+    ft = vt.engine.build_tree(desc, d, 3, 2)
+    t = vo.build_tree(x, 3, 2, 10)
+    assert np.array_equal(ft.centroids, t["centroids"]) and np.array_equal(ft.count, t["count"])
+    assert np.array_equal(ft.ref_id, t["ref_id"])
+
+
+# ------------------------------------------------------------------------------------------ encode
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("all_nodes", [True, False])
+def test_encode_matches_propagate(vt, cuda, name, all_nodes):
+    torch = _torch()
+    ft, g, meta, images = _flat_from_golden(vt, name)
+    voc = vt.encoders.VocabularyTree(ft.k, ft.depth, descriptor=lambda im: im).set_tree(ft)
+    csr = voc.encode_batch(images, want_df=True, all_nodes=all_nodes)
+    ro, node, count = (csr[k_].cpu().numpy() for k_ in ("row_off", "node", "count"))
+    dense = csr_to_dense(ro, node, count, ft.n_ref)
+    ot = oracle_tree_from_flat(ft)
+    want = np.stack([vo.path_counts(ot, im, all_nodes=all_nodes) for im in images])
+    assert np.array_equal(dense, want)
+    if all_nodes:
+        assert np.array_equal(dense, g["counts"])                       # the reference's postings
+    assert np.array_equal(csr["sumsq"].cpu().numpy(), (want.astype(np.int64) ** 2).sum(1))
+    assert np.array_equal(csr["df"].cpu().numpy(), (want > 0).sum(0))
+    assert (ro[1:] - ro[:-1] == (want > 0).sum(1)).all()
+    assert (count > 0).all()
+    del torch
+
+
+def test_encode_large_images(vt, cuda):
+    """images near the shared-memory capacity (8192 descriptors) and a mix of sizes"""
+    ft, g, meta, images = _flat_from_golden(vt, "small")
+    rng = np.random.default_rng(3)
+    pool = np.concatenate(images)
+    imgs = [pool[rng.integers(0, len(pool), n)] for n in (8192, 1, 2049, 0, 1025, 5000, 33)]
+    voc = vt.encoders.VocabularyTree(ft.k, ft.depth, descriptor=lambda im: im).set_tree(ft)
+    ot = oracle_tree_from_flat(ft)
+    for all_nodes in (True, False):
+        csr = voc.encode_batch(imgs, all_nodes=all_nodes)
+        dense = csr_to_dense(*(csr[k_].cpu().numpy() for k_ in ("row_off", "node", "count")), ft.n_ref)
+        want = np.stack([vo.path_counts(ot, im, all_nodes=all_nodes) for im in imgs])
+        assert np.array_equal(dense, want)
+    with pytest.raises(ValueError):
+        voc.encode_batch([pool[rng.integers(0, len(pool), 8193)]])
+
+
+# ------------------------------------------------------------------------------------------ index + score
+def _expected_scores(counts, q_rows):
+    emb = np.stack([vo.embedding_dense(c) for c in counts])
+    return np.array([[vo.score_dense(emb[i], emb[q]) for i in range(len(counts))] for q in q_rows])
+
+
+def _assert_topk(ids, scores, want_scores_full, k, rtol=1e-5):
+    """ids must be the reference's order; swaps are only tolerated inside groups whose reference
+    scores agree to 1e-9 (rounding-level ties, documented in DESIGN.md)."""
+    for qi in range(len(ids)):
+        ws = want_scores_full[qi]
+        order = vo.retrieve_order(ws)[:k]
+        got = ids[qi][:len(order)]
+        np.testing.assert_allclose(scores[qi][:len(order)], ws[order], rtol=rtol, atol=1e-7)
+        bad = np.nonzero(got != order)[0]
+        for b in bad:
+            assert abs(ws[got[b]] - ws[order[b]]) <= 1e-9 * max(1.0, abs(ws[order[b]])), (qi, b, got, order)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_postings_and_topk_match_reference(vt, cuda, name):
+    ft, g, meta, images = _flat_from_golden(vt, name)
+    voc = vt.encoders.VocabularyTree(ft.k, ft.depth, descriptor=lambda im: im).set_tree(ft)
+    csr = voc.encode_batch(images, want_df=True)
+    index = vt.engine.build_index(csr, ft.n_ref)
+    # posting lists: per node the (image, count) pairs, in image order
+    off = index["post_off"].cpu().numpy().astype(np.int64)
+    post = index["postings"].cpu().numpy()
+    counts = g["counts"]
+    assert off[-1] == (counts > 0).sum()
+    for node in range(ft.n_ref):
+        seg = post[off[node]:off[node + 1]]
+        imgs = np.nonzero(counts[:, node])[0]
+        assert np.array_equal(seg[:, 0], imgs) and np.array_equal(seg[:, 1], counts[imgs, node])
+    # top-k for every image as query
+    k = min(10, len(images))
+    out = vt.engine.score(index, csr, k, want_all=True)
+    ids, sc = out["id"].cpu().numpy(), out["score"].cpu().numpy()
+    ref_sc = np.empty_like(g["scores"])
+    for qi in range(len(g["q_idx"])):
+        ref_sc[qi, g["order"][qi]] = g["scores"][qi]
+    assert np.array_equal(g["q_idx"], np.arange(len(images)))
+    _assert_topk(ids, sc, ref_sc, k)
+    # exact reference order (no tolerance) wherever the reference scores are distinct
+    for qi in range(len(images)):
+        top = g["order"][qi][:k]
+        if len(np.unique(g["scores"][qi][:k + 1])) == min(k + 1, len(images)):
+            assert np.array_equal(ids[qi], top)
+
+
+def test_score_multi_shard_random_csr(vt, cuda):
+    """20 k images (3 shards), synthetic sparse count vectors, leaf-words shaped."""
+    torch = _torch()
+    import scipy.sparse as sp
+    rng = np.random.default_rng(9)
+    n_img, n_ref, nnz_per = 20_000, 5000, 40
+    rows = np.repeat(np.arange(n_img), nnz_per)
+    cols = rng.integers(0, n_ref, n_img * nnz_per)
+    m = sp.coo_matrix((np.ones(len(rows), np.int64), (rows, cols)), shape=(n_img, n_ref)).tocsr()
+    m.sum_duplicates()
+    m.sort_indices()
+    m[17] = 0
+    m.eliminate_zeros()                                         # an image without words
+    m = m.tocsr()
+    csr = dict(row_off=torch.from_numpy(m.indptr.astype(np.int64)).to(cuda),
+               node=torch.from_numpy(m.indices.astype(np.int32)).to(cuda),
+               count=torch.from_numpy(m.data.astype(np.int32)).to(cuda),
+               sumsq=torch.from_numpy(np.asarray(m.multiply(m).sum(1)).ravel().astype(np.int64)).to(cuda),
+               n_img=n_img, nnz=m.nnz)
+    index = vt.engine.build_index(csr, n_ref)
+    assert index["n_shards"] == 3
+    q_rows = np.array([0, 5, 8191, 8192, 16384, 19999, 17, 12345])
+    mq = m[q_rows]
+    q = dict(row_off=torch.from_numpy(mq.indptr.astype(np.int64)).to(cuda),
+             node=torch.from_numpy(mq.indices.astype(np.int32)).to(cuda),
+             count=torch.from_numpy(mq.data.astype(np.int32)).to(cuda),
+             sumsq=torch.from_numpy(np.asarray(mq.multiply(mq).sum(1)).ravel().astype(np.int64)).to(cuda),
+             n_img=len(q_rows), nnz=mq.nnz)
+    k = 10
+    out = vt.engine.score(index, q, k, want_all=True)
+    ids, sc, allk = out["id"].cpu().numpy(), out["score"].cpu().numpy(), out["all_key"].cpu().numpy()
+    norm = np.sqrt(np.asarray(m.multiply(m).sum(1)).ravel().astype(np.float64))
+    dots = np.asarray((mq @ m.T).todense()).astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        key = np.where(norm > 0, dots / norm, -1.0)
+    np.testing.assert_allclose(allk, key, rtol=1e-12)
+    for qi, qr in enumerate(q_rows):
+        if norm[qr] == 0:
+            assert (sc[qi] == 1e6).all()
+            continue
+        order = np.lexsort((np.arange(n_img), -key[qi]))[:k]
+        assert np.array_equal(ids[qi], order), (qi, ids[qi], order)
+        want = np.sqrt(np.maximum(0, 2 - 2 * key[qi][order] / norm[qr]))
+        want[order == qr] = 0.0
+        np.testing.assert_allclose(sc[qi], want, rtol=1e-5, atol=1e-7)
+        assert ids[qi][0] == qr and sc[qi][0] == 0.0            # self match first, exactly zero
+
+
+@pytest.mark.parametrize("norm", ["l2", "l1"])
+def test_tfidf_modes_against_dense_oracle(vt, cuda, norm):
+    ft, g, meta, images = _flat_from_golden(vt, "orb")
+    voc = vt.encoders.VocabularyTree(ft.k, ft.depth, descriptor=lambda im: im).set_tree(ft)
+    ds = vt.ArrayDataset(images)
+    db = vt.Database(ds, voc, weighting="tfidf", norm=norm)
+    db.index()
+    counts = g["counts"].astype(np.int64)
+    w = vo.idf_weights(counts)
+    emb = np.stack([vo.weighted_embedding(c, w, norm) for c in counts])
+    q_rows = [0, 3, 40, 79]
+    ids, sc = db.retrieve_batch([ds.image_paths[i] for i in q_rows], k=8)
+    for qi, q in enumerate(q_rows):
+        ws = np.array([vo.score_lp(emb[i], emb[q], norm) for i in range(len(images))])
+        order = vo.retrieve_order(ws)[:8]
+        np.testing.assert_allclose(sc[qi], ws[order], rtol=2e-4, atol=2e-6)   # float32 weights
+        assert ids[qi][0] == q
+
+
+# ------------------------------------------------------------------------------------------ API flow
+@pytest.mark.parametrize("name", CASES)
+def test_notebook_flow_matches_reference(vt, cuda, name):
+    """NB[78-91]: VocabularyTree(...).fit -> Database(...).index -> retrieve, through the public
+    API, against the reference's outputs on the same inputs."""
+    g, meta = load_golden(name)
+    images, k, depth, n_iter = golden_inputs(name)
+    ds = vt.ArrayDataset([im.astype(np.float32) for im in images])
+    voc = vt.encoders.VocabularyTree(n_branches=k, depth=depth, descriptor=lambda im: im, n_iter=n_iter)
+    features = np.concatenate([ds.read_image(p) for p in ds.image_paths])
+    voc.fit(features)
+    nodes, tree = golden_tree_dicts(g, k)
+    assert voc.tree == tree
+    assert all(np.array_equal(voc.nodes[i], nodes[i]) for i in range(1, len(nodes)))
+    np.testing.assert_allclose(voc.nodes[0], nodes[0], rtol=1e-5, atol=1e-5)
+    # propagate_feature paths end at the reference's leaf
+    for i in range(0, len(features), max(1, len(features) // 25)):
+        p = voc.propagate_feature(features[i])
+        assert p[0] == 0 and p[-1] == g["ref_leaf"][i] and len(p) - 1 == g["ref_depth"][i]
+    db = vt.Database(ds, voc)
+    db.index()
+    for i in (0, len(images) // 2, len(images) - 1):
+        assert np.array_equal(db.embedding(ds.image_paths[i]), g["emb"][i], equal_nan=True)
+        assert np.array_equal(voc.embedding(ds.read_image(ds.image_paths[i])), g["emb"][i], equal_nan=True)
+    for qi in (0, len(images) // 3, len(images) - 1):
+        res = db.retrieve(ds.image_paths[qi])
+        got_order = [ds.image_paths.index(p) for p in res]
+        ws = np.empty(len(images))
+        ws[g["order"][qi]] = g["scores"][qi]
+        np.testing.assert_allclose(list(res.values()), g["scores"][qi], rtol=1e-5, atol=1e-7)
+        for r, (a, b) in enumerate(zip(got_order, g["order"][qi])):
+            assert a == b or abs(ws[a] - ws[b]) <= 1e-9, (qi, r)
+        s = db.score(ds.image_paths[1], ds.image_paths[qi])
+        assert s == ws[1]
+    # reference-shaped postings
+    post = voc.postings()
+    sha = vt.utils.get_image_id(ds.read_image(ds.image_paths[0]))
+    got0 = {n_: d_[sha] for n_, d_ in post.items() if sha in d_}
+    assert got0 == {int(n_): int(c) for n_, c in enumerate(g["counts"][0]) if c > 0}
