@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the vocabulary-tree hot path (BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU arm (oracle port of the reference)
+
+Primary metric: descriptors/s quantised through a k=10, L=6 (1 M-leaf) tree; one step = one pass
+of the fused descent kernel over this rank's shard of synthetic SIFT-shaped byte descriptors
+(BASELINE configs[2]: 100 M x 128 per GPU, tree replicated, no data-path collective -> weak
+scaling).  `value` is device-resident throughput, `e2e` the same metric through the host-buffer
+C-ABI call (vt_quantize_host: pinned host rows in, word ids out, copies inside the timed region).
+Secondary metric (same JSON line, key "secondary"): queries/s top-10 over a 1 M-image inverted
+file (BASELINE configs[3], leaf-words mode), database sharded by image id across ranks.
+
+Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+K_BRANCH, DEPTH, DIM = 10, 6, 128
+METRIC = "descriptors/s quantized (k=10,L=6 tree)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-desc", type=int, default=100_000_000, help="descriptors per GPU")
+    ap.add_argument("--e2e-desc", type=int, default=32_000_000, help="descriptors per end-to-end step per GPU")
+    ap.add_argument("--db-images", type=int, default=1_000_000, help="database images (whole job)")
+    ap.add_argument("--queries", type=int, default=10_000)
+    ap.add_argument("--words-per-image", type=int, default=1000)
+    ap.add_argument("--no-retrieval", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md recipe)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------- synthetic data
+def full_tree_tables(vt, k, depth):
+    nh = vt.tree.heap_size(k, depth)
+    exists = np.ones(nh, np.uint8)
+    internal = np.zeros(nh, np.uint8)
+    internal[:vt.tree.level_offset(k, depth)] = 1
+    ref_id, n_ref = vt.tree.reference_ids(exists, internal, k, depth)
+    return exists, internal, ref_id, n_ref
+
+
+def hashed_words(torch, img_ids, words_per_image, n_leaf, leaf_ref_base, device):
+    """Deterministic pseudo-random leaf words for any image id (so every rank can regenerate any
+    image): a 64-bit mix of (image, slot) reduced modulo the number of leaves."""
+    slot = torch.arange(words_per_image, device=device, dtype=torch.int64)[None, :]
+    x = img_ids.to(torch.int64)[:, None] * 1_000_003 + slot + 0x9E3779B9
+    x = (x ^ (x >> 15)) * 0x2C1B3C6D
+    x = (x ^ (x >> 12)) * 0x297A2D39
+    x = x ^ (x >> 15)
+    leaf = (x & 0x7FFFFFFFFFFF) % n_leaf
+    return leaf_ref_base[leaf].to(torch.int32).reshape(-1)
+
+
+# ----------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm for the path (oracle port, all host threads)
+    timed on a bounded sample of the same workload.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    import vtree_b200 as vt
+    from oracle import vt_oracle as vo
+    cent = vt.synth.hierarchical_tree(K_BRANCH, DEPTH, DIM, seed=7, device="cpu")
+    exists, internal, ref_id, n_ref = full_tree_tables(vt, K_BRANCH, DEPTH)
+    tree = dict(k=K_BRANCH, depth=DEPTH, D=DIM, DP=DIM, centroids=cent.numpy(), exists=exists, internal=internal,
+                ref_id=ref_id, n_ref=n_ref)
+    cores = os.cpu_count() or 1
+    probe = vt.synth.descriptors_from_tree(cent, K_BRANCH, DEPTH, 20_000, seed=11).numpy()
+    t0 = time.perf_counter()
+    vo.descend(tree, probe)
+    rate = len(probe) / (time.perf_counter() - t0)
+    sample = int(max(20_000, min(5_000_000, rate * 2.0)))           # ~2 s of CPU work per step
+    x = vt.synth.descriptors_from_tree(cent, K_BRANCH, DEPTH, sample, seed=12).numpy()
+    for _ in range(max(1, min(args.warmup, 2))):
+        vo.descend(tree, x[:max(1, sample // 4)])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        vo.descend(tree, x)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "descriptors/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "quantize SIFT-128 byte descriptors, k=10 L=6 (1M-leaf) tree, CPU sample of %d per step" % sample},
+            "cpu_baseline": {"value": value, "unit": "descriptors/s", "cores": cores, "kind": "port",
+                             "sample": "%d descriptors x %d steps, OpenMP over all host threads" % (sample, args.steps)},
+            "e2e": {"value": value, "unit": "descriptors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    del torch
+
+
+# ----------------------------------------------------------------------------------- our arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import vtree_b200 as vt
+    from vtree_b200 import engine, _native as nat
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    nat.require_device()
+    lib = nat.load()
+    comm = vt.dist.Comm() if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- tree (replicated) and this rank's descriptor shard -------------------------------------
+    cent = vt.synth.hierarchical_tree(K_BRANCH, DEPTH, DIM, seed=7, device=dev)
+    exists, internal, ref_id, n_ref = full_tree_tables(vt, K_BRANCH, DEPTH)
+    tree_dev = dict(centroids=cent, internal=torch.from_numpy(internal).to(dev), ref_id=torch.from_numpy(ref_id).to(dev))
+    n = args.n_desc
+    desc = vt.synth.descriptors_from_tree(cent, K_BRANCH, DEPTH, n, seed=100 + rank)
+    stats = torch.zeros(4, dtype=torch.int64, device=dev)
+
+    # ---- FP32 pipe peak on this box ---------------------------------------------------------------
+    scratch = torch.empty(148 * 8 * 256 * 2, dtype=torch.float32, device=dev)
+    peak_tf, peak_ms = C.c_double(0), C.c_double(0)
+    nat.check(lib.vt_measure_fp32_peak(nat.ptr(scratch), 4096, 5, C.byref(peak_tf), C.byref(peak_ms), nat.stream_ptr()),
+              "vt_measure_fp32_peak")
+
+    # ---- device-resident throughput ---------------------------------------------------------------
+    for _ in range(args.warmup):
+        words = engine.quantize(tree_dev, K_BRANCH, DEPTH, desc, stats=stats)
+    stats.zero_()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    with ClockSampler(local) as clocks:
+        t0 = time.perf_counter()
+        for a, b in ev:
+            a.record()
+            words = engine.quantize(tree_dev, K_BRANCH, DEPTH, desc, stats=stats)   # 12.8 GB input >> 126 MB L2
+            b.record()
+        barrier()
+        wall = time.perf_counter() - t0
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    step_ms = max_over_ranks(max(wall / args.steps * 1e3, kern_ms))
+    value = n * world / (step_ms * 1e-3)
+    rechecks = int(stats[0].item())
+
+    # ---- end to end through the host-buffer C-ABI call ------------------------------------------
+    n_e2e = min(n, args.e2e_desc)
+    h_desc = torch.empty((n_e2e, DIM), dtype=torch.uint8).pin_memory()
+    h_desc.copy_(desc[:n_e2e])
+    h_word = torch.empty(n_e2e, dtype=torch.int32).pin_memory()
+    e2e_steps = max(3, min(args.steps, 5))
+    for _ in range(2):
+        engine.quantize_host(tree_dev, K_BRANCH, DEPTH, h_desc, h_word)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        engine.quantize_host(tree_dev, K_BRANCH, DEPTH, h_desc, h_word)               # blocks until h_word is filled
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) / e2e_steps * 1e3)
+    e2e_value = n_e2e * world / (e2e_ms * 1e-3)
+    e2e_ok = bool(torch.equal(h_word, words[:n_e2e].cpu()))
+
+    # ---- secondary metric: queries/s top-10 over the sharded inverted file ---------------------
+    secondary = None
+    if not args.no_retrieval:
+        secondary = bench_retrieval(args, torch, vt, engine, nat, dev, rank, world, comm, ref_id, n_ref, barrier,
+                                    max_over_ranks)
+
+    # ---- CPU baseline (rank 0, single-GPU runs only) -------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args, vt, cent, exists, internal, ref_id, n_ref, desc, words)
+
+    if rank == 0:
+        flop_per_desc = 3 * K_BRANCH * DIM * DEPTH                 # sub, mul, add per element per candidate
+        alg_bytes = DIM + 4                                        # byte row in, int32 word id out
+        per_launch = n
+        achieved_tf = flop_per_desc * per_launch / (kern_ms * 1e-3) / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        line = {
+            "metric": METRIC, "value": value, "unit": "descriptors/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[2]: quantize %d SIFT-128 byte descriptors per GPU through a "
+                                   "k=10 L=6 (1,111,111-node) tree, tree replicated, descriptors sharded" % n,
+                       "l2": "input (%.1f GB) is larger than L2; nothing is flushed between steps" % (n * DIM / 1e9),
+                       "tree": "synthetic hierarchical mixture, seed 7", "binary64_rechecks_per_step": rechecks // max(args.steps, 1)},
+            "e2e": {"value": e2e_value, "unit": "descriptors/s", "h2d_bytes_per_step": n_e2e * DIM,
+                    "d2h_bytes_per_step": n_e2e * 4, "descriptors_per_step": n_e2e, "matches_device_path": e2e_ok,
+                    "api": "vt_quantize_host (engine.quantize_host)"},
+            "gpu_launches": args.steps,
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "fp32", "kernel": "quantize_kernel<uint8_t,128>",
+                         "achieved": achieved_tf, "peak": peak_tf.value, "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak_tf.value if peak_tf.value else None,
+                         "peak_source": "FFMA microbenchmark on this device (vt_measure_fp32_peak)",
+                         "flop_per_descriptor": flop_per_desc, "kernel_ms": kern_ms,
+                         "hbm": {"achieved": alg_bytes * per_launch / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                                 "unit": "GB/s", "bytes_per_descriptor": alg_bytes,
+                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+                         "traffic": None},
+            "cpu_baseline": cpu,
+            "secondary": secondary,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_retrieval(args, torch, vt, engine, nat, dev, rank, world, comm, ref_id, n_ref, barrier, max_over_ranks):
+    n_leaf = K_BRANCH ** DEPTH
+    leaf_ref = torch.from_numpy(ref_id[vt.tree.level_offset(K_BRANCH, DEPTH):].astype(np.int64)).to(dev)
+    lo, hi = vt.dist.shard_range(args.db_images, rank, world)
+    wpi = args.words_per_image
+    dummy = dict(parent_ref=torch.zeros(1, dtype=torch.int32, device=dev), level_ref=torch.zeros(1, dtype=torch.uint8, device=dev))
+
+    def encode_ids(ids):
+        words = torch.empty(len(ids) * wpi, dtype=torch.int32, device=dev)
+        step = 65536
+        for s in range(0, len(ids), step):
+            e = min(len(ids), s + step)
+            words[s * wpi:e * wpi] = hashed_words(torch, ids[s:e], wpi, n_leaf, leaf_ref, dev)
+        off = torch.arange(len(ids) + 1, dtype=torch.int64, device=dev) * wpi
+        return engine.encode(words, off, dummy, DEPTH, n_ref, all_nodes=False)
+
+    t0 = time.perf_counter()
+    csr = encode_ids(torch.arange(lo, hi, device=dev))
+    index = engine.build_index(csr, n_ref)
+    torch.cuda.synchronize()
+    t_index = time.perf_counter() - t0
+    q = args.queries
+    member = (torch.arange(q // 2, device=dev, dtype=torch.int64) * 197) % max(args.db_images, 1)
+    fresh = args.db_images + torch.arange(q - q // 2, device=dev, dtype=torch.int64)
+    qcsr = encode_ids(torch.cat([member, fresh]))
+    topk = 10
+
+    def one_pass():
+        local_out = engine.score(index, qcsr, topk)
+        if world == 1:
+            return local_out["id"], local_out["score"]
+        ids, sc, _ = vt.dist.retrieve_sharded(lambda: local_out, lo, topk, comm)
+        return ids, sc
+
+    for _ in range(2):
+        ids, sc = one_pass()
+    steps = 3
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ids, sc = one_pass()
+    barrier()
+    ms = max_over_ranks((time.perf_counter() - t0) / steps * 1e3)
+    ok = bool((ids[:q // 2, 0].to(torch.int64) == member).all().item() and (sc[:q // 2, 0] == 0).all().item())
+    postings_per_query = float(csr["nnz"]) * world / max(args.db_images, 1) * wpi / n_leaf * 1.0
+    return {"metric": "queries/s top-10 @1M images", "value": q / (ms * 1e-3), "unit": "queries/s",
+            "ms_per_batch": ms, "queries": q, "db_images": args.db_images, "words_per_image": wpi, "mode": "leaf-words tf/L2",
+            "self_match_rank0": ok, "index_build_s": t_index, "n_shards_per_gpu": index["n_shards"],
+            "hbm": {"algorithmic_bytes_per_query": 8.0 * wpi * (args.db_images * wpi / n_leaf),
+                    "achieved_GBps": 8.0 * wpi * (args.db_images * wpi / n_leaf) * q / (ms * 1e-3) / 1e9},
+            "postings_per_word": postings_per_query}
+
+
+def cpu_baseline(args, vt, cent, exists, internal, ref_id, n_ref, desc, words):
+    """The oracle (C port of the reference's descent, OpenMP over all host threads) on a bounded
+    sample of the same descriptors; its output doubles as a parity check of the GPU words."""
+    from oracle import vt_oracle as vo
+    tree = dict(k=K_BRANCH, depth=DEPTH, D=DIM, DP=DIM, centroids=cent.cpu().numpy(), exists=exists,
+                internal=internal, ref_id=ref_id, n_ref=n_ref)
+    probe = desc[:20_000].cpu().numpy()
+    t0 = time.perf_counter()
+    vo.descend(tree, probe)
+    rate = len(probe) / (time.perf_counter() - t0)
+    sample = int(max(20_000, min(len(desc), rate * args.cpu_seconds)))
+    x = desc[:sample].cpu().numpy()
+    t0 = time.perf_counter()
+    leaf = vo.descend(tree, x)
+    dt = time.perf_counter() - t0
+    mism = int((ref_id[leaf] != words[:sample].cpu().numpy()).sum())
+    return {"value": sample / dt, "unit": "descriptors/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "first %d descriptors of the GPU workload, oracle/vt_oracle.c vt_or_descend (binary64), %.1f s" % (sample, dt),
+            "gpu_word_mismatches_on_sample": mism}
+
+
+if __name__ == "__main__":
+    main()

@@ -11,7 +11,7 @@
  *
  * Conventions
  *   - every pointer named d_* is DEVICE memory owned by the caller (nothing is allocated or
- *     freed behind the ABI except by the vt_pipe_* / vt_host_* helpers, which say so);
+ *     freed behind the ABI except by vt_quantize_host, which stages through its own buffers);
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
  *   - every function returns 0 on success, a negative VT_E* code otherwise, and
  *     vt_last_error() then returns a human-readable message (thread-local);
@@ -169,6 +169,11 @@ int vt_topk_merge(const double *d_in_key, const int32_t *d_in_id, int64_t n_quer
                   int topk, int mode, const double *d_q_rnorm, const uint64_t *d_q_sumsq,
                   const uint64_t *d_img_sumsq, double *d_out_key, int32_t *d_out_id,
                   double *d_out_score, void *stream);
+
+/* ---- measurement helper (bench.py): best-of-reps FP32 FFMA throughput of the current device in
+ * TFLOP/s; d_scratch holds at least sm_count*8*256 floats. */
+int vt_measure_fp32_peak(float *d_scratch, int iters, int reps, double *tflops, double *ms_best,
+                         void *stream);
 
 #ifdef __cplusplus
 }

@@ -17,6 +17,7 @@ from .tree import FlatTree  # noqa: F401
 from . import encoders  # noqa: F401
 from .database import Database  # noqa: F401
 from . import engine  # noqa: F401
+from . import dist  # noqa: F401
 from . import _native  # noqa: F401
 
 __all__ = ["Database", "Dataset", "ArrayDataset", "FlatTree", "encoders", "utils", "engine", "synth"]

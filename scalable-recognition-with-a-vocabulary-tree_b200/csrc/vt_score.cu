@@ -192,6 +192,9 @@ topk_merge_kernel(const double *__restrict__ in_key, const int32_t *__restrict__
                             }
                         } else if (MODE == VT_SCORE_W_L2) {
                             s = sqrt(fmax(0.0, 2.0 - 2.0 * key));
+                            // float32 weights leave ~1e-7 noise on the cosine; identical bags (same tf
+                            // norm, cosine 1 within that noise) score exactly 0 like in tf mode
+                            if (q_sumsq && img_sumsq && img_sumsq[id] == q_sumsq[q] && key >= 1.0 - 4e-6) s = 0.0;
                         } else {
                             s = fmax(0.0, 2.0 - key);
                         }

@@ -131,22 +131,62 @@ class _NoComm:
         return t[None]
 
 
+class CudaLevelOps:
+    """The five per-level device steps of the build, each one C-ABI call.  ``build_tree`` only
+    talks to this interface so that the multi-rank protocol around it can be exercised on CPU
+    (gloo) with a test double; the product always uses this class."""
+
+    def __init__(self):
+        nat.require_device()
+        self.lib = _lib()
+
+    def column_sums(self, desc):
+        n, dp = desc.shape
+        col = torch.zeros(dp, dtype=torch.int64, device=desc.device)
+        nat.check(self.lib.vt_column_sums(nat.ptr(desc), VT_U8, n, dp, nat.ptr(col), nat.stream_ptr()), "vt_column_sums")
+        return col
+
+    def kmeans_init(self, desc, perm, seg_begin, seg_local, seg_global, rank0, n_nodes, k, child_cent):
+        nat.check(self.lib.vt_kmeans_init(nat.ptr(desc), VT_U8, desc.shape[1], nat.ptr(perm), nat.ptr(seg_begin),
+                                          nat.ptr(seg_local), nat.ptr(seg_global), nat.ptr(rank0), n_nodes, k,
+                                          nat.ptr(child_cent), nat.stream_ptr()), "vt_kmeans_init")
+
+    def kmeans_assign(self, desc, perm, parent, n_active, node_internal, n_nodes, k, child_cent, label, sums,
+                      counts, changed, stats):
+        nat.check(self.lib.vt_kmeans_assign(nat.ptr(desc), VT_U8, desc.shape[1], nat.ptr(perm), nat.ptr(parent),
+                                            n_active, nat.ptr(node_internal), n_nodes, k, nat.ptr(child_cent),
+                                            nat.ptr(label), nat.ptr(sums), nat.ptr(counts), nat.ptr(changed),
+                                            nat.ptr(stats), nat.stream_ptr()), "vt_kmeans_assign")
+
+    def kmeans_update(self, sums, counts, n_rows, dp, child_cent):
+        nat.check(self.lib.vt_kmeans_update(nat.ptr(sums), nat.ptr(counts), n_rows, dp, nat.ptr(child_cent),
+                                            nat.stream_ptr()), "vt_kmeans_update")
+
+    def partition(self, parent, label, n_active, node_internal, k, n_rows, perm):
+        """stable partition of every node's members into its children (vocabulary.py:64-66):
+        returns (child index per member, member rows), both sorted by child index; members of leaf
+        nodes carry the sentinel key ``n_rows`` and end up last."""
+        keys = torch.empty(max(n_active, 1), dtype=torch.int32, device=parent.device)
+        nat.check(self.lib.vt_partition_keys(nat.ptr(parent), nat.ptr(label), n_active, nat.ptr(node_internal), k,
+                                             n_rows, nat.ptr(keys), nat.stream_ptr()), "vt_partition_keys")
+        return sort_pairs(keys[:n_active], perm, int(n_rows).bit_length())
+
+
 def build_tree(desc: torch.Tensor, d: int, k: int, depth: int, n_iter: int = 10, comm=None,
-               stats: torch.Tensor = None, log=None) -> FlatTree:
+               stats: torch.Tensor = None, log=None, ops=None) -> FlatTree:
     """Level-synchronous hierarchical k-means over byte descriptors [N, DP] (this rank's shard).
 
     Per level: seeded initial centres (member floor(j*m/k) of every node), ``n_iter`` exact Lloyd
     steps over ALL nodes of the level at once (early exit when no label changes), stable
     partition of the members into the children.  With ``comm`` (see ``dist.Comm``) the integer
     sums/counts are all-reduced, so every rank ends with the same tree, bit for bit."""
-    lib = _lib()
     if desc.dtype != torch.uint8:
         raise TypeError("build_tree needs byte descriptors (integer valued 0..255); stage() keeps float rows only "
                         "when the data is not byte-exact, which the exact-sum k-means does not support")
+    ops = ops or CudaLevelOps()
     comm = comm or _NoComm()
     dev = desc.device
     n, dp = desc.shape
-    s = nat.stream_ptr()
     n_heap = heap_size(k, depth)
     cent = torch.zeros((n_heap, dp), dtype=torch.float32, device=dev)
     internal = torch.zeros(n_heap, dtype=torch.uint8, device=dev)
@@ -155,9 +195,7 @@ def build_tree(desc: torch.Tensor, d: int, k: int, depth: int, n_iter: int = 10,
     exists[0] = 1
 
     # root = mean of all features (vocabulary.py:48-49), exact
-    col = torch.zeros(dp + 1, dtype=torch.int64, device=dev)
-    nat.check(lib.vt_column_sums(nat.ptr(desc), VT_U8, n, dp, nat.ptr(col), s), "vt_column_sums")
-    col[dp] = n
+    col = torch.cat([ops.column_sums(desc), torch.tensor([n], dtype=torch.int64, device=dev)])
     col = comm.all_reduce(col)
     n_total = int(col[dp].item())
     if n_total > 0:
@@ -182,15 +220,11 @@ def build_tree(desc: torch.Tensor, d: int, k: int, depth: int, n_iter: int = 10,
         seg_begin = torch.cumsum(seg_local, 0) - seg_local
         if comm.world > 1:
             allc = comm.all_gather_counts(seg_local)                      # [world, n_nodes]
-            rank0 = allc[:comm.rank].sum(0) if comm.rank > 0 else torch.zeros_like(seg_local)
-            nat.check(lib.vt_kmeans_init(nat.ptr(desc), VT_U8, dp, nat.ptr(perm), nat.ptr(seg_begin),
-                                         nat.ptr(seg_local), nat.ptr(seg_global), nat.ptr(rank0.contiguous()),
-                                         n_nodes, k, nat.ptr(child_cent), s), "vt_kmeans_init")
-            comm.all_reduce(child_cent)                                    # one owner per row: exact
+            rank0 = (allc[:comm.rank].sum(0) if comm.rank > 0 else torch.zeros_like(seg_local)).contiguous()
+            ops.kmeans_init(desc, perm, seg_begin, seg_local, seg_global, rank0, n_nodes, k, child_cent)
+            comm.all_reduce(child_cent)                                   # one owner per row: exact
         else:
-            nat.check(lib.vt_kmeans_init(nat.ptr(desc), VT_U8, dp, nat.ptr(perm), nat.ptr(seg_begin),
-                                         nat.ptr(seg_local), None, None, n_nodes, k, nat.ptr(child_cent), s),
-                      "vt_kmeans_init")
+            ops.kmeans_init(desc, perm, seg_begin, seg_local, None, None, n_nodes, k, child_cent)
 
         label = torch.full((max(n_active, 1),), 255, dtype=torch.uint8, device=dev)
         acc = torch.zeros(n_rows * dp + n_rows + 1, dtype=torch.int64, device=dev)   # sums | counts | changed
@@ -200,13 +234,11 @@ def build_tree(desc: torch.Tensor, d: int, k: int, depth: int, n_iter: int = 10,
         def assign():
             nonlocal local_counts
             acc.zero_()
-            nat.check(lib.vt_kmeans_assign(nat.ptr(desc), VT_U8, dp, nat.ptr(perm), nat.ptr(parent), n_active,
-                                           nat.ptr(node_internal), n_nodes, k, nat.ptr(child_cent), nat.ptr(label),
-                                           nat.ptr(sums), nat.ptr(counts), nat.ptr(changed), nat.ptr(stats), s),
-                      "vt_kmeans_assign")
+            ops.kmeans_assign(desc, perm, parent, n_active, node_internal, n_nodes, k, child_cent, label, sums,
+                              counts, changed, stats)
             if comm.world > 1:
                 local_counts = counts.clone()
-                comm.all_reduce(acc)                                       # sums, counts and changed in one go
+                comm.all_reduce(acc)                                      # sums, counts and changed in one go
             else:
                 local_counts = counts
 
@@ -215,13 +247,12 @@ def build_tree(desc: torch.Tensor, d: int, k: int, depth: int, n_iter: int = 10,
         for it in range(n_iter):
             assign()
             if it > 0 and int(changed.item()) == 0:
-                converged = True                                           # labels repeat: fixed point
+                converged = True                                          # labels repeat: fixed point
                 break
-            nat.check(lib.vt_kmeans_update(nat.ptr(sums), nat.ptr(counts), n_rows, dp, nat.ptr(child_cent), s),
-                      "vt_kmeans_update")
+            ops.kmeans_update(sums, counts, n_rows, dp, child_cent)
             iters += 1
         if not converged:
-            assign()                                                       # labels_ against the final centres
+            assign()                                                      # labels_ against the final centres
         if log is not None:
             log(level=level, nodes=n_nodes, members=n_active, iters=iters, converged=converged)
 
@@ -232,18 +263,15 @@ def build_tree(desc: torch.Tensor, d: int, k: int, depth: int, n_iter: int = 10,
         seg_local = (local_counts * kid_exists).clone()
         if level + 1 >= depth:
             break
-        # stable partition of every node's members into its children (vocabulary.py:64-66)
-        keys = torch.empty(max(n_active, 1), dtype=torch.int32, device=dev)
-        nat.check(lib.vt_partition_keys(nat.ptr(parent), nat.ptr(label), n_active, nat.ptr(node_internal), k,
-                                        n_rows, nat.ptr(keys), s), "vt_partition_keys")
-        skeys, svals = sort_pairs(keys[:n_active], perm, int(n_rows).bit_length())
+        skeys, svals = ops.partition(parent, label, n_active, node_internal, k, n_rows, perm)
         n_next = int(seg_local.sum().item())
         perm = svals[:n_next].contiguous()
         parent = skeys[:n_next].contiguous()
 
     tree = FlatTree(k, depth, d, cent.cpu().numpy(), exists.cpu().numpy(), internal.cpu().numpy(),
                     count_heap.cpu().numpy())
-    tree.adopt_device(dev, cent, internal)
+    if dev.type == "cuda":
+        tree.adopt_device(dev, cent, internal)
     return tree
 
 
