@@ -208,8 +208,14 @@ def main():
               "vt_measure_fp32_peak")
 
     # ---- device-resident throughput ---------------------------------------------------------------
+    work = torch.empty(int(lib.vt_quantize_sorted_work_bytes(n)), dtype=torch.uint8, device=dev)
+
+    def one_step():
+        # level-synchronous sorted descent: 6 level kernels + the radix passes between them
+        return engine.quantize(tree_dev, K_BRANCH, DEPTH, desc, stats=stats, method="sorted", work=work)
+
     for _ in range(args.warmup):
-        words = engine.quantize(tree_dev, K_BRANCH, DEPTH, desc, stats=stats)
+        words = one_step()
     stats.zero_()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
@@ -217,7 +223,7 @@ def main():
         t0 = time.perf_counter()
         for a, b in ev:
             a.record()
-            words = engine.quantize(tree_dev, K_BRANCH, DEPTH, desc, stats=stats)   # 12.8 GB input >> 126 MB L2
+            words = one_step()                                  # 12.8 GB input >> 126 MB L2
             b.record()
         barrier()
         wall = time.perf_counter() - t0
@@ -225,6 +231,32 @@ def main():
     step_ms = max_over_ranks(max(wall / args.steps * 1e3, kern_ms))
     value = n * world / (step_ms * 1e-3)
     rechecks = int(stats[0].item())
+
+    # per-stage CUDA events (same call, measurement variant): which share of a step is the level kernel
+    lvl = (C.c_float * DEPTH)()
+    srt = (C.c_float * DEPTH)()
+    lvl_acc, srt_acc, prof_reps = np.zeros(DEPTH), np.zeros(DEPTH), 3
+    for _ in range(prof_reps):
+        nat.check(lib.vt_quantize_sorted_profile(nat.ptr(desc), 0, n, DIM, nat.ptr(cent), nat.ptr(tree_dev["internal"]),
+                                                 nat.ptr(tree_dev["ref_id"]), K_BRANCH, DEPTH, None, nat.ptr(words), None,
+                                                 nat.ptr(work), work.numel(), lvl, srt, nat.stream_ptr()),
+                  "vt_quantize_sorted_profile")
+        lvl_acc += np.array(list(lvl))
+        srt_acc += np.array(list(srt))
+    level_ms, sort_ms = lvl_acc / prof_reps, srt_acc / prof_reps
+    sort_passes = sum(-(-int(K_BRANCH ** (l + 1)).bit_length() // 8) for l in range(DEPTH - 1))
+    launches_per_step = DEPTH + 3 * sort_passes
+
+    # the single-launch fused descent on a slice, for comparison
+    n_f = min(n, 8_000_000)
+    for _ in range(2):
+        engine.quantize(tree_dev, K_BRANCH, DEPTH, desc[:n_f], method="fused")
+    fa, fb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fa.record()
+    engine.quantize(tree_dev, K_BRANCH, DEPTH, desc[:n_f], method="fused")
+    fb.record()
+    torch.cuda.synchronize()
+    fused_rate = n_f / (fa.elapsed_time(fb) * 1e-3)
 
     # ---- end to end through the host-buffer C-ABI call ------------------------------------------
     n_e2e = min(n, args.e2e_desc)
@@ -258,7 +290,8 @@ def main():
         flop_per_desc = 3 * K_BRANCH * DIM * DEPTH                 # sub, mul, add per element per candidate
         alg_bytes = DIM + 4                                        # byte row in, int32 word id out
         per_launch = n
-        achieved_tf = flop_per_desc * per_launch / (kern_ms * 1e-3) / 1e12
+        lvl_total_ms = float(level_ms.sum())
+        achieved_tf = flop_per_desc * per_launch / (lvl_total_ms * 1e-3) / 1e12
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -276,13 +309,20 @@ def main():
             "e2e": {"value": e2e_value, "unit": "descriptors/s", "h2d_bytes_per_step": n_e2e * DIM,
                     "d2h_bytes_per_step": n_e2e * 4, "descriptors_per_step": n_e2e, "matches_device_path": e2e_ok,
                     "api": "vt_quantize_host (engine.quantize_host)"},
-            "gpu_launches": args.steps,
+            "gpu_launches": args.steps * launches_per_step,
             "clocks": clocks.summary(),
-            "roofline": {"bound": "fp32", "kernel": "quantize_kernel<uint8_t,128>",
+            "roofline": {"bound": "fp32", "kernel": "level_kernel<128> (vt_quantize_sorted.cu), %d launches per step" % DEPTH,
                          "achieved": achieved_tf, "peak": peak_tf.value, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf.value if peak_tf.value else None,
                          "peak_source": "FFMA microbenchmark on this device (vt_measure_fp32_peak)",
-                         "flop_per_descriptor": flop_per_desc, "kernel_ms": kern_ms,
+                         "flop_per_descriptor": flop_per_desc, "kernel_ms_per_step": lvl_total_ms,
+                         "level_kernel_ms": [round(float(v), 3) for v in level_ms],
+                         "resort_ms": [round(float(v), 3) for v in sort_ms],
+                         "kernel_share_of_step": lvl_total_ms / kern_ms,
+                         "whole_step": {"achieved": flop_per_desc * per_launch / (kern_ms * 1e-3) / 1e12,
+                                        "frac": flop_per_desc * per_launch / (kern_ms * 1e-3) / 1e12 / peak_tf.value,
+                                        "step_ms_events": kern_ms},
+                         "fused_single_launch_descent": {"value": fused_rate, "unit": "descriptors/s", "rows": n_f},
                          "hbm": {"achieved": alg_bytes * per_launch / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak,
                                  "unit": "GB/s", "bytes_per_descriptor": alg_bytes,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},

@@ -67,6 +67,25 @@ int vt_quantize(const void *d_desc, int dtype, int64_t n, int dp,
                 int k, int depth, int32_t start,
                 int32_t *d_leaf_heap, int32_t *d_word, uint64_t *d_stats, void *stream);
 
+/* Same contract and bit-identical results, organised for LARGE batches: one pass per tree level
+ * over the batch sorted by current node (warp-uniform centroid loads served by L1 instead of
+ * per-descriptor gathers that miss L2 on deep levels).  Byte descriptors only; d_work is scratch
+ * of vt_quantize_sorted_work_bytes(n) bytes. */
+int64_t vt_quantize_sorted_work_bytes(int64_t n);
+int vt_quantize_sorted(const void *d_desc, int dtype, int64_t n, int dp,
+                       const float *d_centroids, const uint8_t *d_internal, const int32_t *d_ref_id,
+                       int k, int depth, int32_t *d_leaf_heap, int32_t *d_word, uint64_t *d_stats,
+                       void *d_work, int64_t work_bytes, void *stream);
+
+/* Measurement variant of vt_quantize_sorted (bench.py): CUDA events around every stage;
+ * h_level_ms[depth] / h_sort_ms[depth] (host) receive the per-level kernel and re-sort durations.
+ * Synchronises the stream. */
+int vt_quantize_sorted_profile(const void *d_desc, int dtype, int64_t n, int dp,
+                               const float *d_centroids, const uint8_t *d_internal,
+                               const int32_t *d_ref_id, int k, int depth, int32_t *d_leaf_heap,
+                               int32_t *d_word, uint64_t *d_stats, void *d_work, int64_t work_bytes,
+                               float *h_level_ms, float *h_sort_ms, void *stream);
+
 /* Host-buffer convenience used for end-to-end timing: descriptors in (preferably pinned) host
  * memory are streamed to the device in chunks on internal streams (copy/compute overlap), word
  * ids are copied back to h_word.  The tree stays device resident.  `chunk_rows` <= 0 picks a

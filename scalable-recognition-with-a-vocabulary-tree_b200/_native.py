@@ -25,6 +25,9 @@ SIGNATURES = {
     "vt_stage_f32_to_u8": (_int, [_vp, _i64, _int, _vp, _int, _vp, _vp]),
     "vt_stage_pad": (_int, [_vp, _i64, _int, _vp, _int, _int, _vp]),
     "vt_quantize": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _int, _int, _i32, _vp, _vp, _vp, _vp]),
+    "vt_quantize_sorted_work_bytes": (_i64, [_i64]),
+    "vt_quantize_sorted": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _int, _int, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "vt_quantize_sorted_profile": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _int, _int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "vt_quantize_host": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _int, _int, _vp, _i64]),
     "vt_kmeans_init": (_int, [_vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp, _vp]),
     "vt_kmeans_assign": (_int, [_vp, _int, _int, _vp, _vp, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

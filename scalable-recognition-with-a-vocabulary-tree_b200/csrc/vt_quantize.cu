@@ -106,6 +106,9 @@ extern "C" int vt_quantize(const void *d_desc, int dtype, int64_t n, int dp, con
 }
 
 // ---- host-buffer pipeline (end-to-end path) ---------------------------------------------------------
+int vt_quantize_sorted_impl(const void *d_desc, int64_t n, int dp, const float *d_centroids, const uint8_t *d_internal,
+                            const int32_t *d_ref_id, int k, int depth, int32_t *d_leaf_heap, int32_t *d_word,
+                            uint64_t *d_stats, void *d_work, cudaStream_t s, cudaEvent_t *ev);
 extern "C" int vt_quantize_host(const void *h_desc, int dtype, int64_t n, int dp, const float *d_centroids,
                                 const uint8_t *d_internal, const int32_t *d_ref_id, int k, int depth,
                                 int32_t *h_word, int64_t chunk_rows)
@@ -115,11 +118,14 @@ extern "C" int vt_quantize_host(const void *h_desc, int dtype, int64_t n, int dp
     VT_CHECK_ARG(d_ref_id != nullptr, "d_ref_id required");
     if (n == 0) return VT_OK;
     const size_t esz = dtype == VT_U8 ? 1 : 4;
-    if (chunk_rows <= 0) chunk_rows = (int64_t)1 << 20;
+    if (chunk_rows <= 0) chunk_rows = (int64_t)1 << 22;
     if (chunk_rows > n) chunk_rows = n;
+    // large byte chunks go through the level-synchronous sorted descent (same ids, far less DRAM traffic)
+    const bool sorted = dtype == VT_U8 && depth >= 2 && chunk_rows >= ((int64_t)1 << 18);
     constexpr int NS = 3;
     cudaStream_t st[NS] = {};
     void *dbuf[NS] = {};
+    void *work[NS] = {};
     int32_t *wbuf[NS] = {};
     int rc = VT_OK;
     auto cleanup = [&]() {
@@ -127,12 +133,14 @@ extern "C" int vt_quantize_host(const void *h_desc, int dtype, int64_t n, int dp
             if (st[s]) { cudaStreamSynchronize(st[s]); cudaStreamDestroy(st[s]); }
             if (dbuf[s]) cudaFree(dbuf[s]);
             if (wbuf[s]) cudaFree(wbuf[s]);
+            if (work[s]) cudaFree(work[s]);
         }
     };
     for (int s = 0; s < NS; ++s) {
         if (cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking) != cudaSuccess ||
             cudaMalloc(&dbuf[s], (size_t)chunk_rows * dp * esz) != cudaSuccess ||
-            cudaMalloc((void **)&wbuf[s], (size_t)chunk_rows * sizeof(int32_t)) != cudaSuccess) {
+            cudaMalloc((void **)&wbuf[s], (size_t)chunk_rows * sizeof(int32_t)) != cudaSuccess ||
+            (sorted && cudaMalloc(&work[s], (size_t)vt_quantize_sorted_work_bytes(chunk_rows)) != cudaSuccess)) {
             vt_set_error("vt_quantize_host: staging allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
             cleanup();
             return VT_ENOMEM;
@@ -148,8 +156,12 @@ extern "C" int vt_quantize_host(const void *h_desc, int dtype, int64_t n, int dp
             rc = VT_ECUDA;
             break;
         }
-        rc = vt_quantize_dispatch(dbuf[s], dtype, rows, dp, d_centroids, d_internal, d_ref_id, k, depth, 0, nullptr,
-                                  wbuf[s], nullptr, st[s]);
+        if (sorted && rows >= ((int64_t)1 << 16))
+            rc = vt_quantize_sorted_impl(dbuf[s], rows, dp, d_centroids, d_internal, d_ref_id, k, depth, nullptr, wbuf[s],
+                                         nullptr, work[s], st[s], nullptr);
+        else
+            rc = vt_quantize_dispatch(dbuf[s], dtype, rows, dp, d_centroids, d_internal, d_ref_id, k, depth, 0, nullptr,
+                                      wbuf[s], nullptr, st[s]);
         if (rc != VT_OK) break;
         if (cudaMemcpyAsync(h_word + done, wbuf[s], (size_t)rows * sizeof(int32_t), cudaMemcpyDeviceToHost, st[s]) !=
             cudaSuccess) {

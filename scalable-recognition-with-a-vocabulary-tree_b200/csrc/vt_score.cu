@@ -197,6 +197,7 @@ topk_merge_kernel(const double *__restrict__ in_key, const int32_t *__restrict__
                             if (q_sumsq && img_sumsq && img_sumsq[id] == q_sumsq[q] && key >= 1.0 - 4e-6) s = 0.0;
                         } else {
                             s = fmax(0.0, 2.0 - key);
+                            if (q_sumsq && img_sumsq && img_sumsq[id] == q_sumsq[q] && key >= 2.0 - 8e-6) s = 0.0;
                         }
                     }
                     out_score[q * topk + r] = s;

@@ -139,8 +139,8 @@ extern "C" int64_t vt_sort_scratch_bytes(int64_t n)
     return (256 * (nblocks > 0 ? nblocks : 1) + 256) * (int64_t)sizeof(uint32_t);
 }
 
-extern "C" int vt_sort_pairs(uint32_t *d_keys, uint32_t *d_vals, uint32_t *d_tmp_keys, uint32_t *d_tmp_vals, int64_t n,
-                             int n_bits, void *d_hist, int *result_in_tmp, void *stream)
+int vt_sort_pairs_impl(uint32_t *d_keys, uint32_t *d_vals, uint32_t *d_tmp_keys, uint32_t *d_tmp_vals, int64_t n,
+                       int n_bits, void *d_hist, int *result_in_tmp, cudaStream_t s)
 {
     VT_CHECK_ARG(n >= 0 && n < ((int64_t)1 << 31), "n must be below 2^31");
     VT_CHECK_ARG(n_bits >= 0 && n_bits <= 32, "n_bits out of range");
@@ -148,7 +148,6 @@ extern "C" int vt_sort_pairs(uint32_t *d_keys, uint32_t *d_vals, uint32_t *d_tmp
     *result_in_tmp = 0;
     if (n == 0 || n_bits == 0) return VT_OK;
     VT_CHECK_ARG(d_keys && d_vals && d_tmp_keys && d_tmp_vals && d_hist, "null buffer");
-    cudaStream_t s = (cudaStream_t)stream;
     const int nblocks = (int)((n + SORT_TILE - 1) / SORT_TILE);
     uint32_t *hist = (uint32_t *)d_hist;
     uint32_t *digit_total = hist + (size_t)256 * nblocks;
@@ -168,4 +167,11 @@ extern "C" int vt_sort_pairs(uint32_t *d_keys, uint32_t *d_vals, uint32_t *d_tmp
     }
     *result_in_tmp = flips & 1;
     return VT_OK;
+}
+
+extern "C" int vt_sort_pairs(uint32_t *d_keys, uint32_t *d_vals, uint32_t *d_tmp_keys, uint32_t *d_tmp_vals, int64_t n,
+                             int n_bits, void *d_hist, int *result_in_tmp, void *stream)
+{
+    return vt_sort_pairs_impl(d_keys, d_vals, d_tmp_keys, d_tmp_vals, n, n_bits, d_hist, result_in_tmp,
+                              (cudaStream_t)stream);
 }

@@ -77,17 +77,35 @@ def stage(x, device="cuda", prefer_bytes: bool = True):
 
 
 # --------------------------------------------------------------------------------------- descent
+SORTED_MIN_ROWS = 1 << 18      # below this the fused single-launch descent wins (launch count, short segments)
+
+
 def quantize(tree_dev: dict, k: int, depth: int, desc: torch.Tensor, want_heap: bool = False,
-             stats: torch.Tensor = None, start: int = 0):
+             stats: torch.Tensor = None, start: int = 0, method: str = "auto", work: torch.Tensor = None):
     """Reference node id of the stop node of every descriptor (int32 [n]); optionally also the
-    heap index.  ``stats`` (int64 [4], zeroed by the caller) receives the binary64 recheck count."""
+    heap index.  ``stats`` (int64 [4], zeroed by the caller) receives the binary64 recheck count.
+
+    ``method``: "fused" = one launch, warp-per-descriptor descent (any dtype, any start node);
+    "sorted" = level-synchronous descent over the batch sorted by node (bytes, large batches);
+    "auto" picks by batch size.  Both return identical ids."""
     lib = _lib()
     n, dp = desc.shape
     word = torch.empty(n, dtype=torch.int32, device=desc.device)
     leaf = torch.empty(n, dtype=torch.int32, device=desc.device) if want_heap else None
-    nat.check(lib.vt_quantize(nat.ptr(desc), _dtype_code(desc), n, dp, nat.ptr(tree_dev["centroids"]),
-                              nat.ptr(tree_dev["internal"]), nat.ptr(tree_dev["ref_id"]), k, depth, start,
-                              nat.ptr(leaf), nat.ptr(word), nat.ptr(stats), nat.stream_ptr()), "vt_quantize")
+    if method == "auto":
+        method = "sorted" if (desc.dtype == torch.uint8 and start == 0 and n >= SORTED_MIN_ROWS and depth >= 2) else "fused"
+    if method == "sorted":
+        need = int(lib.vt_quantize_sorted_work_bytes(n))
+        if work is None or work.numel() * work.element_size() < need:
+            work = torch.empty(need, dtype=torch.uint8, device=desc.device)
+        nat.check(lib.vt_quantize_sorted(nat.ptr(desc), _dtype_code(desc), n, dp, nat.ptr(tree_dev["centroids"]),
+                                         nat.ptr(tree_dev["internal"]), nat.ptr(tree_dev["ref_id"]), k, depth,
+                                         nat.ptr(leaf), nat.ptr(word), nat.ptr(stats), nat.ptr(work),
+                                         work.numel() * work.element_size(), nat.stream_ptr()), "vt_quantize_sorted")
+    else:
+        nat.check(lib.vt_quantize(nat.ptr(desc), _dtype_code(desc), n, dp, nat.ptr(tree_dev["centroids"]),
+                                  nat.ptr(tree_dev["internal"]), nat.ptr(tree_dev["ref_id"]), k, depth, start,
+                                  nat.ptr(leaf), nat.ptr(word), nat.ptr(stats), nat.stream_ptr()), "vt_quantize")
     return (word, leaf) if want_heap else word
 
 

@@ -52,10 +52,15 @@ def test_quantize_matches_oracle_and_reference(vt, cuda, name, as_float):
     desc, d = vt.engine.stage(x.astype(np.float32) if as_float else x, cuda, prefer_bytes=not as_float)
     assert desc.dtype == (torch.float32 if as_float else torch.uint8)
     stats = torch.zeros(4, dtype=torch.int64, device=cuda)
-    word, heap = vt.engine.quantize(ft.device(cuda), ft.k, ft.depth, desc, want_heap=True, stats=stats)
+    word, heap = vt.engine.quantize(ft.device(cuda), ft.k, ft.depth, desc, want_heap=True, stats=stats, method="fused")
     heap, word = heap.cpu().numpy(), word.cpu().numpy()
     assert np.array_equal(heap, want_heap), "%d rows differ from the binary64 oracle" % (heap != want_heap).sum()
     assert np.array_equal(word, ft.ref_id[want_heap])
+    if not as_float:                                             # level-synchronous sorted path: same ids
+        st2 = torch.zeros(4, dtype=torch.int64, device=cuda)
+        w2, h2 = vt.engine.quantize(ft.device(cuda), ft.k, ft.depth, desc, want_heap=True, stats=st2, method="sorted")
+        assert np.array_equal(h2.cpu().numpy(), want_heap) and np.array_equal(w2.cpu().numpy(), word)
+        assert int(st2[0].item()) == int(stats[0].item())
     # against the reference's own float32 propagate_feature: only near-ties may differ
     ref_leaf = g["ref_leaf"].astype(np.int32)[:len(x)]
     mism = np.nonzero(word != ref_leaf)[0]
@@ -99,10 +104,16 @@ def test_quantize_random_trees(vt, cuda, k, depth, d, tie_heavy):
         exp = want if arr.dtype == np.uint8 or tie_heavy else vo.descend(oracle_tree_from_flat(ft), arr)
         desc, _ = vt.engine.stage(arr, cuda)
         stats = torch.zeros(4, dtype=torch.int64, device=cuda)
-        _, heap = vt.engine.quantize(ft.device(cuda), k, depth, desc, want_heap=True, stats=stats)
+        _, heap = vt.engine.quantize(ft.device(cuda), k, depth, desc, want_heap=True, stats=stats, method="fused")
         assert np.array_equal(heap.cpu().numpy(), exp)
         if tie_heavy and k > 1:
             assert int(stats[0].item()) > 0            # the binary64 path really ran
+        if desc.dtype == torch.uint8:
+            st2 = torch.zeros(4, dtype=torch.int64, device=cuda)
+            w2, h2 = vt.engine.quantize(ft.device(cuda), k, depth, desc, want_heap=True, stats=st2, method="sorted")
+            assert np.array_equal(h2.cpu().numpy(), exp)
+            assert np.array_equal(w2.cpu().numpy(), ft.ref_id[exp])
+            assert int(st2[0].item()) == int(stats[0].item())
     if tie_heavy and k > 1:
         assert (gap == 0).any()                        # exact ties were present (first child must win)
 
