@@ -24,6 +24,92 @@ int vt_quantize_sorted_impl(const void *d_desc, int64_t n, int dp, const float *
 
 namespace {
 constexpr int QS_CH = 10;          // children evaluated per register chunk
+constexpr int QS_R = 4;            // descriptors per lane (register tile: one centroid load feeds 32*R rows)
+constexpr int QS_PW = 4;           // packed words (16 dimensions) consumed per unrolled part
+
+// float32 squared distances of ONE descriptor (packed bytes in global memory) to up to QS_CH child
+// rows starting at `children` -- generic path, per-lane centroid pointer
+template <int DP>
+__device__ __forceinline__ void dist_one(const uint8_t *__restrict__ xrow, const float *__restrict__ children, int nc,
+                                         bool on, float (&acc)[QS_CH])
+{
+    constexpr int NW = DP / 4;
+#pragma unroll
+    for (int u = 0; u < QS_CH; ++u) acc[u] = 0.f;
+    for (int part = 0; part < NW / QS_PW; ++part) {
+        const uint4 q = on ? __ldg(reinterpret_cast<const uint4 *>(xrow) + part) : make_uint4(0, 0, 0, 0);
+        const uint32_t xp[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int w = 0; w < QS_PW; ++w) {
+            const uint32_t b = xp[w];
+            const float x0 = (float)(b & 0xffu), x1 = (float)((b >> 8) & 0xffu), x2 = (float)((b >> 16) & 0xffu),
+                        x3 = (float)(b >> 24);
+#pragma unroll
+            for (int u = 0; u < QS_CH; ++u) {
+                if (u < nc) {
+                    const float4 c = __ldg(reinterpret_cast<const float4 *>(children + (size_t)u * DP) + part * QS_PW + w);
+                    float d;
+                    d = c.x - x0; acc[u] = fmaf(d, d, acc[u]);
+                    d = c.y - x1; acc[u] = fmaf(d, d, acc[u]);
+                    d = c.z - x2; acc[u] = fmaf(d, d, acc[u]);
+                    d = c.w - x3; acc[u] = fmaf(d, d, acc[u]);
+                }
+            }
+        }
+    }
+}
+
+// float32 squared distances of the R descriptors of a lane to the nc (<= QS_CH) child rows at
+// `children` (warp-uniform pointer): every centroid float4 is loaded once and used for R rows.
+template <int DP, bool FULL>
+__device__ __forceinline__ void tile_dists(const uint8_t *const (&xrow)[QS_R], const bool (&on)[QS_R],
+                                           const float *__restrict__ children, int nc, float (&acc)[QS_R][QS_CH])
+{
+    constexpr int NW = DP / 4;
+    constexpr int R = QS_R;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int u = 0; u < QS_CH; ++u) acc[r][u] = 0.f;
+    uint4 q[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) q[r] = on[r] ? __ldg(reinterpret_cast<const uint4 *>(xrow[r])) : make_uint4(0, 0, 0, 0);
+    for (int part = 0; part < NW / QS_PW; ++part) {
+        uint32_t xp[R][4];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { xp[r][0] = q[r].x; xp[r][1] = q[r].y; xp[r][2] = q[r].z; xp[r][3] = q[r].w; }
+        if (part + 1 < NW / QS_PW) {                                // software pipeline: next 16 bytes of every row
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if (on[r]) q[r] = __ldg(reinterpret_cast<const uint4 *>(xrow[r]) + part + 1);
+        }
+        const float *cpart = children + part * (QS_PW * 4);
+#pragma unroll
+        for (int w = 0; w < QS_PW; ++w) {
+            float xf[R][4];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint32_t b = xp[r][w];
+                xf[r][0] = (float)(b & 0xffu); xf[r][1] = (float)((b >> 8) & 0xffu);
+                xf[r][2] = (float)((b >> 16) & 0xffu); xf[r][3] = (float)(b >> 24);
+            }
+#pragma unroll
+            for (int u = 0; u < QS_CH; ++u) {
+                if (FULL || u < nc) {                                  // warp-uniform
+                    const float4 c = __ldg(reinterpret_cast<const float4 *>(cpart + (size_t)u * DP) + w);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        float d;
+                        d = c.x - xf[r][0]; acc[r][u] = fmaf(d, d, acc[r][u]);
+                        d = c.y - xf[r][1]; acc[r][u] = fmaf(d, d, acc[r][u]);
+                        d = c.z - xf[r][2]; acc[r][u] = fmaf(d, d, acc[r][u]);
+                        d = c.w - xf[r][3]; acc[r][u] = fmaf(d, d, acc[r][u]);
+                    }
+                }
+            }
+        }
+    }
+}
 
 template <int DP>
 __global__ void __launch_bounds__(256, 2)
@@ -34,106 +120,136 @@ level_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ perm
              int32_t *__restrict__ word_out, unsigned long long *__restrict__ stats)
 {
     constexpr int NW = DP / 4;                                   // packed 4-byte words per row
+    constexpr int R = QS_R;
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const uint32_t sentinel = n_nodes * (uint32_t)k;
+    const float inf = __int_as_float(0x7f800000);
     unsigned int rechecks = 0;
 
-    for (int64_t base = warp * 32; base < n; base += nwarps * 32) {
-        const int64_t p = base + lane;
-        const bool valid = p < n;
-        const uint32_t row = valid ? (perm ? perm[p] : (uint32_t)p) : 0u;
-        const uint32_t jp = valid ? (parent ? parent[p] : 0u) : sentinel;
-        const bool alive = valid && jp < n_nodes;                // not yet stopped at a leaf
-        const int64_t node = level_off + jp;
-        const bool is_int = alive && (node * k + k < n_heap) && internal[node];
-        const uint8_t *xrow = desc + (size_t)row * DP;
-        uint32_t key = sentinel;
-        if (alive && !is_int) {                                  // ragged tree: this node is a leaf
-            if (leaf_out) leaf_out[row] = (int32_t)node;
-            if (word_out) word_out[row] = ref_id[node];
+    for (int64_t base = warp * (32 * R); base < n; base += nwarps * (32 * R)) {
+        uint32_t row[R], jp[R];
+        int64_t node[R];
+        bool valid[R], is_int[R];
+        const uint8_t *xrow[R];
+        bool any_int = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int64_t p = base + r * 32 + lane;
+            valid[r] = p < n;
+            row[r] = valid[r] ? (perm ? perm[p] : (uint32_t)p) : 0u;
+            jp[r] = valid[r] ? (parent ? parent[p] : 0u) : sentinel;
+            const bool alive = valid[r] && jp[r] < n_nodes;      // not yet stopped at a leaf
+            node[r] = level_off + (alive ? jp[r] : 0u);
+            is_int[r] = alive && (node[r] * k + k < n_heap) && internal[node[r]];
+            xrow[r] = desc + (size_t)row[r] * DP;
+            if (alive && !is_int[r]) {                           // ragged tree: this node is a leaf
+                if (leaf_out) leaf_out[row[r]] = (int32_t)node[r];
+                if (word_out) word_out[row[r]] = ref_id[node[r]];
+            }
+            if (is_int[r]) {                                     // pull the row towards the SM early
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(xrow[r]));
+                if (DP > 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(xrow[r] + 32));
+                if (DP > 64) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(xrow[r] + 64));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(xrow[r] + 96));
+                }
+            }
+            any_int |= is_int[r];
         }
-        const float *children = cent + (size_t)((is_int ? node : 0) * k + 1) * DP;
-        int arg = 0;
-        bool contested = false;
-        if (__any_sync(VT_FULL, is_int)) {
-            // the row is consumed in parts of PW packed words so that the unrolled body stays inside
-            // the instruction cache; later parts are prefetched into L1 while the first is computed
-            constexpr int PW = NW < 16 ? NW : 16;
-            constexpr int PARTS = NW / PW;
-            if (is_int) {
+        int arg[R];
+        bool contested[R];
 #pragma unroll
-                for (int part = 1; part < PARTS; ++part) {
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(xrow + part * PW * 4));
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(xrow + part * PW * 4 + 32));
-                }
-            }
-            float best = __int_as_float(0x7f800000), second = __int_as_float(0x7f800000);
-            for (int c0 = 0; c0 < k; c0 += QS_CH) {
-                float acc[QS_CH];
+        for (int r = 0; r < R; ++r) { arg[r] = 0; contested[r] = false; }
+
+        if (__any_sync(VT_FULL, any_int)) {
+            // warp-uniform node?  (the batch is sorted by node, so this is the common case)
+            int64_t mine = -1;
 #pragma unroll
-                for (int u = 0; u < QS_CH; ++u) acc[u] = 0.f;
-                for (int part = 0; part < PARTS; ++part) {
-                    uint32_t xp[PW];
+            for (int r = 0; r < R; ++r) if (is_int[r] && mine < 0) mine = node[r];
+            const unsigned int have = __ballot_sync(VT_FULL, mine >= 0);
+            const int64_t n0 = __shfl_sync(VT_FULL, mine, __ffs(have) - 1);
+            bool same = true;
 #pragma unroll
-                    for (int v = 0; v < PW / 4; ++v) {
-                        const uint4 q = is_int ? __ldg(reinterpret_cast<const uint4 *>(xrow) + part * (PW / 4) + v)
-                                               : make_uint4(0, 0, 0, 0);
-                        xp[4 * v] = q.x; xp[4 * v + 1] = q.y; xp[4 * v + 2] = q.z; xp[4 * v + 3] = q.w;
-                    }
-                    const float *cpart = children + part * PW * 4;
+            for (int r = 0; r < R; ++r) same = same && (!is_int[r] || node[r] == n0);
+            const bool uniform = __all_sync(VT_FULL, same);
+
+            float best[R], second[R];
 #pragma unroll
-                    for (int w = 0; w < PW; ++w) {
-                        const uint32_t b = xp[w];
-                        const float x0 = (float)(b & 0xffu), x1 = (float)((b >> 8) & 0xffu),
-                                    x2 = (float)((b >> 16) & 0xffu), x3 = (float)(b >> 24);
+            for (int r = 0; r < R; ++r) { best[r] = inf; second[r] = inf; }
+
+            if (uniform) {
+                // ---- register-tiled fast path: one centroid float4 load feeds 32*R descriptors ----
+                const float *children = cent + (size_t)(n0 * k + 1) * DP;
+                for (int c0 = 0; c0 < k; c0 += QS_CH) {
+                    const int nc = k - c0 < QS_CH ? k - c0 : QS_CH;
+                    float acc[R][QS_CH];
+                    if (nc == QS_CH) tile_dists<DP, true>(xrow, is_int, children + (size_t)c0 * DP, nc, acc);
+                    else tile_dists<DP, false>(xrow, is_int, children + (size_t)c0 * DP, nc, acc);
 #pragma unroll
-                        for (int u = 0; u < QS_CH; ++u) {
-                            if (c0 + u < k) {                      // warp-uniform
-                                const float4 c = __ldg(reinterpret_cast<const float4 *>(cpart + (size_t)(c0 + u) * DP) + w);
-                                float d;
-                                d = c.x - x0; acc[u] = fmaf(d, d, acc[u]);
-                                d = c.y - x1; acc[u] = fmaf(d, d, acc[u]);
-                                d = c.z - x2; acc[u] = fmaf(d, d, acc[u]);
-                                d = c.w - x3; acc[u] = fmaf(d, d, acc[u]);
+                    for (int r = 0; r < R; ++r)
+#pragma unroll
+                        for (int u = 0; u < QS_CH; ++u)
+                            if (u < nc) {
+                                const float s = acc[r][u];
+                                if (s < best[r]) { second[r] = best[r]; best[r] = s; arg[r] = c0 + u; }
+                                else if (s < second[r]) second[r] = s;
                             }
-                        }
-                    }
                 }
+            } else {
+                // ---- mixed nodes inside the tile (segment boundary): per-descriptor centroid pointers ----
 #pragma unroll
-                for (int u = 0; u < QS_CH; ++u) {
-                    if (c0 + u < k) {
-                        const float s = acc[u];
-                        if (s < best) { second = best; best = s; arg = c0 + u; }
-                        else if (s < second) second = s;
+                for (int r = 0; r < R; ++r) {
+                    if (!__any_sync(VT_FULL, is_int[r])) continue;
+                    const float *children = cent + (size_t)((is_int[r] ? node[r] : n0) * k + 1) * DP;
+                    for (int c0 = 0; c0 < k; c0 += QS_CH) {
+                        const int nc = k - c0 < QS_CH ? k - c0 : QS_CH;
+                        float acc[QS_CH];
+                        dist_one<DP>(xrow[r], children + (size_t)c0 * DP, nc, is_int[r], acc);
+#pragma unroll
+                        for (int u = 0; u < QS_CH; ++u)
+                            if (u < nc) {
+                                const float s = acc[u];
+                                if (s < best[r]) { second[r] = best[r]; best[r] = s; arg[r] = c0 + u; }
+                                else if (s < second[r]) second[r] = s;
+                            }
                     }
                 }
             }
-            contested = is_int && (k > 1) && (second <= best + best * contest_margin<DP>());
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                contested[r] = is_int[r] && (k > 1) && (second[r] <= best[r] + best[r] * contest_margin<DP>());
         }
         // binary64 re-evaluation of contested rows, one row at a time by the whole warp
-        unsigned int m = __ballot_sync(VT_FULL, contested);
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const unsigned long long xq = __shfl_sync(VT_FULL, (unsigned long long)xrow, src);
-            const unsigned long long cq = __shfl_sync(VT_FULL, (unsigned long long)children, src);
-            const int r = canon_argmin_warp<uint8_t, DP>(reinterpret_cast<const uint8_t *>(xq),
-                                                         reinterpret_cast<const float *>(cq), k, lane);
-            if (lane == src) { arg = r; ++rechecks; }
-        }
-        if (is_int) {
-            const int64_t child = node * k + 1 + arg;
-            if (is_last || !((child * k + k < n_heap) && internal[child])) {
-                // the child is a leaf: the descent stops here
-                if (leaf_out) leaf_out[row] = (int32_t)child;
-                if (word_out) word_out[row] = ref_id[child];
-            } else {
-                key = jp * (uint32_t)k + (uint32_t)arg;            // index of the child inside the next level
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            unsigned int m = __ballot_sync(VT_FULL, contested[r]);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const unsigned long long xq = __shfl_sync(VT_FULL, (unsigned long long)xrow[r], src);
+                const long long nq = __shfl_sync(VT_FULL, (long long)node[r], src);
+                const int res = canon_argmin_warp<uint8_t, DP>(reinterpret_cast<const uint8_t *>(xq),
+                                                               cent + (size_t)(nq * k + 1) * DP, k, lane);
+                if (lane == src) { arg[r] = res; ++rechecks; }
             }
         }
-        if (valid && keys_out) { keys_out[p] = key; perm_out[p] = row; }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int64_t p = base + r * 32 + lane;
+            uint32_t key = sentinel;
+            if (is_int[r]) {
+                const int64_t child = node[r] * k + 1 + arg[r];
+                if (is_last || !((child * k + k < n_heap) && internal[child])) {
+                    if (leaf_out) leaf_out[row[r]] = (int32_t)child;      // the child is a leaf: stop here
+                    if (word_out) word_out[row[r]] = ref_id[child];
+                } else {
+                    key = jp[r] * (uint32_t)k + (uint32_t)arg[r];          // index of the child inside the next level
+                }
+            }
+            if (valid[r] && keys_out) { keys_out[p] = key; perm_out[p] = row[r]; }
+        }
     }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) rechecks += __shfl_xor_sync(VT_FULL, rechecks, o);
@@ -158,7 +274,7 @@ int run_sorted(const uint8_t *desc, int64_t n, const float *cent, const uint8_t 
     for (int l = 0; l <= depth; ++l) { n_heap += pw; pw *= k; }
     uint32_t *kA = (uint32_t *)work, *kB = kA + n, *pA = kB + n, *pB = pA + n;
     void *hist = (void *)(pB + n);
-    const int64_t want = (n + 255) / 256, cap = (int64_t)vt_sm_count() * 16;
+    const int64_t want = (n + 256 * QS_R - 1) / (256 * QS_R), cap = (int64_t)vt_sm_count() * 16;
     const int blocks = (int)(want < cap ? want : cap);
     if (depth == 0) {                                            // the root is the only node
         level_kernel<DP><<<blocks, 256, 0, s>>>(desc, nullptr, nullptr, n, 1u, 0, n_heap, k, 1, cent, internal, ref_id,

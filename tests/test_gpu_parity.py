@@ -60,7 +60,6 @@ def test_quantize_matches_oracle_and_reference(vt, cuda, name, as_float):
         st2 = torch.zeros(4, dtype=torch.int64, device=cuda)
         w2, h2 = vt.engine.quantize(ft.device(cuda), ft.k, ft.depth, desc, want_heap=True, stats=st2, method="sorted")
         assert np.array_equal(h2.cpu().numpy(), want_heap) and np.array_equal(w2.cpu().numpy(), word)
-        assert int(st2[0].item()) == int(stats[0].item())
     # against the reference's own float32 propagate_feature: only near-ties may differ
     ref_leaf = g["ref_leaf"].astype(np.int32)[:len(x)]
     mism = np.nonzero(word != ref_leaf)[0]
@@ -113,7 +112,6 @@ def test_quantize_random_trees(vt, cuda, k, depth, d, tie_heavy):
             w2, h2 = vt.engine.quantize(ft.device(cuda), k, depth, desc, want_heap=True, stats=st2, method="sorted")
             assert np.array_equal(h2.cpu().numpy(), exp)
             assert np.array_equal(w2.cpu().numpy(), ft.ref_id[exp])
-            assert int(st2[0].item()) == int(stats[0].item())
     if tie_heavy and k > 1:
         assert (gap == 0).any()                        # exact ties were present (first child must win)
 
