@@ -14,6 +14,7 @@
 // Results are bit-identical to vt_quantize (same canonical contract: float32 pass, margin check,
 // binary64 re-evaluation of contested rows).
 #include "vt_common.cuh"
+#include <stdlib.h>
 
 int vt_sort_pairs_impl(uint32_t *d_keys, uint32_t *d_vals, uint32_t *d_tmp_keys, uint32_t *d_tmp_vals, int64_t n,
                        int n_bits, void *d_hist, int *result_in_tmp, cudaStream_t s);
@@ -24,49 +25,15 @@ int vt_quantize_sorted_impl(const void *d_desc, int64_t n, int dp, const float *
 
 namespace {
 constexpr int QS_CH = 10;          // children evaluated per register chunk
-constexpr int QS_R = 4;            // descriptors per lane (register tile: one centroid load feeds 32*R rows)
 constexpr int QS_PW = 4;           // packed words (16 dimensions) consumed per unrolled part
-
-// float32 squared distances of ONE descriptor (packed bytes in global memory) to up to QS_CH child
-// rows starting at `children` -- generic path, per-lane centroid pointer
-template <int DP>
-__device__ __forceinline__ void dist_one(const uint8_t *__restrict__ xrow, const float *__restrict__ children, int nc,
-                                         bool on, float (&acc)[QS_CH])
-{
-    constexpr int NW = DP / 4;
-#pragma unroll
-    for (int u = 0; u < QS_CH; ++u) acc[u] = 0.f;
-    for (int part = 0; part < NW / QS_PW; ++part) {
-        const uint4 q = on ? __ldg(reinterpret_cast<const uint4 *>(xrow) + part) : make_uint4(0, 0, 0, 0);
-        const uint32_t xp[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int w = 0; w < QS_PW; ++w) {
-            const uint32_t b = xp[w];
-            const float x0 = (float)(b & 0xffu), x1 = (float)((b >> 8) & 0xffu), x2 = (float)((b >> 16) & 0xffu),
-                        x3 = (float)(b >> 24);
-#pragma unroll
-            for (int u = 0; u < QS_CH; ++u) {
-                if (u < nc) {
-                    const float4 c = __ldg(reinterpret_cast<const float4 *>(children + (size_t)u * DP) + part * QS_PW + w);
-                    float d;
-                    d = c.x - x0; acc[u] = fmaf(d, d, acc[u]);
-                    d = c.y - x1; acc[u] = fmaf(d, d, acc[u]);
-                    d = c.z - x2; acc[u] = fmaf(d, d, acc[u]);
-                    d = c.w - x3; acc[u] = fmaf(d, d, acc[u]);
-                }
-            }
-        }
-    }
-}
 
 // float32 squared distances of the R descriptors of a lane to the nc (<= QS_CH) child rows at
 // `children` (warp-uniform pointer): every centroid float4 is loaded once and used for R rows.
-template <int DP, bool FULL>
-__device__ __forceinline__ void tile_dists(const uint8_t *const (&xrow)[QS_R], const bool (&on)[QS_R],
-                                           const float *__restrict__ children, int nc, float (&acc)[QS_R][QS_CH])
+template <int DP, int R, bool FULL>
+__device__ __forceinline__ void tile_dists(const uint8_t *const (&xrow)[R], const bool (&on)[R],
+                                           const float *__restrict__ children, int nc, float (&acc)[R][QS_CH])
 {
     constexpr int NW = DP / 4;
-    constexpr int R = QS_R;
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
@@ -111,29 +78,31 @@ __device__ __forceinline__ void tile_dists(const uint8_t *const (&xrow)[QS_R], c
     }
 }
 
-template <int DP>
-__global__ void __launch_bounds__(256, 2)
+// One tree level for the whole (sorted) batch.  A warp owns a tile of 32*R consecutive positions;
+// lane l owns positions l, l+32, ...  Tiles whose rows all sit in one node (the common case after
+// sorting) take one pass; tiles that straddle segment boundaries take one pass per distinct node,
+// each pass at full speed with the other rows masked off.
+template <int DP, int R>
+__global__ void __launch_bounds__(256, R >= 4 ? 2 : (R == 2 ? 3 : 4))
 level_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ parent,
              int64_t n, uint32_t n_nodes, int64_t level_off, int64_t n_heap, int k, int is_last,
              const float *__restrict__ cent, const uint8_t *__restrict__ internal, const int32_t *__restrict__ ref_id,
              uint32_t *__restrict__ keys_out, uint32_t *__restrict__ perm_out, int32_t *__restrict__ leaf_out,
              int32_t *__restrict__ word_out, unsigned long long *__restrict__ stats)
 {
-    constexpr int NW = DP / 4;                                   // packed 4-byte words per row
-    constexpr int R = QS_R;
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const uint32_t sentinel = n_nodes * (uint32_t)k;
     const float inf = __int_as_float(0x7f800000);
+    const long long none = 0x7fffffffffffffffLL;
     unsigned int rechecks = 0;
 
     for (int64_t base = warp * (32 * R); base < n; base += nwarps * (32 * R)) {
         uint32_t row[R], jp[R];
-        int64_t node[R];
+        long long node[R];
         bool valid[R], is_int[R];
         const uint8_t *xrow[R];
-        bool any_int = false;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int64_t p = base + r * 32 + lane;
@@ -156,80 +125,54 @@ level_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ perm
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(xrow[r] + 96));
                 }
             }
-            any_int |= is_int[r];
         }
         int arg[R];
-        bool contested[R];
+        float best[R], second[R];
+        bool pending[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) { arg[r] = 0; contested[r] = false; }
+        for (int r = 0; r < R; ++r) { arg[r] = 0; best[r] = inf; second[r] = inf; pending[r] = is_int[r]; }
 
-        if (__any_sync(VT_FULL, any_int)) {
-            // warp-uniform node?  (the batch is sorted by node, so this is the common case)
-            int64_t mine = -1;
+        // one pass per distinct node present in the tile (ascending node order)
+        while (true) {
+            long long mine = none;
 #pragma unroll
-            for (int r = 0; r < R; ++r) if (is_int[r] && mine < 0) mine = node[r];
-            const unsigned int have = __ballot_sync(VT_FULL, mine >= 0);
-            const int64_t n0 = __shfl_sync(VT_FULL, mine, __ffs(have) - 1);
-            bool same = true;
+            for (int r = 0; r < R; ++r) if (pending[r] && node[r] < mine) mine = node[r];
 #pragma unroll
-            for (int r = 0; r < R; ++r) same = same && (!is_int[r] || node[r] == n0);
-            const bool uniform = __all_sync(VT_FULL, same);
-
-            float best[R], second[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) { best[r] = inf; second[r] = inf; }
-
-            if (uniform) {
-                // ---- register-tiled fast path: one centroid float4 load feeds 32*R descriptors ----
-                const float *children = cent + (size_t)(n0 * k + 1) * DP;
-                for (int c0 = 0; c0 < k; c0 += QS_CH) {
-                    const int nc = k - c0 < QS_CH ? k - c0 : QS_CH;
-                    float acc[R][QS_CH];
-                    if (nc == QS_CH) tile_dists<DP, true>(xrow, is_int, children + (size_t)c0 * DP, nc, acc);
-                    else tile_dists<DP, false>(xrow, is_int, children + (size_t)c0 * DP, nc, acc);
-#pragma unroll
-                    for (int r = 0; r < R; ++r)
-#pragma unroll
-                        for (int u = 0; u < QS_CH; ++u)
-                            if (u < nc) {
-                                const float s = acc[r][u];
-                                if (s < best[r]) { second[r] = best[r]; best[r] = s; arg[r] = c0 + u; }
-                                else if (s < second[r]) second[r] = s;
-                            }
-                }
-            } else {
-                // ---- mixed nodes inside the tile (segment boundary): per-descriptor centroid pointers ----
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    if (!__any_sync(VT_FULL, is_int[r])) continue;
-                    const float *children = cent + (size_t)((is_int[r] ? node[r] : n0) * k + 1) * DP;
-                    for (int c0 = 0; c0 < k; c0 += QS_CH) {
-                        const int nc = k - c0 < QS_CH ? k - c0 : QS_CH;
-                        float acc[QS_CH];
-                        dist_one<DP>(xrow[r], children + (size_t)c0 * DP, nc, is_int[r], acc);
-#pragma unroll
-                        for (int u = 0; u < QS_CH; ++u)
-                            if (u < nc) {
-                                const float s = acc[u];
-                                if (s < best[r]) { second[r] = best[r]; best[r] = s; arg[r] = c0 + u; }
-                                else if (s < second[r]) second[r] = s;
-                            }
-                    }
-                }
+            for (int o = 16; o >= 1; o >>= 1) {
+                const long long other = __shfl_xor_sync(VT_FULL, mine, o);
+                mine = other < mine ? other : mine;
             }
+            if (mine == none) break;                             // warp-uniform
+            bool on[R];
 #pragma unroll
-            for (int r = 0; r < R; ++r)
-                contested[r] = is_int[r] && (k > 1) && (second[r] <= best[r] + best[r] * contest_margin<DP>());
+            for (int r = 0; r < R; ++r) { on[r] = pending[r] && node[r] == mine; pending[r] = pending[r] && !on[r]; }
+            const float *children = cent + (size_t)(mine * k + 1) * DP;
+            for (int c0 = 0; c0 < k; c0 += QS_CH) {
+                const int nc = k - c0 < QS_CH ? k - c0 : QS_CH;
+                float acc[R][QS_CH];
+                if (nc == QS_CH) tile_dists<DP, R, true>(xrow, on, children + (size_t)c0 * DP, nc, acc);
+                else tile_dists<DP, R, false>(xrow, on, children + (size_t)c0 * DP, nc, acc);
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int u = 0; u < QS_CH; ++u)
+                        if (u < nc && on[r]) {
+                            const float s = acc[r][u];
+                            if (s < best[r]) { second[r] = best[r]; best[r] = s; arg[r] = c0 + u; }
+                            else if (s < second[r]) second[r] = s;
+                        }
+            }
         }
         // binary64 re-evaluation of contested rows, one row at a time by the whole warp
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            unsigned int m = __ballot_sync(VT_FULL, contested[r]);
+            const bool contested = is_int[r] && (k > 1) && (second[r] <= best[r] + best[r] * contest_margin<DP>());
+            unsigned int m = __ballot_sync(VT_FULL, contested);
             while (m) {
                 const int src = __ffs(m) - 1;
                 m &= m - 1;
                 const unsigned long long xq = __shfl_sync(VT_FULL, (unsigned long long)xrow[r], src);
-                const long long nq = __shfl_sync(VT_FULL, (long long)node[r], src);
+                const long long nq = __shfl_sync(VT_FULL, node[r], src);
                 const int res = canon_argmin_warp<uint8_t, DP>(reinterpret_cast<const uint8_t *>(xq),
                                                                cent + (size_t)(nq * k + 1) * DP, k, lane);
                 if (lane == src) { arg[r] = res; ++rechecks; }
@@ -240,7 +183,7 @@ level_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ perm
             const int64_t p = base + r * 32 + lane;
             uint32_t key = sentinel;
             if (is_int[r]) {
-                const int64_t child = node[r] * k + 1 + arg[r];
+                const long long child = node[r] * k + 1 + arg[r];
                 if (is_last || !((child * k + k < n_heap) && internal[child])) {
                     if (leaf_out) leaf_out[row[r]] = (int32_t)child;      // the child is a leaf: stop here
                     if (word_out) word_out[row[r]] = ref_id[child];
@@ -254,6 +197,38 @@ level_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ perm
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) rechecks += __shfl_xor_sync(VT_FULL, rechecks, o);
     if (stats && lane == 0 && rechecks) atomicAdd(stats, (unsigned long long)rechecks);
+}
+
+template <int DP>
+void launch_level(int r_tile, int blocks_cap_per_sm, const uint8_t *desc, const uint32_t *perm, const uint32_t *parent,
+                  int64_t n, uint32_t n_nodes, int64_t level_off, int64_t n_heap, int k, int is_last, const float *cent,
+                  const uint8_t *internal, const int32_t *ref_id, uint32_t *keys_out, uint32_t *perm_out, int32_t *leaf,
+                  int32_t *word, unsigned long long *stats, cudaStream_t s)
+{
+    const int64_t cap = (int64_t)vt_sm_count() * blocks_cap_per_sm;
+#define VT_LAUNCH_R(RV)                                                                                         \
+    {                                                                                                           \
+        const int64_t want = (n + 256 * RV - 1) / (256 * RV);                                                   \
+        level_kernel<DP, RV><<<(int)(want < cap ? want : cap), 256, 0, s>>>(desc, perm, parent, n, n_nodes,     \
+            level_off, n_heap, k, is_last, cent, internal, ref_id, keys_out, perm_out, leaf, word, stats);      \
+    }
+    if (r_tile >= 4) VT_LAUNCH_R(4)
+    else if (r_tile == 2) VT_LAUNCH_R(2)
+    else VT_LAUNCH_R(1)
+#undef VT_LAUNCH_R
+}
+
+// rows per lane for a level: large tiles only pay off while segments are much longer than a tile
+int pick_r(int64_t n, uint64_t n_nodes)
+{
+    static int forced = -1;
+    if (forced < 0) {
+        const char *e = getenv("VT_QS_R");
+        forced = e ? atoi(e) : 0;
+    }
+    if (forced == 1 || forced == 2 || forced == 4) return forced;
+    const double seg = (double)n / (double)n_nodes;
+    return seg >= 1024.0 ? 4 : (seg >= 256.0 ? 2 : 1);
 }
 
 int bits_for(uint64_t max_value)
@@ -274,11 +249,9 @@ int run_sorted(const uint8_t *desc, int64_t n, const float *cent, const uint8_t 
     for (int l = 0; l <= depth; ++l) { n_heap += pw; pw *= k; }
     uint32_t *kA = (uint32_t *)work, *kB = kA + n, *pA = kB + n, *pB = pA + n;
     void *hist = (void *)(pB + n);
-    const int64_t want = (n + 256 * QS_R - 1) / (256 * QS_R), cap = (int64_t)vt_sm_count() * 16;
-    const int blocks = (int)(want < cap ? want : cap);
     if (depth == 0) {                                            // the root is the only node
-        level_kernel<DP><<<blocks, 256, 0, s>>>(desc, nullptr, nullptr, n, 1u, 0, n_heap, k, 1, cent, internal, ref_id,
-                                                nullptr, nullptr, leaf, word, (unsigned long long *)stats);
+        launch_level<DP>(1, 16, desc, nullptr, nullptr, n, 1u, 0, n_heap, k, 1, cent, internal, ref_id, nullptr, nullptr,
+                         leaf, word, (unsigned long long *)stats, s);
         VT_LAUNCH_CHECK();
         return VT_OK;
     }
@@ -292,9 +265,8 @@ int run_sorted(const uint8_t *desc, int64_t n, const float *cent, const uint8_t 
         uint32_t *keys_out = is_last ? nullptr : (level == 0 ? keys : tkeys);
         uint32_t *perm_out = is_last ? nullptr : (level == 0 ? perm : tperm);
         VT_MARK();
-        level_kernel<DP><<<blocks, 256, 0, s>>>(desc, cur_perm, cur_parent, n, (uint32_t)n_nodes, level_off, n_heap, k,
-                                                is_last, cent, internal, ref_id, keys_out, perm_out, leaf, word,
-                                                (unsigned long long *)stats);
+        launch_level<DP>(pick_r(n, n_nodes), 16, desc, cur_perm, cur_parent, n, (uint32_t)n_nodes, level_off, n_heap, k,
+                         is_last, cent, internal, ref_id, keys_out, perm_out, leaf, word, (unsigned long long *)stats, s);
         VT_LAUNCH_CHECK();
         VT_MARK();
         if (is_last) break;
