@@ -228,7 +228,7 @@ int pick_r(int64_t n, uint64_t n_nodes)
     }
     if (forced == 1 || forced == 2 || forced == 4) return forced;
     const double seg = (double)n / (double)n_nodes;
-    return seg >= 1024.0 ? 4 : (seg >= 256.0 ? 2 : 1);
+    return seg >= 192.0 ? 2 : 1;        // measured on B200: R=2 (24 warps/SM) beats R=4 (16 warps/SM); VT_QS_R overrides
 }
 
 int bits_for(uint64_t max_value)
