@@ -126,9 +126,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)     # torchrun pins it to 1; the arm uses every core
     import torch
     import vtree_b200 as vt
     from oracle import vt_oracle as vo
+    torch.set_num_threads(os.cpu_count() or 1)
     cent = vt.synth.hierarchical_tree(K_BRANCH, DEPTH, DIM, seed=7, device="cpu")
     exists, internal, ref_id, n_ref = full_tree_tables(vt, K_BRANCH, DEPTH)
     tree = dict(k=K_BRANCH, depth=DEPTH, D=DIM, DP=DIM, centroids=cent.numpy(), exists=exists, internal=internal,
