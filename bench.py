@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--queries", type=int, default=10_000)
     ap.add_argument("--words-per-image", type=int, default=1000)
     ap.add_argument("--no-retrieval", action="store_true")
+    ap.add_argument("--no-build", action="store_true")
+    ap.add_argument("--build-desc", type=int, default=10_000_000, help="descriptors for the tree-build leg (whole job)")
+    ap.add_argument("--build-iters", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     return ap.parse_args()
@@ -283,6 +286,11 @@ def main():
         secondary = bench_retrieval(args, torch, vt, engine, nat, dev, rank, world, comm, ref_id, n_ref, barrier,
                                     max_over_ranks)
 
+    # ---- tertiary: BASELINE configs[1], tree build k=10 L=6 on 10 M descriptors ----------------
+    build = None
+    if not args.no_build:
+        build = bench_build(args, torch, vt, engine, dev, rank, world, comm, desc, barrier, max_over_ranks)
+
     # ---- CPU baseline (rank 0, single-GPU runs only) -------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -331,6 +339,7 @@ def main():
                          "traffic": None},
             "cpu_baseline": cpu,
             "secondary": secondary,
+            "build": build,
         }
         print(json.dumps(line))
     if world > 1:
@@ -388,6 +397,28 @@ def bench_retrieval(args, torch, vt, engine, nat, dev, rank, world, comm, ref_id
             "hbm": {"algorithmic_bytes_per_query": 8.0 * wpi * (args.db_images * wpi / n_leaf),
                     "achieved_GBps": 8.0 * wpi * (args.db_images * wpi / n_leaf) * q / (ms * 1e-3) / 1e9},
             "postings_per_word": postings_per_query}
+
+
+def bench_build(args, torch, vt, engine, dev, rank, world, comm, desc, barrier, max_over_ranks):
+    """VocabularyTree.fit at BASELINE configs[1]: k=10, L=6 on 10 M descriptors (sharded over the
+    ranks, integer sums all-reduced per level-iteration)."""
+    lo, hi = vt.dist.shard_range(args.build_desc, rank, world)
+    x = desc[: hi - lo]
+    log = []
+    stats = torch.zeros(4, dtype=torch.int64, device=dev)
+    barrier()
+    t0 = time.perf_counter()
+    tree = engine.build_tree(x, DIM, K_BRANCH, DEPTH, n_iter=args.build_iters, comm=comm, stats=stats,
+                             log=lambda **kw: log.append(kw))
+    barrier()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    passes = sum(l["iters"] + (0 if l["converged"] else 1) + (1 if l["converged"] else 0) for l in log)
+    member_passes = sum(l["members"] * (l["iters"] + 1) for l in log) * world
+    return {"metric": "tree build k=10 L=6", "seconds": dt, "descriptors": args.build_desc, "n_iter": args.build_iters,
+            "nodes": int(tree.n_ref), "leaves_reached_depth": int((tree.level_ref == DEPTH).sum()),
+            "assign_passes": passes, "member_assignments_per_s": member_passes / dt,
+            "descriptors_per_s": args.build_desc / dt, "binary64_rechecks": int(stats[0].item()),
+            "levels": [{"level": l["level"], "iters": l["iters"], "converged": l["converged"]} for l in log]}
 
 
 def cpu_baseline(args, vt, cent, exists, internal, ref_id, n_ref, desc, words):
