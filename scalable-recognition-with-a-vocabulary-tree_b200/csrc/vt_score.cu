@@ -51,6 +51,21 @@ __device__ __forceinline__ void block_best(double &key, int32_t &id, int &owner,
     __syncthreads();
 }
 
+constexpr uint32_t SC_LONG = 24;
+
+template <int MODE>
+__device__ __forceinline__ void accumulate(int *s_acci, float *s_accf, const uint2 pe, const float qv)
+{
+    if (MODE == VT_SCORE_TF_L2) {
+        atomicAdd(&s_acci[pe.x], (int)qv * (int)pe.y);
+    } else if (MODE == VT_SCORE_W_L2) {
+        atomicAdd(&s_accf[pe.x], qv * __uint_as_float(pe.y));
+    } else {
+        const float dv = __uint_as_float(pe.y);
+        atomicAdd(&s_accf[pe.x], qv + dv - fabsf(qv - dv));
+    }
+}
+
 // MODE: VT_SCORE_*.  R: images per shard.
 template <int MODE, int R>
 __global__ void __launch_bounds__(SC_THREADS)
@@ -77,23 +92,32 @@ score_shard_kernel(const uint32_t *__restrict__ post_off, const uint2 *__restric
         const int n_here = (int)((n_img - img0) < R ? (n_img - img0) : R);
         for (int t = threadIdx.x; t < R; t += SC_THREADS) s_acci[t] = 0;
         __syncthreads();
-        // accumulate: one warp per query word, lanes over its postings in this shard
+        // accumulate: one LANE per query word (32 independent row-pointer / posting fetches in flight
+        // per warp -- the walk is latency bound, not bandwidth bound); posting lists longer than
+        // SC_LONG are handed to the whole warp so that one lane never serialises a long list
         const int64_t qb = q_off[q], qe = q_off[q + 1];
         const uint32_t *off = post_off + (size_t)shard * n_ref;
-        for (int64_t w = qb + warp; w < qe; w += SC_WARPS) {
-            const int32_t node = q_node[w];
-            const float qv = q_val[w];
-            const uint32_t b = off[node], e = off[node + 1];
-            for (uint32_t p = b + lane; p < e; p += 32) {
-                const uint2 pe = postings[p];
-                if (MODE == VT_SCORE_TF_L2) {
-                    atomicAdd(&s_acci[pe.x], (int)qv * (int)pe.y);
-                } else if (MODE == VT_SCORE_W_L2) {
-                    atomicAdd(&s_accf[pe.x], qv * __uint_as_float(pe.y));
-                } else {
-                    const float dv = __uint_as_float(pe.y);
-                    atomicAdd(&s_accf[pe.x], qv + dv - fabsf(qv - dv));
-                }
+        for (int64_t w0 = qb + (int64_t)warp * 32; w0 < qe; w0 += SC_THREADS) {
+            const int64_t w = w0 + lane;
+            uint32_t b = 0, e = 0;
+            float qv = 0.f;
+            if (w < qe) {
+                const int32_t node = __ldg(q_node + w);
+                qv = __ldg(q_val + w);
+                b = __ldg(off + node);
+                e = __ldg(off + node + 1);
+            }
+            const bool is_long = (e - b) > SC_LONG;
+            if (!is_long) {
+                for (uint32_t p = b; p < e; ++p) accumulate<MODE>(s_acci, s_accf, postings[p], qv);
+            }
+            unsigned int m = __ballot_sync(VT_FULL, is_long);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t lb = __shfl_sync(VT_FULL, b, src), le = __shfl_sync(VT_FULL, e, src);
+                const float lq = __shfl_sync(VT_FULL, qv, src);
+                for (uint32_t p = lb + lane; p < le; p += 32) accumulate<MODE>(s_acci, s_accf, postings[p], lq);
             }
         }
         __syncthreads();
