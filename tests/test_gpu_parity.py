@@ -385,8 +385,9 @@ def test_notebook_flow_matches_reference(vt, cuda, name):
         np.testing.assert_allclose(list(res.values()), g["scores"][qi], rtol=1e-5, atol=1e-7)
         for r, (a, b) in enumerate(zip(got_order, g["order"][qi])):
             assert a == b or abs(ws[a] - ws[b]) <= 1e-9, (qi, r)
-        s = db.score(ds.image_paths[1], ds.image_paths[qi])
-        assert s == ws[1]
+        other = min(1, len(images) - 1)
+        s = db.score(ds.image_paths[other], ds.image_paths[qi])
+        assert s == ws[other]
     # reference-shaped postings
     post = voc.postings()
     sha = vt.utils.get_image_id(ds.read_image(ds.image_paths[0]))
