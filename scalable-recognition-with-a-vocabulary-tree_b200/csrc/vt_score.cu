@@ -77,14 +77,13 @@ score_shard_kernel(const uint32_t *__restrict__ post_off, const uint2 *__restric
 {
     constexpr int PER = R / SC_THREADS;
     extern __shared__ unsigned char s_raw[];
-    float *s_accf = reinterpret_cast<float *>(s_raw);                          // [R] (aliased int/float)
-    int *s_acci = reinterpret_cast<int *>(s_raw);
+    double *s_keys = reinterpret_cast<double *>(s_raw);                        // [R]
+    float *s_accf = reinterpret_cast<float *>(s_raw + (size_t)R * 8);          // [R] (aliased int/float)
+    int *s_acci = reinterpret_cast<int *>(s_accf);
     __shared__ double r_key[SC_WARPS];
     __shared__ int32_t r_id[SC_WARPS];
     __shared__ int r_owner[SC_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int TAKEN_I = (int)0x80000000;
-    const float TAKEN_F = -__int_as_float(0x7f800000);
 
     for (int64_t pair = blockIdx.x; pair < n_query * n_shards; pair += gridDim.x) {
         const int64_t q = pair / n_shards;
@@ -122,29 +121,26 @@ score_shard_kernel(const uint32_t *__restrict__ post_off, const uint2 *__restric
             }
         }
         __syncthreads();
-        // rank key of slot t (recomputed on demand: no second shared array, more CTAs per SM)
-        auto key_of = [&](int t) -> double {
-            if (t >= n_here) return -2.0;                                       // padding slots never win
-            if (MODE == VT_SCORE_TF_L2) {
-                const int a = s_acci[t];
-                if (a == TAKEN_I) return -2.0;
-                const double rn = __ldg(img_rnorm + img0 + t);
-                return rn < 0.0 ? -1.0 : (double)a * rn;
-            } else {
-                const float a = s_accf[t];
-                if (a == TAKEN_F) return -2.0;
-                const double rn = img_rnorm ? __ldg(img_rnorm + img0 + t) : 1.0;
-                return rn < 0.0 ? -1.0 : (double)a;
-            }
-        };
+        // rank keys + per-thread best
         double bkey = -2.0; int32_t bid = 0x7fffffff;
 #pragma unroll 4
         for (int u = 0; u < PER; ++u) {
             const int t = u * SC_THREADS + threadIdx.x;
-            const double key = key_of(t);
-            if (all_key && t < n_here) all_key[q * n_img + img0 + t] = key;
+            double key = -2.0;                                                  // padding slots never win
+            if (t < n_here) {
+                if (MODE == VT_SCORE_TF_L2) {
+                    const double rn = img_rnorm[img0 + t];
+                    key = rn < 0.0 ? -1.0 : (double)s_acci[t] * rn;
+                } else {
+                    const double rn = img_rnorm ? img_rnorm[img0 + t] : 1.0;
+                    key = rn < 0.0 ? -1.0 : (double)s_accf[t];
+                }
+                if (all_key) all_key[q * n_img + img0 + t] = key;
+            }
+            s_keys[t] = key;
             if (better(key, (int32_t)(img0 + t), bkey, bid)) { bkey = key; bid = (int32_t)(img0 + t); }
         }
+        __syncthreads();
         // k rounds of block argmax; only the winning thread rescans its slice
         for (int r = 0; r < topk; ++r) {
             double key = bkey; int32_t id = bid; int owner;
@@ -155,14 +151,11 @@ score_shard_kernel(const uint32_t *__restrict__ post_off, const uint2 *__restric
                 out_id[o] = key > -2.0 ? id : -1;
             }
             if (threadIdx.x == owner) {
-                if (key > -2.0) {
-                    if (MODE == VT_SCORE_TF_L2) s_acci[id - img0] = TAKEN_I;
-                    else s_accf[id - img0] = TAKEN_F;
-                }
+                if (key > -2.0) s_keys[id - img0] = -2.0;
                 bkey = -2.0; bid = 0x7fffffff;
                 for (int u = 0; u < PER; ++u) {
                     const int t = u * SC_THREADS + threadIdx.x;
-                    const double k2 = key_of(t);
+                    const double k2 = s_keys[t];
                     if (better(k2, (int32_t)(img0 + t), bkey, bid)) { bkey = k2; bid = (int32_t)(img0 + t); }
                 }
             }
@@ -268,10 +261,10 @@ static int launch_score(const uint32_t *post_off, const void *postings, const do
     constexpr int R = 8192;
     const int n_shards = (int)((n_img + R - 1) / R);
     auto kern = score_shard_kernel<MODE, R>;
-    const size_t smem = (size_t)R * 4;
+    const size_t smem = (size_t)R * 12;
     VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t pairs = n_query * n_shards;
-    const int64_t cap = (int64_t)vt_sm_count() * 6 * 4;
+    const int64_t cap = (int64_t)vt_sm_count() * 2 * 8;
     kern<<<(int)(pairs < cap ? pairs : cap), SC_THREADS, smem, s>>>(post_off, (const uint2 *)postings, img_rnorm, n_img, n_ref,
                                                                     n_shards, q_off, q_node, q_val, n_query, topk, out_key,
                                                                     out_id, all_key);
