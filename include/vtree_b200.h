@@ -86,6 +86,24 @@ int vt_quantize_sorted_profile(const void *d_desc, int dtype, int64_t n, int dp,
                                int32_t *d_word, uint64_t *d_stats, void *d_work, int64_t work_bytes,
                                float *h_level_ms, float *h_sort_ms, void *stream);
 
+/* Tensor-core variant of vt_quantize_sorted (tcgen05.mma kind::i8, accumulators in TMEM): after
+ * sorting, the 128 descriptors of a tile meet the same <= 16 child centroids, so the distance step
+ * is a dense byte contraction done exactly in integers (centroids rounded to 8.16 fixed point and
+ * split into three byte planes; provable rounding margin + binary64 re-evaluation of contested
+ * rows => ids bit-identical to vt_quantize).  Needs dp == 128, k <= 16 and child centroids in
+ * [0, 255.99] (d_stats[1] counts nodes that violate this).  vt_quantize_mma_profile is the
+ * measurement variant (see vt_quantize_sorted_profile). */
+int64_t vt_quantize_mma_work_bytes(int64_t n, int k, int depth);
+int vt_quantize_mma(const void *d_desc, int dtype, int64_t n, int dp,
+                    const float *d_centroids, const uint8_t *d_internal, const int32_t *d_ref_id,
+                    int k, int depth, int32_t *d_leaf_heap, int32_t *d_word, uint64_t *d_stats,
+                    void *d_work, int64_t work_bytes, void *stream);
+int vt_quantize_mma_profile(const void *d_desc, int dtype, int64_t n, int dp,
+                            const float *d_centroids, const uint8_t *d_internal,
+                            const int32_t *d_ref_id, int k, int depth, int32_t *d_leaf_heap,
+                            int32_t *d_word, uint64_t *d_stats, void *d_work, int64_t work_bytes,
+                            float *h_level_ms, float *h_sort_ms, void *stream);
+
 /* Host-buffer convenience used for end-to-end timing: descriptors in (preferably pinned) host
  * memory are streamed to the device in chunks on internal streams (copy/compute overlap), word
  * ids are copied back to h_word.  The tree stays device resident.  `chunk_rows` <= 0 picks a

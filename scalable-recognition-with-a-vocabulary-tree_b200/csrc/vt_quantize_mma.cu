@@ -1,0 +1,405 @@
+// vt_quantize_mma.cu -- tcgen05 (5th-gen tensor core) variant of the level-synchronous descent
+// (VocabularyTree.propagate_feature, cbir/encoders/vocabulary.py:104-124) for byte descriptors.
+//
+// After the batch is sorted by node, the 128 descriptors of a tile meet the SAME <=16 child
+// centroids: the distance step really is a dense contraction  X[128 x 128] . C^T[128 x 16].
+// It is done EXACTLY in integers on the INT8 tensor pipe:
+//   * descriptors are bytes -> the A operand is the gathered rows as they lie in HBM (cp.async
+//     into a 128B-swizzled K-major tile, no conversion);
+//   * centroids are rounded to 8.16 fixed point (|delta| <= 2^-17) and split into three byte
+//     planes -> B operand = 3 x 16 rows of bytes per node, prepared once per call;
+//   * tcgen05.mma kind::i8, M=128, N=48, K=32 x 4, int32 accumulators in TMEM (exact: 128 * 255 * 255
+//     < 2^31); tcgen05.ld brings one accumulator row to the thread that owns that descriptor;
+//   * s'_c = |c|^2 - 2 x.c is combined in int64 (units 2^-32) -> exact argmin for the ROUNDED centroids.
+// The only approximation is the centroid rounding: |s'_c(rounded) - s'_c(float32 centroid)| <=
+// 2^-16 * sqrt(D) * ||c - x|| + D * 2^-34, so rows whose runner-up is inside that provable margin
+// are re-evaluated in canonical binary64 exactly like in the SIMT kernels.  Results are therefore
+// bit-identical to vt_quantize / vt_quantize_sorted.
+//
+// Preconditions: dp == 128, k <= 16, every child centroid in [0, 255.99] (true for trees built from
+// byte descriptors; the prepare kernel reports violations in d_stats[1]).
+#include "vt_common.cuh"
+#include <stdlib.h>
+
+int vt_sort_pairs_impl(uint32_t *d_keys, uint32_t *d_vals, uint32_t *d_tmp_keys, uint32_t *d_tmp_vals, int64_t n,
+                       int n_bits, void *d_hist, int *result_in_tmp, cudaStream_t s);
+
+namespace {
+constexpr int MM_TILE = 128;                    // descriptors per tile == threads per CTA == UMMA M
+constexpr int MM_N = 48;                        // 3 byte planes x 16 child slots
+constexpr int MM_A_BYTES = MM_TILE * 128;       // 16 KB
+constexpr int MM_B_BYTES = MM_N * 128;          // 6 KB
+constexpr int MM_TMEM_COLS = 64;                // power of two >= MM_N
+constexpr uint32_t MM_IDESC = (2u << 4) | ((uint32_t)(MM_N >> 3) << 17) | ((uint32_t)(MM_TILE >> 4) << 24);
+//                             c_format = S32; a_format = b_format = 0 (unsigned 8 bit); K-major A and B
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// byte offset of (row, k) inside a 128B-swizzled K-major tile whose rows are 128 bytes
+__device__ __forceinline__ uint32_t sw128_offset(int row, int kbyte)
+{
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((kbyte >> 4) ^ (row & 7))) << 4) + (kbyte & 15));
+}
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
+{
+    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | (1ull << 16) /* LBO (unused) */ | (64ull << 32) /* SBO = 1024 B */ |
+           (1ull << 46) /* sm100 descriptor version */ | (2ull << 61) /* SWIZZLE_128B */;
+}
+
+// ---- per-call preparation: byte planes + fixed-point squared norms of every node's children --------
+__global__ void __launch_bounds__(128)
+prep_planes_kernel(const float *__restrict__ cent, int64_t n_int, int k, uint8_t *__restrict__ bimg,
+                   unsigned long long *__restrict__ cn, unsigned long long *__restrict__ stats)
+{
+    __shared__ unsigned long long s_part[4];
+    const int d = threadIdx.x;
+    for (int64_t h = blockIdx.x; h < n_int; h += gridDim.x) {
+        uint8_t *img = bimg + (size_t)h * MM_B_BYTES;
+        bool bad = false;
+        for (int c = 0; c < 16; ++c) {
+            uint32_t fx = 0;
+            if (c < k) {
+                const float v = cent[(size_t)(h * k + 1 + c) * 128 + d];
+                if (!(v >= 0.f) || v > 255.99f) bad = true;
+                fx = (uint32_t)rintf(fminf(fmaxf(v, 0.f), 255.99f) * 65536.f);
+            }
+            img[sw128_offset(c, d)] = (uint8_t)(fx >> 16);
+            img[sw128_offset(16 + c, d)] = (uint8_t)(fx >> 8);
+            img[sw128_offset(32 + c, d)] = (uint8_t)fx;
+            unsigned long long sq = (unsigned long long)fx * fx;
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) sq += __shfl_xor_sync(VT_FULL, sq, o);
+            if ((d & 31) == 0) s_part[d >> 5] = sq;
+            __syncthreads();
+            if (d == 0 && c < k) cn[h * k + 1 + c] = s_part[0] + s_part[1] + s_part[2] + s_part[3];
+            __syncthreads();
+        }
+        if (bad && stats) atomicAdd(stats + 1, 1ull);
+    }
+}
+
+// ---- one tree level -------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MM_TILE)
+level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ parent,
+                 int64_t n, uint32_t n_nodes, int64_t level_off, int64_t n_heap, int k, int is_last,
+                 const float *__restrict__ cent, const uint8_t *__restrict__ internal, const int32_t *__restrict__ ref_id,
+                 const uint8_t *__restrict__ bimg, const unsigned long long *__restrict__ cn,
+                 uint32_t *__restrict__ keys_out, uint32_t *__restrict__ perm_out, int32_t *__restrict__ leaf_out,
+                 int32_t *__restrict__ word_out, unsigned long long *__restrict__ stats)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // the swizzled tiles need a 1024 B aligned base (the launch reserves 1 KB of slack for this)
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + MM_A_BYTES;
+    __shared__ __align__(8) unsigned long long mbar;
+    __shared__ uint32_t s_tmem;
+    __shared__ uint32_t s_row[MM_TILE];
+    __shared__ long long s_min[4];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t sentinel = n_nodes * (uint32_t)k;
+    const long long none = 0x7fffffffffffffffLL;
+    unsigned int rechecks = 0;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(MM_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = s_tmem;
+    const uint64_t a_desc = make_desc(smem_u32(sA));
+    const uint64_t b_desc = make_desc(smem_u32(sB));
+    uint32_t phase = 0;
+
+    for (int64_t base = (int64_t)blockIdx.x * MM_TILE; base < n; base += (int64_t)gridDim.x * MM_TILE) {
+        const int64_t p = base + tid;
+        const bool valid = p < n;
+        const uint32_t row = valid ? (perm ? perm[p] : (uint32_t)p) : 0u;
+        const uint32_t jp = valid ? (parent ? parent[p] : 0u) : sentinel;
+        const bool alive = valid && jp < n_nodes;
+        const long long node = level_off + (alive ? jp : 0u);
+        const bool is_int = alive && (node * k + k < n_heap) && internal[node];
+        const uint8_t *xrow = desc + (size_t)row * 128;
+        if (alive && !is_int) {                                  // ragged tree: this node is a leaf
+            if (leaf_out) leaf_out[row] = (int32_t)node;
+            if (word_out) word_out[row] = ref_id[node];
+        }
+        s_row[tid] = is_int ? row : 0xffffffffu;
+        __syncthreads();
+        // A tile: 8 lanes copy one 128 B row (coalesced), 16 rows per pass, swizzled destination
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = (tid >> 3) + 16 * i, j = tid & 7;
+            const uint32_t rr = s_row[r];
+            const uint8_t *src = rr != 0xffffffffu ? desc + (size_t)rr * 128 + j * 16 : desc;
+            const uint32_t dst = smem_u32(sA) + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
+            const int nbytes = rr != 0xffffffffu ? 16 : 0;     // zero fill for rows that take no part
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes));
+        }
+        long long best = none, second = none;
+        int arg = 0;
+        bool pending = is_int;
+        unsigned int xn = 0;                                    // exact |x|^2, filled after the first wait
+
+        // one MMA pass per distinct node present in the tile (sorted batch: almost always one)
+        for (int pass = 0;; ++pass) {
+            long long mine = pending ? node : none;
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) {
+                const long long other = __shfl_xor_sync(VT_FULL, mine, o);
+                mine = other < mine ? other : mine;
+            }
+            if (lane == 0) s_min[warp] = mine;
+            __syncthreads();
+            mine = s_min[0];
+#pragma unroll
+            for (int w = 1; w < 4; ++w) mine = s_min[w] < mine ? s_min[w] : mine;
+            if (mine == none) break;                            // block-uniform
+            const bool on = pending && node == mine;
+            pending = pending && !on;
+            // B tile of this node: 384 x 16 B, already in swizzled image form
+            const uint8_t *bsrc = bimg + (size_t)mine * MM_B_BYTES;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int c = tid + MM_TILE * i;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sB) + c * 16), "l"(bsrc + c * 16));
+            }
+            asm volatile("cp.async.commit_group;");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> tensor core
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {                // K = 4 x 32 bytes
+                    const uint32_t acc = ks > 0 ? 1u : 0u;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                        ::"r"(tmem), "l"(a_desc + 2 * ks), "l"(b_desc + 2 * ks), "r"(MM_IDESC), "r"(acc), "r"(0u));
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
+            }
+            if (pass == 0 && is_int) {                          // overlap with the MMA: |x|^2 from the staged tile
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint4 q = *reinterpret_cast<const uint4 *>(sA + (tid >> 3) * 1024 + (tid & 7) * 128 + ((j ^ (tid & 7)) << 4));
+                    xn = __dp4a(q.x, q.x, xn); xn = __dp4a(q.y, q.y, xn); xn = __dp4a(q.z, q.z, xn); xn = __dp4a(q.w, q.w, xn);
+                }
+            }
+            {   // wait for the accumulator
+                uint32_t done;
+                do {
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                                 : "=r"(done) : "r"(smem_u32(&mbar)), "r"(phase) : "memory");
+                } while (!done);
+                phase ^= 1u;
+            }
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            uint32_t v[MM_N];
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                             : "=r"(v[16 * g + 0]), "=r"(v[16 * g + 1]), "=r"(v[16 * g + 2]), "=r"(v[16 * g + 3]),
+                               "=r"(v[16 * g + 4]), "=r"(v[16 * g + 5]), "=r"(v[16 * g + 6]), "=r"(v[16 * g + 7]),
+                               "=r"(v[16 * g + 8]), "=r"(v[16 * g + 9]), "=r"(v[16 * g + 10]), "=r"(v[16 * g + 11]),
+                               "=r"(v[16 * g + 12]), "=r"(v[16 * g + 13]), "=r"(v[16 * g + 14]), "=r"(v[16 * g + 15])
+                             : "r"(taddr + 16 * g));
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (on) {
+                const unsigned long long *cnc = cn + (mine * k + 1);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    if (c < k) {
+                        const long long dot = ((long long)v[c] << 16) + ((long long)v[16 + c] << 8) + (long long)v[32 + c];
+                        const long long s = (long long)cnc[c] - (dot << 17);      // |c|^2 - 2 x.c, units 2^-32
+                        if (s < best) { second = best; best = s; arg = c; }
+                        else if (s < second) second = s;
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncthreads();                                    // TMEM and the B tile may be reused
+        }
+
+        // provable margin for the centroid rounding; contested rows go to canonical binary64
+        bool contested = false;
+        if (is_int && k > 1) {
+            const double xn2 = (double)xn;
+            const double d2a = fmax(0.0, (double)best * 2.3283064365386963e-10 + xn2);
+            const double d2b = fmax(0.0, (double)second * 2.3283064365386963e-10 + xn2);
+            const double margin = 1.52587890625e-05 * 11.313708498984761 * 1.02 * (sqrt(d2a) + sqrt(d2b)) + 1e-6;
+            contested = (double)(second - best) * 2.3283064365386963e-10 <= margin;
+        }
+        unsigned int m = __ballot_sync(VT_FULL, contested);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const unsigned long long xq = __shfl_sync(VT_FULL, (unsigned long long)xrow, src);
+            const long long nq = __shfl_sync(VT_FULL, node, src);
+            const int res = canon_argmin_warp<uint8_t, 128>(reinterpret_cast<const uint8_t *>(xq),
+                                                            cent + (size_t)(nq * k + 1) * 128, k, lane);
+            if (lane == src) { arg = res; ++rechecks; }
+        }
+        uint32_t key = sentinel;
+        if (is_int) {
+            const long long child = node * k + 1 + arg;
+            if (is_last || !((child * k + k < n_heap) && internal[child])) {
+                if (leaf_out) leaf_out[row] = (int32_t)child;
+                if (word_out) word_out[row] = ref_id[child];
+            } else {
+                key = jp * (uint32_t)k + (uint32_t)arg;
+            }
+        }
+        if (valid && keys_out) { keys_out[p] = key; perm_out[p] = row; }
+        __syncthreads();                                        // s_row / A tile reused by the next tile
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) rechecks += __shfl_xor_sync(VT_FULL, rechecks, o);
+    if (stats && lane == 0 && rechecks) atomicAdd(stats, (unsigned long long)rechecks);
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(MM_TMEM_COLS));
+}
+
+int bits_for_mma(uint64_t max_value)
+{
+    int b = 0;
+    while (max_value) { ++b; max_value >>= 1; }
+    return b;
+}
+}  // namespace
+
+static int64_t mma_int_nodes(int k, int depth)
+{
+    int64_t n = 0, p = 1;
+    for (int l = 0; l < depth; ++l) { n += p; p *= k; }
+    return n;
+}
+
+extern "C" int64_t vt_quantize_mma_work_bytes(int64_t n, int k, int depth)
+{
+    if (n < 1) n = 1;
+    int64_t n_heap = 0, p = 1;
+    for (int l = 0; l <= depth; ++l) { n_heap += p; p *= k; }
+    const int64_t planes = ((mma_int_nodes(k, depth) * MM_B_BYTES + 255) / 256) * 256;
+    const int64_t norms = ((n_heap * 8 + 255) / 256) * 256;
+    return planes + norms + 16 * n + vt_sort_scratch_bytes(n);
+}
+
+int vt_quantize_mma_impl(const void *d_desc, int64_t n, const float *cent, const uint8_t *internal, const int32_t *ref_id,
+                         int k, int depth, int32_t *leaf, int32_t *word, uint64_t *stats, void *work, cudaStream_t s,
+                         cudaEvent_t *ev)
+{
+    int n_ev = 0;
+#define VT_MARK() do { if (ev) VT_CUDA(cudaEventRecord(ev[n_ev++], s)); } while (0)
+    int64_t n_heap = 0, pw = 1;
+    for (int l = 0; l <= depth; ++l) { n_heap += pw; pw *= k; }
+    const int64_t n_int = mma_int_nodes(k, depth);
+    uint8_t *bimg = (uint8_t *)work;
+    const int64_t planes = ((n_int * MM_B_BYTES + 255) / 256) * 256;
+    unsigned long long *cn = (unsigned long long *)(bimg + planes);
+    const int64_t norms = ((n_heap * 8 + 255) / 256) * 256;
+    uint32_t *kA = (uint32_t *)((uint8_t *)cn + norms), *kB = kA + n, *pA = kB + n, *pB = pA + n;
+    void *hist = (void *)(pB + n);
+    const uint8_t *desc = (const uint8_t *)d_desc;
+
+    VT_MARK();
+    {
+        const int64_t cap = (int64_t)vt_sm_count() * 16;
+        prep_planes_kernel<<<(int)(n_int < cap ? n_int : cap), 128, 0, s>>>(cent, n_int, k, bimg, cn, (unsigned long long *)stats);
+        VT_LAUNCH_CHECK();
+    }
+    static bool attr_set = false;
+    const int smem = MM_A_BYTES + MM_B_BYTES + 1024;
+    if (!attr_set) {
+        VT_CUDA(cudaFuncSetAttribute(level_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    const int64_t want = (n + MM_TILE - 1) / MM_TILE, cap = (int64_t)vt_sm_count() * 7;
+    const int blocks = (int)(want < cap ? want : cap);
+    uint32_t *keys = kA, *perm = pA, *tkeys = kB, *tperm = pB;
+    const uint32_t *cur_perm = nullptr, *cur_parent = nullptr;
+    int64_t level_off = 0;
+    uint64_t n_nodes = 1;
+    for (int level = 0; level < depth; ++level) {
+        const int is_last = level + 1 == depth;
+        uint32_t *keys_out = is_last ? nullptr : (level == 0 ? keys : tkeys);
+        uint32_t *perm_out = is_last ? nullptr : (level == 0 ? perm : tperm);
+        if (level > 0) VT_MARK();
+        level_mma_kernel<<<blocks, MM_TILE, smem, s>>>(desc, cur_perm, cur_parent, n, (uint32_t)n_nodes, level_off, n_heap, k,
+                                                       is_last, cent, internal, ref_id, bimg, cn, keys_out, perm_out, leaf,
+                                                       word, (unsigned long long *)stats);
+        VT_LAUNCH_CHECK();
+        VT_MARK();
+        if (is_last) break;
+        if (level > 0) { uint32_t *t; t = keys; keys = tkeys; tkeys = t; t = perm; perm = tperm; tperm = t; }
+        int flip = 0;
+        const int rc = vt_sort_pairs_impl(keys, perm, tkeys, tperm, n, bits_for_mma(n_nodes * (uint64_t)k), hist, &flip, s);
+        if (rc != VT_OK) return rc;
+        if (flip) { uint32_t *t; t = keys; keys = tkeys; tkeys = t; t = perm; perm = tperm; tperm = t; }
+        cur_parent = keys;
+        cur_perm = perm;
+        level_off += (int64_t)n_nodes;
+        n_nodes *= (uint64_t)k;
+    }
+#undef VT_MARK
+    return VT_OK;
+}
+
+// Same contract as vt_quantize_sorted (bit-identical ids); tensor-core distance step.
+extern "C" int vt_quantize_mma(const void *d_desc, int dtype, int64_t n, int dp, const float *d_centroids,
+                               const uint8_t *d_internal, const int32_t *d_ref_id, int k, int depth,
+                               int32_t *d_leaf_heap, int32_t *d_word, uint64_t *d_stats, void *d_work,
+                               int64_t work_bytes, void *stream)
+{
+    VT_CHECK_ARG(dtype == VT_U8 && dp == 128, "the tensor-core descent takes 128-byte descriptor rows");
+    VT_CHECK_ARG(n >= 0 && n < ((int64_t)1 << 31), "n out of range");
+    VT_CHECK_ARG(k >= 1 && k <= 16 && depth >= 1 && depth <= 16, "k must be <= 16 and depth >= 1");
+    VT_CHECK_ARG(d_centroids && d_internal, "null tree");
+    VT_CHECK_ARG(d_word == nullptr || d_ref_id != nullptr, "d_word needs d_ref_id");
+    VT_CHECK_ARG(d_work && work_bytes >= vt_quantize_mma_work_bytes(n, k, depth), "workspace too small");
+    {
+        double rows = 1.0;
+        for (int l = 0; l < depth; ++l) rows *= k;
+        VT_CHECK_ARG(rows < 4.0e9, "k^depth must fit 32 bits");
+    }
+    if (n == 0) return VT_OK;
+    return vt_quantize_mma_impl(d_desc, n, d_centroids, d_internal, d_ref_id, k, depth, d_leaf_heap, d_word, d_stats, d_work,
+                                (cudaStream_t)stream, nullptr);
+}
+
+// measurement variant: h_level_ms[depth] (level kernels; entry 0 includes the plane preparation),
+// h_sort_ms[depth] (re-sorts)
+extern "C" int vt_quantize_mma_profile(const void *d_desc, int dtype, int64_t n, int dp, const float *d_centroids,
+                                       const uint8_t *d_internal, const int32_t *d_ref_id, int k, int depth,
+                                       int32_t *d_leaf_heap, int32_t *d_word, uint64_t *d_stats, void *d_work,
+                                       int64_t work_bytes, float *h_level_ms, float *h_sort_ms, void *stream)
+{
+    VT_CHECK_ARG(dtype == VT_U8 && dp == 128 && n > 0 && k <= 16 && depth >= 1 && depth <= 16, "bad arguments");
+    VT_CHECK_ARG(d_work && work_bytes >= vt_quantize_mma_work_bytes(n, k, depth), "workspace too small");
+    VT_CHECK_ARG(h_level_ms && h_sort_ms, "null output");
+    cudaEvent_t ev[40];
+    const int n_ev = 2 * depth;
+    for (int i = 0; i < n_ev; ++i) VT_CUDA(cudaEventCreate(&ev[i]));
+    int rc = vt_quantize_mma_impl(d_desc, n, d_centroids, d_internal, d_ref_id, k, depth, d_leaf_heap, d_word, d_stats,
+                                  d_work, (cudaStream_t)stream, ev);
+    if (rc == VT_OK && cudaEventSynchronize(ev[n_ev - 1]) != cudaSuccess) rc = VT_ECUDA;
+    for (int l = 0; l < depth && rc == VT_OK; ++l) {
+        cudaEventElapsedTime(&h_level_ms[l], ev[2 * l], ev[2 * l + 1]);
+        h_sort_ms[l] = 0.f;
+        if (l + 1 < depth) cudaEventElapsedTime(&h_sort_ms[l], ev[2 * l + 1], ev[2 * l + 2]);
+    }
+    for (int i = 0; i < n_ev; ++i) cudaEventDestroy(ev[i]);
+    return rc;
+}

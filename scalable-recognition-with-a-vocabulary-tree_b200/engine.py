@@ -87,14 +87,23 @@ def quantize(tree_dev: dict, k: int, depth: int, desc: torch.Tensor, want_heap: 
 
     ``method``: "fused" = one launch, warp-per-descriptor descent (any dtype, any start node);
     "sorted" = level-synchronous descent over the batch sorted by node (bytes, large batches);
-    "auto" picks by batch size.  Both return identical ids."""
+    "mma" = the same with the distance step on the INT8 tensor pipe (tcgen05, 128-byte rows, k <= 16,
+    centroids in [0, 255.99]); "auto" picks by batch size.  All return identical ids."""
     lib = _lib()
     n, dp = desc.shape
     word = torch.empty(n, dtype=torch.int32, device=desc.device)
     leaf = torch.empty(n, dtype=torch.int32, device=desc.device) if want_heap else None
     if method == "auto":
         method = "sorted" if (desc.dtype == torch.uint8 and start == 0 and n >= SORTED_MIN_ROWS and depth >= 2) else "fused"
-    if method == "sorted":
+    if method == "mma":
+        need = int(lib.vt_quantize_mma_work_bytes(n, k, depth))
+        if work is None or work.numel() * work.element_size() < need:
+            work = torch.empty(need, dtype=torch.uint8, device=desc.device)
+        nat.check(lib.vt_quantize_mma(nat.ptr(desc), _dtype_code(desc), n, dp, nat.ptr(tree_dev["centroids"]),
+                                      nat.ptr(tree_dev["internal"]), nat.ptr(tree_dev["ref_id"]), k, depth,
+                                      nat.ptr(leaf), nat.ptr(word), nat.ptr(stats), nat.ptr(work),
+                                      work.numel() * work.element_size(), nat.stream_ptr()), "vt_quantize_mma")
+    elif method == "sorted":
         need = int(lib.vt_quantize_sorted_work_bytes(n))
         if work is None or work.numel() * work.element_size() < need:
             work = torch.empty(need, dtype=torch.uint8, device=desc.device)

@@ -116,6 +116,32 @@ def test_quantize_random_trees(vt, cuda, k, depth, d, tie_heavy):
         assert (gap == 0).any()                        # exact ties were present (first child must win)
 
 
+@pytest.mark.parametrize("case", ["small", "c1", "rand-k10", "rand-k16-d100", "ties-k4", "ragged-k3"])
+def test_quantize_tensor_core_path_matches_oracle(vt, cuda, case):
+    """vt_quantize_mma (tcgen05 kind::i8, exact integer distances + provable rounding margin) must
+    return the same ids as the binary64 oracle."""
+    torch = _torch()
+    rng = np.random.default_rng(len(case))
+    if case in ("small", "c1"):
+        ft, g, meta, images = _flat_from_golden(vt, case)
+        x = np.concatenate(images)
+    else:
+        k, depth, d, tie = {"rand-k10": (10, 4, 128, False), "rand-k16-d100": (16, 3, 100, False),
+                            "ties-k4": (4, 5, 128, True), "ragged-k3": (3, 6, 128, False)}[case]
+        ft = _random_tree(vt, rng, k, depth, d, ragged=True, tie_heavy=tie)
+        x = rng.integers(0, 4 if tie else 256, (50_003, d)).astype(np.uint8)
+    want = vo.descend(oracle_tree_from_flat(ft), x)
+    desc, _ = vt.engine.stage(x, cuda)
+    stats = torch.zeros(4, dtype=torch.int64, device=cuda)
+    word, heap = vt.engine.quantize(ft.device(cuda), ft.k, ft.depth, desc, want_heap=True, stats=stats, method="mma")
+    torch.cuda.synchronize()
+    assert int(stats[1].item()) == 0                       # no centroid outside the fixed-point range
+    heap = heap.cpu().numpy()
+    assert np.array_equal(heap, want), "%d of %d rows differ" % ((heap != want).sum(), len(want))
+    assert np.array_equal(word.cpu().numpy(), ft.ref_id[want])
+    print(case, "binary64 rechecks:", int(stats[0].item()), "of", len(x) * ft.depth)
+
+
 def test_quantize_start_node_and_empty_batch(vt, cuda):
     torch = _torch()
     ft, g, meta, images = _flat_from_golden(vt, "small")
