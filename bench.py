@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--db-images", type=int, default=1_000_000, help="database images (whole job)")
     ap.add_argument("--queries", type=int, default=10_000)
     ap.add_argument("--words-per-image", type=int, default=1000)
+    ap.add_argument("--engine", default="mma", choices=["mma", "simt"],
+                    help="distance step of the sorted descent: tcgen05 INT8 tensor cores or FP32 SIMT")
     ap.add_argument("--no-retrieval", action="store_true")
     ap.add_argument("--no-build", action="store_true")
     ap.add_argument("--build-desc", type=int, default=10_000_000, help="descriptors for the tree-build leg (whole job)")
@@ -213,11 +215,13 @@ def main():
               "vt_measure_fp32_peak")
 
     # ---- device-resident throughput ---------------------------------------------------------------
-    work = torch.empty(int(lib.vt_quantize_sorted_work_bytes(n)), dtype=torch.uint8, device=dev)
+    work = torch.empty(int(max(lib.vt_quantize_sorted_work_bytes(n), lib.vt_quantize_mma_work_bytes(n, K_BRANCH, DEPTH))),
+                       dtype=torch.uint8, device=dev)
+    method = "mma" if args.engine == "mma" else "sorted"
 
     def one_step():
         # level-synchronous sorted descent: 6 level kernels + the radix passes between them
-        return engine.quantize(tree_dev, K_BRANCH, DEPTH, desc, stats=stats, method="sorted", work=work)
+        return engine.quantize(tree_dev, K_BRANCH, DEPTH, desc, stats=stats, method=method, work=work)
 
     for _ in range(args.warmup):
         words = one_step()
@@ -238,17 +242,20 @@ def main():
     rechecks = int(stats[0].item())
 
     # per-stage CUDA events (same call, measurement variant): which share of a step is the level kernel
-    lvl = (C.c_float * DEPTH)()
-    srt = (C.c_float * DEPTH)()
-    lvl_acc, srt_acc, prof_reps = np.zeros(DEPTH), np.zeros(DEPTH), 3
-    for _ in range(prof_reps):
-        nat.check(lib.vt_quantize_sorted_profile(nat.ptr(desc), 0, n, DIM, nat.ptr(cent), nat.ptr(tree_dev["internal"]),
-                                                 nat.ptr(tree_dev["ref_id"]), K_BRANCH, DEPTH, None, nat.ptr(words), None,
-                                                 nat.ptr(work), work.numel(), lvl, srt, nat.stream_ptr()),
-                  "vt_quantize_sorted_profile")
-        lvl_acc += np.array(list(lvl))
-        srt_acc += np.array(list(srt))
-    level_ms, sort_ms = lvl_acc / prof_reps, srt_acc / prof_reps
+    def stage_profile(fn, reps=3):
+        lvl = (C.c_float * DEPTH)()
+        srt = (C.c_float * DEPTH)()
+        lvl_acc, srt_acc = np.zeros(DEPTH), np.zeros(DEPTH)
+        for _ in range(reps):
+            nat.check(fn(nat.ptr(desc), 0, n, DIM, nat.ptr(cent), nat.ptr(tree_dev["internal"]), nat.ptr(tree_dev["ref_id"]),
+                         K_BRANCH, DEPTH, None, nat.ptr(words), None, nat.ptr(work), work.numel(), lvl, srt,
+                         nat.stream_ptr()), "profile variant")
+            lvl_acc += np.array(list(lvl))
+            srt_acc += np.array(list(srt))
+        return lvl_acc / reps, srt_acc / reps
+
+    level_ms, sort_ms = stage_profile(lib.vt_quantize_mma_profile if method == "mma" else lib.vt_quantize_sorted_profile)
+    other_ms, _ = stage_profile(lib.vt_quantize_sorted_profile if method == "mma" else lib.vt_quantize_mma_profile, reps=1)
     sort_passes = sum(-(-int(K_BRANCH ** (l + 1)).bit_length() // 8) for l in range(DEPTH - 1))
     launches_per_step = DEPTH + 3 * sort_passes
 
@@ -301,17 +308,48 @@ def main():
         alg_bytes = DIM + 4                                        # byte row in, int32 word id out
         per_launch = n
         lvl_total_ms = float(level_ms.sum())
-        achieved_tf = flop_per_desc * per_launch / (lvl_total_ms * 1e-3) / 1e12
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except OSError:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        other_total_ms = float(other_ms.sum())
+        # bytes the level kernels must move per descriptor-level: 128 B row gather + 4 B permutation +
+        # 4 B node key in, 4 B key + 4 B permutation out (the last level writes the 4 B word id instead)
+        level_bytes = [DIM + (8 if l > 0 else 0) + (8 if l + 1 < DEPTH else 4) for l in range(DEPTH)]
+        simt = {"bound": "fp32", "kernel": "level_kernel<128,R> (vt_quantize_sorted.cu)", "unit": "TFLOP/s",
+                "peak": peak_tf.value, "peak_source": "FFMA microbenchmark on this device (vt_measure_fp32_peak)",
+                "flop_per_descriptor": flop_per_desc}
+        mma = {"bound": "hbm", "kernel": "level_mma_kernel (vt_quantize_mma.cu, tcgen05.mma kind::i8)", "unit": "GB/s",
+               "peak": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+               "bytes_per_descriptor_level": level_bytes}
+        def fill(d, total_ms):
+            if d["bound"] == "fp32":
+                d["achieved"] = flop_per_desc * per_launch / (total_ms * 1e-3) / 1e12
+            else:
+                d["achieved"] = sum(level_bytes) * per_launch / (total_ms * 1e-3) / 1e9
+            d["frac"] = d["achieved"] / d["peak"] if d["peak"] else None
+            d["kernel_ms_per_step"] = total_ms
+            return d
+        main_r, other_r = (mma, simt) if method == "mma" else (simt, mma)
+        roofline = fill(main_r, lvl_total_ms)
+        roofline.update({
+            "launches_per_step": DEPTH,
+            "level_kernel_ms": [round(float(v), 3) for v in level_ms],
+            "resort_ms": [round(float(v), 3) for v in sort_ms],
+            "kernel_share_of_step": lvl_total_ms / kern_ms,
+            "whole_step": {"step_ms_events": kern_ms,
+                           "algorithmic_GBps": alg_bytes * per_launch / (kern_ms * 1e-3) / 1e9,
+                           "algorithmic_TFLOPs": flop_per_desc * per_launch / (kern_ms * 1e-3) / 1e12},
+            "traffic": None,
+            "other_engine": dict(fill(other_r, other_total_ms), level_kernel_ms=[round(float(v), 3) for v in other_ms]),
+            "fused_single_launch_descent": {"value": fused_rate, "unit": "descriptors/s", "rows": n_f},
+        })
         line = {
             "metric": METRIC, "value": value, "unit": "descriptors/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "u8 x fixed-point (int32 accumulate)" if method == "mma" else "f32", "data": "synthetic",
             "config": {"workload": "BASELINE configs[2]: quantize %d SIFT-128 byte descriptors per GPU through a "
                                    "k=10 L=6 (1,111,111-node) tree, tree replicated, descriptors sharded" % n,
                        "l2": "input (%.1f GB) is larger than L2; nothing is flushed between steps" % (n * DIM / 1e9),
@@ -321,22 +359,7 @@ def main():
                     "api": "vt_quantize_host (engine.quantize_host)"},
             "gpu_launches": args.steps * launches_per_step,
             "clocks": clocks.summary(),
-            "roofline": {"bound": "fp32", "kernel": "level_kernel<128> (vt_quantize_sorted.cu), %d launches per step" % DEPTH,
-                         "achieved": achieved_tf, "peak": peak_tf.value, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf.value if peak_tf.value else None,
-                         "peak_source": "FFMA microbenchmark on this device (vt_measure_fp32_peak)",
-                         "flop_per_descriptor": flop_per_desc, "kernel_ms_per_step": lvl_total_ms,
-                         "level_kernel_ms": [round(float(v), 3) for v in level_ms],
-                         "resort_ms": [round(float(v), 3) for v in sort_ms],
-                         "kernel_share_of_step": lvl_total_ms / kern_ms,
-                         "whole_step": {"achieved": flop_per_desc * per_launch / (kern_ms * 1e-3) / 1e12,
-                                        "frac": flop_per_desc * per_launch / (kern_ms * 1e-3) / 1e12 / peak_tf.value,
-                                        "step_ms_events": kern_ms},
-                         "fused_single_launch_descent": {"value": fused_rate, "unit": "descriptors/s", "rows": n_f},
-                         "hbm": {"achieved": alg_bytes * per_launch / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak,
-                                 "unit": "GB/s", "bytes_per_descriptor": alg_bytes,
-                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
-                         "traffic": None},
+            "roofline": roofline,
             "cpu_baseline": cpu,
             "secondary": secondary,
             "build": build,
