@@ -7,6 +7,7 @@
 // through L1/L2 as coalesced 128 B rows.  Algorithmic work per descriptor: 2*k*DP*L float32
 // lane-slots (sub + fma), DP*sizeof(T) + 4 bytes.
 #include "vt_common.cuh"
+#include <stdlib.h>
 
 template <typename T, int DP>
 __global__ void __launch_bounds__(256, 3)
@@ -109,6 +110,11 @@ extern "C" int vt_quantize(const void *d_desc, int dtype, int64_t n, int dp, con
 int vt_quantize_sorted_impl(const void *d_desc, int64_t n, int dp, const float *d_centroids, const uint8_t *d_internal,
                             const int32_t *d_ref_id, int k, int depth, int32_t *d_leaf_heap, int32_t *d_word,
                             uint64_t *d_stats, void *d_work, cudaStream_t s, cudaEvent_t *ev);
+int vt_mma_prepare(const float *cent, int k, int depth, void *planes_and_norms, uint64_t *stats, cudaStream_t s);
+int64_t vt_mma_prepared_bytes(int k, int depth);
+int vt_mma_levels(const void *d_desc, int64_t n, const float *cent, const uint8_t *internal, const int32_t *ref_id, int k,
+                  int depth, int32_t *leaf, int32_t *word, uint64_t *stats, const void *prepared, void *sortwork,
+                  cudaStream_t s, cudaEvent_t *ev, int *n_ev_io);
 extern "C" int vt_quantize_host(const void *h_desc, int dtype, int64_t n, int dp, const float *d_centroids,
                                 const uint8_t *d_internal, const int32_t *d_ref_id, int k, int depth,
                                 int32_t *h_word, int64_t chunk_rows)
@@ -122,6 +128,10 @@ extern "C" int vt_quantize_host(const void *h_desc, int dtype, int64_t n, int dp
     if (chunk_rows > n) chunk_rows = n;
     // large byte chunks go through the level-synchronous sorted descent (same ids, far less DRAM traffic)
     const bool sorted = dtype == VT_U8 && depth >= 2 && chunk_rows >= ((int64_t)1 << 18);
+    // 128-byte rows and k <= 16: distance step on the INT8 tensor pipe (planes prepared once, shared by all chunks)
+    const bool mma = sorted && dp == 128 && k <= 16 && getenv("VT_NO_MMA") == nullptr;
+    void *prepared = nullptr;
+    bool use_mma = false;
     constexpr int NS = 3;
     cudaStream_t st[NS] = {};
     void *dbuf[NS] = {};
@@ -134,6 +144,7 @@ extern "C" int vt_quantize_host(const void *h_desc, int dtype, int64_t n, int dp
             if (dbuf[s]) cudaFree(dbuf[s]);
             if (wbuf[s]) cudaFree(wbuf[s]);
             if (work[s]) cudaFree(work[s]);
+            if (s == 0 && prepared) cudaFree(prepared);
         }
     };
     for (int s = 0; s < NS; ++s) {
@@ -146,6 +157,23 @@ extern "C" int vt_quantize_host(const void *h_desc, int dtype, int64_t n, int dp
             return VT_ENOMEM;
         }
     }
+    if (mma) {
+        if (cudaMalloc(&prepared, (size_t)vt_mma_prepared_bytes(k, depth)) != cudaSuccess) {
+            vt_set_error("vt_quantize_host: plane allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+            cleanup();
+            return VT_ENOMEM;
+        }
+        // the tensor path needs every child centroid inside the 8.16 fixed-point range: the prepare
+        // kernel counts violations and the chunks fall back to the FP32 kernels if there is one
+        unsigned long long *d_flag = nullptr, h_flag[4] = {0, 0, 0, 0};
+        if (cudaMalloc((void **)&d_flag, sizeof h_flag) != cudaSuccess || cudaMemsetAsync(d_flag, 0, sizeof h_flag, st[0]) != cudaSuccess)
+            rc = VT_ENOMEM;
+        if (rc == VT_OK) rc = vt_mma_prepare(d_centroids, k, depth, prepared, (uint64_t *)d_flag, st[0]);
+        if (rc == VT_OK && (cudaMemcpyAsync(h_flag, d_flag, sizeof h_flag, cudaMemcpyDeviceToHost, st[0]) != cudaSuccess ||
+                            cudaStreamSynchronize(st[0]) != cudaSuccess)) rc = VT_ECUDA;
+        if (d_flag) cudaFree(d_flag);
+        use_mma = rc == VT_OK && h_flag[1] == 0;
+    }
     int64_t done = 0;
     for (int c = 0; done < n && rc == VT_OK; ++c, done += chunk_rows) {
         const int s = c % NS;
@@ -156,7 +184,10 @@ extern "C" int vt_quantize_host(const void *h_desc, int dtype, int64_t n, int dp
             rc = VT_ECUDA;
             break;
         }
-        if (sorted && rows >= ((int64_t)1 << 16))
+        if (use_mma && rows >= ((int64_t)1 << 16))
+            rc = vt_mma_levels(dbuf[s], rows, d_centroids, d_internal, d_ref_id, k, depth, nullptr, wbuf[s], nullptr, prepared,
+                               work[s], st[s], nullptr, nullptr);
+        else if (sorted && rows >= ((int64_t)1 << 16))
             rc = vt_quantize_sorted_impl(dbuf[s], rows, dp, d_centroids, d_internal, d_ref_id, k, depth, nullptr, wbuf[s],
                                          nullptr, work[s], st[s], nullptr);
         else

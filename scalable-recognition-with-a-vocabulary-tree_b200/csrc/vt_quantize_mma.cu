@@ -280,6 +280,8 @@ int bits_for_mma(uint64_t max_value)
 }
 }  // namespace
 
+int64_t vt_mma_prepared_bytes(int k, int depth);
+
 static int64_t mma_int_nodes(int k, int depth)
 {
     int64_t n = 0, p = 1;
@@ -292,34 +294,46 @@ extern "C" int64_t vt_quantize_mma_work_bytes(int64_t n, int k, int depth)
     if (n < 1) n = 1;
     int64_t n_heap = 0, p = 1;
     for (int l = 0; l <= depth; ++l) { n_heap += p; p *= k; }
-    const int64_t planes = ((mma_int_nodes(k, depth) * MM_B_BYTES + 255) / 256) * 256;
-    const int64_t norms = ((n_heap * 8 + 255) / 256) * 256;
-    return planes + norms + 16 * n + vt_sort_scratch_bytes(n);
+    (void)n_heap;
+    return vt_mma_prepared_bytes(k, depth) + 16 * n + vt_sort_scratch_bytes(n);
 }
 
-int vt_quantize_mma_impl(const void *d_desc, int64_t n, const float *cent, const uint8_t *internal, const int32_t *ref_id,
-                         int k, int depth, int32_t *leaf, int32_t *word, uint64_t *stats, void *work, cudaStream_t s,
-                         cudaEvent_t *ev)
+// byte planes + fixed-point norms for the whole tree (once per call / per tree)
+int vt_mma_prepare(const float *cent, int k, int depth, void *planes_and_norms, uint64_t *stats, cudaStream_t s)
 {
-    int n_ev = 0;
+    const int64_t n_int = mma_int_nodes(k, depth);
+    uint8_t *bimg = (uint8_t *)planes_and_norms;
+    const int64_t planes = ((n_int * MM_B_BYTES + 255) / 256) * 256;
+    unsigned long long *cn = (unsigned long long *)(bimg + planes);
+    const int64_t cap = (int64_t)vt_sm_count() * 16;
+    prep_planes_kernel<<<(int)(n_int < cap ? n_int : cap), 128, 0, s>>>(cent, n_int, k, bimg, cn, (unsigned long long *)stats);
+    VT_LAUNCH_CHECK();
+    return VT_OK;
+}
+
+int64_t vt_mma_prepared_bytes(int k, int depth)
+{
+    int64_t n_heap = 0, p = 1;
+    for (int l = 0; l <= depth; ++l) { n_heap += p; p *= k; }
+    return ((mma_int_nodes(k, depth) * MM_B_BYTES + 255) / 256) * 256 + ((n_heap * 8 + 255) / 256) * 256;
+}
+
+// the level loop; `prepared` from vt_mma_prepare, `sortwork` = 16 n + vt_sort_scratch_bytes(n) bytes
+int vt_mma_levels(const void *d_desc, int64_t n, const float *cent, const uint8_t *internal, const int32_t *ref_id, int k,
+                  int depth, int32_t *leaf, int32_t *word, uint64_t *stats, const void *prepared, void *sortwork,
+                  cudaStream_t s, cudaEvent_t *ev, int *n_ev_io)
+{
+    int n_ev = n_ev_io ? *n_ev_io : 0;
 #define VT_MARK() do { if (ev) VT_CUDA(cudaEventRecord(ev[n_ev++], s)); } while (0)
     int64_t n_heap = 0, pw = 1;
     for (int l = 0; l <= depth; ++l) { n_heap += pw; pw *= k; }
     const int64_t n_int = mma_int_nodes(k, depth);
-    uint8_t *bimg = (uint8_t *)work;
+    const uint8_t *bimg = (const uint8_t *)prepared;
     const int64_t planes = ((n_int * MM_B_BYTES + 255) / 256) * 256;
-    unsigned long long *cn = (unsigned long long *)(bimg + planes);
-    const int64_t norms = ((n_heap * 8 + 255) / 256) * 256;
-    uint32_t *kA = (uint32_t *)((uint8_t *)cn + norms), *kB = kA + n, *pA = kB + n, *pB = pA + n;
+    const unsigned long long *cn = (const unsigned long long *)(bimg + planes);
+    uint32_t *kA = (uint32_t *)sortwork, *kB = kA + n, *pA = kB + n, *pB = pA + n;
     void *hist = (void *)(pB + n);
     const uint8_t *desc = (const uint8_t *)d_desc;
-
-    VT_MARK();
-    {
-        const int64_t cap = (int64_t)vt_sm_count() * 16;
-        prep_planes_kernel<<<(int)(n_int < cap ? n_int : cap), 128, 0, s>>>(cent, n_int, k, bimg, cn, (unsigned long long *)stats);
-        VT_LAUNCH_CHECK();
-    }
     static bool attr_set = false;
     const int smem = MM_A_BYTES + MM_B_BYTES + 1024;
     if (!attr_set) {
@@ -354,7 +368,20 @@ int vt_quantize_mma_impl(const void *d_desc, int64_t n, const float *cent, const
         n_nodes *= (uint64_t)k;
     }
 #undef VT_MARK
+    if (n_ev_io) *n_ev_io = n_ev;
     return VT_OK;
+}
+
+int vt_quantize_mma_impl(const void *d_desc, int64_t n, const float *cent, const uint8_t *internal, const int32_t *ref_id,
+                         int k, int depth, int32_t *leaf, int32_t *word, uint64_t *stats, void *work, cudaStream_t s,
+                         cudaEvent_t *ev)
+{
+    int n_ev = 0;
+    if (ev) VT_CUDA(cudaEventRecord(ev[n_ev++], s));           // the first stage includes the plane preparation
+    int rc = vt_mma_prepare(cent, k, depth, work, stats, s);
+    if (rc != VT_OK) return rc;
+    return vt_mma_levels(d_desc, n, cent, internal, ref_id, k, depth, leaf, word, stats, work,
+                         (uint8_t *)work + vt_mma_prepared_bytes(k, depth), s, ev, &n_ev);
 }
 
 // Same contract as vt_quantize_sorted (bit-identical ids); tensor-core distance step.

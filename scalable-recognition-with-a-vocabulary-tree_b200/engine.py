@@ -94,7 +94,8 @@ def quantize(tree_dev: dict, k: int, depth: int, desc: torch.Tensor, want_heap: 
     word = torch.empty(n, dtype=torch.int32, device=desc.device)
     leaf = torch.empty(n, dtype=torch.int32, device=desc.device) if want_heap else None
     if method == "auto":
-        method = "sorted" if (desc.dtype == torch.uint8 and start == 0 and n >= SORTED_MIN_ROWS and depth >= 2) else "fused"
+        big = desc.dtype == torch.uint8 and start == 0 and n >= SORTED_MIN_ROWS and depth >= 2
+        method = ("mma" if tree_dev.get("mma_ok", False) else "sorted") if big else "fused"
     if method == "mma":
         need = int(lib.vt_quantize_mma_work_bytes(n, k, depth))
         if work is None or work.numel() * work.element_size() < need:

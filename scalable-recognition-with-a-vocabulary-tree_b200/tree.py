@@ -96,6 +96,7 @@ class FlatTree:
         key = str(device)
         if key not in self._dev:
             self._dev[key] = dict(
+                mma_ok=self.mma_ok(),
                 centroids=torch.from_numpy(self.centroids).to(device),
                 internal=torch.from_numpy(self.internal).to(device),
                 ref_id=torch.from_numpy(self.ref_id).to(device),
@@ -109,11 +110,20 @@ class FlatTree:
         import torch
         key = str(torch.device(device))
         self._dev[key] = dict(
+            mma_ok=self.mma_ok(),
             centroids=centroids, internal=internal,
             ref_id=torch.from_numpy(self.ref_id).to(device),
             parent_ref=torch.from_numpy(self.parent_ref).to(device),
             level_ref=torch.from_numpy(self.level_ref).to(device),
         )
+
+    def mma_ok(self) -> bool:
+        """The tensor-core descent (vt_quantize_mma) needs 128-byte rows, k <= 16 and every centroid
+        inside the 8.16 fixed-point range -- true for any tree built from byte descriptors."""
+        if self.DP != 128 or self.k > 16 or self.depth < 1:
+            return False
+        c = self.centroids
+        return bool(c.size == 0 or (float(c.min()) >= 0.0 and float(c.max()) <= 255.99))
 
     # ------------------------------------------------------------------ reference views
     def nodes_dict(self) -> dict:
