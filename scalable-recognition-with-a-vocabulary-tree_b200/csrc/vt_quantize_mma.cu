@@ -80,7 +80,7 @@ prep_planes_kernel(const float *__restrict__ cent, int64_t n_int, int k, uint8_t
 }
 
 // ---- one tree level -------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MM_TILE)
+__global__ void __launch_bounds__(MM_TILE, 8)
 level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ parent,
                  int64_t n, uint32_t n_nodes, int64_t level_off, int64_t n_heap, int k, int is_last,
                  const float *__restrict__ cent, const uint8_t *__restrict__ internal, const int32_t *__restrict__ ref_id,
@@ -235,11 +235,12 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
         // provable margin for the centroid rounding; contested rows go to canonical binary64
         bool contested = false;
         if (is_int && k > 1) {
-            const double xn2 = (double)xn;
-            const double d2a = fmax(0.0, (double)best * 2.3283064365386963e-10 + xn2);
-            const double d2b = fmax(0.0, (double)second * 2.3283064365386963e-10 + xn2);
-            const double margin = 1.52587890625e-05 * 11.313708498984761 * 1.02 * (sqrt(d2a) + sqrt(d2b)) + 1e-6;
-            contested = (double)(second - best) * 2.3283064365386963e-10 <= margin;
+            // |error| <= m * (da + db) + tiny with m = 2^-16 * sqrt(128) * 1.02 and da <= db, so
+            // "gap <= 2 m db + 1e-6" is a safe (slightly wider) test; squared to avoid the square roots
+            const double d2b = fmax(0.0, (double)second * 2.3283064365386963e-10 + (double)xn);
+            const double gap = (double)(second - best) * 2.3283064365386963e-10 - 1e-6;
+            const double two_m = 2.0 * 1.52587890625e-05 * 11.313708498984761 * 1.02;
+            contested = gap <= 0.0 || gap * gap <= two_m * two_m * d2b;
         }
         unsigned int m = __ballot_sync(VT_FULL, contested);
         while (m) {
@@ -340,7 +341,7 @@ int vt_mma_levels(const void *d_desc, int64_t n, const float *cent, const uint8_
         VT_CUDA(cudaFuncSetAttribute(level_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    const int64_t want = (n + MM_TILE - 1) / MM_TILE, cap = (int64_t)vt_sm_count() * 7;
+    const int64_t want = (n + MM_TILE - 1) / MM_TILE, cap = (int64_t)vt_sm_count() * 8;
     const int blocks = (int)(want < cap ? want : cap);
     uint32_t *keys = kA, *perm = pA, *tkeys = kB, *tperm = pB;
     const uint32_t *cur_perm = nullptr, *cur_parent = nullptr;
