@@ -256,8 +256,8 @@ def main():
 
     level_ms, sort_ms = stage_profile(lib.vt_quantize_mma_profile if method == "mma" else lib.vt_quantize_sorted_profile)
     other_ms, _ = stage_profile(lib.vt_quantize_sorted_profile if method == "mma" else lib.vt_quantize_mma_profile, reps=1)
-    sort_passes = sum(-(-int(K_BRANCH ** (l + 1)).bit_length() // 8) for l in range(DEPTH - 1))
-    launches_per_step = DEPTH + 3 * sort_passes
+    sort_passes = DEPTH - 1                     # packed paths: one radix pass (hist, scan, scatter) per level transition
+    launches_per_step = DEPTH + 3 * sort_passes + (1 if method == "mma" else 0)
 
     # the single-launch fused descent on a slice, for comparison
     n_f = min(n, 8_000_000)

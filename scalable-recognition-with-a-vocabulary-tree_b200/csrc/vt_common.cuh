@@ -137,3 +137,23 @@ __device__ __forceinline__ int descend_one_level(const float4 (&x)[DP / 32], con
     }
     return arg;
 }
+
+// ---- packed descent paths (level-synchronous kernels) ---------------------------------------------
+// Between levels the batch only has to be GROUPED by node, not ordered by node index.  A row's key is
+// its path from the root packed `bits` bits per level, newest child index in the low bits; one stable
+// radix pass over the low 8 bits groups the rows by their new node (rows of one node were contiguous
+// before the pass and share all digits, so they stay contiguous inside their new digit class).  A row
+// that stopped at a leaf of a ragged tree carries the all-ones digit and sorts to the end of its class.
+__host__ __device__ __forceinline__ int path_bits(int k)
+{
+    int b = 1;
+    while ((1 << b) - 1 < k) ++b;          // labels 0..k-1 plus the all-ones "stopped" marker
+    return b;
+}
+__device__ __forceinline__ long long path_to_heap(uint32_t path, int level, int bits, int k)
+{
+    const uint32_t mask = (1u << bits) - 1u;
+    long long h = 0;
+    for (int i = level - 1; i >= 0; --i) h = h * k + 1 + (long long)((path >> (bits * i)) & mask);
+    return h;
+}

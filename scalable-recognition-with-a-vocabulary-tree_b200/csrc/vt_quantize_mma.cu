@@ -82,7 +82,7 @@ prep_planes_kernel(const float *__restrict__ cent, int64_t n_int, int k, uint8_t
 // ---- one tree level -------------------------------------------------------------------------------
 __global__ void __launch_bounds__(MM_TILE, 8)
 level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ parent,
-                 int64_t n, uint32_t n_nodes, int64_t level_off, int64_t n_heap, int k, int is_last,
+                 int64_t n, int level, int bits, int64_t n_heap, int k, int is_last,
                  const float *__restrict__ cent, const uint8_t *__restrict__ internal, const int32_t *__restrict__ ref_id,
                  const uint8_t *__restrict__ bimg, const unsigned long long *__restrict__ cn,
                  uint32_t *__restrict__ keys_out, uint32_t *__restrict__ perm_out, int32_t *__restrict__ leaf_out,
@@ -99,7 +99,7 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
     __shared__ long long s_min[4];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t sentinel = n_nodes * (uint32_t)k;
+    const uint32_t dmask = (1u << bits) - 1u;                    // all-ones digit = "stopped at a leaf"
     const long long none = 0x7fffffffffffffffLL;
     unsigned int rechecks = 0;
 
@@ -123,9 +123,9 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
         const int64_t p = base + tid;
         const bool valid = p < n;
         const uint32_t row = valid ? (perm ? perm[p] : (uint32_t)p) : 0u;
-        const uint32_t jp = valid ? (parent ? parent[p] : 0u) : sentinel;
-        const bool alive = valid && jp < n_nodes;
-        const long long node = level_off + (alive ? jp : 0u);
+        const uint32_t jp = valid && parent ? parent[p] : 0u;    // packed path from the root
+        const bool alive = valid && (level == 0 || (jp & dmask) != dmask);
+        const long long node = alive ? path_to_heap(jp, level, bits, k) : 0;
         const bool is_int = alive && (node * k + k < n_heap) && internal[node];
         const uint8_t *xrow = desc + (size_t)row * 128;
         if (alive && !is_int) {                                  // ragged tree: this node is a leaf
@@ -252,14 +252,14 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
                                                             cent + (size_t)(nq * k + 1) * 128, k, lane);
             if (lane == src) { arg = res; ++rechecks; }
         }
-        uint32_t key = sentinel;
+        uint32_t key = (jp << bits) | dmask;                     // stopped
         if (is_int) {
             const long long child = node * k + 1 + arg;
             if (is_last || !((child * k + k < n_heap) && internal[child])) {
                 if (leaf_out) leaf_out[row] = (int32_t)child;
                 if (word_out) word_out[row] = ref_id[child];
             } else {
-                key = jp * (uint32_t)k + (uint32_t)arg;
+                key = (jp << bits) | (uint32_t)arg;              // path of the child
             }
         }
         if (valid && keys_out) { keys_out[p] = key; perm_out[p] = row; }
@@ -273,12 +273,6 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(MM_TMEM_COLS));
 }
 
-int bits_for_mma(uint64_t max_value)
-{
-    int b = 0;
-    while (max_value) { ++b; max_value >>= 1; }
-    return b;
-}
 }  // namespace
 
 int64_t vt_mma_prepared_bytes(int k, int depth);
@@ -345,14 +339,13 @@ int vt_mma_levels(const void *d_desc, int64_t n, const float *cent, const uint8_
     const int blocks = (int)(want < cap ? want : cap);
     uint32_t *keys = kA, *perm = pA, *tkeys = kB, *tperm = pB;
     const uint32_t *cur_perm = nullptr, *cur_parent = nullptr;
-    int64_t level_off = 0;
-    uint64_t n_nodes = 1;
+    const int bits = path_bits(k);
     for (int level = 0; level < depth; ++level) {
         const int is_last = level + 1 == depth;
         uint32_t *keys_out = is_last ? nullptr : (level == 0 ? keys : tkeys);
         uint32_t *perm_out = is_last ? nullptr : (level == 0 ? perm : tperm);
         if (level > 0) VT_MARK();
-        level_mma_kernel<<<blocks, MM_TILE, smem, s>>>(desc, cur_perm, cur_parent, n, (uint32_t)n_nodes, level_off, n_heap, k,
+        level_mma_kernel<<<blocks, MM_TILE, smem, s>>>(desc, cur_perm, cur_parent, n, level, bits, n_heap, k,
                                                        is_last, cent, internal, ref_id, bimg, cn, keys_out, perm_out, leaf,
                                                        word, (unsigned long long *)stats);
         VT_LAUNCH_CHECK();
@@ -360,13 +353,12 @@ int vt_mma_levels(const void *d_desc, int64_t n, const float *cent, const uint8_
         if (is_last) break;
         if (level > 0) { uint32_t *t; t = keys; keys = tkeys; tkeys = t; t = perm; perm = tperm; tperm = t; }
         int flip = 0;
-        const int rc = vt_sort_pairs_impl(keys, perm, tkeys, tperm, n, bits_for_mma(n_nodes * (uint64_t)k), hist, &flip, s);
+        // ONE stable pass over the low 8 bits of the packed paths groups the rows by their new node
+        const int rc = vt_sort_pairs_impl(keys, perm, tkeys, tperm, n, 8, hist, &flip, s);
         if (rc != VT_OK) return rc;
         if (flip) { uint32_t *t; t = keys; keys = tkeys; tkeys = t; t = perm; perm = tperm; tperm = t; }
         cur_parent = keys;
         cur_perm = perm;
-        level_off += (int64_t)n_nodes;
-        n_nodes *= (uint64_t)k;
     }
 #undef VT_MARK
     if (n_ev_io) *n_ev_io = n_ev;
@@ -397,11 +389,7 @@ extern "C" int vt_quantize_mma(const void *d_desc, int dtype, int64_t n, int dp,
     VT_CHECK_ARG(d_centroids && d_internal, "null tree");
     VT_CHECK_ARG(d_word == nullptr || d_ref_id != nullptr, "d_word needs d_ref_id");
     VT_CHECK_ARG(d_work && work_bytes >= vt_quantize_mma_work_bytes(n, k, depth), "workspace too small");
-    {
-        double rows = 1.0;
-        for (int l = 0; l < depth; ++l) rows *= k;
-        VT_CHECK_ARG(rows < 4.0e9, "k^depth must fit 32 bits");
-    }
+    VT_CHECK_ARG((depth - 1) * path_bits(k) <= 32, "k / depth too large for 32-bit packed paths");
     if (n == 0) return VT_OK;
     return vt_quantize_mma_impl(d_desc, n, d_centroids, d_internal, d_ref_id, k, depth, d_leaf_heap, d_word, d_stats, d_work,
                                 (cudaStream_t)stream, nullptr);

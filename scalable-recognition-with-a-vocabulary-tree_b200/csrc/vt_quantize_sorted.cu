@@ -85,7 +85,7 @@ __device__ __forceinline__ void tile_dists(const uint8_t *const (&xrow)[R], cons
 template <int DP, int R>
 __global__ void __launch_bounds__(256, R >= 4 ? 2 : (R == 2 ? 3 : 4))
 level_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ parent,
-             int64_t n, uint32_t n_nodes, int64_t level_off, int64_t n_heap, int k, int is_last,
+             int64_t n, int level, int bits, int64_t n_heap, int k, int is_last,
              const float *__restrict__ cent, const uint8_t *__restrict__ internal, const int32_t *__restrict__ ref_id,
              uint32_t *__restrict__ keys_out, uint32_t *__restrict__ perm_out, int32_t *__restrict__ leaf_out,
              int32_t *__restrict__ word_out, unsigned long long *__restrict__ stats)
@@ -93,7 +93,7 @@ level_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ perm
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const uint32_t sentinel = n_nodes * (uint32_t)k;
+    const uint32_t dmask = (1u << bits) - 1u;                    // all-ones digit = "stopped at a leaf"
     const float inf = __int_as_float(0x7f800000);
     const long long none = 0x7fffffffffffffffLL;
     unsigned int rechecks = 0;
@@ -108,9 +108,9 @@ level_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ perm
             const int64_t p = base + r * 32 + lane;
             valid[r] = p < n;
             row[r] = valid[r] ? (perm ? perm[p] : (uint32_t)p) : 0u;
-            jp[r] = valid[r] ? (parent ? parent[p] : 0u) : sentinel;
-            const bool alive = valid[r] && jp[r] < n_nodes;      // not yet stopped at a leaf
-            node[r] = level_off + (alive ? jp[r] : 0u);
+            jp[r] = valid[r] && parent ? parent[p] : 0u;         // packed path from the root
+            const bool alive = valid[r] && (level == 0 || (jp[r] & dmask) != dmask);   // not yet stopped at a leaf
+            node[r] = alive ? path_to_heap(jp[r], level, bits, k) : 0;
             is_int[r] = alive && (node[r] * k + k < n_heap) && internal[node[r]];
             xrow[r] = desc + (size_t)row[r] * DP;
             if (alive && !is_int[r]) {                           // ragged tree: this node is a leaf
@@ -181,14 +181,14 @@ level_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ perm
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int64_t p = base + r * 32 + lane;
-            uint32_t key = sentinel;
+            uint32_t key = (jp[r] << bits) | dmask;                         // stopped
             if (is_int[r]) {
                 const long long child = node[r] * k + 1 + arg[r];
                 if (is_last || !((child * k + k < n_heap) && internal[child])) {
                     if (leaf_out) leaf_out[row[r]] = (int32_t)child;      // the child is a leaf: stop here
                     if (word_out) word_out[row[r]] = ref_id[child];
                 } else {
-                    key = jp[r] * (uint32_t)k + (uint32_t)arg[r];          // index of the child inside the next level
+                    key = (jp[r] << bits) | (uint32_t)arg[r];              // path of the child
                 }
             }
             if (valid[r] && keys_out) { keys_out[p] = key; perm_out[p] = row[r]; }
@@ -201,7 +201,7 @@ level_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ perm
 
 template <int DP>
 void launch_level(int r_tile, int blocks_cap_per_sm, const uint8_t *desc, const uint32_t *perm, const uint32_t *parent,
-                  int64_t n, uint32_t n_nodes, int64_t level_off, int64_t n_heap, int k, int is_last, const float *cent,
+                  int64_t n, int level, int bits, int64_t n_heap, int k, int is_last, const float *cent,
                   const uint8_t *internal, const int32_t *ref_id, uint32_t *keys_out, uint32_t *perm_out, int32_t *leaf,
                   int32_t *word, unsigned long long *stats, cudaStream_t s)
 {
@@ -209,8 +209,8 @@ void launch_level(int r_tile, int blocks_cap_per_sm, const uint8_t *desc, const 
 #define VT_LAUNCH_R(RV)                                                                                         \
     {                                                                                                           \
         const int64_t want = (n + 256 * RV - 1) / (256 * RV);                                                   \
-        level_kernel<DP, RV><<<(int)(want < cap ? want : cap), 256, 0, s>>>(desc, perm, parent, n, n_nodes,     \
-            level_off, n_heap, k, is_last, cent, internal, ref_id, keys_out, perm_out, leaf, word, stats);      \
+        level_kernel<DP, RV><<<(int)(want < cap ? want : cap), 256, 0, s>>>(desc, perm, parent, n, level,       \
+            bits, n_heap, k, is_last, cent, internal, ref_id, keys_out, perm_out, leaf, word, stats);           \
     }
     if (r_tile >= 4) VT_LAUNCH_R(4)
     else if (r_tile == 2) VT_LAUNCH_R(2)
@@ -231,13 +231,6 @@ int pick_r(int64_t n, uint64_t n_nodes)
     return seg >= 192.0 ? 2 : 1;        // measured on B200: R=2 (24 warps/SM) beats R=4 (16 warps/SM); VT_QS_R overrides
 }
 
-int bits_for(uint64_t max_value)
-{
-    int b = 0;
-    while (max_value) { ++b; max_value >>= 1; }
-    return b;
-}
-
 template <int DP>
 int run_sorted(const uint8_t *desc, int64_t n, const float *cent, const uint8_t *internal, const int32_t *ref_id, int k,
                int depth, int32_t *leaf, int32_t *word, uint64_t *stats, void *work, cudaStream_t s,
@@ -250,14 +243,14 @@ int run_sorted(const uint8_t *desc, int64_t n, const float *cent, const uint8_t 
     uint32_t *kA = (uint32_t *)work, *kB = kA + n, *pA = kB + n, *pB = pA + n;
     void *hist = (void *)(pB + n);
     if (depth == 0) {                                            // the root is the only node
-        launch_level<DP>(1, 16, desc, nullptr, nullptr, n, 1u, 0, n_heap, k, 1, cent, internal, ref_id, nullptr, nullptr,
-                         leaf, word, (unsigned long long *)stats, s);
+        launch_level<DP>(1, 16, desc, nullptr, nullptr, n, 0, path_bits(k), n_heap, k, 1, cent, internal, ref_id, nullptr,
+                         nullptr, leaf, word, (unsigned long long *)stats, s);
         VT_LAUNCH_CHECK();
         return VT_OK;
     }
     uint32_t *keys = kA, *perm = pA, *tkeys = kB, *tperm = pB;
     const uint32_t *cur_perm = nullptr, *cur_parent = nullptr;
-    int64_t level_off = 0;
+    const int bits = path_bits(k);
     uint64_t n_nodes = 1;
     for (int level = 0; level < depth; ++level) {
         const int is_last = level + 1 == depth;
@@ -265,19 +258,19 @@ int run_sorted(const uint8_t *desc, int64_t n, const float *cent, const uint8_t 
         uint32_t *keys_out = is_last ? nullptr : (level == 0 ? keys : tkeys);
         uint32_t *perm_out = is_last ? nullptr : (level == 0 ? perm : tperm);
         VT_MARK();
-        launch_level<DP>(pick_r(n, n_nodes), 16, desc, cur_perm, cur_parent, n, (uint32_t)n_nodes, level_off, n_heap, k,
+        launch_level<DP>(pick_r(n, n_nodes), 16, desc, cur_perm, cur_parent, n, level, bits, n_heap, k,
                          is_last, cent, internal, ref_id, keys_out, perm_out, leaf, word, (unsigned long long *)stats, s);
         VT_LAUNCH_CHECK();
         VT_MARK();
         if (is_last) break;
         if (level > 0) { uint32_t *t; t = keys; keys = tkeys; tkeys = t; t = perm; perm = tperm; tperm = t; }
         int flip = 0;
-        const int rc = vt_sort_pairs_impl(keys, perm, tkeys, tperm, n, bits_for(n_nodes * (uint64_t)k), hist, &flip, s);
+        // ONE stable pass over the low 8 bits of the packed paths groups the rows by their new node
+        const int rc = vt_sort_pairs_impl(keys, perm, tkeys, tperm, n, 8, hist, &flip, s);
         if (rc != VT_OK) return rc;
         if (flip) { uint32_t *t; t = keys; keys = tkeys; tkeys = t; t = perm; perm = tperm; tperm = t; }
         cur_parent = keys;
         cur_perm = perm;
-        level_off += (int64_t)n_nodes;
         n_nodes *= (uint64_t)k;
     }
 #undef VT_MARK
@@ -302,11 +295,7 @@ extern "C" int vt_quantize_sorted(const void *d_desc, int dtype, int64_t n, int 
     VT_CHECK_ARG(d_centroids && d_internal, "null tree");
     VT_CHECK_ARG(d_word == nullptr || d_ref_id != nullptr, "d_word needs d_ref_id");
     VT_CHECK_ARG(d_work && work_bytes >= vt_quantize_sorted_work_bytes(n), "workspace too small");
-    {
-        double rows = 1.0;
-        for (int l = 0; l < depth; ++l) rows *= k;
-        VT_CHECK_ARG(rows < 4.0e9, "k^depth must fit 32 bits");
-    }
+    VT_CHECK_ARG(path_bits(k) <= 8 && (depth - 1) * path_bits(k) <= 32, "k / depth too large for 32-bit packed paths");
     return vt_quantize_sorted_impl(d_desc, n, dp, d_centroids, d_internal, d_ref_id, k, depth, d_leaf_heap, d_word,
                                    d_stats, d_work, (cudaStream_t)stream, nullptr);
 }
