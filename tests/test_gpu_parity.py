@@ -419,3 +419,77 @@ def test_notebook_flow_matches_reference(vt, cuda, name):
     sha = vt.utils.get_image_id(ds.read_image(ds.image_paths[0]))
     got0 = {n_: d_[sha] for n_, d_ in post.items() if sha in d_}
     assert got0 == {int(n_): int(c) for n_, c in enumerate(g["counts"][0]) if c > 0}
+
+
+# ------------------------------------------------------------------------------------------ full size
+def test_full_size_quantize_properties(vt, cuda):
+    """BASELINE configs[2] shape at a size the oracle cannot check row by row (20 M x 128 through a
+    1,111,111-node tree): size-independent properties + an oracle spot check.
+    * all three engines (fused / sorted SIMT / tcgen05) agree on every row;
+    * the result does not depend on how the batch is chunked or ordered (permutation equivariance);
+    * a checksum of checksums over chunks equals the whole-batch checksum;
+    * every word is a deepest-level node; a 50 k sample equals the binary64 oracle."""
+    torch = _torch()
+    k, depth, d, n = 10, 6, 128, 20_000_000
+    cent = vt.synth.hierarchical_tree(k, depth, d, seed=7, device=cuda)
+    nh = vt.tree.heap_size(k, depth)
+    exists = np.ones(nh, np.uint8)
+    internal = np.zeros(nh, np.uint8)
+    internal[:vt.tree.level_offset(k, depth)] = 1
+    ref_id, n_ref = vt.tree.reference_ids(exists, internal, k, depth)
+    tree_dev = dict(centroids=cent, internal=torch.from_numpy(internal).to(cuda), ref_id=torch.from_numpy(ref_id).to(cuda))
+    desc = vt.synth.descriptors_from_tree(cent, k, depth, n, seed=3)
+    w_mma = vt.engine.quantize(tree_dev, k, depth, desc, method="mma")
+    w_sorted = vt.engine.quantize(tree_dev, k, depth, desc, method="sorted")
+    assert torch.equal(w_mma, w_sorted)
+    w_fused = vt.engine.quantize(tree_dev, k, depth, desc[:4_000_000], method="fused")
+    assert torch.equal(w_fused, w_mma[:4_000_000])
+    # chunk invariance + checksum of checksums
+    total = int(w_mma.to(torch.int64).sum().item())
+    parts = 0
+    for lo in range(0, n, 7_000_003):
+        hi = min(n, lo + 7_000_003)
+        wc = vt.engine.quantize(tree_dev, k, depth, desc[lo:hi], method="mma")
+        assert torch.equal(wc, w_mma[lo:hi])
+        parts += int(wc.to(torch.int64).sum().item())
+    assert parts == total
+    # permutation equivariance
+    perm = torch.randperm(2_000_000, device=cuda)
+    wp = vt.engine.quantize(tree_dev, k, depth, desc[:2_000_000][perm].contiguous(), method="mma")
+    assert torch.equal(wp, w_mma[:2_000_000][perm])
+    # words are leaves of the full tree
+    leaf_ids = torch.from_numpy(ref_id[vt.tree.level_offset(k, depth):]).to(cuda)
+    assert bool(torch.isin(w_mma[:1_000_000], leaf_ids).all().item())
+    # oracle spot check
+    sample = torch.randint(0, n, (50_000,), device=cuda)
+    ot = dict(k=k, depth=depth, D=d, DP=d, centroids=cent.cpu().numpy(), exists=exists, internal=internal,
+              ref_id=ref_id, n_ref=n_ref)
+    want = ref_id[vo.descend(ot, desc[sample].cpu().numpy())]
+    assert np.array_equal(w_mma[sample].cpu().numpy(), want)
+
+
+def test_full_size_retrieval_properties(vt, cuda):
+    """200 k-image inverted file (25 shards): every database image queried against the index ranks
+    itself first with score exactly 0, scores ascend, and top-k is a prefix of top-(k+5)."""
+    torch = _torch()
+    rng = np.random.default_rng(4)
+    n_img, n_ref, wpi = 200_000, 1_111_111, 300
+    words = torch.from_numpy(rng.integers(1, n_ref, n_img * wpi).astype(np.int32)).to(cuda)
+    off = torch.arange(n_img + 1, dtype=torch.int64, device=cuda) * wpi
+    dummy = dict(parent_ref=torch.zeros(1, dtype=torch.int32, device=cuda), level_ref=torch.zeros(1, dtype=torch.uint8, device=cuda))
+    csr = vt.engine.encode(words, off, dummy, 6, n_ref, all_nodes=False)
+    index = vt.engine.build_index(csr, n_ref)
+    assert index["n_shards"] == 25
+    q_rows = torch.from_numpy(rng.integers(0, n_img, 512)).to(cuda)
+    ro = csr["row_off"]
+    sizes = (ro[q_rows + 1] - ro[q_rows])
+    qoff = torch.zeros(len(q_rows) + 1, dtype=torch.int64, device=cuda)
+    qoff[1:] = torch.cumsum(sizes, 0)
+    idx = torch.cat([torch.arange(int(ro[r]), int(ro[r + 1]), device=cuda) for r in q_rows.tolist()])
+    q = dict(row_off=qoff, node=csr["node"][idx].contiguous(), count=csr["count"][idx].contiguous(),
+             sumsq=csr["sumsq"][q_rows].contiguous(), n_img=len(q_rows), nnz=int(qoff[-1]))
+    o10 = vt.engine.score(index, q, 10)
+    o15 = vt.engine.score(index, q, 15)
+    assert torch.equal(o10["id"][:, 0].long(), q_rows) and bool((o10["score"][:, 0] == 0).all())
+    assert bool((o10["score"][:, 1:] >= o10["score"][:, :-1]).all())
+    assert torch.equal(o10["id"], o15["id"][:, :10])
