@@ -52,6 +52,7 @@ __device__ __forceinline__ void block_best(double &key, int32_t &id, int &owner,
 }
 
 constexpr uint32_t SC_LONG = 24;
+constexpr int SC_UNROLL = 4;
 
 template <int MODE>
 __device__ __forceinline__ void accumulate(int *s_acci, float *s_accf, const uint2 pe, const float qv)
@@ -73,7 +74,7 @@ score_shard_kernel(const uint32_t *__restrict__ post_off, const uint2 *__restric
                    const double *__restrict__ img_rnorm, int64_t n_img, int64_t n_ref, int n_shards,
                    const int64_t *__restrict__ q_off, const int32_t *__restrict__ q_node,
                    const float *__restrict__ q_val, int64_t n_query, int topk, double *__restrict__ out_key,
-                   int32_t *__restrict__ out_id, double *__restrict__ all_key)
+                   int32_t *__restrict__ out_id, double *__restrict__ all_key, const uint8_t *__restrict__ shard_empty)
 {
     constexpr int PER = R / SC_THREADS;
     extern __shared__ unsigned char s_raw[];
@@ -90,6 +91,9 @@ score_shard_kernel(const uint32_t *__restrict__ post_off, const uint2 *__restric
         const int shard = (int)(pair - q * n_shards);
         const int64_t img0 = (int64_t)shard * R;
         const int n_here = (int)((n_img - img0) < R ? (n_img - img0) : R);
+        // images the query does not touch have key 0 without looking at their norm -- unless the shard
+        // holds images without descriptors (key -1, score 1e6), which only the norm reveals
+        const bool lazy_norm = !all_key && shard_empty && !shard_empty[shard];
         for (int t = threadIdx.x; t < R; t += SC_THREADS) s_acci[t] = 0;
         __syncthreads();
         // accumulate: one LANE per query word (32 independent row-pointer / posting fetches in flight
@@ -97,27 +101,37 @@ score_shard_kernel(const uint32_t *__restrict__ post_off, const uint2 *__restric
         // SC_LONG are handed to the whole warp so that one lane never serialises a long list
         const int64_t qb = q_off[q], qe = q_off[q + 1];
         const uint32_t *off = post_off + (size_t)shard * n_ref;
-        for (int64_t w0 = qb + (int64_t)warp * 32; w0 < qe; w0 += SC_THREADS) {
-            const int64_t w = w0 + lane;
-            uint32_t b = 0, e = 0;
-            float qv = 0.f;
-            if (w < qe) {
-                const int32_t node = __ldg(q_node + w);
-                qv = __ldg(q_val + w);
-                b = __ldg(off + node);
-                e = __ldg(off + node + 1);
+        // SC_UNROLL words per lane are in flight together: the q_node -> row pointer -> posting chain is
+        // three dependent DRAM/L2 round trips, so independent chains are what hides the latency
+        for (int64_t w0 = qb + (int64_t)warp * 32; w0 < qe; w0 += (int64_t)SC_THREADS * SC_UNROLL) {
+            int32_t node[SC_UNROLL];
+            float qv[SC_UNROLL];
+            uint32_t b[SC_UNROLL], e[SC_UNROLL];
+#pragma unroll
+            for (int u = 0; u < SC_UNROLL; ++u) {
+                const int64_t w = w0 + (int64_t)u * SC_THREADS + lane;
+                node[u] = w < qe ? __ldg(q_node + w) : -1;
+                qv[u] = w < qe ? __ldg(q_val + w) : 0.f;
             }
-            const bool is_long = (e - b) > SC_LONG;
-            if (!is_long) {
-                for (uint32_t p = b; p < e; ++p) accumulate<MODE>(s_acci, s_accf, postings[p], qv);
+#pragma unroll
+            for (int u = 0; u < SC_UNROLL; ++u) {
+                b[u] = node[u] >= 0 ? __ldg(off + node[u]) : 0u;
+                e[u] = node[u] >= 0 ? __ldg(off + node[u] + 1) : 0u;
             }
-            unsigned int m = __ballot_sync(VT_FULL, is_long);
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const uint32_t lb = __shfl_sync(VT_FULL, b, src), le = __shfl_sync(VT_FULL, e, src);
-                const float lq = __shfl_sync(VT_FULL, qv, src);
-                for (uint32_t p = lb + lane; p < le; p += 32) accumulate<MODE>(s_acci, s_accf, postings[p], lq);
+#pragma unroll
+            for (int u = 0; u < SC_UNROLL; ++u) {
+                const bool is_long = (e[u] - b[u]) > SC_LONG;
+                if (!is_long) {
+                    for (uint32_t p = b[u]; p < e[u]; ++p) accumulate<MODE>(s_acci, s_accf, __ldg(postings + p), qv[u]);
+                }
+                unsigned int m = __ballot_sync(VT_FULL, is_long);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t lb = __shfl_sync(VT_FULL, b[u], src), le = __shfl_sync(VT_FULL, e[u], src);
+                    const float lq = __shfl_sync(VT_FULL, qv[u], src);
+                    for (uint32_t p = lb + lane; p < le; p += 32) accumulate<MODE>(s_acci, s_accf, __ldg(postings + p), lq);
+                }
             }
         }
         __syncthreads();
@@ -129,8 +143,13 @@ score_shard_kernel(const uint32_t *__restrict__ post_off, const uint2 *__restric
             double key = -2.0;                                                  // padding slots never win
             if (t < n_here) {
                 if (MODE == VT_SCORE_TF_L2) {
-                    const double rn = img_rnorm[img0 + t];
-                    key = rn < 0.0 ? -1.0 : (double)s_acci[t] * rn;
+                    const int a = s_acci[t];
+                    if (a == 0 && lazy_norm) {
+                        key = 0.0;
+                    } else {
+                        const double rn = img_rnorm[img0 + t];
+                        key = rn < 0.0 ? -1.0 : (double)a * rn;
+                    }
                 } else {
                     const double rn = img_rnorm ? img_rnorm[img0 + t] : 1.0;
                     key = rn < 0.0 ? -1.0 : (double)s_accf[t];
@@ -256,7 +275,8 @@ extern "C" int vt_rnorm(const uint64_t *d_sumsq, int64_t n, double *d_rnorm, voi
 template <int MODE>
 static int launch_score(const uint32_t *post_off, const void *postings, const double *img_rnorm, int64_t n_img,
                         int64_t n_ref, const int64_t *q_off, const int32_t *q_node, const float *q_val, int64_t n_query,
-                        int topk, double *out_key, int32_t *out_id, double *all_key, cudaStream_t s)
+                        int topk, double *out_key, int32_t *out_id, double *all_key, const uint8_t *shard_empty,
+                        cudaStream_t s)
 {
     constexpr int R = 8192;
     const int n_shards = (int)((n_img + R - 1) / R);
@@ -267,7 +287,7 @@ static int launch_score(const uint32_t *post_off, const void *postings, const do
     const int64_t cap = (int64_t)vt_sm_count() * 2 * 8;
     kern<<<(int)(pairs < cap ? pairs : cap), SC_THREADS, smem, s>>>(post_off, (const uint2 *)postings, img_rnorm, n_img, n_ref,
                                                                     n_shards, q_off, q_node, q_val, n_query, topk, out_key,
-                                                                    out_id, all_key);
+                                                                    out_id, all_key, shard_empty);
     VT_LAUNCH_CHECK();
     return VT_OK;
 }
@@ -275,7 +295,7 @@ static int launch_score(const uint32_t *post_off, const void *postings, const do
 extern "C" int vt_score_topk(const uint32_t *d_post_off, const void *d_postings, const double *d_img_rnorm, int64_t n_img,
                              int64_t n_ref, const int64_t *d_q_off, const int32_t *d_q_node, const float *d_q_val,
                              int64_t n_query, int mode, int topk, double *d_shard_key, int32_t *d_shard_id,
-                             double *d_all_key, void *stream)
+                             double *d_all_key, const uint8_t *d_shard_empty, void *stream)
 {
     VT_CHECK_ARG(n_img > 0 && n_ref > 0 && n_query >= 0, "bad sizes");
     VT_CHECK_ARG(topk >= 1 && topk <= SC_MAXK, "topk out of range");
@@ -283,9 +303,9 @@ extern "C" int vt_score_topk(const uint32_t *d_post_off, const void *d_postings,
     if (n_query == 0) return VT_OK;
     cudaStream_t s = (cudaStream_t)stream;
     switch (mode) {
-    case VT_SCORE_TF_L2: return launch_score<VT_SCORE_TF_L2>(d_post_off, d_postings, d_img_rnorm, n_img, n_ref, d_q_off, d_q_node, d_q_val, n_query, topk, d_shard_key, d_shard_id, d_all_key, s);
-    case VT_SCORE_W_L2: return launch_score<VT_SCORE_W_L2>(d_post_off, d_postings, d_img_rnorm, n_img, n_ref, d_q_off, d_q_node, d_q_val, n_query, topk, d_shard_key, d_shard_id, d_all_key, s);
-    case VT_SCORE_W_L1: return launch_score<VT_SCORE_W_L1>(d_post_off, d_postings, d_img_rnorm, n_img, n_ref, d_q_off, d_q_node, d_q_val, n_query, topk, d_shard_key, d_shard_id, d_all_key, s);
+    case VT_SCORE_TF_L2: return launch_score<VT_SCORE_TF_L2>(d_post_off, d_postings, d_img_rnorm, n_img, n_ref, d_q_off, d_q_node, d_q_val, n_query, topk, d_shard_key, d_shard_id, d_all_key, d_shard_empty, s);
+    case VT_SCORE_W_L2: return launch_score<VT_SCORE_W_L2>(d_post_off, d_postings, d_img_rnorm, n_img, n_ref, d_q_off, d_q_node, d_q_val, n_query, topk, d_shard_key, d_shard_id, d_all_key, d_shard_empty, s);
+    case VT_SCORE_W_L1: return launch_score<VT_SCORE_W_L1>(d_post_off, d_postings, d_img_rnorm, n_img, n_ref, d_q_off, d_q_node, d_q_val, n_query, topk, d_shard_key, d_shard_id, d_all_key, d_shard_empty, s);
     }
     vt_set_error("vt_score_topk: unknown mode %d", mode);
     return VT_EINVAL;

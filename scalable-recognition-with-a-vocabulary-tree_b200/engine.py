@@ -379,7 +379,12 @@ def build_index(csr: dict, n_ref: int, weight: torch.Tensor = None) -> dict:
               "vt_posting_fill")
     rnorm = torch.empty(max(n_img, 1), dtype=torch.float64, device=dev)
     nat.check(lib.vt_rnorm(nat.ptr(csr["sumsq"]), n_img, nat.ptr(rnorm), s), "vt_rnorm")
+    shard_empty = torch.zeros(n_shards, dtype=torch.uint8, device=dev)
+    empty = torch.nonzero(csr["sumsq"][:n_img] == 0).flatten()
+    if empty.numel():
+        shard_empty[(empty // shard).unique()] = 1
     return dict(post_off=post_off, postings=postings[:nnz], rnorm=rnorm[:n_img], sumsq=csr["sumsq"], n_img=n_img,
+                shard_empty=shard_empty,
                 n_ref=n_ref, shard=shard, n_shards=n_shards, nnz=nnz, weighted=weight is not None)
 
 
@@ -403,7 +408,8 @@ def score(index: dict, q: dict, topk: int, mode: int = nat.SCORE_TF_L2, q_val: t
     all_key = torch.empty((max(nq, 1), n_img), dtype=torch.float64, device=dev) if want_all else None
     nat.check(lib.vt_score_topk(nat.ptr(index["post_off"]), nat.ptr(index["postings"]), nat.ptr(index["rnorm"]),
                                 n_img, index["n_ref"], nat.ptr(q["row_off"]), nat.ptr(q["node"]), nat.ptr(q_val),
-                                nq, mode, topk, nat.ptr(shard_key), nat.ptr(shard_id), nat.ptr(all_key), s),
+                                nq, mode, topk, nat.ptr(shard_key), nat.ptr(shard_id), nat.ptr(all_key),
+                                nat.ptr(index.get("shard_empty")), s),
               "vt_score_topk")
     out = dict(all_key=all_key, shard_key=shard_key, shard_id=shard_id, topk=topk)
     if merge:
