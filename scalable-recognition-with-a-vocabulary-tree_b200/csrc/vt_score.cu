@@ -183,6 +183,208 @@ score_shard_kernel(const uint32_t *__restrict__ post_off, const uint2 *__restric
     }
 }
 
+// ---- TF / L2 fast path ---------------------------------------------------------------------------
+// Same walk as score_shard_kernel, but the selection never touches most images: the dot products
+// are small exact integers, so an integer bound discards everything that cannot reach the top-k.
+//   T  = a lower bound of the k-th largest dot in the shard (k-th largest among the top-J lane maxima
+//        of every warp, J = ceil(k/8): a subset of all values);
+//   an image with dot < T * rho  (rho = min norm^-1 / max norm^-1 of the shard) has key
+//   dot/|d| < T * min|d|^-1 <= the key of each of the >= k images with dot >= T  ->  not in the top-k.
+// Survivors (typically a few dozen of 8192) get their binary64 key and one warp picks the k best.
+// Shards with images without descriptors (rho < 0), T == 0 or more than SC_CAND survivors fall back
+// to the exhaustive selection (keys recomputed on demand).
+constexpr int SC_CAND = 1024;
+
+template <int R>
+__global__ void __launch_bounds__(SC_THREADS)
+score_shard_tf_kernel(const uint32_t *__restrict__ post_off, const uint2 *__restrict__ postings,
+                      const double *__restrict__ img_rnorm, int64_t n_img, int64_t n_ref, int n_shards,
+                      const int64_t *__restrict__ q_off, const int32_t *__restrict__ q_node,
+                      const float *__restrict__ q_val, int64_t n_query, int topk, double *__restrict__ out_key,
+                      int32_t *__restrict__ out_id, const double *__restrict__ shard_rho)
+{
+    constexpr int PER = R / SC_THREADS;
+    extern __shared__ unsigned char s_raw[];
+    int *s_acc = reinterpret_cast<int *>(s_raw);                               // [R]
+    double *s_ckey = reinterpret_cast<double *>(s_raw + (size_t)R * 4);        // [SC_CAND]
+    int *s_cslot = reinterpret_cast<int *>(s_raw + (size_t)R * 4 + SC_CAND * 8);   // [SC_CAND]
+    __shared__ int s_top[SC_WARPS * 8];
+    __shared__ int s_thr, s_ncand;
+    __shared__ double r_key[SC_WARPS];
+    __shared__ int32_t r_id[SC_WARPS];
+    __shared__ int r_owner[SC_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int TAKEN = (int)0x80000000;
+    const int J = (topk + SC_WARPS - 1) / SC_WARPS;                            // lane maxima kept per warp (<= 8)
+
+    for (int64_t pair = blockIdx.x; pair < n_query * n_shards; pair += gridDim.x) {
+        const int64_t q = pair / n_shards;
+        const int shard = (int)(pair - q * n_shards);
+        const int64_t img0 = (int64_t)shard * R;
+        const int n_here = (int)((n_img - img0) < R ? (n_img - img0) : R);
+        for (int t = threadIdx.x; t < R; t += SC_THREADS) s_acc[t] = 0;
+        if (threadIdx.x == 0) s_ncand = 0;
+        __syncthreads();
+        const int64_t qb = q_off[q], qe = q_off[q + 1];
+        const uint32_t *off = post_off + (size_t)shard * n_ref;
+        for (int64_t w0 = qb + (int64_t)warp * 32; w0 < qe; w0 += (int64_t)SC_THREADS * SC_UNROLL) {
+            int32_t node[SC_UNROLL];
+            float qv[SC_UNROLL];
+            uint32_t b[SC_UNROLL], e[SC_UNROLL];
+#pragma unroll
+            for (int u = 0; u < SC_UNROLL; ++u) {
+                const int64_t w = w0 + (int64_t)u * SC_THREADS + lane;
+                node[u] = w < qe ? __ldg(q_node + w) : -1;
+                qv[u] = w < qe ? __ldg(q_val + w) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < SC_UNROLL; ++u) {
+                b[u] = node[u] >= 0 ? __ldg(off + node[u]) : 0u;
+                e[u] = node[u] >= 0 ? __ldg(off + node[u] + 1) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < SC_UNROLL; ++u) {
+                const bool is_long = (e[u] - b[u]) > SC_LONG;
+                if (!is_long)
+                    for (uint32_t p = b[u]; p < e[u]; ++p) accumulate<VT_SCORE_TF_L2>(s_acc, nullptr, __ldg(postings + p), qv[u]);
+                unsigned int m = __ballot_sync(VT_FULL, is_long);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t lb = __shfl_sync(VT_FULL, b[u], src), le = __shfl_sync(VT_FULL, e[u], src);
+                    const float lq = __shfl_sync(VT_FULL, qv[u], src);
+                    for (uint32_t p = lb + lane; p < le; p += 32) accumulate<VT_SCORE_TF_L2>(s_acc, nullptr, __ldg(postings + p), lq);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- integer bound -------------------------------------------------------------------------
+        const double rho = shard_rho ? shard_rho[shard] : -1.0;
+        int mymax = 0;
+#pragma unroll 8
+        for (int u = 0; u < PER; ++u) {
+            const int a = s_acc[u * SC_THREADS + threadIdx.x];
+            mymax = a > mymax ? a : mymax;
+        }
+        {
+            int v = mymax;
+            for (int j = 0; j < J; ++j) {                                       // top-J lane maxima of this warp
+                int w = v;
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) { const int t2 = __shfl_xor_sync(VT_FULL, w, o); w = t2 > w ? t2 : w; }
+                const unsigned int holders = __ballot_sync(VT_FULL, v == w);
+                if (lane == __ffs(holders) - 1) v = -1;                          // remove one instance
+                if (lane == 0) s_top[warp * 8 + j] = w;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            // k-th largest of the SC_WARPS*J collected values (selection by repeated maximum, tiny)
+            int thr = 0;
+            for (int r = 0; r < topk; ++r) {
+                int bi = -1, bv = -2;
+                for (int i = 0; i < SC_WARPS * J; ++i) {
+                    const int v = s_top[(i / J) * 8 + (i % J)];
+                    if (v > bv) { bv = v; bi = i; }
+                }
+                thr = bv;
+                if (bi >= 0) s_top[(bi / J) * 8 + (bi % J)] = -2;
+            }
+            int d_lo = 0;
+            if (rho > 0.0 && thr >= 1) {
+                d_lo = (int)floor((double)thr * rho);
+                if (d_lo < 1) d_lo = 1;
+            }
+            s_thr = d_lo;                                                        // 0 => exhaustive fallback
+        }
+        __syncthreads();
+        const int d_lo = s_thr;
+        bool fast = d_lo > 0;
+        if (fast) {
+#pragma unroll 8
+            for (int u = 0; u < PER; ++u) {
+                const int t = u * SC_THREADS + threadIdx.x;
+                if (s_acc[t] >= d_lo) {
+                    const int pos = atomicAdd(&s_ncand, 1);
+                    if (pos < SC_CAND) s_cslot[pos] = t;
+                }
+            }
+            __syncthreads();
+            fast = s_ncand <= SC_CAND;                                           // block-uniform
+        }
+        if (fast) {
+            const int nc = s_ncand;
+            for (int i = threadIdx.x; i < nc; i += SC_THREADS) {
+                const int t = s_cslot[i];
+                s_ckey[i] = (double)s_acc[t] * __ldg(img_rnorm + img0 + t);
+            }
+            __syncthreads();
+            if (warp == 0) {                                                     // one warp selects the k best survivors
+                for (int r = 0; r < topk; ++r) {
+                    double bk = -2.0; int32_t bid = 0x7fffffff; int bslot = -1;
+                    for (int i = lane; i < nc; i += 32) {
+                        const double k2 = s_ckey[i];
+                        const int32_t i2 = (int32_t)(img0 + s_cslot[i]);
+                        if (k2 > -2.0 && better(k2, i2, bk, bid)) { bk = k2; bid = i2; bslot = i; }
+                    }
+#pragma unroll
+                    for (int o = 16; o >= 1; o >>= 1) {
+                        const double k2 = __shfl_xor_sync(VT_FULL, bk, o);
+                        const int32_t i2 = __shfl_xor_sync(VT_FULL, bid, o);
+                        const int s2 = __shfl_xor_sync(VT_FULL, bslot, o);
+                        if (better(k2, i2, bk, bid)) { bk = k2; bid = i2; bslot = s2; }
+                    }
+                    if (lane == 0) {
+                        const size_t o = ((size_t)q * n_shards + shard) * topk + r;
+                        // fewer survivors than k: the rest of the list is images the query does not touch
+                        // (key 0) -- they are not candidates of the fast path, so the slot is reported
+                        // empty; with >= k images of dot >= T this cannot happen for r < k
+                        out_key[o] = bk;
+                        out_id[o] = bk > -2.0 ? bid : -1;
+                        if (bslot >= 0) s_ckey[bslot] = -2.0;
+                    }
+                    __syncwarp();
+                }
+            }
+        } else {
+            // ---- exhaustive fallback: every slot is a candidate, keys recomputed on demand ------------
+            auto key_of = [&](int t) -> double {
+                if (t >= n_here) return -2.0;
+                const int a = s_acc[t];
+                if (a == TAKEN) return -2.0;
+                const double rn = __ldg(img_rnorm + img0 + t);
+                return rn < 0.0 ? -1.0 : (double)a * rn;
+            };
+            double bkey = -2.0; int32_t bid = 0x7fffffff;
+            for (int u = 0; u < PER; ++u) {
+                const int t = u * SC_THREADS + threadIdx.x;
+                const double key = key_of(t);
+                if (better(key, (int32_t)(img0 + t), bkey, bid)) { bkey = key; bid = (int32_t)(img0 + t); }
+            }
+            for (int r = 0; r < topk; ++r) {
+                double key = bkey; int32_t id = bid; int owner;
+                block_best(key, id, owner, r_key, r_id, r_owner);
+                if (threadIdx.x == 0) {
+                    const size_t o = ((size_t)q * n_shards + shard) * topk + r;
+                    out_key[o] = key;
+                    out_id[o] = key > -2.0 ? id : -1;
+                }
+                if (threadIdx.x == owner) {
+                    if (key > -2.0) s_acc[id - img0] = TAKEN;
+                    bkey = -2.0; bid = 0x7fffffff;
+                    for (int u = 0; u < PER; ++u) {
+                        const int t = u * SC_THREADS + threadIdx.x;
+                        const double k2 = key_of(t);
+                        if (better(k2, (int32_t)(img0 + t), bkey, bid)) { bkey = k2; bid = (int32_t)(img0 + t); }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // merge n_lists sorted-or-not candidate lists of a query into its top-k, compute final scores
 template <int MODE>
 __global__ void __launch_bounds__(SC_THREADS)
@@ -292,16 +494,37 @@ static int launch_score(const uint32_t *post_off, const void *postings, const do
     return VT_OK;
 }
 
+static int launch_score_tf(const uint32_t *post_off, const void *postings, const double *img_rnorm, int64_t n_img,
+                           int64_t n_ref, const int64_t *q_off, const int32_t *q_node, const float *q_val, int64_t n_query,
+                           int topk, double *out_key, int32_t *out_id, const double *shard_rho, cudaStream_t s)
+{
+    constexpr int R = 8192;
+    const int n_shards = (int)((n_img + R - 1) / R);
+    auto kern = score_shard_tf_kernel<R>;
+    const size_t smem = (size_t)R * 4 + SC_CAND * 12;
+    VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t pairs = n_query * n_shards;
+    const int64_t cap = (int64_t)vt_sm_count() * 5 * 4;
+    kern<<<(int)(pairs < cap ? pairs : cap), SC_THREADS, smem, s>>>(post_off, (const uint2 *)postings, img_rnorm, n_img, n_ref,
+                                                                    n_shards, q_off, q_node, q_val, n_query, topk, out_key,
+                                                                    out_id, shard_rho);
+    VT_LAUNCH_CHECK();
+    return VT_OK;
+}
+
 extern "C" int vt_score_topk(const uint32_t *d_post_off, const void *d_postings, const double *d_img_rnorm, int64_t n_img,
                              int64_t n_ref, const int64_t *d_q_off, const int32_t *d_q_node, const float *d_q_val,
                              int64_t n_query, int mode, int topk, double *d_shard_key, int32_t *d_shard_id,
-                             double *d_all_key, const uint8_t *d_shard_empty, void *stream)
+                             double *d_all_key, const uint8_t *d_shard_empty, const double *d_shard_rho, void *stream)
 {
     VT_CHECK_ARG(n_img > 0 && n_ref > 0 && n_query >= 0, "bad sizes");
     VT_CHECK_ARG(topk >= 1 && topk <= SC_MAXK, "topk out of range");
     VT_CHECK_ARG(mode != VT_SCORE_TF_L2 || d_img_rnorm != nullptr, "tf mode needs image norms");
     if (n_query == 0) return VT_OK;
     cudaStream_t s = (cudaStream_t)stream;
+    if (mode == VT_SCORE_TF_L2 && d_all_key == nullptr && d_shard_rho != nullptr)
+        return launch_score_tf(d_post_off, d_postings, d_img_rnorm, n_img, n_ref, d_q_off, d_q_node, d_q_val, n_query, topk,
+                               d_shard_key, d_shard_id, d_shard_rho, s);
     switch (mode) {
     case VT_SCORE_TF_L2: return launch_score<VT_SCORE_TF_L2>(d_post_off, d_postings, d_img_rnorm, n_img, n_ref, d_q_off, d_q_node, d_q_val, n_query, topk, d_shard_key, d_shard_id, d_all_key, d_shard_empty, s);
     case VT_SCORE_W_L2: return launch_score<VT_SCORE_W_L2>(d_post_off, d_postings, d_img_rnorm, n_img, n_ref, d_q_off, d_q_node, d_q_val, n_query, topk, d_shard_key, d_shard_id, d_all_key, d_shard_empty, s);

@@ -383,8 +383,15 @@ def build_index(csr: dict, n_ref: int, weight: torch.Tensor = None) -> dict:
     empty = torch.nonzero(csr["sumsq"][:n_img] == 0).flatten()
     if empty.numel():
         shard_empty[(empty // shard).unique()] = 1
+    # per-shard spread of the norms (tf-mode fast selection): rho = min(1/|d|) / max(1/|d|), -1 with empties
+    pad = n_shards * shard - n_img
+    rn = rnorm[:n_img]
+    lo = torch.cat([rn, rn.new_full((pad,), float("inf"))]).view(n_shards, shard).min(1).values
+    hi = torch.cat([rn, rn.new_full((pad,), 0.0)]).view(n_shards, shard).max(1).values
+    shard_rho = torch.where((shard_empty == 0) & (hi > 0), lo / hi.clamp(min=1e-300) * (1.0 - 1e-9),
+                            torch.full_like(lo, -1.0)).contiguous()
     return dict(post_off=post_off, postings=postings[:nnz], rnorm=rnorm[:n_img], sumsq=csr["sumsq"], n_img=n_img,
-                shard_empty=shard_empty,
+                shard_empty=shard_empty, shard_rho=shard_rho,
                 n_ref=n_ref, shard=shard, n_shards=n_shards, nnz=nnz, weighted=weight is not None)
 
 
@@ -409,7 +416,7 @@ def score(index: dict, q: dict, topk: int, mode: int = nat.SCORE_TF_L2, q_val: t
     nat.check(lib.vt_score_topk(nat.ptr(index["post_off"]), nat.ptr(index["postings"]), nat.ptr(index["rnorm"]),
                                 n_img, index["n_ref"], nat.ptr(q["row_off"]), nat.ptr(q["node"]), nat.ptr(q_val),
                                 nq, mode, topk, nat.ptr(shard_key), nat.ptr(shard_id), nat.ptr(all_key),
-                                nat.ptr(index.get("shard_empty")), s),
+                                nat.ptr(index.get("shard_empty")), nat.ptr(index.get("shard_rho")), s),
               "vt_score_topk")
     out = dict(all_key=all_key, shard_key=shard_key, shard_id=shard_id, topk=topk)
     if merge:
