@@ -293,7 +293,7 @@ score_shard_tf_kernel(const uint32_t *__restrict__ post_off, const uint2 *__rest
             }
             int d_lo = 0;
             if (rho > 0.0 && thr >= 1) {
-                d_lo = (int)floor((double)thr * rho);
+                d_lo = (int)ceil((double)thr * rho);     // dot < d_lo  =>  dot <= d_lo - 1 < thr * rho: cannot win
                 if (d_lo < 1) d_lo = 1;
             }
             s_thr = d_lo;                                                        // 0 => exhaustive fallback
