@@ -172,7 +172,8 @@ int vt_encode(const int32_t *d_word, const int64_t *d_img_off, int64_t n_img, in
 int vt_encode_max_words(void);
 
 /* ---- inverted file: the dict-per-node postings of vocabulary.py:96-100 as CSR, sharded by image
- * range (vt_score_shard_size() images per shard).  Row key = (img / shard_size) * n_ref + node.
+ * range (vt_score_shard_size() images per shard).  Row key = node * n_shards + img / shard_size, so a
+ * node's posting list is one contiguous image-ordered run and shards are consecutive ranges of it.
  * vt_posting_keys writes, for every forward-CSR entry e, its key, e itself and its image;
  * sort (key, e) with vt_sort_pairs (stable => postings stay in image order); vt_posting_fill then
  * gathers the postings (uint32 local image id, uint32 payload = tf count, or float weight bits

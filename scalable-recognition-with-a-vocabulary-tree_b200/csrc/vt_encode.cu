@@ -175,11 +175,14 @@ __global__ void posting_keys_kernel(const int64_t *__restrict__ row_off, const i
                                     int32_t shard_size, int64_t n_ref, uint32_t *__restrict__ keys,
                                     uint32_t *__restrict__ entry, int32_t *__restrict__ entry_img)
 {
+    const uint32_t n_shards = (uint32_t)((n_img + shard_size - 1) / shard_size);
     for (int64_t img = blockIdx.x; img < n_img; img += gridDim.x) {
         const int64_t b = row_off[img], e = row_off[img + 1];
-        const uint32_t shard_base = (uint32_t)((img / shard_size) * n_ref);
+        const uint32_t shard = (uint32_t)(img / shard_size);
         for (int64_t t = b + threadIdx.x; t < e; t += blockDim.x) {
-            keys[t] = shard_base + (uint32_t)node[t];
+            // node-major rows: the posting list of a node is one contiguous, image-ordered run and the
+            // shards are consecutive ranges of it (row pointers of one node for all shards are adjacent)
+            keys[t] = (uint32_t)node[t] * n_shards + shard;
             entry[t] = (uint32_t)t;
             entry_img[t] = (int32_t)img;
         }

@@ -100,7 +100,7 @@ score_shard_kernel(const uint32_t *__restrict__ post_off, const uint2 *__restric
         // per warp -- the walk is latency bound, not bandwidth bound); posting lists longer than
         // SC_LONG are handed to the whole warp so that one lane never serialises a long list
         const int64_t qb = q_off[q], qe = q_off[q + 1];
-        const uint32_t *off = post_off + (size_t)shard * n_ref;
+        const uint32_t *off = post_off + shard;                 // row of (node, shard) = node * n_shards + shard
         // SC_UNROLL words per lane are in flight together: the q_node -> row pointer -> posting chain is
         // three dependent DRAM/L2 round trips, so independent chains are what hides the latency
         for (int64_t w0 = qb + (int64_t)warp * 32; w0 < qe; w0 += (int64_t)SC_THREADS * SC_UNROLL) {
@@ -115,8 +115,8 @@ score_shard_kernel(const uint32_t *__restrict__ post_off, const uint2 *__restric
             }
 #pragma unroll
             for (int u = 0; u < SC_UNROLL; ++u) {
-                b[u] = node[u] >= 0 ? __ldg(off + node[u]) : 0u;
-                e[u] = node[u] >= 0 ? __ldg(off + node[u] + 1) : 0u;
+                b[u] = node[u] >= 0 ? __ldg(off + (size_t)node[u] * n_shards) : 0u;
+                e[u] = node[u] >= 0 ? __ldg(off + (size_t)node[u] * n_shards + 1) : 0u;
             }
 #pragma unroll
             for (int u = 0; u < SC_UNROLL; ++u) {
@@ -226,7 +226,7 @@ score_shard_tf_kernel(const uint32_t *__restrict__ post_off, const uint2 *__rest
         if (threadIdx.x == 0) s_ncand = 0;
         __syncthreads();
         const int64_t qb = q_off[q], qe = q_off[q + 1];
-        const uint32_t *off = post_off + (size_t)shard * n_ref;
+        const uint32_t *off = post_off + shard;                 // row of (node, shard) = node * n_shards + shard
         for (int64_t w0 = qb + (int64_t)warp * 32; w0 < qe; w0 += (int64_t)SC_THREADS * SC_UNROLL) {
             int32_t node[SC_UNROLL];
             float qv[SC_UNROLL];
@@ -239,8 +239,8 @@ score_shard_tf_kernel(const uint32_t *__restrict__ post_off, const uint2 *__rest
             }
 #pragma unroll
             for (int u = 0; u < SC_UNROLL; ++u) {
-                b[u] = node[u] >= 0 ? __ldg(off + node[u]) : 0u;
-                e[u] = node[u] >= 0 ? __ldg(off + node[u] + 1) : 0u;
+                b[u] = node[u] >= 0 ? __ldg(off + (size_t)node[u] * n_shards) : 0u;
+                e[u] = node[u] >= 0 ? __ldg(off + (size_t)node[u] * n_shards + 1) : 0u;
             }
 #pragma unroll
             for (int u = 0; u < SC_UNROLL; ++u) {
