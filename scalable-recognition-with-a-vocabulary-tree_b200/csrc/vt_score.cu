@@ -67,6 +67,22 @@ __device__ __forceinline__ void accumulate(int *s_acci, float *s_accf, const uin
     }
 }
 
+// one lane walks a short posting list: four postings are fetched before any is accumulated, so the
+// DRAM round trips of a list overlap instead of serialising behind the shared-memory atomics
+template <int MODE>
+__device__ __forceinline__ void walk_short(int *s_acci, float *s_accf, const uint2 *__restrict__ postings, uint32_t b,
+                                           uint32_t e, float qv)
+{
+    for (uint32_t p = b; p < e; p += 4) {
+        uint2 pe[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pe[i] = p + i < e ? __ldg(postings + p + i) : make_uint2(0u, 0u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (p + i < e) accumulate<MODE>(s_acci, s_accf, pe[i], qv);
+    }
+}
+
 // MODE: VT_SCORE_*.  R: images per shard.
 template <int MODE, int R>
 __global__ void __launch_bounds__(SC_THREADS)
@@ -121,9 +137,7 @@ score_shard_kernel(const uint32_t *__restrict__ post_off, const uint2 *__restric
 #pragma unroll
             for (int u = 0; u < SC_UNROLL; ++u) {
                 const bool is_long = (e[u] - b[u]) > SC_LONG;
-                if (!is_long) {
-                    for (uint32_t p = b[u]; p < e[u]; ++p) accumulate<MODE>(s_acci, s_accf, __ldg(postings + p), qv[u]);
-                }
+                if (!is_long) walk_short<MODE>(s_acci, s_accf, postings, b[u], e[u], qv[u]);
                 unsigned int m = __ballot_sync(VT_FULL, is_long);
                 while (m) {
                     const int src = __ffs(m) - 1;
@@ -245,8 +259,7 @@ score_shard_tf_kernel(const uint32_t *__restrict__ post_off, const uint2 *__rest
 #pragma unroll
             for (int u = 0; u < SC_UNROLL; ++u) {
                 const bool is_long = (e[u] - b[u]) > SC_LONG;
-                if (!is_long)
-                    for (uint32_t p = b[u]; p < e[u]; ++p) accumulate<VT_SCORE_TF_L2>(s_acc, nullptr, __ldg(postings + p), qv[u]);
+                if (!is_long) walk_short<VT_SCORE_TF_L2>(s_acc, nullptr, postings, b[u], e[u], qv[u]);
                 unsigned int m = __ballot_sync(VT_FULL, is_long);
                 while (m) {
                     const int src = __ffs(m) - 1;
