@@ -53,6 +53,7 @@ __device__ __forceinline__ void block_best(double &key, int32_t &id, int &owner,
 
 constexpr uint32_t SC_LONG = 24;
 constexpr int SC_UNROLL = 4;
+constexpr int SC_FETCH = 8;         // postings fetched together by one lane
 
 template <int MODE>
 __device__ __forceinline__ void accumulate(int *s_acci, float *s_accf, const uint2 pe, const float qv)
@@ -67,18 +68,18 @@ __device__ __forceinline__ void accumulate(int *s_acci, float *s_accf, const uin
     }
 }
 
-// one lane walks a short posting list: four postings are fetched before any is accumulated, so the
+// one lane walks a short posting list: SC_FETCH postings are fetched before any is accumulated, so the
 // DRAM round trips of a list overlap instead of serialising behind the shared-memory atomics
 template <int MODE>
 __device__ __forceinline__ void walk_short(int *s_acci, float *s_accf, const uint2 *__restrict__ postings, uint32_t b,
                                            uint32_t e, float qv)
 {
-    for (uint32_t p = b; p < e; p += 4) {
-        uint2 pe[4];
+    for (uint32_t p = b; p < e; p += SC_FETCH) {
+        uint2 pe[SC_FETCH];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) pe[i] = p + i < e ? __ldg(postings + p + i) : make_uint2(0u, 0u);
+        for (int i = 0; i < SC_FETCH; ++i) pe[i] = p + i < e ? __ldg(postings + p + i) : make_uint2(0u, 0u);
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < SC_FETCH; ++i)
             if (p + i < e) accumulate<MODE>(s_acci, s_accf, pe[i], qv);
     }
 }
