@@ -137,6 +137,18 @@ int vt_kmeans_assign(const void *d_desc, int dtype, int dp, const int32_t *d_per
                      int64_t n_nodes, int k, const float *d_child_centroids, uint8_t *d_label,
                      uint64_t *d_sums, uint64_t *d_counts, uint64_t *d_changed,
                      uint64_t *d_stats, void *stream);
+/* Tensor-core variant (dp == 128, k <= 16): distance step AND the per-cluster sums are tcgen05.mma
+ * kind::i8 products on the same shared-memory tile (sums = X^T . one-hot(labels)); results are
+ * bit-identical to vt_kmeans_assign.  d_planes = vt_kmeans_planes(...) of the CURRENT centres
+ * (vt_kmeans_planes_bytes(n_nodes, k) bytes), refreshed after every vt_kmeans_update. */
+int64_t vt_kmeans_planes_bytes(int64_t n_nodes, int k);
+int vt_kmeans_planes(const float *d_child_centroids, int64_t n_nodes, int k, int dp, void *d_planes,
+                     uint64_t *d_stats, void *stream);
+int vt_kmeans_assign_mma(const void *d_desc, int dtype, int dp, const int32_t *d_perm,
+                         const int32_t *d_parent, int64_t n_members, const uint8_t *d_node_internal,
+                         int64_t n_nodes, int k, const float *d_child_centroids, const void *d_planes,
+                         uint8_t *d_label, uint64_t *d_sums, uint64_t *d_counts, uint64_t *d_changed,
+                         uint64_t *d_stats, void *stream);
 /* centre = (float)((double)sum / (double)count) where count > 0; empty clusters keep their centre */
 int vt_kmeans_update(const uint64_t *d_sums, const uint64_t *d_counts, int64_t n_rows, int dp,
                      float *d_child_centroids, void *stream);

@@ -34,6 +34,9 @@ SIGNATURES = {
     "vt_quantize_host": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _int, _int, _vp, _i64]),
     "vt_kmeans_init": (_int, [_vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp, _vp]),
     "vt_kmeans_assign": (_int, [_vp, _int, _int, _vp, _vp, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vt_kmeans_planes_bytes": (_i64, [_i64, _int]),
+    "vt_kmeans_planes": (_int, [_vp, _i64, _int, _int, _vp, _vp, _vp]),
+    "vt_kmeans_assign_mma": (_int, [_vp, _int, _int, _vp, _vp, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vt_kmeans_update": (_int, [_vp, _vp, _i64, _int, _vp, _vp]),
     "vt_column_sums": (_int, [_vp, _int, _i64, _int, _vp, _vp]),
     "vt_partition_keys": (_int, [_vp, _vp, _i64, _vp, _int, C.c_uint32, _vp, _vp]),

@@ -275,6 +275,358 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
 
 }  // namespace
 
+// =====================================================================================================
+// k-means assignment + exact accumulation of one tree level on the tensor pipe (VocabularyTree.fit,
+// cbir/encoders/vocabulary.py:62-66 with the seeded exact Lloyd).  Same distance step as
+// level_mma_kernel; the per-cluster sums are a SECOND integer MMA on the same shared-memory tile:
+//   S^T[d][c] = sum_i X[i][d] * onehot[i][c]      (A = X read MN-major, B = one-hot labels, K = 128 rows)
+// so the 128 x 128 bytes of a tile are added up by the tensor core instead of 16 K atomics.  Every
+// thread then owns one dimension d of the 16 running cluster sums of the node it is working on and
+// flushes them with uint64 atomics only when the node changes.
+// Level-local indexing (as vt_kmeans_assign): parent[p] = node index inside the level, child rows
+// j*k + c, bimg/cn prepared per level by vt_kmeans_planes.
+// =====================================================================================================
+namespace {
+constexpr uint32_t MM_IDESC_SUM = (2u << 4) | (1u << 15) /* A is MN-major */ | ((uint32_t)(16 >> 3) << 17) |
+                                  ((uint32_t)(MM_TILE >> 4) << 24);
+constexpr int MM_H_BYTES = 16 * 128;           // one-hot tile: 16 clusters x 128 rows
+
+__global__ void __launch_bounds__(128)
+prep_level_planes_kernel(const float *__restrict__ child_cent, int64_t n_nodes, int k, uint8_t *__restrict__ bimg,
+                         unsigned long long *__restrict__ cn, unsigned long long *__restrict__ stats)
+{
+    __shared__ unsigned long long s_part[4];
+    const int d = threadIdx.x;
+    for (int64_t h = blockIdx.x; h < n_nodes; h += gridDim.x) {
+        uint8_t *img = bimg + (size_t)h * MM_B_BYTES;
+        bool bad = false;
+        for (int c = 0; c < 16; ++c) {
+            uint32_t fx = 0;
+            if (c < k) {
+                const float v = child_cent[(size_t)(h * k + c) * 128 + d];
+                if (!(v >= 0.f) || v > 255.99f) bad = true;
+                fx = (uint32_t)rintf(fminf(fmaxf(v, 0.f), 255.99f) * 65536.f);
+            }
+            img[sw128_offset(c, d)] = (uint8_t)(fx >> 16);
+            img[sw128_offset(16 + c, d)] = (uint8_t)(fx >> 8);
+            img[sw128_offset(32 + c, d)] = (uint8_t)fx;
+            unsigned long long sq = (unsigned long long)fx * fx;
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) sq += __shfl_xor_sync(VT_FULL, sq, o);
+            if ((d & 31) == 0) s_part[d >> 5] = sq;
+            __syncthreads();
+            if (d == 0 && c < k) cn[h * k + c] = s_part[0] + s_part[1] + s_part[2] + s_part[3];
+            __syncthreads();
+        }
+        if (bad && stats) atomicAdd(stats + 1, 1ull);
+    }
+}
+
+__global__ void __launch_bounds__(MM_TILE, 6)
+kmeans_mma_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ perm, const int32_t *__restrict__ parent,
+                  int64_t n, const uint8_t *__restrict__ node_internal, int k, const float *__restrict__ child_cent,
+                  const uint8_t *__restrict__ bimg, const unsigned long long *__restrict__ cn,
+                  uint8_t *__restrict__ label, unsigned long long *__restrict__ sums,
+                  unsigned long long *__restrict__ counts, unsigned long long *__restrict__ changed,
+                  unsigned long long *__restrict__ stats)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + MM_A_BYTES;                 // 6 KB centroid planes
+    uint8_t *sH = smem + MM_A_BYTES + 6 * 1024;      // 2 KB one-hot labels (1024 B aligned)
+    __shared__ __align__(8) unsigned long long mbar;
+    __shared__ uint32_t s_tmem;
+    __shared__ uint32_t s_row[MM_TILE];
+    __shared__ long long s_min[4];
+    __shared__ int s_cnt[16];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long none = 0x7fffffffffffffffLL;
+    unsigned int rechecks = 0, n_changed = 0;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(MM_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    if (tid < 16) s_cnt[tid] = 0;
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = s_tmem;
+    const uint64_t a_desc = make_desc(smem_u32(sA));
+    const uint64_t b_desc = make_desc(smem_u32(sB));
+    const uint64_t h_desc = make_desc(smem_u32(sH));
+    uint32_t phase = 0;
+
+    // running sums of the node this CTA is working on: thread = dimension, 16 clusters
+    int run[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) run[c] = 0;
+    long long run_node = -1;
+    int run_tiles = 0;
+
+    auto flush = [&]() {
+        if (run_node >= 0) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+                if (c < k && run[c]) atomicAdd(&sums[(size_t)(run_node * k + c) * 128 + tid], (unsigned long long)run[c]);
+            if (tid < k && s_cnt[tid]) atomicAdd(&counts[run_node * k + tid], (unsigned long long)s_cnt[tid]);
+        }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) run[c] = 0;
+        __syncthreads();
+        if (tid < 16) s_cnt[tid] = 0;
+        __syncthreads();
+        run_tiles = 0;
+    };
+
+    auto wait_mma = [&]() {
+        uint32_t done;
+        do {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_u32(&mbar)), "r"(phase) : "memory");
+        } while (!done);
+        phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;");
+    };
+
+    for (int64_t base = (int64_t)blockIdx.x * MM_TILE; base < n; base += (int64_t)gridDim.x * MM_TILE) {
+        const int64_t p = base + tid;
+        const bool valid = p < n;
+        const uint32_t row = valid ? (uint32_t)perm[p] : 0u;
+        const long long node = valid ? (long long)parent[p] : 0;
+        const bool is_int = valid && node_internal[node];
+        const uint8_t *xrow = desc + (size_t)row * 128;
+        s_row[tid] = is_int ? row : 0xffffffffu;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = (tid >> 3) + 16 * i, j = tid & 7;
+            const uint32_t rr = s_row[r];
+            const uint8_t *src = rr != 0xffffffffu ? desc + (size_t)rr * 128 + j * 16 : desc;
+            const uint32_t dst = smem_u32(sA) + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
+            const int nbytes = rr != 0xffffffffu ? 16 : 0;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes));
+        }
+        long long best = none, second = none;
+        int arg = 0;
+        bool pending = is_int;
+        unsigned int xn = 0;
+
+        // ---- assignment: one distance MMA per distinct node of the tile --------------------------------
+        for (int pass = 0;; ++pass) {
+            long long mine = pending ? node : none;
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) {
+                const long long other = __shfl_xor_sync(VT_FULL, mine, o);
+                mine = other < mine ? other : mine;
+            }
+            if (lane == 0) s_min[warp] = mine;
+            __syncthreads();
+            mine = s_min[0];
+#pragma unroll
+            for (int w = 1; w < 4; ++w) mine = s_min[w] < mine ? s_min[w] : mine;
+            if (mine == none) break;
+            const bool on = pending && node == mine;
+            pending = pending && !on;
+            const uint8_t *bsrc = bimg + (size_t)mine * MM_B_BYTES;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int c = tid + MM_TILE * i;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sB) + c * 16), "l"(bsrc + c * 16));
+            }
+            asm volatile("cp.async.commit_group;");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint32_t acc = ks > 0 ? 1u : 0u;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                        ::"r"(tmem), "l"(a_desc + 2 * ks), "l"(b_desc + 2 * ks), "r"(MM_IDESC), "r"(acc), "r"(0u));
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
+            }
+            if (pass == 0 && is_int) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint4 q = *reinterpret_cast<const uint4 *>(sA + (tid >> 3) * 1024 + (tid & 7) * 128 + ((j ^ (tid & 7)) << 4));
+                    xn = __dp4a(q.x, q.x, xn); xn = __dp4a(q.y, q.y, xn); xn = __dp4a(q.z, q.z, xn); xn = __dp4a(q.w, q.w, xn);
+                }
+            }
+            wait_mma();
+            uint32_t v[MM_N];
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                             : "=r"(v[16 * g + 0]), "=r"(v[16 * g + 1]), "=r"(v[16 * g + 2]), "=r"(v[16 * g + 3]),
+                               "=r"(v[16 * g + 4]), "=r"(v[16 * g + 5]), "=r"(v[16 * g + 6]), "=r"(v[16 * g + 7]),
+                               "=r"(v[16 * g + 8]), "=r"(v[16 * g + 9]), "=r"(v[16 * g + 10]), "=r"(v[16 * g + 11]),
+                               "=r"(v[16 * g + 12]), "=r"(v[16 * g + 13]), "=r"(v[16 * g + 14]), "=r"(v[16 * g + 15])
+                             : "r"(taddr + 16 * g));
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (on) {
+                const unsigned long long *cnc = cn + mine * k;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    if (c < k) {
+                        const long long dot = ((long long)v[c] << 16) + ((long long)v[16 + c] << 8) + (long long)v[32 + c];
+                        const long long s = (long long)cnc[c] - (dot << 17);
+                        if (s < best) { second = best; best = s; arg = c; }
+                        else if (s < second) second = s;
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncthreads();
+        }
+        bool contested = false;
+        if (is_int && k > 1) {
+            const double d2b = fmax(0.0, (double)second * 2.3283064365386963e-10 + (double)xn);
+            const double gap = (double)(second - best) * 2.3283064365386963e-10 - 1e-6;
+            const double two_m = 2.0 * 1.52587890625e-05 * 11.313708498984761 * 1.02;
+            contested = gap <= 0.0 || gap * gap <= two_m * two_m * d2b;
+        }
+        unsigned int m = __ballot_sync(VT_FULL, contested);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const unsigned long long xq = __shfl_sync(VT_FULL, (unsigned long long)xrow, src);
+            const long long nq = __shfl_sync(VT_FULL, node, src);
+            const int res = canon_argmin_warp<uint8_t, 128>(reinterpret_cast<const uint8_t *>(xq),
+                                                            child_cent + (size_t)(nq * k) * 128, k, lane);
+            if (lane == src) { arg = res; ++rechecks; }
+        }
+        if (is_int) {
+            if (label[p] != (uint8_t)arg) { ++n_changed; label[p] = (uint8_t)arg; }
+        }
+
+        // ---- accumulation: one one-hot MMA per distinct node of the tile --------------------------------
+        pending = is_int;
+        for (;;) {
+            long long mine = pending ? node : none;
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) {
+                const long long other = __shfl_xor_sync(VT_FULL, mine, o);
+                mine = other < mine ? other : mine;
+            }
+            if (lane == 0) s_min[warp] = mine;
+            __syncthreads();
+            mine = s_min[0];
+#pragma unroll
+            for (int w = 1; w < 4; ++w) mine = s_min[w] < mine ? s_min[w] : mine;
+            if (mine == none) break;
+            const bool on = pending && node == mine;
+            pending = pending && !on;
+            if (mine != run_node || run_tiles >= 60000) { flush(); run_node = mine; }   // block-uniform
+            ++run_tiles;
+            // one-hot tile: row c (cluster), byte i (this thread's row): 1 iff label == c
+#pragma unroll
+            for (int c = 0; c < 16; ++c) sH[sw128_offset(c, tid)] = (on && arg == c) ? 1 : 0;
+            if (on) atomicAdd(&s_cnt[arg], 1);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {                // K = 4 x 32 rows; A advances 32 rows = 4096 B
+                    const uint32_t acc = ks > 0 ? 1u : 0u;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                        ::"r"(tmem + 48u), "l"(a_desc + 256 * ks), "l"(h_desc + 2 * ks), "r"(MM_IDESC_SUM), "r"(acc), "r"(0u));
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
+            }
+            wait_mma();
+            uint32_t sv[16];
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + 48u;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                         : "=r"(sv[0]), "=r"(sv[1]), "=r"(sv[2]), "=r"(sv[3]), "=r"(sv[4]), "=r"(sv[5]), "=r"(sv[6]), "=r"(sv[7]),
+                           "=r"(sv[8]), "=r"(sv[9]), "=r"(sv[10]), "=r"(sv[11]), "=r"(sv[12]), "=r"(sv[13]), "=r"(sv[14]), "=r"(sv[15])
+                         : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < 16; ++c) run[c] += (int)sv[c];
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncthreads();
+        }
+        __syncthreads();
+    }
+    flush();
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        rechecks += __shfl_xor_sync(VT_FULL, rechecks, o);
+        n_changed += __shfl_xor_sync(VT_FULL, n_changed, o);
+    }
+    if (lane == 0) {
+        if (n_changed && changed) atomicAdd(changed, (unsigned long long)n_changed);
+        if (rechecks && stats) atomicAdd(stats, (unsigned long long)rechecks);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(MM_TMEM_COLS));
+}
+}  // namespace
+
+// centroid byte planes + fixed-point norms of one LEVEL (node j -> image j, child rows j*k + c)
+extern "C" int64_t vt_kmeans_planes_bytes(int64_t n_nodes, int k)
+{
+    return ((n_nodes * MM_B_BYTES + 255) / 256) * 256 + ((n_nodes * k * 8 + 255) / 256) * 256;
+}
+
+extern "C" int vt_kmeans_planes(const float *d_child_centroids, int64_t n_nodes, int k, int dp, void *d_planes,
+                                uint64_t *d_stats, void *stream)
+{
+    VT_CHECK_ARG(dp == 128 && k >= 1 && k <= 16 && n_nodes >= 1, "tensor-core k-means needs dp == 128 and k <= 16");
+    uint8_t *bimg = (uint8_t *)d_planes;
+    unsigned long long *cn = (unsigned long long *)(bimg + ((n_nodes * MM_B_BYTES + 255) / 256) * 256);
+    const int64_t cap = (int64_t)vt_sm_count() * 16;
+    prep_level_planes_kernel<<<(int)(n_nodes < cap ? n_nodes : cap), 128, 0, (cudaStream_t)stream>>>(
+        d_child_centroids, n_nodes, k, bimg, cn, (unsigned long long *)d_stats);
+    VT_LAUNCH_CHECK();
+    return VT_OK;
+}
+
+// Same contract as vt_kmeans_assign (labels, exact uint64 sums / counts, changed counter), distance
+// step and cluster sums on the INT8 tensor pipe.  d_planes from vt_kmeans_planes for the CURRENT centres.
+extern "C" int vt_kmeans_assign_mma(const void *d_desc, int dtype, int dp, const int32_t *d_perm, const int32_t *d_parent,
+                                    int64_t n_members, const uint8_t *d_node_internal, int64_t n_nodes, int k,
+                                    const float *d_child_centroids, const void *d_planes, uint8_t *d_label,
+                                    uint64_t *d_sums, uint64_t *d_counts, uint64_t *d_changed, uint64_t *d_stats,
+                                    void *stream)
+{
+    VT_CHECK_ARG(dtype == VT_U8 && dp == 128 && k >= 1 && k <= 16, "tensor-core k-means needs byte rows, dp == 128, k <= 16");
+    VT_CHECK_ARG(n_members >= 0 && n_nodes >= 1 && d_planes, "bad arguments");
+    if (n_members == 0) return VT_OK;
+    const uint8_t *bimg = (const uint8_t *)d_planes;
+    const unsigned long long *cn = (const unsigned long long *)(bimg + ((n_nodes * MM_B_BYTES + 255) / 256) * 256);
+    static bool attr_set = false;
+    const int smem = MM_A_BYTES + 6 * 1024 + MM_H_BYTES + 1024;
+    if (!attr_set) {
+        VT_CUDA(cudaFuncSetAttribute(kmeans_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    const int64_t want = (n_members + MM_TILE - 1) / MM_TILE, cap = (int64_t)vt_sm_count() * 6;
+    kmeans_mma_kernel<<<(int)(want < cap ? want : cap), MM_TILE, smem, (cudaStream_t)stream>>>(
+        (const uint8_t *)d_desc, d_perm, d_parent, n_members, d_node_internal, k, d_child_centroids, bimg, cn, d_label,
+        (unsigned long long *)d_sums, (unsigned long long *)d_counts, (unsigned long long *)d_changed,
+        (unsigned long long *)d_stats);
+    VT_LAUNCH_CHECK();
+    return VT_OK;
+}
+
 int64_t vt_mma_prepared_bytes(int k, int depth);
 
 static int64_t mma_int_nodes(int k, int depth)

@@ -164,9 +164,11 @@ class CudaLevelOps:
     talks to this interface so that the multi-rank protocol around it can be exercised on CPU
     (gloo) with a test double; the product always uses this class."""
 
-    def __init__(self):
+    def __init__(self, use_tensor_cores: bool = True):
         nat.require_device()
         self.lib = _lib()
+        self.use_tensor_cores = use_tensor_cores
+        self._planes = None
 
     def column_sums(self, desc):
         n, dp = desc.shape
@@ -181,6 +183,19 @@ class CudaLevelOps:
 
     def kmeans_assign(self, desc, perm, parent, n_active, node_internal, n_nodes, k, child_cent, label, sums,
                       counts, changed, stats):
+        if self.use_tensor_cores and desc.shape[1] == 128 and k <= 16 and n_active > 0:
+            # byte descriptors => centres lie in [0, 255]: inside the 8.16 fixed-point range of the planes
+            need = int(self.lib.vt_kmeans_planes_bytes(n_nodes, k))
+            if self._planes is None or self._planes.numel() < need:
+                self._planes = torch.empty(need, dtype=torch.uint8, device=desc.device)
+            s = nat.stream_ptr()
+            nat.check(self.lib.vt_kmeans_planes(nat.ptr(child_cent), n_nodes, k, 128, nat.ptr(self._planes), None, s),
+                      "vt_kmeans_planes")
+            nat.check(self.lib.vt_kmeans_assign_mma(nat.ptr(desc), VT_U8, 128, nat.ptr(perm), nat.ptr(parent), n_active,
+                                                    nat.ptr(node_internal), n_nodes, k, nat.ptr(child_cent),
+                                                    nat.ptr(self._planes), nat.ptr(label), nat.ptr(sums), nat.ptr(counts),
+                                                    nat.ptr(changed), nat.ptr(stats), s), "vt_kmeans_assign_mma")
+            return
         nat.check(self.lib.vt_kmeans_assign(nat.ptr(desc), VT_U8, desc.shape[1], nat.ptr(perm), nat.ptr(parent),
                                             n_active, nat.ptr(node_internal), n_nodes, k, nat.ptr(child_cent),
                                             nat.ptr(label), nat.ptr(sums), nat.ptr(counts), nat.ptr(changed),

@@ -206,6 +206,19 @@ def test_build_medium_tree_bit_exact(vt, cuda):
     assert len(log) == 4
 
 
+def test_build_simt_and_tensor_paths_agree(vt, cuda):
+    """the FP32/atomic assign kernel and the tcgen05 assign+accumulate kernel build the same tree"""
+    x = vt.synth.sift_like(60_000, 128, n_centres=500, seed=9)
+    x[1000:1400] = x[1000]                                      # a big block of duplicates -> empty clusters
+    desc, d = vt.engine.stage(x, cuda)
+    a = vt.engine.build_tree(desc, d, 10, 3, n_iter=5, ops=vt.engine.CudaLevelOps(use_tensor_cores=True))
+    b = vt.engine.build_tree(desc, d, 10, 3, n_iter=5, ops=vt.engine.CudaLevelOps(use_tensor_cores=False))
+    t = vo.build_tree(x, 10, 3, 5)
+    for ft in (a, b):
+        assert np.array_equal(ft.centroids, t["centroids"]) and np.array_equal(ft.count, t["count"])
+        assert np.array_equal(ft.internal, t["internal"])
+
+
 def test_build_degenerate_inputs(vt, cuda):
     # fewer points than branches: the root is a leaf (vocabulary.py:55)
     x = np.array([[3, 4], [5, 6]], np.uint8)
