@@ -311,10 +311,12 @@ def build_tree(desc: torch.Tensor, d: int, k: int, depth: int, n_iter: int = 10,
         perm = svals[:n_next].contiguous()
         parent = skeys[:n_next].contiguous()
 
-    tree = FlatTree(k, depth, d, cent.cpu().numpy(), exists.cpu().numpy(), internal.cpu().numpy(),
-                    count_heap.cpu().numpy())
-    if dev.type == "cuda":
+    if dev.type == "cuda":       # the 4 * n_heap * DP bytes of centres stay on the device; host copy on demand
+        tree = FlatTree(k, depth, d, cent, exists.cpu().numpy(), internal.cpu().numpy(), count_heap.cpu().numpy(),
+                        byte_built=True)
         tree.adopt_device(dev, cent, internal)
+    else:
+        tree = FlatTree(k, depth, d, cent.numpy(), exists.numpy(), internal.numpy(), count_heap.numpy(), byte_built=True)
     return tree
 
 

@@ -62,13 +62,21 @@ def reference_ids(exists: np.ndarray, internal: np.ndarray, k: int, depth: int):
 class FlatTree:
     """Host mirror of a built tree plus lazily created device tensors."""
 
-    def __init__(self, k: int, depth: int, d: int, centroids: np.ndarray, exists: np.ndarray,
-                 internal: np.ndarray, count=None):
+    def __init__(self, k: int, depth: int, d: int, centroids, exists: np.ndarray,
+                 internal: np.ndarray, count=None, byte_built: bool = False):
+        """``centroids``: float32 [n_heap, DP] as a numpy array, or a torch tensor that stays on its
+        device (the host copy is then made lazily, on first access of ``.centroids``)."""
         self.k, self.depth, self.D = int(k), int(depth), int(d)
         self.DP = int(centroids.shape[1])
         self.n_heap = heap_size(k, depth)
         assert centroids.shape[0] == self.n_heap
-        self.centroids = np.ascontiguousarray(centroids, np.float32)
+        self._byte_built = bool(byte_built)       # built from byte descriptors => every centre in [0, 255]
+        if isinstance(centroids, np.ndarray):
+            self._centroids = np.ascontiguousarray(centroids, np.float32)
+            self._centroids_dev = None
+        else:
+            self._centroids = None
+            self._centroids_dev = centroids
         self.exists = np.ascontiguousarray(exists, np.uint8)
         self.internal = np.ascontiguousarray(internal, np.uint8)
         self.count = None if count is None else np.ascontiguousarray(count, np.int64)
@@ -86,6 +94,12 @@ class FlatTree:
             lvl[o: o + self.k ** level] = level
         self.level_ref = lvl[heap].astype(np.uint8)
         self._dev = {}
+
+    @property
+    def centroids(self) -> np.ndarray:
+        if self._centroids is None:
+            self._centroids = self._centroids_dev.detach().cpu().numpy()
+        return self._centroids
 
     # ------------------------------------------------------------------ device copies
     def device(self, device=None):
@@ -122,6 +136,8 @@ class FlatTree:
         inside the 8.16 fixed-point range -- true for any tree built from byte descriptors."""
         if self.DP != 128 or self.k > 16 or self.depth < 1:
             return False
+        if self._byte_built:
+            return True
         c = self.centroids
         return bool(c.size == 0 or (float(c.min()) >= 0.0 and float(c.max()) <= 255.99))
 
