@@ -151,18 +151,15 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
 
         // one MMA pass per distinct node present in the tile (sorted batch: almost always one)
         for (int pass = 0;; ++pass) {
-            long long mine = pending ? node : none;
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) {
-                const long long other = __shfl_xor_sync(VT_FULL, mine, o);
-                mine = other < mine ? other : mine;
-            }
-            if (lane == 0) s_min[warp] = mine;
+            // heap / level indices fit 31 bits (ids are int32 across the ABI): 32-bit warp minimum
+            int mine32 = pending ? (int)node : 0x7fffffff;
+            mine32 = __reduce_min_sync(VT_FULL, mine32);
+            if (lane == 0) s_min[warp] = mine32;
             __syncthreads();
-            mine = s_min[0];
+            long long mine = s_min[0];
 #pragma unroll
             for (int w = 1; w < 4; ++w) mine = s_min[w] < mine ? s_min[w] : mine;
-            if (mine == none) break;                            // block-uniform
+            if (mine == 0x7fffffff) break;                            // block-uniform
             const bool on = pending && node == mine;
             pending = pending && !on;
             // B tile of this node: 384 x 16 B, already in swizzled image form
@@ -220,12 +217,13 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
                 const unsigned long long *cnc = cn + (mine * k + 1);
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
-                    if (c < k) {
-                        const long long dot = ((long long)v[c] << 16) + ((long long)v[16 + c] << 8) + (long long)v[32 + c];
-                        const long long s = (long long)cnc[c] - (dot << 17);      // |c|^2 - 2 x.c, units 2^-32
-                        if (s < best) { second = best; best = s; arg = c; }
-                        else if (s < second) second = s;
-                    }
+                    if (c >= k) break;                                            // block-uniform: no predicated-off work
+                    // v1 * 256 + v2 < 2^32 (each accumulator < 2^23), so only one 64-bit multiply-add
+                    const unsigned int lo = (v[16 + c] << 8) + v[32 + c];
+                    const long long dot = (long long)(((unsigned long long)v[c] << 16) + lo);
+                    const long long s = (long long)cnc[c] - (dot << 17);          // |c|^2 - 2 x.c, units 2^-32
+                    if (s < best) { second = best; best = s; arg = c; }
+                    else if (s < second) second = s;
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
@@ -420,18 +418,15 @@ kmeans_mma_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ 
 
         // ---- assignment: one distance MMA per distinct node of the tile --------------------------------
         for (int pass = 0;; ++pass) {
-            long long mine = pending ? node : none;
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) {
-                const long long other = __shfl_xor_sync(VT_FULL, mine, o);
-                mine = other < mine ? other : mine;
-            }
-            if (lane == 0) s_min[warp] = mine;
+            // heap / level indices fit 31 bits (ids are int32 across the ABI): 32-bit warp minimum
+            int mine32 = pending ? (int)node : 0x7fffffff;
+            mine32 = __reduce_min_sync(VT_FULL, mine32);
+            if (lane == 0) s_min[warp] = mine32;
             __syncthreads();
-            mine = s_min[0];
+            long long mine = s_min[0];
 #pragma unroll
             for (int w = 1; w < 4; ++w) mine = s_min[w] < mine ? s_min[w] : mine;
-            if (mine == none) break;
+            if (mine == 0x7fffffff) break;
             const bool on = pending && node == mine;
             pending = pending && !on;
             const uint8_t *bsrc = bimg + (size_t)mine * MM_B_BYTES;
@@ -480,12 +475,12 @@ kmeans_mma_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ 
                 const unsigned long long *cnc = cn + mine * k;
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
-                    if (c < k) {
-                        const long long dot = ((long long)v[c] << 16) + ((long long)v[16 + c] << 8) + (long long)v[32 + c];
-                        const long long s = (long long)cnc[c] - (dot << 17);
-                        if (s < best) { second = best; best = s; arg = c; }
-                        else if (s < second) second = s;
-                    }
+                    if (c >= k) break;
+                    const unsigned int lo = (v[16 + c] << 8) + v[32 + c];
+                    const long long dot = (long long)(((unsigned long long)v[c] << 16) + lo);
+                    const long long s = (long long)cnc[c] - (dot << 17);
+                    if (s < best) { second = best; best = s; arg = c; }
+                    else if (s < second) second = s;
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
@@ -515,18 +510,15 @@ kmeans_mma_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ 
         // ---- accumulation: one one-hot MMA per distinct node of the tile --------------------------------
         pending = is_int;
         for (;;) {
-            long long mine = pending ? node : none;
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) {
-                const long long other = __shfl_xor_sync(VT_FULL, mine, o);
-                mine = other < mine ? other : mine;
-            }
-            if (lane == 0) s_min[warp] = mine;
+            // heap / level indices fit 31 bits (ids are int32 across the ABI): 32-bit warp minimum
+            int mine32 = pending ? (int)node : 0x7fffffff;
+            mine32 = __reduce_min_sync(VT_FULL, mine32);
+            if (lane == 0) s_min[warp] = mine32;
             __syncthreads();
-            mine = s_min[0];
+            long long mine = s_min[0];
 #pragma unroll
             for (int w = 1; w < 4; ++w) mine = s_min[w] < mine ? s_min[w] : mine;
-            if (mine == none) break;
+            if (mine == 0x7fffffff) break;
             const bool on = pending && node == mine;
             pending = pending && !on;
             if (mine != run_node || run_tiles >= 60000) { flush(); run_node = mine; }   // block-uniform
