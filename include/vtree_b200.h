@@ -107,10 +107,12 @@ int vt_quantize_mma_profile(const void *d_desc, int dtype, int64_t n, int dp,
 /* Host-buffer convenience used for end-to-end timing: descriptors in (preferably pinned) host
  * memory are streamed to the device in chunks on internal streams (copy/compute overlap), word
  * ids are copied back to h_word.  The tree stays device resident.  `chunk_rows` <= 0 picks a
- * default.  Blocks until h_word is complete. */
+ * default.  Blocks until h_word is complete.  Not re-entrant (one staging state per process). */
 int vt_quantize_host(const void *h_desc, int dtype, int64_t n, int dp,
                      const float *d_centroids, const uint8_t *d_internal, const int32_t *d_ref_id,
                      int k, int depth, int32_t *h_word, int64_t chunk_rows);
+/* vt_quantize_host keeps its device staging buffers and streams between calls; this frees them. */
+int vt_host_release(void);
 
 /* ---- tree build: VocabularyTree.fit, vocabulary.py:36-76, one LEVEL per call -------------
  * Members of all nodes of a level are processed in one launch.  d_perm[p] is the descriptor

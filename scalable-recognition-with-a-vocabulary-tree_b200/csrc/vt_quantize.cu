@@ -115,6 +115,74 @@ int64_t vt_mma_prepared_bytes(int k, int depth);
 int vt_mma_levels(const void *d_desc, int64_t n, const float *cent, const uint8_t *internal, const int32_t *ref_id, int k,
                   int depth, int32_t *leaf, int32_t *word, uint64_t *stats, const void *prepared, void *sortwork,
                   cudaStream_t s, cudaEvent_t *ev, int *n_ev_io);
+// Staging state of vt_quantize_host, kept between calls (allocating and freeing ~2 GB of device
+// buffers per call costs more than the copies it overlaps).  Released by vt_host_release().
+namespace {
+constexpr int HP_NS = 3;
+struct HostPipe {
+    bool valid = false;
+    int device = -1;
+    int64_t chunk_rows = 0, row_bytes = 0, work_bytes = 0, prepared_bytes = 0;
+    cudaStream_t st[HP_NS] = {};
+    void *dbuf[HP_NS] = {};
+    void *work[HP_NS] = {};
+    int32_t *wbuf[HP_NS] = {};
+    void *prepared = nullptr;
+    unsigned long long *d_flag = nullptr;
+};
+HostPipe g_pipe;
+
+void host_pipe_free()
+{
+    for (int s = 0; s < HP_NS; ++s) {
+        if (g_pipe.st[s]) { cudaStreamSynchronize(g_pipe.st[s]); cudaStreamDestroy(g_pipe.st[s]); }
+        if (g_pipe.dbuf[s]) cudaFree(g_pipe.dbuf[s]);
+        if (g_pipe.wbuf[s]) cudaFree(g_pipe.wbuf[s]);
+        if (g_pipe.work[s]) cudaFree(g_pipe.work[s]);
+    }
+    if (g_pipe.prepared) cudaFree(g_pipe.prepared);
+    if (g_pipe.d_flag) cudaFree(g_pipe.d_flag);
+    g_pipe = HostPipe();
+}
+
+int host_pipe_prepare(int64_t chunk_rows, int64_t row_bytes, int64_t work_bytes, int64_t prepared_bytes)
+{
+    int dev = 0;
+    VT_CUDA(cudaGetDevice(&dev));
+    if (g_pipe.valid && g_pipe.device == dev && g_pipe.chunk_rows == chunk_rows && g_pipe.row_bytes == row_bytes &&
+        g_pipe.work_bytes >= work_bytes && g_pipe.prepared_bytes >= prepared_bytes)
+        return VT_OK;
+    host_pipe_free();
+    bool ok = true;
+    for (int s = 0; s < HP_NS && ok; ++s) {
+        ok = cudaStreamCreateWithFlags(&g_pipe.st[s], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaMalloc(&g_pipe.dbuf[s], (size_t)(chunk_rows * row_bytes)) == cudaSuccess &&
+             cudaMalloc((void **)&g_pipe.wbuf[s], (size_t)chunk_rows * sizeof(int32_t)) == cudaSuccess &&
+             (work_bytes == 0 || cudaMalloc(&g_pipe.work[s], (size_t)work_bytes) == cudaSuccess);
+    }
+    ok = ok && (prepared_bytes == 0 || cudaMalloc(&g_pipe.prepared, (size_t)prepared_bytes) == cudaSuccess);
+    ok = ok && cudaMalloc((void **)&g_pipe.d_flag, 4 * sizeof(unsigned long long)) == cudaSuccess;
+    if (!ok) {
+        vt_set_error("vt_quantize_host: staging allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        host_pipe_free();
+        return VT_ENOMEM;
+    }
+    g_pipe.valid = true;
+    g_pipe.device = dev;
+    g_pipe.chunk_rows = chunk_rows;
+    g_pipe.row_bytes = row_bytes;
+    g_pipe.work_bytes = work_bytes;
+    g_pipe.prepared_bytes = prepared_bytes;
+    return VT_OK;
+}
+}  // namespace
+
+extern "C" int vt_host_release(void)
+{
+    host_pipe_free();
+    return VT_OK;
+}
+
 extern "C" int vt_quantize_host(const void *h_desc, int dtype, int64_t n, int dp, const float *d_centroids,
                                 const uint8_t *d_internal, const int32_t *d_ref_id, int k, int depth,
                                 int32_t *h_word, int64_t chunk_rows)
@@ -123,88 +191,59 @@ extern "C" int vt_quantize_host(const void *h_desc, int dtype, int64_t n, int dp
     VT_CHECK_ARG(dtype == VT_U8 || dtype == VT_F32, "bad dtype");
     VT_CHECK_ARG(d_ref_id != nullptr, "d_ref_id required");
     if (n == 0) return VT_OK;
-    const size_t esz = dtype == VT_U8 ? 1 : 4;
+    const int64_t esz = dtype == VT_U8 ? 1 : 4;
     if (chunk_rows <= 0) chunk_rows = (int64_t)1 << 22;
     if (chunk_rows > n) chunk_rows = n;
-    // large byte chunks go through the level-synchronous sorted descent (same ids, far less DRAM traffic)
-    const bool sorted = dtype == VT_U8 && depth >= 2 && chunk_rows >= ((int64_t)1 << 18);
-    // 128-byte rows and k <= 16: distance step on the INT8 tensor pipe (planes prepared once, shared by all chunks)
+    // large byte chunks go through the level-synchronous descent (same ids, far less DRAM traffic);
+    // 128-byte rows and k <= 16: distance step on the INT8 tensor pipe (planes prepared once per call)
+    const bool sorted = dtype == VT_U8 && depth >= 2 && chunk_rows >= ((int64_t)1 << 18) &&
+                        path_bits(k) <= 8 && (depth - 1) * path_bits(k) <= 32;
     const bool mma = sorted && dp == 128 && k <= 16 && getenv("VT_NO_MMA") == nullptr;
-    void *prepared = nullptr;
+    int rc = host_pipe_prepare(chunk_rows, dp * esz, sorted ? vt_quantize_sorted_work_bytes(chunk_rows) : 0,
+                               mma ? vt_mma_prepared_bytes(k, depth) : 0);
+    if (rc != VT_OK) return rc;
+    HostPipe &hp = g_pipe;
     bool use_mma = false;
-    constexpr int NS = 3;
-    cudaStream_t st[NS] = {};
-    void *dbuf[NS] = {};
-    void *work[NS] = {};
-    int32_t *wbuf[NS] = {};
-    int rc = VT_OK;
-    auto cleanup = [&]() {
-        for (int s = 0; s < NS; ++s) {
-            if (st[s]) { cudaStreamSynchronize(st[s]); cudaStreamDestroy(st[s]); }
-            if (dbuf[s]) cudaFree(dbuf[s]);
-            if (wbuf[s]) cudaFree(wbuf[s]);
-            if (work[s]) cudaFree(work[s]);
-            if (s == 0 && prepared) cudaFree(prepared);
-        }
-    };
-    for (int s = 0; s < NS; ++s) {
-        if (cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking) != cudaSuccess ||
-            cudaMalloc(&dbuf[s], (size_t)chunk_rows * dp * esz) != cudaSuccess ||
-            cudaMalloc((void **)&wbuf[s], (size_t)chunk_rows * sizeof(int32_t)) != cudaSuccess ||
-            (sorted && cudaMalloc(&work[s], (size_t)vt_quantize_sorted_work_bytes(chunk_rows)) != cudaSuccess)) {
-            vt_set_error("vt_quantize_host: staging allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
-            cleanup();
-            return VT_ENOMEM;
-        }
-    }
     if (mma) {
-        if (cudaMalloc(&prepared, (size_t)vt_mma_prepared_bytes(k, depth)) != cudaSuccess) {
-            vt_set_error("vt_quantize_host: plane allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
-            cleanup();
-            return VT_ENOMEM;
-        }
         // the tensor path needs every child centroid inside the 8.16 fixed-point range: the prepare
         // kernel counts violations and the chunks fall back to the FP32 kernels if there is one
-        unsigned long long *d_flag = nullptr, h_flag[4] = {0, 0, 0, 0};
-        if (cudaMalloc((void **)&d_flag, sizeof h_flag) != cudaSuccess || cudaMemsetAsync(d_flag, 0, sizeof h_flag, st[0]) != cudaSuccess)
-            rc = VT_ENOMEM;
-        if (rc == VT_OK) rc = vt_mma_prepare(d_centroids, k, depth, prepared, (uint64_t *)d_flag, st[0]);
-        if (rc == VT_OK && (cudaMemcpyAsync(h_flag, d_flag, sizeof h_flag, cudaMemcpyDeviceToHost, st[0]) != cudaSuccess ||
-                            cudaStreamSynchronize(st[0]) != cudaSuccess)) rc = VT_ECUDA;
-        if (d_flag) cudaFree(d_flag);
+        unsigned long long h_flag[4] = {0, 0, 0, 0};
+        if (cudaMemsetAsync(hp.d_flag, 0, sizeof h_flag, hp.st[0]) != cudaSuccess) rc = VT_ECUDA;
+        if (rc == VT_OK) rc = vt_mma_prepare(d_centroids, k, depth, hp.prepared, (uint64_t *)hp.d_flag, hp.st[0]);
+        if (rc == VT_OK && (cudaMemcpyAsync(h_flag, hp.d_flag, sizeof h_flag, cudaMemcpyDeviceToHost, hp.st[0]) != cudaSuccess ||
+                            cudaStreamSynchronize(hp.st[0]) != cudaSuccess)) rc = VT_ECUDA;
         use_mma = rc == VT_OK && h_flag[1] == 0;
     }
     int64_t done = 0;
     for (int c = 0; done < n && rc == VT_OK; ++c, done += chunk_rows) {
-        const int s = c % NS;
+        const int s = c % HP_NS;
         const int64_t rows = (n - done) < chunk_rows ? (n - done) : chunk_rows;
-        const char *src = (const char *)h_desc + (size_t)done * dp * esz;
-        if (cudaMemcpyAsync(dbuf[s], src, (size_t)rows * dp * esz, cudaMemcpyHostToDevice, st[s]) != cudaSuccess) {
+        const char *src = (const char *)h_desc + (size_t)(done * dp * esz);
+        if (cudaMemcpyAsync(hp.dbuf[s], src, (size_t)(rows * dp * esz), cudaMemcpyHostToDevice, hp.st[s]) != cudaSuccess) {
             vt_set_error("vt_quantize_host: H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
             rc = VT_ECUDA;
             break;
         }
         if (use_mma && rows >= ((int64_t)1 << 16))
-            rc = vt_mma_levels(dbuf[s], rows, d_centroids, d_internal, d_ref_id, k, depth, nullptr, wbuf[s], nullptr, prepared,
-                               work[s], st[s], nullptr, nullptr);
+            rc = vt_mma_levels(hp.dbuf[s], rows, d_centroids, d_internal, d_ref_id, k, depth, nullptr, hp.wbuf[s], nullptr,
+                               hp.prepared, hp.work[s], hp.st[s], nullptr, nullptr);
         else if (sorted && rows >= ((int64_t)1 << 16))
-            rc = vt_quantize_sorted_impl(dbuf[s], rows, dp, d_centroids, d_internal, d_ref_id, k, depth, nullptr, wbuf[s],
-                                         nullptr, work[s], st[s], nullptr);
+            rc = vt_quantize_sorted_impl(hp.dbuf[s], rows, dp, d_centroids, d_internal, d_ref_id, k, depth, nullptr,
+                                         hp.wbuf[s], nullptr, hp.work[s], hp.st[s], nullptr);
         else
-            rc = vt_quantize_dispatch(dbuf[s], dtype, rows, dp, d_centroids, d_internal, d_ref_id, k, depth, 0, nullptr,
-                                      wbuf[s], nullptr, st[s]);
+            rc = vt_quantize_dispatch(hp.dbuf[s], dtype, rows, dp, d_centroids, d_internal, d_ref_id, k, depth, 0, nullptr,
+                                      hp.wbuf[s], nullptr, hp.st[s]);
         if (rc != VT_OK) break;
-        if (cudaMemcpyAsync(h_word + done, wbuf[s], (size_t)rows * sizeof(int32_t), cudaMemcpyDeviceToHost, st[s]) !=
+        if (cudaMemcpyAsync(h_word + done, hp.wbuf[s], (size_t)rows * sizeof(int32_t), cudaMemcpyDeviceToHost, hp.st[s]) !=
             cudaSuccess) {
             vt_set_error("vt_quantize_host: D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
             rc = VT_ECUDA;
         }
     }
-    for (int s = 0; s < NS; ++s)
-        if (st[s] && cudaStreamSynchronize(st[s]) != cudaSuccess && rc == VT_OK) {
+    for (int s = 0; s < HP_NS; ++s)
+        if (cudaStreamSynchronize(hp.st[s]) != cudaSuccess && rc == VT_OK) {
             vt_set_error("vt_quantize_host: stream sync failed: %s", cudaGetErrorString(cudaGetLastError()));
             rc = VT_ECUDA;
         }
-    cleanup();
     return rc;
 }
