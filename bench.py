@@ -429,7 +429,7 @@ def bench_build(args, torch, vt, engine, dev, rank, world, comm, desc, barrier, 
     x = desc[: hi - lo]
     log = []
     stats = torch.zeros(4, dtype=torch.int64, device=dev)
-    engine.build_tree(x[: max(1, min(len(x), 500_000))], DIM, K_BRANCH, 3, n_iter=2, comm=comm)   # warm-up (module load, allocator)
+    engine.build_tree(x, DIM, K_BRANCH, DEPTH, n_iter=1, comm=comm)   # warm-up: module load, allocator pools for every level
     barrier()
     t0 = time.perf_counter()
     tree = engine.build_tree(x, DIM, K_BRANCH, DEPTH, n_iter=args.build_iters, comm=comm, stats=stats,
