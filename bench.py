@@ -425,8 +425,12 @@ def bench_retrieval(args, torch, vt, engine, nat, dev, rank, world, comm, ref_id
 def bench_build(args, torch, vt, engine, dev, rank, world, comm, desc, barrier, max_over_ranks):
     """VocabularyTree.fit at BASELINE configs[1]: k=10, L=6 on 10 M descriptors (sharded over the
     ranks, integer sums all-reduced per level-iteration)."""
+    # the SAME global dataset at every GPU count (rank r owns rows [lo, hi) of it), so the tree -- and the
+    # checksum reported below -- must not depend on the number of GPUs
     lo, hi = vt.dist.shard_range(args.build_desc, rank, world)
-    x = desc[: hi - lo]
+    cent0 = vt.synth.hierarchical_tree(K_BRANCH, DEPTH, DIM, seed=7, device=dev)
+    x = vt.synth.descriptors_from_tree(cent0, K_BRANCH, DEPTH, args.build_desc, seed=4242)[lo:hi].contiguous()
+    del cent0
     log = []
     stats = torch.zeros(4, dtype=torch.int64, device=dev)
     engine.build_tree(x, DIM, K_BRANCH, DEPTH, n_iter=1, comm=comm)   # warm-up: module load, allocator pools for every level
@@ -439,6 +443,7 @@ def bench_build(args, torch, vt, engine, dev, rank, world, comm, desc, barrier, 
     passes = sum(l["iters"] + (0 if l["converged"] else 1) + (1 if l["converged"] else 0) for l in log)
     member_passes = sum(l["members"] * (l["iters"] + 1) for l in log) * world
     return {"metric": "tree build k=10 L=6", "seconds": dt, "descriptors": args.build_desc, "n_iter": args.build_iters,
+            "tree_checksum": int(tree.device(dev)["centroids"].view(torch.int32).to(torch.int64).sum().item()),
             "nodes": int(tree.n_ref), "leaves_reached_depth": int((tree.level_ref == DEPTH).sum()),
             "assign_passes": passes, "member_assignments_per_s": member_passes / dt,
             "descriptors_per_s": args.build_desc / dt, "binary64_rechecks": int(stats[0].item()),
