@@ -201,8 +201,7 @@ score_shard_kernel(const uint32_t *__restrict__ post_off, const uint2 *__restric
 // ---- TF / L2 fast path ---------------------------------------------------------------------------
 // Same walk as score_shard_kernel, but the selection never touches most images: the dot products
 // are small exact integers, so an integer bound discards everything that cannot reach the top-k.
-//   T  = a lower bound of the k-th largest dot in the shard (k-th largest among the top-J lane maxima
-//        of every warp, J = ceil(k/8): a subset of all values);
+//   T  = the k-th largest dot in the shard (exact, from a 64-bin histogram of the dots >= 2);
 //   an image with dot < T * rho  (rho = min norm^-1 / max norm^-1 of the shard) has key
 //   dot/|d| < T * min|d|^-1 <= the key of each of the >= k images with dot >= T  ->  not in the top-k.
 // Survivors (typically a few dozen of 8192) get their binary64 key and one warp picks the k best.
@@ -223,14 +222,13 @@ score_shard_tf_kernel(const uint32_t *__restrict__ post_off, const uint2 *__rest
     int *s_acc = reinterpret_cast<int *>(s_raw);                               // [R]
     double *s_ckey = reinterpret_cast<double *>(s_raw + (size_t)R * 4);        // [SC_CAND]
     int *s_cslot = reinterpret_cast<int *>(s_raw + (size_t)R * 4 + SC_CAND * 8);   // [SC_CAND]
-    __shared__ int s_top[SC_WARPS * 8];
+    __shared__ int s_hist[64];
     __shared__ int s_thr, s_ncand;
     __shared__ double r_key[SC_WARPS];
     __shared__ int32_t r_id[SC_WARPS];
     __shared__ int r_owner[SC_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int TAKEN = (int)0x80000000;
-    const int J = (topk + SC_WARPS - 1) / SC_WARPS;                            // lane maxima kept per warp (<= 8)
 
     for (int64_t pair = blockIdx.x; pair < n_query * n_shards; pair += gridDim.x) {
         const int64_t q = pair / n_shards;
@@ -239,6 +237,7 @@ score_shard_tf_kernel(const uint32_t *__restrict__ post_off, const uint2 *__rest
         const int n_here = (int)((n_img - img0) < R ? (n_img - img0) : R);
         for (int t = threadIdx.x; t < R; t += SC_THREADS) s_acc[t] = 0;
         if (threadIdx.x == 0) s_ncand = 0;
+        if (threadIdx.x < 64) s_hist[threadIdx.x] = 0;
         __syncthreads();
         const int64_t qb = q_off[q], qe = q_off[q + 1];
         const uint32_t *off = post_off + shard;                 // row of (node, shard) = node * n_shards + shard
@@ -274,54 +273,49 @@ score_shard_tf_kernel(const uint32_t *__restrict__ post_off, const uint2 *__rest
         __syncthreads();
 
         // ---- integer bound -------------------------------------------------------------------------
+        // exact histogram of the dots >= 2 (clamped at 63); T = the k-th largest dot (or 63)
         const double rho = shard_rho ? shard_rho[shard] : -1.0;
-        int mymax = 0;
-#pragma unroll 8
+        int mine_acc[PER];
+#pragma unroll
         for (int u = 0; u < PER; ++u) {
             const int a = s_acc[u * SC_THREADS + threadIdx.x];
-            mymax = a > mymax ? a : mymax;
-        }
-        {
-            int v = mymax;
-            for (int j = 0; j < J; ++j) {                                       // top-J lane maxima of this warp
-                int w = v;
-#pragma unroll
-                for (int o = 16; o >= 1; o >>= 1) { const int t2 = __shfl_xor_sync(VT_FULL, w, o); w = t2 > w ? t2 : w; }
-                const unsigned int holders = __ballot_sync(VT_FULL, v == w);
-                if (lane == __ffs(holders) - 1) v = -1;                          // remove one instance
-                if (lane == 0) s_top[warp * 8 + j] = w;
-            }
+            mine_acc[u] = a;
+            if (a >= 2) atomicAdd(&s_hist[a < 63 ? a : 63], 1);
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            // k-th largest of the SC_WARPS*J collected values (selection by repeated maximum, tiny)
-            int thr = 0;
-            for (int r = 0; r < topk; ++r) {
-                int bi = -1, bv = -2;
-                for (int i = 0; i < SC_WARPS * J; ++i) {
-                    const int v = s_top[(i / J) * 8 + (i % J)];
-                    if (v > bv) { bv = v; bi = i; }
-                }
-                thr = bv;
-                if (bi >= 0) s_top[(bi / J) * 8 + (bi % J)] = -2;
+        if (warp == 0) {
+            // lanes walk the bins from the top: lane l owns bins 63-l and 31-l; inclusive prefix = images
+            // with a dot at least that large
+            int hi = s_hist[63 - lane], lo = lane < 30 ? s_hist[31 - lane] : 0;   // bins 0 and 1 are not counted
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t1 = __shfl_up_sync(VT_FULL, hi, o), t2 = __shfl_up_sync(VT_FULL, lo, o);
+                if (lane >= o) { hi += t1; lo += t2; }
             }
+            lo += __shfl_sync(VT_FULL, hi, 31);
+            const unsigned int mh = __ballot_sync(VT_FULL, hi >= topk), ml = __ballot_sync(VT_FULL, lo >= topk);
+            int thr = mh ? 63 - (__ffs(mh) - 1) : (ml ? 31 - (__ffs(ml) - 1) : 0);
             int d_lo = 0;
-            if (rho > 0.0 && thr >= 1) {
+            if (rho > 0.0 && thr >= 2) {
                 d_lo = (int)ceil((double)thr * rho);     // dot < d_lo  =>  dot <= d_lo - 1 < thr * rho: cannot win
-                if (d_lo < 1) d_lo = 1;
+                if (d_lo < 2) d_lo = 2;                  // (a bound of 1 keeps every touched image: use the fallback)
             }
-            s_thr = d_lo;                                                        // 0 => exhaustive fallback
+            if (lane == 0) s_thr = d_lo;                 // 0 => exhaustive fallback
         }
         __syncthreads();
         const int d_lo = s_thr;
         bool fast = d_lo > 0;
         if (fast) {
-#pragma unroll 8
+#pragma unroll
             for (int u = 0; u < PER; ++u) {
-                const int t = u * SC_THREADS + threadIdx.x;
-                if (s_acc[t] >= d_lo) {
-                    const int pos = atomicAdd(&s_ncand, 1);
-                    if (pos < SC_CAND) s_cslot[pos] = t;
+                const bool keep = mine_acc[u] >= d_lo;
+                const unsigned int m = __ballot_sync(VT_FULL, keep);
+                if (m) {                                                         // one atomic per warp and pass
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_ncand, __popc(m));
+                    base = __shfl_sync(VT_FULL, base, 0);
+                    const int pos = base + __popc(m & ((1u << lane) - 1u));
+                    if (keep && pos < SC_CAND) s_cslot[pos] = u * SC_THREADS + threadIdx.x;
                 }
             }
             __syncthreads();
