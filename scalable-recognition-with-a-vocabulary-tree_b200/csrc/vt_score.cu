@@ -207,7 +207,7 @@ score_shard_kernel(const uint32_t *__restrict__ post_off, const uint2 *__restric
 // Survivors (typically a few dozen of 8192) get their binary64 key and one warp picks the k best.
 // Shards with images without descriptors (rho < 0), T == 0 or more than SC_CAND survivors fall back
 // to the exhaustive selection (keys recomputed on demand).
-constexpr int SC_CAND = 1024;
+constexpr int SC_CAND = 256;
 
 template <int R>
 __global__ void __launch_bounds__(SC_THREADS)
@@ -512,7 +512,7 @@ static int launch_score_tf(const uint32_t *post_off, const void *postings, const
     const size_t smem = (size_t)R * 4 + SC_CAND * 12;
     VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t pairs = n_query * n_shards;
-    const int64_t cap = (int64_t)vt_sm_count() * 5 * 4;
+    const int64_t cap = (int64_t)vt_sm_count() * 6 * 4;
     kern<<<(int)(pairs < cap ? pairs : cap), SC_THREADS, smem, s>>>(post_off, (const uint2 *)postings, img_rnorm, n_img, n_ref,
                                                                     n_shards, q_off, q_node, q_val, n_query, topk, out_key,
                                                                     out_id, shard_rho);
