@@ -38,7 +38,7 @@ METRIC = "descriptors/s quantized (k=10,L=6 tree)"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-desc", type=int, default=100_000_000, help="descriptors per GPU")
