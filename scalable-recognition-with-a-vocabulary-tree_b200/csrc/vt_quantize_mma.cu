@@ -119,23 +119,11 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
     const uint64_t b_desc = make_desc(smem_u32(sB));
     uint32_t phase = 0;
 
-    // software pipeline across tiles: the permutation / path of the NEXT tile is loaded while the current
-    // one is processed, and its rows are pulled into L2 as soon as their indices are known
-    uint32_t nx_row = 0, nx_jp = 0;
-    {
-        const int64_t p0 = (int64_t)blockIdx.x * MM_TILE + tid;
-        if (p0 < n) { nx_row = perm ? perm[p0] : (uint32_t)p0; nx_jp = parent ? parent[p0] : 0u; }
-    }
     for (int64_t base = (int64_t)blockIdx.x * MM_TILE; base < n; base += (int64_t)gridDim.x * MM_TILE) {
         const int64_t p = base + tid;
         const bool valid = p < n;
-        const uint32_t row = valid ? nx_row : 0u;
-        const uint32_t jp = valid ? nx_jp : 0u;                  // packed path from the root
-        {
-            const int64_t pn = p + (int64_t)gridDim.x * MM_TILE;
-            nx_row = 0; nx_jp = 0;
-            if (pn < n) { nx_row = perm ? perm[pn] : (uint32_t)pn; nx_jp = parent ? parent[pn] : 0u; }
-        }
+        const uint32_t row = valid ? (perm ? perm[p] : (uint32_t)p) : 0u;
+        const uint32_t jp = valid && parent ? parent[p] : 0u;    // packed path from the root
         const bool alive = valid && (level == 0 || (jp & dmask) != dmask);
         const long long node = alive ? path_to_heap(jp, level, bits, k) : 0;
         const bool is_int = alive && (node * k + k < n_heap) && internal[node];
@@ -197,8 +185,6 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
                 }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
             }
-            if (pass == 0 && p + (int64_t)gridDim.x * MM_TILE < n)  // next tile's row on its way to L2
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(desc + (size_t)nx_row * 128));
             if (pass == 0 && is_int) {                          // overlap with the MMA: |x|^2 from the staged tile
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
