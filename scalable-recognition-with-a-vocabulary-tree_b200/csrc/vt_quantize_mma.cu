@@ -135,14 +135,20 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
         s_row[tid] = is_int ? row : 0xffffffffu;
         __syncthreads();
         // A tile: 8 lanes copy one 128 B row (coalesced), 16 rows per pass, swizzled destination
+        {
+            // row r = (tid >> 3) + 16 i: its swizzle phase (r & 7) does not depend on i, so the destination
+            // advances by a constant 2 KB per pass
+            const int r0 = tid >> 3, j = tid & 7;
+            const uint32_t dst0 = smem_u32(sA) + (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128 + ((j ^ (r0 & 7)) << 4));
+            const uint8_t *col = desc + j * 16;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = (tid >> 3) + 16 * i, j = tid & 7;
-            const uint32_t rr = s_row[r];
-            const uint8_t *src = rr != 0xffffffffu ? desc + (size_t)rr * 128 + j * 16 : desc;
-            const uint32_t dst = smem_u32(sA) + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
-            const int nbytes = rr != 0xffffffffu ? 16 : 0;     // zero fill for rows that take no part
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes));
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t rr = s_row[r0 + 16 * i];
+                const bool ok = rr != 0xffffffffu;
+                const uint8_t *src = col + (size_t)(ok ? rr : 0u) * 128;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + 2048u * i), "l"(src),
+                             "r"(ok ? 16 : 0));                 // zero fill for rows that take no part
+            }
         }
         long long best = none, second = none;
         int arg = 0;
@@ -402,14 +408,17 @@ kmeans_mma_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ 
         const uint8_t *xrow = desc + (size_t)row * 128;
         s_row[tid] = is_int ? row : 0xffffffffu;
         __syncthreads();
+        {
+            const int r0 = tid >> 3, j = tid & 7;
+            const uint32_t dst0 = smem_u32(sA) + (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128 + ((j ^ (r0 & 7)) << 4));
+            const uint8_t *col = desc + j * 16;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = (tid >> 3) + 16 * i, j = tid & 7;
-            const uint32_t rr = s_row[r];
-            const uint8_t *src = rr != 0xffffffffu ? desc + (size_t)rr * 128 + j * 16 : desc;
-            const uint32_t dst = smem_u32(sA) + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
-            const int nbytes = rr != 0xffffffffu ? 16 : 0;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes));
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t rr = s_row[r0 + 16 * i];
+                const bool ok = rr != 0xffffffffu;
+                const uint8_t *src = col + (size_t)(ok ? rr : 0u) * 128;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + 2048u * i), "l"(src), "r"(ok ? 16 : 0));
+            }
         }
         long long best = none, second = none;
         int arg = 0;
