@@ -506,3 +506,36 @@ def test_full_size_retrieval_properties(vt, cuda):
     assert torch.equal(o10["id"][:, 0].long(), q_rows) and bool((o10["score"][:, 0] == 0).all())
     assert bool((o10["score"][:, 1:] >= o10["score"][:, :-1]).all())
     assert torch.equal(o10["id"], o15["id"][:, :10])
+
+
+# ------------------------------------------------------------------------------------------ persistence
+def test_save_load_round_trip_and_reference_import(vt, cuda, tmp_path):
+    """VocabularyTree.save/load (vocabulary.py:148-159 has no load; ours adds it), Database.save/load
+    (database.py:83-101), and import of a tree the REFERENCE built (its nodes/tree dicts)."""
+    import pickle
+    g, meta = load_golden("small")
+    images, k, depth, n_iter = golden_inputs("small")
+    ds = vt.ArrayDataset(images)
+    voc = vt.encoders.VocabularyTree(k, depth, descriptor=lambda im: im, n_iter=n_iter)
+    voc.fit(np.concatenate(images))
+    db = vt.Database(ds, voc)
+    db.index()
+    want_ids, want_sc = db.retrieve_batch(ds.image_paths[:10], k=5)
+    assert voc.save(str(tmp_path)) and db.save(str(tmp_path))
+    # reference-format nodes.pickle: dict id -> centre
+    nodes = pickle.load(open(tmp_path / "nodes.pickle", "rb"))
+    assert all(np.array_equal(nodes[i], g["ref_nodes"][i]) for i in range(1, len(nodes)))
+    voc2 = vt.encoders.VocabularyTree(k, depth, descriptor=lambda im: im)
+    assert voc2.load(str(tmp_path))
+    db2 = vt.Database(ds, voc2)
+    assert db2.load(str(tmp_path)) and db2.is_indexed(ds.image_paths[3])
+    ids, sc = db2.retrieve_batch(ds.image_paths[:10], k=5)
+    assert np.array_equal(ids, want_ids) and np.array_equal(sc, want_sc)
+    # a tree handed over by the reference (dicts as in voc.nodes / voc.tree)
+    ref_nodes, ref_tree = golden_tree_dicts(g, k)
+    voc3 = vt.encoders.VocabularyTree(k, depth, descriptor=lambda im: im)
+    voc3.set_tree(vt.FlatTree.from_reference_dicts(ref_nodes, ref_tree, k, depth))
+    x = np.concatenate(images)
+    assert np.array_equal(voc3.quantize(x), voc.quantize(x))
+    # loading a missing index prints and carries on, like the reference's bare except (database.py:99-100)
+    assert vt.Database(ds, voc2).load(str(tmp_path / "nowhere"))
