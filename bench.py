@@ -342,7 +342,10 @@ def main():
             "whole_step": {"step_ms_events": kern_ms,
                            "algorithmic_GBps": alg_bytes * per_launch / (kern_ms * 1e-3) / 1e9,
                            "algorithmic_TFLOPs": flop_per_desc * per_launch / (kern_ms * 1e-3) / 1e12},
-            "traffic": None,
+            # DRAM bytes per launch of the dominant kernel: ncu --set full (profiles/r01_ncu_final_level_mma_and_scorer.txt,
+            # dram__bytes_read.sum + dram__bytes_write.sum of a 16 M-row level-0 launch = 136.2 B per row), scaled to this launch
+            "traffic": (136.2 * per_launch) if method == "mma" else None,
+            "traffic_source": "ncu capture of a 16 M-row launch, scaled by rows (not re-measured in this run)" if method == "mma" else None,
             "other_engine": dict(fill(other_r, other_total_ms), level_kernel_ms=[round(float(v), 3) for v in other_ms]),
             "fused_single_launch_descent": {"value": fused_rate, "unit": "descriptors/s", "rows": n_f},
         })
