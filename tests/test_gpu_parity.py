@@ -539,3 +539,47 @@ def test_save_load_round_trip_and_reference_import(vt, cuda, tmp_path):
     assert np.array_equal(voc3.quantize(x), voc.quantize(x))
     # loading a missing index prints and carries on, like the reference's bare except (database.py:99-100)
     assert vt.Database(ds, voc2).load(str(tmp_path / "nowhere"))
+
+
+def test_c1_full_pipeline_matches_reference(vt, cuda):
+    """BASELINE configs[0] at full size through the public API: 1,491 images x 1,000 SIFT-128, k=10, L=3.
+    fit -> the reference's tree (bit exact); index -> the reference's postings / embeddings; retrieve ->
+    the reference's top-32 order for the 64 stored queries (float32 near-tie rows aside)."""
+    import hashlib
+    g, meta = load_golden("c1")
+    images, k, depth, n_iter = golden_inputs("c1")
+    ds = vt.ArrayDataset(images)
+    voc = vt.encoders.VocabularyTree(k, depth, descriptor=lambda im: im, n_iter=n_iter)
+    x = np.concatenate(images)
+    voc.fit(x)
+    nodes, tree = golden_tree_dicts(g, k)
+    assert voc.tree == tree
+    mine = voc.nodes
+    assert all(np.array_equal(mine[i], nodes[i]) for i in range(1, len(nodes)))
+    words = voc.quantize(x)
+    ref_leaf = g["ref_leaf"].astype(np.int32)
+    diff = np.nonzero(words != ref_leaf)[0]
+    assert len(diff) <= 30                                      # the float32 near-ties of the literal reference
+    db = vt.Database(ds, voc)
+    db.index()
+    touched = set((np.searchsorted(np.cumsum([len(i) for i in images]), diff, side="right")).tolist())
+    ro, node, count = db._host
+    dense = csr_to_dense(ro[:17], node, count, voc.flat.n_ref)
+    for i in range(16):
+        if i not in touched:
+            assert np.array_equal(dense[i], g["counts_head"][i])
+            assert np.array_equal(db.embedding(ds.image_paths[i]), g["emb_head"][i])
+    if not touched:
+        full = csr_to_dense(ro, node, count, voc.flat.n_ref).astype(np.int32)
+        assert hashlib.sha256(full.tobytes()).hexdigest() == str(g["counts_sha256"])
+    q_idx = g["q_idx"]
+    ids, sc = db.retrieve_batch([ds.image_paths[i] for i in q_idx], k=32)
+    ref_order, ref_sc = g["order"].astype(np.int64), g["scores"]
+    for qi in range(len(q_idx)):
+        if touched and (int(q_idx[qi]) in touched or touched & set(ref_order[qi].tolist())):
+            continue                                            # a near-tie descriptor moved one count: skip that row
+        np.testing.assert_allclose(sc[qi], ref_sc[qi], rtol=1e-5, atol=1e-7)
+        bad = np.nonzero(ids[qi] != ref_order[qi])[0]
+        for b in bad:                                           # only rounding-level score ties may swap
+            assert abs(ref_sc[qi][b] - sc[qi][b]) <= 1e-9 and ids[qi][b] in ref_order[qi]
+    assert ids[0][0] == q_idx[0] and sc[0][0] == 0.0
