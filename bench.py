@@ -257,7 +257,7 @@ def main():
     level_ms, sort_ms = stage_profile(lib.vt_quantize_mma_profile if method == "mma" else lib.vt_quantize_sorted_profile)
     other_ms, _ = stage_profile(lib.vt_quantize_sorted_profile if method == "mma" else lib.vt_quantize_mma_profile, reps=1)
     sort_passes = DEPTH - 1                     # packed paths: one radix pass (hist, scan, scatter) per level transition
-    launches_per_step = DEPTH + 3 * sort_passes + (1 if method == "mma" else 0)
+    launches_per_step = DEPTH + 3 * sort_passes     # (the tensor path's byte planes are prepared once per tree, outside the steps)
 
     # the single-launch fused descent on a slice, for comparison
     n_f = min(n, 8_000_000)

@@ -98,6 +98,16 @@ int vt_quantize_mma(const void *d_desc, int dtype, int64_t n, int dp,
                     const float *d_centroids, const uint8_t *d_internal, const int32_t *d_ref_id,
                     int k, int depth, int32_t *d_leaf_heap, int32_t *d_word, uint64_t *d_stats,
                     void *d_work, int64_t work_bytes, void *stream);
+/* planes depend only on the tree: prepare them once (vt_quantize_mma_planes_bytes(k, depth) bytes) and
+ * reuse them for every batch; d_work then only needs 16 n + vt_sort_scratch_bytes(n) bytes */
+int64_t vt_quantize_mma_planes_bytes(int k, int depth);
+int vt_quantize_mma_prepare(const float *d_centroids, int k, int depth, void *d_planes,
+                            uint64_t *d_stats, void *stream);
+int vt_quantize_mma_prepared(const void *d_desc, int dtype, int64_t n, int dp,
+                             const float *d_centroids, const uint8_t *d_internal,
+                             const int32_t *d_ref_id, int k, int depth, int32_t *d_leaf_heap,
+                             int32_t *d_word, uint64_t *d_stats, const void *d_planes, void *d_work,
+                             int64_t work_bytes, void *stream);
 int vt_quantize_mma_profile(const void *d_desc, int dtype, int64_t n, int dp,
                             const float *d_centroids, const uint8_t *d_internal,
                             const int32_t *d_ref_id, int k, int depth, int32_t *d_leaf_heap,

@@ -30,6 +30,9 @@ SIGNATURES = {
     "vt_quantize_sorted_profile": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _int, _int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "vt_quantize_mma_work_bytes": (_i64, [_i64, _int, _int]),
     "vt_quantize_mma": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _int, _int, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "vt_quantize_mma_planes_bytes": (_i64, [_int, _int]),
+    "vt_quantize_mma_prepare": (_int, [_vp, _int, _int, _vp, _vp, _vp]),
+    "vt_quantize_mma_prepared": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "vt_quantize_mma_profile": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _int, _int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "vt_quantize_host": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _int, _int, _vp, _i64]),
     "vt_host_release": (_int, []),

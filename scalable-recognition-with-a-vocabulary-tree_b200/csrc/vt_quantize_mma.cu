@@ -772,3 +772,31 @@ extern "C" int vt_quantize_mma_profile(const void *d_desc, int dtype, int64_t n,
     for (int i = 0; i < n_ev; ++i) cudaEventDestroy(ev[i]);
     return rc;
 }
+
+// ---- planes prepared once per tree (they only depend on the centroids) -----------------------------------
+extern "C" int64_t vt_quantize_mma_planes_bytes(int k, int depth) { return vt_mma_prepared_bytes(k, depth); }
+
+extern "C" int vt_quantize_mma_prepare(const float *d_centroids, int k, int depth, void *d_planes, uint64_t *d_stats,
+                                       void *stream)
+{
+    VT_CHECK_ARG(d_centroids && d_planes && k >= 1 && k <= 16 && depth >= 1 && depth <= 16, "bad arguments");
+    return vt_mma_prepare(d_centroids, k, depth, d_planes, d_stats, (cudaStream_t)stream);
+}
+
+// vt_quantize_mma with planes from vt_quantize_mma_prepare; d_work: 16 n + vt_sort_scratch_bytes(n) bytes
+extern "C" int vt_quantize_mma_prepared(const void *d_desc, int dtype, int64_t n, int dp, const float *d_centroids,
+                                        const uint8_t *d_internal, const int32_t *d_ref_id, int k, int depth,
+                                        int32_t *d_leaf_heap, int32_t *d_word, uint64_t *d_stats, const void *d_planes,
+                                        void *d_work, int64_t work_bytes, void *stream)
+{
+    VT_CHECK_ARG(dtype == VT_U8 && dp == 128, "the tensor-core descent takes 128-byte descriptor rows");
+    VT_CHECK_ARG(n >= 0 && n < ((int64_t)1 << 31), "n out of range");
+    VT_CHECK_ARG(k >= 1 && k <= 16 && depth >= 1 && depth <= 16, "k must be <= 16 and depth >= 1");
+    VT_CHECK_ARG(d_centroids && d_internal && d_planes, "null tree / planes");
+    VT_CHECK_ARG(d_word == nullptr || d_ref_id != nullptr, "d_word needs d_ref_id");
+    VT_CHECK_ARG(d_work && work_bytes >= 16 * (n > 0 ? n : 1) + vt_sort_scratch_bytes(n), "workspace too small");
+    VT_CHECK_ARG((depth - 1) * path_bits(k) <= 32, "k / depth too large for 32-bit packed paths");
+    if (n == 0) return VT_OK;
+    return vt_mma_levels(d_desc, n, d_centroids, d_internal, d_ref_id, k, depth, d_leaf_heap, d_word, d_stats, d_planes,
+                         d_work, (cudaStream_t)stream, nullptr, nullptr);
+}

@@ -97,13 +97,22 @@ def quantize(tree_dev: dict, k: int, depth: int, desc: torch.Tensor, want_heap: 
         big = desc.dtype == torch.uint8 and start == 0 and n >= SORTED_MIN_ROWS and depth >= 2
         method = ("mma" if tree_dev.get("mma_ok", False) else "sorted") if big else "fused"
     if method == "mma":
-        need = int(lib.vt_quantize_mma_work_bytes(n, k, depth))
+        # the byte planes depend only on the tree: prepared once and kept with the tree's device tensors
+        planes = tree_dev.get("_mma_planes")
+        if planes is None or tree_dev.get("_mma_planes_for") != (tree_dev["centroids"].data_ptr(), k, depth):
+            planes = torch.empty(int(lib.vt_quantize_mma_planes_bytes(k, depth)), dtype=torch.uint8, device=desc.device)
+            nat.check(lib.vt_quantize_mma_prepare(nat.ptr(tree_dev["centroids"]), k, depth, nat.ptr(planes), nat.ptr(stats),
+                                                  nat.stream_ptr()), "vt_quantize_mma_prepare")
+            tree_dev["_mma_planes"] = planes
+            tree_dev["_mma_planes_for"] = (tree_dev["centroids"].data_ptr(), k, depth)
+        need = 16 * max(n, 1) + int(lib.vt_sort_scratch_bytes(n))
         if work is None or work.numel() * work.element_size() < need:
             work = torch.empty(need, dtype=torch.uint8, device=desc.device)
-        nat.check(lib.vt_quantize_mma(nat.ptr(desc), _dtype_code(desc), n, dp, nat.ptr(tree_dev["centroids"]),
-                                      nat.ptr(tree_dev["internal"]), nat.ptr(tree_dev["ref_id"]), k, depth,
-                                      nat.ptr(leaf), nat.ptr(word), nat.ptr(stats), nat.ptr(work),
-                                      work.numel() * work.element_size(), nat.stream_ptr()), "vt_quantize_mma")
+        nat.check(lib.vt_quantize_mma_prepared(nat.ptr(desc), _dtype_code(desc), n, dp, nat.ptr(tree_dev["centroids"]),
+                                               nat.ptr(tree_dev["internal"]), nat.ptr(tree_dev["ref_id"]), k, depth,
+                                               nat.ptr(leaf), nat.ptr(word), nat.ptr(stats), nat.ptr(planes),
+                                               nat.ptr(work), work.numel() * work.element_size(), nat.stream_ptr()),
+                  "vt_quantize_mma_prepared")
     elif method == "sorted":
         need = int(lib.vt_quantize_sorted_work_bytes(n))
         if work is None or work.numel() * work.element_size() < need:
