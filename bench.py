@@ -469,7 +469,17 @@ def cpu_baseline(args, vt, cent, exists, internal, ref_id, n_ref, desc, words):
     leaf = vo.descend(tree, x)
     dt = time.perf_counter() - t0
     mism = int((ref_id[leaf] != words[:sample].cpu().numpy()).sum())
-    return {"value": sample / dt, "unit": "descriptors/s", "cores": os.cpu_count(), "kind": "port",
+    # what the reference's own Python costs per descriptor: its propagate_feature loop restated line by line
+    # (float32 np.linalg.norm per child, one interpreter thread), on a small slice
+    n_lit = 3000
+    t0 = time.perf_counter()
+    lit = vo.descend_literal(tree, x[:n_lit])
+    dt_lit = time.perf_counter() - t0
+    lit_mism = int((lit != leaf[:n_lit]).sum())
+    return {"python_literal": {"value": n_lit / dt_lit, "unit": "descriptors/s", "cores": 1, "sample": n_lit,
+                               "what": "line-by-line restatement of VocabularyTree.propagate_feature (vocabulary.py:104-124)",
+                               "differs_from_binary64_oracle_on": lit_mism},
+            "value": sample / dt, "unit": "descriptors/s", "cores": os.cpu_count(), "kind": "port",
             "sample": "first %d descriptors of the GPU workload, oracle/vt_oracle.c vt_or_descend (binary64), %.1f s" % (sample, dt),
             "gpu_word_mismatches_on_sample": mism}
 

@@ -248,6 +248,32 @@ def descend(tree: dict, x, want_path: bool = False, want_gap: bool = False):
     return out[0] if len(out) == 1 else tuple(out)
 
 
+def descend_literal(tree: dict, x) -> np.ndarray:
+    """Line-by-line restatement of ``VocabularyTree.propagate_feature`` (vocabulary.py:104-124) with the
+    reference's own arithmetic: float32 ``np.linalg.norm([centre - feature])`` per child, strict ``<``.
+    Pure-Python loops -- only for small samples (it is what the reference costs per descriptor) and for
+    pinning: on the machine that made the goldens it reproduces ``ref_leaf`` exactly."""
+    x = np.asarray(x, dtype=np.float32)
+    d = x.shape[1]
+    k = tree["k"]
+    cent = tree["centroids"][:, :d]
+    internal = tree["internal"]
+    out = np.empty(len(x), np.int32)
+    for i, feature in enumerate(x):
+        node = 0
+        while node * k + k < len(internal) and internal[node]:      # graph.out_degree(node) > 0
+            min_dist = float("inf")
+            closest = None
+            for child in range(node * k + 1, node * k + 1 + k):     # insertion order == child index order
+                distance = np.linalg.norm([cent[child] - feature])
+                if distance < min_dist:
+                    min_dist = distance
+                    closest = child
+            node = closest
+        out[i] = node
+    return out
+
+
 def heap_path_to_ref(tree: dict, path: np.ndarray) -> list:
     """heap paths [n, depth+1] (-1 padded) -> list of reference-id lists, like
     ``propagate_feature`` returns (vocabulary.py:111-124)."""

@@ -2,13 +2,16 @@
 // cbir/database.py:59-81), batched over queries.
 //
 // The database is sharded by image range (shard_size images, the same rule that shards it across
-// GPUs).  One CTA scores one (query, shard) pair: it walks the posting list of every query word
-// inside that shard (CSR, 8 B per posting: local image id + tf or weight), accumulates the sparse
-// dot products of all shard images in shared memory, converts them to rank keys and selects the
-// shard's top-k.  A second kernel merges the per-shard lists of a query and turns keys into the
+// GPUs).  One CTA scores one (query, shard) pair: its lanes walk the posting lists of the query's
+// words inside that shard (node-major CSR, 8 B per posting: local image id + tf or weight) with
+// several words and postings in flight per lane, accumulate the sparse dot products of all shard
+// images in shared memory, and select the shard's top-k -- in tf mode (the reference's semantics,
+// score_shard_tf_kernel) through an exact integer bound so that only a few dozen survivors need a
+// binary64 rank key; the float tf-idf / L1 modes and the full score dump use the exhaustive
+// score_shard_kernel.  A second kernel merges the per-shard lists of a query and turns keys into the
 // reference's score (database.py:66-70: L2 distance of the L2-normalised vectors, NaN -> 1e6).
 // HBM traffic per query: 8 B x (sum of the posting lengths of its words) + 8 B per (word, shard)
-// row-pointer pair.
+// row-pointer pair; the measured bound is the shared-memory atomic rate (one atomic per posting).
 //
 // Rank key (larger is better), ties broken by smaller image index like the reference's stable
 // ascending sort (database.py:79-80):
@@ -22,8 +25,6 @@ namespace {
 constexpr int SC_THREADS = 256;
 constexpr int SC_WARPS = SC_THREADS / 32;
 constexpr int SC_MAXK = 64;
-
-struct Cand { double key; int32_t id; };
 
 __device__ __forceinline__ bool better(double ka, int32_t ia, double kb, int32_t ib)
 {

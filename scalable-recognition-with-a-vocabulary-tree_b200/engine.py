@@ -7,6 +7,7 @@ Reference functions covered (cbir/encoders/vocabulary.py, cbir/database.py):
 ``stage``      input side of ``extract_features`` (:29-34)        -> byte / float rows on device
 ``build_tree`` ``VocabularyTree.fit`` (:36-76), level synchronous  -> FlatTree
 ``quantize``   ``propagate_feature`` (:104-124), batched           -> reference node ids
+               (three engines with identical ids: fused SIMT, level-synchronous SIMT, tcgen05)
 ``encode``     ``propagate`` + ``embedding`` (:78-137), batched    -> CSR (node, tf), norms
 ``build_index``the per-node posting dicts (:96-100)                -> sharded inverted CSR
 ``score``      ``Database.score`` / ``retrieve`` (database.py:59-81) -> top-k ids and scores

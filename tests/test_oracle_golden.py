@@ -70,6 +70,20 @@ def test_encoding_and_scoring_match_reference(name):
         assert np.array_equal(sc[order], g["scores"][qi])
 
 
+@pytest.mark.parametrize("name", ["small", "orb"])
+def test_literal_restatement_reproduces_reference_paths(name):
+    """The Python-loop restatement with the reference's float32 arithmetic gives the reference's leaves
+    (checked on a slice; exact on the machine/BLAS that generated the goldens, near-ties aside elsewhere)."""
+    g, meta = load_golden(name)
+    images, k, depth, n_iter = golden_inputs(name)
+    x = np.concatenate(images)[:1500]
+    t = vo.build_tree(np.concatenate(images), k, depth, n_iter)
+    got = t["ref_id"][vo.descend_literal(t, x)]
+    _, gap = vo.descend(t, x, want_gap=True)
+    bad = np.nonzero(got != g["ref_leaf"][:len(x)])[0]
+    assert np.all(gap[bad] < 1e-5) and len(bad) <= 2
+
+
 def test_adversarial_case_has_the_edge_cases():
     g, meta = load_golden("adversarial")
     counts = g["counts"]
