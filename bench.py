@@ -126,6 +126,25 @@ def hashed_words(torch, img_ids, words_per_image, n_leaf, leaf_ref_base, device)
     return leaf_ref_base[leaf].to(torch.int32).reshape(-1)
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pin this process to the CPUs NVML reports as local to GPU `index` (multi-socket hosts: the pinned
+    staging buffers of the end-to-end path then live on the GPU's own NUMA node).  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * w + b for w, bits in enumerate(words) for b in range(64) if (bits >> b) & 1 and 64 * w + b < n_cpu]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return len(allowed)
+    except Exception:
+        pass
+    return None
+
+
 # ----------------------------------------------------------------------------------- reference arm
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm for the path (oracle port, all host threads)
@@ -183,6 +202,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = bind_to_gpu_numa_node(local)      # pinned host buffers are first-touched next to the GPU's PCIe root
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -359,14 +379,14 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "descriptors/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8 x fixed-point (int32 accumulate)" if method == "mma" else "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "u8" if method == "mma" else "f32", "data": "synthetic",
             "config": {"workload": "BASELINE configs[2]: quantize %d SIFT-128 byte descriptors per GPU through a "
                                    "k=10 L=6 (1,111,111-node) tree, tree replicated, descriptors sharded" % n,
                        "l2": "input (%.1f GB) is larger than L2; nothing is flushed between steps" % (n * DIM / 1e9),
                        "tree": "synthetic hierarchical mixture, seed 7", "binary64_rechecks_per_step": rechecks // max(args.steps, 1)},
             "e2e": {"value": e2e_value, "unit": "descriptors/s", "h2d_bytes_per_step": n_e2e * DIM,
                     "d2h_bytes_per_step": n_e2e * 4, "descriptors_per_step": n_e2e, "matches_device_path": e2e_ok,
-                    "api": "vt_quantize_host (engine.quantize_host)"},
+                    "api": "vt_quantize_host (engine.quantize_host)", "cpus_bound_to_gpu_node": affinity},
             "gpu_launches": args.steps * launches_per_step,
             "clocks": clocks.summary(),
             "roofline": roofline,
