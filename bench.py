@@ -430,11 +430,25 @@ def bench_retrieval(args, torch, vt, engine, nat, dev, rank, world, comm, ref_id
         off = torch.arange(len(ids) + 1, dtype=torch.int64, device=dev) * wpi
         return engine.encode(words, off, dummy, DEPTH, n_ref, all_nodes=all_nodes)
 
+    # words of this rank's images (synthetic), then the two index-side stages timed separately
+    db_ids = torch.arange(lo, hi, device=dev)
+    db_words = torch.empty(len(db_ids) * wpi, dtype=torch.int32, device=dev)
+    for s0 in range(0, len(db_ids), 65536):
+        e0 = min(len(db_ids), s0 + 65536)
+        db_words[s0 * wpi:e0 * wpi] = hashed_words(torch, db_ids[s0:e0], wpi, n_leaf, leaf_ref, dev)
+    db_off = torch.arange(len(db_ids) + 1, dtype=torch.int64, device=dev) * wpi
+    engine.encode(db_words[:wpi * 64], db_off[:65], dummy, DEPTH, n_ref, all_nodes=all_nodes)      # warm-up
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    csr = encode_ids(torch.arange(lo, hi, device=dev))
+    csr = engine.encode(db_words, db_off, dummy, DEPTH, n_ref, all_nodes=all_nodes)
+    torch.cuda.synchronize()
+    t_encode = time.perf_counter() - t0
+    del db_words
+    t0 = time.perf_counter()
     index = engine.build_index(csr, n_ref)
     torch.cuda.synchronize()
-    t_index = time.perf_counter() - t0
+    t_invert = time.perf_counter() - t0
+    t_index = t_encode + t_invert
     q = args.queries if queries is None else queries
     member = (torch.arange(q // 2, device=dev, dtype=torch.int64) * 197) % max(db_images, 1)
     fresh = db_images + torch.arange(q - q // 2, device=dev, dtype=torch.int64)
@@ -462,7 +476,14 @@ def bench_retrieval(args, torch, vt, engine, nat, dev, rank, world, comm, ref_id
            "value": q / (ms * 1e-3), "unit": "queries/s", "ms_per_batch": ms, "queries": q, "db_images": db_images,
            "words_per_image": wpi, "mode": "all-nodes tf/L2 (reference semantics)" if all_nodes else "leaf-words tf/L2",
            "entries_per_image": float(csr["nnz"]) / max(hi - lo, 1),
-           "self_match_rank0": ok, "index_build_s": t_index, "n_shards_per_gpu": index["n_shards"]}
+           "self_match_rank0": ok, "index_build_s": t_index, "n_shards_per_gpu": index["n_shards"],
+           # HBM-bound index-side stages: bytes that must move (two encode passes read the 4 B words, the fill pass
+           # writes 8 B per entry; inversion = 12 B keys/entry/image out + radix passes at 20 B + 16 B gather/fill)
+           "encode": {"seconds": t_encode, "images_per_s": (hi - lo) / t_encode,
+                      "algorithmic_GBps": (8.0 * (hi - lo) * wpi + 8.0 * csr["nnz"]) / t_encode / 1e9},
+           "invert": {"seconds": t_invert, "postings_per_s": csr["nnz"] / t_invert,
+                      "algorithmic_GBps": csr["nnz"] * (12.0 + 20.0 * -(-int(index["n_shards"] * n_ref).bit_length() // 8) + 16.0)
+                                          / t_invert / 1e9}}
     if not all_nodes:
         alg = 8.0 * wpi * (db_images * wpi / n_leaf)
         out["hbm"] = {"algorithmic_bytes_per_query": alg, "achieved_GBps": alg * q / (ms * 1e-3) / 1e9}
@@ -489,7 +510,9 @@ def bench_build(args, torch, vt, engine, dev, rank, world, comm, desc, barrier, 
     dt = max_over_ranks(time.perf_counter() - t0)
     passes = sum(l["iters"] + (0 if l["converged"] else 1) + (1 if l["converged"] else 0) for l in log)
     member_passes = sum(l["members"] * (l["iters"] + 1) for l in log) * world
-    return {"metric": "tree build k=10 L=6", "seconds": dt, "descriptors": args.build_desc, "n_iter": args.build_iters,
+    return {"metric": "tree build k=10 L=6", "seconds": dt,
+            # 128 B row + 4 B permutation + 4 B node + 1 B label per member and assignment pass
+            "algorithmic_GBps": 137.0 * member_passes / dt / 1e9, "descriptors": args.build_desc, "n_iter": args.build_iters,
             "tree_checksum": int(tree.device(dev)["centroids"].view(torch.int32).to(torch.int64).sum().item()),
             "nodes": int(tree.n_ref), "leaves_reached_depth": int((tree.level_ref == DEPTH).sum()),
             "assign_passes": passes, "member_assignments_per_s": member_passes / dt,
