@@ -80,7 +80,7 @@ prep_planes_kernel(const float *__restrict__ cent, int64_t n_int, int k, uint8_t
 }
 
 // ---- one tree level -------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MM_TILE, 8)
+__global__ void __launch_bounds__(MM_TILE, 6)
 level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ parent,
                  int64_t n, int level, int bits, int64_t n_heap, int k, int is_last,
                  const float *__restrict__ cent, const uint8_t *__restrict__ internal, const int32_t *__restrict__ ref_id,
@@ -688,7 +688,7 @@ int vt_mma_levels(const void *d_desc, int64_t n, const float *cent, const uint8_
         VT_CUDA(cudaFuncSetAttribute(level_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    const int64_t want = (n + MM_TILE - 1) / MM_TILE, cap = (int64_t)vt_sm_count() * 8;
+    const int64_t want = (n + MM_TILE - 1) / MM_TILE, cap = (int64_t)vt_sm_count() * 6;
     const int blocks = (int)(want < cap ? want : cap);
     uint32_t *keys = kA, *perm = pA, *tkeys = kB, *tperm = pB;
     const uint32_t *cur_perm = nullptr, *cur_parent = nullptr;
