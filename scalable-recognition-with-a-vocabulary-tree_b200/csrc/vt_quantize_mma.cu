@@ -119,11 +119,23 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
     const uint64_t b_desc = make_desc(smem_u32(sB));
     uint32_t phase = 0;
 
+    // the permutation / path of the NEXT tile is loaded while the current one is processed: one DRAM round
+    // trip less on the per-tile dependency chain (prefetching the rows themselves into L2 measured slower)
+    uint32_t nx_row = 0, nx_jp = 0;
+    {
+        const int64_t p0 = (int64_t)blockIdx.x * MM_TILE + tid;
+        if (p0 < n) { nx_row = perm ? perm[p0] : (uint32_t)p0; nx_jp = parent ? parent[p0] : 0u; }
+    }
     for (int64_t base = (int64_t)blockIdx.x * MM_TILE; base < n; base += (int64_t)gridDim.x * MM_TILE) {
         const int64_t p = base + tid;
         const bool valid = p < n;
-        const uint32_t row = valid ? (perm ? perm[p] : (uint32_t)p) : 0u;
-        const uint32_t jp = valid && parent ? parent[p] : 0u;    // packed path from the root
+        const uint32_t row = valid ? nx_row : 0u;
+        const uint32_t jp = valid ? nx_jp : 0u;                  // packed path from the root
+        {
+            const int64_t pn = p + (int64_t)gridDim.x * MM_TILE;
+            nx_row = 0; nx_jp = 0;
+            if (pn < n) { nx_row = perm ? perm[pn] : (uint32_t)pn; nx_jp = parent ? parent[pn] : 0u; }
+        }
         const bool alive = valid && (level == 0 || (jp & dmask) != dmask);
         const long long node = alive ? path_to_heap(jp, level, bits, k) : 0;
         const bool is_int = alive && (node * k + k < n_heap) && internal[node];
