@@ -146,10 +146,45 @@ def run_case(name: str, n_query=None, store_full=True):
         name, n_ref, t_fit, t_desc, t_index, t_ret, path, os.path.getsize(path) / 1024))
 
 
+def run_persist(name="adversarial"):
+    """tests/golden/persist/: the files the reference's own ``VocabularyTree.save`` and
+    ``Database.save`` write (vocabulary.py:148-159, database.py:83-91) for one small case.
+    ``nx.write_gpickle`` no longer exists in the installed networkx 3; it is restored for the call
+    with its networkx-2 body (``pickle.dump(G, f, HIGHEST_PROTOCOL)``).  ``keys.json`` records the
+    salted ``hash(abspath)`` key the reference gave each image in the generating process."""
+    import pickle
+    import networkx as nx
+    cbir = ref_harness.import_reference()
+    SynthDataset = ref_harness.make_dataset_class(cbir)
+    images_u8, k, depth, n_iter = case_images(name)
+    images = [np.ascontiguousarray(a, dtype=np.float32) for a in images_u8]
+    dataset = SynthDataset(images)
+    voc = ref_harness.reference_build(cbir, np.concatenate(images, axis=0), k, depth, n_iter)
+    db = cbir.Database(dataset, voc)
+    with ref_harness.quiet():
+        db.index()
+    out = os.path.join(GOLDEN, "persist")
+    os.makedirs(out, exist_ok=True)
+    if not hasattr(nx, "write_gpickle"):
+        def write_gpickle(G, path, protocol=pickle.HIGHEST_PROTOCOL):
+            with open(path, "wb") as f:
+                pickle.dump(G, f, protocol)
+        nx.write_gpickle = write_gpickle
+    voc.save(out)
+    db.save(out)
+    keys = {p: db.get_image_id(p) for p in dataset.image_paths}
+    with open(os.path.join(out, "keys.json"), "w") as f:
+        json.dump(dict(case=name, k=k, depth=depth, keys=keys), f)
+    print("persist: %s -> %s (%s)" % (name, out, ", ".join(
+        "%s %.1f KB" % (fn, os.path.getsize(os.path.join(out, fn)) / 1024) for fn in sorted(os.listdir(out)))))
+
+
 def main(argv):
-    cases = argv or ["toy", "small", "orb", "adversarial"]
+    cases = argv or ["toy", "small", "orb", "adversarial", "persist"]
     for c in cases:
-        if c == "c1":
+        if c == "persist":
+            run_persist()
+        elif c == "c1":
             run_case("c1", n_query=64, store_full=False)
         else:
             run_case(c)

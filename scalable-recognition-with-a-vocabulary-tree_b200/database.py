@@ -170,38 +170,95 @@ class Database(object):
         return {paths[i]: float(scores[i]) for i in order}
 
     # ------------------------------------------------------------------ persistence
-    def save(self, path=None):
-        """``index.pickle`` (database.py:83-91): here the forward CSR of the indexed images."""
+    @staticmethod
+    def reference_key(image_path):
+        """The reference's image key (database.py:25-34): Python's salted ``hash`` of the absolute
+        path.  Only stable inside one process or under a fixed PYTHONHASHSEED."""
+        return hash(os.path.abspath(image_path))
+
+    @staticmethod
+    def counts_from_embedding(e):
+        """Integer visit counts behind one reference embedding ``c / ||c||`` (vocabulary.py:126-137).
+        The smallest non-zero count is tried as 1, 2, ...; any common factor leaves every score
+        unchanged.  NaN / all-zero embeddings (images without descriptors) give an empty row."""
+        e = np.asarray(e, dtype=np.float64)
+        nz = np.flatnonzero(np.nan_to_num(e) > 0)
+        if nz.size == 0:
+            return nz.astype(np.int32), np.zeros(0, np.int32)
+        v = e[nz]
+        for m in range(1, 65):
+            c = v * (m / v.min())
+            r = np.rint(c)
+            if np.all(np.abs(c - r) <= 1e-6 * np.maximum(r, 1.0)):
+                return nz.astype(np.int32), r.astype(np.int32)
+        raise ValueError("embedding is not a normalised integer count vector")
+
+    def _install(self, rows, host):
+        """Forward CSR on the host -> device CSR + inverted file."""
+        import torch
+        ro, node, count = host
+        dev = torch.device(self.encoder.device)
+        n_img = len(ro) - 1
+        n_ref = self.encoder.flat.n_ref
+        sumsq = np.add.reduceat(count.astype(np.int64) ** 2, ro[:-1]) if len(count) else np.zeros(n_img, np.int64)
+        sumsq = np.where(ro[1:] > ro[:-1], sumsq, 0)
+        csr = dict(row_off=torch.from_numpy(ro).to(dev), node=torch.from_numpy(node).to(dev),
+                   count=torch.from_numpy(count).to(dev), sumsq=torch.from_numpy(sumsq).to(dev),
+                   n_img=n_img, nnz=len(node), df=None)
+        self._rows, self._host, self._csr = rows, host, csr
+        weight = None
+        if self.weighting == "tfidf":
+            df = torch.bincount(csr["node"].long(), minlength=n_ref).to(torch.float64)
+            self._idf = torch.where(df > 0, torch.log(max(n_img, 1) / df.clamp(min=1)),
+                                    torch.zeros_like(df)).to(torch.float32)
+            weight = engine.tfidf_weights(csr, self._idf, self.norm)
+        self._index = engine.build_index(csr, n_ref, weight)
+        self._extra = {}
+
+    def save(self, path=None, reference_format=False, key=None):
+        """``index.pickle`` (database.py:83-91).  Default: the forward CSR of the indexed images.
+        ``reference_format=True`` writes what the reference writes -- its ``_database`` dict
+        ``key(image_path) -> dense embedding`` -- for trees small enough to hold dense rows."""
         if path is None:
             path = "data"
         os.makedirs(path, exist_ok=True)
+        if reference_format:
+            key = key or self.reference_key
+            n_ref = self.encoder.flat.n_ref
+            if len(self._rows) * n_ref * 8 > (1 << 31):
+                raise ValueError("dense reference-format index would exceed 2 GiB; use the CSR format")
+            payload = {key(p): self.embedding(p) for p in self._rows}
+        else:
+            payload = dict(rows=self._rows, host=self._host, weighting=self.weighting, norm=self.norm)
         with open(os.path.join(path, "index.pickle"), "wb") as f:
-            pickle.dump(dict(rows=self._rows, host=self._host, weighting=self.weighting, norm=self.norm), f)
+            pickle.dump(payload, f)
         return True
 
-    def load(self, path="data"):
+    def load(self, path="data", key=None):
+        """Loads ``index.pickle`` in either format.  A reference-written file (dict of dense
+        embeddings keyed by ``hash(abspath)``, database.py:83-101) is matched to
+        ``dataset.image_paths`` through ``key`` (default: the reference's own key, which only
+        matches under the PYTHONHASHSEED the file was written with) and converted back to integer
+        counts.  Failures print the reference's message and leave the database unchanged."""
         try:
-            import torch
             with open(os.path.join(path, "index.pickle"), "rb") as f:
                 st = pickle.load(f)
-            ro, node, count = st["host"]
-            dev = torch.device(self.encoder.device)
-            n_img = len(ro) - 1
-            sumsq = np.add.reduceat(count.astype(np.int64) ** 2, ro[:-1]) if len(count) else np.zeros(n_img, np.int64)
-            sumsq = np.where(ro[1:] > ro[:-1], sumsq, 0)
-            csr = dict(row_off=torch.from_numpy(ro).to(dev), node=torch.from_numpy(node).to(dev),
-                       count=torch.from_numpy(count).to(dev), sumsq=torch.from_numpy(sumsq).to(dev),
-                       n_img=n_img, nnz=len(node), df=None)
-            self._rows, self._host, self._csr = st["rows"], st["host"], csr
-            self.weighting, self.norm = st["weighting"], st["norm"]
-            weight = None
-            if self.weighting == "tfidf":
-                df = torch.bincount(csr["node"].long(), minlength=self.encoder.flat.n_ref).to(torch.float64)
-                self._idf = torch.where(df > 0, torch.log(max(n_img, 1) / df.clamp(min=1)),
-                                        torch.zeros_like(df)).to(torch.float32)
-                weight = engine.tfidf_weights(csr, self._idf, self.norm)
-            self._index = engine.build_index(csr, self.encoder.flat.n_ref, weight)
-        except (OSError, KeyError, pickle.UnpicklingError):
+            if isinstance(st, dict) and "host" in st and "rows" in st:
+                self.weighting, self.norm = st["weighting"], st["norm"]
+                self._install(st["rows"], st["host"])
+                return True
+            key = key or self.reference_key
+            paths = list(self.dataset.image_paths)
+            nodes, counts, ro = [], [], np.zeros(len(paths) + 1, np.int64)
+            for i, p in enumerate(paths):
+                nd, ct = self.counts_from_embedding(st[key(p)])
+                nodes.append(nd)
+                counts.append(ct)
+                ro[i + 1] = ro[i] + len(nd)
+            host = (ro, np.concatenate(nodes).astype(np.int32) if nodes else np.zeros(0, np.int32),
+                    np.concatenate(counts).astype(np.int32) if counts else np.zeros(0, np.int32))
+            self._install({p: i for i, p in enumerate(paths)}, host)
+        except (OSError, KeyError, ValueError, pickle.UnpicklingError):
             print("Cannot load index file from %s/index.pickle" % path)
         return True
 

@@ -182,22 +182,69 @@ class VocabularyTree(object):
             return e / np.linalg.norm(e, ord=2)
 
     # ------------------------------------------------------------------ persistence
+    GRAPH_PICKLE_MAX_NODES = 2_000_000
+
     def save(self, path=None):
-        """Flat-array checkpoint ``tree.npz`` plus the reference's ``nodes.pickle`` dict
-        (vocabulary.py:148-159; its graph.pickle needs networkx<3 and is not written)."""
+        """Flat-array checkpoint ``tree.npz`` plus the reference's two files (vocabulary.py:148-159):
+        ``nodes.pickle`` (node id -> centre) and ``graph.pickle`` (the networkx DiGraph with the
+        {image sha1: count} postings as node attributes; ``nx.write_gpickle`` was a plain
+        ``pickle.dump`` of the graph at the highest protocol, which is what is written here --
+        the function itself is gone from networkx 3).  The graph is skipped for huge trees."""
         if path is None:
             path = "data"
         os.makedirs(path, exist_ok=True)
         np.savez_compressed(os.path.join(path, "tree.npz"), **self.flat.state())
         with open(os.path.join(path, "nodes.pickle"), "wb") as f:
             pickle.dump(self.nodes, f)
+        if self.flat.n_ref <= self.GRAPH_PICKLE_MAX_NODES:
+            with open(os.path.join(path, "graph.pickle"), "wb") as f:
+                pickle.dump(self.graph, f, pickle.HIGHEST_PROTOCOL)
         return True
 
     def load(self, path="data"):
-        st = np.load(os.path.join(path, "tree.npz"))
-        self.set_tree(FlatTree.from_state(st))
-        self.n_branches, self.depth = self.flat.k, self.flat.depth
+        """Restores a tree: the flat checkpoint if present, else a tree the REFERENCE saved
+        (``nodes.pickle`` + ``graph.pickle``): children in edge-insertion order, postings taken
+        from the node attributes (vocabulary.py:96-100).  The reference has no ``load``."""
+        npz = os.path.join(path, "tree.npz")
+        if os.path.exists(npz):
+            self.set_tree(FlatTree.from_state(np.load(npz)))
+            self.n_branches, self.depth = self.flat.k, self.flat.depth
+            return True
+        with open(os.path.join(path, "nodes.pickle"), "rb") as f:
+            nodes = pickle.load(f)
+        with open(os.path.join(path, "graph.pickle"), "rb") as f:
+            graph = pickle.load(f)
+        self.import_reference(nodes, graph)
         return True
+
+    def import_reference(self, nodes, graph):
+        """Adopt a reference-built tree: ``nodes`` dict and networkx ``graph`` (or the ``tree``
+        dict node -> children).  Branching factor and depth are read off the structure."""
+        if hasattr(graph, "successors"):
+            tree = {n_: list(graph.successors(n_)) for n_ in graph.nodes if graph.out_degree(n_) > 0}
+        else:
+            tree = {n_: list(c) for n_, c in graph.items() if len(c) > 0}
+        k = max((len(c) for c in tree.values()), default=self.n_branches)
+        depth, frontier = 0, [0]
+        while True:
+            frontier = [c for n_ in frontier for c in tree.get(n_, [])]
+            if not frontier:
+                break
+            depth += 1
+        self.set_tree(FlatTree.from_reference_dicts(nodes, tree, k, max(depth, 1)))
+        if self._flat.tree_dict() != tree:
+            raise ValueError("node ids are not in the reference's creation order (vocabulary.py:69-72)")
+        self.n_branches, self.depth = k, max(depth, 1)
+        if hasattr(graph, "nodes"):
+            per_image = {}
+            for n_, attrs in graph.nodes(data=True):
+                for image_id, c in attrs.items():
+                    per_image.setdefault(image_id, []).append((n_, c))
+            for image_id, pairs in per_image.items():
+                pairs.sort()
+                self._propagated[image_id] = (np.array([p_[0] for p_ in pairs], np.int32),
+                                              np.array([p_[1] for p_ in pairs], np.int32))
+        return self
 
     def draw(self, *args, **kwargs):
         raise NotImplementedError("plotting is outside the accelerated path; use .graph with networkx")

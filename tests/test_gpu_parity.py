@@ -5,7 +5,8 @@ import numpy as np
 import pytest
 
 from oracle import vt_oracle as vo
-from helpers import (csr_to_dense, golden_inputs, golden_tree_dicts, load_golden, oracle_tree_from_flat)
+from helpers import (csr_to_dense, golden_inputs, golden_tree_dicts, load_golden, near_tie_rows,
+                     oracle_tree_from_flat)
 
 pytestmark = pytest.mark.gpu
 CASES = ["toy", "small", "orb", "adversarial"]
@@ -539,6 +540,52 @@ def test_save_load_round_trip_and_reference_import(vt, cuda, tmp_path):
     assert np.array_equal(voc3.quantize(x), voc.quantize(x))
     # loading a missing index prints and carries on, like the reference's bare except (database.py:99-100)
     assert vt.Database(ds, voc2).load(str(tmp_path / "nowhere"))
+
+
+def test_reference_written_files_drive_the_gpu_engine(vt, cuda, tmp_path):
+    """the files the reference's own save() wrote (tests/golden/persist, generated by
+    oracle/make_golden.py persist) are imported -- tree from nodes.pickle + graph.pickle, index from
+    index.pickle -- and the GPU engine then reproduces the reference's descent and retrieval without
+    ever seeing the descriptors of the database images; export in the reference's format round-trips."""
+    import json
+    import os
+    import pickle
+    from helpers import GOLDEN
+    pdir = os.path.join(GOLDEN, "persist")
+    g, meta = load_golden("adversarial")
+    images, k, depth, n_iter = golden_inputs("adversarial")
+    ds = vt.ArrayDataset([im.astype(np.float32) for im in images])
+    keys = json.load(open(os.path.join(pdir, "keys.json")))["keys"]
+    voc = vt.encoders.VocabularyTree(1, 1, descriptor=lambda im: im)
+    assert voc.load(pdir)
+    x = np.concatenate(images)
+    mism = np.nonzero(voc.quantize(x) != g["ref_leaf"])[0]      # float32 near-ties only (DESIGN 3)
+    assert len(mism) <= 2 and np.all(near_tie_rows(oracle_tree_from_flat(voc.flat), x[mism].astype(np.float32)))
+    db = vt.Database(ds, voc)
+    assert db.load(pdir, key=lambda p: keys[p])
+    assert all(db.is_indexed(p) for p in ds.image_paths)
+    n_img = len(images)
+    for qi in range(n_img):
+        res = db.retrieve(ds.image_paths[qi])
+        ws = np.empty(n_img)
+        ws[g["order"][qi]] = g["scores"][qi]
+        np.testing.assert_allclose(list(res.values()), g["scores"][qi], rtol=1e-5, atol=1e-7)
+        for a, b in zip([ds.image_paths.index(p) for p in res], g["order"][qi]):
+            assert a == b or abs(ws[a] - ws[b]) <= 1e-9
+    # export in the reference's formats and compare with what the reference wrote
+    assert voc.save(str(tmp_path)) and db.save(str(tmp_path), reference_format=True, key=lambda p: keys[p])
+    ref_index = pickle.load(open(os.path.join(pdir, "index.pickle"), "rb"))
+    our_index = pickle.load(open(tmp_path / "index.pickle", "rb"))
+    assert set(ref_index) == set(our_index)
+    for key_, e in ref_index.items():
+        np.testing.assert_allclose(our_index[key_], e, rtol=1e-12, atol=0, equal_nan=True)
+    ref_graph = pickle.load(open(os.path.join(pdir, "graph.pickle"), "rb"))
+    our_graph = pickle.load(open(tmp_path / "graph.pickle", "rb"))
+    assert list(ref_graph.edges) == list(our_graph.edges) or sorted(ref_graph.edges) == sorted(our_graph.edges)
+    assert {n_: dict(a) for n_, a in ref_graph.nodes(data=True)} == {n_: dict(a) for n_, a in our_graph.nodes(data=True)}
+    # a wrong key function fails like the reference's load: message, database unchanged
+    db_bad = vt.Database(ds, voc)
+    assert db_bad.load(pdir, key=lambda p: 12345) and not db_bad.is_indexed(ds.image_paths[0])
 
 
 def test_c1_full_pipeline_matches_reference(vt, cuda):
