@@ -57,13 +57,19 @@ class Database(object):
     def _descriptors(self, image_path):
         return np.asarray(self.encoder.descriptor(self.dataset.read_image(image_path)))
 
-    def index(self):
+    def index(self, batch_images=4096):
         """Encode every dataset image (in ``image_paths`` order) and build the inverted file
-        (database.py:36-44)."""
+        (database.py:36-44).  Images are read, staged and encoded ``batch_images`` at a time, so the
+        descriptors of the whole dataset are never resident at once; only the bag-of-words CSR
+        (8 B per posting) accumulates on the device."""
         import torch
         paths = list(self.dataset.image_paths)
-        feats = [self._descriptors(p) for p in paths]
-        csr = self.encoder.encode_batch(feats, want_df=True)
+        step = max(1, int(batch_images))
+        parts = []
+        for b0 in range(0, max(len(paths), 1), step):
+            feats = [self._descriptors(p) for p in paths[b0:b0 + step]]
+            parts.append(self.encoder.encode_batch(feats, want_df=True))
+        csr = engine.concat_csr(parts)
         n_ref = self.encoder.flat.n_ref
         weight = None
         if self.weighting == "tfidf":

@@ -361,6 +361,22 @@ def encode(words: torch.Tensor, img_off: torch.Tensor, tree_dev: dict, depth: in
                 n_img=n_img, nnz=total)
 
 
+def concat_csr(parts: list) -> dict:
+    """Concatenates forward CSRs of consecutive image batches (streaming ``Database.index``)."""
+    if len(parts) == 1:
+        return parts[0]
+    offs, base = [parts[0]["row_off"][:1]], 0
+    for p in parts:
+        offs.append(p["row_off"][1:] + base)
+        base += p["nnz"]
+    df = None
+    if all(p["df"] is not None for p in parts):
+        df = torch.stack([p["df"] for p in parts]).sum(0, dtype=torch.int32)
+    return dict(row_off=torch.cat(offs), node=torch.cat([p["node"] for p in parts]),
+                count=torch.cat([p["count"] for p in parts]), sumsq=torch.cat([p["sumsq"] for p in parts]),
+                df=df, n_img=sum(p["n_img"] for p in parts), nnz=base)
+
+
 def entry_rows(csr: dict) -> torch.Tensor:
     """image index of every CSR entry (int64 [nnz])."""
     n_img = csr["n_img"]

@@ -435,6 +435,36 @@ def test_notebook_flow_matches_reference(vt, cuda, name):
     assert got0 == {int(n_): int(c) for n_, c in enumerate(g["counts"][0]) if c > 0}
 
 
+def test_streaming_index_equals_one_batch(vt, cuda):
+    """Database.index(batch_images=b): images encoded b at a time give the same inverted file
+    (streaming index) -- CSR, document frequencies and retrieval are identical."""
+    import torch
+    g, meta = load_golden("adversarial")
+    images, k, depth, n_iter = golden_inputs("adversarial")
+    ds = vt.ArrayDataset(images)
+    voc = vt.encoders.VocabularyTree(k, depth, descriptor=lambda im: im, n_iter=n_iter)
+    voc.fit(np.concatenate(images))
+    dbs = []
+    for b in (4096, 7, 1):
+        for weighting in ("tf", "tfidf"):
+            db = vt.Database(ds, voc, weighting=weighting)
+            db.index(batch_images=b)
+            dbs.append((weighting, db))
+    for weighting in ("tf", "tfidf"):
+        same = [db for w, db in dbs if w == weighting]
+        for db in same[1:]:
+            for a, b_ in zip(same[0]._host, db._host):
+                assert np.array_equal(a, b_)
+            assert torch.equal(same[0]._csr["df"], db._csr["df"])
+            ids0, sc0 = same[0].retrieve_batch(ds.image_paths, k=5)
+            ids1, sc1 = db.retrieve_batch(ds.image_paths, k=5)
+            assert np.array_equal(ids0, ids1)
+            if weighting == "tf":                                  # integer arithmetic: identical
+                assert np.array_equal(sc0, sc1)
+            else:                                                  # float32 weights, atomically summed norms
+                np.testing.assert_allclose(sc0, sc1, rtol=1e-5, atol=1e-6)
+
+
 # ------------------------------------------------------------------------------------------ full size
 def test_full_size_quantize_properties(vt, cuda):
     """BASELINE configs[2] shape at a size the oracle cannot check row by row (20 M x 128 through a
