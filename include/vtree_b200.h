@@ -182,9 +182,10 @@ int vt_sort_pairs(uint32_t *d_keys, uint32_t *d_vals, uint32_t *d_tmp_keys, uint
 /* ---- bag-of-words encoding: VocabularyTree.propagate + embedding, vocabulary.py:78-137 ----
  * d_word [n_desc] reference node ids of the stop nodes, grouped by image (d_img_off [n_img+1]);
  * max_words = largest number of descriptors in one image (<= vt_encode_max_words()).
- * all_nodes != 0 counts every node on the path (reference semantics, vocabulary.py:92-100) using
- * d_parent_ref/d_level_ref ([n_ref] parent id / depth of each reference node); 0 counts stop
- * nodes only ("leaf words").  Two-pass CSR: call with d_out_node == NULL to get d_nnz [n_img]
+ * all_nodes == 1 counts every node on the path (reference semantics, vocabulary.py:92-100) using
+ * d_parent_ref/d_level_ref ([n_ref] parent id / depth of each reference node); all_nodes = 1 + m
+ * keeps only the nodes at level >= m (Nister & Stewenius' level mask: weight 0 above level m; the
+ * weights vocabulary.py:131,137 leave commented out); 0 counts stop nodes only ("leaf words").  Two-pass CSR: call with d_out_node == NULL to get d_nnz [n_img]
  * (entries per image), prefix-sum it into d_row_off [n_img+1], call again to fill.
  *   d_out_node/d_out_count : CSR columns (reference node id) and term frequencies
  *   d_sumsq [n_img] uint64 : sum of squared counts (exact squared L2 norm), written in pass 2

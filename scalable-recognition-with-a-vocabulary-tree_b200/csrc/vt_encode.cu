@@ -111,9 +111,11 @@ encode_kernel(const int32_t *__restrict__ word, const int64_t *__restrict__ img_
         for (int t = threadIdx.x; t < m; t += ENC_THREADS) { A[t] = A2[t]; C[t] = C2[t]; }
         __syncthreads();
 
-        // emit levels from the deepest up; without all_nodes emit everything at once
+        // emit levels from the deepest up; without all_nodes emit everything at once.  all_nodes = m >= 1
+        // keeps the levels >= m-1 only (level mask: the levels above carry weight 0)
         unsigned long long sq = 0ull;
         const int first_level = all_nodes ? depth : 0;
+        const int min_level = all_nodes ? all_nodes - 1 : 0;
         for (int dd = first_level; dd >= 0; --dd) {
             // flag entries that leave the working list at this step
             for (int t = threadIdx.x; t < m; t += ENC_THREADS)
@@ -135,7 +137,7 @@ encode_kernel(const int32_t *__restrict__ word, const int64_t *__restrict__ img_
             }
             emitted += n_emit;
             __syncthreads();
-            if (!all_nodes || dd == 0) break;
+            if (!all_nodes || dd <= min_level) break;
             // lift: entries of level dd move to their parent, then merge adjacent equal ids
             for (int t = threadIdx.x; t < m; t += ENC_THREADS)
                 if (level_ref[A[t]] == dd) A[t] = (uint32_t)parent_ref[A[t]];
@@ -239,6 +241,7 @@ extern "C" int vt_encode(const int32_t *d_word, const int64_t *d_img_off, int64_
 {
     VT_CHECK_ARG(n_img >= 0 && d_img_off, "bad image offsets");
     VT_CHECK_ARG(max_words >= 0 && max_words <= ENC_MAX, "an image has more descriptors than vt_encode_max_words()");
+    VT_CHECK_ARG(all_nodes >= 0 && all_nodes <= depth + 1, "all_nodes must be 0 (stop nodes) or 1 + first kept level");
     VT_CHECK_ARG(!all_nodes || (d_parent_ref && d_level_ref), "all_nodes needs parent/level tables");
     VT_CHECK_ARG((d_out_node == nullptr) == (d_out_count == nullptr), "out_node/out_count must come together");
     VT_CHECK_ARG(d_out_node != nullptr || d_nnz != nullptr, "count pass needs d_nnz");

@@ -26,13 +26,14 @@ from ..tree import FlatTree
 
 
 class VocabularyTree(object):
-    def __init__(self, n_branches, depth, descriptor, *, n_iter=10, all_nodes=True, device="cuda"):
+    def __init__(self, n_branches, depth, descriptor, *, n_iter=10, all_nodes=True, min_level=0, device="cuda"):
         self.n_branches = n_branches
         self.depth = depth
         self.descriptor = descriptor
         # keyword-only additions
         self.n_iter = n_iter
         self.all_nodes = all_nodes          # reference semantics: count every node on the path
+        self.min_level = min_level          # level mask: nodes above this level carry weight 0
         self.device = device
         # private
         self._flat = None                   # FlatTree
@@ -153,7 +154,8 @@ class VocabularyTree(object):
         else:
             words = torch.zeros(1, dtype=torch.int32, device=dev)
         return engine.encode(words, off.to(dev), t.device(dev), t.depth, t.n_ref,
-                             all_nodes=self.all_nodes if all_nodes is None else all_nodes, want_df=want_df)
+                             all_nodes=self.all_nodes if all_nodes is None else all_nodes, want_df=want_df,
+                             min_level=min(self.min_level, t.depth))
 
     def propagate(self, image):
         """Send an image's features down the tree and record its visit counts

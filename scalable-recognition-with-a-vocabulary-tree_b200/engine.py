@@ -332,9 +332,10 @@ def build_tree(desc: torch.Tensor, d: int, k: int, depth: int, n_iter: int = 10,
 
 # --------------------------------------------------------------------------------------- encode
 def encode(words: torch.Tensor, img_off: torch.Tensor, tree_dev: dict, depth: int, n_ref: int,
-           all_nodes: bool = True, want_df: bool = False) -> dict:
+           all_nodes: bool = True, want_df: bool = False, min_level: int = 0) -> dict:
     """Bag-of-words CSR of a batch of images.  ``words`` int32 [n_desc] (reference ids of the
-    stop nodes) grouped by image, ``img_off`` int64 [n_img+1] on the device."""
+    stop nodes) grouped by image, ``img_off`` int64 [n_img+1] on the device.  ``min_level`` > 0
+    (all-nodes mode) drops the nodes above that level: the level mask of Nister & Stewenius."""
     lib = _lib()
     dev = words.device
     n_img = img_off.numel() - 1
@@ -345,7 +346,9 @@ def encode(words: torch.Tensor, img_off: torch.Tensor, tree_dev: dict, depth: in
         raise ValueError("an image has %d descriptors; vt_encode handles at most %d per image"
                          % (max_words, lib.vt_encode_max_words()))
     nnz = torch.zeros(max(n_img, 1), dtype=torch.int32, device=dev)
-    args = (nat.ptr(words), nat.ptr(img_off), n_img, max_words, 1 if all_nodes else 0,
+    if not 0 <= min_level <= depth:
+        raise ValueError("min_level must lie in [0, depth]")
+    args = (nat.ptr(words), nat.ptr(img_off), n_img, max_words, 1 + int(min_level) if all_nodes else 0,
             nat.ptr(tree_dev["parent_ref"]), nat.ptr(tree_dev["level_ref"]), depth)
     nat.check(lib.vt_encode(*args, nat.ptr(nnz), None, None, None, None, None, s), "vt_encode(count)")
     row_off = torch.zeros(n_img + 1, dtype=torch.int64, device=dev)

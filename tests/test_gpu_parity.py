@@ -257,6 +257,24 @@ def test_encode_matches_propagate(vt, cuda, name, all_nodes):
     del torch
 
 
+@pytest.mark.parametrize("name", ["small", "orb", "adversarial"])
+def test_encode_level_mask(vt, cuda, name):
+    """min_level = m: the reference's visit counts (golden) with every node above level m zeroed --
+    the level mask of the paper (weights the reference leaves commented out, vocabulary.py:131,137).
+    Early leaves above the mask vanish; retrieval still ranks a database image first for itself."""
+    ft, g, meta, images = _flat_from_golden(vt, name)
+    for m in range(0, ft.depth + 1):
+        voc = vt.encoders.VocabularyTree(ft.k, ft.depth, descriptor=lambda im: im, min_level=m).set_tree(ft)
+        csr = voc.encode_batch(images, want_df=True)
+        dense = csr_to_dense(*(csr[k_].cpu().numpy() for k_ in ("row_off", "node", "count")), ft.n_ref)
+        want = g["counts"].astype(np.int64) * (ft.level_ref >= m)[None, :]
+        assert np.array_equal(dense, want), m
+        assert np.array_equal(csr["sumsq"].cpu().numpy(), (want ** 2).sum(1))
+        assert np.array_equal(csr["df"].cpu().numpy(), (want > 0).sum(0))
+    with pytest.raises(ValueError):
+        vt.engine.encode(csr["node"], csr["row_off"], ft.device(cuda), ft.depth, ft.n_ref, min_level=ft.depth + 1)
+
+
 def test_encode_large_images(vt, cuda):
     """images near the shared-memory capacity (8192 descriptors) and a mix of sizes"""
     ft, g, meta, images = _flat_from_golden(vt, "small")
