@@ -150,6 +150,15 @@ __host__ __device__ __forceinline__ int path_bits(int k)
     while ((1 << b) - 1 < k) ++b;          // labels 0..k-1 plus the all-ones "stopped" marker
     return b;
 }
+// same, for trees whose heap has fewer than 2^31 slots (32-bit arithmetic: 3 instructions per level)
+__device__ __forceinline__ uint32_t path_to_heap32(uint32_t path, int level, int bits, uint32_t k)
+{
+    const uint32_t mask = (1u << bits) - 1u;
+    uint32_t h = 0;
+    int sh = bits * (level - 1);
+    for (int i = 0; i < level; ++i, sh -= bits) h = h * k + 1u + ((path >> sh) & mask);
+    return h;
+}
 __device__ __forceinline__ long long path_to_heap(uint32_t path, int level, int bits, int k)
 {
     const uint32_t mask = (1u << bits) - 1u;

@@ -23,6 +23,8 @@
 
 int vt_sort_pairs_impl(uint32_t *d_keys, uint32_t *d_vals, uint32_t *d_tmp_keys, uint32_t *d_tmp_vals, int64_t n,
                        int n_bits, void *d_hist, int *result_in_tmp, cudaStream_t s);
+int vt_sort_pass_impl(const uint32_t *kin, const uint32_t *vin, uint32_t *kout, uint32_t *vout, int64_t n, int shift,
+                      uint32_t mask, void *d_hist, cudaStream_t s);
 
 namespace {
 constexpr int MM_TILE = 128;                    // descriptors per tile == threads per CTA == UMMA M
@@ -47,10 +49,69 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
            (1ull << 46) /* sm100 descriptor version */ | (2ull << 61) /* SWIZZLE_128B */;
 }
 
+// ---- epilogue arithmetic ------------------------------------------------------------------------------
+// Scores are compared in 32 bits, units 2^-7:  s_c = floor(|c|^2 * 2^7) - (v0 << 8) - v1 - (v2 >> 8)  where
+// v0, v1, v2 are the accumulators of the three centroid byte planes (2 x.c * 2^7 = v0 2^8 + v1 + v2 2^-8).
+// Each s_c is within ONE unit of the exact score of the rounded centroid, so a gap of the 32-bit scores
+// is within two units of the exact gap; the contest test below subtracts three.  Fits int32: v0 < 2^23.
+constexpr int MM_S_SHIFT = 25;                  // 2^-32 units -> 2^-7 units
+
+__device__ __forceinline__ void score_children(const uint32_t (&v)[MM_N], const int *s_cn, int k, int &best, int &second,
+                                               int &arg)
+{
+    int cq[16];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int4 t = reinterpret_cast<const int4 *>(s_cn)[g];
+        cq[4 * g] = t.x; cq[4 * g + 1] = t.y; cq[4 * g + 2] = t.z; cq[4 * g + 3] = t.w;
+    }
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        if (c >= k) break;                                       // block-uniform: no predicated-off work
+        const int sc = cq[c] - (int)((v[c] << 8) + v[16 + c] + (v[32 + c] >> 8));
+        if (sc < best) { second = best; best = sc; arg = c; }
+        else second = sc < second ? sc : second;
+    }
+}
+
+// provable margin for the centroid rounding (|error| <= m (da + db), m = 2^-16 sqrt(128) 1.02, da <= db) plus
+// the three units of the 32-bit scores: "gap <= 2 m db", squared to avoid the square root.  xn = |x|^2.
+__device__ __forceinline__ bool contest_test(int best, int second, float xn)
+{
+    const float gap = (float)(second - best - 3) * 0.0078125f;
+    const float d2b = fmaxf(0.f, (float)(second + 1) * 0.0078125f + xn);
+    const float two_m = 2.0f * 1.52587890625e-05f * 11.313708498984761f * 1.02f;
+    return gap <= 0.f || gap * gap <= two_m * two_m * 1.001f * d2b;
+}
+
+// |x|^2 of the row this thread owns, from the swizzled A tile
+__device__ __forceinline__ unsigned int row_norm2(const uint8_t *sA, int tid)
+{
+    unsigned int xn = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint4 q = *reinterpret_cast<const uint4 *>(sA + (tid >> 3) * 1024 + (tid & 7) * 128 + ((j ^ (tid & 7)) << 4));
+        xn = __dp4a(q.x, q.x, xn); xn = __dp4a(q.y, q.y, xn); xn = __dp4a(q.z, q.z, xn); xn = __dp4a(q.w, q.w, xn);
+    }
+    return xn;
+}
+
+// two-stage contest test: the crude bound |x|^2 <= 128 * 255^2 settles almost every row; only warps that
+// still hold a candidate read their rows' exact norms
+__device__ __forceinline__ bool contested_row(bool active, int best, int second, const uint8_t *sA, int tid)
+{
+    bool contested = active && contest_test(best, second, 8323200.f);
+    if (__any_sync(VT_FULL, contested)) {
+        const unsigned int xn = row_norm2(sA, tid);
+        contested = contested && contest_test(best, second, (float)xn * 1.0000002f);
+    }
+    return contested;
+}
+
 // ---- per-call preparation: byte planes + fixed-point squared norms of every node's children --------
 __global__ void __launch_bounds__(128)
 prep_planes_kernel(const float *__restrict__ cent, int64_t n_int, int k, uint8_t *__restrict__ bimg,
-                   unsigned long long *__restrict__ cn, unsigned long long *__restrict__ stats)
+                   unsigned long long *__restrict__ cn, int *__restrict__ cn32, unsigned long long *__restrict__ stats)
 {
     __shared__ unsigned long long s_part[4];
     const int d = threadIdx.x;
@@ -72,7 +133,11 @@ prep_planes_kernel(const float *__restrict__ cent, int64_t n_int, int k, uint8_t
             for (int o = 16; o >= 1; o >>= 1) sq += __shfl_xor_sync(VT_FULL, sq, o);
             if ((d & 31) == 0) s_part[d >> 5] = sq;
             __syncthreads();
-            if (d == 0 && c < k) cn[h * k + 1 + c] = s_part[0] + s_part[1] + s_part[2] + s_part[3];
+            if (d == 0) {
+                const unsigned long long tot = s_part[0] + s_part[1] + s_part[2] + s_part[3];
+                if (c < k) cn[h * k + 1 + c] = tot;
+                cn32[h * 16 + c] = c < k ? (int)(tot >> MM_S_SHIFT) : 0x3fffffff;     // |c|^2 in units 2^-7, rounded down
+            }
             __syncthreads();
         }
         if (bad && stats) atomicAdd(stats + 1, 1ull);
@@ -80,11 +145,12 @@ prep_planes_kernel(const float *__restrict__ cent, int64_t n_int, int k, uint8_t
 }
 
 // ---- one tree level -------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MM_TILE, 6)
+template <int MINB>
+__global__ void __launch_bounds__(MM_TILE, MINB)
 level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ parent,
                  int64_t n, int level, int bits, int64_t n_heap, int k, int is_last,
                  const float *__restrict__ cent, const uint8_t *__restrict__ internal, const int32_t *__restrict__ ref_id,
-                 const uint8_t *__restrict__ bimg, const unsigned long long *__restrict__ cn,
+                 const uint8_t *__restrict__ bimg, const int *__restrict__ cn32,
                  uint32_t *__restrict__ keys_out, uint32_t *__restrict__ perm_out, int32_t *__restrict__ leaf_out,
                  int32_t *__restrict__ word_out, unsigned long long *__restrict__ stats)
 {
@@ -97,10 +163,11 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
     __shared__ uint32_t s_tmem;
     __shared__ uint32_t s_row[MM_TILE];
     __shared__ long long s_min[4];
+    __shared__ __align__(16) int s_cn[16];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t dmask = (1u << bits) - 1u;                    // all-ones digit = "stopped at a leaf"
-    const long long none = 0x7fffffffffffffffLL;
+    const int none = 0x7fffffff;
     unsigned int rechecks = 0;
 
     if (warp == 0) {
@@ -137,7 +204,7 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
             if (pn < n) { nx_row = perm ? perm[pn] : (uint32_t)pn; nx_jp = parent ? parent[pn] : 0u; }
         }
         const bool alive = valid && (level == 0 || (jp & dmask) != dmask);
-        const long long node = alive ? path_to_heap(jp, level, bits, k) : 0;
+        const long long node = alive ? (long long)path_to_heap32(jp, level, bits, (uint32_t)k) : 0;
         const bool is_int = alive && (node * k + k < n_heap) && internal[node];
         const uint8_t *xrow = desc + (size_t)row * 128;
         if (alive && !is_int) {                                  // ragged tree: this node is a leaf
@@ -162,10 +229,8 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
                              "r"(ok ? 16 : 0));                 // zero fill for rows that take no part
             }
         }
-        long long best = none, second = none;
-        int arg = 0;
+        int best = none, second = none, arg = 0;
         bool pending = is_int;
-        unsigned int xn = 0;                                    // exact |x|^2, filled after the first wait
 
         // one MMA pass per distinct node present in the tile (sorted batch: almost always one)
         for (int pass = 0;; ++pass) {
@@ -187,6 +252,8 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
                 const int c = tid + MM_TILE * i;
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sB) + c * 16), "l"(bsrc + c * 16));
             }
+            if (tid < 4)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_cn) + tid * 16), "l"(cn32 + mine * 16 + tid * 4));
             asm volatile("cp.async.commit_group;");
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> tensor core
@@ -202,13 +269,6 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
                         ::"r"(tmem), "l"(a_desc + 2 * ks), "l"(b_desc + 2 * ks), "r"(MM_IDESC), "r"(acc), "r"(0u));
                 }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
-            }
-            if (pass == 0 && is_int) {                          // overlap with the MMA: |x|^2 from the staged tile
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint4 q = *reinterpret_cast<const uint4 *>(sA + (tid >> 3) * 1024 + (tid & 7) * 128 + ((j ^ (tid & 7)) << 4));
-                    xn = __dp4a(q.x, q.x, xn); xn = __dp4a(q.y, q.y, xn); xn = __dp4a(q.z, q.z, xn); xn = __dp4a(q.w, q.w, xn);
-                }
             }
             {   // wait for the accumulator
                 uint32_t done;
@@ -231,33 +291,13 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
                              : "r"(taddr + 16 * g));
             }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (on) {
-                const unsigned long long *cnc = cn + (mine * k + 1);
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    if (c >= k) break;                                            // block-uniform: no predicated-off work
-                    // v1 * 256 + v2 < 2^32 (each accumulator < 2^23), so only one 64-bit multiply-add
-                    const unsigned int lo = (v[16 + c] << 8) + v[32 + c];
-                    const long long dot = (long long)(((unsigned long long)v[c] << 16) + lo);
-                    const long long s = (long long)cnc[c] - (dot << 17);          // |c|^2 - 2 x.c, units 2^-32
-                    if (s < best) { second = best; best = s; arg = c; }
-                    else if (s < second) second = s;
-                }
-            }
+            if (on) score_children(v, s_cn, k, best, second, arg);
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncthreads();                                    // TMEM and the B tile may be reused
         }
 
         // provable margin for the centroid rounding; contested rows go to canonical binary64
-        bool contested = false;
-        if (is_int && k > 1) {
-            // |error| <= m * (da + db) + tiny with m = 2^-16 * sqrt(128) * 1.02 and da <= db, so
-            // "gap <= 2 m db + 1e-6" is a safe (slightly wider) test; squared to avoid the square roots
-            const double d2b = fmax(0.0, (double)second * 2.3283064365386963e-10 + (double)xn);
-            const double gap = (double)(second - best) * 2.3283064365386963e-10 - 1e-6;
-            const double two_m = 2.0 * 1.52587890625e-05 * 11.313708498984761 * 1.02;
-            contested = gap <= 0.0 || gap * gap <= two_m * two_m * d2b;
-        }
+        const bool contested = contested_row(is_int && k > 1, best, second, sA, tid);
         unsigned int m = __ballot_sync(VT_FULL, contested);
         while (m) {
             const int src = __ffs(m) - 1;
@@ -269,16 +309,22 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
             if (lane == src) { arg = res; ++rechecks; }
         }
         uint32_t key = (jp << bits) | dmask;                     // stopped
-        if (is_int) {
-            const long long child = node * k + 1 + arg;
-            if (is_last || !((child * k + k < n_heap) && internal[child])) {
-                if (leaf_out) leaf_out[row] = (int32_t)child;
-                if (word_out) word_out[row] = ref_id[child];
-            } else {
-                key = (jp << bits) | (uint32_t)arg;              // path of the child
+        const long long child = node * k + 1 + arg;
+        if (is_last == 2) {
+            // deferred output: (row, child) pairs leave in tile order (coalesced); vt_mma_levels buckets them
+            // by row range and writes the ids from there, instead of 4-byte writes all over the output here
+            if (valid) { keys_out[p] = is_int ? row : 0xffffffffu; perm_out[p] = (uint32_t)child; }
+        } else {
+            if (is_int) {
+                if (is_last || !((child * k + k < n_heap) && internal[child])) {
+                    if (leaf_out) leaf_out[row] = (int32_t)child;
+                    if (word_out) word_out[row] = ref_id[child];
+                } else {
+                    key = (jp << bits) | (uint32_t)arg;          // path of the child
+                }
             }
+            if (valid && keys_out) { keys_out[p] = key; perm_out[p] = row; }
         }
-        if (valid && keys_out) { keys_out[p] = key; perm_out[p] = row; }
         __syncthreads();                                        // s_row / A tile reused by the next tile
     }
 #pragma unroll
@@ -289,6 +335,27 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(MM_TMEM_COLS));
 }
 
+// deferred output of the last level: pairs bucketed by row range, so the 4-byte writes of neighbouring CTAs
+// fall into a window of a few MB that the L2 turns into full lines
+__global__ void __launch_bounds__(256)
+deferred_output_kernel(const uint32_t *__restrict__ rows, const uint32_t *__restrict__ child, int64_t n,
+                       const int32_t *__restrict__ ref_id, int32_t *__restrict__ leaf_out, int32_t *__restrict__ word_out)
+{
+    // the partially written sectors of the current bucket must stay in L2 until their other words arrive
+    // (evict_last); the pairs are read once (evict_first)
+    unsigned long long keep, stream;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(stream));
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t r, c;
+        asm volatile("ld.global.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(r) : "l"(rows + p), "l"(stream));
+        if (r == 0xffffffffu) continue;
+        asm volatile("ld.global.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(c) : "l"(child + p), "l"(stream));
+        if (leaf_out) asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(leaf_out + r), "r"(c), "l"(keep) : "memory");
+        if (word_out)
+            asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(word_out + r), "r"(ref_id[c]), "l"(keep) : "memory");
+    }
+}
 }  // namespace
 
 // =====================================================================================================
@@ -665,8 +732,12 @@ int vt_mma_prepare(const float *cent, int k, int depth, void *planes_and_norms, 
     uint8_t *bimg = (uint8_t *)planes_and_norms;
     const int64_t planes = ((n_int * MM_B_BYTES + 255) / 256) * 256;
     unsigned long long *cn = (unsigned long long *)(bimg + planes);
+    int64_t n_heap = 0, pw = 1;
+    for (int l = 0; l <= depth; ++l) { n_heap += pw; pw *= k; }
+    int *cn32 = (int *)(bimg + planes + ((n_heap * 8 + 255) / 256) * 256);
     const int64_t cap = (int64_t)vt_sm_count() * 16;
-    prep_planes_kernel<<<(int)(n_int < cap ? n_int : cap), 128, 0, s>>>(cent, n_int, k, bimg, cn, (unsigned long long *)stats);
+    prep_planes_kernel<<<(int)(n_int < cap ? n_int : cap), 128, 0, s>>>(cent, n_int, k, bimg, cn, cn32,
+                                                                          (unsigned long long *)stats);
     VT_LAUNCH_CHECK();
     return VT_OK;
 }
@@ -675,7 +746,8 @@ int64_t vt_mma_prepared_bytes(int k, int depth)
 {
     int64_t n_heap = 0, p = 1;
     for (int l = 0; l <= depth; ++l) { n_heap += p; p *= k; }
-    return ((mma_int_nodes(k, depth) * MM_B_BYTES + 255) / 256) * 256 + ((n_heap * 8 + 255) / 256) * 256;
+    return ((mma_int_nodes(k, depth) * MM_B_BYTES + 255) / 256) * 256 + ((n_heap * 8 + 255) / 256) * 256 +
+           mma_int_nodes(k, depth) * 64;                         // planes, 64-bit norms, 32-bit norms (16 per node)
 }
 
 // the level loop; `prepared` from vt_mma_prepare, `sortwork` = 16 n + vt_sort_scratch_bytes(n) bytes
@@ -687,41 +759,64 @@ int vt_mma_levels(const void *d_desc, int64_t n, const float *cent, const uint8_
 #define VT_MARK() do { if (ev) VT_CUDA(cudaEventRecord(ev[n_ev++], s)); } while (0)
     int64_t n_heap = 0, pw = 1;
     for (int l = 0; l <= depth; ++l) { n_heap += pw; pw *= k; }
+    VT_CHECK_ARG(n_heap < ((int64_t)1 << 31), "tree too large for 32-bit node ids");
     const int64_t n_int = mma_int_nodes(k, depth);
     const uint8_t *bimg = (const uint8_t *)prepared;
     const int64_t planes = ((n_int * MM_B_BYTES + 255) / 256) * 256;
-    const unsigned long long *cn = (const unsigned long long *)(bimg + planes);
+    const int *cn = (const int *)(bimg + planes + ((n_heap * 8 + 255) / 256) * 256);     // 32-bit norms
     uint32_t *kA = (uint32_t *)sortwork, *kB = kA + n, *pA = kB + n, *pB = pA + n;
     void *hist = (void *)(pB + n);
     const uint8_t *desc = (const uint8_t *)d_desc;
     static bool attr_set = false;
+    static int ctas = 7;                                         // resident CTAs per SM the grid is sized for
+    static int64_t defer_min = (int64_t)1 << 22;                 // batches from this size on defer the last level's output
     const int smem = MM_A_BYTES + MM_B_BYTES + 1024;
     if (!attr_set) {
-        VT_CUDA(cudaFuncSetAttribute(level_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        const char *e = getenv("VT_MMA_CTAS");
+        if (e && atoi(e) >= 1 && atoi(e) <= 7) ctas = atoi(e);
+        e = getenv("VT_MMA_DEFER_MIN");
+        if (e) defer_min = atoll(e);
+        VT_CUDA(cudaFuncSetAttribute(level_mma_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    const int64_t want = (n + MM_TILE - 1) / MM_TILE, cap = (int64_t)vt_sm_count() * 6;
+    const int64_t want = (n + MM_TILE - 1) / MM_TILE, cap = (int64_t)vt_sm_count() * ctas;
     const int blocks = (int)(want < cap ? want : cap);
     uint32_t *keys = kA, *perm = pA, *tkeys = kB, *tperm = pB;
     const uint32_t *cur_perm = nullptr, *cur_parent = nullptr;
     const int bits = path_bits(k);
+    const bool defer = n >= defer_min;
     for (int level = 0; level < depth; ++level) {
-        const int is_last = level + 1 == depth;
-        uint32_t *keys_out = is_last ? nullptr : (level == 0 ? keys : tkeys);
-        uint32_t *perm_out = is_last ? nullptr : (level == 0 ? perm : tperm);
+        const bool last = level + 1 == depth;
+        const int is_last = last ? (defer ? 2 : 1) : 0;
+        uint32_t *keys_out = last && !defer ? nullptr : (level == 0 ? keys : tkeys);
+        uint32_t *perm_out = last && !defer ? nullptr : (level == 0 ? perm : tperm);
         if (level > 0) VT_MARK();
-        level_mma_kernel<<<blocks, MM_TILE, smem, s>>>(desc, cur_perm, cur_parent, n, level, bits, n_heap, k,
-                                                       is_last, cent, internal, ref_id, bimg, cn, keys_out, perm_out, leaf,
-                                                       word, (unsigned long long *)stats);
+        level_mma_kernel<7><<<blocks, MM_TILE, smem, s>>>(desc, cur_perm, cur_parent, n, level, bits, n_heap, k, is_last,
+                                                          cent, internal, ref_id, bimg, cn, keys_out, perm_out, leaf, word,
+                                                          (unsigned long long *)stats);
         VT_LAUNCH_CHECK();
+        if (last && defer) {
+            // (row, child) pairs -> 256 buckets of consecutive rows -> ids written bucket by bucket
+            uint32_t *ok = level == 0 ? tkeys : keys, *op = level == 0 ? tperm : perm;
+            int nb = 0;
+            while (((int64_t)1 << nb) < n) ++nb;
+            const int rc = vt_sort_pass_impl(keys_out, perm_out, ok, op, n, nb > 8 ? nb - 8 : 0, 0xffu, hist, s);
+            if (rc != VT_OK) return rc;
+            // one resident wave, grid-stride: all CTAs sweep the buckets together, so the rows being written at
+            // any moment lie in one or two buckets
+            const int64_t w2 = (n + 255) / 256, c2 = (int64_t)vt_sm_count() * 8;
+            deferred_output_kernel<<<(int)(w2 < c2 ? w2 : c2), 256, 0, s>>>(ok, op, n, ref_id, leaf, word);
+            VT_LAUNCH_CHECK();
+        }
         VT_MARK();
-        if (is_last) break;
+        if (last) break;
         if (level > 0) { uint32_t *t; t = keys; keys = tkeys; tkeys = t; t = perm; perm = tperm; tperm = t; }
-        int flip = 0;
-        // ONE stable pass over the low 8 bits of the packed paths groups the rows by their new node
-        const int rc = vt_sort_pairs_impl(keys, perm, tkeys, tperm, n, 8, hist, &flip, s);
+        // The rows are grouped by node already, so ONE stable pass over the newest digit of the packed paths
+        // regroups them by child node (digit-major: the rows of one (node, child) pair stay contiguous).
+        // Few long runs per tile -> long coalesced segments in the scatter.
+        const int rc = vt_sort_pass_impl(keys, perm, tkeys, tperm, n, 0, bits <= 8 ? (1u << bits) - 1u : 0xffu, hist, s);
         if (rc != VT_OK) return rc;
-        if (flip) { uint32_t *t; t = keys; keys = tkeys; tkeys = t; t = perm; perm = tperm; tperm = t; }
+        { uint32_t *t; t = keys; keys = tkeys; tkeys = t; t = perm; perm = tperm; tperm = t; }
         cur_parent = keys;
         cur_perm = perm;
     }

@@ -18,7 +18,8 @@ constexpr int SORT_WARP_ITEMS = 32 * SORT_ROUNDS;        // 512 contiguous items
 constexpr int SORT_TILE = SORT_WARP_ITEMS * SORT_WARPS;  // 4096 items per block
 
 __global__ void __launch_bounds__(SORT_THREADS)
-sort_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift, uint32_t *__restrict__ hist, int nblocks)
+sort_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift, uint32_t mask, uint32_t *__restrict__ hist,
+                 int nblocks)
 {
     __shared__ uint32_t cnt[256];
     cnt[threadIdx.x] = 0;
@@ -27,7 +28,7 @@ sort_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift, uint32
 #pragma unroll 4
     for (int r = 0; r < SORT_ROUNDS; ++r) {
         const int64_t idx = start + r * SORT_THREADS + threadIdx.x;
-        if (idx < n) atomicAdd(&cnt[(keys[idx] >> shift) & 0xffu], 1u);
+        if (idx < n) atomicAdd(&cnt[(keys[idx] >> shift) & mask], 1u);
     }
     __syncthreads();
     hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = cnt[threadIdx.x];
@@ -68,7 +69,7 @@ sort_scan_kernel(uint32_t *__restrict__ hist, int nblocks, uint32_t *__restrict_
 
 __global__ void __launch_bounds__(SORT_THREADS)
 sort_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
-                    uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n, int shift,
+                    uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n, int shift, uint32_t mask,
                     const uint32_t *__restrict__ hist, const uint32_t *__restrict__ digit_total, int nblocks)
 {
     // The tile is first ordered by digit in shared memory and then written out run by run, so that the
@@ -106,7 +107,7 @@ sort_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__rest
         const bool valid = idx < n;
         key[r] = valid ? keys_in[idx] : 0u;
         val[r] = valid ? vals_in[idx] : 0u;
-        const uint32_t d = (key[r] >> shift) & 0xffu;
+        const uint32_t d = (key[r] >> shift) & mask;
         const uint32_t tag = valid ? d : (0x100u | (uint32_t)lane);        // invalid lanes match nobody
         const uint32_t peers = __match_any_sync(VT_FULL, tag);
         const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
@@ -151,7 +152,7 @@ sort_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__rest
     for (int r = 0; r < SORT_ROUNDS; ++r) {
         const int64_t idx = wstart + r * 32 + lane;
         if (idx < n) {
-            const uint32_t d = (key[r] >> shift) & 0xffu;
+            const uint32_t d = (key[r] >> shift) & mask;
             const uint32_t pos = tstart[d] + wcnt[warp][d] + lrank[r];
             s_key[pos] = key[r];
             s_val[pos] = val[r];
@@ -161,7 +162,7 @@ sort_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__rest
     const uint32_t n_tile = tstart[256];
     for (uint32_t i = threadIdx.x; i < n_tile; i += SORT_THREADS) {
         const uint32_t k2 = s_key[i];
-        const uint32_t d = (k2 >> shift) & 0xffu;
+        const uint32_t d = (k2 >> shift) & mask;
         const uint32_t pos = dbase[d] + (i - tstart[d]);
         keys_out[pos] = k2;
         vals_out[pos] = s_val[i];
@@ -189,12 +190,13 @@ int vt_sort_pairs_impl(uint32_t *d_keys, uint32_t *d_vals, uint32_t *d_tmp_keys,
     uint32_t *digit_total = hist + (size_t)256 * nblocks;
     uint32_t *kin = d_keys, *vin = d_vals, *kout = d_tmp_keys, *vout = d_tmp_vals;
     int flips = 0;
+    const uint32_t mask = 0xffu;
     for (int shift = 0; shift < n_bits; shift += 8) {
-        sort_hist_kernel<<<nblocks, SORT_THREADS, 0, s>>>(kin, n, shift, hist, nblocks);
+        sort_hist_kernel<<<nblocks, SORT_THREADS, 0, s>>>(kin, n, shift, mask, hist, nblocks);
         VT_LAUNCH_CHECK();
         sort_scan_kernel<<<256, SORT_THREADS, 0, s>>>(hist, nblocks, digit_total);
         VT_LAUNCH_CHECK();
-        sort_scatter_kernel<<<nblocks, SORT_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, hist, digit_total, nblocks);
+        sort_scatter_kernel<<<nblocks, SORT_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, mask, hist, digit_total, nblocks);
         VT_LAUNCH_CHECK();
         uint32_t *t;
         t = kin; kin = kout; kout = t;
@@ -202,6 +204,24 @@ int vt_sort_pairs_impl(uint32_t *d_keys, uint32_t *d_vals, uint32_t *d_tmp_keys,
         ++flips;
     }
     *result_in_tmp = flips & 1;
+    return VT_OK;
+}
+
+// one stable pass over the digit (key >> shift) & mask, mask <= 0xff (kin/vin -> kout/vout)
+int vt_sort_pass_impl(const uint32_t *kin, const uint32_t *vin, uint32_t *kout, uint32_t *vout, int64_t n, int shift,
+                      uint32_t mask, void *d_hist, cudaStream_t s)
+{
+    VT_CHECK_ARG(n > 0 && n < ((int64_t)1 << 31) && shift >= 0 && shift <= 24 && mask <= 0xffu, "bad arguments");
+    VT_CHECK_ARG(kin && vin && kout && vout && d_hist, "null buffer");
+    const int nblocks = (int)((n + SORT_TILE - 1) / SORT_TILE);
+    uint32_t *hist = (uint32_t *)d_hist;
+    uint32_t *digit_total = hist + (size_t)256 * nblocks;
+    sort_hist_kernel<<<nblocks, SORT_THREADS, 0, s>>>(kin, n, shift, mask, hist, nblocks);
+    VT_LAUNCH_CHECK();
+    sort_scan_kernel<<<256, SORT_THREADS, 0, s>>>(hist, nblocks, digit_total);
+    VT_LAUNCH_CHECK();
+    sort_scatter_kernel<<<nblocks, SORT_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, mask, hist, digit_total, nblocks);
+    VT_LAUNCH_CHECK();
     return VT_OK;
 }
 
