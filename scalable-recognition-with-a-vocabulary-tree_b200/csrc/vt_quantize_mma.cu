@@ -376,7 +376,7 @@ constexpr int MM_H_BYTES = 16 * 128;           // one-hot tile: 16 clusters x 12
 
 __global__ void __launch_bounds__(128)
 prep_level_planes_kernel(const float *__restrict__ child_cent, int64_t n_nodes, int k, uint8_t *__restrict__ bimg,
-                         unsigned long long *__restrict__ cn, unsigned long long *__restrict__ stats)
+                         int *__restrict__ cn32, unsigned long long *__restrict__ stats)
 {
     __shared__ unsigned long long s_part[4];
     const int d = threadIdx.x;
@@ -398,7 +398,8 @@ prep_level_planes_kernel(const float *__restrict__ child_cent, int64_t n_nodes, 
             for (int o = 16; o >= 1; o >>= 1) sq += __shfl_xor_sync(VT_FULL, sq, o);
             if ((d & 31) == 0) s_part[d >> 5] = sq;
             __syncthreads();
-            if (d == 0 && c < k) cn[h * k + c] = s_part[0] + s_part[1] + s_part[2] + s_part[3];
+            if (d == 0)     // |c|^2 in units 2^-7, rounded down (see score_children)
+                cn32[h * 16 + c] = c < k ? (int)((s_part[0] + s_part[1] + s_part[2] + s_part[3]) >> MM_S_SHIFT) : 0x3fffffff;
             __syncthreads();
         }
         if (bad && stats) atomicAdd(stats + 1, 1ull);
@@ -408,7 +409,7 @@ prep_level_planes_kernel(const float *__restrict__ child_cent, int64_t n_nodes, 
 __global__ void __launch_bounds__(MM_TILE, 6)
 kmeans_mma_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ perm, const int32_t *__restrict__ parent,
                   int64_t n, const uint8_t *__restrict__ node_internal, int k, const float *__restrict__ child_cent,
-                  const uint8_t *__restrict__ bimg, const unsigned long long *__restrict__ cn,
+                  const uint8_t *__restrict__ bimg, const int *__restrict__ cn32,
                   uint8_t *__restrict__ label, unsigned long long *__restrict__ sums,
                   unsigned long long *__restrict__ counts, unsigned long long *__restrict__ changed,
                   unsigned long long *__restrict__ stats)
@@ -423,9 +424,10 @@ kmeans_mma_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ 
     __shared__ uint32_t s_row[MM_TILE];
     __shared__ long long s_min[4];
     __shared__ int s_cnt[16];
+    __shared__ __align__(16) int s_cn[16];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long none = 0x7fffffffffffffffLL;
+    const int none = 0x7fffffff;
     unsigned int rechecks = 0, n_changed = 0;
 
     if (warp == 0) {
@@ -499,10 +501,8 @@ kmeans_mma_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ 
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + 2048u * i), "l"(src), "r"(ok ? 16 : 0));
             }
         }
-        long long best = none, second = none;
-        int arg = 0;
+        int best = none, second = none, arg = 0;
         bool pending = is_int;
-        unsigned int xn = 0;
 
         // ---- assignment: one distance MMA per distinct node of the tile --------------------------------
         for (int pass = 0;; ++pass) {
@@ -523,6 +523,8 @@ kmeans_mma_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ 
                 const int c = tid + MM_TILE * i;
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sB) + c * 16), "l"(bsrc + c * 16));
             }
+            if (tid < 4)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_cn) + tid * 16), "l"(cn32 + mine * 16 + tid * 4));
             asm volatile("cp.async.commit_group;");
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -539,13 +541,6 @@ kmeans_mma_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ 
                 }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
             }
-            if (pass == 0 && is_int) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint4 q = *reinterpret_cast<const uint4 *>(sA + (tid >> 3) * 1024 + (tid & 7) * 128 + ((j ^ (tid & 7)) << 4));
-                    xn = __dp4a(q.x, q.x, xn); xn = __dp4a(q.y, q.y, xn); xn = __dp4a(q.z, q.z, xn); xn = __dp4a(q.w, q.w, xn);
-                }
-            }
             wait_mma();
             uint32_t v[MM_N];
             const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
@@ -559,28 +554,11 @@ kmeans_mma_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ 
                              : "r"(taddr + 16 * g));
             }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (on) {
-                const unsigned long long *cnc = cn + mine * k;
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    if (c >= k) break;
-                    const unsigned int lo = (v[16 + c] << 8) + v[32 + c];
-                    const long long dot = (long long)(((unsigned long long)v[c] << 16) + lo);
-                    const long long s = (long long)cnc[c] - (dot << 17);
-                    if (s < best) { second = best; best = s; arg = c; }
-                    else if (s < second) second = s;
-                }
-            }
+            if (on) score_children(v, s_cn, k, best, second, arg);
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncthreads();
         }
-        bool contested = false;
-        if (is_int && k > 1) {
-            const double d2b = fmax(0.0, (double)second * 2.3283064365386963e-10 + (double)xn);
-            const double gap = (double)(second - best) * 2.3283064365386963e-10 - 1e-6;
-            const double two_m = 2.0 * 1.52587890625e-05 * 11.313708498984761 * 1.02;
-            contested = gap <= 0.0 || gap * gap <= two_m * two_m * d2b;
-        }
+        const bool contested = contested_row(is_int && k > 1, best, second, sA, tid);
         unsigned int m = __ballot_sync(VT_FULL, contested);
         while (m) {
             const int src = __ffs(m) - 1;
@@ -663,7 +641,8 @@ kmeans_mma_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ 
 // centroid byte planes + fixed-point norms of one LEVEL (node j -> image j, child rows j*k + c)
 extern "C" int64_t vt_kmeans_planes_bytes(int64_t n_nodes, int k)
 {
-    return ((n_nodes * MM_B_BYTES + 255) / 256) * 256 + ((n_nodes * k * 8 + 255) / 256) * 256;
+    (void)k;
+    return ((n_nodes * MM_B_BYTES + 255) / 256) * 256 + n_nodes * 64;      // byte planes + 16 32-bit norms per node
 }
 
 extern "C" int vt_kmeans_planes(const float *d_child_centroids, int64_t n_nodes, int k, int dp, void *d_planes,
@@ -671,7 +650,7 @@ extern "C" int vt_kmeans_planes(const float *d_child_centroids, int64_t n_nodes,
 {
     VT_CHECK_ARG(dp == 128 && k >= 1 && k <= 16 && n_nodes >= 1, "tensor-core k-means needs dp == 128 and k <= 16");
     uint8_t *bimg = (uint8_t *)d_planes;
-    unsigned long long *cn = (unsigned long long *)(bimg + ((n_nodes * MM_B_BYTES + 255) / 256) * 256);
+    int *cn = (int *)(bimg + ((n_nodes * MM_B_BYTES + 255) / 256) * 256);
     const int64_t cap = (int64_t)vt_sm_count() * 16;
     prep_level_planes_kernel<<<(int)(n_nodes < cap ? n_nodes : cap), 128, 0, (cudaStream_t)stream>>>(
         d_child_centroids, n_nodes, k, bimg, cn, (unsigned long long *)d_stats);
@@ -691,7 +670,7 @@ extern "C" int vt_kmeans_assign_mma(const void *d_desc, int dtype, int dp, const
     VT_CHECK_ARG(n_members >= 0 && n_nodes >= 1 && d_planes, "bad arguments");
     if (n_members == 0) return VT_OK;
     const uint8_t *bimg = (const uint8_t *)d_planes;
-    const unsigned long long *cn = (const unsigned long long *)(bimg + ((n_nodes * MM_B_BYTES + 255) / 256) * 256);
+    const int *cn = (const int *)(bimg + ((n_nodes * MM_B_BYTES + 255) / 256) * 256);
     static bool attr_set = false;
     const int smem = MM_A_BYTES + 6 * 1024 + MM_H_BYTES + 1024;
     if (!attr_set) {
@@ -785,6 +764,7 @@ int vt_mma_levels(const void *d_desc, int64_t n, const float *cent, const uint8_
     const uint32_t *cur_perm = nullptr, *cur_parent = nullptr;
     const int bits = path_bits(k);
     const bool defer = n >= defer_min;
+    const uint32_t dmask = (1u << bits) - 1u;                    // bits <= 5 for k <= 16
     for (int level = 0; level < depth; ++level) {
         const bool last = level + 1 == depth;
         const int is_last = last ? (defer ? 2 : 1) : 0;
@@ -814,7 +794,7 @@ int vt_mma_levels(const void *d_desc, int64_t n, const float *cent, const uint8_
         // The rows are grouped by node already, so ONE stable pass over the newest digit of the packed paths
         // regroups them by child node (digit-major: the rows of one (node, child) pair stay contiguous).
         // Few long runs per tile -> long coalesced segments in the scatter.
-        const int rc = vt_sort_pass_impl(keys, perm, tkeys, tperm, n, 0, bits <= 8 ? (1u << bits) - 1u : 0xffu, hist, s);
+        const int rc = vt_sort_pass_impl(keys, perm, tkeys, tperm, n, 0, dmask, hist, s);
         if (rc != VT_OK) return rc;
         { uint32_t *t; t = keys; keys = tkeys; tkeys = t; t = perm; perm = tperm; tperm = t; }
         cur_parent = keys;

@@ -83,19 +83,23 @@ sort_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__rest
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int w = 0; w < SORT_WARPS; ++w) wcnt[w][threadIdx.x] = 0;
-    // exclusive scan of the 256 digit totals (Hillis-Steele) -> global digit bases
-    uint32_t mine = digit_total[threadIdx.x];
-    dbase[threadIdx.x] = mine;
-    __syncthreads();
-    for (int o = 1; o < 256; o <<= 1) {
-        const uint32_t t = threadIdx.x >= o ? dbase[threadIdx.x - o] : 0u;
+    // exclusive scan of the 256 digit totals (warp shuffles + one exchange) -> global digit bases
+    {
+        __shared__ uint32_t dtot[SORT_WARPS];
+        const uint32_t mine = digit_total[threadIdx.x];
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(VT_FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) dtot[warp] = incl;
         __syncthreads();
-        dbase[threadIdx.x] += t;
-        __syncthreads();
+        uint32_t woff = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w) if (w < warp) woff += dtot[w];
+        dbase[threadIdx.x] = woff + incl - mine + (threadIdx.x <= mask ? hist[(size_t)threadIdx.x * nblocks + blockIdx.x] : 0u);
     }
-    const uint32_t excl = dbase[threadIdx.x] - mine;
-    __syncthreads();
-    dbase[threadIdx.x] = excl + hist[(size_t)threadIdx.x * nblocks + blockIdx.x];
     __syncthreads();
 
     const int64_t tile0 = (int64_t)blockIdx.x * SORT_TILE;
@@ -218,7 +222,8 @@ int vt_sort_pass_impl(const uint32_t *kin, const uint32_t *vin, uint32_t *kout, 
     uint32_t *digit_total = hist + (size_t)256 * nblocks;
     sort_hist_kernel<<<nblocks, SORT_THREADS, 0, s>>>(kin, n, shift, mask, hist, nblocks);
     VT_LAUNCH_CHECK();
-    sort_scan_kernel<<<256, SORT_THREADS, 0, s>>>(hist, nblocks, digit_total);
+    VT_CUDA(cudaMemsetAsync(digit_total, 0, 256 * sizeof(uint32_t), s));
+    sort_scan_kernel<<<(int)mask + 1, SORT_THREADS, 0, s>>>(hist, nblocks, digit_total);      // digits above the mask do not occur
     VT_LAUNCH_CHECK();
     sort_scatter_kernel<<<nblocks, SORT_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, mask, hist, digit_total, nblocks);
     VT_LAUNCH_CHECK();
