@@ -172,6 +172,143 @@ sort_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__rest
         vals_out[pos] = s_val[i];
     }
 }
+
+// ---- narrow digits (<= 32 classes): the regrouping pass of the level-synchronous descent -------------
+// Same hist -> scan -> scatter scheme and the same scratch layout, but a warp ranks its items with one
+// ballot per digit bit: lane j derives the member mask of class j from the ballots (its running count
+// stays in a register) and every lane the mask of its own class -- no shared-memory counters, no
+// intra-warp synchronisation in the ranking loop.
+template <int NB>
+__global__ void __launch_bounds__(SORT_THREADS)
+split_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift, uint32_t *__restrict__ hist, int nblocks)
+{
+    constexpr int NC = 1 << NB;
+    __shared__ uint32_t cnt[NC];
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < NC) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t start = (int64_t)blockIdx.x * SORT_TILE;
+    uint32_t mine = 0;                                   // lane j: items of class j seen by this warp
+#pragma unroll 4
+    for (int r = 0; r < SORT_ROUNDS; ++r) {
+        const int64_t idx = start + r * SORT_THREADS + threadIdx.x;
+        const bool valid = idx < n;
+        const uint32_t d = valid ? (keys[idx] >> shift) & (NC - 1) : 0u;
+        uint32_t cm = __ballot_sync(VT_FULL, valid);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const uint32_t bb = __ballot_sync(VT_FULL, (d >> b) & 1u);
+            cm &= ((lane >> b) & 1) ? bb : ~bb;
+        }
+        mine += __popc(cm);
+    }
+    if (lane < NC && mine) atomicAdd(&cnt[lane], mine);
+    __syncthreads();
+    if (threadIdx.x < NC) hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = cnt[threadIdx.x];
+}
+
+template <int NB>
+__global__ void __launch_bounds__(SORT_THREADS)
+split_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                     uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n, int shift,
+                     const uint32_t *__restrict__ hist, const uint32_t *__restrict__ digit_total, int nblocks)
+{
+    constexpr int NC = 1 << NB;
+    static_assert(NC <= 32, "one lane per class");
+    __shared__ uint32_t wcnt[SORT_WARPS][NC];         // per-warp class totals -> offsets inside the class run
+    __shared__ uint32_t dbase[NC];                    // global position of this tile's first element of class d
+    __shared__ uint32_t tstart[NC + 1];               // tile-local start of class d
+    __shared__ uint32_t s_key[SORT_TILE];
+    __shared__ uint32_t s_val[SORT_TILE];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    if (warp == 0) {                                  // exclusive scan of the class totals + this tile's offsets
+        const uint32_t v = lane < NC ? digit_total[lane] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(VT_FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane < NC) dbase[lane] = incl - v + hist[(size_t)lane * nblocks + blockIdx.x];
+    }
+    const int64_t tile0 = (int64_t)blockIdx.x * SORT_TILE;
+    const int64_t wstart = tile0 + (int64_t)warp * SORT_WARP_ITEMS;
+    uint32_t key[SORT_ROUNDS], val[SORT_ROUNDS], lrank[SORT_ROUNDS];
+    uint32_t wc = 0;                                  // lane j: this warp's running count of class j
+#pragma unroll
+    for (int r = 0; r < SORT_ROUNDS; ++r) {
+        const int64_t idx = wstart + r * 32 + lane;
+        const bool valid = idx < n;
+        key[r] = valid ? keys_in[idx] : 0u;
+        val[r] = valid ? vals_in[idx] : 0u;
+        const uint32_t d = (key[r] >> shift) & (NC - 1);
+        const uint32_t vm = __ballot_sync(VT_FULL, valid);
+        uint32_t cm = vm, pm = vm;                    // members of class `lane` / of this lane's own class
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const uint32_t bb = __ballot_sync(VT_FULL, (d >> b) & 1u);
+            cm &= ((lane >> b) & 1) ? bb : ~bb;
+            pm &= ((d >> b) & 1u) ? bb : ~bb;
+        }
+        lrank[r] = __shfl_sync(VT_FULL, wc, (int)d) + __popc(pm & lt);
+        wc += __popc(cm);
+    }
+    if (lane < NC) wcnt[warp][lane] = wc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t run = 0;
+        if (lane < NC) {
+#pragma unroll
+            for (int w = 0; w < SORT_WARPS; ++w) {
+                const uint32_t t = wcnt[w][lane];
+                wcnt[w][lane] = run;
+                run += t;
+            }
+        }
+        uint32_t incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(VT_FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane < NC) tstart[lane] = incl - run;
+        if (lane == NC - 1) tstart[NC] = incl;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SORT_ROUNDS; ++r) {
+        const int64_t idx = wstart + r * 32 + lane;
+        if (idx < n) {
+            const uint32_t d = (key[r] >> shift) & (NC - 1);
+            const uint32_t pos = tstart[d] + wcnt[warp][d] + lrank[r];
+            s_key[pos] = key[r];
+            s_val[pos] = val[r];
+        }
+    }
+    __syncthreads();
+    const uint32_t n_tile = tstart[NC];
+    for (uint32_t i = threadIdx.x; i < n_tile; i += SORT_THREADS) {
+        const uint32_t k2 = s_key[i];
+        const uint32_t d = (k2 >> shift) & (NC - 1);
+        const uint32_t pos = dbase[d] + (i - tstart[d]);
+        keys_out[pos] = k2;
+        vals_out[pos] = s_val[i];
+    }
+}
+
+template <int NB>
+static int launch_split(const uint32_t *kin, const uint32_t *vin, uint32_t *kout, uint32_t *vout, int64_t n, int shift,
+                        uint32_t *hist, uint32_t *digit_total, int nblocks, cudaStream_t s)
+{
+    split_hist_kernel<NB><<<nblocks, SORT_THREADS, 0, s>>>(kin, n, shift, hist, nblocks);
+    VT_LAUNCH_CHECK();
+    sort_scan_kernel<<<1 << NB, SORT_THREADS, 0, s>>>(hist, nblocks, digit_total);
+    VT_LAUNCH_CHECK();
+    split_scatter_kernel<NB><<<nblocks, SORT_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, hist, digit_total, nblocks);
+    VT_LAUNCH_CHECK();
+    return VT_OK;
+}
 }  // namespace
 
 extern "C" int64_t vt_sort_scratch_bytes(int64_t n)
@@ -220,6 +357,8 @@ int vt_sort_pass_impl(const uint32_t *kin, const uint32_t *vin, uint32_t *kout, 
     const int nblocks = (int)((n + SORT_TILE - 1) / SORT_TILE);
     uint32_t *hist = (uint32_t *)d_hist;
     uint32_t *digit_total = hist + (size_t)256 * nblocks;
+    if (mask <= 15u) return launch_split<4>(kin, vin, kout, vout, n, shift, hist, digit_total, nblocks, s);
+    if (mask <= 31u) return launch_split<5>(kin, vin, kout, vout, n, shift, hist, digit_total, nblocks, s);
     sort_hist_kernel<<<nblocks, SORT_THREADS, 0, s>>>(kin, n, shift, mask, hist, nblocks);
     VT_LAUNCH_CHECK();
     VT_CUDA(cudaMemsetAsync(digit_total, 0, 256 * sizeof(uint32_t), s));
