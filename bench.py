@@ -279,7 +279,9 @@ def main():
     level_ms, sort_ms = stage_profile(lib.vt_quantize_mma_profile if method == "mma" else lib.vt_quantize_sorted_profile)
     other_ms, _ = stage_profile(lib.vt_quantize_sorted_profile if method == "mma" else lib.vt_quantize_mma_profile, reps=1)
     sort_passes = DEPTH - 1                     # packed paths: one radix pass (hist, scan, scatter) per level transition
-    launches_per_step = DEPTH + 3 * sort_passes     # (the tensor path's byte planes are prepared once per tree, outside the steps)
+    # (the tensor path's byte planes are prepared once per tree, outside the steps); batches of >= 2^22 rows add the
+    # deferred output of the last level: one more radix pass (3 kernels) + the bucketed id write
+    launches_per_step = DEPTH + 3 * sort_passes + (4 if method == "mma" and n >= (1 << 22) else 0)
 
     # the single-launch fused descent on a slice, for comparison
     n_f = min(n, 8_000_000)
@@ -369,10 +371,12 @@ def main():
             "whole_step": {"step_ms_events": kern_ms,
                            "algorithmic_GBps": alg_bytes * per_launch / (kern_ms * 1e-3) / 1e9,
                            "algorithmic_TFLOPs": flop_per_desc * per_launch / (kern_ms * 1e-3) / 1e12},
-            # DRAM bytes per launch of the dominant kernel: ncu --set full (profiles/r01_ncu_final_level_mma_and_scorer.txt,
-            # dram__bytes_read.sum + dram__bytes_write.sum of a 16 M-row level-0 launch = 136.2 B per row), scaled to this launch
-            "traffic": (136.2 * per_launch) if method == "mma" else None,
-            "traffic_source": "ncu capture of a 16 M-row launch, scaled by rows (not re-measured in this run)" if method == "mma" else None,
+            # DRAM bytes per launch of the dominant kernel: ncu capture of this command at 100 M rows
+            # (profiles/r01_launches_final.csv: dram__bytes_read.sum + dram__bytes_write.sum of the six level launches
+            # = 13.6 / 14.4 / 14.4 / 14.4 / 14.5 / 16.0 GB, mean 145.5 B per row), scaled to this launch
+            "traffic": (145.5 * per_launch) if method == "mma" else None,
+            "traffic_source": "ncu launch list of this command at 100 M rows, mean of the six level launches, scaled by rows (not re-measured in this run)" if method == "mma" else None,
+            "level_kernel_ms_note": "entry 0 includes the per-call plane preparation of the profile variant; the last entry includes the deferred output (bucket pass + id write)",
             "other_engine": dict(fill(other_r, other_total_ms), level_kernel_ms=[round(float(v), 3) for v in other_ms]),
             "fused_single_launch_descent": {"value": fused_rate, "unit": "descriptors/s", "rows": n_f},
         })

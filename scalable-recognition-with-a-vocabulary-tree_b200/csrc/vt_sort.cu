@@ -34,7 +34,8 @@ sort_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift, uint32
     hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = cnt[threadIdx.x];
 }
 
-// one block per digit: exclusive scan of that digit's per-tile counts, in place; total -> digit_total
+// one block per digit: exclusive scan of that digit's per-tile counts, in place; total -> digit_total.
+// Four consecutive entries per thread and iteration (the block-wide step is the latency of this kernel).
 __global__ void __launch_bounds__(SORT_THREADS)
 sort_scan_kernel(uint32_t *__restrict__ hist, int nblocks, uint32_t *__restrict__ digit_total)
 {
@@ -42,10 +43,13 @@ sort_scan_kernel(uint32_t *__restrict__ hist, int nblocks, uint32_t *__restrict_
     uint32_t *row = hist + (size_t)blockIdx.x * nblocks;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t carry = 0;
-    for (int base = 0; base < nblocks; base += SORT_THREADS) {
-        const int idx = base + threadIdx.x;
-        const uint32_t v = idx < nblocks ? row[idx] : 0u;
-        uint32_t incl = v;
+    for (int base = 0; base < nblocks; base += 4 * SORT_THREADS) {
+        const int idx = base + 4 * threadIdx.x;
+        uint32_t v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = idx + j < nblocks ? row[idx + j] : 0u;
+        const uint32_t mine = v[0] + v[1] + v[2] + v[3];
+        uint32_t incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t t = __shfl_up_sync(VT_FULL, incl, o);
@@ -60,7 +64,12 @@ sort_scan_kernel(uint32_t *__restrict__ hist, int nblocks, uint32_t *__restrict_
             if (w < warp) woff += t;
             total += t;
         }
-        if (idx < nblocks) row[idx] = carry + woff + incl - v;
+        uint32_t run = carry + woff + incl - mine;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (idx + j < nblocks) row[idx + j] = run;
+            run += v[j];
+        }
         carry += total;
         __syncthreads();
     }
@@ -189,11 +198,17 @@ split_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift, uint3
     __syncthreads();
     const int64_t start = (int64_t)blockIdx.x * SORT_TILE;
     uint32_t mine = 0;                                   // lane j: items of class j seen by this warp
-#pragma unroll 4
+    uint32_t kreg[SORT_ROUNDS];
+#pragma unroll
+    for (int r = 0; r < SORT_ROUNDS; ++r) {                 // every load of the tile in flight before the first ballot
+        const int64_t idx = start + r * SORT_THREADS + threadIdx.x;
+        kreg[r] = idx < n ? keys[idx] : 0u;
+    }
+#pragma unroll
     for (int r = 0; r < SORT_ROUNDS; ++r) {
         const int64_t idx = start + r * SORT_THREADS + threadIdx.x;
         const bool valid = idx < n;
-        const uint32_t d = valid ? (keys[idx] >> shift) & (NC - 1) : 0u;
+        const uint32_t d = (kreg[r] >> shift) & (NC - 1);
         uint32_t cm = __ballot_sync(VT_FULL, valid);
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
