@@ -163,6 +163,7 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
     __shared__ uint32_t s_tmem;
     __shared__ uint32_t s_row[MM_TILE];
     __shared__ long long s_min[4];
+    __shared__ int s_max[4];
     __shared__ __align__(16) int s_cn[16];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -235,14 +236,23 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
         // one MMA pass per distinct node present in the tile (sorted batch: almost always one)
         for (int pass = 0;; ++pass) {
             // heap / level indices fit 31 bits (ids are int32 across the ABI): 32-bit warp minimum
+            // (the maximum rides along: when it equals the minimum this is the tile's only node and the loop
+            // ends after this pass without another block-wide reduction)
             int mine32 = pending ? (int)node : 0x7fffffff;
+            int max32 = pending ? (int)node : -1;
             mine32 = __reduce_min_sync(VT_FULL, mine32);
-            if (lane == 0) s_min[warp] = mine32;
+            max32 = __reduce_max_sync(VT_FULL, max32);
+            if (lane == 0) { s_min[warp] = mine32; s_max[warp] = max32; }
             __syncthreads();
             long long mine = s_min[0];
+            int maxn = s_max[0];
 #pragma unroll
-            for (int w = 1; w < 4; ++w) mine = s_min[w] < mine ? s_min[w] : mine;
+            for (int w = 1; w < 4; ++w) {
+                mine = s_min[w] < mine ? s_min[w] : mine;
+                maxn = s_max[w] > maxn ? s_max[w] : maxn;
+            }
             if (mine == 0x7fffffff) break;                            // block-uniform
+            const bool only_node = (long long)maxn == mine;           // block-uniform
             const bool on = pending && node == mine;
             pending = pending && !on;
             // B tile of this node: 384 x 16 B, already in swizzled image form
@@ -294,6 +304,7 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
             if (on) score_children(v, s_cn, k, best, second, arg);
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncthreads();                                    // TMEM and the B tile may be reused
+            if (only_node) break;
         }
 
         // provable margin for the centroid rounding; contested rows go to canonical binary64
