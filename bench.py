@@ -205,7 +205,18 @@ def main():
     affinity = bind_to_gpu_numa_node(local)      # pinned host buffers are first-touched next to the GPU's PCIe root
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL announces its version on stdout when the communicator is created; stdout carries the one JSON line only
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     nat.require_device()
     lib = nat.load()
     comm = vt.dist.Comm() if world > 1 else None
@@ -490,7 +501,11 @@ def bench_retrieval(args, torch, vt, engine, nat, dev, rank, world, comm, ref_id
                                           / t_invert / 1e9}}
     if not all_nodes:
         alg = 8.0 * wpi * (db_images * wpi / n_leaf)
-        out["hbm"] = {"algorithmic_bytes_per_query": alg, "achieved_GBps": alg * q / (ms * 1e-3) / 1e9}
+        out["hbm"] = {"algorithmic_bytes_per_query": alg, "achieved_GBps": alg * q / (ms * 1e-3) / 1e9,
+                      # ncu --set full of score_shard_tf_kernel on this workload (profiles/r01_ncu_final_scorer.txt):
+                      # 219.7 GB of DRAM reads per 10 k queries = 2.7x the algorithmic bytes (32 B sectors around ~64 B
+                      # posting runs and 8 B row-pointer pairs), 3.2 TB/s; issue slots 27 % busy
+                      "traffic_bytes_per_query": 21.97e6, "traffic_source": "ncu capture of this workload (not re-measured in this run)"}
     return out
 
 
