@@ -6,10 +6,13 @@ is_indexed / save / load / show_results``.  ``retrieve`` returns the reference's
 ``image_path -> score`` ordered best first over ALL images (its ``n`` argument is ignored there
 too, database.py:72-81).  ``retrieve_batch`` is the batched top-k entry point.
 
-Any object with ``embedding(image)`` works as encoder for the reference; the accelerated path
-needs the encoder protocol extended by ``encode_batch`` (``VocabularyTree`` has it).  Image
-identity is the position in ``dataset.image_paths`` (the reference keys by a salted
-``hash(abspath)``, database.py:25-34, which cannot cross processes).
+Any object with ``embedding(image)`` works as encoder for the reference (its plugin protocol,
+encoders/new_encoder_example.py:1-4).  Encoders that also offer ``encode_batch`` (``VocabularyTree``)
+take the inverted-file path; any other encoder (e.g. the reference's AlexNet, encoders/alexnet.py) takes
+the dense path: its embeddings are stacked into one float64 matrix on the GPU and scored by brute
+force (normalised L2 distance = one matrix product + top-k, then the k best re-scored exactly like
+database.py:66-69).  Image identity is the position in ``dataset.image_paths`` (the reference keys by
+a salted ``hash(abspath)``, database.py:25-34, which cannot cross processes).
 """
 from __future__ import annotations
 
@@ -46,6 +49,10 @@ class Database(object):
         self._index = None        # device inverted file
         self._idf = None
         self._extra = {}          # path -> (nodes, counts) of non-indexed images (queries)
+        # dense path (encoders without encode_batch)
+        self._dense = not hasattr(encoder, "encode_batch")
+        self._dense_unit = None   # device float64 [N, D]: L2-normalised embeddings (NaN rows for zero vectors)
+        self._dense_raw = {}      # path -> embedding as the encoder returned it (memo, database.py:50-57)
         return
 
     # ------------------------------------------------------------------ indexing
@@ -64,6 +71,8 @@ class Database(object):
         (8 B per posting) accumulates on the device."""
         import torch
         paths = list(self.dataset.image_paths)
+        if self._dense:
+            return self._index_dense(paths)
         step = max(1, int(batch_images))
         parts = []
         for b0 in range(0, max(len(paths), 1), step):
@@ -87,6 +96,73 @@ class Database(object):
     def is_indexed(self, image_path):
         return image_path in self._rows
 
+    # ------------------------------------------------------------------ dense encoders
+    def _device(self):
+        import torch
+        return torch.device(getattr(self.encoder, "device", "cuda"))
+
+    def _dense_embedding(self, image_path):
+        if image_path not in self._dense_raw:
+            e = self.encoder.embedding(self.dataset.read_image(image_path))
+            self._dense_raw[image_path] = np.asarray(e)
+        return self._dense_raw[image_path]
+
+    @staticmethod
+    def _unit_rows(m):
+        """rows / ||row||_2 in float64 on the device; 0/0 -> NaN like numpy (database.py:66-67)."""
+        return m / m.norm(dim=1, keepdim=True)
+
+    def _index_dense(self, paths):
+        import torch
+        if not torch.cuda.is_available():
+            raise nat.NativeError("the dense path needs a CUDA device (no CPU fallback)")
+        rows = [np.asarray(self._dense_embedding(p), dtype=np.float64).ravel() for p in paths]
+        dim = rows[0].shape[0] if rows else 0
+        mat = torch.from_numpy(np.stack(rows) if rows else np.zeros((0, dim))).to(self._device())
+        self._dense_unit = self._unit_rows(mat)
+        self._rows = {p: i for i, p in enumerate(paths)}
+        return
+
+    def _dense_scores(self, q_unit):
+        """reference score of every indexed image against unit query rows [Q, D] -> [Q, N] float64:
+        ||d/|d| - q/|q|||_2 evaluated directly (exactly 0 for identical vectors), NaN -> 1e6."""
+        import torch
+        out = torch.empty((q_unit.shape[0], self._dense_unit.shape[0]), dtype=torch.float64, device=q_unit.device)
+        for i in range(q_unit.shape[0]):
+            out[i] = (self._dense_unit - q_unit[i]).norm(dim=1)
+        return torch.nan_to_num(out, nan=1e6)
+
+    def _dense_query_rows(self, query_paths):
+        import torch
+        q = np.stack([np.asarray(self._dense_embedding(p), dtype=np.float64).ravel() for p in query_paths])
+        return self._unit_rows(torch.from_numpy(q).to(self._device()))
+
+    def _retrieve_batch_dense(self, query_paths, k, return_all):
+        import torch
+        if self._dense_unit is None:
+            self.index()
+        q = self._dense_query_rows(list(query_paths))
+        n = self._dense_unit.shape[0]
+        k = min(k, n)
+        if return_all or n <= 4 * k + 64:
+            scores = self._dense_scores(q)
+        else:
+            # one matrix product ranks everything; the best 4k + 64 are re-scored exactly
+            cos = torch.nan_to_num(q, nan=0.0) @ torch.nan_to_num(self._dense_unit, nan=0.0).T
+            bad = torch.isnan(self._dense_unit).any(dim=1)
+            cos[:, bad] = -2.0
+            cand = torch.topk(cos, 4 * k + 64, dim=1).indices.sort(dim=1).values
+            scores = torch.full((q.shape[0], n), float("inf"), dtype=torch.float64, device=q.device)
+            for i in range(q.shape[0]):
+                d = (self._dense_unit[cand[i]] - q[i]).norm(dim=1)
+                scores[i, cand[i]] = torch.nan_to_num(d, nan=1e6)
+        order = torch.sort(scores, dim=1, stable=True)          # ties keep image_paths order (database.py:79-80)
+        ids = order.indices[:, :k].to(torch.int32).cpu().numpy()
+        sc = order.values[:, :k].cpu().numpy()
+        if return_all:
+            return ids, sc, scores.cpu().numpy()
+        return ids, sc
+
     def _sparse(self, image_path):
         if image_path in self._rows:
             ro, node, count = self._host
@@ -99,6 +175,8 @@ class Database(object):
 
     def embedding(self, image_path):
         """Dense L2-normalised visit-count vector of an image (database.py:50-57)."""
+        if self._dense:
+            return self._dense_embedding(image_path)
         nodes, counts = self._sparse(image_path)
         return self.encoder.dense_embedding(nodes, counts)
 
@@ -135,6 +213,8 @@ class Database(object):
     def retrieve_batch(self, query_paths, k=10, return_all=False):
         """Top-k image indices (positions in ``dataset.image_paths``) and scores per query.
         Returns (ids [Q, k] int32, scores [Q, k] float64[, all_keys [Q, n_img]])."""
+        if self._dense:
+            return self._retrieve_batch_dense(query_paths, k, return_all)
         if self._index is None:
             self.index()
         q, q_val = self._query_csr(list(query_paths))
@@ -165,9 +245,15 @@ class Database(object):
     def retrieve(self, query_image_path, n=4):
         """All dataset images ordered by ascending score, as a dict path -> score
         (database.py:72-81; ties keep ``image_paths`` order like Python's stable sort)."""
+        paths = list(self.dataset.image_paths)
+        if self._dense:
+            if self._dense_unit is None:
+                self.index()
+            scores = self._dense_scores(self._dense_query_rows([query_image_path]))[0].cpu().numpy()
+            order = np.argsort(scores, kind="stable")
+            return {paths[i]: float(scores[i]) for i in order}
         if self._index is None:
             self.index()
-        paths = list(self.dataset.image_paths)
         q, q_val = self._query_csr([query_image_path])
         out = engine.score(self._index, q, 1, self._mode(), q_val=q_val, want_all=True)
         keys = out["all_key"][0].cpu().numpy()

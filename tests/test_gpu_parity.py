@@ -483,6 +483,51 @@ def test_streaming_index_equals_one_batch(vt, cuda):
                 np.testing.assert_allclose(sc0, sc1, rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("name", ["small", "orb", "adversarial"])
+def test_dense_encoder_protocol(vt, cuda, name):
+    """ANY object with ``embedding(image)`` is an encoder for Database
+    (encoders/new_encoder_example.py:1-4, e.g. the reference's AlexNet).  Here the plugin returns the
+    reference's own embeddings (golden), so Database.retrieve through the dense GPU path must reproduce
+    the reference's scores and order -- including the NaN -> 1e6 image and the exact 0 of identical images."""
+    g, meta = load_golden(name)
+    images, k, depth, n_iter = golden_inputs(name)
+    ds = vt.ArrayDataset(images)
+    row_of = {}
+    for i, im in enumerate(images):
+        row_of.setdefault(vt.utils.get_image_id(np.ascontiguousarray(im)), i)
+
+    class Plugin(object):
+        calls = 0
+
+        def embedding(self, cv_image):
+            Plugin.calls += 1
+            return g["emb"][row_of[vt.utils.get_image_id(np.ascontiguousarray(cv_image))]]
+
+    db = vt.Database(ds, Plugin())
+    db.index()
+    n_img = len(images)
+    assert Plugin.calls == n_img and all(db.is_indexed(p) for p in ds.image_paths)
+    assert np.array_equal(db.embedding(ds.image_paths[0]), g["emb"][0], equal_nan=True) and Plugin.calls == n_img
+    for qi in range(0, n_img, max(1, n_img // 12)):
+        res = db.retrieve(ds.image_paths[qi])
+        ws = np.empty(n_img)
+        ws[g["order"][qi]] = g["scores"][qi]
+        np.testing.assert_allclose(list(res.values()), g["scores"][qi], rtol=1e-9, atol=1e-12)
+        for a, b in zip([ds.image_paths.index(p) for p in res], g["order"][qi]):
+            assert a == b or abs(ws[a] - ws[b]) <= 1e-9
+        assert db.score(ds.image_paths[min(1, n_img - 1)], ds.image_paths[qi]) == pytest.approx(ws[min(1, n_img - 1)], abs=1e-12)
+    # batched top-k (matrix product + exact re-score of the best candidates when the set is large)
+    ids, sc = db.retrieve_batch(ds.image_paths, k=5)
+    for qi in range(n_img):
+        ws = np.empty(n_img)
+        ws[g["order"][qi]] = g["scores"][qi]
+        np.testing.assert_allclose(sc[qi], g["scores"][qi][:5], rtol=1e-9, atol=1e-12)
+        for a, b in zip(ids[qi], g["order"][qi][:5]):
+            assert a == b or abs(ws[a] - ws[b]) <= 1e-9
+    with pytest.raises(TypeError):
+        vt.Database(42, Plugin())
+
+
 # ------------------------------------------------------------------------------------------ full size
 def test_full_size_quantize_properties(vt, cuda):
     """BASELINE configs[2] shape at a size the oracle cannot check row by row (20 M x 128 through a
