@@ -143,6 +143,22 @@ def test_quantize_tensor_core_path_matches_oracle(vt, cuda, case):
     print(case, "binary64 rechecks:", int(stats[0].item()), "of", len(x) * ft.depth)
 
 
+def test_tensor_core_deferred_output_on_small_batches(cuda):
+    """The last level of batches >= 2^22 rows leaves through the deferred-output path (row-range buckets).
+    A child process lowers that threshold to 1 row (the library reads VT_MMA_DEFER_MIN once) and repeats
+    the tensor-core parity cases -- ragged trees, exact ties, k = 16 -- on small batches."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, VT_MMA_DEFER_MIN="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-x",
+                          "-m", "gpu", "-k", "test_quantize_tensor_core_path_matches_oracle", "-p", "no:cacheprovider"],
+                         env=env, cwd=root, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "6 passed" in out.stdout
+
+
 def test_quantize_start_node_and_empty_batch(vt, cuda):
     torch = _torch()
     ft, g, meta, images = _flat_from_golden(vt, "small")
