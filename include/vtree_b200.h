@@ -225,6 +225,10 @@ int vt_posting_fill(const uint32_t *d_sorted_keys, const uint32_t *d_sorted_entr
  *   d_shard_rho [n_shards] (nullable): (smallest 1/||tf_d||) / (largest 1/||tf_d||) of the shard, scaled
  *        by (1 - 1e-9), or -1 when the shard holds an image without descriptors; enables the tf-mode
  *        fast selection (integer bound on the dot products, binary64 keys for the survivors only)
+ *   long_lists: hint for the tf-mode selection kernel.  0: the posting lists of a query's words are short
+ *        inside a shard (leaf-word indexes: a handful of postings per word and shard); != 0: long lists
+ *        dominate (all-nodes indexes, where the top tree levels list every image) and the kernel is
+ *        launched with a register budget for 6 instead of 4 CTAs per SM.  Results do not depend on it.
  *   d_q_rnorm / d_q_sumsq [n_query], d_img_sumsq [n_img]: norms for the final score (tf mode) */
 int vt_score_shard_size(void);
 int vt_score_max_topk(void);
@@ -233,7 +237,7 @@ int vt_score_topk(const uint32_t *d_post_off, const void *d_postings, const doub
                   int64_t n_img, int64_t n_ref, const int64_t *d_q_off, const int32_t *d_q_node,
                   const float *d_q_val, int64_t n_query, int mode, int topk, double *d_shard_key,
                   int32_t *d_shard_id, double *d_all_key, const uint8_t *d_shard_empty,
-                  const double *d_shard_rho, void *stream);
+                  const double *d_shard_rho, int long_lists, void *stream);
 int vt_topk_merge(const double *d_in_key, const int32_t *d_in_id, int64_t n_query, int n_cand,
                   int topk, int mode, const double *d_q_rnorm, const uint64_t *d_q_sumsq,
                   const uint64_t *d_img_sumsq, double *d_out_key, int32_t *d_out_id,

@@ -210,8 +210,10 @@ score_shard_kernel(const uint32_t *__restrict__ post_off, const uint2 *__restric
 // to the exhaustive selection (keys recomputed on demand).
 constexpr int SC_CAND = 256;
 
-template <int R>
-__global__ void __launch_bounds__(SC_THREADS)
+// MINB: resident CTAs per SM the register budget is set for (4: the lane-per-word walk of short lists keeps its
+// postings in registers; 6: long lists are walked by whole warps and want occupancy instead)
+template <int R, int MINB>
+__global__ void __launch_bounds__(SC_THREADS, MINB)
 score_shard_tf_kernel(const uint32_t *__restrict__ post_off, const uint2 *__restrict__ postings,
                       const double *__restrict__ img_rnorm, int64_t n_img, int64_t n_ref, int n_shards,
                       const int64_t *__restrict__ q_off, const int32_t *__restrict__ q_node,
@@ -505,18 +507,26 @@ static int launch_score(const uint32_t *post_off, const void *postings, const do
 
 static int launch_score_tf(const uint32_t *post_off, const void *postings, const double *img_rnorm, int64_t n_img,
                            int64_t n_ref, const int64_t *q_off, const int32_t *q_node, const float *q_val, int64_t n_query,
-                           int topk, double *out_key, int32_t *out_id, const double *shard_rho, cudaStream_t s)
+                           int topk, double *out_key, int32_t *out_id, const double *shard_rho, int long_lists,
+                           cudaStream_t s)
 {
     constexpr int R = 8192;
     const int n_shards = (int)((n_img + R - 1) / R);
-    auto kern = score_shard_tf_kernel<R>;
     const size_t smem = (size_t)R * 4 + SC_CAND * 12;
-    VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t pairs = n_query * n_shards;
     const int64_t cap = (int64_t)vt_sm_count() * 6 * 4;
-    kern<<<(int)(pairs < cap ? pairs : cap), SC_THREADS, smem, s>>>(post_off, (const uint2 *)postings, img_rnorm, n_img, n_ref,
-                                                                    n_shards, q_off, q_node, q_val, n_query, topk, out_key,
-                                                                    out_id, shard_rho);
+    const int blocks = (int)(pairs < cap ? pairs : cap);
+    if (long_lists) {
+        auto kern = score_shard_tf_kernel<R, 6>;
+        VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<blocks, SC_THREADS, smem, s>>>(post_off, (const uint2 *)postings, img_rnorm, n_img, n_ref, n_shards, q_off,
+                                              q_node, q_val, n_query, topk, out_key, out_id, shard_rho);
+    } else {
+        auto kern = score_shard_tf_kernel<R, 4>;
+        VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<blocks, SC_THREADS, smem, s>>>(post_off, (const uint2 *)postings, img_rnorm, n_img, n_ref, n_shards, q_off,
+                                              q_node, q_val, n_query, topk, out_key, out_id, shard_rho);
+    }
     VT_LAUNCH_CHECK();
     return VT_OK;
 }
@@ -524,7 +534,8 @@ static int launch_score_tf(const uint32_t *post_off, const void *postings, const
 extern "C" int vt_score_topk(const uint32_t *d_post_off, const void *d_postings, const double *d_img_rnorm, int64_t n_img,
                              int64_t n_ref, const int64_t *d_q_off, const int32_t *d_q_node, const float *d_q_val,
                              int64_t n_query, int mode, int topk, double *d_shard_key, int32_t *d_shard_id,
-                             double *d_all_key, const uint8_t *d_shard_empty, const double *d_shard_rho, void *stream)
+                             double *d_all_key, const uint8_t *d_shard_empty, const double *d_shard_rho, int long_lists,
+                             void *stream)
 {
     VT_CHECK_ARG(n_img > 0 && n_ref > 0 && n_query >= 0, "bad sizes");
     VT_CHECK_ARG(topk >= 1 && topk <= SC_MAXK, "topk out of range");
@@ -533,7 +544,7 @@ extern "C" int vt_score_topk(const uint32_t *d_post_off, const void *d_postings,
     cudaStream_t s = (cudaStream_t)stream;
     if (mode == VT_SCORE_TF_L2 && d_all_key == nullptr && d_shard_rho != nullptr)
         return launch_score_tf(d_post_off, d_postings, d_img_rnorm, n_img, n_ref, d_q_off, d_q_node, d_q_val, n_query, topk,
-                               d_shard_key, d_shard_id, d_shard_rho, s);
+                               d_shard_key, d_shard_id, d_shard_rho, long_lists, s);
     switch (mode) {
     case VT_SCORE_TF_L2: return launch_score<VT_SCORE_TF_L2>(d_post_off, d_postings, d_img_rnorm, n_img, n_ref, d_q_off, d_q_node, d_q_val, n_query, topk, d_shard_key, d_shard_id, d_all_key, d_shard_empty, s);
     case VT_SCORE_W_L2: return launch_score<VT_SCORE_W_L2>(d_post_off, d_postings, d_img_rnorm, n_img, n_ref, d_q_off, d_q_node, d_q_val, n_query, topk, d_shard_key, d_shard_id, d_all_key, d_shard_empty, s);

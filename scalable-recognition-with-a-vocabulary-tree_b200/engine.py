@@ -436,8 +436,12 @@ def build_index(csr: dict, n_ref: int, weight: torch.Tensor = None) -> dict:
     hi = torch.cat([rn, rn.new_full((pad,), 0.0)]).view(n_shards, shard).max(1).values
     shard_rho = torch.where((shard_empty == 0) & (hi > 0), lo / hi.clamp(min=1e-300) * (1.0 - 1e-9),
                             torch.full_like(lo, -1.0)).contiguous()
+    # size-biased mean length of a (node, shard) posting run = the run a random posting sits in: a few postings
+    # for leaf-word indexes, thousands once the top tree levels (which list every image) are indexed
+    lens = (post_off[1:] - post_off[:-1]).to(torch.float64)
+    long_lists = bool(nnz > 0 and float((lens * lens).sum().item()) / float(nnz) > 64.0)
     return dict(post_off=post_off, postings=postings[:nnz], rnorm=rnorm[:n_img], sumsq=csr["sumsq"], n_img=n_img,
-                shard_empty=shard_empty, shard_rho=shard_rho,
+                shard_empty=shard_empty, shard_rho=shard_rho, long_lists=long_lists,
                 n_ref=n_ref, shard=shard, n_shards=n_shards, nnz=nnz, weighted=weight is not None)
 
 
@@ -462,7 +466,8 @@ def score(index: dict, q: dict, topk: int, mode: int = nat.SCORE_TF_L2, q_val: t
     nat.check(lib.vt_score_topk(nat.ptr(index["post_off"]), nat.ptr(index["postings"]), nat.ptr(index["rnorm"]),
                                 n_img, index["n_ref"], nat.ptr(q["row_off"]), nat.ptr(q["node"]), nat.ptr(q_val),
                                 nq, mode, topk, nat.ptr(shard_key), nat.ptr(shard_id), nat.ptr(all_key),
-                                nat.ptr(index.get("shard_empty")), nat.ptr(index.get("shard_rho")), s),
+                                nat.ptr(index.get("shard_empty")), nat.ptr(index.get("shard_rho")),
+                                int(index.get("long_lists", 0)), s),
               "vt_score_topk")
     out = dict(all_key=all_key, shard_key=shard_key, shard_id=shard_id, topk=topk)
     if merge:
