@@ -435,6 +435,7 @@ kmeans_mma_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ 
     __shared__ uint32_t s_row[MM_TILE];
     __shared__ long long s_min[4];
     __shared__ int s_cnt[16];
+    __shared__ int s_max[4];
     __shared__ __align__(16) int s_cn[16];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -516,16 +517,27 @@ kmeans_mma_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ 
         bool pending = is_int;
 
         // ---- assignment: one distance MMA per distinct node of the tile --------------------------------
+        // (the maximum rides along with the minimum: a tile with a single node -- the usual case -- leaves
+        // both loops after one pass without another block-wide reduction)
+        long long tile_node = -1;                               // the tile's only node, if it has just one
         for (int pass = 0;; ++pass) {
             // heap / level indices fit 31 bits (ids are int32 across the ABI): 32-bit warp minimum
             int mine32 = pending ? (int)node : 0x7fffffff;
+            int max32 = pending ? (int)node : -1;
             mine32 = __reduce_min_sync(VT_FULL, mine32);
-            if (lane == 0) s_min[warp] = mine32;
+            max32 = __reduce_max_sync(VT_FULL, max32);
+            if (lane == 0) { s_min[warp] = mine32; s_max[warp] = max32; }
             __syncthreads();
             long long mine = s_min[0];
+            int maxn = s_max[0];
 #pragma unroll
-            for (int w = 1; w < 4; ++w) mine = s_min[w] < mine ? s_min[w] : mine;
+            for (int w = 1; w < 4; ++w) {
+                mine = s_min[w] < mine ? s_min[w] : mine;
+                maxn = s_max[w] > maxn ? s_max[w] : maxn;
+            }
             if (mine == 0x7fffffff) break;
+            const bool only_node = (long long)maxn == mine;           // block-uniform
+            if (pass == 0 && only_node) tile_node = mine;
             const bool on = pending && node == mine;
             pending = pending && !on;
             const uint8_t *bsrc = bimg + (size_t)mine * MM_B_BYTES;
@@ -568,6 +580,7 @@ kmeans_mma_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ 
             if (on) score_children(v, s_cn, k, best, second, arg);
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncthreads();
+            if (only_node) break;
         }
         const bool contested = contested_row(is_int && k > 1, best, second, sA, tid);
         unsigned int m = __ballot_sync(VT_FULL, contested);
@@ -587,15 +600,18 @@ kmeans_mma_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ 
         // ---- accumulation: one one-hot MMA per distinct node of the tile --------------------------------
         pending = is_int;
         for (;;) {
-            // heap / level indices fit 31 bits (ids are int32 across the ABI): 32-bit warp minimum
-            int mine32 = pending ? (int)node : 0x7fffffff;
-            mine32 = __reduce_min_sync(VT_FULL, mine32);
-            if (lane == 0) s_min[warp] = mine32;
-            __syncthreads();
-            long long mine = s_min[0];
+            long long mine = tile_node;
+            if (tile_node < 0) {
+                // heap / level indices fit 31 bits (ids are int32 across the ABI): 32-bit warp minimum
+                int mine32 = pending ? (int)node : 0x7fffffff;
+                mine32 = __reduce_min_sync(VT_FULL, mine32);
+                if (lane == 0) s_min[warp] = mine32;
+                __syncthreads();
+                mine = s_min[0];
 #pragma unroll
-            for (int w = 1; w < 4; ++w) mine = s_min[w] < mine ? s_min[w] : mine;
-            if (mine == 0x7fffffff) break;
+                for (int w = 1; w < 4; ++w) mine = s_min[w] < mine ? s_min[w] : mine;
+                if (mine == 0x7fffffff) break;
+            }
             const bool on = pending && node == mine;
             pending = pending && !on;
             if (mine != run_node || run_tiles >= 60000) { flush(); run_node = mine; }   // block-uniform
@@ -630,6 +646,7 @@ kmeans_mma_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ 
             for (int c = 0; c < 16; ++c) run[c] += (int)sv[c];
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncthreads();
+            if (tile_node >= 0) break;
         }
         __syncthreads();
     }
