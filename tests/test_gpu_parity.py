@@ -143,6 +143,41 @@ def test_quantize_tensor_core_path_matches_oracle(vt, cuda, case):
     print(case, "binary64 rechecks:", int(stats[0].item()), "of", len(x) * ft.depth)
 
 
+@pytest.mark.parametrize("scale", [2.0 ** -6, 2.0 ** -10, 2.0 ** -14, 2.0 ** -18])
+def test_tensor_core_margin_under_near_ties(vt, cuda, scale):
+    """The tensor-core kernel compares scores of ROUNDED centroids (8.16 fixed point) in units of 2^-7;
+    whatever that loses must be inside its margin.  Siblings that differ by perturbations of the order of
+    those granularities (and descriptors drawn close to the centroids, so squared distances are small and
+    gaps tiny) make the margin decide a large share of the rows; ids must still equal the binary64 oracle."""
+    torch = _torch()
+    rng = np.random.default_rng(int(-np.log2(scale)))
+    k, depth, d = 10, 3, 128
+    ft = _random_tree(vt, rng, k, depth, d, ragged=False, tie_heavy=False)
+    cent = ft.centroids.copy()
+    for h in range(vt.tree.heap_size(k, depth - 1)):            # every internal node: children = one base + noise
+        kids = slice(h * k + 1, h * k + 1 + k)
+        base = cent[h * k + 1].copy()
+        noise = rng.standard_normal((k, cent.shape[1])).astype(np.float32) * np.float32(scale * 40.0)
+        cent[kids] = np.clip(base[None, :] + noise, 0.0, 255.0)
+        cent[h * k + 1 + 3] = cent[h * k + 1 + 2]               # and one exact duplicate (first child must win)
+    cent[:, d:] = 0
+    ft = vt.FlatTree(k, depth, d, cent, ft.exists, ft.internal)
+    leaves = cent[vt.tree.heap_size(k, depth - 1):]
+    pick = rng.integers(0, len(leaves), 40_003)
+    x = np.clip(np.rint(leaves[pick][:, :d] + rng.standard_normal((len(pick), d)) * 2.0), 0, 255).astype(np.uint8)
+    want = vo.descend(oracle_tree_from_flat(ft), x)
+    desc, _ = vt.engine.stage(x, cuda)
+    stats = torch.zeros(4, dtype=torch.int64, device=cuda)
+    word, heap = vt.engine.quantize(ft.device(cuda), k, depth, desc, want_heap=True, stats=stats, method="mma")
+    torch.cuda.synchronize()
+    assert int(stats[1].item()) == 0
+    heap = heap.cpu().numpy()
+    assert np.array_equal(heap, want), "%d of %d rows differ" % ((heap != want).sum(), len(want))
+    rechecks = int(stats[0].item())
+    assert rechecks > 0                                          # the margin was exercised
+    print("scale 2^%d: %d binary64 rechecks for %d descriptor-levels" % (int(np.log2(scale)), rechecks, len(x) * depth))
+
+
 def test_tensor_core_deferred_output_on_small_batches(cuda):
     """The last level of batches >= 2^22 rows leaves through the deferred-output path (row-range buckets).
     A child process lowers that threshold to 1 row (the library reads VT_MMA_DEFER_MIN once) and repeats
