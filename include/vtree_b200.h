@@ -88,9 +88,10 @@ int vt_quantize_sorted_profile(const void *d_desc, int dtype, int64_t n, int dp,
 
 /* Tensor-core variant of vt_quantize_sorted (tcgen05.mma kind::i8, accumulators in TMEM): after
  * sorting, the 128 descriptors of a tile meet the same <= 16 child centroids, so the distance step
- * is a dense byte contraction done exactly in integers (centroids rounded to 8.16 fixed point and
- * split into three byte planes; provable rounding margin + binary64 re-evaluation of contested
- * rows => ids bit-identical to vt_quantize).  Needs dp == 128, k <= 16 and child centroids in
+ * is a dense byte contraction done in integers (centroids rounded to 8.16 fixed point and split
+ * into three byte planes, exact int32 accumulation, scores compared in units of 2^-7; a provable
+ * margin for both roundings + binary64 re-evaluation of the contested rows => ids bit-identical
+ * to vt_quantize).  Needs dp == 128, k <= 16 and child centroids in
  * [0, 255.99] (d_stats[1] counts nodes that violate this).  vt_quantize_mma_profile is the
  * measurement variant (see vt_quantize_sorted_profile). */
 int64_t vt_quantize_mma_work_bytes(int64_t n, int k, int depth);
