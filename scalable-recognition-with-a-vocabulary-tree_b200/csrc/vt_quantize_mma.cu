@@ -35,6 +35,17 @@ constexpr int MM_TMEM_COLS = 64;                // power of two >= MM_N
 constexpr uint32_t MM_IDESC = (2u << 4) | ((uint32_t)(MM_N >> 3) << 17) | ((uint32_t)(MM_TILE >> 4) << 24);
 //                             c_format = S32; a_format = b_format = 0 (unsigned 8 bit); K-major A and B
 
+// The descent keeps KP child slots per byte plane: 16 in general, 10 when k <= 10 (the usual vocabulary tree) --
+// then the three planes fit N = 32 accumulator columns instead of 48: a third less plane traffic, 32 instead of
+// 64 TMEM columns and 16 fewer accumulator registers per thread, which is what lets 8 CTAs share an SM.
+template <int KP>
+struct PlaneCfg {
+    static constexpr int N = (3 * KP + 15) / 16 * 16;
+    static constexpr int B_BYTES = N * 128;
+    static constexpr int TMEM_COLS = N <= 32 ? 32 : 64;
+    static constexpr uint32_t IDESC = (2u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(MM_TILE >> 4) << 24);
+};
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // byte offset of (row, k) inside a 128B-swizzled K-major tile whose rows are 128 bytes
@@ -56,7 +67,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
 // is within two units of the exact gap; the contest test below subtracts three.  Fits int32: v0 < 2^23.
 constexpr int MM_S_SHIFT = 25;                  // 2^-32 units -> 2^-7 units
 
-__device__ __forceinline__ void score_children(const uint32_t (&v)[MM_N], const int *s_cn, int k, int &best, int &second,
+template <int KP, int N>
+__device__ __forceinline__ void score_children(const uint32_t (&v)[N], const int *s_cn, int k, int &best, int &second,
                                                int &arg)
 {
     int cq[16];
@@ -66,9 +78,9 @@ __device__ __forceinline__ void score_children(const uint32_t (&v)[MM_N], const 
         cq[4 * g] = t.x; cq[4 * g + 1] = t.y; cq[4 * g + 2] = t.z; cq[4 * g + 3] = t.w;
     }
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
+    for (int c = 0; c < KP; ++c) {
         if (c >= k) break;                                       // block-uniform: no predicated-off work
-        const int sc = cq[c] - (int)((v[c] << 8) + v[16 + c] + (v[32 + c] >> 8));
+        const int sc = cq[c] - (int)((v[c] << 8) + v[KP + c] + (v[2 * KP + c] >> 8));
         if (sc < best) { second = best; best = sc; arg = c; }
         else second = sc < second ? sc : second;
     }
@@ -109,6 +121,7 @@ __device__ __forceinline__ bool contested_row(bool active, int best, int second,
 }
 
 // ---- per-call preparation: byte planes + fixed-point squared norms of every node's children --------
+template <int KP>
 __global__ void __launch_bounds__(128)
 prep_planes_kernel(const float *__restrict__ cent, int64_t n_int, int k, uint8_t *__restrict__ bimg,
                    unsigned long long *__restrict__ cn, int *__restrict__ cn32, unsigned long long *__restrict__ stats)
@@ -116,7 +129,8 @@ prep_planes_kernel(const float *__restrict__ cent, int64_t n_int, int k, uint8_t
     __shared__ unsigned long long s_part[4];
     const int d = threadIdx.x;
     for (int64_t h = blockIdx.x; h < n_int; h += gridDim.x) {
-        uint8_t *img = bimg + (size_t)h * MM_B_BYTES;
+        uint8_t *img = bimg + (size_t)h * PlaneCfg<KP>::B_BYTES;
+        for (int r = 3 * KP; r < PlaneCfg<KP>::N; ++r) img[sw128_offset(r, d)] = 0;      // unused accumulator columns
         bool bad = false;
         for (int c = 0; c < 16; ++c) {
             uint32_t fx = 0;
@@ -125,9 +139,11 @@ prep_planes_kernel(const float *__restrict__ cent, int64_t n_int, int k, uint8_t
                 if (!(v >= 0.f) || v > 255.99f) bad = true;
                 fx = (uint32_t)rintf(fminf(fmaxf(v, 0.f), 255.99f) * 65536.f);
             }
-            img[sw128_offset(c, d)] = (uint8_t)(fx >> 16);
-            img[sw128_offset(16 + c, d)] = (uint8_t)(fx >> 8);
-            img[sw128_offset(32 + c, d)] = (uint8_t)fx;
+            if (c < KP) {                                        // (k <= KP: the other slots do not exist)
+                img[sw128_offset(c, d)] = (uint8_t)(fx >> 16);
+                img[sw128_offset(KP + c, d)] = (uint8_t)(fx >> 8);
+                img[sw128_offset(2 * KP + c, d)] = (uint8_t)fx;
+            }
             unsigned long long sq = (unsigned long long)fx * fx;
 #pragma unroll
             for (int o = 16; o >= 1; o >>= 1) sq += __shfl_xor_sync(VT_FULL, sq, o);
@@ -145,7 +161,7 @@ prep_planes_kernel(const float *__restrict__ cent, int64_t n_int, int k, uint8_t
 }
 
 // ---- one tree level -------------------------------------------------------------------------------
-template <int MINB>
+template <int MINB, int KP>
 __global__ void __launch_bounds__(MM_TILE, MINB)
 level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ parent,
                  int64_t n, int level, int bits, int64_t n_heap, int k, int is_last,
@@ -154,6 +170,7 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
                  uint32_t *__restrict__ keys_out, uint32_t *__restrict__ perm_out, int32_t *__restrict__ leaf_out,
                  int32_t *__restrict__ word_out, unsigned long long *__restrict__ stats)
 {
+    using Cfg = PlaneCfg<KP>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // the swizzled tiles need a 1024 B aligned base (the launch reserves 1 KB of slack for this)
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -172,7 +189,7 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
     unsigned int rechecks = 0;
 
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(MM_TMEM_COLS));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(Cfg::TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 0) {
@@ -256,9 +273,9 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
             const bool on = pending && node == mine;
             pending = pending && !on;
             // B tile of this node: 384 x 16 B, already in swizzled image form
-            const uint8_t *bsrc = bimg + (size_t)mine * MM_B_BYTES;
+            const uint8_t *bsrc = bimg + (size_t)mine * Cfg::B_BYTES;
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
+            for (int i = 0; i < Cfg::B_BYTES / 16 / MM_TILE; ++i) {
                 const int c = tid + MM_TILE * i;
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sB) + c * 16), "l"(bsrc + c * 16));
             }
@@ -276,7 +293,7 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
                     asm volatile(
                         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-                        ::"r"(tmem), "l"(a_desc + 2 * ks), "l"(b_desc + 2 * ks), "r"(MM_IDESC), "r"(acc), "r"(0u));
+                        ::"r"(tmem), "l"(a_desc + 2 * ks), "l"(b_desc + 2 * ks), "r"(Cfg::IDESC), "r"(acc), "r"(0u));
                 }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
             }
@@ -289,10 +306,10 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
                 phase ^= 1u;
             }
             asm volatile("tcgen05.fence::after_thread_sync;");
-            uint32_t v[MM_N];
+            uint32_t v[Cfg::N];
             const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll
-            for (int g = 0; g < 3; ++g) {
+            for (int g = 0; g < Cfg::N / 16; ++g) {
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                              : "=r"(v[16 * g + 0]), "=r"(v[16 * g + 1]), "=r"(v[16 * g + 2]), "=r"(v[16 * g + 3]),
                                "=r"(v[16 * g + 4]), "=r"(v[16 * g + 5]), "=r"(v[16 * g + 6]), "=r"(v[16 * g + 7]),
@@ -301,7 +318,7 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
                              : "r"(taddr + 16 * g));
             }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (on) score_children(v, s_cn, k, best, second, arg);
+            if (on) score_children<KP, Cfg::N>(v, s_cn, k, best, second, arg);
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncthreads();                                    // TMEM and the B tile may be reused
             if (only_node) break;
@@ -343,7 +360,7 @@ level_mma_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ 
     if (stats && lane == 0 && rechecks) atomicAdd(stats, (unsigned long long)rechecks);
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(MM_TMEM_COLS));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(Cfg::TMEM_COLS));
 }
 
 // deferred output of the last level: pairs bucketed by row range, so the 4-byte writes of neighbouring CTAs
@@ -577,7 +594,7 @@ kmeans_mma_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ 
                              : "r"(taddr + 16 * g));
             }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (on) score_children(v, s_cn, k, best, second, arg);
+            if (on) score_children<16, MM_N>(v, s_cn, k, best, second, arg);
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncthreads();
             if (only_node) break;
@@ -733,18 +750,24 @@ extern "C" int64_t vt_quantize_mma_work_bytes(int64_t n, int k, int depth)
 }
 
 // byte planes + fixed-point norms for the whole tree (once per call / per tree)
+static int mma_slots(int k) { return k <= 10 ? 10 : 16; }      // child slots per byte plane (PlaneCfg)
+static int64_t mma_plane_bytes(int k) { return k <= 10 ? PlaneCfg<10>::B_BYTES : PlaneCfg<16>::B_BYTES; }
+
 int vt_mma_prepare(const float *cent, int k, int depth, void *planes_and_norms, uint64_t *stats, cudaStream_t s)
 {
     const int64_t n_int = mma_int_nodes(k, depth);
     uint8_t *bimg = (uint8_t *)planes_and_norms;
-    const int64_t planes = ((n_int * MM_B_BYTES + 255) / 256) * 256;
+    const int64_t planes = ((n_int * mma_plane_bytes(k) + 255) / 256) * 256;
     unsigned long long *cn = (unsigned long long *)(bimg + planes);
     int64_t n_heap = 0, pw = 1;
     for (int l = 0; l <= depth; ++l) { n_heap += pw; pw *= k; }
     int *cn32 = (int *)(bimg + planes + ((n_heap * 8 + 255) / 256) * 256);
     const int64_t cap = (int64_t)vt_sm_count() * 16;
-    prep_planes_kernel<<<(int)(n_int < cap ? n_int : cap), 128, 0, s>>>(cent, n_int, k, bimg, cn, cn32,
-                                                                          (unsigned long long *)stats);
+    const int blocks = (int)(n_int < cap ? n_int : cap);
+    if (mma_slots(k) == 10)
+        prep_planes_kernel<10><<<blocks, 128, 0, s>>>(cent, n_int, k, bimg, cn, cn32, (unsigned long long *)stats);
+    else
+        prep_planes_kernel<16><<<blocks, 128, 0, s>>>(cent, n_int, k, bimg, cn, cn32, (unsigned long long *)stats);
     VT_LAUNCH_CHECK();
     return VT_OK;
 }
@@ -753,7 +776,7 @@ int64_t vt_mma_prepared_bytes(int k, int depth)
 {
     int64_t n_heap = 0, p = 1;
     for (int l = 0; l <= depth; ++l) { n_heap += p; p *= k; }
-    return ((mma_int_nodes(k, depth) * MM_B_BYTES + 255) / 256) * 256 + ((n_heap * 8 + 255) / 256) * 256 +
+    return ((mma_int_nodes(k, depth) * mma_plane_bytes(k) + 255) / 256) * 256 + ((n_heap * 8 + 255) / 256) * 256 +
            mma_int_nodes(k, depth) * 64;                         // planes, 64-bit norms, 32-bit norms (16 per node)
 }
 
@@ -769,24 +792,28 @@ int vt_mma_levels(const void *d_desc, int64_t n, const float *cent, const uint8_
     VT_CHECK_ARG(n_heap < ((int64_t)1 << 31), "tree too large for 32-bit node ids");
     const int64_t n_int = mma_int_nodes(k, depth);
     const uint8_t *bimg = (const uint8_t *)prepared;
-    const int64_t planes = ((n_int * MM_B_BYTES + 255) / 256) * 256;
+    const int64_t planes = ((n_int * mma_plane_bytes(k) + 255) / 256) * 256;
     const int *cn = (const int *)(bimg + planes + ((n_heap * 8 + 255) / 256) * 256);     // 32-bit norms
     uint32_t *kA = (uint32_t *)sortwork, *kB = kA + n, *pA = kB + n, *pB = pA + n;
     void *hist = (void *)(pB + n);
     const uint8_t *desc = (const uint8_t *)d_desc;
     static bool attr_set = false;
-    static int ctas = 7;                                         // resident CTAs per SM the grid is sized for
+    static int ctas10 = 8, ctas16 = 7;                           // resident CTAs per SM the grid is sized for (k <= 10 / k <= 16)
     static int64_t defer_min = (int64_t)1 << 22;                 // batches from this size on defer the last level's output
-    const int smem = MM_A_BYTES + MM_B_BYTES + 1024;
+    const bool narrow = mma_slots(k) == 10;
+    const int smem = MM_A_BYTES + (int)mma_plane_bytes(k) + 1024;
     if (!attr_set) {
         const char *e = getenv("VT_MMA_CTAS");
-        if (e && atoi(e) >= 1 && atoi(e) <= 7) ctas = atoi(e);
+        if (e && atoi(e) >= 1 && atoi(e) <= 8) { ctas10 = atoi(e); ctas16 = atoi(e) < 7 ? atoi(e) : 7; }
         e = getenv("VT_MMA_DEFER_MIN");
         if (e) defer_min = atoll(e);
-        VT_CUDA(cudaFuncSetAttribute(level_mma_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        VT_CUDA(cudaFuncSetAttribute(level_mma_kernel<7, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     MM_A_BYTES + PlaneCfg<16>::B_BYTES + 1024));
+        VT_CUDA(cudaFuncSetAttribute(level_mma_kernel<8, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     MM_A_BYTES + PlaneCfg<10>::B_BYTES + 1024));
         attr_set = true;
     }
-    const int64_t want = (n + MM_TILE - 1) / MM_TILE, cap = (int64_t)vt_sm_count() * ctas;
+    const int64_t want = (n + MM_TILE - 1) / MM_TILE, cap = (int64_t)vt_sm_count() * (narrow ? ctas10 : ctas16);
     const int blocks = (int)(want < cap ? want : cap);
     uint32_t *keys = kA, *perm = pA, *tkeys = kB, *tperm = pB;
     const uint32_t *cur_perm = nullptr, *cur_parent = nullptr;
@@ -799,9 +826,14 @@ int vt_mma_levels(const void *d_desc, int64_t n, const float *cent, const uint8_
         uint32_t *keys_out = last && !defer ? nullptr : (level == 0 ? keys : tkeys);
         uint32_t *perm_out = last && !defer ? nullptr : (level == 0 ? perm : tperm);
         if (level > 0) VT_MARK();
-        level_mma_kernel<7><<<blocks, MM_TILE, smem, s>>>(desc, cur_perm, cur_parent, n, level, bits, n_heap, k, is_last,
-                                                          cent, internal, ref_id, bimg, cn, keys_out, perm_out, leaf, word,
-                                                          (unsigned long long *)stats);
+        if (narrow)
+            level_mma_kernel<8, 10><<<blocks, MM_TILE, smem, s>>>(desc, cur_perm, cur_parent, n, level, bits, n_heap, k,
+                                                                  is_last, cent, internal, ref_id, bimg, cn, keys_out,
+                                                                  perm_out, leaf, word, (unsigned long long *)stats);
+        else
+            level_mma_kernel<7, 16><<<blocks, MM_TILE, smem, s>>>(desc, cur_perm, cur_parent, n, level, bits, n_heap, k,
+                                                                  is_last, cent, internal, ref_id, bimg, cn, keys_out,
+                                                                  perm_out, leaf, word, (unsigned long long *)stats);
         VT_LAUNCH_CHECK();
         if (last && defer) {
             // (row, child) pairs -> 256 buckets of consecutive rows -> ids written bucket by bucket
