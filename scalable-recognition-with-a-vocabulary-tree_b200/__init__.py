@@ -7,17 +7,19 @@ epignatelli/scalable-recognition-with-a-vocabulary-tree.
     db = cbir.Database(dataset, voc); db.index(); db.retrieve(path)
 
 Only the path named in BASELINE.json is here: tree build, descent, bag-of-words encoding,
-inverted-file scoring + top-k.  Feature extraction, plotting, downloads
-and the teaching helpers of the reference are out of scope.
+inverted-file scoring + top-k.  ``descriptors`` holds thin CPU front-ends (OpenCV
+ORB) so that the notebook flow runs; GPU feature extraction, plotting, downloads and the teaching
+helpers of the reference are out of scope.
 """
 from . import utils  # noqa: F401
 from . import synth  # noqa: F401
 from .dataset import Dataset, ArrayDataset  # noqa: F401
 from .tree import FlatTree  # noqa: F401
 from . import encoders  # noqa: F401
+from . import descriptors  # noqa: F401
 from .database import Database  # noqa: F401
 from . import engine  # noqa: F401
 from . import dist  # noqa: F401
 from . import _native  # noqa: F401
 
-__all__ = ["Database", "Dataset", "ArrayDataset", "FlatTree", "encoders", "utils", "engine", "synth"]
+__all__ = ["Database", "Dataset", "ArrayDataset", "FlatTree", "encoders", "descriptors", "utils", "engine", "synth"]

@@ -774,3 +774,47 @@ def test_c1_full_pipeline_matches_reference(vt, cuda):
         for b in bad:                                           # only rounding-level score ties may swap
             assert abs(ref_sc[qi][b] - sc[qi][b]) <= 1e-9 and ids[qi][b] in ref_order[qi]
     assert ids[0][0] == q_idx[0] and sc[0][0] == 0.0
+
+
+# ------------------------------------------------------------------------------------------ literal notebook
+def test_notebook_cells_78_to_91_with_real_images(vt, cuda, tmp_path):
+    """The literal notebook flow (NB[78-91]) on image FILES: Dataset(folder) -> Orb descriptor ->
+    VocabularyTree(4, 4, orb).extract_features / fit -> Database(dataset, voc).index / save / retrieve.
+    Images are synthetic textures; every image must retrieve itself first with score exactly 0, a
+    near-duplicate (same texture, small shift) must come second, and reloading the saved tree/index
+    gives the same ranking."""
+    import cv2
+    rng = np.random.default_rng(78)
+    base = []
+    for i in range(6):
+        small = rng.integers(0, 256, (24, 32, 3), dtype=np.uint8)
+        img = cv2.resize(small, (320, 240), interpolation=cv2.INTER_NEAREST)
+        img = cv2.GaussianBlur(img, (3, 3), 0)
+        base.append(img)
+        assert cv2.imwrite(str(tmp_path / ("%d00.png" % (i + 1))), img)
+        assert cv2.imwrite(str(tmp_path / ("%d01.png" % (i + 1))), np.roll(img, 3, axis=1))     # near-duplicate
+    dataset = vt.Dataset(str(tmp_path))
+    orb = vt.descriptors.Orb()
+    voc = vt.encoders.VocabularyTree(n_branches=4, depth=4, descriptor=orb)
+    features = voc.extract_features(dataset)               # every descriptor of every image, stacked (utils.py:8-27)
+    assert features.ndim == 2 and features.shape[1] == 32 and features.shape[0] > 100 * len(dataset)
+    voc.fit(features)
+    db = vt.Database(dataset, voc)
+    db.index()
+    order = {}
+    for name in dataset.image_paths:
+        res = db.retrieve(name)
+        ranked = list(res.items())
+        assert ranked[0][0] == name and ranked[0][1] == 0.0
+        twin = name[0] + ("01.png" if name.endswith("00.png") else "00.png")
+        assert ranked[1][0] == twin, (name, ranked[:3])
+        order[name] = [p for p, _ in ranked]
+    store = tmp_path / "store"
+    store.mkdir()
+    assert voc.save(str(store)) and db.save(str(store))
+    voc2 = vt.encoders.VocabularyTree(n_branches=4, depth=4, descriptor=orb)
+    assert voc2.load(str(store))
+    db2 = vt.Database(dataset, voc2)
+    assert db2.load(str(store))
+    for name in dataset.image_paths[:4]:
+        assert [p for p in db2.retrieve(name)] == order[name]
