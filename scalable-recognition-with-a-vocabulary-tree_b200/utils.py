@@ -28,3 +28,12 @@ def show_progress(func, iterable, quiet: bool = False, **kwargs):
 def get_image_id(array) -> str:
     """sha1 hex digest of the array's buffer (C-contiguous arrays, like the reference)."""
     return hashlib.sha1(np.ascontiguousarray(array)).hexdigest()
+
+
+def is_cuda_capable() -> bool:
+    """True when a CUDA device this build can run on is visible (cbir/utils.py:39-50 asks the same
+    question for its AlexNet encoder).  The kernels here are sm_100a only."""
+    import torch
+    if not torch.cuda.is_available():
+        return False
+    return all(torch.cuda.get_device_capability(d)[0] >= 10 for d in range(torch.cuda.device_count()))
