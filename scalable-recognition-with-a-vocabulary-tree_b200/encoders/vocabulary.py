@@ -248,5 +248,34 @@ class VocabularyTree(object):
                                               np.array([p_[1] for p_ in pairs], np.int32))
         return self
 
-    def draw(self, *args, **kwargs):
-        raise NotImplementedError("plotting is outside the accelerated path; use .graph with networkx")
+    def subgraph(self, image_id, draw=True):
+        """The nodes an image visited, as a networkx subgraph of the tree (vocabulary.py:139-146).
+        ``image_id`` is the sha1 key of a propagated image (``utils.get_image_id``).  Like the reference
+        the tree is drawn with those nodes highlighted -- when matplotlib is importable and ``draw``."""
+        graph = self.graph
+        sub = graph.subgraph([n_ for n_, v in graph.nodes(data=image_id, default=None) if v is not None])
+        if draw:
+            colours = ["C0"] * graph.number_of_nodes()
+            for n_ in sub.nodes:
+                colours[n_] = "C3"
+            try:
+                self.draw(node_color=colours)
+            except ImportError:
+                pass
+        return sub
+
+    def draw(self, figsize=None, node_color=None, layout="tree", labels=None):
+        """Plots the tree with networkx (vocabulary.py:162-178; plotting-only optional dependencies:
+        matplotlib, and pygraphviz for the "tree" / "radial" layouts -- without it networkx's default layout)."""
+        import matplotlib.pyplot as plt
+        import networkx as nx
+        fig = plt.figure(figsize=(30, 10) if figsize is None else figsize)
+        graph, pos = self.graph, None
+        prog = "dot" if "tree" in layout.lower() else ("twopi" if "radial" in layout.lower() else None)
+        if prog is not None:
+            try:
+                pos = nx.drawing.nx_agraph.graphviz_layout(graph, prog=prog)
+            except ImportError:
+                pos = None
+        nx.draw(graph, pos=pos, with_labels=labels is None, labels=labels, node_color=node_color)
+        return fig
