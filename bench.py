@@ -384,8 +384,8 @@ def main():
                            "algorithmic_TFLOPs": flop_per_desc * per_launch / (kern_ms * 1e-3) / 1e12},
             # DRAM bytes per launch of the dominant kernel: ncu capture of this command at 100 M rows
             # (profiles/r01_launches_final.csv: dram__bytes_read.sum + dram__bytes_write.sum of the six level launches
-            # = 13.6 / 14.4 / 14.4 / 14.4 / 14.5 / 16.0 GB, mean 145.5 B per row), scaled to this launch
-            "traffic": (145.5 * per_launch) if method == "mma" else None,
+            # = 13.6 / 14.4 / 14.4 / 14.4 / 14.5 / 15.5 GB, mean 144.6 B per row), scaled to this launch
+            "traffic": (144.6 * per_launch) if method == "mma" else None,
             "traffic_source": "ncu launch list of this command at 100 M rows, mean of the six level launches, scaled by rows (not re-measured in this run)" if method == "mma" else None,
             "level_kernel_ms_note": "entry 0 includes the per-call plane preparation of the profile variant; the last entry includes the deferred output (bucket pass + id write)",
             "other_engine": dict(fill(other_r, other_total_ms), level_kernel_ms=[round(float(v), 3) for v in other_ms]),
