@@ -1,20 +1,27 @@
 // vt_quantize_mma.cu -- tcgen05 (5th-gen tensor core) variant of the level-synchronous descent
-// (VocabularyTree.propagate_feature, cbir/encoders/vocabulary.py:104-124) for byte descriptors.
+// (VocabularyTree.propagate_feature, cbir/encoders/vocabulary.py:104-124) for byte descriptors, and of the
+// k-means assignment of the tree build (VocabularyTree.fit, vocabulary.py:62-66).
 //
-// After the batch is sorted by node, the 128 descriptors of a tile meet the SAME <=16 child
-// centroids: the distance step really is a dense contraction  X[128 x 128] . C^T[128 x 16].
-// It is done EXACTLY in integers on the INT8 tensor pipe:
+// After the batch is grouped by node, the 128 descriptors of a tile meet the SAME <= 16 child
+// centroids: the distance step really is a dense contraction  X[128 x 128] . C^T[128 x k].
+// It is done in integers on the INT8 tensor pipe:
 //   * descriptors are bytes -> the A operand is the gathered rows as they lie in HBM (cp.async
 //     into a 128B-swizzled K-major tile, no conversion);
 //   * centroids are rounded to 8.16 fixed point (|delta| <= 2^-17) and split into three byte
-//     planes -> B operand = 3 x 16 rows of bytes per node, prepared once per call;
-//   * tcgen05.mma kind::i8, M=128, N=48, K=32 x 4, int32 accumulators in TMEM (exact: 128 * 255 * 255
+//     planes -> B operand = 3 x KP rows of bytes per node (KP = 10 child slots when k <= 10, else 16),
+//     prepared once per tree;
+//   * tcgen05.mma kind::i8, M=128, N=32 or 48, K=32 x 4, int32 accumulators in TMEM (exact: 128 * 255 * 255
 //     < 2^31); tcgen05.ld brings one accumulator row to the thread that owns that descriptor;
-//   * s'_c = |c|^2 - 2 x.c is combined in int64 (units 2^-32) -> exact argmin for the ROUNDED centroids.
-// The only approximation is the centroid rounding: |s'_c(rounded) - s'_c(float32 centroid)| <=
-// 2^-16 * sqrt(D) * ||c - x|| + D * 2^-34, so rows whose runner-up is inside that provable margin
-// are re-evaluated in canonical binary64 exactly like in the SIMT kernels.  Results are therefore
-// bit-identical to vt_quantize / vt_quantize_sorted.
+//   * s_c = |c|^2 - 2 x.c is compared in 32 bits, units 2^-7 (score_children): each score is within one
+//     unit of the exact score of the ROUNDED centroid.
+// Two bounded approximations, then: the centroid rounding, |s_c(rounded) - s_c(float32 centroid)| <=
+// 2^-16 * sqrt(D) * ||c - x|| + D * 2^-34, and the 2^-7 score units.  Rows whose runner-up is inside the
+// margin that covers both (contest_test) are re-evaluated in canonical binary64 exactly like in the
+// SIMT kernels.  Results are therefore bit-identical to vt_quantize / vt_quantize_sorted and the oracle.
+//
+// The last level of large batches does not write its ids straight to the (row-indexed) output -- 4-byte
+// writes all over a 400 MB array -- but emits (row, child) pairs in tile order, buckets them by row range
+// with one radix pass and writes the ids bucket by bucket (deferred_output_kernel).
 //
 // Preconditions: dp == 128, k <= 16, every child centroid in [0, 255.99] (true for trees built from
 // byte descriptors; the prepare kernel reports violations in d_stats[1]).
@@ -28,7 +35,7 @@ int vt_sort_pass_impl(const uint32_t *kin, const uint32_t *vin, uint32_t *kout, 
 
 namespace {
 constexpr int MM_TILE = 128;                    // descriptors per tile == threads per CTA == UMMA M
-constexpr int MM_N = 48;                        // 3 byte planes x 16 child slots
+constexpr int MM_N = 48;                        // 3 byte planes x 16 child slots (k-means kernel; the descent: PlaneCfg)
 constexpr int MM_A_BYTES = MM_TILE * 128;       // 16 KB
 constexpr int MM_B_BYTES = MM_N * 128;          // 6 KB
 constexpr int MM_TMEM_COLS = 64;                // power of two >= MM_N
