@@ -10,8 +10,12 @@
 // binary64 rank key; the float tf-idf / L1 modes and the full score dump use the exhaustive
 // score_shard_kernel.  A second kernel merges the per-shard lists of a query and turns keys into the
 // reference's score (database.py:66-70: L2 distance of the L2-normalised vectors, NaN -> 1e6).
-// HBM traffic per query: 8 B x (sum of the posting lengths of its words) + 8 B per (word, shard)
-// row-pointer pair; the measured bound is the shared-memory atomic rate (one atomic per posting).
+// Algorithmic HBM traffic per query: 8 B x (sum of the posting lengths of its words) + 8 B per (word, shard)
+// row-pointer pair.  Measured (ncu, 1 M images, leaf words): 2.7x that -- a (word, shard) run is ~8 postings, so
+// 32 B sectors around 64 B runs and 8 B pointer pairs dominate -- at 3.2 TB/s, issue slots 27 % busy: the
+// kernel is bound by the two dependent DRAM round trips per word at ~1 warp instruction per posting, not by
+// the shared-memory atomics (9 % of their peak).  Long runs (all-nodes indexes) are walked by whole warps
+// and move 460 G postings/s.
 //
 // Rank key (larger is better), ties broken by smaller image index like the reference's stable
 // ascending sort (database.py:79-80):

@@ -7,7 +7,10 @@
 // pairs = 20 B per element per pass.
 //
 // Per pass:  hist (per-tile digit counts, digit-major)  ->  scan (one block per digit, exclusive
-// over tiles)  ->  scatter (per-warp stable ranking with match_any, tile = 8 warps x 512 items).
+// over tiles)  ->  scatter (per-warp stable ranking with match_any, tile = 8 warps x 512 items, written out
+// through a digit-ordered shared-memory tile so that every digit's run leaves as coalesced segments).
+// Digits of at most 5 bits -- the regrouping pass of the level-synchronous descent -- take the split_*
+// kernels below: same scheme, warps rank with one ballot per digit bit.
 #include "vt_common.cuh"
 
 namespace {
