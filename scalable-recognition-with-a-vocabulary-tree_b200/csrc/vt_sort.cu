@@ -226,7 +226,7 @@ split_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift, uint3
 }
 
 template <int NB>
-__global__ void __launch_bounds__(SORT_THREADS)
+__global__ void __launch_bounds__(SORT_THREADS, 4)
 split_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                      uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n, int shift,
                      const uint32_t *__restrict__ hist, const uint32_t *__restrict__ digit_total, int nblocks)
@@ -252,24 +252,27 @@ split_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
     }
     const int64_t tile0 = (int64_t)blockIdx.x * SORT_TILE;
     const int64_t wstart = tile0 + (int64_t)warp * SORT_WARP_ITEMS;
-    uint32_t key[SORT_ROUNDS], val[SORT_ROUNDS], lrank[SORT_ROUNDS];
-    uint32_t wc = 0;                                  // lane j: this warp's running count of class j
+    // The ranking runs twice -- once to count the warp's items per class, once (after the tile offsets are known)
+    // to place them -- instead of keeping 16 ranks per thread alive across the barrier: ballots are cheap, the
+    // registers buy a fourth resident CTA for a kernel that waits on memory most of the time.
+    uint32_t key[SORT_ROUNDS];
+    uint32_t wc = 0;                                  // lane j: this warp's count of class j
 #pragma unroll
     for (int r = 0; r < SORT_ROUNDS; ++r) {
         const int64_t idx = wstart + r * 32 + lane;
         const bool valid = idx < n;
         key[r] = valid ? keys_in[idx] : 0u;
-        val[r] = valid ? vals_in[idx] : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < SORT_ROUNDS; ++r) {
+        const int64_t idx = wstart + r * 32 + lane;
         const uint32_t d = (key[r] >> shift) & (NC - 1);
-        const uint32_t vm = __ballot_sync(VT_FULL, valid);
-        uint32_t cm = vm, pm = vm;                    // members of class `lane` / of this lane's own class
+        uint32_t cm = __ballot_sync(VT_FULL, idx < n);
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
             const uint32_t bb = __ballot_sync(VT_FULL, (d >> b) & 1u);
             cm &= ((lane >> b) & 1) ? bb : ~bb;
-            pm &= ((d >> b) & 1u) ? bb : ~bb;
         }
-        lrank[r] = __shfl_sync(VT_FULL, wc, (int)d) + __popc(pm & lt);
         wc += __popc(cm);
     }
     if (lane < NC) wcnt[warp][lane] = wc;
@@ -293,16 +296,30 @@ split_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
         if (lane < NC) tstart[lane] = incl - run;
         if (lane == NC - 1) tstart[NC] = incl;
     }
-    __syncthreads();
+    uint32_t val[SORT_ROUNDS];
 #pragma unroll
     for (int r = 0; r < SORT_ROUNDS; ++r) {
         const int64_t idx = wstart + r * 32 + lane;
-        if (idx < n) {
-            const uint32_t d = (key[r] >> shift) & (NC - 1);
-            const uint32_t pos = tstart[d] + wcnt[warp][d] + lrank[r];
-            s_key[pos] = key[r];
-            s_val[pos] = val[r];
+        val[r] = idx < n ? vals_in[idx] : 0u;
+    }
+    __syncthreads();
+    wc = lane < NC ? tstart[lane] + wcnt[warp][lane] : 0u;      // lane j: tile position of this warp's next item of class j
+#pragma unroll
+    for (int r = 0; r < SORT_ROUNDS; ++r) {
+        const int64_t idx = wstart + r * 32 + lane;
+        const bool valid = idx < n;
+        const uint32_t d = (key[r] >> shift) & (NC - 1);
+        const uint32_t vm = __ballot_sync(VT_FULL, valid);
+        uint32_t cm = vm, pm = vm;                    // members of class `lane` / of this lane's own class
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const uint32_t bb = __ballot_sync(VT_FULL, (d >> b) & 1u);
+            cm &= ((lane >> b) & 1) ? bb : ~bb;
+            pm &= ((d >> b) & 1u) ? bb : ~bb;
         }
+        const uint32_t pos = __shfl_sync(VT_FULL, wc, (int)d) + __popc(pm & lt);
+        if (valid) { s_key[pos] = key[r]; s_val[pos] = val[r]; }
+        wc += __popc(cm);
     }
     __syncthreads();
     const uint32_t n_tile = tstart[NC];
