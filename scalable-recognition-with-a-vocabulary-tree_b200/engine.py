@@ -321,10 +321,8 @@ def build_tree(desc: torch.Tensor, d: int, k: int, depth: int, n_iter: int = 10,
         perm = svals[:n_next].contiguous()
         parent = skeys[:n_next].contiguous()
 
-    if dev.type == "cuda":       # the 4 * n_heap * DP bytes of centres stay on the device; host copy on demand
-        tree = FlatTree(k, depth, d, cent, exists.cpu().numpy(), internal.cpu().numpy(), count_heap.cpu().numpy(),
-                        byte_built=True)
-        tree.adopt_device(dev, cent, internal)
+    if dev.type == "cuda":       # everything stays on the device: numbering computed there, host mirrors on demand
+        tree = FlatTree.from_device(k, depth, d, cent, exists, internal, count_heap, byte_built=True)
     else:
         tree = FlatTree(k, depth, d, cent.numpy(), exists.numpy(), internal.numpy(), count_heap.numpy(), byte_built=True)
     return tree

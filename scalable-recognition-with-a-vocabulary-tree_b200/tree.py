@@ -37,26 +37,70 @@ def reference_ids(exists: np.ndarray, internal: np.ndarray, k: int, depth: int):
     """DFS pre-order numbering of the existing nodes (vocabulary.py:70-75), vectorised per level.
 
     id(child c of n) = id(n) + 1 + sum of the subtree sizes of the children before c.
-    Returns (ref_id [n_heap] int32 with -1 for unused slots, n_ref)."""
+    Returns (ref_id [n_heap] int32 with -1 for unused slots, n_ref).  32-bit arithmetic in place (ids are
+    int32 across the ABI): this runs on the host at the end of every build."""
     n_heap = exists.shape[0]
-    size = exists.astype(np.int64).copy()                     # subtree sizes, bottom-up
+    size = exists.astype(np.int32)                            # subtree sizes, bottom-up
+    inter = internal != 0
     for level in range(depth - 1, -1, -1):
         o, n_l = level_offset(k, level), k ** level
         co = level_offset(k, level + 1)
-        child = size[co: co + n_l * k].reshape(n_l, k)
-        size[o: o + n_l] += np.where(internal[o: o + n_l] != 0, child.sum(axis=1), 0)
-    ref = np.full(n_heap, -1, np.int64)
+        kids = size[co: co + n_l * k].reshape(n_l, k).sum(axis=1, dtype=np.int32)
+        np.add(size[o: o + n_l], kids, out=size[o: o + n_l], where=inter[o: o + n_l])
+    ref = np.full(n_heap, -1, np.int32)
     if n_heap and exists[0]:
         ref[0] = 0
     for level in range(depth):
         o, n_l = level_offset(k, level), k ** level
         co = level_offset(k, level + 1)
         child = size[co: co + n_l * k].reshape(n_l, k)
-        before = np.cumsum(child, axis=1) - child             # exclusive prefix over siblings
-        cid = ref[o: o + n_l, None] + 1 + before
-        ok = (internal[o: o + n_l, None] != 0) & (exists[co: co + n_l * k].reshape(n_l, k) != 0)
-        ref[co: co + n_l * k] = np.where(ok, cid, -1).reshape(-1)
-    return ref.astype(np.int32), int(size[0]) if n_heap else 0
+        cid = np.cumsum(child, axis=1, dtype=np.int32)
+        cid -= child                                          # exclusive prefix over siblings
+        cid += (ref[o: o + n_l] + 1)[:, None]
+        ok = inter[o: o + n_l, None] & (exists[co: co + n_l * k].reshape(n_l, k) != 0)
+        cid[~ok] = -1
+        ref[co: co + n_l * k] = cid.reshape(-1)
+    return ref, int(size[0]) if n_heap else 0
+
+
+def reference_tables_torch(exists, internal, k: int, depth: int):
+    """``reference_ids`` + the per-id tables (heap slot, parent id, level) with torch ops, on whatever device the
+    inputs live -- the build keeps them on the GPU, so the numbering of a 1.1 M-node tree costs microseconds there
+    instead of tens of milliseconds of numpy on the host.  Same arithmetic as the numpy versions (tested equal)."""
+    import torch
+    dev = exists.device
+    n_heap = exists.shape[0]
+    size = exists.to(torch.int32).clone()
+    inter = internal != 0
+    exb = exists != 0
+    zero = torch.zeros((), dtype=torch.int32, device=dev)
+    for level in range(depth - 1, -1, -1):
+        o, n_l, co = level_offset(k, level), k ** level, level_offset(k, level + 1)
+        kids = size[co: co + n_l * k].view(n_l, k).sum(1, dtype=torch.int32)
+        size[o: o + n_l] += torch.where(inter[o: o + n_l], kids, zero)
+    ref = torch.full((n_heap,), -1, dtype=torch.int32, device=dev)
+    ref[0] = torch.where(exb[0], 0, -1).to(torch.int32)
+    parent_heap = torch.full((n_heap,), -1, dtype=torch.int32, device=dev)
+    level_heap = torch.zeros(n_heap, dtype=torch.uint8, device=dev)
+    minus1 = torch.full((), -1, dtype=torch.int32, device=dev)
+    for level in range(depth):
+        o, n_l, co = level_offset(k, level), k ** level, level_offset(k, level + 1)
+        child = size[co: co + n_l * k].view(n_l, k)
+        cid = torch.cumsum(child, 1, dtype=torch.int32) - child + (ref[o: o + n_l] + 1)[:, None]
+        ok = inter[o: o + n_l, None] & exb[co: co + n_l * k].view(n_l, k)
+        ref[co: co + n_l * k] = torch.where(ok, cid, minus1).reshape(-1)
+        parent_heap[co: co + n_l * k] = ref[o: o + n_l].repeat_interleave(k)
+        level_heap[co: co + n_l * k] = level + 1
+    n_ref = int(size[0].item()) if n_heap else 0
+    ex = torch.nonzero(exb).flatten()
+    ids = ref[ex].long()
+    heap_of_ref = torch.full((n_ref,), -1, dtype=torch.int64, device=dev)
+    heap_of_ref[ids] = ex
+    parent_ref = torch.empty(n_ref, dtype=torch.int32, device=dev)
+    parent_ref[ids] = parent_heap[ex]
+    level_ref = torch.empty(n_ref, dtype=torch.uint8, device=dev)
+    level_ref[ids] = level_heap[ex]
+    return ref, n_ref, heap_of_ref, parent_ref, level_ref
 
 
 class FlatTree:
@@ -81,19 +125,61 @@ class FlatTree:
         self.internal = np.ascontiguousarray(internal, np.uint8)
         self.count = None if count is None else np.ascontiguousarray(count, np.int64)
         self.ref_id, self.n_ref = reference_ids(self.exists, self.internal, self.k, self.depth)
-        ex = np.nonzero(self.exists)[0]
+        # per reference id: heap slot, parent id and depth (the bag-of-words encoder lifts counts with them).
+        # Built level by level in heap space -- the parent of every child of a level is the parent's id repeated
+        # k times -- and scattered through ref_id once.
+        parent_heap = np.full(self.n_heap, -1, np.int32)
+        level_heap = np.zeros(self.n_heap, np.uint8)
+        for level in range(self.depth):
+            o, n_l = level_offset(self.k, level), self.k ** level
+            co = level_offset(self.k, level + 1)
+            parent_heap[co: co + n_l * self.k] = np.repeat(self.ref_id[o: o + n_l], self.k)
+            level_heap[co: co + n_l * self.k] = level + 1
+        ex = np.flatnonzero(self.exists)
+        ids = self.ref_id[ex]
         self.heap_of_ref = np.full(self.n_ref, -1, np.int64)
-        self.heap_of_ref[self.ref_id[ex]] = ex
-        # per reference id: parent id and depth (used by the bag-of-words encoder)
-        heap = self.heap_of_ref
-        parent_heap = np.maximum(heap - 1, 0) // self.k
-        self.parent_ref = np.where(heap > 0, self.ref_id[parent_heap], -1).astype(np.int32)
-        lvl = np.zeros(self.n_heap, np.uint8)
-        for level in range(1, self.depth + 1):
-            o = level_offset(self.k, level)
-            lvl[o: o + self.k ** level] = level
-        self.level_ref = lvl[heap].astype(np.uint8)
+        self.heap_of_ref[ids] = ex
+        self.parent_ref = np.empty(self.n_ref, np.int32)
+        self.parent_ref[ids] = parent_heap[ex]
+        self.level_ref = np.empty(self.n_ref, np.uint8)
+        self.level_ref[ids] = level_heap[ex]
         self._dev = {}
+
+    # host arrays that a device-built tree materialises on first use (FlatTree.from_device)
+    _LAZY = ("exists", "internal", "count", "ref_id", "heap_of_ref", "parent_ref", "level_ref")
+
+    def __getattr__(self, name):                      # only reached when the attribute is not set yet
+        lazy = self.__dict__.get("_lazy")
+        if lazy is not None and name in lazy:
+            value = lazy[name].detach().cpu().numpy()
+            self.__dict__[name] = value
+            return value
+        raise AttributeError(name)
+
+    @classmethod
+    def from_device(cls, k: int, depth: int, d: int, centroids, exists, internal, count=None,
+                    byte_built: bool = False) -> "FlatTree":
+        """Tree whose arrays are torch tensors on one device (the end of ``engine.build_tree``): the reference
+        numbering and the per-id tables are computed there, the device dict is ready at once, and the numpy
+        mirrors (``exists``, ``ref_id``, ``heap_of_ref`` ...) are copied to the host only when first read."""
+        self = cls.__new__(cls)
+        self.k, self.depth, self.D = int(k), int(depth), int(d)
+        self.DP = int(centroids.shape[1])
+        self.n_heap = heap_size(k, depth)
+        assert centroids.shape[0] == self.n_heap
+        self._byte_built = bool(byte_built)
+        self._centroids, self._centroids_dev = None, centroids
+        ref, n_ref, heap_of_ref, parent_ref, level_ref = reference_tables_torch(exists, internal, self.k, self.depth)
+        self.n_ref = n_ref
+        self._lazy = dict(exists=exists, internal=internal, ref_id=ref, heap_of_ref=heap_of_ref,
+                          parent_ref=parent_ref, level_ref=level_ref)
+        if count is None:
+            self.count = None
+        else:
+            self._lazy["count"] = count
+        self._dev = {str(centroids.device): dict(mma_ok=self.mma_ok(), centroids=centroids, internal=internal,
+                                                 ref_id=ref, parent_ref=parent_ref, level_ref=level_ref)}
+        return self
 
     @property
     def centroids(self) -> np.ndarray:
@@ -107,6 +193,8 @@ class FlatTree:
         parent_ref, level_ref."""
         import torch
         device = torch.device(device if device is not None else "cuda")
+        if device.type == "cuda" and device.index is None:     # "cuda" and "cuda:<current>" are the same cache entry
+            device = torch.device("cuda", torch.cuda.current_device())
         key = str(device)
         if key not in self._dev:
             self._dev[key] = dict(
@@ -122,7 +210,10 @@ class FlatTree:
     def adopt_device(self, device, centroids, internal):
         """Reuse tensors the build already holds on the device instead of re-uploading."""
         import torch
-        key = str(torch.device(device))
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        key = str(device)
         self._dev[key] = dict(
             mma_ok=self.mma_ok(),
             centroids=centroids, internal=internal,
