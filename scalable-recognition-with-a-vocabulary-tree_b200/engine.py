@@ -413,14 +413,19 @@ def build_index(csr: dict, n_ref: int, weight: torch.Tensor = None) -> dict:
     keys = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
     entry = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
     entry_img = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
-    nat.check(lib.vt_posting_keys(nat.ptr(csr["row_off"]), nat.ptr(csr["node"]), n_img, shard, n_ref, nat.ptr(keys),
-                                  nat.ptr(entry), nat.ptr(entry_img), s), "vt_posting_keys")
-    skeys, sentry = sort_pairs(keys[:nnz], entry[:nnz], int(n_keys).bit_length())
-    post_off = torch.empty(n_keys + 1, dtype=torch.int32, device=dev)
+    skeys, sentry = keys[:0], entry[:0]
+    if nnz > 0:
+        nat.check(lib.vt_posting_keys(nat.ptr(csr["row_off"]), nat.ptr(csr["node"]), n_img, shard, n_ref, nat.ptr(keys),
+                                      nat.ptr(entry), nat.ptr(entry_img), s), "vt_posting_keys")
+        skeys, sentry = sort_pairs(keys[:nnz], entry[:nnz], int(n_keys).bit_length())
     postings = torch.empty((max(nnz, 1), 2), dtype=torch.int32, device=dev)
-    nat.check(lib.vt_posting_fill(nat.ptr(skeys), nat.ptr(sentry), nnz, nat.ptr(entry_img), nat.ptr(csr["count"]),
-                                  nat.ptr(weight), shard, n_keys, nat.ptr(post_off), nat.ptr(postings), s),
-              "vt_posting_fill")
+    if nnz == 0:                 # no image has a descriptor (or there is no image): every posting list is empty
+        post_off = torch.zeros(n_keys + 1, dtype=torch.int32, device=dev)
+    else:
+        post_off = torch.empty(n_keys + 1, dtype=torch.int32, device=dev)
+        nat.check(lib.vt_posting_fill(nat.ptr(skeys), nat.ptr(sentry), nnz, nat.ptr(entry_img), nat.ptr(csr["count"]),
+                                      nat.ptr(weight), shard, n_keys, nat.ptr(post_off), nat.ptr(postings), s),
+                  "vt_posting_fill")
     rnorm = torch.empty(max(n_img, 1), dtype=torch.float64, device=dev)
     nat.check(lib.vt_rnorm(nat.ptr(csr["sumsq"]), n_img, nat.ptr(rnorm), s), "vt_rnorm")
     shard_empty = torch.zeros(n_shards, dtype=torch.uint8, device=dev)

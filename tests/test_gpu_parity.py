@@ -579,6 +579,22 @@ def test_dense_encoder_protocol(vt, cuda, name):
         vt.Database(42, Plugin())
 
 
+def test_database_of_images_without_descriptors(vt, cuda):
+    """Every image empty: the reference's embeddings are NaN, every score is the 1e6 sentinel (database.py:70) and
+    the stable sort leaves the images in dataset order -- the inverted file is empty but must still work."""
+    ft, g, meta, images = _flat_from_golden(vt, "adversarial")
+    d = images[0].shape[1]
+    empties = [np.zeros((0, d), np.uint8) for _ in range(5)]
+    ds = vt.ArrayDataset(empties)
+    voc = vt.encoders.VocabularyTree(ft.k, ft.depth, descriptor=lambda im: im).set_tree(ft)
+    db = vt.Database(ds, voc)
+    db.index()
+    res = db.retrieve(ds.image_paths[2])
+    assert list(res.keys()) == ds.image_paths and all(v == 1e6 for v in res.values())
+    ids, sc = db.retrieve_batch(ds.image_paths[:2], k=3)
+    assert np.array_equal(ids, [[0, 1, 2], [0, 1, 2]]) and np.all(sc == 1e6)
+
+
 # ------------------------------------------------------------------------------------------ full size
 def test_full_size_quantize_properties(vt, cuda):
     """BASELINE configs[2] shape at a size the oracle cannot check row by row (20 M x 128 through a
