@@ -211,6 +211,16 @@ int vt_posting_fill(const uint32_t *d_sorted_keys, const uint32_t *d_sorted_entr
                     const int32_t *d_entry_img, const int32_t *d_count, const float *d_weight,
                     int32_t shard_size, int64_t n_keys, uint32_t *d_post_off, void *d_postings,
                     void *stream);
+/* tf-mode variant without the gather: vt_posting_pack writes the key and, as the value to sort with it,
+ * the posting itself -- (count << log2(shard_size)) | local image id (shard_size a power of two; counts
+ * fit: an image has at most vt_encode_max_words() descriptors); vt_posting_unpack turns the sorted pairs
+ * into d_postings / d_post_off (nnz > 0).  Same result as vt_posting_keys + vt_posting_fill with counts. */
+int vt_posting_pack(const int64_t *d_row_off, const int32_t *d_node, const int32_t *d_count,
+                    int64_t n_img, int32_t shard_size, int64_t n_ref, uint32_t *d_keys,
+                    uint32_t *d_packed, void *stream);
+int vt_posting_unpack(const uint32_t *d_sorted_keys, const uint32_t *d_sorted_packed, int64_t nnz,
+                      int32_t shard_size, int64_t n_keys, uint32_t *d_post_off, void *d_postings,
+                      void *stream);
 
 /* ---- scoring + top-k: Database.score / Database.retrieve, database.py:59-81 -----------------
  * Queries are a CSR batch (d_q_off [n_query+1], d_q_node, d_q_val = tf as float or weight).

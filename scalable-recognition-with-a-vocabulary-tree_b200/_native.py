@@ -50,6 +50,8 @@ SIGNATURES = {
     "vt_encode_max_words": (_int, []),
     "vt_posting_keys": (_int, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp]),
     "vt_posting_fill": (_int, [_vp, _vp, _i64, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp]),
+    "vt_posting_pack": (_int, [_vp, _vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp]),
+    "vt_posting_unpack": (_int, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp]),
     "vt_score_shard_size": (_int, []),
     "vt_score_max_topk": (_int, []),
     "vt_rnorm": (_int, [_vp, _i64, _vp, _vp]),

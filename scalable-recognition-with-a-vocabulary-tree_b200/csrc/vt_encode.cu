@@ -209,6 +209,40 @@ __global__ void posting_fill_kernel(const uint32_t *__restrict__ skeys, const ui
     }
 }
 
+// tf postings without a gather: the sort value carries the posting itself, (count << shard_bits) | local image
+__global__ void posting_pack_kernel(const int64_t *__restrict__ row_off, const int32_t *__restrict__ node,
+                                    const int32_t *__restrict__ count, int64_t n_img, int shard_bits, int64_t n_ref,
+                                    uint32_t *__restrict__ keys, uint32_t *__restrict__ packed)
+{
+    const uint32_t shard_size = 1u << shard_bits;
+    const uint32_t n_shards = (uint32_t)((n_img + shard_size - 1) >> shard_bits);
+    for (int64_t img = blockIdx.x; img < n_img; img += gridDim.x) {
+        const int64_t b = row_off[img], e = row_off[img + 1];
+        const uint32_t shard = (uint32_t)(img >> shard_bits), local = (uint32_t)img & (shard_size - 1u);
+        for (int64_t t = b + threadIdx.x; t < e; t += blockDim.x) {
+            keys[t] = (uint32_t)node[t] * n_shards + shard;
+            packed[t] = ((uint32_t)count[t] << shard_bits) | local;
+        }
+    }
+}
+
+__global__ void posting_unpack_kernel(const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ spacked, int64_t nnz,
+                                      int shard_bits, int64_t n_keys, uint32_t *__restrict__ post_off,
+                                      uint2 *__restrict__ postings)
+{
+    const uint32_t lmask = (1u << shard_bits) - 1u;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t key = skeys[p];
+        const uint32_t v = spacked[p];
+        postings[p] = make_uint2(v & lmask, v >> shard_bits);
+        // row pointers: every key in (previous key, key] starts at p
+        const int64_t prev = p == 0 ? -1 : (int64_t)skeys[p - 1];
+        for (int64_t kk = prev + 1; kk <= (int64_t)key; ++kk) post_off[kk] = (uint32_t)p;
+        if (p == nnz - 1)
+            for (int64_t kk = (int64_t)key + 1; kk <= n_keys; ++kk) post_off[kk] = (uint32_t)nnz;
+    }
+}
+
 __global__ void fill_u32_kernel(uint32_t *a, int64_t n, uint32_t v)
 {
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) a[t] = v;
@@ -286,6 +320,43 @@ extern "C" int vt_posting_fill(const uint32_t *d_sorted_keys, const uint32_t *d_
     posting_fill_kernel<<<(int)(want < cap ? want : cap), 256, 0, s>>>(d_sorted_keys, d_sorted_entry, nnz, d_entry_img,
                                                                        d_count, d_weight, shard_size, n_keys, d_post_off,
                                                                        (uint2 *)d_postings);
+    VT_LAUNCH_CHECK();
+    return VT_OK;
+}
+
+// tf-mode variant of vt_posting_keys / vt_posting_fill: the value sorted along with the key IS the posting,
+// (count << log2(shard_size)) | local image id, so building the inverted file needs no gather through entry
+// indices (the two random 4-byte reads per posting of vt_posting_fill).  shard_size must be a power of two and
+// counts must fit the remaining bits (vt_encode_max_words() = 8192 descriptors per image do).
+extern "C" int vt_posting_pack(const int64_t *d_row_off, const int32_t *d_node, const int32_t *d_count, int64_t n_img,
+                               int32_t shard_size, int64_t n_ref, uint32_t *d_keys, uint32_t *d_packed, void *stream)
+{
+    VT_CHECK_ARG(n_img >= 0 && shard_size > 0 && (shard_size & (shard_size - 1)) == 0 && n_ref > 0, "bad sizes");
+    int shard_bits = 0;
+    while ((1 << shard_bits) < shard_size) ++shard_bits;
+    VT_CHECK_ARG(ENC_MAX < (1 << (32 - shard_bits)), "counts do not fit beside the local image id");
+    const int64_t n_shards = (n_img + shard_size - 1) / shard_size;
+    VT_CHECK_ARG(n_shards * n_ref < ((int64_t)1 << 32), "shards * nodes must fit 32 bits");
+    if (n_img == 0) return VT_OK;
+    VT_CHECK_ARG(d_row_off && d_node && d_count && d_keys && d_packed, "null buffer");
+    const int64_t cap = (int64_t)vt_sm_count() * 16;
+    posting_pack_kernel<<<(int)(n_img < cap ? n_img : cap), 128, 0, (cudaStream_t)stream>>>(
+        d_row_off, d_node, d_count, n_img, shard_bits, n_ref, d_keys, d_packed);
+    VT_LAUNCH_CHECK();
+    return VT_OK;
+}
+
+extern "C" int vt_posting_unpack(const uint32_t *d_sorted_keys, const uint32_t *d_sorted_packed, int64_t nnz,
+                                 int32_t shard_size, int64_t n_keys, uint32_t *d_post_off, void *d_postings, void *stream)
+{
+    VT_CHECK_ARG(nnz > 0 && nnz < ((int64_t)1 << 32) && n_keys >= 0, "bad sizes");
+    VT_CHECK_ARG(shard_size > 0 && (shard_size & (shard_size - 1)) == 0, "shard_size must be a power of two");
+    VT_CHECK_ARG(d_sorted_keys && d_sorted_packed && d_post_off && d_postings, "null buffer");
+    int shard_bits = 0;
+    while ((1 << shard_bits) < shard_size) ++shard_bits;
+    const int64_t cap = (int64_t)vt_sm_count() * 16, want = (nnz + 255) / 256;
+    posting_unpack_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
+        d_sorted_keys, d_sorted_packed, nnz, shard_bits, n_keys, d_post_off, (uint2 *)d_postings);
     VT_LAUNCH_CHECK();
     return VT_OK;
 }

@@ -412,17 +412,24 @@ def build_index(csr: dict, n_ref: int, weight: torch.Tensor = None) -> dict:
     n_keys = n_shards * n_ref
     keys = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
     entry = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
-    entry_img = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
-    skeys, sentry = keys[:0], entry[:0]
-    if nnz > 0:
-        nat.check(lib.vt_posting_keys(nat.ptr(csr["row_off"]), nat.ptr(csr["node"]), n_img, shard, n_ref, nat.ptr(keys),
-                                      nat.ptr(entry), nat.ptr(entry_img), s), "vt_posting_keys")
-        skeys, sentry = sort_pairs(keys[:nnz], entry[:nnz], int(n_keys).bit_length())
     postings = torch.empty((max(nnz, 1), 2), dtype=torch.int32, device=dev)
+    n_bits = int(n_keys).bit_length()
     if nnz == 0:                 # no image has a descriptor (or there is no image): every posting list is empty
         post_off = torch.zeros(n_keys + 1, dtype=torch.int32, device=dev)
+    elif weight is None:
+        # tf postings: the value sorted with the key is the posting itself (count | local image), no gather
+        post_off = torch.empty(n_keys + 1, dtype=torch.int32, device=dev)
+        nat.check(lib.vt_posting_pack(nat.ptr(csr["row_off"]), nat.ptr(csr["node"]), nat.ptr(csr["count"]), n_img, shard,
+                                      n_ref, nat.ptr(keys), nat.ptr(entry), s), "vt_posting_pack")
+        skeys, spacked = sort_pairs(keys[:nnz], entry[:nnz], n_bits)
+        nat.check(lib.vt_posting_unpack(nat.ptr(skeys), nat.ptr(spacked), nnz, shard, n_keys, nat.ptr(post_off),
+                                        nat.ptr(postings), s), "vt_posting_unpack")
     else:
         post_off = torch.empty(n_keys + 1, dtype=torch.int32, device=dev)
+        entry_img = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+        nat.check(lib.vt_posting_keys(nat.ptr(csr["row_off"]), nat.ptr(csr["node"]), n_img, shard, n_ref, nat.ptr(keys),
+                                      nat.ptr(entry), nat.ptr(entry_img), s), "vt_posting_keys")
+        skeys, sentry = sort_pairs(keys[:nnz], entry[:nnz], n_bits)
         nat.check(lib.vt_posting_fill(nat.ptr(skeys), nat.ptr(sentry), nnz, nat.ptr(entry_img), nat.ptr(csr["count"]),
                                       nat.ptr(weight), shard, n_keys, nat.ptr(post_off), nat.ptr(postings), s),
                   "vt_posting_fill")
