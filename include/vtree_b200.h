@@ -196,6 +196,12 @@ int vt_encode(const int32_t *d_word, const int64_t *d_img_off, int64_t n_img, in
               int32_t *d_nnz, const int64_t *d_row_off, int32_t *d_out_node, int32_t *d_out_count,
               uint64_t *d_sumsq, uint32_t *d_df, void *stream);
 int vt_encode_max_words(void);
+/* Single-pass alternative for all_nodes == 0 (an image then has at most as many entries as descriptors):
+ * call vt_encode once with d_row_off = d_img_off AND d_nnz set (the fill pass reports the row lengths too),
+ * prefix-sum d_nnz into the packed d_row_off and let vt_csr_compact move the rows there. */
+int vt_csr_compact(const int64_t *d_in_off, const int32_t *d_nnz, const int64_t *d_row_off,
+                   int64_t n_img, const int32_t *d_node_in, const int32_t *d_count_in,
+                   int32_t *d_node_out, int32_t *d_count_out, void *stream);
 
 /* ---- inverted file: the dict-per-node postings of vocabulary.py:96-100 as CSR, sharded by image
  * range (vt_score_shard_size() images per shard).  Row key = node * n_shards + img / shard_size, so a

@@ -48,6 +48,7 @@ SIGNATURES = {
     "vt_sort_pairs": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, C.POINTER(_int), _vp]),
     "vt_encode": (_int, [_vp, _vp, _i64, _i32, _int, _vp, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vt_encode_max_words": (_int, []),
+    "vt_csr_compact": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "vt_posting_keys": (_int, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp]),
     "vt_posting_fill": (_int, [_vp, _vp, _i64, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp]),
     "vt_posting_pack": (_int, [_vp, _vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp]),

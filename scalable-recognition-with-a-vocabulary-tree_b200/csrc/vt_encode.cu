@@ -86,7 +86,7 @@ encode_kernel(const int32_t *__restrict__ word, const int64_t *__restrict__ img_
         uint32_t emitted = 0;
         if (threadIdx.x == 0) s_sq = 0ull;
         if (n == 0) {
-            if (threadIdx.x == 0) { if (!fill) nnz_out[img] = 0; else if (sumsq) sumsq[img] = 0ull; }
+            if (threadIdx.x == 0) { if (nnz_out) nnz_out[img] = 0; if (fill && sumsq) sumsq[img] = 0ull; }
             __syncthreads();
             continue;
         }
@@ -165,8 +165,8 @@ encode_kernel(const int32_t *__restrict__ word, const int64_t *__restrict__ img_
         atomicAdd(&s_sq, sq);
         __syncthreads();
         if (threadIdx.x == 0) {
-            if (!fill) nnz_out[img] = (int32_t)emitted;
-            else if (sumsq) sumsq[img] = s_sq;
+            if (nnz_out) nnz_out[img] = (int32_t)emitted;
+            if (fill && sumsq) sumsq[img] = s_sq;
         }
         __syncthreads();
     }
@@ -240,6 +240,24 @@ __global__ void posting_unpack_kernel(const uint32_t *__restrict__ skeys, const 
         for (int64_t kk = prev + 1; kk <= (int64_t)key; ++kk) post_off[kk] = (uint32_t)p;
         if (p == nnz - 1)
             for (int64_t kk = (int64_t)key + 1; kk <= n_keys; ++kk) post_off[kk] = (uint32_t)nnz;
+    }
+}
+
+// rows written at loose offsets (in_off, lengths nnz) -> packed CSR (row_off)
+__global__ void csr_compact_kernel(const int64_t *__restrict__ in_off, const int32_t *__restrict__ nnz,
+                                   const int64_t *__restrict__ row_off, int64_t n_img, const int32_t *__restrict__ node_in,
+                                   const int32_t *__restrict__ count_in, int32_t *__restrict__ node_out,
+                                   int32_t *__restrict__ count_out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t img = warp; img < n_img; img += n_warps) {
+        const int64_t src = in_off[img], dst = row_off[img];
+        const int len = nnz[img];
+        for (int t = lane; t < len; t += 32) {
+            node_out[dst + t] = node_in[src + t];
+            count_out[dst + t] = count_in[src + t];
+        }
     }
 }
 
@@ -357,6 +375,23 @@ extern "C" int vt_posting_unpack(const uint32_t *d_sorted_keys, const uint32_t *
     const int64_t cap = (int64_t)vt_sm_count() * 16, want = (nnz + 255) / 256;
     posting_unpack_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
         d_sorted_keys, d_sorted_packed, nnz, shard_bits, n_keys, d_post_off, (uint2 *)d_postings);
+    VT_LAUNCH_CHECK();
+    return VT_OK;
+}
+
+
+// Single-pass encoding: vt_encode may be called ONCE with d_row_off = d_img_off (an image never has more entries
+// than descriptors when only stop nodes are counted) and d_nnz set; this packs the loosely placed rows.
+extern "C" int vt_csr_compact(const int64_t *d_in_off, const int32_t *d_nnz, const int64_t *d_row_off, int64_t n_img,
+                              const int32_t *d_node_in, const int32_t *d_count_in, int32_t *d_node_out,
+                              int32_t *d_count_out, void *stream)
+{
+    VT_CHECK_ARG(n_img >= 0, "bad sizes");
+    if (n_img == 0) return VT_OK;
+    VT_CHECK_ARG(d_in_off && d_nnz && d_row_off && d_node_in && d_count_in && d_node_out && d_count_out, "null buffer");
+    const int64_t cap = (int64_t)vt_sm_count() * 8, want = (n_img * 32 + 255) / 256;
+    csr_compact_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
+        d_in_off, d_nnz, d_row_off, n_img, d_node_in, d_count_in, d_node_out, d_count_out);
     VT_LAUNCH_CHECK();
     return VT_OK;
 }

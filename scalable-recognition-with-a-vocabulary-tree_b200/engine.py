@@ -329,6 +329,9 @@ def build_tree(desc: torch.Tensor, d: int, k: int, depth: int, n_iter: int = 10,
 
 
 # --------------------------------------------------------------------------------------- encode
+_SINGLE_PASS_WORDS = 1 << 31        # the single-pass encoder stages 8 B per descriptor
+
+
 def encode(words: torch.Tensor, img_off: torch.Tensor, tree_dev: dict, depth: int, n_ref: int,
            all_nodes: bool = True, want_df: bool = False, min_level: int = 0) -> dict:
     """Bag-of-words CSR of a batch of images.  ``words`` int32 [n_desc] (reference ids of the
@@ -348,16 +351,32 @@ def encode(words: torch.Tensor, img_off: torch.Tensor, tree_dev: dict, depth: in
         raise ValueError("min_level must lie in [0, depth]")
     args = (nat.ptr(words), nat.ptr(img_off), n_img, max_words, 1 + int(min_level) if all_nodes else 0,
             nat.ptr(tree_dev["parent_ref"]), nat.ptr(tree_dev["level_ref"]), depth)
-    nat.check(lib.vt_encode(*args, nat.ptr(nnz), None, None, None, None, None, s), "vt_encode(count)")
-    row_off = torch.zeros(n_img + 1, dtype=torch.int64, device=dev)
-    row_off[1:] = torch.cumsum(nnz[:n_img].to(torch.int64), 0)
-    total = int(row_off[-1].item())
-    node = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
-    count = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
     sumsq = torch.zeros(max(n_img, 1), dtype=torch.int64, device=dev)
     df = torch.zeros(n_ref, dtype=torch.int32, device=dev) if want_df else None
-    nat.check(lib.vt_encode(*args, None, nat.ptr(row_off), nat.ptr(node), nat.ptr(count), nat.ptr(sumsq),
-                            nat.ptr(df), s), "vt_encode(fill)")
+    row_off = torch.zeros(n_img + 1, dtype=torch.int64, device=dev)
+    n_words = int(words.numel())
+    if not all_nodes and 0 < n_words <= _SINGLE_PASS_WORDS:
+        # stop nodes only: an image has at most as many entries as descriptors, so ONE pass writes its row at the
+        # image's word offset (and reports the row length); a copy kernel then packs the rows
+        node_tmp = torch.empty(n_words, dtype=torch.int32, device=dev)
+        count_tmp = torch.empty(n_words, dtype=torch.int32, device=dev)
+        nat.check(lib.vt_encode(*args, nat.ptr(nnz), nat.ptr(img_off), nat.ptr(node_tmp), nat.ptr(count_tmp),
+                                nat.ptr(sumsq), nat.ptr(df), s), "vt_encode(single pass)")
+        row_off[1:] = torch.cumsum(nnz[:n_img].to(torch.int64), 0)
+        total = int(row_off[-1].item())
+        node = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        count = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        nat.check(lib.vt_csr_compact(nat.ptr(img_off), nat.ptr(nnz), nat.ptr(row_off), n_img, nat.ptr(node_tmp),
+                                     nat.ptr(count_tmp), nat.ptr(node), nat.ptr(count), s), "vt_csr_compact")
+        del node_tmp, count_tmp
+    else:
+        nat.check(lib.vt_encode(*args, nat.ptr(nnz), None, None, None, None, None, s), "vt_encode(count)")
+        row_off[1:] = torch.cumsum(nnz[:n_img].to(torch.int64), 0)
+        total = int(row_off[-1].item())
+        node = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        count = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        nat.check(lib.vt_encode(*args, None, nat.ptr(row_off), nat.ptr(node), nat.ptr(count), nat.ptr(sumsq),
+                                nat.ptr(df), s), "vt_encode(fill)")
     return dict(row_off=row_off, node=node[:total], count=count[:total], sumsq=sumsq[:n_img], df=df,
                 n_img=n_img, nnz=total)
 
