@@ -409,6 +409,7 @@ constexpr uint32_t MM_IDESC_SUM = (2u << 4) | (1u << 15) /* A is MN-major */ | (
                                   ((uint32_t)(MM_TILE >> 4) << 24);
 constexpr int MM_H_BYTES = 16 * 128;           // one-hot tile: 16 clusters x 128 rows
 
+template <int KP>
 __global__ void __launch_bounds__(128)
 prep_level_planes_kernel(const float *__restrict__ child_cent, int64_t n_nodes, int k, uint8_t *__restrict__ bimg,
                          int *__restrict__ cn32, unsigned long long *__restrict__ stats)
@@ -416,7 +417,8 @@ prep_level_planes_kernel(const float *__restrict__ child_cent, int64_t n_nodes, 
     __shared__ unsigned long long s_part[4];
     const int d = threadIdx.x;
     for (int64_t h = blockIdx.x; h < n_nodes; h += gridDim.x) {
-        uint8_t *img = bimg + (size_t)h * MM_B_BYTES;
+        uint8_t *img = bimg + (size_t)h * PlaneCfg<KP>::B_BYTES;
+        for (int r = 3 * KP; r < PlaneCfg<KP>::N; ++r) img[sw128_offset(r, d)] = 0;      // unused accumulator columns
         bool bad = false;
         for (int c = 0; c < 16; ++c) {
             uint32_t fx = 0;
@@ -425,9 +427,11 @@ prep_level_planes_kernel(const float *__restrict__ child_cent, int64_t n_nodes, 
                 if (!(v >= 0.f) || v > 255.99f) bad = true;
                 fx = (uint32_t)rintf(fminf(fmaxf(v, 0.f), 255.99f) * 65536.f);
             }
-            img[sw128_offset(c, d)] = (uint8_t)(fx >> 16);
-            img[sw128_offset(16 + c, d)] = (uint8_t)(fx >> 8);
-            img[sw128_offset(32 + c, d)] = (uint8_t)fx;
+            if (c < KP) {                                        // (k <= KP: the other slots do not exist)
+                img[sw128_offset(c, d)] = (uint8_t)(fx >> 16);
+                img[sw128_offset(KP + c, d)] = (uint8_t)(fx >> 8);
+                img[sw128_offset(2 * KP + c, d)] = (uint8_t)fx;
+            }
             unsigned long long sq = (unsigned long long)fx * fx;
 #pragma unroll
             for (int o = 16; o >= 1; o >>= 1) sq += __shfl_xor_sync(VT_FULL, sq, o);
@@ -441,6 +445,7 @@ prep_level_planes_kernel(const float *__restrict__ child_cent, int64_t n_nodes, 
     }
 }
 
+template <int KP>
 __global__ void __launch_bounds__(MM_TILE, 6)
 kmeans_mma_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ perm, const int32_t *__restrict__ parent,
                   int64_t n, const uint8_t *__restrict__ node_internal, int k, const float *__restrict__ child_cent,
@@ -452,8 +457,9 @@ kmeans_mma_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *sA = smem;
-    uint8_t *sB = smem + MM_A_BYTES;                 // 6 KB centroid planes
-    uint8_t *sH = smem + MM_A_BYTES + 6 * 1024;      // 2 KB one-hot labels (1024 B aligned)
+    using Cfg = PlaneCfg<KP>;
+    uint8_t *sB = smem + MM_A_BYTES;                 // 4 or 6 KB centroid planes
+    uint8_t *sH = smem + MM_A_BYTES + Cfg::B_BYTES;  // 2 KB one-hot labels (1024 B aligned)
     __shared__ __align__(8) unsigned long long mbar;
     __shared__ uint32_t s_tmem;
     __shared__ uint32_t s_row[MM_TILE];
@@ -564,9 +570,9 @@ kmeans_mma_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ 
             if (pass == 0 && only_node) tile_node = mine;
             const bool on = pending && node == mine;
             pending = pending && !on;
-            const uint8_t *bsrc = bimg + (size_t)mine * MM_B_BYTES;
+            const uint8_t *bsrc = bimg + (size_t)mine * Cfg::B_BYTES;
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
+            for (int i = 0; i < Cfg::B_BYTES / 16 / MM_TILE; ++i) {
                 const int c = tid + MM_TILE * i;
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sB) + c * 16), "l"(bsrc + c * 16));
             }
@@ -584,15 +590,15 @@ kmeans_mma_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ 
                     asm volatile(
                         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-                        ::"r"(tmem), "l"(a_desc + 2 * ks), "l"(b_desc + 2 * ks), "r"(MM_IDESC), "r"(acc), "r"(0u));
+                        ::"r"(tmem), "l"(a_desc + 2 * ks), "l"(b_desc + 2 * ks), "r"(Cfg::IDESC), "r"(acc), "r"(0u));
                 }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
             }
             wait_mma();
-            uint32_t v[MM_N];
+            uint32_t v[Cfg::N];
             const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll
-            for (int g = 0; g < 3; ++g) {
+            for (int g = 0; g < Cfg::N / 16; ++g) {
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                              : "=r"(v[16 * g + 0]), "=r"(v[16 * g + 1]), "=r"(v[16 * g + 2]), "=r"(v[16 * g + 3]),
                                "=r"(v[16 * g + 4]), "=r"(v[16 * g + 5]), "=r"(v[16 * g + 6]), "=r"(v[16 * g + 7]),
@@ -601,7 +607,7 @@ kmeans_mma_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ 
                              : "r"(taddr + 16 * g));
             }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (on) score_children<16, MM_N>(v, s_cn, k, best, second, arg);
+            if (on) score_children<KP, Cfg::N>(v, s_cn, k, best, second, arg);
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncthreads();
             if (only_node) break;
@@ -654,13 +660,13 @@ kmeans_mma_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ 
                     asm volatile(
                         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-                        ::"r"(tmem + 48u), "l"(a_desc + 256 * ks), "l"(h_desc + 2 * ks), "r"(MM_IDESC_SUM), "r"(acc), "r"(0u));
+                        ::"r"(tmem + (uint32_t)Cfg::N), "l"(a_desc + 256 * ks), "l"(h_desc + 2 * ks), "r"(MM_IDESC_SUM), "r"(acc), "r"(0u));
                 }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
             }
             wait_mma();
             uint32_t sv[16];
-            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + 48u;
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)Cfg::N;
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                          : "=r"(sv[0]), "=r"(sv[1]), "=r"(sv[2]), "=r"(sv[3]), "=r"(sv[4]), "=r"(sv[5]), "=r"(sv[6]), "=r"(sv[7]),
                            "=r"(sv[8]), "=r"(sv[9]), "=r"(sv[10]), "=r"(sv[11]), "=r"(sv[12]), "=r"(sv[13]), "=r"(sv[14]), "=r"(sv[15])
@@ -693,8 +699,8 @@ kmeans_mma_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ 
 // centroid byte planes + fixed-point norms of one LEVEL (node j -> image j, child rows j*k + c)
 extern "C" int64_t vt_kmeans_planes_bytes(int64_t n_nodes, int k)
 {
-    (void)k;
-    return ((n_nodes * MM_B_BYTES + 255) / 256) * 256 + n_nodes * 64;      // byte planes + 16 32-bit norms per node
+    const int64_t plane = k <= 10 ? PlaneCfg<10>::B_BYTES : PlaneCfg<16>::B_BYTES;
+    return ((n_nodes * plane + 255) / 256) * 256 + n_nodes * 64;           // byte planes + 16 32-bit norms per node
 }
 
 extern "C" int vt_kmeans_planes(const float *d_child_centroids, int64_t n_nodes, int k, int dp, void *d_planes,
@@ -702,10 +708,16 @@ extern "C" int vt_kmeans_planes(const float *d_child_centroids, int64_t n_nodes,
 {
     VT_CHECK_ARG(dp == 128 && k >= 1 && k <= 16 && n_nodes >= 1, "tensor-core k-means needs dp == 128 and k <= 16");
     uint8_t *bimg = (uint8_t *)d_planes;
-    int *cn = (int *)(bimg + ((n_nodes * MM_B_BYTES + 255) / 256) * 256);
+    const int64_t plane = k <= 10 ? PlaneCfg<10>::B_BYTES : PlaneCfg<16>::B_BYTES;
+    int *cn = (int *)(bimg + ((n_nodes * plane + 255) / 256) * 256);
     const int64_t cap = (int64_t)vt_sm_count() * 16;
-    prep_level_planes_kernel<<<(int)(n_nodes < cap ? n_nodes : cap), 128, 0, (cudaStream_t)stream>>>(
-        d_child_centroids, n_nodes, k, bimg, cn, (unsigned long long *)d_stats);
+    const int blocks = (int)(n_nodes < cap ? n_nodes : cap);
+    if (k <= 10)
+        prep_level_planes_kernel<10><<<blocks, 128, 0, (cudaStream_t)stream>>>(d_child_centroids, n_nodes, k, bimg, cn,
+                                                                               (unsigned long long *)d_stats);
+    else
+        prep_level_planes_kernel<16><<<blocks, 128, 0, (cudaStream_t)stream>>>(d_child_centroids, n_nodes, k, bimg, cn,
+                                                                               (unsigned long long *)d_stats);
     VT_LAUNCH_CHECK();
     return VT_OK;
 }
@@ -722,18 +734,29 @@ extern "C" int vt_kmeans_assign_mma(const void *d_desc, int dtype, int dp, const
     VT_CHECK_ARG(n_members >= 0 && n_nodes >= 1 && d_planes, "bad arguments");
     if (n_members == 0) return VT_OK;
     const uint8_t *bimg = (const uint8_t *)d_planes;
-    const int *cn = (const int *)(bimg + ((n_nodes * MM_B_BYTES + 255) / 256) * 256);
+    const int64_t plane = k <= 10 ? PlaneCfg<10>::B_BYTES : PlaneCfg<16>::B_BYTES;
+    const int *cn = (const int *)(bimg + ((n_nodes * plane + 255) / 256) * 256);
     static bool attr_set = false;
-    const int smem = MM_A_BYTES + 6 * 1024 + MM_H_BYTES + 1024;
+    const int smem = MM_A_BYTES + (int)plane + MM_H_BYTES + 1024;
     if (!attr_set) {
-        VT_CUDA(cudaFuncSetAttribute(kmeans_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        VT_CUDA(cudaFuncSetAttribute(kmeans_mma_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     MM_A_BYTES + PlaneCfg<10>::B_BYTES + MM_H_BYTES + 1024));
+        VT_CUDA(cudaFuncSetAttribute(kmeans_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     MM_A_BYTES + PlaneCfg<16>::B_BYTES + MM_H_BYTES + 1024));
         attr_set = true;
     }
     const int64_t want = (n_members + MM_TILE - 1) / MM_TILE, cap = (int64_t)vt_sm_count() * 6;
-    kmeans_mma_kernel<<<(int)(want < cap ? want : cap), MM_TILE, smem, (cudaStream_t)stream>>>(
-        (const uint8_t *)d_desc, d_perm, d_parent, n_members, d_node_internal, k, d_child_centroids, bimg, cn, d_label,
-        (unsigned long long *)d_sums, (unsigned long long *)d_counts, (unsigned long long *)d_changed,
-        (unsigned long long *)d_stats);
+    const int blocks = (int)(want < cap ? want : cap);
+    if (k <= 10)
+        kmeans_mma_kernel<10><<<blocks, MM_TILE, smem, (cudaStream_t)stream>>>(
+            (const uint8_t *)d_desc, d_perm, d_parent, n_members, d_node_internal, k, d_child_centroids, bimg, cn, d_label,
+            (unsigned long long *)d_sums, (unsigned long long *)d_counts, (unsigned long long *)d_changed,
+            (unsigned long long *)d_stats);
+    else
+        kmeans_mma_kernel<16><<<blocks, MM_TILE, smem, (cudaStream_t)stream>>>(
+            (const uint8_t *)d_desc, d_perm, d_parent, n_members, d_node_internal, k, d_child_centroids, bimg, cn, d_label,
+            (unsigned long long *)d_sums, (unsigned long long *)d_counts, (unsigned long long *)d_changed,
+            (unsigned long long *)d_stats);
     VT_LAUNCH_CHECK();
     return VT_OK;
 }
