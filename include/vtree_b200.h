@@ -260,6 +260,31 @@ int vt_topk_merge(const double *d_in_key, const int32_t *d_in_id, int64_t n_quer
                   const uint64_t *d_img_sumsq, double *d_out_key, int32_t *d_out_id,
                   double *d_out_score, void *stream);
 
+/* vt_topk_merge for candidates that already carry their final score (d_in_score [n_query, n_cand]): the merge
+ * of the all-gathered per-rank top-k lists of a database sharded by image id (section 8e row 4). */
+int vt_topk_merge_scored(const double *d_in_key, const int32_t *d_in_id, const double *d_in_score,
+                         int64_t n_query, int n_cand, int topk, double *d_out_key, int32_t *d_out_id,
+                         double *d_out_score, void *stream);
+
+/* ---- TF-IDF weighting + L1/L2 normalisation (what vocabulary.py:131,137 leaves commented out; opt-in) ----
+ * Everything in binary64; the inverted file stays the exact integer tf index, the weights enter on the query
+ * side (csrc/vt_weight.cu).  vt_idf: idf_n = ln(N / df_n), 0 where df_n == 0.  vt_weighted_rnorm: per CSR row
+ * 1 / |idf * tf|_2 (norm_l1 == 0) or 1 / |idf * tf|_1, -1 for all-zero rows (0/0 -> NaN -> score 1e6).
+ * vt_query_weights: the per-entry query factors of the keys (d_qv, d_qi [nnz_q]).  vt_score_topk_weighted: same
+ * outputs as vt_score_topk, mode VT_SCORE_W_L2 (key = cosine, score = sqrt(2 - 2 key)) or VT_SCORE_W_L1
+ * (key = sum over common words of q + d - |q - d|, score = 2 - key); merge with vt_topk_merge in the same mode. */
+int vt_idf(const int32_t *d_df, int64_t n_ref, int64_t n_total, double *d_idf, void *stream);
+int vt_weighted_rnorm(const int64_t *d_row_off, const int32_t *d_node, const int32_t *d_count, int64_t n_img,
+                      const double *d_idf, int norm_l1, double *d_rnorm, void *stream);
+int vt_query_weights(const int64_t *d_row_off, const int32_t *d_node, const int32_t *d_count, int64_t n_query,
+                     const double *d_idf, const double *d_q_rnorm, int norm_l1, double *d_qv, double *d_qi,
+                     void *stream);
+int vt_score_topk_weighted(const uint32_t *d_post_off, const void *d_postings, const double *d_img_rnorm,
+                           int64_t n_img, int64_t n_ref, const int64_t *d_q_off, const int32_t *d_q_node,
+                           const double *d_qv, const double *d_qi, const double *d_q_rnorm, int64_t n_query,
+                           int mode, int topk, double *d_shard_key, int32_t *d_shard_id, double *d_all_key,
+                           void *stream);
+
 /* ---- measurement helper (bench.py): best-of-reps FP32 FFMA throughput of the current device in
  * TFLOP/s; d_scratch holds at least sm_count*8*256 floats. */
 int vt_measure_fp32_peak(float *d_scratch, int iters, int reps, double *tflops, double *ms_best,

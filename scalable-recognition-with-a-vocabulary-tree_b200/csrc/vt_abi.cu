@@ -18,16 +18,17 @@ extern "C" const char *vt_last_error(void) { return g_err; }
 
 int vt_sm_count()
 {
-    static int cached = 0;
-    if (!cached) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            cached = n;
+    // per device: a process may drive several GPUs (VocabularyTree(device="cuda:1") while device 0 is current)
+    static int cached[64] = {0};
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!cached[dev]) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            cached[dev] = n;
         else
             return 148;
     }
-    return cached;
+    return cached[dev];
 }
 
 extern "C" int vt_device_info(int *sm_count, int *cc_major, int *cc_minor)

@@ -468,6 +468,47 @@ topk_merge_kernel(const double *__restrict__ in_key, const int32_t *__restrict__
     }
 }
 
+// merge candidate lists that already carry their final score (the per-rank top-k lists of a sharded
+// database, all-gathered): same comparator, the winner's score is copied instead of recomputed
+__global__ void __launch_bounds__(SC_THREADS)
+topk_merge_scored_kernel(const double *__restrict__ in_key, const int32_t *__restrict__ in_id,
+                         const double *__restrict__ in_score, int64_t n_query, int n_cand, int topk,
+                         double *__restrict__ out_key, int32_t *__restrict__ out_id, double *__restrict__ out_score)
+{
+    extern __shared__ unsigned char s_raw[];
+    double *s_keys = reinterpret_cast<double *>(s_raw);                      // [n_cand]
+    int32_t *s_ids = reinterpret_cast<int32_t *>(s_raw + (size_t)n_cand * 8);
+    __shared__ double r_key[SC_WARPS];
+    __shared__ int32_t r_id[SC_WARPS];
+    __shared__ int r_owner[SC_WARPS];
+    for (int64_t q = blockIdx.x; q < n_query; q += gridDim.x) {
+        for (int t = threadIdx.x; t < n_cand; t += SC_THREADS) {
+            const int32_t id = in_id[q * n_cand + t];
+            s_ids[t] = id;
+            s_keys[t] = id >= 0 ? in_key[q * n_cand + t] : -2.0;
+        }
+        __syncthreads();
+        for (int r = 0; r < topk; ++r) {
+            double bkey = -2.0; int32_t bid = 0x7fffffff; int bslot = -1;
+            for (int t = threadIdx.x; t < n_cand; t += SC_THREADS) {
+                const double k2 = s_keys[t];
+                const int32_t i2 = k2 > -2.0 ? s_ids[t] : 0x7fffffff;
+                if (better(k2, i2, bkey, bid)) { bkey = k2; bid = i2; bslot = t; }
+            }
+            double key = bkey; int32_t id = bid; int owner;
+            block_best(key, id, owner, r_key, r_id, r_owner);
+            const bool ok = key > -2.0;
+            if (threadIdx.x == owner) {
+                if (ok) s_keys[bslot] = -2.0;
+                out_key[q * topk + r] = key;
+                out_id[q * topk + r] = ok ? id : -1;
+                out_score[q * topk + r] = ok ? in_score[q * n_cand + bslot] : 1e6;
+            }
+            __syncthreads();
+        }
+    }
+}
+
 __global__ void rnorm_kernel(const unsigned long long *__restrict__ sumsq, int64_t n, double *__restrict__ rnorm)
 {
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
@@ -589,4 +630,23 @@ extern "C" int vt_topk_merge(const double *d_in_key, const int32_t *d_in_id, int
 #undef VT_M
     vt_set_error("vt_topk_merge: unknown mode %d", mode);
     return VT_EINVAL;
+}
+
+// vt_topk_merge for candidates that carry their score (d_in_score [n_query, n_cand]): the multi-GPU merge of
+// the all-gathered per-rank lists (ids global, -1 = empty slot).
+extern "C" int vt_topk_merge_scored(const double *d_in_key, const int32_t *d_in_id, const double *d_in_score,
+                                    int64_t n_query, int n_cand, int topk, double *d_out_key, int32_t *d_out_id,
+                                    double *d_out_score, void *stream)
+{
+    VT_CHECK_ARG(n_query >= 0 && n_cand >= 1 && topk >= 1 && topk <= SC_MAXK, "bad sizes");
+    VT_CHECK_ARG((size_t)n_cand * 12 <= 200 * 1024, "too many candidates per query for one merge");
+    VT_CHECK_ARG(d_in_key && d_in_id && d_in_score && d_out_key && d_out_id && d_out_score, "null buffer");
+    if (n_query == 0) return VT_OK;
+    const size_t smem = (size_t)n_cand * 12;
+    VT_CUDA(cudaFuncSetAttribute(topk_merge_scored_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t cap = (int64_t)vt_sm_count() * 8;
+    topk_merge_scored_kernel<<<(int)(n_query < cap ? n_query : cap), SC_THREADS, smem, (cudaStream_t)stream>>>(
+        d_in_key, d_in_id, d_in_score, n_query, n_cand, topk, d_out_key, d_out_id, d_out_score);
+    VT_LAUNCH_CHECK();
+    return VT_OK;
 }

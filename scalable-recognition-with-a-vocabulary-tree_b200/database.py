@@ -47,7 +47,7 @@ class Database(object):
         self._host = None         # host copy of the forward CSR (row_off, node, count)
         self._csr = None          # device forward CSR of the indexed images
         self._index = None        # device inverted file
-        self._idf = None
+        self._weights = None      # tf-idf modes: dict(idf, img_rnorm, norm), binary64 device tensors
         self._extra = {}          # path -> (nodes, counts) of non-indexed images (queries)
         # dense path (encoders without encode_batch)
         self._dense = not hasattr(encoder, "encode_batch")
@@ -80,18 +80,22 @@ class Database(object):
             parts.append(self.encoder.encode_batch(feats, want_df=True))
         csr = engine.concat_csr(parts)
         n_ref = self.encoder.flat.n_ref
-        weight = None
-        if self.weighting == "tfidf":
-            n = max(len(paths), 1)
-            df = csr["df"].to(torch.float64)
-            self._idf = torch.where(df > 0, torch.log(n / df.clamp(min=1)), torch.zeros_like(df)).to(torch.float32)
-            weight = engine.tfidf_weights(csr, self._idf, self.norm)
         self._csr = csr
-        self._index = engine.build_index(csr, n_ref, weight)
+        self._index = engine.build_index(csr, n_ref)
+        self._set_weights(csr["df"], len(paths))
         self._rows = {p: i for i, p in enumerate(paths)}
         self._host = (csr["row_off"].cpu().numpy(), csr["node"].cpu().numpy(), csr["count"].cpu().numpy())
         self._extra = {}
         return
+
+    def _set_weights(self, df, n_images):
+        """tf-idf modes: idf_n = ln(N / df_n) and the per-image weighted norms, binary64, on the device.  The
+        inverted file itself stays the integer tf index (csrc/vt_weight.cu)."""
+        self._weights = None
+        if self.weighting != "tfidf":
+            return
+        idf = engine.idf_from_df(df, max(int(n_images), 1))
+        self._weights = dict(idf=idf, norm=self.norm, img_rnorm=engine.weighted_rnorm(self._csr, idf, self.norm))
 
     def is_indexed(self, image_path):
         return image_path in self._rows
@@ -205,10 +209,7 @@ class Database(object):
         q = dict(row_off=off.to(dev), node=torch.from_numpy(node.astype(np.int32)).to(dev),
                  count=torch.from_numpy(count.astype(np.int32)).to(dev), sumsq=sumsq.to(dev),
                  n_img=len(rows), nnz=int(off[-1]))
-        q_val = None
-        if self.weighting == "tfidf":
-            q_val = engine.tfidf_weights(q, self._idf, self.norm)
-        return q, q_val
+        return q
 
     def retrieve_batch(self, query_paths, k=10, return_all=False):
         """Top-k image indices (positions in ``dataset.image_paths``) and scores per query.
@@ -217,8 +218,8 @@ class Database(object):
             return self._retrieve_batch_dense(query_paths, k, return_all)
         if self._index is None:
             self.index()
-        q, q_val = self._query_csr(list(query_paths))
-        out = engine.score(self._index, q, k, self._mode(), q_val=q_val, want_all=return_all)
+        q = self._query_csr(list(query_paths))
+        out = engine.score(self._index, q, k, self._mode(), want_all=return_all, weights=self._weights)
         ids, sc = out["id"].cpu().numpy(), out["score"].cpu().numpy()
         if return_all:
             return ids, sc, out["all_key"].cpu().numpy()
@@ -254,8 +255,8 @@ class Database(object):
             return {paths[i]: float(scores[i]) for i in order}
         if self._index is None:
             self.index()
-        q, q_val = self._query_csr([query_image_path])
-        out = engine.score(self._index, q, 1, self._mode(), q_val=q_val, want_all=True)
+        q = self._query_csr([query_image_path])
+        out = engine.score(self._index, q, 1, self._mode(), want_all=True, weights=self._weights)
         keys = out["all_key"][0].cpu().numpy()
         scores = self._scores_from_keys(keys, int(q["sumsq"][0].item()))
         order = np.argsort(scores, kind="stable")
@@ -292,19 +293,17 @@ class Database(object):
         dev = torch.device(self.encoder.device)
         n_img = len(ro) - 1
         n_ref = self.encoder.flat.n_ref
-        sumsq = np.add.reduceat(count.astype(np.int64) ** 2, ro[:-1]) if len(count) else np.zeros(n_img, np.int64)
-        sumsq = np.where(ro[1:] > ro[:-1], sumsq, 0)
+        # per-image sum of squares from an exact int64 prefix sum (np.add.reduceat raises when trailing images
+        # have no descriptors: its last index then equals len(count))
+        prefix = np.concatenate([np.zeros(1, np.int64), np.cumsum(count.astype(np.int64) ** 2)])
+        sumsq = prefix[ro[1:]] - prefix[ro[:-1]]
         csr = dict(row_off=torch.from_numpy(ro).to(dev), node=torch.from_numpy(node).to(dev),
                    count=torch.from_numpy(count).to(dev), sumsq=torch.from_numpy(sumsq).to(dev),
                    n_img=n_img, nnz=len(node), df=None)
         self._rows, self._host, self._csr = rows, host, csr
-        weight = None
+        self._index = engine.build_index(csr, n_ref)
         if self.weighting == "tfidf":
-            df = torch.bincount(csr["node"].long(), minlength=n_ref).to(torch.float64)
-            self._idf = torch.where(df > 0, torch.log(max(n_img, 1) / df.clamp(min=1)),
-                                    torch.zeros_like(df)).to(torch.float32)
-            weight = engine.tfidf_weights(csr, self._idf, self.norm)
-        self._index = engine.build_index(csr, n_ref, weight)
+            self._set_weights(torch.bincount(csr["node"].long(), minlength=n_ref).to(torch.int32), n_img)
         self._extra = {}
 
     def save(self, path=None, reference_format=False, key=None):

@@ -1,9 +1,15 @@
 """Multi-GPU layer: one process per GPU, ``torch.distributed`` (NCCL over NVLink/NVSwitch) for
 the two real exchange steps of the path:
 
-* build     -- descriptors sharded contiguously; per level-iteration ONE all-reduce of the
-               [rows, D] integer sums + counts (+ changed counter) the assign kernel wrote.
-               Integer sums make the tree independent of the number of GPUs, bit for bit.
+* build     -- descriptors sharded contiguously.  Top levels: per level-iteration ONE all-reduce of the
+               [rows, D] integer sums + counts (+ changed counter) the assign kernel wrote.  From the
+               first level with >= 4 nodes per rank on: ONE all-to-all hands every rank the members of
+               the subtrees it owns (``engine.build_tree``), the levels below need no collective, and one
+               all-reduce with a single contributor per row publishes the finished subtrees.  Integer
+               sums and order-preserving exchange make the tree independent of the number of GPUs, bit
+               for bit.
+* index     -- images sharded by id; tf-idf only: ONE all-reduce of the per-node document
+               frequencies (``Database.index``).
 * quantise  -- descriptors sharded, tree replicated: no data-path collective.
 * retrieve  -- inverted file sharded by image id; per-shard top-k, then ONE all-gather of the
                [Q, k] (rank key, global id, score) triples and a merge with the reference's
@@ -39,6 +45,16 @@ class Comm:
     def all_gather(self, t: torch.Tensor) -> torch.Tensor:
         return self.all_gather_counts(t)
 
+    def all_reduce_max(self, t: torch.Tensor) -> torch.Tensor:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return t
+
+    def all_to_all_rows(self, out: torch.Tensor, inp: torch.Tensor, out_rows, in_rows) -> torch.Tensor:
+        """Row exchange: ``inp`` [sum(in_rows), ...] is cut into per-destination row blocks, ``out`` receives the
+        blocks of every source in rank order."""
+        dist.all_to_all_single(out, inp, [int(x) for x in out_rows], [int(x) for x in in_rows], group=self.group)
+        return out
+
     def barrier(self):
         dist.barrier(group=self.group)
 
@@ -53,27 +69,33 @@ def shard_range(n: int, rank: int, world: int):
 def merge_ranked(keys: torch.Tensor, ids: torch.Tensor, scores: torch.Tensor, topk: int):
     """Merge per-rank top-k lists.  keys/ids/scores: [world, Q, k] (ids global, -1 = empty slot).
     Order: key descending, ties by ascending image index -- the reference's stable ascending sort
-    on scores (database.py:79-80).  Returns ([Q, topk] ids, scores, keys)."""
+    on scores (database.py:79-80).  Returns ([Q, topk] ids, scores, keys).  One launch of
+    ``vt_topk_merge_scored`` (the comparator of the single-GPU merge); no CPU path."""
+    from . import _native as nat
+    lib = nat.load()
+    if not keys.is_cuda:
+        raise nat.NativeError("merge_ranked runs on the device (vt_topk_merge_scored); got CPU tensors")
     w, q, k = keys.shape
-    keys = keys.permute(1, 0, 2).reshape(q, w * k)
-    ids = ids.permute(1, 0, 2).reshape(q, w * k)
-    scores = scores.permute(1, 0, 2).reshape(q, w * k)
-    big = torch.iinfo(torch.int32).max
-    ids_key = torch.where(ids >= 0, ids, torch.full_like(ids, big))
-    keys = torch.where(ids >= 0, keys, torch.full_like(keys, float("-inf")))
-    o1 = torch.sort(ids_key, dim=1, stable=True).indices                    # secondary: image index
-    k1 = torch.gather(keys, 1, o1)
-    o2 = torch.sort(k1, dim=1, descending=True, stable=True).indices        # primary: key
-    order = torch.gather(o1, 1, o2)[:, :topk]
-    return torch.gather(ids, 1, order), torch.gather(scores, 1, order), torch.gather(keys, 1, order)
+    topk = int(topk)
+    with torch.cuda.device(keys.device):
+        ck = keys.permute(1, 0, 2).reshape(q, w * k).contiguous()
+        ci = ids.permute(1, 0, 2).reshape(q, w * k).to(torch.int32).contiguous()
+        cs = scores.permute(1, 0, 2).reshape(q, w * k).contiguous()
+        ok = torch.empty((max(q, 1), topk), dtype=torch.float64, device=keys.device)
+        oi = torch.empty((max(q, 1), topk), dtype=torch.int32, device=keys.device)
+        osc = torch.empty((max(q, 1), topk), dtype=torch.float64, device=keys.device)
+        nat.check(lib.vt_topk_merge_scored(nat.ptr(ck), nat.ptr(ci), nat.ptr(cs), q, w * k, topk, nat.ptr(ok), nat.ptr(oi),
+                                           nat.ptr(osc), nat.stream_ptr()), "vt_topk_merge_scored")
+    return oi[:q], osc[:q], ok[:q]
 
 
-def retrieve_sharded(score_local, img_base: int, topk: int, comm: Comm):
+def retrieve_sharded(score_local, img_base: int, topk: int, comm: Comm, merge=None):
     """``score_local()`` -> dict(key, id, score) [Q, topk] over this rank's image shard (ids local).
-    All-gathers the lists and merges them; every rank returns the same global result."""
+    ONE all-gather of the packed (key, global id, score) triples, then the merge; every rank returns
+    the same global result.  ``merge`` replaces ``merge_ranked`` (CPU protocol tests pass a test double)."""
     out = score_local()
     ids = torch.where(out["id"] >= 0, out["id"] + int(img_base), out["id"])
-    keys = comm.all_gather(out["key"].contiguous())
-    gids = comm.all_gather(ids.contiguous())
-    scores = comm.all_gather(out["score"].contiguous())
-    return merge_ranked(keys, gids, scores, topk)
+    packed = torch.stack([out["key"].to(torch.float64), ids.to(torch.float64), out["score"].to(torch.float64)])
+    allp = comm.all_gather(packed.contiguous())                  # [world, 3, Q, topk]; ids < 2^31 are exact in binary64
+    keys, gids, scores = allp[:, 0], allp[:, 1].to(torch.int32), allp[:, 2]
+    return (merge or merge_ranked)(keys, gids, scores, topk)

@@ -15,6 +15,7 @@ Reference functions covered (cbir/encoders/vocabulary.py, cbir/database.py):
 from __future__ import annotations
 
 import ctypes as C
+import functools
 
 import numpy as np
 import torch
@@ -27,6 +28,39 @@ VT_U8, VT_F32 = nat.VT_U8, nat.VT_F32
 
 def _lib():
     return nat.load()
+
+
+def _cuda_device_of(obj):
+    """device of the first CUDA tensor found in ``obj`` (tensor, dict / list / tuple of tensors), else None."""
+    if isinstance(obj, torch.Tensor):
+        return obj.device if obj.is_cuda else None
+    if isinstance(obj, dict):
+        obj = obj.values()
+    if isinstance(obj, (list, tuple)) or type(obj).__name__ == "dict_values":
+        for v in obj:
+            if isinstance(v, (torch.Tensor, dict)):
+                d = _cuda_device_of(v)
+                if d is not None:
+                    return d
+    return None
+
+
+def _device_scoped(fn):
+    """Run ``fn`` with the device of its tensor arguments current: the C ABI launches on the CURRENT device and
+    ``nat.stream_ptr()`` is that device's current stream, so tensors on cuda:1 must not be driven from device 0
+    (that would be an illegal address on the wrong context)."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        dev = None
+        for a in list(args) + list(kw.values()):
+            dev = _cuda_device_of(a)
+            if dev is not None:
+                break
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kw)
+        with torch.cuda.device(dev):
+            return fn(*args, **kw)
+    return wrapper
 
 
 def _dtype_code(t: torch.Tensor) -> int:
@@ -44,6 +78,10 @@ def stage(x, device="cuda", prefer_bytes: bool = True):
     anything else stays float32."""
     nat.require_device()
     lib = _lib()
+    target = torch.device(device)
+    if target.type == "cuda" and target.index is not None and target.index != torch.cuda.current_device():
+        with torch.cuda.device(target):
+            return stage(x, target, prefer_bytes)
     if isinstance(x, np.ndarray):
         if x.dtype not in (np.uint8, np.float32):
             x = x.astype(np.float32)
@@ -81,6 +119,7 @@ def stage(x, device="cuda", prefer_bytes: bool = True):
 SORTED_MIN_ROWS = 1 << 18      # below this the fused single-launch descent wins (launch count, short segments)
 
 
+@_device_scoped
 def quantize(tree_dev: dict, k: int, depth: int, desc: torch.Tensor, want_heap: bool = False,
              stats: torch.Tensor = None, start: int = 0, method: str = "auto", work: torch.Tensor = None):
     """Reference node id of the stop node of every descriptor (int32 [n]); optionally also the
@@ -95,7 +134,11 @@ def quantize(tree_dev: dict, k: int, depth: int, desc: torch.Tensor, want_heap: 
     word = torch.empty(n, dtype=torch.int32, device=desc.device)
     leaf = torch.empty(n, dtype=torch.int32, device=desc.device) if want_heap else None
     if method == "auto":
-        big = desc.dtype == torch.uint8 and start == 0 and n >= SORTED_MIN_ROWS and depth >= 2
+        # the level-synchronous engines pack the descent path into 32 bits and index the heap with int32 -- the
+        # same predicate vt_quantize_host applies before it leaves the fused kernel
+        bits = max(1, int(k).bit_length())
+        packed_ok = (depth - 1) * bits <= 32 and heap_size(k, depth) < (1 << 31)
+        big = desc.dtype == torch.uint8 and start == 0 and n >= SORTED_MIN_ROWS and depth >= 2 and packed_ok
         method = ("mma" if tree_dev.get("mma_ok", False) else "sorted") if big else "fused"
     if method == "mma":
         # the byte planes depend only on the tree: prepared once and kept with the tree's device tensors
@@ -129,6 +172,7 @@ def quantize(tree_dev: dict, k: int, depth: int, desc: torch.Tensor, want_heap: 
     return (word, leaf) if want_heap else word
 
 
+@_device_scoped
 def quantize_host(tree_dev: dict, k: int, depth: int, h_desc, h_word, chunk_rows: int = 0):
     """End-to-end variant: host (pinned) descriptor rows in, host word ids out, chunked and
     overlapped inside the native library (``vt_quantize_host``)."""
@@ -142,6 +186,7 @@ def quantize_host(tree_dev: dict, k: int, depth: int, h_desc, h_word, chunk_rows
 
 
 # --------------------------------------------------------------------------------------- sort
+@_device_scoped
 def sort_pairs(keys: torch.Tensor, vals: torch.Tensor, n_bits: int):
     """Stable radix sort of (uint32 key, uint32 value) pairs held in int32 tensors."""
     lib = _lib()
@@ -167,6 +212,27 @@ class _NoComm:
 
     def all_gather_counts(self, t):
         return t[None]
+
+
+def subtree_split_level(k: int, depth: int, world: int):
+    """First level whose nodes give every rank a few whole subtrees (>= 4 nodes per rank); None when the tree
+    is too small for that and the build stays with one all-reduce per Lloyd pass."""
+    for level in range(1, depth):
+        if k ** level >= 4 * world:
+            return level
+    return None
+
+
+def subtree_owners(seg_global: torch.Tensor, world: int) -> torch.Tensor:
+    """Owner rank of every node of the split level: contiguous node ranges balanced by member count (midpoint of
+    the node's member range against equal cuts).  Deterministic from the all-reduced counts, so every rank
+    computes the same map."""
+    c = seg_global.to(torch.float64)
+    total = float(c.sum().item())
+    if total <= 0:
+        return torch.zeros_like(seg_global)
+    mid = torch.cumsum(c, 0) - 0.5 * c
+    return torch.clamp((mid * (world / total)).floor().to(torch.int64), 0, world - 1)
 
 
 class CudaLevelOps:
@@ -215,6 +281,10 @@ class CudaLevelOps:
         nat.check(self.lib.vt_kmeans_update(nat.ptr(sums), nat.ptr(counts), n_rows, dp, nat.ptr(child_cent),
                                             nat.stream_ptr()), "vt_kmeans_update")
 
+    def stable_sort(self, keys, vals, n_bits):
+        """stable sort of (int32 key, int32 value) pairs by key (subtree exchange: regroup received rows by node)."""
+        return sort_pairs(keys, vals, n_bits)
+
     def partition(self, parent, label, n_active, node_internal, k, n_rows, perm):
         """stable partition of every node's members into its children (vocabulary.py:64-66):
         returns (child index per member, member rows), both sorted by child index; members of leaf
@@ -225,6 +295,7 @@ class CudaLevelOps:
         return sort_pairs(keys[:n_active], perm, int(n_rows).bit_length())
 
 
+@_device_scoped
 def build_tree(desc: torch.Tensor, d: int, k: int, depth: int, n_iter: int = 10, comm=None,
                stats: torch.Tensor = None, log=None, ops=None) -> FlatTree:
     """Level-synchronous hierarchical k-means over byte descriptors [N, DP] (this rank's shard).
@@ -260,9 +331,37 @@ def build_tree(desc: torch.Tensor, d: int, k: int, depth: int, n_iter: int = 10,
     seg_local = torch.tensor([n], dtype=torch.int64, device=dev)
     seg_global = torch.tensor([n_total], dtype=torch.int64, device=dev)
 
+    split = subtree_split_level(k, depth, comm.world) if comm.world > 1 else None
+    publish, published_from = None, None
     for level in range(depth):
         n_nodes = k ** level
         n_rows = n_nodes * k
+        if split is not None and level == split:
+            # ---- subtree ownership: ONE all-to-all moves every member of a node to the rank that owns the node's
+            # subtree; the levels from here on run without any collective.  Ranks hold contiguous ranges of the
+            # global row order and send their members node by node, so concatenating the blocks in rank order and
+            # regrouping them by node with a STABLE sort keeps every node's members in global order -- the seeded
+            # initial centres (member floor(j*m/k)) and hence the tree are those of the single-process build.
+            allc = comm.all_gather_counts(seg_local)                      # [world, n_nodes]
+            owner = subtree_owners(seg_global, comm.world)
+            mine = owner == comm.rank
+            send_rows = desc.index_select(0, perm.long())                 # members in node order (perm is node-grouped)
+            send_counts = torch.zeros(comm.world, dtype=torch.int64, device=dev).index_add_(0, owner, seg_local)
+            recv_per_src = (allc * mine[None, :].to(allc.dtype))          # [world, n_nodes] rows I receive
+            recv_counts = recv_per_src.sum(1)
+            sc_h, rc_h = send_counts.cpu().tolist(), recv_counts.cpu().tolist()
+            recv = torch.empty((int(sum(rc_h)), dp), dtype=desc.dtype, device=dev)
+            comm.all_to_all_rows(recv, send_rows, rc_h, sc_h)
+            node_ids = torch.arange(n_nodes, dtype=torch.int32, device=dev)
+            keys = torch.repeat_interleave(node_ids.repeat(comm.world), recv_per_src.reshape(-1))
+            order = torch.arange(keys.numel(), dtype=torch.int32, device=dev)
+            parent, perm = ops.stable_sort(keys.contiguous(), order, max(1, int(n_nodes).bit_length()))
+            desc, n = recv, int(recv.shape[0])
+            seg_global = torch.where(mine, seg_global, torch.zeros_like(seg_global))
+            seg_local = seg_global.clone()
+            publish, published_from = comm, level
+            comm = _NoComm()
+            del send_rows
         n_active = perm.numel()
         node_internal = (seg_global >= k).to(torch.uint8)                 # vocabulary.py:55
         if int(node_internal.sum().item()) == 0:
@@ -321,6 +420,15 @@ def build_tree(desc: torch.Tensor, d: int, k: int, depth: int, n_iter: int = 10,
         perm = svals[:n_next].contiguous()
         parent = skeys[:n_next].contiguous()
 
+    if publish is not None:
+        # every heap row below the split level was written by exactly one owner (zeros elsewhere): the sum is exact
+        o, co = level_offset(k, published_from), level_offset(k, published_from + 1)
+        publish.all_reduce(cent[co:])
+        publish.all_reduce(count_heap[co:])
+        flags = torch.cat([internal[o:], exists[co:]]).to(torch.int32)
+        publish.all_reduce(flags)
+        internal[o:] = flags[:n_heap - o].to(torch.uint8)
+        exists[co:] = flags[n_heap - o:].to(torch.uint8)
     if dev.type == "cuda":       # everything stays on the device: numbering computed there, host mirrors on demand
         tree = FlatTree.from_device(k, depth, d, cent, exists, internal, count_heap, byte_built=True)
     else:
@@ -332,6 +440,7 @@ def build_tree(desc: torch.Tensor, d: int, k: int, depth: int, n_iter: int = 10,
 _SINGLE_PASS_WORDS = 1 << 31        # the single-pass encoder stages 8 B per descriptor
 
 
+@_device_scoped
 def encode(words: torch.Tensor, img_off: torch.Tensor, tree_dev: dict, depth: int, n_ref: int,
            all_nodes: bool = True, want_df: bool = False, min_level: int = 0) -> dict:
     """Bag-of-words CSR of a batch of images.  ``words`` int32 [n_desc] (reference ids of the
@@ -404,22 +513,43 @@ def entry_rows(csr: dict) -> torch.Tensor:
     return torch.repeat_interleave(torch.arange(n_img, device=sizes.device), sizes)
 
 
-def tfidf_weights(csr: dict, idf: torch.Tensor, norm: str = "l2"):
-    """Opt-in Nister & Stewenius weighting (what vocabulary.py:131,137 leaves commented out):
-    w = tf * idf[node], normalised per image in L2 or L1.  Returns float32 [nnz]."""
-    w = csr["count"].to(torch.float32) * idf[csr["node"].long()]
-    rows = entry_rows(csr)
-    tot = torch.zeros(csr["n_img"], dtype=torch.float64, device=w.device)
-    if norm == "l2":
-        tot.index_add_(0, rows, (w.double() ** 2))
-        tot = tot.sqrt()
-    else:
-        tot.index_add_(0, rows, w.double().abs())
-    scale = torch.where(tot > 0, 1.0 / tot, torch.zeros_like(tot))
-    return (w.double() * scale[rows]).to(torch.float32)
+@_device_scoped
+def idf_from_df(df: torch.Tensor, n_images: int) -> torch.Tensor:
+    """idf_n = ln(N / df_n) in binary64 (0 where no image visits the node) -- the Nister & Stewenius weight
+    that vocabulary.py:131,137 leaves commented out.  ``df`` int32 [n_ref] (all-reduced over the ranks first
+    when the images are sharded)."""
+    lib = _lib()
+    idf = torch.empty(df.numel(), dtype=torch.float64, device=df.device)
+    nat.check(lib.vt_idf(nat.ptr(df.contiguous()), df.numel(), int(n_images), nat.ptr(idf), nat.stream_ptr()), "vt_idf")
+    return idf
+
+
+@_device_scoped
+def weighted_rnorm(csr: dict, idf: torch.Tensor, norm: str = "l2") -> torch.Tensor:
+    """1 / |idf * tf|_2 (or _1) per CSR row, binary64 [n_img]; -1 for all-zero rows."""
+    lib = _lib()
+    rn = torch.empty(max(csr["n_img"], 1), dtype=torch.float64, device=idf.device)
+    nat.check(lib.vt_weighted_rnorm(nat.ptr(csr["row_off"]), nat.ptr(csr["node"]), nat.ptr(csr["count"]), csr["n_img"],
+                                    nat.ptr(idf), int(norm == "l1"), nat.ptr(rn), nat.stream_ptr()), "vt_weighted_rnorm")
+    return rn[:csr["n_img"]]
+
+
+@_device_scoped
+def query_weights(q: dict, idf: torch.Tensor, norm: str = "l2") -> dict:
+    """Query-side factors of the weighted rank keys (csrc/vt_weight.cu): dict(qv, qi, rnorm), binary64."""
+    lib = _lib()
+    rn = weighted_rnorm(q, idf, norm)
+    qv = torch.empty(max(q["nnz"], 1), dtype=torch.float64, device=idf.device)
+    qi = torch.empty(max(q["nnz"], 1), dtype=torch.float64, device=idf.device)
+    rn_full = rn if rn.numel() else torch.full((1,), -1.0, dtype=torch.float64, device=idf.device)
+    nat.check(lib.vt_query_weights(nat.ptr(q["row_off"]), nat.ptr(q["node"]), nat.ptr(q["count"]), q["n_img"],
+                                   nat.ptr(idf), nat.ptr(rn_full), int(norm == "l1"), nat.ptr(qv), nat.ptr(qi),
+                                   nat.stream_ptr()), "vt_query_weights")
+    return dict(qv=qv, qi=qi, rnorm=rn_full)
 
 
 # --------------------------------------------------------------------------------------- index
+@_device_scoped
 def build_index(csr: dict, n_ref: int, weight: torch.Tensor = None) -> dict:
     """Forward CSR -> inverted file sharded by image range (postings in image order)."""
     lib = _lib()
@@ -475,8 +605,9 @@ def build_index(csr: dict, n_ref: int, weight: torch.Tensor = None) -> dict:
 
 
 # --------------------------------------------------------------------------------------- score
+@_device_scoped
 def score(index: dict, q: dict, topk: int, mode: int = nat.SCORE_TF_L2, q_val: torch.Tensor = None,
-          want_all: bool = False, merge: bool = True) -> dict:
+          want_all: bool = False, merge: bool = True, weights: dict = None) -> dict:
     """Score a CSR batch of queries against the inverted file and select the top-k per query.
 
     Returns dict(key [Q, topk] f64, id [Q, topk] i32, score [Q, topk] f64, all_key [Q, n_img] | None,
@@ -486,12 +617,30 @@ def score(index: dict, q: dict, topk: int, mode: int = nat.SCORE_TF_L2, q_val: t
     s = nat.stream_ptr()
     nq = q["n_img"]
     n_img, n_shards = index["n_img"], index["n_shards"]
-    topk = int(min(topk, lib.vt_score_max_topk()))
-    if q_val is None:
-        q_val = q["count"].to(torch.float32)
+    if topk > lib.vt_score_max_topk():
+        raise ValueError("top-%d requested; the block-wide selection keeps at most %d per query (use retrieve() for "
+                         "the full order)" % (topk, lib.vt_score_max_topk()))
+    topk = int(topk)
     shard_key = torch.empty((max(nq, 1), n_shards, topk), dtype=torch.float64, device=dev)
     shard_id = torch.empty((max(nq, 1), n_shards, topk), dtype=torch.int32, device=dev)
     all_key = torch.empty((max(nq, 1), n_img), dtype=torch.float64, device=dev) if want_all else None
+    if mode != nat.SCORE_TF_L2 and not index.get("weighted", False):
+        # tf-idf modes over the integer tf index: binary64 weights on the query side, per-image weighted norms
+        if weights is None or "img_rnorm" not in weights:
+            raise ValueError("weighted scoring needs weights=dict(idf=..., img_rnorm=..., norm=...)")
+        qw = query_weights(q, weights["idf"], weights["norm"])
+        nat.check(lib.vt_score_topk_weighted(nat.ptr(index["post_off"]), nat.ptr(index["postings"]),
+                                             nat.ptr(weights["img_rnorm"]), n_img, index["n_ref"], nat.ptr(q["row_off"]),
+                                             nat.ptr(q["node"]), nat.ptr(qw["qv"]), nat.ptr(qw["qi"]), nat.ptr(qw["rnorm"]),
+                                             nq, mode, topk, nat.ptr(shard_key), nat.ptr(shard_id), nat.ptr(all_key), s),
+                  "vt_score_topk_weighted")
+        out = dict(all_key=all_key, shard_key=shard_key, shard_id=shard_id, topk=topk)
+        if merge:
+            out.update(merge_topk(shard_key.view(max(nq, 1), -1), shard_id.view(max(nq, 1), -1), nq, topk, mode,
+                                  q["sumsq"], index["sumsq"]))
+        return out
+    if q_val is None:
+        q_val = q["count"].to(torch.float32)
     nat.check(lib.vt_score_topk(nat.ptr(index["post_off"]), nat.ptr(index["postings"]), nat.ptr(index["rnorm"]),
                                 n_img, index["n_ref"], nat.ptr(q["row_off"]), nat.ptr(q["node"]), nat.ptr(q_val),
                                 nq, mode, topk, nat.ptr(shard_key), nat.ptr(shard_id), nat.ptr(all_key),
@@ -505,6 +654,7 @@ def score(index: dict, q: dict, topk: int, mode: int = nat.SCORE_TF_L2, q_val: t
     return out
 
 
+@_device_scoped
 def merge_topk(cand_key: torch.Tensor, cand_id: torch.Tensor, nq: int, topk: int, mode: int,
                q_sumsq: torch.Tensor, img_sumsq: torch.Tensor) -> dict:
     """Merge ``n_cand`` (key, id) candidates per query into the final top-k + reference scores."""

@@ -51,9 +51,30 @@ class OracleLevelOps:
         mask = (counts > 0)[:, None].expand(-1, dp)
         child_cent[mask] = upd[mask]
 
+    def stable_sort(self, keys, vals, n_bits):
+        order = torch.sort(keys, stable=True).indices
+        return keys[order], vals[order]
+
     def partition(self, parent, label, n_active, node_internal, k, n_rows, perm):
         par = parent[:n_active].long()
         keys = torch.where(node_internal[par] != 0, par * k + label[:n_active].long(),
                            torch.full_like(par, n_rows))
         order = torch.sort(keys, stable=True).indices
         return keys[order].to(torch.int32), perm[:n_active][order]
+
+
+def merge_ranked_cpu(keys, ids, scores, topk):
+    """Test double for ``dist.merge_ranked`` (the product runs vt_topk_merge_scored on the device): the same
+    comparator -- key descending, ties by ascending image index, empty slots (id -1) last -- with torch sorts."""
+    w, q, k = keys.shape
+    keys = keys.permute(1, 0, 2).reshape(q, w * k)
+    ids = ids.permute(1, 0, 2).reshape(q, w * k)
+    scores = scores.permute(1, 0, 2).reshape(q, w * k)
+    big = torch.iinfo(torch.int32).max
+    ids_key = torch.where(ids >= 0, ids, torch.full_like(ids, big))
+    keys = torch.where(ids >= 0, keys, torch.full_like(keys, float("-inf")))
+    o1 = torch.sort(ids_key, dim=1, stable=True).indices
+    k1 = torch.gather(keys, 1, o1)
+    o2 = torch.sort(k1, dim=1, descending=True, stable=True).indices
+    order = torch.gather(o1, 1, o2)[:, :topk]
+    return torch.gather(ids, 1, order), torch.gather(scores, 1, order), torch.gather(keys, 1, order)

@@ -5,11 +5,17 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from oracle import vt_oracle as vo
+
+
+def vt_split_level(k, depth, world):
+    import vtree_b200 as vt
+    return vt.engine.subtree_split_level(k, depth, world)
 
 
 def _free_port():
@@ -45,8 +51,11 @@ def _build_worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_sharded_build_is_bit_identical_to_single_process():
-    world = 2
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_build_is_bit_identical_to_single_process(world):
+    """k=4, depth=4: levels 0-1 all-reduce integer sums, level 2 (16 nodes >= 4 per rank) is the subtree
+    exchange (all-to-all of member rows), levels 2-3 run without collectives, one publish at the end."""
+    assert vt_split_level(4, 4, world) == 2
     port = _free_port()
     out = mp.Manager().dict()
     mp.spawn(_build_worker, args=(world, port, out), nprocs=world, join=True)
@@ -64,6 +73,7 @@ def test_single_process_build_with_oracle_ops_matches_oracle():
 
 def _retrieve_worker(rank, world, port, out):
     import vtree_b200 as vt
+    from oracle_ops import merge_ranked_cpu
     _init(rank, world, port)
     try:
         rng = np.random.default_rng(0)
@@ -77,7 +87,7 @@ def _retrieve_worker(rank, world, port, out):
             ks = np.take_along_axis(kk, order, 1)
             return dict(key=torch.from_numpy(ks), id=torch.from_numpy(order.astype(np.int32)),
                         score=torch.from_numpy(np.sqrt(2 - 2 * ks)))
-        ids, sc, ks = vt.dist.retrieve_sharded(score_local, lo, k, vt.dist.Comm())
+        ids, sc, ks = vt.dist.retrieve_sharded(score_local, lo, k, vt.dist.Comm(), merge=merge_ranked_cpu)
         want = np.lexsort((np.broadcast_to(np.arange(n_img), key.shape), -key), axis=1)[:, :k]
         out[rank] = bool(np.array_equal(ids.numpy(), want) and
                          np.allclose(sc.numpy(), np.sqrt(2 - 2 * np.take_along_axis(key, want, 1))))
@@ -94,11 +104,11 @@ def test_sharded_retrieval_merge_matches_global_order():
 
 
 def test_merge_ranked_handles_empty_slots():
-    import vtree_b200 as vt
+    from oracle_ops import merge_ranked_cpu
     keys = torch.tensor([[[0.5, 0.2, -2.0]], [[0.5, 0.4, 0.1]]], dtype=torch.float64)     # [world=2, Q=1, k=3]
     ids = torch.tensor([[[3, 9, -1]], [[1, 7, 8]]], dtype=torch.int32)
     sc = torch.zeros_like(keys)
-    got, _, _ = vt.dist.merge_ranked(keys, ids, sc, 4)
+    got, _, _ = merge_ranked_cpu(keys, ids, sc, 4)
     assert got.tolist() == [[1, 3, 7, 9]]
 
 
