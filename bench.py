@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--all-nodes-images", type=int, default=100_000)
     ap.add_argument("--all-nodes-queries", type=int, default=500)
     ap.add_argument("--no-retrieval", action="store_true")
+    ap.add_argument("--no-all-nodes", action="store_true")
     ap.add_argument("--no-build", action="store_true")
     ap.add_argument("--build-desc", type=int, default=10_000_000, help="descriptors for the tree-build leg (whole job)")
     ap.add_argument("--build-iters", type=int, default=10)
@@ -289,10 +290,33 @@ def main():
 
     level_ms, sort_ms = stage_profile(lib.vt_quantize_mma_profile if method == "mma" else lib.vt_quantize_sorted_profile)
     other_ms, _ = stage_profile(lib.vt_quantize_sorted_profile if method == "mma" else lib.vt_quantize_mma_profile, reps=1)
-    sort_passes = DEPTH - 1                     # packed paths: one radix pass (hist, scan, scatter) per level transition
-    # (the tensor path's byte planes are prepared once per tree, outside the steps); batches of >= 2^22 rows add the
-    # deferred output of the last level: one more radix pass (3 kernels) + the bucketed id write
-    launches_per_step = DEPTH + 3 * sort_passes + (4 if method == "mma" and n >= (1 << 22) else 0)
+    # kernels per step.  tcgen05 engine, batches >= 2^20 rows: ceil(L/2) two-level launches, one radix pass (hist, scan,
+    # scatter) between consecutive launches, and from 2^22 rows on the deferred output (one more pass + the id write);
+    # the byte planes are prepared once per tree, outside the steps.  SIMT engine: one launch and one pass per level.
+    if method == "mma" and n >= (1 << 20):
+        n_launch = (DEPTH + 1) // 2
+        launches_per_step = n_launch + 3 * (n_launch - 1) + (4 if n >= (1 << 22) else 0)
+    else:
+        launches_per_step = DEPTH + 3 * (DEPTH - 1) + (4 if method == "mma" and n >= (1 << 22) else 0)
+
+    # float32 input (the primary feed is fp32 [N, 128]; bytes are its lossless compressed form): the staging
+    # pass vt_stage_f32_to_u8 (512 B read + 128 B written per descriptor) is part of the step
+    n_32 = min(n, 16_000_000)
+    x32 = desc[:n_32].to(torch.float32)
+    for _ in range(2):
+        d8, _ = engine.stage(x32, dev)
+        w32 = engine.quantize(tree_dev, K_BRANCH, DEPTH, d8, method=method, work=work)
+    fa, fb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fa.record()
+    for _ in range(3):
+        d8, _ = engine.stage(x32, dev)
+        w32 = engine.quantize(tree_dev, K_BRANCH, DEPTH, d8, method=method, work=work)
+    fb.record()
+    torch.cuda.synchronize()
+    fp32_in = {"value": 3 * n_32 / (fa.elapsed_time(fb) * 1e-3), "unit": "descriptors/s", "rows": n_32,
+               "bytes_per_descriptor": 4 * DIM + 4, "same_words_as_byte_input": bool(torch.equal(w32, words[:n_32])),
+               "what": "float32 rows resident in HBM -> vt_stage_f32_to_u8 -> descent, staging inside the timed region"}
+    del x32, d8, w32
 
     # the single-launch fused descent on a slice, for comparison
     n_f = min(n, 8_000_000)
@@ -321,17 +345,30 @@ def main():
     e2e_ms = max_over_ranks((time.perf_counter() - t0) / e2e_steps * 1e3)
     e2e_value = n_e2e * world / (e2e_ms * 1e-3)
     e2e_ok = bool(torch.equal(h_word, words[:n_e2e].cpu()))
+    # the ceiling of that path: a plain pinned host->device copy of the same bytes, issued on every rank at the same time
+    # (the ranks of one box share the host's PCIe root ports and memory controllers)
+    d_tmp = torch.empty((n_e2e, DIM), dtype=torch.uint8, device=dev)
+    d_tmp.copy_(h_desc, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        d_tmp.copy_(h_desc, non_blocking=True)
+    barrier()
+    copy_ms = max_over_ranks((time.perf_counter() - t0) / 3 * 1e3)
+    h2d_ceiling = {"aggregate_GBps": n_e2e * DIM * world / (copy_ms * 1e-3) / 1e9, "per_gpu_GBps": n_e2e * DIM / (copy_ms * 1e-3) / 1e9,
+                   "what": "concurrent plain pinned cudaMemcpyAsync of the e2e input on every rank, max over ranks"}
+    del d_tmp
 
     # ---- secondary metric: queries/s top-10 over the sharded inverted file ---------------------
     secondary = None
     if not args.no_retrieval:
-        secondary = bench_retrieval(args, torch, vt, engine, nat, dev, rank, world, comm, ref_id, n_ref, barrier,
+        secondary = bench_retrieval(args, torch, vt, engine, nat, dev, rank, world, comm, cent, exists, internal, barrier,
                                     max_over_ranks)
-        # the reference's own embedding semantics (every node on the path counts): long posting lists for the
-        # top 111 nodes, still walked posting by posting in round 1 -- reported on a smaller database
-        secondary["all_nodes_mode"] = bench_retrieval(args, torch, vt, engine, nat, dev, rank, world, comm, ref_id, n_ref,
-                                                      barrier, max_over_ranks, all_nodes=True,
-                                                      db_images=args.all_nodes_images, queries=args.all_nodes_queries)
+        # the reference's own embedding semantics (every node on the path counts, vocabulary.py:92-100)
+        if not args.no_all_nodes:
+            secondary["all_nodes_mode"] = bench_retrieval(args, torch, vt, engine, nat, dev, rank, world, comm, cent, exists,
+                                                          internal, barrier, max_over_ranks, all_nodes=True,
+                                                          db_images=args.all_nodes_images, queries=args.all_nodes_queries)
 
     # ---- tertiary: BASELINE configs[1], tree build k=10 L=6 on 10 M descriptors ----------------
     build = None
@@ -345,8 +382,9 @@ def main():
 
     if rank == 0:
         flop_per_desc = 3 * K_BRANCH * DIM * DEPTH                 # sub, mul, add per element per candidate
-        alg_bytes = DIM + 4                                        # byte row in, int32 word id out
+        alg_bytes = DIM + 4                                        # byte row in, int32 word id out = 132 B per descriptor
         per_launch = n
+        n_stages = int((level_ms > 0).sum())
         lvl_total_ms = float(level_ms.sum())
         peaks = {}
         try:
@@ -355,41 +393,50 @@ def main():
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         other_total_ms = float(other_ms.sum())
-        # bytes the level kernels must move per descriptor-level: 128 B row gather + 4 B permutation +
-        # 4 B node key in, 4 B key + 4 B permutation out (the last level writes the 4 B word id instead)
-        level_bytes = [DIM + (8 if l > 0 else 0) + (8 if l + 1 < DEPTH else 4) for l in range(DEPTH)]
+        # DRAM bytes per descriptor and step of the descent kernels, from the committed ncu launch list of this command
+        # (profiles/r02_descent_traffic.json, written by tools/summarise_launches.py from the capture); null when no
+        # capture of the current kernels is committed
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_descent_traffic.json")))
+            traffic, traffic_src = float(tj["level_kernel_dram_bytes_per_row"]) * per_launch, tj["source"]
+        except (OSError, KeyError, ValueError):
+            pass
         simt = {"bound": "fp32", "kernel": "level_kernel<128,R> (vt_quantize_sorted.cu)", "unit": "TFLOP/s",
                 "peak": peak_tf.value, "peak_source": "FFMA microbenchmark on this device (vt_measure_fp32_peak)",
                 "flop_per_descriptor": flop_per_desc}
-        mma = {"bound": "hbm", "kernel": "level_mma_kernel (vt_quantize_mma.cu, tcgen05.mma kind::i8)", "unit": "GB/s",
-               "peak": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-               "bytes_per_descriptor_level": level_bytes}
+        mma = {"bound": "hbm", "kernel": "level_pair_kernel<10> (vt_quantize_pair.cu, tcgen05.mma kind::i8, two tree levels per launch)",
+               "unit": "GB/s", "peak": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+               "bytes_per_descriptor": alg_bytes}
         def fill(d, total_ms):
             if d["bound"] == "fp32":
                 d["achieved"] = flop_per_desc * per_launch / (total_ms * 1e-3) / 1e12
             else:
-                d["achieved"] = sum(level_bytes) * per_launch / (total_ms * 1e-3) / 1e9
+                # ALGORITHMIC bytes of the whole descent (132 B per descriptor: the row once, the id once)
+                # over the summed duration of the descent kernels -- re-reads of the row by later levels are traffic,
+                # not algorithmic bytes
+                d["achieved"] = alg_bytes * per_launch / (total_ms * 1e-3) / 1e9
             d["frac"] = d["achieved"] / d["peak"] if d["peak"] else None
             d["kernel_ms_per_step"] = total_ms
             return d
         main_r, other_r = (mma, simt) if method == "mma" else (simt, mma)
         roofline = fill(main_r, lvl_total_ms)
         roofline.update({
-            "launches_per_step": DEPTH,
-            "level_kernel_ms": [round(float(v), 3) for v in level_ms],
-            "resort_ms": [round(float(v), 3) for v in sort_ms],
+            "launches_per_step": n_stages,
+            "level_kernel_ms": [round(float(v), 3) for v in level_ms[:n_stages]],
+            "resort_ms": [round(float(v), 3) for v in sort_ms[:n_stages]],
             "kernel_share_of_step": lvl_total_ms / kern_ms,
             "whole_step": {"step_ms_events": kern_ms,
                            "algorithmic_GBps": alg_bytes * per_launch / (kern_ms * 1e-3) / 1e9,
-                           "algorithmic_TFLOPs": flop_per_desc * per_launch / (kern_ms * 1e-3) / 1e12},
-            # DRAM bytes per launch of the dominant kernel: ncu capture of this command at 100 M rows
-            # (profiles/r01_launches_final.csv: dram__bytes_read.sum + dram__bytes_write.sum of the six level launches
-            # = 13.6 / 14.4 / 14.4 / 14.4 / 14.5 / 15.5 GB, mean 144.6 B per row), scaled to this launch
-            "traffic": (144.6 * per_launch) if method == "mma" else None,
-            "traffic_source": "ncu launch list of this command at 100 M rows, mean of the six level launches, scaled by rows (not re-measured in this run)" if method == "mma" else None,
-            "level_kernel_ms_note": "entry 0 includes the per-call plane preparation of the profile variant; the last entry includes the deferred output (bucket pass + id write)",
+                           "frac_of_hbm_peak": alg_bytes * per_launch / (kern_ms * 1e-3) / 1e9 / hbm_peak,
+                           "algorithmic_TFLOPs": flop_per_desc * per_launch / (kern_ms * 1e-3) / 1e12,
+                           "hbm_bound_descriptors_per_s": hbm_peak * 1e9 / alg_bytes},
+            "traffic": traffic,
+            "traffic_source": traffic_src,
+            "level_kernel_ms_note": "one entry per launch (two tree levels each); entry 0 includes the per-call plane preparation of the profile variant, the last entry the deferred output (bucket pass + id write)",
             "other_engine": dict(fill(other_r, other_total_ms), level_kernel_ms=[round(float(v), 3) for v in other_ms]),
             "fused_single_launch_descent": {"value": fused_rate, "unit": "descriptors/s", "rows": n_f},
+            "fp32_input": fp32_in,
         })
         line = {
             "metric": METRIC, "value": value, "unit": "descriptors/s", "n_gpus": world, "steps": args.steps,
@@ -401,7 +448,8 @@ def main():
                        "tree": "synthetic hierarchical mixture, seed 7", "binary64_rechecks_per_step": rechecks // max(args.steps, 1)},
             "e2e": {"value": e2e_value, "unit": "descriptors/s", "h2d_bytes_per_step": n_e2e * DIM,
                     "d2h_bytes_per_step": n_e2e * 4, "descriptors_per_step": n_e2e, "matches_device_path": e2e_ok,
-                    "api": "vt_quantize_host (engine.quantize_host)", "cpus_bound_to_gpu_node": affinity},
+                    "api": "vt_quantize_host (engine.quantize_host)", "cpus_bound_to_gpu_node": affinity,
+                    "h2d_achieved_GBps": n_e2e * DIM * world / (e2e_ms * 1e-3) / 1e9, "h2d_ceiling": h2d_ceiling},
             "gpu_launches": args.steps * launches_per_step,
             "clocks": clocks.summary(),
             "roofline": roofline,
@@ -414,128 +462,190 @@ def main():
         dist.destroy_process_group()
 
 
-def bench_retrieval(args, torch, vt, engine, nat, dev, rank, world, comm, ref_id, n_ref, barrier, max_over_ranks,
+def bench_retrieval(args, torch, vt, engine, nat, dev, rank, world, comm, cent, exists, internal, barrier, max_over_ranks,
                     all_nodes=False, db_images=None, queries=None):
-    """leaf-words mode (headline, ~1k words per image) or all-nodes mode (the reference's semantics,
-    vocabulary.py:92-100: every node on the path counts, ~3.7k entries per image)."""
+    """queries/s top-10 through the PUBLIC API: ``Database(dataset, VocabularyTree, comm=...)``.
+
+    The database images' words are synthetic (hashed leaves, ~1k per image: BASELINE configs[3]) and adopted as this
+    rank's forward CSR; the QUERIES are descriptor arrays on the host: ``Database.retrieve_batch(paths, k)`` packs them
+    into pinned memory, uploads, quantises them through the tree, encodes, scores the inverted file, merges the shard
+    / rank lists and returns host ids -- the end-to-end number.  Half of the queries are database members (their
+    database rows are the quantised words of the same descriptors), so the self-match must rank first with score 0.
+    ``leaf-words`` (headline) counts the stop nodes only; ``all-nodes`` is the reference's embedding semantics
+    (vocabulary.py:92-100: every node on the path counts)."""
     n_leaf = K_BRANCH ** DEPTH
-    leaf_ref = torch.from_numpy(ref_id[vt.tree.level_offset(K_BRANCH, DEPTH):].astype(np.int64)).to(dev)
+    flat = vt.FlatTree.from_device(K_BRANCH, DEPTH, DIM, cent, torch.from_numpy(exists).to(dev),
+                                   torch.from_numpy(internal).to(dev), byte_built=True)
+    tdev = flat.device(dev)
+    leaf_ref = tdev["ref_id"][vt.tree.level_offset(K_BRANCH, DEPTH):].to(torch.int64)
     db_images = args.db_images if db_images is None else db_images
     lo, hi = vt.dist.shard_range(db_images, rank, world)
     wpi = args.words_per_image
-    if all_nodes:        # parent / level tables of the full tree, in reference-id space
-        nh = vt.tree.heap_size(K_BRANCH, DEPTH)
-        heap_of_ref = np.empty(n_ref, np.int64)
-        heap_of_ref[ref_id] = np.arange(nh)
-        parent_ref = np.where(heap_of_ref > 0, ref_id[np.maximum(heap_of_ref - 1, 0) // K_BRANCH], -1).astype(np.int32)
-        lvl = np.zeros(nh, np.uint8)
-        for level in range(1, DEPTH + 1):
-            o = vt.tree.level_offset(K_BRANCH, level)
-            lvl[o:o + K_BRANCH ** level] = level
-        dummy = dict(parent_ref=torch.from_numpy(parent_ref).to(dev), level_ref=torch.from_numpy(lvl[heap_of_ref]).to(dev))
-    else:
-        dummy = dict(parent_ref=torch.zeros(1, dtype=torch.int32, device=dev), level_ref=torch.zeros(1, dtype=torch.uint8, device=dev))
+    q = args.queries if queries is None else queries
+    voc = vt.encoders.VocabularyTree(K_BRANCH, DEPTH, descriptor=lambda im: im, all_nodes=all_nodes, device=dev).set_tree(flat)
 
-    def encode_ids(ids):
-        words = torch.empty(len(ids) * wpi, dtype=torch.int32, device=dev)
-        step = 65536
-        for s in range(0, len(ids), step):
-            e = min(len(ids), s + step)
-            words[s * wpi:e * wpi] = hashed_words(torch, ids[s:e], wpi, n_leaf, leaf_ref, dev)
-        off = torch.arange(len(ids) + 1, dtype=torch.int64, device=dev) * wpi
-        return engine.encode(words, off, dummy, DEPTH, n_ref, all_nodes=all_nodes)
+    # ---- queries: host descriptor arrays (the same on every rank) --------------------------------------------------
+    n_member = q // 2
+    member = (torch.arange(n_member, device=dev, dtype=torch.int64) * 197) % max(db_images, 1)
+    q_desc = vt.synth.descriptors_from_tree(cent, K_BRANCH, DEPTH, q * wpi, seed=555)
+    member_words = engine.quantize(tdev, K_BRANCH, DEPTH, q_desc[:n_member * wpi])
+    h_q = q_desc.cpu().numpy().reshape(q, wpi, DIM)
+    del q_desc
+    names = ["q%06d" % i for i in range(q)]
+    qds = vt.ArrayDataset([h_q[i] for i in range(q)], names)
 
-    # words of this rank's images (synthetic), then the two index-side stages timed separately
-    db_ids = torch.arange(lo, hi, device=dev)
-    db_words = torch.empty(len(db_ids) * wpi, dtype=torch.int32, device=dev)
-    for s0 in range(0, len(db_ids), 65536):
-        e0 = min(len(db_ids), s0 + 65536)
-        db_words[s0 * wpi:e0 * wpi] = hashed_words(torch, db_ids[s0:e0], wpi, n_leaf, leaf_ref, dev)
-    db_off = torch.arange(len(db_ids) + 1, dtype=torch.int64, device=dev) * wpi
-    engine.encode(db_words[:wpi * 64], db_off[:65], dummy, DEPTH, n_ref, all_nodes=all_nodes)      # warm-up
+    # ---- this rank's database shard --------------------------------------------------------------------------------
+    def shard_words(a, b):
+        ids = torch.arange(a, b, device=dev)
+        w = torch.empty(len(ids) * wpi, dtype=torch.int32, device=dev)
+        for s0 in range(0, len(ids), 65536):
+            e0 = min(len(ids), s0 + 65536)
+            w[s0 * wpi:e0 * wpi] = hashed_words(torch, ids[s0:e0], wpi, n_leaf, leaf_ref, dev)
+        mine = torch.nonzero((member >= a) & (member < b)).flatten()           # members: the words of their descriptors
+        if mine.numel():
+            dst = ((member[mine] - a)[:, None] * wpi + torch.arange(wpi, device=dev)[None, :]).reshape(-1)
+            src = (mine[:, None] * wpi + torch.arange(wpi, device=dev)[None, :]).reshape(-1)
+            w[dst] = member_words[src]
+        return w, torch.arange(len(ids) + 1, dtype=torch.int64, device=dev) * wpi
+
+    db_words, db_off = shard_words(lo, hi)
+    engine.encode(db_words[:wpi * 64], db_off[:65], tdev, DEPTH, flat.n_ref, all_nodes=all_nodes)      # warm-up
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    csr = engine.encode(db_words, db_off, dummy, DEPTH, n_ref, all_nodes=all_nodes)
+    csr = engine.encode(db_words, db_off, tdev, DEPTH, flat.n_ref, all_nodes=all_nodes)
     torch.cuda.synchronize()
     t_encode = time.perf_counter() - t0
     del db_words
+    db = vt.Database(qds, voc, comm=comm)
     t0 = time.perf_counter()
-    index = engine.build_index(csr, n_ref)
+    db._adopt(csr, {}, db_images, lo)                      # inverted file of this rank's shard (Database.index minus the image loop)
     torch.cuda.synchronize()
     t_invert = time.perf_counter() - t0
-    t_index = t_encode + t_invert
-    q = args.queries if queries is None else queries
-    member = (torch.arange(q // 2, device=dev, dtype=torch.int64) * 197) % max(db_images, 1)
-    fresh = db_images + torch.arange(q - q // 2, device=dev, dtype=torch.int64)
-    qcsr = encode_ids(torch.cat([member, fresh]))
+    index = db._index
     topk = 10
 
-    def one_pass():
-        local_out = engine.score(index, qcsr, topk)
+    # ---- device-resident: the query CSR stays in HBM, per-rank score + merged top-k --------------------------------
+    qcsr, back = db._query_csr(names)
+
+    def resident_pass():
+        out = db._score_local(qcsr, topk, False)
         if world == 1:
-            return local_out["id"], local_out["score"]
-        ids, sc, _ = vt.dist.retrieve_sharded(lambda: local_out, lo, topk, comm)
+            return out["id"], out["score"]
+        ids, sc, _ = vt.dist.retrieve_sharded(lambda: out, lo, topk, comm)
         return ids, sc
 
     for _ in range(2):
-        ids, sc = one_pass()
+        ids, sc = resident_pass()
     steps = 3
     barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
-        ids, sc = one_pass()
+        ids, sc = resident_pass()
     barrier()
     ms = max_over_ranks((time.perf_counter() - t0) / steps * 1e3)
-    ok = bool((ids[:q // 2, 0].to(torch.int64) == member).all().item() and (sc[:q // 2, 0] == 0).all().item())
+    back_t = torch.from_numpy(back).to(dev)
+    ids_q, sc_q = ids[back_t], sc[back_t]
+    ok = bool((ids_q[:n_member, 0].to(torch.int64) == member).all().item() and (sc_q[:n_member, 0] == 0).all().item())
+
+    # ---- end to end through Database.retrieve_batch: host descriptors in, host ids out -----------------------------
+    def e2e_pass():
+        db._extra_csr.clear()                              # nothing cached between steps: every query is staged and encoded again
+        return db.retrieve_batch(names, k=topk)
+
+    for _ in range(2):
+        h_ids, h_sc = e2e_pass()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        h_ids, h_sc = e2e_pass()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) / steps * 1e3)
+    e2e_ok = bool(np.array_equal(h_ids, ids_q.cpu().numpy()) and np.array_equal(h_sc, sc_q.cpu().numpy()))
+
+    # ---- N > 1: rank 0 recomputes on ONE GPU and the merged result must be identical -------------------------------
+    same_as_single = None
+    if world > 1 and rank == 0:
+        n_chk = min(q, 256)
+        words_all, off_all = shard_words(0, db_images)
+        csr1 = engine.encode(words_all, off_all, tdev, DEPTH, flat.n_ref, all_nodes=all_nodes)
+        del words_all
+        db1 = vt.Database(qds, voc)
+        db1._adopt(csr1, {}, db_images, 0)
+        ids1, sc1 = db1.retrieve_batch(names[:n_chk], k=topk)
+        same_as_single = bool(np.array_equal(ids1, h_ids[:n_chk]) and np.array_equal(sc1, h_sc[:n_chk]))
+        del db1, csr1
+
     out = {"metric": "queries/s top-10 @%s images" % ("1M" if db_images == 1_000_000 else db_images),
            "value": q / (ms * 1e-3), "unit": "queries/s", "ms_per_batch": ms, "queries": q, "db_images": db_images,
            "words_per_image": wpi, "mode": "all-nodes tf/L2 (reference semantics)" if all_nodes else "leaf-words tf/L2",
+           "api": "Database(dataset, VocabularyTree%s)" % (", comm=Comm()" if world > 1 else ""),
            "entries_per_image": float(csr["nnz"]) / max(hi - lo, 1),
-           "self_match_rank0": ok, "index_build_s": t_index, "n_shards_per_gpu": index["n_shards"],
+           "self_match_rank0": ok, "index_build_s": t_encode + t_invert, "n_shards_per_gpu": index["n_shards"],
+           "e2e": {"value": q / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_batch": e2e_ms,
+                   "h2d_bytes_per_step": int(q) * wpi * DIM, "d2h_bytes_per_step": int(q) * topk * 12,
+                   "api": "Database.retrieve_batch(paths, k=10): host descriptor arrays -> pinned staging -> H2D -> quantise -> encode -> score -> merge -> host ids",
+                   "equals_device_resident_result": e2e_ok},
+           "equals_single_gpu_recomputation": same_as_single,
            # HBM-bound index-side stages: bytes that must move (two encode passes read the 4 B words, the fill pass
            # writes 8 B per entry; inversion = 12 B keys/entry/image out + radix passes at 20 B + 16 B gather/fill)
            "encode": {"seconds": t_encode, "images_per_s": (hi - lo) / t_encode,
                       "algorithmic_GBps": (8.0 * (hi - lo) * wpi + 8.0 * csr["nnz"]) / t_encode / 1e9},
            "invert": {"seconds": t_invert, "postings_per_s": csr["nnz"] / t_invert,
-                      "algorithmic_GBps": csr["nnz"] * (12.0 + 20.0 * -(-int(index["n_shards"] * n_ref).bit_length() // 8) + 16.0)
+                      "algorithmic_GBps": csr["nnz"] * (12.0 + 20.0 * -(-int(index["n_shards"] * flat.n_ref).bit_length() // 8) + 16.0)
                                           / t_invert / 1e9}}
     if not all_nodes:
         alg = 8.0 * wpi * (db_images * wpi / n_leaf)
-        out["hbm"] = {"algorithmic_bytes_per_query": alg, "achieved_GBps": alg * q / (ms * 1e-3) / 1e9,
-                      # ncu --set full of score_shard_tf_kernel on this workload (profiles/r01_ncu_final_scorer.txt):
-                      # 219.7 GB of DRAM reads per 10 k queries = 2.7x the algorithmic bytes (32 B sectors around ~64 B
-                      # posting runs and 8 B row-pointer pairs), 3.2 TB/s; issue slots 27 % busy
-                      "traffic_bytes_per_query": 21.97e6, "traffic_source": "ncu capture of this workload (not re-measured in this run)"}
+        hbm = {"algorithmic_bytes_per_query": alg, "achieved_GBps": alg * q / (ms * 1e-3) / 1e9}
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_scorer_traffic.json")))
+            hbm["traffic_bytes_per_query"], hbm["traffic_source"] = float(tj["dram_bytes_per_query"]), tj["source"]
+        except (OSError, KeyError, ValueError):
+            hbm["traffic_bytes_per_query"], hbm["traffic_source"] = None, None
+        out["hbm"] = hbm
+    del db, csr, index, qcsr
+    torch.cuda.empty_cache()
     return out
 
 
 def bench_build(args, torch, vt, engine, dev, rank, world, comm, desc, barrier, max_over_ranks):
-    """VocabularyTree.fit at BASELINE configs[1]: k=10, L=6 on 10 M descriptors (sharded over the
-    ranks, integer sums all-reduced per level-iteration)."""
+    """VocabularyTree.fit at BASELINE configs[1]: k=10, L=6 on 10 M descriptors, through the public class
+    (``VocabularyTree(..., comm=)``: descriptors sharded over the ranks; integer sums all-reduced on the top
+    levels, subtree ownership below)."""
     # the SAME global dataset at every GPU count (rank r owns rows [lo, hi) of it), so the tree -- and the
     # checksum reported below -- must not depend on the number of GPUs
     lo, hi = vt.dist.shard_range(args.build_desc, rank, world)
     cent0 = vt.synth.hierarchical_tree(K_BRANCH, DEPTH, DIM, seed=7, device=dev)
-    x = vt.synth.descriptors_from_tree(cent0, K_BRANCH, DEPTH, args.build_desc, seed=4242)[lo:hi].contiguous()
+    x_all = vt.synth.descriptors_from_tree(cent0, K_BRANCH, DEPTH, args.build_desc, seed=4242)
+    x = x_all[lo:hi].contiguous()
     del cent0
-    log = []
-    stats = torch.zeros(4, dtype=torch.int64, device=dev)
-    engine.build_tree(x, DIM, K_BRANCH, DEPTH, n_iter=1, comm=comm)   # warm-up: module load, allocator pools for every level
+
+    def checksum(ft):
+        return int(ft.device(dev)["centroids"].view(torch.int32).to(torch.int64).sum().item())
+
+    warm = vt.encoders.VocabularyTree(K_BRANCH, DEPTH, descriptor=None, n_iter=1, device=dev, comm=comm)
+    warm.fit(x)                                            # warm-up: module load, allocator pools for every level
+    voc = vt.encoders.VocabularyTree(K_BRANCH, DEPTH, descriptor=None, n_iter=args.build_iters, device=dev, comm=comm)
     barrier()
     t0 = time.perf_counter()
-    tree = engine.build_tree(x, DIM, K_BRANCH, DEPTH, n_iter=args.build_iters, comm=comm, stats=stats,
-                             log=lambda **kw: log.append(kw))
+    voc.fit(x)
     barrier()
     dt = max_over_ranks(time.perf_counter() - t0)
-    passes = sum(l["iters"] + (0 if l["converged"] else 1) + (1 if l["converged"] else 0) for l in log)
-    member_passes = sum(l["members"] * (l["iters"] + 1) for l in log) * world
-    return {"metric": "tree build k=10 L=6", "seconds": dt,
-            # 128 B row + 4 B permutation + 4 B node + 1 B label per member and assignment pass
-            "algorithmic_GBps": 137.0 * member_passes / dt / 1e9, "descriptors": args.build_desc, "n_iter": args.build_iters,
-            "tree_checksum": int(tree.device(dev)["centroids"].view(torch.int32).to(torch.int64).sum().item()),
+    tree, log = voc.flat, voc.build_log
+    same = None
+    if world > 1 and rank == 0:                             # the sharded tree must be the single-GPU tree, bit for bit
+        one = vt.encoders.VocabularyTree(K_BRANCH, DEPTH, descriptor=None, n_iter=args.build_iters, device=dev).fit(x_all)
+        same = bool(checksum(one.flat) == checksum(tree) and
+                    torch.equal(one.flat.device(dev)["centroids"], tree.device(dev)["centroids"]))
+        del one
+    del x_all
+    passes = sum(l["iters"] + 1 for l in log)
+    member_passes = sum(l["members"] * (l["iters"] + 1) for l in log) * (world if world == 1 else 1)
+    return {"metric": "tree build k=10 L=6", "seconds": dt, "api": "VocabularyTree(...%s).fit(shard)" % (", comm=Comm()" if world > 1 else ""),
+            # 128 B row + 4 B permutation + 4 B node + 1 B label per member and assignment pass (this rank's passes)
+            "algorithmic_GBps_rank0": 137.0 * member_passes / dt / 1e9, "descriptors": args.build_desc, "n_iter": args.build_iters,
+            "tree_checksum": checksum(tree), "equals_single_gpu_recomputation": same,
             "nodes": int(tree.n_ref), "leaves_reached_depth": int((tree.level_ref == DEPTH).sum()),
-            "assign_passes": passes, "member_assignments_per_s": member_passes / dt,
-            "descriptors_per_s": args.build_desc / dt, "binary64_rechecks": int(stats[0].item()),
+            "assign_passes_rank0": passes, "descriptors_per_s": args.build_desc / dt,
             "levels": [{"level": l["level"], "iters": l["iters"], "converged": l["converged"]} for l in log]}
 
 

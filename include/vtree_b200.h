@@ -266,6 +266,24 @@ int vt_topk_merge_scored(const double *d_in_key, const int32_t *d_in_id, const d
                          int64_t n_query, int n_cand, int topk, double *d_out_key, int32_t *d_out_id,
                          double *d_out_score, void *stream);
 
+/* ---- dense top of an ALL-NODES index (vocabulary.py:92-100,132: every node on the path counts, so the top tree
+ * levels list every image).  Levels 0..1 ("top", counts up to the descriptors per image) are int32 rows
+ * d_top [n_img, n_top]; levels 2..Ld a uint8 block d_block [n_img, kd] (kd multiple of 128); deeper levels stay
+ * postings.  d_col_of_ref [n_ref]: >= 0 dense column, -1 posting node, -2 - t top column t.
+ * vt_dense_scatter fills the rows of a batch of images from their all-nodes CSR (raises *d_overflow when a dense
+ * count exceeds 255).  vt_dense_dots is the tcgen05 INT8 GEMM D[q][img] = A[q].B[img] + QT[q].T[img] (int32, exact);
+ * row counts padded to 256.  vt_score_topk_seeded = vt_score_topk (tf) with the accumulators started from D. */
+int vt_dense_scatter(const int64_t *d_row_off, const int32_t *d_node, const int32_t *d_count, int64_t n_img,
+                     int64_t img_base, const int32_t *d_col_of_ref, uint8_t *d_block, int64_t kd, int32_t *d_top,
+                     int n_top, int *d_overflow, void *stream);
+int vt_dense_dots(const uint8_t *d_a, const int32_t *d_qt, const uint8_t *d_b, const int32_t *d_t, int64_t qp,
+                  int64_t np, int64_t kd, int n_top, int32_t *d_out, int64_t ldd, void *stream);
+int vt_score_topk_seeded(const uint32_t *d_post_off, const void *d_postings, const double *d_img_rnorm,
+                         int64_t n_img, int64_t n_ref, const int64_t *d_q_off, const int32_t *d_q_node,
+                         const float *d_q_val, int64_t n_query, int topk, const int32_t *d_seed,
+                         int64_t seed_stride, double *d_shard_key, int32_t *d_shard_id, double *d_all_key,
+                         void *stream);
+
 /* ---- TF-IDF weighting + L1/L2 normalisation (what vocabulary.py:131,137 leaves commented out; opt-in) ----
  * Everything in binary64; the inverted file stays the exact integer tf index, the weights enter on the query
  * side (csrc/vt_weight.cu).  vt_idf: idf_n = ln(N / df_n), 0 where df_n == 0.  vt_weighted_rnorm: per CSR row

@@ -58,6 +58,9 @@ SIGNATURES = {
     "vt_rnorm": (_int, [_vp, _i64, _vp, _vp]),
     "vt_score_topk": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _int, _int, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "vt_topk_merge_scored": (_int, [_vp, _vp, _vp, _i64, _int, _int, _vp, _vp, _vp, _vp]),
+    "vt_dense_scatter": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _int, _vp, _vp]),
+    "vt_dense_dots": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp, _i64, _vp]),
+    "vt_score_topk_seeded": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _int, _vp, _i64, _vp, _vp, _vp, _vp]),
     "vt_idf": (_int, [_vp, _i64, _i64, _vp, _vp]),
     "vt_weighted_rnorm": (_int, [_vp, _vp, _vp, _i64, _vp, _int, _vp, _vp]),
     "vt_query_weights": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _int, _vp, _vp, _vp]),

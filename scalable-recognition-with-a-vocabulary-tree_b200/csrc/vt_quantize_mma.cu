@@ -25,7 +25,7 @@
 //
 // Preconditions: dp == 128, k <= 16, every child centroid in [0, 255.99] (true for trees built from
 // byte descriptors; the prepare kernel reports violations in d_stats[1]).
-#include "vt_common.cuh"
+#include "vt_mma_common.cuh"
 #include <stdlib.h>
 
 int vt_sort_pairs_impl(uint32_t *d_keys, uint32_t *d_vals, uint32_t *d_tmp_keys, uint32_t *d_tmp_vals, int64_t n,
@@ -34,99 +34,6 @@ int vt_sort_pass_impl(const uint32_t *kin, const uint32_t *vin, uint32_t *kout, 
                       uint32_t mask, void *d_hist, cudaStream_t s);
 
 namespace {
-constexpr int MM_TILE = 128;                    // descriptors per tile == threads per CTA == UMMA M
-constexpr int MM_N = 48;                        // 3 byte planes x 16 child slots (k-means kernel; the descent: PlaneCfg)
-constexpr int MM_A_BYTES = MM_TILE * 128;       // 16 KB
-constexpr int MM_B_BYTES = MM_N * 128;          // 6 KB
-constexpr int MM_TMEM_COLS = 64;                // power of two >= MM_N
-constexpr uint32_t MM_IDESC = (2u << 4) | ((uint32_t)(MM_N >> 3) << 17) | ((uint32_t)(MM_TILE >> 4) << 24);
-//                             c_format = S32; a_format = b_format = 0 (unsigned 8 bit); K-major A and B
-
-// The descent keeps KP child slots per byte plane: 16 in general, 10 when k <= 10 (the usual vocabulary tree) --
-// then the three planes fit N = 32 accumulator columns instead of 48: a third less plane traffic, 32 instead of
-// 64 TMEM columns and 16 fewer accumulator registers per thread, which is what lets 8 CTAs share an SM.
-template <int KP>
-struct PlaneCfg {
-    static constexpr int N = (3 * KP + 15) / 16 * 16;
-    static constexpr int B_BYTES = N * 128;
-    static constexpr int TMEM_COLS = N <= 32 ? 32 : 64;
-    static constexpr uint32_t IDESC = (2u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(MM_TILE >> 4) << 24);
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// byte offset of (row, k) inside a 128B-swizzled K-major tile whose rows are 128 bytes
-__device__ __forceinline__ uint32_t sw128_offset(int row, int kbyte)
-{
-    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((kbyte >> 4) ^ (row & 7))) << 4) + (kbyte & 15));
-}
-
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
-{
-    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | (1ull << 16) /* LBO (unused) */ | (64ull << 32) /* SBO = 1024 B */ |
-           (1ull << 46) /* sm100 descriptor version */ | (2ull << 61) /* SWIZZLE_128B */;
-}
-
-// ---- epilogue arithmetic ------------------------------------------------------------------------------
-// Scores are compared in 32 bits, units 2^-7:  s_c = floor(|c|^2 * 2^7) - (v0 << 8) - v1 - (v2 >> 8)  where
-// v0, v1, v2 are the accumulators of the three centroid byte planes (2 x.c * 2^7 = v0 2^8 + v1 + v2 2^-8).
-// Each s_c is within ONE unit of the exact score of the rounded centroid, so a gap of the 32-bit scores
-// is within two units of the exact gap; the contest test below subtracts three.  Fits int32: v0 < 2^23.
-constexpr int MM_S_SHIFT = 25;                  // 2^-32 units -> 2^-7 units
-
-template <int KP, int N>
-__device__ __forceinline__ void score_children(const uint32_t (&v)[N], const int *s_cn, int k, int &best, int &second,
-                                               int &arg)
-{
-    int cq[16];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        const int4 t = reinterpret_cast<const int4 *>(s_cn)[g];
-        cq[4 * g] = t.x; cq[4 * g + 1] = t.y; cq[4 * g + 2] = t.z; cq[4 * g + 3] = t.w;
-    }
-#pragma unroll
-    for (int c = 0; c < KP; ++c) {
-        if (c >= k) break;                                       // block-uniform: no predicated-off work
-        const int sc = cq[c] - (int)((v[c] << 8) + v[KP + c] + (v[2 * KP + c] >> 8));
-        if (sc < best) { second = best; best = sc; arg = c; }
-        else second = sc < second ? sc : second;
-    }
-}
-
-// provable margin for the centroid rounding (|error| <= m (da + db), m = 2^-16 sqrt(128) 1.02, da <= db) plus
-// the three units of the 32-bit scores: "gap <= 2 m db", squared to avoid the square root.  xn = |x|^2.
-__device__ __forceinline__ bool contest_test(int best, int second, float xn)
-{
-    const float gap = (float)(second - best - 3) * 0.0078125f;
-    const float d2b = fmaxf(0.f, (float)(second + 1) * 0.0078125f + xn);
-    const float two_m = 2.0f * 1.52587890625e-05f * 11.313708498984761f * 1.02f;
-    return gap <= 0.f || gap * gap <= two_m * two_m * 1.001f * d2b;
-}
-
-// |x|^2 of the row this thread owns, from the swizzled A tile
-__device__ __forceinline__ unsigned int row_norm2(const uint8_t *sA, int tid)
-{
-    unsigned int xn = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const uint4 q = *reinterpret_cast<const uint4 *>(sA + (tid >> 3) * 1024 + (tid & 7) * 128 + ((j ^ (tid & 7)) << 4));
-        xn = __dp4a(q.x, q.x, xn); xn = __dp4a(q.y, q.y, xn); xn = __dp4a(q.z, q.z, xn); xn = __dp4a(q.w, q.w, xn);
-    }
-    return xn;
-}
-
-// two-stage contest test: the crude bound |x|^2 <= 128 * 255^2 settles almost every row; only warps that
-// still hold a candidate read their rows' exact norms
-__device__ __forceinline__ bool contested_row(bool active, int best, int second, const uint8_t *sA, int tid)
-{
-    bool contested = active && contest_test(best, second, 8323200.f);
-    if (__any_sync(VT_FULL, contested)) {
-        const unsigned int xn = row_norm2(sA, tid);
-        contested = contested && contest_test(best, second, (float)xn * 1.0000002f);
-    }
-    return contested;
-}
-
 // ---- per-call preparation: byte planes + fixed-point squared norms of every node's children --------
 template <int KP>
 __global__ void __launch_bounds__(128)
@@ -762,6 +669,21 @@ extern "C" int vt_kmeans_assign_mma(const void *d_desc, int dtype, int dp, const
 }
 
 int64_t vt_mma_prepared_bytes(int k, int depth);
+int vt_mma_levels_paired(const void *d_desc, int64_t n, const float *cent, const uint8_t *internal, const int32_t *ref_id,
+                         int k, int depth, int32_t *leaf, int32_t *word, uint64_t *stats, const uint8_t *bimg,
+                         const int *cn32, void *sortwork, bool defer, cudaStream_t s, cudaEvent_t *ev, int *n_ev_io);
+
+// ids of (row, child) pairs that were bucketed by row range (the deferred output of the last level)
+int vt_mma_deferred_output(const uint32_t *rows, const uint32_t *child, int64_t n, const int32_t *ref_id, int32_t *leaf,
+                           int32_t *word, cudaStream_t s)
+{
+    // one resident wave, grid-stride: all CTAs sweep the buckets together, so the rows being written at
+    // any moment lie in one or two buckets
+    const int64_t w2 = (n + 255) / 256, c2 = (int64_t)vt_sm_count() * 8;
+    deferred_output_kernel<<<(int)(w2 < c2 ? w2 : c2), 256, 0, s>>>(rows, child, n, ref_id, leaf, word);
+    VT_LAUNCH_CHECK();
+    return VT_OK;
+}
 
 static int64_t mma_int_nodes(int k, int depth)
 {
@@ -830,6 +752,7 @@ int vt_mma_levels(const void *d_desc, int64_t n, const float *cent, const uint8_
     static bool attr_set = false;
     static int ctas10 = 8, ctas16 = 7;                           // resident CTAs per SM the grid is sized for (k <= 10 / k <= 16)
     static int64_t defer_min = (int64_t)1 << 22;                 // batches from this size on defer the last level's output
+    static int64_t pair_min = (int64_t)1 << 20;                  // batches from this size on take two levels per launch
     const bool narrow = mma_slots(k) == 10;
     const int smem = MM_A_BYTES + (int)mma_plane_bytes(k) + 1024;
     if (!attr_set) {
@@ -837,11 +760,20 @@ int vt_mma_levels(const void *d_desc, int64_t n, const float *cent, const uint8_
         if (e && atoi(e) >= 1 && atoi(e) <= 8) { ctas10 = atoi(e); ctas16 = atoi(e) < 7 ? atoi(e) : 7; }
         e = getenv("VT_MMA_DEFER_MIN");
         if (e) defer_min = atoll(e);
+        e = getenv("VT_MMA_PAIR_MIN");                            // <= 0 switches the two-level kernel off
+        if (e) pair_min = atoll(e) > 0 ? atoll(e) : ((int64_t)1 << 62);
         VT_CUDA(cudaFuncSetAttribute(level_mma_kernel<7, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      MM_A_BYTES + PlaneCfg<16>::B_BYTES + 1024));
         VT_CUDA(cudaFuncSetAttribute(level_mma_kernel<8, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      MM_A_BYTES + PlaneCfg<10>::B_BYTES + 1024));
         attr_set = true;
+    }
+    if (n >= pair_min && depth >= 2) {
+        // two levels per launch (vt_quantize_pair.cu): every row is read from DRAM once per PAIR of levels
+        const int rc = vt_mma_levels_paired(d_desc, n, cent, internal, ref_id, k, depth, leaf, word, stats, bimg, cn, sortwork,
+                                            n >= defer_min, s, ev, &n_ev);
+        if (n_ev_io) *n_ev_io = n_ev;
+        return rc;
     }
     const int64_t want = (n + MM_TILE - 1) / MM_TILE, cap = (int64_t)vt_sm_count() * (narrow ? ctas10 : ctas16);
     const int blocks = (int)(want < cap ? want : cap);
@@ -897,14 +829,16 @@ int vt_mma_levels(const void *d_desc, int64_t n, const float *cent, const uint8_
 
 int vt_quantize_mma_impl(const void *d_desc, int64_t n, const float *cent, const uint8_t *internal, const int32_t *ref_id,
                          int k, int depth, int32_t *leaf, int32_t *word, uint64_t *stats, void *work, cudaStream_t s,
-                         cudaEvent_t *ev)
+                         cudaEvent_t *ev, int *n_ev_out = nullptr)
 {
     int n_ev = 0;
     if (ev) VT_CUDA(cudaEventRecord(ev[n_ev++], s));           // the first stage includes the plane preparation
     int rc = vt_mma_prepare(cent, k, depth, work, stats, s);
     if (rc != VT_OK) return rc;
-    return vt_mma_levels(d_desc, n, cent, internal, ref_id, k, depth, leaf, word, stats, work,
-                         (uint8_t *)work + vt_mma_prepared_bytes(k, depth), s, ev, &n_ev);
+    rc = vt_mma_levels(d_desc, n, cent, internal, ref_id, k, depth, leaf, word, stats, work,
+                       (uint8_t *)work + vt_mma_prepared_bytes(k, depth), s, ev, &n_ev);
+    if (n_ev_out) *n_ev_out = n_ev;
+    return rc;
 }
 
 // Same contract as vt_quantize_sorted (bit-identical ids); tensor-core distance step.
@@ -938,13 +872,16 @@ extern "C" int vt_quantize_mma_profile(const void *d_desc, int dtype, int64_t n,
     cudaEvent_t ev[40];
     const int n_ev = 2 * depth;
     for (int i = 0; i < n_ev; ++i) VT_CUDA(cudaEventCreate(&ev[i]));
+    int n_used = 0;
     int rc = vt_quantize_mma_impl(d_desc, n, d_centroids, d_internal, d_ref_id, k, depth, d_leaf_heap, d_word, d_stats,
-                                  d_work, (cudaStream_t)stream, ev);
-    if (rc == VT_OK && cudaEventSynchronize(ev[n_ev - 1]) != cudaSuccess) rc = VT_ECUDA;
+                                  d_work, (cudaStream_t)stream, ev, &n_used);
+    // (the two-levels-per-launch path records one stage per launch: entries beyond its stages stay 0)
+    if (rc == VT_OK && cudaDeviceSynchronize() != cudaSuccess) rc = VT_ECUDA;
     for (int l = 0; l < depth && rc == VT_OK; ++l) {
-        cudaEventElapsedTime(&h_level_ms[l], ev[2 * l], ev[2 * l + 1]);
+        h_level_ms[l] = 0.f;
         h_sort_ms[l] = 0.f;
-        if (l + 1 < depth) cudaEventElapsedTime(&h_sort_ms[l], ev[2 * l + 1], ev[2 * l + 2]);
+        if (2 * l + 1 < n_used) cudaEventElapsedTime(&h_level_ms[l], ev[2 * l], ev[2 * l + 1]);
+        if (2 * l + 2 < n_used) cudaEventElapsedTime(&h_sort_ms[l], ev[2 * l + 1], ev[2 * l + 2]);
     }
     for (int i = 0; i < n_ev; ++i) cudaEventDestroy(ev[i]);
     return rc;

@@ -96,7 +96,8 @@ score_shard_kernel(const uint32_t *__restrict__ post_off, const uint2 *__restric
                    const double *__restrict__ img_rnorm, int64_t n_img, int64_t n_ref, int n_shards,
                    const int64_t *__restrict__ q_off, const int32_t *__restrict__ q_node,
                    const float *__restrict__ q_val, int64_t n_query, int topk, double *__restrict__ out_key,
-                   int32_t *__restrict__ out_id, double *__restrict__ all_key, const uint8_t *__restrict__ shard_empty)
+                   int32_t *__restrict__ out_id, double *__restrict__ all_key, const uint8_t *__restrict__ shard_empty,
+                   const int32_t *__restrict__ seed, int64_t seed_stride)
 {
     constexpr int PER = R / SC_THREADS;
     extern __shared__ unsigned char s_raw[];
@@ -115,8 +116,10 @@ score_shard_kernel(const uint32_t *__restrict__ post_off, const uint2 *__restric
         const int n_here = (int)((n_img - img0) < R ? (n_img - img0) : R);
         // images the query does not touch have key 0 without looking at their norm -- unless the shard
         // holds images without descriptors (key -1, score 1e6), which only the norm reveals
-        const bool lazy_norm = !all_key && shard_empty && !shard_empty[shard];
-        for (int t = threadIdx.x; t < R; t += SC_THREADS) s_acci[t] = 0;
+        const bool lazy_norm = !all_key && !seed && shard_empty && !shard_empty[shard];
+        // tf mode may be seeded with the dots over the dense top levels (vt_dense_dots): the postings add the rest
+        for (int t = threadIdx.x; t < R; t += SC_THREADS)
+            s_acci[t] = (seed && t < n_here) ? seed[(size_t)q * seed_stride + img0 + t] : 0;
         __syncthreads();
         // accumulate: one LANE per query word (32 independent row-pointer / posting fetches in flight
         // per warp -- the walk is latency bound, not bandwidth bound); posting lists longer than
@@ -545,7 +548,7 @@ static int launch_score(const uint32_t *post_off, const void *postings, const do
     const int64_t cap = (int64_t)vt_sm_count() * 2 * 8;
     kern<<<(int)(pairs < cap ? pairs : cap), SC_THREADS, smem, s>>>(post_off, (const uint2 *)postings, img_rnorm, n_img, n_ref,
                                                                     n_shards, q_off, q_node, q_val, n_query, topk, out_key,
-                                                                    out_id, all_key, shard_empty);
+                                                                    out_id, all_key, shard_empty, nullptr, 0);
     VT_LAUNCH_CHECK();
     return VT_OK;
 }
@@ -647,6 +650,31 @@ extern "C" int vt_topk_merge_scored(const double *d_in_key, const int32_t *d_in_
     const int64_t cap = (int64_t)vt_sm_count() * 8;
     topk_merge_scored_kernel<<<(int)(n_query < cap ? n_query : cap), SC_THREADS, smem, (cudaStream_t)stream>>>(
         d_in_key, d_in_id, d_in_score, n_query, n_cand, topk, d_out_key, d_out_id, d_out_score);
+    VT_LAUNCH_CHECK();
+    return VT_OK;
+}
+
+// vt_score_topk (tf mode, exhaustive selection) whose shard accumulators start from d_seed[q * seed_stride + img]
+// instead of zero: the int32 dots over the dense top levels of an all-nodes index (vt_dense_dots, csrc/vt_dense.cu);
+// the postings then only hold the deep levels.
+extern "C" int vt_score_topk_seeded(const uint32_t *d_post_off, const void *d_postings, const double *d_img_rnorm,
+                                    int64_t n_img, int64_t n_ref, const int64_t *d_q_off, const int32_t *d_q_node,
+                                    const float *d_q_val, int64_t n_query, int topk, const int32_t *d_seed,
+                                    int64_t seed_stride, double *d_shard_key, int32_t *d_shard_id, double *d_all_key,
+                                    void *stream)
+{
+    VT_CHECK_ARG(n_img > 0 && n_ref > 0 && n_query >= 0 && d_img_rnorm && d_seed && seed_stride >= n_img, "bad arguments");
+    VT_CHECK_ARG(topk >= 1 && topk <= SC_MAXK, "topk out of range");
+    if (n_query == 0) return VT_OK;
+    constexpr int R = 8192;
+    const int n_shards = (int)((n_img + R - 1) / R);
+    auto kern = score_shard_kernel<VT_SCORE_TF_L2, R>;
+    const size_t smem = (size_t)R * 12;
+    VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t pairs = n_query * n_shards, cap = (int64_t)vt_sm_count() * 2 * 8;
+    kern<<<(int)(pairs < cap ? pairs : cap), SC_THREADS, smem, (cudaStream_t)stream>>>(
+        d_post_off, (const uint2 *)d_postings, d_img_rnorm, n_img, n_ref, n_shards, d_q_off, d_q_node, d_q_val, n_query, topk,
+        d_shard_key, d_shard_id, d_all_key, nullptr, d_seed, seed_stride);
     VT_LAUNCH_CHECK();
     return VT_OK;
 }

@@ -27,7 +27,7 @@ from .dataset import Dataset
 
 
 class Database(object):
-    def __init__(self, dataset, encoder, *, weighting="tf", norm="l2"):
+    def __init__(self, dataset, encoder, *, weighting="tf", norm="l2", comm=None):
         # public:
         if isinstance(dataset, Dataset):
             self.dataset = dataset
@@ -41,14 +41,20 @@ class Database(object):
         if weighting == "tf" and norm != "l2":
             raise ValueError("the reference's tf scoring is L2 only; use weighting='tfidf' for L1")
         self.weighting, self.norm = weighting, norm
+        # multi-GPU (one process per GPU): ``comm`` is a ``dist.Comm``; the images are sharded by id over its ranks,
+        # every rank indexes its own range and ``retrieve_batch`` merges the per-rank top-k lists
+        self.comm = comm if comm is not None and getattr(comm, "world", 1) > 1 else None
 
         # private:
-        self._rows = {}           # image path -> row in the indexed CSR
-        self._host = None         # host copy of the forward CSR (row_off, node, count)
+        self._rows = {}           # image path -> row in this rank's indexed CSR
+        self._n_images = 0        # images of the whole (global) database
+        self._img_base = 0        # global index of this rank's first image
+        self._row_off_host = None  # host copy of the row pointers only (8 B per image); entries are fetched on demand
         self._csr = None          # device forward CSR of the indexed images
         self._index = None        # device inverted file
         self._weights = None      # tf-idf modes: dict(idf, img_rnorm, norm), binary64 device tensors
-        self._extra = {}          # path -> (nodes, counts) of non-indexed images (queries)
+        self._extra = {}          # path -> (nodes, counts) of non-indexed images (host, for embedding())
+        self._extra_csr = {}      # path -> (device CSR of the batch it was encoded in, row) of non-indexed queries
         # dense path (encoders without encode_batch)
         self._dense = not hasattr(encoder, "encode_batch")
         self._dense_unit = None   # device float64 [N, D]: L2-normalised embeddings (NaN rows for zero vectors)
@@ -64,29 +70,59 @@ class Database(object):
     def _descriptors(self, image_path):
         return np.asarray(self.encoder.descriptor(self.dataset.read_image(image_path)))
 
+    def _load_batch(self, paths, slot):
+        """Loader thread: read the images of one batch, run the descriptor and pack the rows into a pinned
+        staging buffer (two alternating slots), while the device encodes the previous batch."""
+        feats = [self._descriptors(p) for p in paths]
+        return self.encoder.stage_host(feats, slot)
+
     def index(self, batch_images=4096):
         """Encode every dataset image (in ``image_paths`` order) and build the inverted file
-        (database.py:36-44).  Images are read, staged and encoded ``batch_images`` at a time, so the
-        descriptors of the whole dataset are never resident at once; only the bag-of-words CSR
-        (8 B per posting) accumulates on the device."""
-        import torch
+        (database.py:36-44).  Images are read, staged and encoded ``batch_images`` at a time: a loader thread
+        reads and packs batch b+1 into pinned memory while the device quantises and encodes batch b, so the
+        descriptors of the whole dataset are never resident at once and host work overlaps device work; only the
+        bag-of-words CSR (8 B per posting) accumulates on the device.  With ``comm`` every rank indexes its own
+        contiguous image range and the document frequencies are all-reduced (tf-idf)."""
+        from concurrent.futures import ThreadPoolExecutor
+        from .dist import shard_range
         paths = list(self.dataset.image_paths)
         if self._dense:
             return self._index_dense(paths)
+        lo, hi = (0, len(paths)) if self.comm is None else shard_range(len(paths), self.comm.rank, self.comm.world)
+        local = paths[lo:hi]
         step = max(1, int(batch_images))
+        batches = [local[b0:b0 + step] for b0 in range(0, max(len(local), 1), step)]
         parts = []
-        for b0 in range(0, max(len(paths), 1), step):
-            feats = [self._descriptors(p) for p in paths[b0:b0 + step]]
-            parts.append(self.encoder.encode_batch(feats, want_df=True))
-        csr = engine.concat_csr(parts)
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            pending = pool.submit(self._load_batch, batches[0], 0)
+            for bi in range(len(batches)):
+                staged = pending.result()
+                if bi + 1 < len(batches):
+                    pending = pool.submit(self._load_batch, batches[bi + 1], (bi + 1) & 1)
+                parts.append(self.encoder.encode_batch(None, want_df=True, staged=staged))
+        self._adopt(engine.concat_csr(parts), {p: i for i, p in enumerate(local)}, len(paths), lo)
+        return
+
+    def _adopt(self, csr, rows, n_images, img_base, df=None):
+        """device forward CSR of this rank's images -> inverted file, weights, bookkeeping."""
         n_ref = self.encoder.flat.n_ref
         self._csr = csr
-        self._index = engine.build_index(csr, n_ref)
-        self._set_weights(csr["df"], len(paths))
-        self._rows = {p: i for i, p in enumerate(paths)}
-        self._host = (csr["row_off"].cpu().numpy(), csr["node"].cpu().numpy(), csr["count"].cpu().numpy())
+        self._rows, self._n_images, self._img_base = rows, int(n_images), int(img_base)
+        self._row_off_host = csr["row_off"].cpu().numpy()
+        self._index = engine.build_index(csr, n_ref) if csr["n_img"] > 0 else None
+        if self.weighting == "tfidf":
+            import torch
+            if df is None:
+                df = csr["df"]
+            if df is None:
+                df = torch.bincount(csr["node"].long(), minlength=n_ref).to(torch.int32)
+            df = df.clone()
+            if self.comm is not None:
+                self.comm.all_reduce(df)                          # document frequencies over ALL images (8e row 3)
+            self._set_weights(df, n_images)
+        else:
+            self._weights = None
         self._extra = {}
-        return
 
     def _set_weights(self, df, n_images):
         """tf-idf modes: idf_n = ln(N / df_n) and the per-image weighted norms, binary64, on the device.  The
@@ -98,7 +134,9 @@ class Database(object):
         self._weights = dict(idf=idf, norm=self.norm, img_rnorm=engine.weighted_rnorm(self._csr, idf, self.norm))
 
     def is_indexed(self, image_path):
-        return image_path in self._rows
+        if self.comm is None:
+            return image_path in self._rows
+        return self._n_images > 0 and image_path in set(self.dataset.image_paths)
 
     # ------------------------------------------------------------------ dense encoders
     def _device(self):
@@ -169,9 +207,10 @@ class Database(object):
 
     def _sparse(self, image_path):
         if image_path in self._rows:
-            ro, node, count = self._host
+            # one image's entries, fetched from the device CSR on demand (no host mirror of the whole index)
             i = self._rows[image_path]
-            return node[ro[i]:ro[i + 1]], count[ro[i]:ro[i + 1]]
+            b, e = int(self._row_off_host[i]), int(self._row_off_host[i + 1])
+            return self._csr["node"][b:e].cpu().numpy(), self._csr["count"][b:e].cpu().numpy()
         if image_path not in self._extra:
             csr = self.encoder.encode_batch([self._descriptors(image_path)])
             self._extra[image_path] = (csr["node"].cpu().numpy(), csr["count"].cpu().numpy())
@@ -196,33 +235,95 @@ class Database(object):
 
     # ------------------------------------------------------------------ retrieval
     def _query_csr(self, query_paths):
-        """CSR batch (device) for a list of image paths; indexed images reuse their rows."""
+        """CSR batch (device) for a list of image paths, plus the permutation that puts the rows back into query
+        order.  Images indexed on this rank reuse their rows (gathered on the device); all others are encoded in
+        ONE batch (pinned staging, like ``index``)."""
         import torch
-        dev = self._csr["row_off"].device
-        rows = [self._sparse(p) for p in query_paths]
-        sizes = torch.tensor([len(r[0]) for r in rows], dtype=torch.int64)
-        off = torch.zeros(len(rows) + 1, dtype=torch.int64)
-        off[1:] = torch.cumsum(sizes, 0)
-        node = np.concatenate([r[0] for r in rows]) if rows else np.zeros(0, np.int32)
-        count = np.concatenate([r[1] for r in rows]) if rows else np.zeros(0, np.int32)
-        sumsq = torch.tensor([int((r[1].astype(np.int64) ** 2).sum()) for r in rows], dtype=torch.int64)
-        q = dict(row_off=off.to(dev), node=torch.from_numpy(node.astype(np.int32)).to(dev),
-                 count=torch.from_numpy(count.astype(np.int32)).to(dev), sumsq=sumsq.to(dev),
-                 n_img=len(rows), nnz=int(off[-1]))
-        return q
+        dev = torch.device(self.encoder.device)
+        known = [(qi, self._rows[p]) for qi, p in enumerate(query_paths) if p in self._rows]
+        fresh = [(qi, p) for qi, p in enumerate(query_paths) if p not in self._rows]
+        parts, order = [], []
+        if known:
+            parts.append(engine.csr_rows(self._csr, torch.tensor([r for _, r in known], dtype=torch.int64, device=dev)))
+            order += [qi for qi, _ in known]
+        if fresh:
+            uniq = {}
+            for qi, p in fresh:
+                uniq.setdefault(p, []).append(qi)
+            missing = [p for p in uniq if p not in self._extra_csr]
+            if missing:
+                staged = self._load_batch(missing, 0)
+                csr = self.encoder.encode_batch(None, staged=staged)
+                for j, p in enumerate(missing):
+                    self._extra_csr[p] = (csr, j)
+            # rows of the (possibly several) cached encode batches, in `fresh` order
+            by_batch = {}
+            for qi, p in fresh:
+                csr, j = self._extra_csr[p]
+                by_batch.setdefault(id(csr), (csr, []))[1].append((qi, j))
+            for csr, pairs in by_batch.values():
+                parts.append(engine.csr_rows(csr, torch.tensor([j for _, j in pairs], dtype=torch.int64, device=dev)))
+                order += [qi for qi, _ in pairs]
+        if not parts:
+            z = torch.zeros(1, dtype=torch.int64, device=dev)
+            q = dict(row_off=z, node=torch.zeros(0, dtype=torch.int32, device=dev),
+                     count=torch.zeros(0, dtype=torch.int32, device=dev), sumsq=torch.zeros(0, dtype=torch.int64, device=dev),
+                     df=None, n_img=0, nnz=0)
+        else:
+            q = engine.concat_csr(parts)
+        back = np.empty(len(order), np.int64)
+        back[np.asarray(order, np.int64)] = np.arange(len(order))
+        return q, back
+
+    def _score_local(self, q, k, return_all):
+        """this rank's top-k over its own image shard (ids local); an empty shard yields empty lists"""
+        import torch
+        if self._index is None:
+            dev = q["row_off"].device
+            nq = q["n_img"]
+            return dict(key=torch.full((nq, k), -2.0, dtype=torch.float64, device=dev),
+                        id=torch.full((nq, k), -1, dtype=torch.int32, device=dev),
+                        score=torch.full((nq, k), 1e6, dtype=torch.float64, device=dev),
+                        all_key=torch.zeros((nq, 0), dtype=torch.float64, device=dev) if return_all else None)
+        return engine.score(self._index, q, k, self._mode(), want_all=return_all, weights=self._weights)
+
+    def _all_keys_global(self, local_keys):
+        """[Q, n_local] rank keys of every rank -> [Q, n_images] in global image order"""
+        import torch
+        if self.comm is None:
+            return local_keys
+        from .dist import shard_range
+        width = max(shard_range(self._n_images, r, self.comm.world)[1] - shard_range(self._n_images, r, self.comm.world)[0]
+                    for r in range(self.comm.world))
+        pad = torch.full((local_keys.shape[0], width), -2.0, dtype=torch.float64, device=local_keys.device)
+        pad[:, :local_keys.shape[1]] = local_keys
+        allk = self.comm.all_gather(pad)
+        cols = []
+        for r in range(self.comm.world):
+            lo, hi = shard_range(self._n_images, r, self.comm.world)
+            cols.append(allk[r][:, :hi - lo])
+        return torch.cat(cols, dim=1)
 
     def retrieve_batch(self, query_paths, k=10, return_all=False):
         """Top-k image indices (positions in ``dataset.image_paths``) and scores per query.
-        Returns (ids [Q, k] int32, scores [Q, k] float64[, all_keys [Q, n_img]])."""
+        Returns (ids [Q, k] int32, scores [Q, k] float64[, all_keys [Q, n_img]]).  With ``comm`` every rank
+        passes the same queries and gets the same, global, result."""
         if self._dense:
             return self._retrieve_batch_dense(query_paths, k, return_all)
-        if self._index is None:
+        if self._csr is None:
             self.index()
-        q = self._query_csr(list(query_paths))
-        out = engine.score(self._index, q, k, self._mode(), want_all=return_all, weights=self._weights)
-        ids, sc = out["id"].cpu().numpy(), out["score"].cpu().numpy()
+        query_paths = list(query_paths)
+        q, back = self._query_csr(query_paths)
+        if self.comm is None:
+            out = self._score_local(q, k, return_all)
+            ids_t, sc_t = out["id"], out["score"]
+        else:
+            from . import dist as vdist
+            out = self._score_local(q, k, return_all)
+            ids_t, sc_t, _ = vdist.retrieve_sharded(lambda: out, self._img_base, k, self.comm)
+        ids, sc = ids_t.cpu().numpy()[back], sc_t.cpu().numpy()[back]
         if return_all:
-            return ids, sc, out["all_key"].cpu().numpy()
+            return ids, sc, self._all_keys_global(out["all_key"]).cpu().numpy()[back]
         return ids, sc
 
     def _scores_from_keys(self, keys, q_sumsq):
@@ -233,7 +334,7 @@ class Database(object):
                 if q_sumsq == 0:
                     return np.full(keys.shape, 1e6)
                 s = np.sqrt(np.maximum(0.0, 2.0 - 2.0 * keys / np.sqrt(float(q_sumsq))))
-                sumsq = self._index["sumsq"].cpu().numpy()
+                sumsq = self._sumsq_global()
                 dot = keys * np.sqrt(sumsq.astype(np.float64))
                 s[(sumsq == q_sumsq) & (np.abs(dot - q_sumsq) < 0.5)] = 0.0
             elif mode == nat.SCORE_W_L2:
@@ -242,6 +343,13 @@ class Database(object):
                 s = np.maximum(0.0, 2.0 - keys)
         s[keys < 0] = 1e6                                        # images without descriptors: NaN -> 1e6
         return s
+
+    def _sumsq_global(self):
+        import torch
+        local = self._csr["sumsq"][:self._csr["n_img"]].to(torch.float64)
+        if self.comm is None:
+            return local.cpu().numpy().astype(np.int64)
+        return self._all_keys_global(local[None, :])[0].cpu().numpy().astype(np.int64)
 
     def retrieve(self, query_image_path, n=4):
         """All dataset images ordered by ascending score, as a dict path -> score
@@ -253,11 +361,11 @@ class Database(object):
             scores = self._dense_scores(self._dense_query_rows([query_image_path]))[0].cpu().numpy()
             order = np.argsort(scores, kind="stable")
             return {paths[i]: float(scores[i]) for i in order}
-        if self._index is None:
+        if self._csr is None:
             self.index()
-        q = self._query_csr([query_image_path])
-        out = engine.score(self._index, q, 1, self._mode(), want_all=True, weights=self._weights)
-        keys = out["all_key"][0].cpu().numpy()
+        q, _ = self._query_csr([query_image_path])
+        out = self._score_local(q, 1, True)
+        keys = self._all_keys_global(out["all_key"])[0].cpu().numpy()
         scores = self._scores_from_keys(keys, int(q["sumsq"][0].item()))
         order = np.argsort(scores, kind="stable")
         return {paths[i]: float(scores[i]) for i in order}
@@ -292,19 +400,20 @@ class Database(object):
         ro, node, count = host
         dev = torch.device(self.encoder.device)
         n_img = len(ro) - 1
-        n_ref = self.encoder.flat.n_ref
         # per-image sum of squares from an exact int64 prefix sum (np.add.reduceat raises when trailing images
         # have no descriptors: its last index then equals len(count))
         prefix = np.concatenate([np.zeros(1, np.int64), np.cumsum(count.astype(np.int64) ** 2)])
         sumsq = prefix[ro[1:]] - prefix[ro[:-1]]
-        csr = dict(row_off=torch.from_numpy(ro).to(dev), node=torch.from_numpy(node).to(dev),
-                   count=torch.from_numpy(count).to(dev), sumsq=torch.from_numpy(sumsq).to(dev),
-                   n_img=n_img, nnz=len(node), df=None)
-        self._rows, self._host, self._csr = rows, host, csr
-        self._index = engine.build_index(csr, n_ref)
-        if self.weighting == "tfidf":
-            self._set_weights(torch.bincount(csr["node"].long(), minlength=n_ref).to(torch.int32), n_img)
-        self._extra = {}
+        csr = dict(row_off=torch.from_numpy(np.ascontiguousarray(ro, np.int64)).to(dev),
+                   node=torch.from_numpy(np.ascontiguousarray(node, np.int32)).to(dev),
+                   count=torch.from_numpy(np.ascontiguousarray(count, np.int32)).to(dev),
+                   sumsq=torch.from_numpy(sumsq).to(dev), n_img=n_img, nnz=len(node), df=None)
+        self._adopt(csr, rows, n_img, 0)
+
+    def _host_csr(self):
+        """host copy of the forward CSR (made when saving; not kept)"""
+        c = self._csr
+        return (c["row_off"].cpu().numpy(), c["node"].cpu().numpy(), c["count"].cpu().numpy())
 
     def save(self, path=None, reference_format=False, key=None):
         """``index.pickle`` (database.py:83-91).  Default: the forward CSR of the indexed images.
@@ -320,7 +429,9 @@ class Database(object):
                 raise ValueError("dense reference-format index would exceed 2 GiB; use the CSR format")
             payload = {key(p): self.embedding(p) for p in self._rows}
         else:
-            payload = dict(rows=self._rows, host=self._host, weighting=self.weighting, norm=self.norm)
+            if self.comm is not None:
+                raise NotImplementedError("save() of a sharded database: save per rank with comm=None databases")
+            payload = dict(rows=self._rows, host=self._host_csr(), weighting=self.weighting, norm=self.norm)
         with open(os.path.join(path, "index.pickle"), "wb") as f:
             pickle.dump(payload, f)
         return True

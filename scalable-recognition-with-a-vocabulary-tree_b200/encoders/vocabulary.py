@@ -26,7 +26,8 @@ from ..tree import FlatTree
 
 
 class VocabularyTree(object):
-    def __init__(self, n_branches, depth, descriptor, *, n_iter=10, all_nodes=True, min_level=0, device="cuda"):
+    def __init__(self, n_branches, depth, descriptor, *, n_iter=10, all_nodes=True, min_level=0, device="cuda",
+                 comm=None):
         self.n_branches = n_branches
         self.depth = depth
         self.descriptor = descriptor
@@ -35,7 +36,12 @@ class VocabularyTree(object):
         self.all_nodes = all_nodes          # reference semantics: count every node on the path
         self.min_level = min_level          # level mask: nodes above this level carry weight 0
         self.device = device
+        # multi-GPU build (one process per GPU): ``fit`` then takes THIS RANK'S shard of the descriptors (contiguous
+        # ranges of the global row order, rank by rank) and every rank ends with the same tree, bit for bit
+        self.comm = comm if comm is not None and getattr(comm, "world", 1) > 1 else None
         # private
+        self._pinned = {}                   # staging slot -> pinned host buffer (Database.index double buffering)
+        self._pinned_free = {}              # staging slot -> CUDA event: the slot's last upload has completed
         self._flat = None                   # FlatTree
         self._propagated = {}               # image sha1 -> (node ids int32, counts int32)
         self._views = {}
@@ -105,7 +111,7 @@ class VocabularyTree(object):
         features = np.asarray(features) if not hasattr(features, "device") else features
         desc, d = engine.stage(features, self.device, prefer_bytes=True)
         self.build_log = []
-        self._flat = engine.build_tree(desc, d, self.n_branches, self.depth, n_iter=self.n_iter,
+        self._flat = engine.build_tree(desc, d, self.n_branches, self.depth, n_iter=self.n_iter, comm=self.comm,
                                        log=lambda **kw: self.build_log.append(kw))
         self._views = {}
         self._propagated = {}
@@ -137,19 +143,52 @@ class VocabularyTree(object):
         return path[path.index(node):]
 
     # ------------------------------------------------------------------ encoding
-    def encode_batch(self, images, want_df=False, all_nodes=None):
-        """Bag-of-words CSR (device tensors) for a list of descriptor arrays."""
+    def stage_host(self, images, slot=0):
+        """Pack a list of descriptor arrays into one pinned host buffer (``slot`` selects one of the alternating
+        staging buffers) -> dict(rows, sizes).  Runs on a loader thread in ``Database.index`` while the device
+        works on the previous batch; the upload from pinned memory is then a true asynchronous copy."""
+        import torch
+        d = self.flat.D
+        arrs = [np.asarray(a) for a in images]
+        sizes = [int(a.shape[0]) for a in arrs]
+        total = int(sum(sizes))
+        as_bytes = all(a.dtype == np.uint8 for a in arrs if a.shape[0] > 0)
+        dtype = torch.uint8 if as_bytes else torch.float32
+        ev = self._pinned_free.get(slot)
+        if ev is not None:
+            ev.synchronize()                                   # the previous upload from this slot has finished
+        buf = self._pinned.get(slot)
+        if buf is None or buf.dtype != dtype or buf.shape[0] < total or buf.shape[1] != d:
+            cap = max(total, 1) if buf is None else max(total, int(buf.shape[0] * 1.5))
+            buf = torch.empty((cap, d), dtype=dtype)
+            if torch.cuda.is_available():
+                buf = buf.pin_memory()
+            self._pinned[slot] = buf
+        view = buf.numpy()
+        o = 0
+        for a, n in zip(arrs, sizes):
+            if n:
+                np.copyto(view[o:o + n], a.reshape(n, d), casting="unsafe")
+                o += n
+        return dict(rows=buf[:total], sizes=sizes, slot=slot)
+
+    def encode_batch(self, images, want_df=False, all_nodes=None, staged=None):
+        """Bag-of-words CSR (device tensors) for a list of descriptor arrays (or a ``stage_host`` result)."""
         import torch
         t = self.flat
-        sizes = [int(np.asarray(a).shape[0]) for a in images]
-        d = t.D
-        nonempty = [np.asarray(a).reshape(-1, d) for a in images if np.asarray(a).shape[0] > 0]
-        off = torch.zeros(len(images) + 1, dtype=torch.int64)
+        if staged is None:
+            staged = self.stage_host(images, slot="sync")
+        sizes = staged["sizes"]
+        off = torch.zeros(len(sizes) + 1, dtype=torch.int64)
         off[1:] = torch.cumsum(torch.tensor(sizes, dtype=torch.int64), 0)
         dev = torch.device(self.device)
-        if nonempty:
-            allrows = np.concatenate(nonempty, axis=0)
-            desc, _ = engine.stage(allrows, dev)
+        if staged["rows"].shape[0] > 0:
+            desc, _ = engine.stage(staged["rows"], dev)
+            if dev.type == "cuda":
+                with torch.cuda.device(dev):
+                    ev = torch.cuda.Event()
+                    ev.record()
+                self._pinned_free[staged["slot"]] = ev
             words = engine.quantize(t.device(dev), t.k, t.depth, desc)
         else:
             words = torch.zeros(1, dtype=torch.int32, device=dev)

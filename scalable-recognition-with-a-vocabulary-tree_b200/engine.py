@@ -506,6 +506,19 @@ def concat_csr(parts: list) -> dict:
                 df=df, n_img=sum(p["n_img"] for p in parts), nnz=base)
 
 
+def csr_rows(csr: dict, rows: torch.Tensor) -> dict:
+    """Sub-CSR of the given rows (int64 device tensor, any order, repeats allowed), gathered on the device --
+    how ``Database.retrieve_batch`` reuses the rows of indexed images as queries without a host mirror."""
+    ro = csr["row_off"]
+    starts, lens = ro[rows], ro[rows + 1] - ro[rows]
+    off = torch.zeros(rows.numel() + 1, dtype=torch.int64, device=ro.device)
+    off[1:] = torch.cumsum(lens, 0)
+    total = int(off[-1].item())
+    idx = torch.repeat_interleave(starts - off[:-1], lens) + torch.arange(total, dtype=torch.int64, device=ro.device)
+    return dict(row_off=off, node=csr["node"][idx], count=csr["count"][idx], sumsq=csr["sumsq"][rows], df=None,
+                n_img=int(rows.numel()), nnz=total)
+
+
 def entry_rows(csr: dict) -> torch.Tensor:
     """image index of every CSR entry (int64 [nnz])."""
     n_img = csr["n_img"]

@@ -194,6 +194,25 @@ def test_tensor_core_deferred_output_on_small_batches(cuda):
     assert "6 passed" in out.stdout
 
 
+@pytest.mark.parametrize("defer", ["0", "1"])
+def test_two_levels_per_launch_on_small_batches(cuda, defer):
+    """Batches >= 2^20 rows take TWO tree levels per launch (vt_quantize_pair.cu: chunked, warp-specialised, the second
+    level re-gathers from L2).  A child process lowers that threshold to 1 row (VT_MMA_PAIR_MIN, read once by the
+    library) and repeats the tensor-core parity cases -- ragged trees, exact ties, k = 16, odd and even depths, near-tie
+    margins -- with the ids written directly (defer=0) and through the deferred (row, child) pairs (defer=1)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, VT_MMA_PAIR_MIN="1", VT_MMA_DEFER_MIN="1" if defer == "1" else str(1 << 40))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-x",
+                          "-m", "gpu", "-k", "test_quantize_tensor_core_path_matches_oracle or test_tensor_core_margin_under_near_ties",
+                          "-p", "no:cacheprovider"],
+                         env=env, cwd=root, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert "10 passed" in out.stdout
+
+
 def test_quantize_start_node_and_empty_batch(vt, cuda):
     torch = _torch()
     ft, g, meta, images = _flat_from_golden(vt, "small")
@@ -536,7 +555,7 @@ def test_streaming_index_equals_one_batch(vt, cuda):
     for weighting in ("tf", "tfidf"):
         same = [db for w, db in dbs if w == weighting]
         for db in same[1:]:
-            for a, b_ in zip(same[0]._host, db._host):
+            for a, b_ in zip(same[0]._host_csr(), db._host_csr()):
                 assert np.array_equal(a, b_)
             assert torch.equal(same[0]._csr["df"], db._csr["df"])
             ids0, sc0 = same[0].retrieve_batch(ds.image_paths, k=5)
@@ -784,7 +803,7 @@ def test_c1_full_pipeline_matches_reference(vt, cuda):
     db = vt.Database(ds, voc)
     db.index()
     touched = set((np.searchsorted(np.cumsum([len(i) for i in images]), diff, side="right")).tolist())
-    ro, node, count = db._host
+    ro, node, count = db._host_csr()
     dense = csr_to_dense(ro[:17], node, count, voc.flat.n_ref)
     for i in range(16):
         if i not in touched:

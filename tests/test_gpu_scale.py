@@ -1,0 +1,231 @@
+"""GPU: full-size certificates that do not need the CPU oracle, multi-GPU runs over NCCL, persistence corners.
+
+* build certificate at BASELINE configs[1] (10 M x 128, k=10, L=6): independent per-level checks with plain torch
+  integer arithmetic -- every level's member counts equal what the canonical descent of the finished tree gives
+  (final labels are the canonical argmin), and on every converged level each centre is (float)(sum / count) of
+  its members (exact integer sums);
+* NCCL: 2 ranks (when >= 2 GPUs are visible) drive the public classes -- sharded build, sharded tf and tf-idf
+  index, merged top-k -- and must reproduce the single-GPU results bit for bit;
+* VT_SLOW=1: the C oracle builds a 2 M-row, L=6 tree on the host and the GPU tree must equal it."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from oracle import vt_oracle as vo
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _level_of_heap(h, k, depth):
+    """level of heap indices (int64 tensor)"""
+    torch = _torch()
+    lvl = torch.zeros_like(h)
+    off = 0
+    for level in range(1, depth + 1):
+        off += k ** (level - 1)
+        lvl += (h >= off).to(h.dtype)
+    return lvl
+
+
+def _certificate(vt, cuda, n, k, depth, n_iter, seed):
+    torch = _torch()
+    cent0 = vt.synth.hierarchical_tree(k, depth, 128, seed=7, device=cuda)
+    x = vt.synth.descriptors_from_tree(cent0, k, depth, n, seed=seed)
+    del cent0
+    log = []
+    ft = vt.engine.build_tree(x, 128, k, depth, n_iter=n_iter, log=lambda **kw: log.append(kw))
+    td = ft.device(cuda)
+    _, heap = vt.engine.quantize(td, k, depth, x, want_heap=True)          # canonical descent of the finished tree
+    heap = heap.long()
+    count = torch.from_numpy(ft.count).to(cuda)
+    cent = td["centroids"]
+    stop_level = _level_of_heap(heap, k, depth)
+    checked_levels, converged_levels = 0, 0
+    for level in range(depth, 0, -1):
+        # ancestor at `level` of every row that reaches it
+        a = heap.clone()
+        steps = stop_level - level
+        for _ in range(depth):
+            up = steps > 0
+            a = torch.where(up, (a - 1) // k, a)
+            steps = steps - up.to(steps.dtype)
+        reach = stop_level >= level
+        o = vt.tree.level_offset(k, level)
+        n_l = k ** level
+        idx = (a[reach] - o)
+        got = torch.bincount(idx, minlength=n_l)
+        # (1) member counts of the build == counts under the canonical descent of the final centres
+        assert torch.equal(got, count[o:o + n_l]), "level %d: partition differs from the canonical argmin" % level
+        checked_levels += 1
+        conv = [l for l in log if l["level"] == level - 1]
+        if conv and conv[0]["converged"]:
+            # (2) converged level: every centre is (float)((double)sum / (double)count) of its members
+            sums = torch.zeros((n_l, 128), dtype=torch.int64, device=cuda)
+            rows = torch.nonzero(reach).flatten()
+            for c0 in range(0, rows.numel(), 1 << 20):
+                r = rows[c0:c0 + (1 << 20)]
+                sums.index_add_(0, a[r] - o, x[r].to(torch.int64))
+            has = got > 0
+            want = (sums[has].to(torch.float64) / got[has].to(torch.float64)[:, None]).to(torch.float32)
+            assert torch.equal(cent[o:o + n_l][has], want), "level %d: a centre is not the mean of its members" % level
+            converged_levels += 1
+    # (3) the partition is stable: internal nodes are exactly those with >= k members (vocabulary.py:55)
+    inner = vt.tree.level_offset(k, depth)
+    assert torch.equal(torch.from_numpy(ft.internal[:inner].astype(bool)).to(cuda),
+                       (count[:inner] >= k) & torch.from_numpy(ft.exists[:inner].astype(bool)).to(cuda))
+    return checked_levels, converged_levels, log
+
+
+def test_build_certificate_at_c2_size(vt, cuda):
+    """BASELINE configs[1]: 10 M descriptors, k=10, L=6, 10 Lloyd iterations."""
+    checked, converged, log = _certificate(vt, cuda, 10_000_000, 10, 6, 10, seed=4242)
+    assert checked == 6
+    assert converged >= 1, log           # the deep levels (a handful of members per cluster) reach their fixed point
+
+
+def test_build_certificate_converged_run(vt, cuda):
+    """Enough iterations for every level to reach its fixed point: the centroid check then covers the whole tree."""
+    checked, converged, log = _certificate(vt, cuda, 400_000, 10, 4, 200, seed=99)
+    assert checked == 4 and converged == 4, log
+
+
+@pytest.mark.slow
+def test_build_equals_oracle_at_2m_rows(vt, cuda):
+    """VT_SLOW=1: the C oracle (seeded exact Lloyd, binary64) builds k=10, L=6 on 2 M rows on the host cores."""
+    torch = _torch()
+    cent0 = vt.synth.hierarchical_tree(10, 6, 128, seed=7, device=cuda)
+    x = vt.synth.descriptors_from_tree(cent0, 10, 6, 2_000_000, seed=5)
+    ft = vt.engine.build_tree(x, 128, 10, 6, n_iter=10)
+    t = vo.build_tree(x.cpu().numpy(), 10, 6, 10)
+    assert np.array_equal(ft.exists, t["exists"]) and np.array_equal(ft.internal, t["internal"])
+    assert np.array_equal(ft.count, t["count"]) and np.array_equal(ft.centroids, t["centroids"])
+
+
+# ------------------------------------------------------------------------------------------ NCCL, 2 ranks
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _nccl_worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    import vtree_b200 as vt
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        comm = vt.dist.Comm()
+        rng = np.random.default_rng(3)
+        images = [np.clip(np.rint(rng.normal(90, 40, (int(rng.integers(40, 90)), 128))), 0, 255).astype(np.uint8)
+                  for _ in range(300)]
+        images[7] = images[5].copy()                                  # duplicate image: exact score ties
+        images[11] = np.zeros((0, 128), np.uint8)                     # image without descriptors
+        feats = np.concatenate(images)
+        lo, hi = vt.dist.shard_range(len(feats), rank, world)
+        res = {}
+        # sharded build through the public class == single-GPU build
+        voc_d = vt.encoders.VocabularyTree(6, 3, descriptor=lambda im: im, device=dev, comm=comm).fit(feats[lo:hi])
+        voc_1 = vt.encoders.VocabularyTree(6, 3, descriptor=lambda im: im, device=dev).fit(feats)
+        res["tree"] = bool(np.array_equal(voc_d.flat.centroids, voc_1.flat.centroids)
+                           and np.array_equal(voc_d.flat.internal, voc_1.flat.internal)
+                           and np.array_equal(voc_d.flat.count, voc_1.flat.count))
+        ds = vt.ArrayDataset(images)
+        queries = ds.image_paths[:40]
+        for weighting, norm in (("tf", "l2"), ("tfidf", "l2"), ("tfidf", "l1")):
+            db_d = vt.Database(ds, voc_d, weighting=weighting, norm=norm, comm=comm)
+            db_d.index(batch_images=64)
+            db_1 = vt.Database(ds, voc_1, weighting=weighting, norm=norm)
+            db_1.index()
+            ids_d, sc_d = db_d.retrieve_batch(queries, k=10)
+            ids_1, sc_1 = db_1.retrieve_batch(queries, k=10)
+            same_ids = bool(np.array_equal(ids_d, ids_1))
+            tol = 0.0 if weighting == "tf" else 1e-12
+            same_sc = bool(np.allclose(sc_d, sc_1, rtol=tol, atol=tol))
+            full_d = db_d.retrieve(queries[3])
+            full_1 = db_1.retrieve(queries[3])
+            same_full = list(full_d) == list(full_1)
+            if weighting == "tfidf":
+                same_full = same_full and bool(torch.equal(db_d._weights["idf"], db_1._weights["idf"]))
+            res["%s/%s" % (weighting, norm)] = same_ids and same_sc and same_full
+        out[rank] = res
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_over_nccl_equal_single_gpu(vt, cuda):
+    torch = _torch()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    out = mp.Manager().dict()
+    mp.spawn(_nccl_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    for r in range(2):
+        assert out.get(r) and all(out[r].values()), dict(out)
+
+
+# ------------------------------------------------------------------------------------------ persistence corner
+def test_save_load_with_trailing_images_without_descriptors(vt, cuda, tmp_path):
+    """np.add.reduceat raised when the LAST images were empty while earlier ones were not."""
+    rng = np.random.default_rng(1)
+    images = [rng.integers(0, 256, (30, 32), dtype=np.uint8) for _ in range(6)]
+    images += [np.zeros((0, 32), np.uint8), np.zeros((0, 32), np.uint8)]
+    voc = vt.encoders.VocabularyTree(3, 2, descriptor=lambda im: im).fit(np.concatenate(images))
+    ds = vt.ArrayDataset(images)
+    db = vt.Database(ds, voc)
+    db.index()
+    ids0, sc0 = db.retrieve_batch(ds.image_paths, k=4)
+    db.save(str(tmp_path))
+    db2 = vt.Database(ds, voc)
+    db2.load(str(tmp_path))
+    ids1, sc1 = db2.retrieve_batch(ds.image_paths, k=4)
+    assert np.array_equal(ids0, ids1) and np.array_equal(sc0, sc1)
+    assert (sc1[-1] == 1e6).all()                                    # NaN -> 1e6 (database.py:70)
+    db.save(str(tmp_path), reference_format=True, key=lambda p: p)
+    db3 = vt.Database(ds, voc)
+    db3.load(str(tmp_path), key=lambda p: p)
+    assert np.array_equal(db3.retrieve_batch(ds.image_paths, k=4)[0], ids0)
+
+
+def test_native_rank_merge_equals_test_double(vt, cuda):
+    """dist.merge_ranked (vt_topk_merge_scored) against the torch-sort restatement used in the gloo tests."""
+    torch = _torch()
+    from oracle_ops import merge_ranked_cpu
+    rng = np.random.default_rng(5)
+    w, q, k = 8, 50, 10
+    keys = np.round(rng.random((w, q, k)), 2)                        # coarse -> exact ties across ranks
+    ids = rng.permutation(w * q * k).reshape(w, q, k).astype(np.int32) % 100000
+    ids = np.stack([np.stack([rng.permutation(5000)[:k] + 5000 * r for _ in range(q)]) for r in range(w)]).astype(np.int32)
+    ids[3, :, 6:] = -1                                               # short lists
+    sc = np.sqrt(2 - 2 * keys)
+    a = merge_ranked_cpu(torch.from_numpy(keys), torch.from_numpy(ids), torch.from_numpy(sc), k)
+    b = vt.dist.merge_ranked(torch.from_numpy(keys).to(cuda), torch.from_numpy(ids).to(cuda),
+                             torch.from_numpy(sc).to(cuda), k)
+    assert torch.equal(a[0], b[0].cpu()) and torch.equal(a[1], b[1].cpu())
+
+
+def test_tensors_on_a_non_current_device_are_served(vt, cuda):
+    """kernels launched on the current device against another device's pointers.  Needs 2 GPUs."""
+    torch = _torch()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rng = np.random.default_rng(2)
+    x = rng.integers(0, 256, (5000, 128), dtype=np.uint8)
+    torch.cuda.set_device(0)
+    v0 = vt.encoders.VocabularyTree(4, 3, descriptor=lambda im: im, device="cuda:0").fit(x)
+    v1 = vt.encoders.VocabularyTree(4, 3, descriptor=lambda im: im, device="cuda:1").fit(x)
+    assert torch.cuda.current_device() == 0
+    assert np.array_equal(v0.flat.centroids, v1.flat.centroids)
+    assert np.array_equal(v0.quantize(x), v1.quantize(x))
