@@ -48,8 +48,8 @@ def parse():
     ap.add_argument("--words-per-image", type=int, default=1000)
     ap.add_argument("--engine", default="mma", choices=["mma", "simt"],
                     help="distance step of the sorted descent: tcgen05 INT8 tensor cores or FP32 SIMT")
-    ap.add_argument("--all-nodes-images", type=int, default=100_000)
-    ap.add_argument("--all-nodes-queries", type=int, default=500)
+    ap.add_argument("--all-nodes-images", type=int, default=1_000_000)
+    ap.add_argument("--all-nodes-queries", type=int, default=2048)
     ap.add_argument("--no-retrieval", action="store_true")
     ap.add_argument("--no-all-nodes", action="store_true")
     ap.add_argument("--no-build", action="store_true")
@@ -508,19 +508,46 @@ def bench_retrieval(args, torch, vt, engine, nat, dev, rank, world, comm, cent, 
             w[dst] = member_words[src]
         return w, torch.arange(len(ids) + 1, dtype=torch.int64, device=dev) * wpi
 
-    db_words, db_off = shard_words(lo, hi)
-    engine.encode(db_words[:wpi * 64], db_off[:65], tdev, DEPTH, flat.n_ref, all_nodes=all_nodes)      # warm-up
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    csr = engine.encode(db_words, db_off, tdev, DEPTH, flat.n_ref, all_nodes=all_nodes)
-    torch.cuda.synchronize()
-    t_encode = time.perf_counter() - t0
-    del db_words
     db = vt.Database(qds, voc, comm=comm)
-    t0 = time.perf_counter()
-    db._adopt(csr, {}, db_images, lo)                      # inverted file of this rank's shard (Database.index minus the image loop)
+    w0, o0 = shard_words(lo, min(hi, lo + 64))
+    engine.encode(w0, o0, tdev, DEPTH, flat.n_ref, all_nodes=all_nodes)                                # warm-up
     torch.cuda.synchronize()
-    t_invert = time.perf_counter() - t0
+    if all_nodes:
+        # the all-nodes forward CSR of 1 M images is 3.7 G entries: encode in batches of 64 K images, scatter the top
+        # levels into the dense block, keep only the deep levels' entries for the posting lists
+        builder = engine.DenseTopBuilder(tdev, DEPTH, flat.n_ref, hi - lo)
+        t_encode, nnz_total, sumsq = 0.0, 0, []
+        t0 = time.perf_counter()
+        for b0 in range(lo, hi, 65536):
+            b1 = min(hi, b0 + 65536)
+            wb, ob = shard_words(b0, b1)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            cb = engine.encode(wb, ob, tdev, DEPTH, flat.n_ref, all_nodes=True)
+            torch.cuda.synchronize()
+            t_encode += time.perf_counter() - t1
+            nnz_total += cb["nnz"]
+            sumsq.append(cb["sumsq"])
+            builder.add(cb, b0 - lo)
+            del wb, cb
+        dense = builder.finish()
+        assert dense is not None, "dense counts overflowed a byte"
+        db._adopt_dense(dense, torch.cat(sumsq), db_images, lo)
+        torch.cuda.synchronize()
+        t_invert = time.perf_counter() - t0 - t_encode
+        csr = dict(nnz=nnz_total)
+        del builder
+    else:
+        db_words, db_off = shard_words(lo, hi)
+        t0 = time.perf_counter()
+        csr = engine.encode(db_words, db_off, tdev, DEPTH, flat.n_ref, all_nodes=False)
+        torch.cuda.synchronize()
+        t_encode = time.perf_counter() - t0
+        del db_words
+        t0 = time.perf_counter()
+        db._adopt(csr, {}, db_images, lo)                  # inverted file of this rank's shard (Database.index minus the image loop)
+        torch.cuda.synchronize()
+        t_invert = time.perf_counter() - t0
     index = db._index
     topk = 10
 
@@ -564,7 +591,7 @@ def bench_retrieval(args, torch, vt, engine, nat, dev, rank, world, comm, cent, 
 
     # ---- N > 1: rank 0 recomputes on ONE GPU and the merged result must be identical -------------------------------
     same_as_single = None
-    if world > 1 and rank == 0:
+    if world > 1 and rank == 0 and not all_nodes:
         n_chk = min(q, 256)
         words_all, off_all = shard_words(0, db_images)
         csr1 = engine.encode(words_all, off_all, tdev, DEPTH, flat.n_ref, all_nodes=all_nodes)

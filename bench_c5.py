@@ -89,10 +89,13 @@ def main():
         if args.sample <= 20_000_000 else vt.synth.descriptors_from_tree(gen_cent, k, depth, hi_s - lo_s, seed=99 + rank)
     sync()
     t0 = time.perf_counter()
-    tree = engine.build_tree(sample, d, k, depth, n_iter=args.iters, comm=comm)
+    voc = vt.encoders.VocabularyTree(k, depth, descriptor=lambda im: im, n_iter=args.iters, all_nodes=False, device=dev,
+                                     comm=comm)
+    voc.fit(sample)                                        # top levels: all-reduce of integer sums; below: subtree ownership
     sync()
     t_build = tmax(time.perf_counter() - t0)
     del sample
+    tree = voc.flat
     tree_dev = tree.device(dev)
     checksum = int(tree_dev["centroids"].view(torch.int32).to(torch.int64).sum().item())
 
@@ -117,30 +120,29 @@ def main():
     off = torch.arange(n_mine + 1, dtype=torch.int64, device=dev) * wpi
     csr = engine.encode(words, off, tree_dev, depth, tree.n_ref, all_nodes=False)
     del words
-    index = engine.build_index(csr, tree.n_ref)
+    import numpy as np
+    db = vt.Database(vt.ArrayDataset([]), voc, comm=comm)
+    db._adopt(csr, {}, args.images, lo)                    # this rank's shard of the inverted file (Database.index minus the image loop)
     sync()
     t_index = tmax(time.perf_counter() - t0)
 
-    # ---- queries: the first images of every rank's first batch, regenerated everywhere ------------------
+    # ---- queries: the first images of every rank's first batch, regenerated everywhere, as HOST descriptor arrays ----
     per_rank = max(1, min(args.queries // world, bi))
-    q_words, q_ids = [], []
+    q_desc, q_ids = [], []
     for r in range(world):
         lo_r, hi_r = vt.dist.shard_range(args.images, r, world)
         nb = min(bi, hi_r - lo_r)
         x = batch_descriptors(lo_r // bi + r * 1_000_000, nb)[:per_rank * wpi]
-        q_words.append(engine.quantize(tree_dev, k, depth, x.contiguous()))
-        q_ids.append(torch.arange(lo_r, lo_r + per_rank, device=dev))
-    q_words, q_ids = torch.cat(q_words), torch.cat(q_ids)
-    nq = q_ids.numel()
-    qoff = torch.arange(nq + 1, dtype=torch.int64, device=dev) * wpi
-    qcsr = engine.encode(q_words, qoff, tree_dev, depth, tree.n_ref, all_nodes=False)
+        q_desc.append(x.cpu().numpy().reshape(per_rank, wpi, d))
+        q_ids.append(np.arange(lo_r, lo_r + per_rank))
+    q_desc, q_ids = np.concatenate(q_desc), np.concatenate(q_ids)
+    nq = len(q_ids)
+    names = ["q%07d" % i for i in range(nq)]
+    db.dataset = vt.ArrayDataset([q_desc[i] for i in range(nq)], names)
 
     def one_pass():
-        out = engine.score(index, qcsr, args.topk)
-        if world == 1:
-            return out["id"].to(torch.int64) + lo, out["score"]
-        ids, sc, _ = vt.dist.retrieve_sharded(lambda: out, lo, args.topk, comm)
-        return ids.to(torch.int64), sc
+        db._extra_csr.clear()
+        return db.retrieve_batch(names, k=args.topk)         # host descriptors -> quantise -> encode -> score -> all-gather + merge
 
     ids, sc = one_pass()
     sync()
@@ -150,7 +152,7 @@ def main():
         ids, sc = one_pass()
     sync()
     t_ret = tmax((time.perf_counter() - t0) / reps)
-    ok = bool((ids[:, 0] == q_ids).all().item() and (sc[:, 0] == 0).all().item())
+    ok = bool((ids[:, 0] == q_ids).all() and (sc[:, 0] == 0).all())
 
     if rank == 0:
         print(json.dumps({
@@ -165,6 +167,7 @@ def main():
             "encode_and_invert": {"seconds": t_index, "postings": int(csr["nnz"]) * world,
                                   "images_per_s": args.images / t_index},
             "retrieve": {"queries": nq, "topk": args.topk, "seconds_per_batch": t_ret, "queries_per_s": nq / t_ret,
+                         "api": "Database.retrieve_batch (host query descriptors in, host ids out)",
                          "every_query_finds_itself_first_with_score_0": ok},
         }))
     if world > 1:

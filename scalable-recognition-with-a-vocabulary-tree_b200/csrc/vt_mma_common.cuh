@@ -63,6 +63,45 @@ __device__ __forceinline__ void score_children(const uint32_t (&v)[N], const int
     }
 }
 
+// Same scores, ranked by a tournament instead of a serial best/second chain (the persistent two-level kernel has one
+// epilogue warp per scheduler, so the dependency chain of 10 compare-select steps would bound its tile rate).  Every
+// score is coarsened to 16 units and carries the child index in its low 4 bits: the minimum of the keys is the best
+// child (lowest index among equals), the second smallest key the runner-up.  best / second come back as the
+// coarsened scores, i.e. the true scores lie in [best, best + 15] and [second, second + 15]: callers subtract 15
+// from `second` before the contest test, so everything this ranking cannot separate goes to the binary64 recheck.
+template <int KP, int N>
+__device__ __forceinline__ void score_children_tree(const uint32_t (&v)[N], const int *s_cn, int &best, int &second, int &arg)
+{
+    int cq[16];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int4 t = reinterpret_cast<const int4 *>(s_cn)[g];
+        cq[4 * g] = t.x; cq[4 * g + 1] = t.y; cq[4 * g + 2] = t.z; cq[4 * g + 3] = t.w;
+    }
+    constexpr int H = KP / 2;
+    int lo[H], hi[H];
+#pragma unroll
+    for (int i = 0; i < H; ++i) {                                // slots >= k hold |c|^2 = 0x3fffffff and zero planes: never the minimum
+        const int s0 = cq[2 * i] - (int)((v[2 * i] << 8) + v[KP + 2 * i] + (v[2 * KP + 2 * i] >> 8));
+        const int s1 = cq[2 * i + 1] - (int)((v[2 * i + 1] << 8) + v[KP + 2 * i + 1] + (v[2 * KP + 2 * i + 1] >> 8));
+        const int k0 = (s0 & ~15) | (2 * i), k1 = (s1 & ~15) | (2 * i + 1);
+        lo[i] = min(k0, k1);
+        hi[i] = max(k0, k1);
+    }
+#pragma unroll
+    for (int stride = 1; stride < H; stride <<= 1) {
+#pragma unroll
+        for (int i = 0; i + stride < H; i += 2 * stride) {
+            const int la = lo[i], lb = lo[i + stride];
+            hi[i] = min(max(la, lb), min(hi[i], hi[i + stride]));
+            lo[i] = min(la, lb);
+        }
+    }
+    best = lo[0] & ~15;
+    second = hi[0] & ~15;
+    arg = lo[0] & 15;
+}
+
 // provable margin for the centroid rounding (|error| <= m (da + db), m = 2^-16 sqrt(128) 1.02, da <= db) plus
 // the three units of the 32-bit scores: "gap <= 2 m db", squared to avoid the square root.  xn = |x|^2.
 __device__ __forceinline__ bool contest_test(int best, int second, float xn)

@@ -28,33 +28,38 @@ int vt_mma_deferred_output(const uint32_t *rows, const uint32_t *child, int64_t 
 
 namespace {
 constexpr int LP_CHUNK = 1024;                  // rows a CTA takes through both levels together
-constexpr int LP_LAG = 2;                       // cp.async groups a producer keeps in flight behind the one it issues
-constexpr int LP_THREADS = 288;
-constexpr int LP_PRODUCERS = 128;
+constexpr int LP_THREADS = 544;                 // warps 0-7 epilogue (two groups), 8-15 producers, 16 MMA issuer
+constexpr int LP_PRODUCERS = 256;
+constexpr int LP_PER = LP_CHUNK / LP_PRODUCERS; // chunk rows per producer thread
 constexpr uint32_t LP_NONE = 0xffffffffu;
-constexpr int LPF_PHASE2 = 1, LPF_LAST_P1 = 2, LPF_END = 4;
-constexpr int LP_STOP = 31;                      // child-index value of a row that takes no part in phase 2 (k <= 16 < 31)
+constexpr int LPF_PHASE2 = 1, LPF_END = 4;
+constexpr int LP_STOP = 31;                     // child-index value of a row that takes no part in phase 2 (k <= 16 < 31)
 
-struct LpTile { int start, len; uint32_t node; int flags; int pos0; };
+struct LpTile { int start, len; uint32_t node; int flags; int pos0; int buf; };
 
 struct LpArgs {
     const uint8_t *desc; const uint32_t *perm; const uint32_t *parent; long long n;
     int level, phases, bits, k, mode;           // mode of the final phase: 0 = paths for the next launch, 1 = ids, 2 = (row, child) pairs
     long long n_heap;
     const float *cent; const uint8_t *internal; const int32_t *ref_id; const uint8_t *bimg; const int *cn32;
+    const uint32_t *cmask;                      // per node: bit c set <=> child c is internal (has children of its own)
     uint32_t *keys_out, *perm_out; int32_t *leaf_out, *word_out; unsigned long long *stats;
 };
 
 template <int KP>
 struct LpCfg {
     using P = PlaneCfg<KP>;
-    static constexpr int STAGES = KP <= 10 ? 4 : 3;
-    static constexpr int TMEM_ALLOC = KP <= 10 ? 128 : 256;     // STAGES x P::TMEM_COLS, power of two
+    static constexpr int STAGES = KP <= 10 ? 8 : 6;             // even: stage parity == epilogue group
+    static constexpr int LAG = STAGES - 2;                      // cp.async groups a producer keeps in flight
+    static constexpr int TMEM_ALLOC = KP <= 10 ? 256 : 512;     // >= STAGES x P::TMEM_COLS, power of two
     static constexpr int OFF_B = STAGES * MM_A_BYTES;
     static constexpr int OFF_CN = OFF_B + STAGES * P::B_BYTES;
-    static constexpr int OFF_LIST = OFF_CN + STAGES * 64;
-    // six u32 lists (c_row c_key c_node s_row s_key s_node), three u8 lists (c_cls s_d1, tile lengths)
-    static constexpr int SMEM = OFF_LIST + 6 * LP_CHUNK * 4 + 3 * LP_CHUNK + 1024;
+    static constexpr int OFF_FLAG = OFF_CN + STAGES * 64;
+    static constexpr int OFF_LIST = OFF_FLAG + 64;
+    // per chunk buffer: six u32 lists (c_row c_key c_node s_row s_key s_node) and two u8 lists (c_cls s_d1); two buffers
+    static constexpr int LIST_BYTES = 6 * LP_CHUNK * 4 + 2 * LP_CHUNK;
+    static constexpr int OFF_TL = OFF_LIST + 2 * LIST_BYTES;    // tile lengths of the phase being issued (u8)
+    static constexpr int SMEM = OFF_TL + LP_CHUNK + 1024;
 };
 
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
@@ -64,6 +69,11 @@ __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void lp_timeout(const char *what)
+{
+    printf("vt level_pair_kernel: %s timeout (block %d thread %d)\n", what, (int)blockIdx.x, (int)threadIdx.x);
+    __trap();
 }
 // spin with a watchdog: a protocol error must end the kernel with a trap, not hang the device
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
@@ -78,14 +88,18 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
         if ((spins & 1023u) == 1023u) {
             const long long t = clock64();
             if (t0 == 0) t0 = t;
-            else if (t - t0 > 8000000000ll) {                  // ~4 s
-                printf("vt level_pair_kernel: barrier timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-                __trap();
-            }
+            else if (t - t0 > 8000000000ll) lp_timeout("barrier");   // ~4 s
         }
     }
 }
-__device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ bool producers_all(bool pred)
+{
+    uint32_t r;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.and.pred p, 1, 256, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(r) : "r"((uint32_t)pred) : "memory");
+    return r != 0;
+}
 
 // Tile list of a node list in shared memory (one warp): maximal runs of equal node ids, cut every 128 rows.  The tiles
 // cover the list back to back, so only their lengths (minus one, a byte) are kept.
@@ -123,7 +137,7 @@ __device__ __forceinline__ void build_tiles(const uint32_t *nodes, int len, uint
 }
 
 template <int KP>
-__global__ void __launch_bounds__(LP_THREADS, 2)
+__global__ void __launch_bounds__(LP_THREADS, 1)
 level_pair_kernel(const LpArgs a)
 {
     using Cfg = LpCfg<KP>;
@@ -134,29 +148,36 @@ level_pair_kernel(const LpArgs a)
     uint8_t *sA = smem;
     uint8_t *sB = smem + Cfg::OFF_B;
     int *s_cn = reinterpret_cast<int *>(smem + Cfg::OFF_CN);
-    uint32_t *c_row = reinterpret_cast<uint32_t *>(smem + Cfg::OFF_LIST);
-    uint32_t *c_key = c_row + LP_CHUNK, *c_node = c_key + LP_CHUNK;
-    uint32_t *s_row = c_node + LP_CHUNK, *s_key = s_row + LP_CHUNK, *s_node = s_key + LP_CHUNK;
-    uint8_t *c_cls = reinterpret_cast<uint8_t *>(s_node + LP_CHUNK);
-    uint8_t *s_d1 = c_cls + LP_CHUNK;
-    uint8_t *tl_len = s_d1 + LP_CHUNK;
-    __shared__ __align__(8) unsigned long long bar_full[S], bar_acc[S], bar_empty[S], bar_p1;
+    uint32_t *s_flag = reinterpret_cast<uint32_t *>(smem + Cfg::OFF_FLAG);   // [S] child-internal bitmask of the stage's node
+    uint8_t *tl_len = smem + Cfg::OFF_TL;
+    __shared__ __align__(8) unsigned long long bar_full[S], bar_acc[S], bar_empty[S];
     __shared__ LpTile tinfo[S];
     __shared__ uint32_t s_tmem;
     __shared__ int s_ntiles, s_nreal;
-    __shared__ int s_wcnt[4][32], s_run[4][32];
+    __shared__ int s_wcnt[8][32], s_run[8][32];
+    __shared__ int s_done[2];                                   // warp-tiles each epilogue group has completed (4 per tile)
+
+    struct Lists { uint32_t *c_row, *c_key, *c_node, *s_row, *s_key, *s_node; uint8_t *c_cls, *s_d1; };
+    auto lists = [&](int buf) {
+        Lists l;
+        l.c_row = reinterpret_cast<uint32_t *>(smem + Cfg::OFF_LIST + (size_t)buf * Cfg::LIST_BYTES);
+        l.c_key = l.c_row + LP_CHUNK; l.c_node = l.c_key + LP_CHUNK;
+        l.s_row = l.c_node + LP_CHUNK; l.s_key = l.s_row + LP_CHUNK; l.s_node = l.s_key + LP_CHUNK;
+        l.c_cls = reinterpret_cast<uint8_t *>(l.s_node + LP_CHUNK); l.s_d1 = l.c_cls + LP_CHUNK;
+        return l;
+    };
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k = a.k, bits = a.bits;
     const uint32_t dmask = (1u << bits) - 1u;
 
-    if (warp == 8) {
+    if (warp == 16) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(Cfg::TMEM_ALLOC));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(&bar_full[s], LP_PRODUCERS); mbar_init(&bar_acc[s], 1); mbar_init(&bar_empty[s], 4); }
-        mbar_init(&bar_p1, 4);
+        s_done[0] = 0; s_done[1] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -165,18 +186,20 @@ level_pair_kernel(const LpArgs a)
     const uint32_t tmem = s_tmem;
     const long long n_chunks = (a.n + LP_CHUNK - 1) / LP_CHUNK;
 
-    if (warp < 4) {
-        // ================================ epilogue: thread = TMEM lane = row of the tile ================================
+    if (warp < 8) {
+        // ================================ epilogue: two groups of four warps; group = tile parity ======================
+        // thread = TMEM lane = row of the tile
+        const int grp = warp >> 2, qw = warp & 3, etid = tid & 127;
         unsigned int rechecks = 0;
         const int none = 0x7fffffff;
-        for (uint32_t g = 0;; ++g) {
+        for (uint32_t g = (uint32_t)grp;; g += 2) {
             const int st = (int)(g % S);
             mbar_wait(&bar_acc[st], (g / S) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;");
             const LpTile ti = tinfo[st];
             if (ti.flags & LPF_END) break;
             uint32_t v[P::N];
-            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(st * P::TMEM_COLS);
+            const uint32_t taddr = tmem + ((uint32_t)(qw * 32) << 16) + (uint32_t)(st * P::TMEM_COLS);
 #pragma unroll
             for (int gq = 0; gq < P::N / 16; ++gq) {
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -187,16 +210,18 @@ level_pair_kernel(const LpArgs a)
                              : "r"(taddr + 16 * gq));
             }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const Lists L = lists(ti.buf);
             const bool p2 = (ti.flags & LPF_PHASE2) != 0;
-            const uint32_t *lrow = p2 ? s_row : c_row;
-            const uint32_t *lkey = p2 ? s_key : c_key;
-            const bool active = tid < ti.len;
-            const int idx = ti.start + tid;
+            const uint32_t *lrow = p2 ? L.s_row : L.c_row;
+            const uint32_t *lkey = p2 ? L.s_key : L.c_key;
+            const bool active = etid < ti.len;
+            const int idx = ti.start + etid;
             const uint32_t row = active ? lrow[idx] : 0u;
             int best = none, second = none, arg = 0;
-            if (active) score_children<KP, P::N>(v, s_cn + st * 16, k, best, second, arg);
+            if (active) score_children_tree<KP, P::N>(v, s_cn + st * 16, best, second, arg);
             const uint8_t *tileA = sA + (size_t)st * MM_A_BYTES;
-            const bool contested = contested_row(active && k > 1, best, second, tileA, tid);
+            // (second - 15: the tournament ranks scores coarsened to 16 units, see score_children_tree)
+            const bool contested = contested_row(active && k > 1, best, second - 15, tileA, etid);
             unsigned int m = __ballot_sync(VT_FULL, contested);
             const uint8_t *xrow = a.desc + (size_t)row * 128;
             while (m) {
@@ -209,17 +234,18 @@ level_pair_kernel(const LpArgs a)
             }
             if (active) {
                 const long long child = (long long)ti.node * k + 1 + arg;
+                const bool cont = ((s_flag[st] >> arg) & 1u) != 0;   // the child has children of its own
                 const bool final_phase = p2 || a.phases == 1;
                 if (!final_phase) {
                     // phase 1 of 2: the child index stays in shared memory; a row whose child is a leaf stops here
-                    if ((child * k + k < a.n_heap) && a.internal[child]) {
-                        c_cls[idx] = (uint8_t)arg;
+                    if (cont) {
+                        L.c_cls[idx] = (uint8_t)arg;
                     } else {
                         if (a.leaf_out) a.leaf_out[row] = (int32_t)child;
                         if (a.word_out) a.word_out[row] = a.ref_id[child];
                     }
                 } else {
-                    const long long pos = (long long)ti.pos0 + tid;
+                    const long long pos = (long long)ti.pos0 + etid;
                     if (a.mode == 2) {
                         a.keys_out[pos] = row;
                         a.perm_out[pos] = (uint32_t)child;
@@ -227,14 +253,13 @@ level_pair_kernel(const LpArgs a)
                         if (a.leaf_out) a.leaf_out[row] = (int32_t)child;
                         if (a.word_out) a.word_out[row] = a.ref_id[child];
                     } else {
-                        const bool cont = (child * k + k < a.n_heap) && a.internal[child];
                         if (!cont) {
                             if (a.leaf_out) a.leaf_out[row] = (int32_t)child;
                             if (a.word_out) a.word_out[row] = a.ref_id[child];
                         }
                         const uint32_t last = cont ? (uint32_t)arg : dmask;
                         const uint32_t old = lkey[idx];
-                        a.keys_out[pos] = a.phases == 2 ? (((old << bits) | (uint32_t)s_d1[idx]) << bits) | last : (old << bits) | last;
+                        a.keys_out[pos] = a.phases == 2 ? (((old << bits) | (uint32_t)L.s_d1[idx]) << bits) | last : (old << bits) | last;
                         a.perm_out[pos] = row;
                     }
                 }
@@ -243,19 +268,26 @@ level_pair_kernel(const LpArgs a)
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(&bar_empty[st]);
-                if (ti.flags & LPF_LAST_P1) mbar_arrive(&bar_p1);
+                __threadfence_block();                          // c_cls of this tile before the completion count
+                atomicAdd(&s_done[grp], 1);
             }
         }
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) rechecks += __shfl_xor_sync(VT_FULL, rechecks, o);
         if (a.stats && lane == 0 && rechecks) atomicAdd(a.stats, (unsigned long long)rechecks);
-    } else if (warp < 8) {
+    } else if (warp < 16) {
         // ================================ producers ================================
-        const int ptid = tid - 128, pw = warp - 4;
-        uint32_t g = 0, p1_uses = 0;
+        // Order of work per CTA:  P1(c0)  P1(c1)  sort(c0) P2(c0)  P1(c2)  sort(c1) P2(c1) ...  -- phase 1 of the NEXT chunk is
+        // in the pipeline while the child indices of the current chunk are collected, so the ring never drains.
+        const int ptid = tid - 256, pw = warp - 8;
+        uint32_t g = 0;
         int pending = 0;                                        // committed gathers whose full barrier is still to be arrived on
+        int issued[2] = {0, 0};                                 // tiles handed to each epilogue group so far
+        int snap_a[2] = {0, 0}, snap_b[2] = {0, 0};             // per list buffer: `issued` when its phase 1 had been issued
+        uint32_t snap_g[2] = {0, 0};
         const int newbits = bits * a.phases;
         const uint32_t newmask = (1u << newbits) - 1u;
+        const long long my_chunks = n_chunks > blockIdx.x ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
         auto arrive_oldest = [&]() {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy smem writes -> tensor core
@@ -265,6 +297,21 @@ level_pair_kernel(const LpArgs a)
         auto flush = [&]() {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             while (pending > 0) arrive_oldest();
+        };
+        // every tile issued before the snapshot has left the epilogue (both groups work in order)
+        auto wait_done = [&](int buf) {
+            if (g - (uint32_t)pending < snap_g[buf]) flush();   // (only when little was issued since: last / sparse chunks)
+            const volatile int *d = s_done;
+            long long t0 = 0;
+            for (uint32_t spins = 0; d[0] < 4 * snap_a[buf] || d[1] < 4 * snap_b[buf]; ++spins) {
+                __nanosleep(40);
+                if ((spins & 1023u) == 1023u) {
+                    const long long t = clock64();
+                    if (t0 == 0) t0 = t;
+                    else if (t - t0 > 8000000000ll) lp_timeout("phase");
+                }
+            }
+            __threadfence_block();
         };
         // rows that take no part in the final phase (stopped earlier, or at phase 1): their slot of the output
         auto none_outputs = [&](const uint32_t *lrow, const uint32_t *lkey, int start, int len, long long base) {
@@ -280,9 +327,9 @@ level_pair_kernel(const LpArgs a)
             }
         };
         auto issue_phase = [&](const uint32_t *lrow, const uint32_t *lkey, const uint32_t *lnode, int phase_flag,
-                               bool final_phase, long long base) {
-            const int nt = s_ntiles, nreal = s_nreal;
-            int seen = 0, start = 0, len = 0;
+                               bool final_phase, long long base, int buf) {
+            const int nt = s_ntiles;
+            int start = 0, len = 0;
             for (int t = 0; t < nt; ++t) {
                 start += len;
                 len = (int)tl_len[t] + 1;
@@ -291,151 +338,242 @@ level_pair_kernel(const LpArgs a)
                     if (final_phase) none_outputs(lrow, lkey, start, len, base);
                     continue;
                 }
-                ++seen;
                 const int st = (int)(g % S);
                 mbar_wait(&bar_empty[st], ((g / S) & 1u) ^ 1u);
-                {   // A tile: 8 lanes copy one 128 B row, 16 rows per pass, swizzled destination (as level_mma_kernel)
+                {   // A tile: 8 lanes copy one 128 B row, 32 rows per pass, swizzled destination (as level_mma_kernel)
                     const int r0 = ptid >> 3, j = ptid & 7;
                     const uint32_t dst0 = smem_u32(sA + (size_t)st * MM_A_BYTES) +
                                           (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128 + ((j ^ (r0 & 7)) << 4));
                     const uint8_t *col = a.desc + j * 16;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = r0 + 16 * i;
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = r0 + 32 * i;
                         const bool ok = r < len;
                         const uint32_t rr = ok ? lrow[start + r] : 0u;
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + 2048u * i),
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + 4096u * i),
                                      "l"(col + (size_t)rr * 128), "r"(ok ? 16 : 0));
                     }
                 }
                 {
                     const uint8_t *bsrc = a.bimg + (size_t)node * P::B_BYTES;
                     const uint32_t bdst = smem_u32(sB + (size_t)st * P::B_BYTES);
-#pragma unroll
-                    for (int i = 0; i < P::B_BYTES / 16 / LP_PRODUCERS; ++i) {
-                        const int c = ptid + LP_PRODUCERS * i;
+                    for (int c = ptid; c < P::B_BYTES / 16; c += LP_PRODUCERS)
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(bdst + c * 16), "l"(bsrc + c * 16));
-                    }
                     if (ptid < 4)
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_cn + st * 16) + ptid * 16),
                                      "l"(a.cn32 + (size_t)node * 16 + ptid * 4));
+                    if (ptid == 4)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(s_flag + st)), "l"(a.cmask + node));
                 }
                 if (ptid == 0) {
                     LpTile ti;
                     ti.start = start; ti.len = len; ti.node = node; ti.pos0 = (int)(base + start);
-                    ti.flags = phase_flag | ((seen == nreal && (!final_phase || a.phases == 1)) ? LPF_LAST_P1 : 0);
+                    ti.flags = phase_flag; ti.buf = buf;
                     tinfo[st] = ti;
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
+                ++issued[g & 1u];
                 ++g;
                 ++pending;
-                if (pending > LP_LAG) {
-                    asm volatile("cp.async.wait_group %0;" ::"n"(LP_LAG) : "memory");
+                if (pending > Cfg::LAG) {
+                    asm volatile("cp.async.wait_group %0;" ::"n"(Cfg::LAG) : "memory");
                     arrive_oldest();
                 }
             }
         };
 
-        for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-            const long long base = chunk * LP_CHUNK;
-            const int clen = (int)((a.n - base) < LP_CHUNK ? (a.n - base) : LP_CHUNK);
-            // ---- load the chunk: row index, packed path, node (NONE: stopped earlier or a leaf right here) ----
-            for (int i = ptid; i < clen; i += LP_PRODUCERS) {
-                const long long pos = base + i;
-                const uint32_t row = a.perm ? a.perm[pos] : (uint32_t)pos;
-                const uint32_t key = a.parent ? a.parent[pos] : 0u;
+        // chunk rows are fetched one chunk ahead: the global loads of chunk i+1 are in flight while chunk i is issued
+        uint32_t rrow[LP_PER], rkey[LP_PER];
+        auto fetch = [&](long long i) {
+            const long long base = (blockIdx.x + i * (long long)gridDim.x) * LP_CHUNK;
+#pragma unroll
+            for (int u = 0; u < LP_PER; ++u) {
+                const long long pos = base + ptid + u * LP_PRODUCERS;
+                const bool in = i < my_chunks && pos < a.n;
+                rrow[u] = in ? (a.perm ? a.perm[pos] : (uint32_t)pos) : 0u;
+                rkey[u] = (in && a.parent) ? a.parent[pos] : 0u;
+            }
+        };
+        // registers -> lists of buffer `buf` + the tile list of phase 1; returns with s_ntiles / s_nreal valid
+        auto commit_load = [&](int clen, int buf) {
+            const Lists L = lists(buf);
+            uint32_t rh[LP_PER];
+            uint8_t rint[LP_PER];
+#pragma unroll
+            for (int u = 0; u < LP_PER; ++u) {
+                const int i = ptid + u * LP_PRODUCERS;
+                const bool alive = i < clen && (a.level == 0 || (rkey[u] & dmask) != dmask);
+                rh[u] = alive ? path_to_heap32(rkey[u], a.level, bits, (uint32_t)k) : LP_NONE;
+                rint[u] = (alive && ((long long)rh[u] * k + k < a.n_heap)) ? a.internal[rh[u]] : (uint8_t)0;
+            }
+            uint32_t first = LP_NONE;
+            bool same = true;
+#pragma unroll
+            for (int u = 0; u < LP_PER; ++u) {
+                const int i = ptid + u * LP_PRODUCERS;
+                if (i >= clen) continue;
                 uint32_t node = LP_NONE;
-                if (a.level == 0 || (key & dmask) != dmask) {
-                    const uint32_t h = path_to_heap32(key, a.level, bits, (uint32_t)k);
-                    if (((long long)h * k + k < a.n_heap) && a.internal[h]) {
-                        node = h;
+                if (rh[u] != LP_NONE) {
+                    if (rint[u]) {
+                        node = rh[u];
                     } else {                                     // ragged tree: this node is a leaf
-                        if (a.leaf_out) a.leaf_out[row] = (int32_t)h;
-                        if (a.word_out) a.word_out[row] = a.ref_id[h];
+                        if (a.leaf_out) a.leaf_out[rrow[u]] = (int32_t)rh[u];
+                        if (a.word_out) a.word_out[rrow[u]] = a.ref_id[rh[u]];
                     }
                 }
-                c_row[i] = row; c_key[i] = key; c_node[i] = node; c_cls[i] = LP_STOP;
+                L.c_row[i] = rrow[u]; L.c_key[i] = rkey[u]; L.c_node[i] = node; L.c_cls[i] = LP_STOP;
+                if (u == 0) first = node; else same = same && node == first;
+            }
+            // one node for the whole chunk (the usual case): the tile list is arithmetic
+            if (ptid == 0) s_run[0][0] = (int)first;
+            producers_sync();
+            const uint32_t node0 = (uint32_t)s_run[0][0];
+            const bool uniform = producers_all(same && (ptid >= clen || first == node0) && node0 != LP_NONE);
+            if (uniform) {
+                const int nt = (clen + MM_TILE - 1) / MM_TILE;
+                if (ptid < nt) tl_len[ptid] = (uint8_t)((clen - ptid * MM_TILE < MM_TILE ? clen - ptid * MM_TILE : MM_TILE) - 1);
+                if (ptid == 0) { s_ntiles = nt; s_nreal = nt; }
+            } else if (pw == 0) {
+                build_tiles(L.c_node, clen, tl_len, &s_ntiles, &s_nreal, lane);
             }
             producers_sync();
-            if (pw == 0) build_tiles(c_node, clen, tl_len, &s_ntiles, &s_nreal, lane);
-            producers_sync();
-            const int nreal1 = s_nreal;
-            issue_phase(c_row, c_key, c_node, 0, a.phases == 1, base);
-            if (a.phases == 1 && nreal1 > 0) {
-                // single-level launch (odd depth): the epilogue reads c_row / c_key for its output, so the lists must
-                // not be reloaded before it is through with this chunk
-                flush();
-                mbar_wait(&bar_p1, p1_uses & 1u);
-                ++p1_uses;
+            return uniform;
+        };
+        auto chunk_len = [&](long long i) {
+            const long long base = (blockIdx.x + i * (long long)gridDim.x) * LP_CHUNK;
+            return (int)((a.n - base) < LP_CHUNK ? (a.n - base) : LP_CHUNK);
+        };
+        auto chunk_base = [&](long long i) { return (blockIdx.x + i * (long long)gridDim.x) * LP_CHUNK; };
+        auto issue_p1 = [&](long long i) {
+            const int buf = (int)(i & 1);
+            const Lists L = lists(buf);
+            issue_phase(L.c_row, L.c_key, L.c_node, 0, a.phases == 1, chunk_base(i), buf);
+            snap_a[buf] = issued[0]; snap_b[buf] = issued[1]; snap_g[buf] = g;
+        };
+
+        bool uni[2] = {false, false};
+        int nreal1[2] = {0, 0};
+        if (my_chunks > 0) {
+            fetch(0);
+            uni[0] = commit_load(chunk_len(0), 0);
+            nreal1[0] = s_nreal;
+            fetch(1);
+            issue_p1(0);
+        }
+        for (long long i = 0; i < my_chunks; ++i) {
+            const int buf = (int)(i & 1), nb = buf ^ 1;
+            if (i + 1 < my_chunks) {
+                // buffer nb held chunk i-1: its phase-1 lists were consumed by sort(i-1) (two-level launches) or are
+                // still being read by the epilogue (single-level launches)
+                if (a.phases == 1 && i >= 1) wait_done(nb);
+                producers_sync();
+                uni[nb] = commit_load(chunk_len(i + 1), nb);
+                nreal1[nb] = s_nreal;
+                fetch(i + 2);
+                issue_p1(i + 1);
             }
             if (a.phases == 2) {
-                if (nreal1 == 0) {
-                    none_outputs(c_row, c_key, 0, clen, base);   // nothing alive in this chunk
+                const Lists L = lists(buf);
+                const int clen = chunk_len(i);
+                const long long base = chunk_base(i);
+                producers_sync();
+                if (nreal1[buf] == 0) {
+                    none_outputs(L.c_row, L.c_key, 0, clen, base);    // nothing alive in this chunk
                 } else {
-                    flush();
-                    mbar_wait(&bar_p1, p1_uses & 1u);            // the epilogue has left every child index in c_cls
-                    ++p1_uses;
+                    wait_done(buf);                              // the epilogue has left every child index in c_cls
                     // ---- stable counting sort of the chunk by child index (LP_STOP = stopped) ----
                     s_wcnt[pw][lane] = 0;
                     __syncwarp();
-                    const int w_lo = pw * (LP_CHUNK / 4);
-                    for (int w0 = w_lo; w0 < w_lo + LP_CHUNK / 4; w0 += 32) {
-                        const int i = w0 + lane;
-                        const int c = i < clen ? (int)c_cls[i] : 32 + lane;      // padding: every lane its own class
+                    const int w_lo = pw * (LP_CHUNK / 8);
+                    for (int w0 = w_lo; w0 < w_lo + LP_CHUNK / 8; w0 += 32) {
+                        const int e = w0 + lane;
+                        const int c = e < clen ? (int)L.c_cls[e] : 32 + lane;      // padding: every lane its own class
                         const unsigned int mm = __match_any_sync(VT_FULL, c);
-                        if (i < clen && lane == __ffs(mm) - 1) s_wcnt[pw][c] += __popc(mm);
+                        if (e < clen && lane == __ffs(mm) - 1) s_wcnt[pw][c] += __popc(mm);
                         __syncwarp();
                     }
                     producers_sync();
+                    int total_c = 0;                             // rows of class `lane` in the whole chunk
                     {
-                        int b = 0;
-                        for (int c = 0; c < lane; ++c) b += s_wcnt[0][c] + s_wcnt[1][c] + s_wcnt[2][c] + s_wcnt[3][c];
-                        for (int w = 0; w < pw; ++w) b += s_wcnt[w][lane];
-                        s_run[pw][lane] = b;
+                        int before = 0;                          // ... of them in the warps ahead of this one
+#pragma unroll
+                        for (int w = 0; w < 8; ++w) {
+                            const int t = s_wcnt[w][lane];
+                            total_c += t;
+                            if (w < pw) before += t;
+                        }
+                        int incl = total_c;                      // exclusive prefix over the classes
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int t = __shfl_up_sync(VT_FULL, incl, o);
+                            if (lane >= o) incl += t;
+                        }
+                        s_run[pw][lane] = incl - total_c + before;
                     }
                     __syncwarp();
-                    for (int w0 = w_lo; w0 < w_lo + LP_CHUNK / 4; w0 += 32) {
-                        const int i = w0 + lane;
-                        const int c = i < clen ? (int)c_cls[i] : 32 + lane;
+                    for (int w0 = w_lo; w0 < w_lo + LP_CHUNK / 8; w0 += 32) {
+                        const int e = w0 + lane;
+                        const int c = e < clen ? (int)L.c_cls[e] : 32 + lane;
                         const unsigned int mm = __match_any_sync(VT_FULL, c);
                         const int leader = __ffs(mm) - 1;
                         int off = 0;
-                        if (i < clen && lane == leader) { off = s_run[pw][c]; s_run[pw][c] = off + __popc(mm); }
+                        if (e < clen && lane == leader) { off = s_run[pw][c]; s_run[pw][c] = off + __popc(mm); }
                         off = __shfl_sync(VT_FULL, off, leader);
-                        if (i < clen) {
+                        if (e < clen) {
                             const int dst = off + __popc(mm & ((1u << lane) - 1u));
-                            s_row[dst] = c_row[i];
-                            s_key[dst] = c_key[i];
-                            s_node[dst] = c == LP_STOP ? LP_NONE : c_node[i] * (uint32_t)k + 1u + (uint32_t)c;
-                            s_d1[dst] = c == LP_STOP ? (uint8_t)dmask : (uint8_t)c;
+                            L.s_row[dst] = L.c_row[e];
+                            L.s_key[dst] = L.c_key[e];
+                            L.s_node[dst] = c == LP_STOP ? LP_NONE : L.c_node[e] * (uint32_t)k + 1u + (uint32_t)c;
+                            L.s_d1[dst] = c == LP_STOP ? (uint8_t)dmask : (uint8_t)c;
                         }
                         __syncwarp();
                     }
-                    producers_sync();
-                    if (pw == 0) build_tiles(s_node, clen, tl_len, &s_ntiles, &s_nreal, lane);
-                    producers_sync();
-                    issue_phase(s_row, s_key, s_node, LPF_PHASE2, true, base);
+                    // ---- tile list of phase 2 ----
+                    if (uni[buf]) {
+                        // one parent node: the runs are the classes, in class order (lane = class)
+                        if (pw == 0) {
+                            const int ntile = (total_c + MM_TILE - 1) / MM_TILE;
+                            int incl = ntile;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const int t = __shfl_up_sync(VT_FULL, incl, o);
+                                if (lane >= o) incl += t;
+                            }
+                            int at = incl - ntile;
+                            for (int r = total_c; r > 0; r -= MM_TILE) tl_len[at++] = (uint8_t)((r < MM_TILE ? r : MM_TILE) - 1);
+                            const int all = __shfl_sync(VT_FULL, incl, 31), stopped = __shfl_sync(VT_FULL, ntile, LP_STOP);
+                            if (lane == 0) { s_ntiles = all; s_nreal = all - stopped; }
+                        }
+                        producers_sync();
+                    } else {
+                        producers_sync();
+                        if (pw == 0) build_tiles(L.s_node, clen, tl_len, &s_ntiles, &s_nreal, lane);
+                        producers_sync();
+                    }
+                    issue_phase(L.s_row, L.s_key, L.s_node, LPF_PHASE2, true, base, buf);
                 }
             }
-            producers_sync();                                    // tile list / chunk lists are rewritten by the next chunk
         }
         flush();
-        {   // end marker through the same pipeline
+        for (int e = 0; e < 2; ++e) {   // end markers through the same pipeline, one per epilogue group
             const int st = (int)(g % S);
             mbar_wait(&bar_empty[st], ((g / S) & 1u) ^ 1u);
-            if (ptid == 0) { LpTile ti; ti.start = 0; ti.len = 0; ti.node = 0; ti.flags = LPF_END; ti.pos0 = 0; tinfo[st] = ti; }
+            if (ptid == 0) { LpTile ti; ti.start = 0; ti.len = 0; ti.node = 0; ti.flags = LPF_END; ti.pos0 = 0; ti.buf = 0; tinfo[st] = ti; }
             mbar_arrive(&bar_full[st]);
+            ++g;
         }
     } else {
         // ================================ MMA issuer ================================
-        for (uint32_t g = 0;; ++g) {
+        int ends = 0;
+        for (uint32_t g = 0; ends < 2; ++g) {
             const int st = (int)(g % S);
             mbar_wait(&bar_full[st], (g / S) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;");
             const int flags = tinfo[st].flags;
             if (flags & LPF_END) {
                 if (lane == 0) mbar_arrive(&bar_acc[st]);
-                break;
+                ++ends;
+                continue;
             }
             if (lane == 0) {
                 const uint64_t a_desc = make_desc(smem_u32(sA + (size_t)st * MM_A_BYTES));
@@ -456,25 +594,29 @@ level_pair_kernel(const LpArgs a)
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
-    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(Cfg::TMEM_ALLOC));
+    if (warp == 16) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(Cfg::TMEM_ALLOC));
+}
+
+// per node: bit c set <=> child c exists as an internal node (the descent continues below it)
+__global__ void child_mask_kernel(const uint8_t *__restrict__ internal, long long n_int, int k, uint32_t *__restrict__ cmask)
+{
+    for (long long h = blockIdx.x * (long long)blockDim.x + threadIdx.x; h < n_int; h += (long long)gridDim.x * blockDim.x) {
+        uint32_t m = 0;
+        for (int c = 0; c < k; ++c) m |= (uint32_t)(internal[h * k + 1 + c] != 0) << c;
+        cmask[h] = m;
+    }
 }
 
 template <int KP>
 int launch_pair(const LpArgs &a, cudaStream_t s)
 {
     static bool attr_set = false;
-    static int ctas_per_sm = 2;
     auto kern = level_pair_kernel<KP>;
     if (!attr_set) {
         VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LpCfg<KP>::SMEM));
-        int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LP_THREADS, LpCfg<KP>::SMEM) == cudaSuccess && occ >= 1)
-            ctas_per_sm = occ < 2 ? occ : 2;
-        const char *e = getenv("VT_PAIR_CTAS");
-        if (e && atoi(e) >= 1 && atoi(e) <= 2) ctas_per_sm = atoi(e);
         attr_set = true;
     }
-    const long long n_chunks = (a.n + LP_CHUNK - 1) / LP_CHUNK, cap = (long long)vt_sm_count() * ctas_per_sm;
+    const long long n_chunks = (a.n + LP_CHUNK - 1) / LP_CHUNK, cap = (long long)vt_sm_count();
     kern<<<(int)(n_chunks < cap ? n_chunks : cap), LP_THREADS, LpCfg<KP>::SMEM, s>>>(a);
     VT_LAUNCH_CHECK();
     return VT_OK;
@@ -485,7 +627,8 @@ int launch_pair(const LpArgs &a, cudaStream_t s)
 // receives one event before and one after every launch-pair stage, for the profile variant.
 int vt_mma_levels_paired(const void *d_desc, int64_t n, const float *cent, const uint8_t *internal, const int32_t *ref_id,
                          int k, int depth, int32_t *leaf, int32_t *word, uint64_t *stats, const uint8_t *bimg,
-                         const int *cn32, void *sortwork, bool defer, cudaStream_t s, cudaEvent_t *ev, int *n_ev_io)
+                         const int *cn32, uint32_t *cmask, void *sortwork, bool defer, cudaStream_t s, cudaEvent_t *ev,
+                         int *n_ev_io)
 {
     int n_ev = n_ev_io ? *n_ev_io : 0;
 #define VT_MARK() do { if (ev) VT_CUDA(cudaEventRecord(ev[n_ev++], s)); } while (0)
@@ -496,13 +639,20 @@ int vt_mma_levels_paired(const void *d_desc, int64_t n, const float *cent, const
     const int bits = path_bits(k);
     uint32_t *keys = kA, *perm = pA, *tkeys = kB, *tperm = pB;
     const uint32_t *cur_perm = nullptr, *cur_parent = nullptr;
+    {   // which children of every internal node continue the descent (4 B per node, next to the prepared planes)
+        int64_t n_int = 0, p = 1;
+        for (int l = 0; l < depth; ++l) { n_int += p; p *= k; }
+        const int64_t want = (n_int + 255) / 256, cap = (int64_t)vt_sm_count() * 8;
+        child_mask_kernel<<<(int)(want < cap ? want : cap), 256, 0, s>>>(internal, n_int, k, cmask);
+        VT_LAUNCH_CHECK();
+    }
     for (int level = 0; level < depth;) {
         const int phases = depth - level >= 2 ? 2 : 1;
         const bool last = level + phases == depth;
         LpArgs a;
         a.desc = (const uint8_t *)d_desc; a.perm = cur_perm; a.parent = cur_parent; a.n = n;
         a.level = level; a.phases = phases; a.bits = bits; a.k = k; a.mode = last ? (defer ? 2 : 1) : 0;
-        a.n_heap = n_heap; a.cent = cent; a.internal = internal; a.ref_id = ref_id; a.bimg = bimg; a.cn32 = cn32;
+        a.n_heap = n_heap; a.cent = cent; a.internal = internal; a.ref_id = ref_id; a.bimg = bimg; a.cn32 = cn32; a.cmask = cmask;
         a.keys_out = last && !defer ? nullptr : tkeys; a.perm_out = last && !defer ? nullptr : tperm;
         a.leaf_out = leaf; a.word_out = word; a.stats = (unsigned long long *)stats;
         if (level > 0) VT_MARK();                                 // (the caller recorded the first event)

@@ -27,7 +27,7 @@ from .dataset import Dataset
 
 
 class Database(object):
-    def __init__(self, dataset, encoder, *, weighting="tf", norm="l2", comm=None):
+    def __init__(self, dataset, encoder, *, weighting="tf", norm="l2", comm=None, dense_top=True):
         # public:
         if isinstance(dataset, Dataset):
             self.dataset = dataset
@@ -44,6 +44,10 @@ class Database(object):
         # multi-GPU (one process per GPU): ``comm`` is a ``dist.Comm``; the images are sharded by id over its ranks,
         # every rank indexes its own range and ``retrieve_batch`` merges the per-rank top-k lists
         self.comm = comm if comm is not None and getattr(comm, "world", 1) > 1 else None
+        # all-nodes tf indexes (the reference's semantics): the top tree levels are kept as a dense count block scored
+        # by one tcgen05 GEMM per query batch, only the deep levels are posting lists (csrc/vt_dense.cu)
+        self.dense_top = bool(dense_top)
+        self._dense_index = None
 
         # private:
         self._rows = {}           # image path -> row in this rank's indexed CSR
@@ -69,6 +73,15 @@ class Database(object):
 
     def _descriptors(self, image_path):
         return np.asarray(self.encoder.descriptor(self.dataset.read_image(image_path)))
+
+    def _adopt_dense(self, dense, sumsq, n_images, img_base):
+        """Adopt an all-nodes index whose dense top was accumulated batch by batch (``engine.DenseTopBuilder``): the
+        forward CSR of the images is not kept, so indexed images cannot be used as queries by name (descriptor
+        arrays can).  Used for databases whose all-nodes forward CSR would not fit (bench.py at 1 M images)."""
+        self._dense_index, self._index = dense, dense["index"]
+        self._csr = dict(row_off=None, node=None, count=None, sumsq=sumsq, df=None, n_img=dense["n_img"], nnz=0)
+        self._rows, self._n_images, self._img_base = {}, int(n_images), int(img_base)
+        self._row_off_host, self._weights, self._extra = None, None, {}
 
     def _load_batch(self, paths, slot):
         """Loader thread: read the images of one batch, run the descriptor and pack the rows into a pinned
@@ -109,7 +122,18 @@ class Database(object):
         self._csr = csr
         self._rows, self._n_images, self._img_base = rows, int(n_images), int(img_base)
         self._row_off_host = csr["row_off"].cpu().numpy()
-        self._index = engine.build_index(csr, n_ref) if csr["n_img"] > 0 else None
+        self._index, self._dense_index = None, None
+        enc = self.encoder
+        if (self.dense_top and self.weighting == "tf" and csr["n_img"] > 0 and getattr(enc, "all_nodes", False)
+                and getattr(enc, "min_level", 0) == 0):
+            tdev = enc.flat.device(csr["row_off"].device)
+            layout = engine.dense_layout(tdev, enc.flat.depth, n_ref)
+            if layout is not None:
+                self._dense_index = engine.DenseTopBuilder(tdev, enc.flat.depth, n_ref, csr["n_img"], layout).add(csr, 0).finish()
+        if self._dense_index is not None:
+            self._index = self._dense_index["index"]          # posting lists of the deep levels only
+        elif csr["n_img"] > 0:
+            self._index = engine.build_index(csr, n_ref)
         if self.weighting == "tfidf":
             import torch
             if df is None:
@@ -285,6 +309,8 @@ class Database(object):
                         id=torch.full((nq, k), -1, dtype=torch.int32, device=dev),
                         score=torch.full((nq, k), 1e6, dtype=torch.float64, device=dev),
                         all_key=torch.zeros((nq, 0), dtype=torch.float64, device=dev) if return_all else None)
+        if self._dense_index is not None:
+            return engine.score_dense(self._dense_index, q, k, want_all=return_all)
         return engine.score(self._index, q, k, self._mode(), want_all=return_all, weights=self._weights)
 
     def _all_keys_global(self, local_keys):

@@ -617,6 +617,145 @@ def build_index(csr: dict, n_ref: int, weight: torch.Tensor = None) -> dict:
                 n_ref=n_ref, shard=shard, n_shards=n_shards, nnz=nnz, weighted=weight is not None)
 
 
+# --------------------------------------------------------------------------------------- dense top (all-nodes indexes)
+DENSE_MAX_LEVEL = 4           # levels 2..4 of a k=10 tree: 11,100 nodes, every one visited by >= ~10 % of the images
+DENSE_MAX_TOP = 17            # levels 0..1: 1 + k nodes, k <= 16
+
+
+def dense_layout(tree_dev: dict, depth: int, n_ref: int, max_level: int = DENSE_MAX_LEVEL):
+    """Which nodes of an all-nodes index leave the posting lists (csrc/vt_dense.cu): levels 0..1 -> int32 "top"
+    columns, levels 2..max_level -> uint8 columns of the dense block, deeper levels stay postings.  None when the
+    tree's top does not fit (k > 16)."""
+    level = tree_dev["level_ref"].to(torch.int64)
+    dev = level.device
+    top = level <= 1
+    n_top = int(top.sum().item())
+    if n_top > DENSE_MAX_TOP or n_top < 1:
+        return None
+    dense = (level >= 2) & (level <= min(max_level, depth))
+    n_dense = int(dense.sum().item())
+    col = torch.full((n_ref,), -1, dtype=torch.int32, device=dev)
+    col[dense] = torch.arange(n_dense, dtype=torch.int32, device=dev)
+    col[top] = -2 - torch.arange(n_top, dtype=torch.int32, device=dev)
+    kd = max(128, (n_dense + 127) // 128 * 128)
+    return dict(col_of_ref=col, n_top=n_top, n_dense=n_dense, kd=kd, max_level=min(max_level, depth))
+
+
+class DenseTopBuilder:
+    """Accumulates the dense top of an all-nodes index batch by batch (``add``), then builds the posting lists of
+    the deep levels (``finish``).  ``finish`` returns None when a dense count exceeded 255 (caller falls back to
+    plain postings)."""
+
+    def __init__(self, tree_dev: dict, depth: int, n_ref: int, n_img: int, layout: dict = None):
+        self.layout = layout or dense_layout(tree_dev, depth, n_ref)
+        self.n_ref, self.n_img = n_ref, int(n_img)
+        dev = tree_dev["level_ref"].device
+        self.np = max(256, (self.n_img + 255) // 256 * 256)
+        self.block = torch.zeros((self.np, self.layout["kd"]), dtype=torch.uint8, device=dev)
+        self.top = torch.zeros((self.np, self.layout["n_top"]), dtype=torch.int32, device=dev)
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.sparse, self.sumsq = [], []
+
+    @staticmethod
+    def scatter(csr: dict, layout: dict, block, top, overflow, img_base: int = 0):
+        lib = _lib()
+        nat.check(lib.vt_dense_scatter(nat.ptr(csr["row_off"]), nat.ptr(csr["node"]), nat.ptr(csr["count"]), csr["n_img"],
+                                       int(img_base), nat.ptr(layout["col_of_ref"]), nat.ptr(block), layout["kd"], nat.ptr(top),
+                                       layout["n_top"], nat.ptr(overflow), nat.stream_ptr()), "vt_dense_scatter")
+
+    @staticmethod
+    def sparse_part(csr: dict, layout: dict) -> dict:
+        """the entries of the deep levels (posting nodes) as their own CSR; norms stay those of the full rows"""
+        keep = layout["col_of_ref"][csr["node"].long()] == -1
+        prefix = torch.zeros(csr["node"].numel() + 1, dtype=torch.int64, device=keep.device)
+        prefix[1:] = torch.cumsum(keep, 0)
+        row_off = prefix[csr["row_off"]]
+        return dict(row_off=row_off, node=csr["node"][keep], count=csr["count"][keep], sumsq=csr["sumsq"], df=None,
+                    n_img=csr["n_img"], nnz=int(row_off[-1].item()))
+
+    @_device_scoped
+    def add(self, csr: dict, img_base: int):
+        self.scatter(csr, self.layout, self.block, self.top, self.overflow, img_base)
+        self.sparse.append(self.sparse_part(csr, self.layout))
+        return self
+
+    def finish(self):
+        if int(self.overflow.item()) != 0:
+            return None
+        sp = concat_csr(self.sparse) if self.sparse else None
+        self.sparse = []
+        index = build_index(sp, self.n_ref)
+        return dict(index=index, block=self.block, top=self.top, layout=self.layout, np=self.np, n_img=self.n_img)
+
+
+@_device_scoped
+def score_dense(dense: dict, q: dict, topk: int, want_all: bool = False, d_budget_bytes: int = 4 << 30) -> dict:
+    """All-nodes tf scoring with the dense top: per chunk of queries ONE tcgen05 INT8 GEMM gives the int32 dots over
+    levels 0..Ld (``vt_dense_dots``), the posting scorer starts its accumulators from them and adds the deep levels
+    (``vt_score_topk_seeded``).  Same outputs as ``score`` (exact integer dots, binary64 keys)."""
+    lib = _lib()
+    index, layout = dense["index"], dense["layout"]
+    dev = dense["block"].device
+    s = nat.stream_ptr()
+    nq, n_img, np_, kd, n_top = q["n_img"], dense["n_img"], dense["np"], layout["kd"], layout["n_top"]
+    if topk > lib.vt_score_max_topk():
+        raise ValueError("top-%d requested; at most %d per query" % (topk, lib.vt_score_max_topk()))
+    n_shards = index["n_shards"]
+    key = torch.empty((max(nq, 1), topk), dtype=torch.float64, device=dev)
+    ids = torch.empty((max(nq, 1), topk), dtype=torch.int32, device=dev)
+    sc = torch.empty((max(nq, 1), topk), dtype=torch.float64, device=dev)
+    all_key = torch.empty((max(nq, 1), n_img), dtype=torch.float64, device=dev) if want_all else None
+    if nq == 0:
+        return dict(key=key[:0], id=ids[:0], score=sc[:0], all_key=all_key, topk=topk)
+    # query side of the GEMM; a query count above 255 in the dense levels is spread over extra rows (the dot is linear)
+    qp = (nq + 255) // 256 * 256
+    a_rows = torch.zeros((qp, kd), dtype=torch.uint8, device=dev)
+    qt = torch.zeros((qp, n_top), dtype=torch.int32, device=dev)
+    over = torch.zeros(1, dtype=torch.int32, device=dev)
+    DenseTopBuilder.scatter(q, layout, a_rows, qt, over, 0)
+    extra = None
+    if int(over.item()) != 0:
+        extra = _dense_query_overflow(q, layout, dense["block"])
+    qs = DenseTopBuilder.sparse_part(q, layout)
+    q_val = qs["count"].to(torch.float32)
+    chunk = int(max(256, min(qp, (d_budget_bytes // (4 * np_)) // 256 * 256)))
+    seed = torch.empty((chunk, np_), dtype=torch.int32, device=dev)
+    for c0 in range(0, nq, chunk):
+        c1 = min(nq, c0 + chunk)
+        rows = (c1 - c0 + 255) // 256 * 256
+        nat.check(lib.vt_dense_dots(nat.ptr(a_rows[c0:]), nat.ptr(qt[c0:]), nat.ptr(dense["block"]), nat.ptr(dense["top"]),
+                                    rows, np_, kd, n_top, nat.ptr(seed), np_, s), "vt_dense_dots")
+        if extra is not None:
+            extra(seed, c0, c1)
+        off = (qs["row_off"][c0:c1 + 1] - qs["row_off"][c0]).contiguous()
+        b = int(qs["row_off"][c0].item())
+        shard_key = torch.empty((c1 - c0, n_shards, topk), dtype=torch.float64, device=dev)
+        shard_id = torch.empty((c1 - c0, n_shards, topk), dtype=torch.int32, device=dev)
+        nat.check(lib.vt_score_topk_seeded(nat.ptr(index["post_off"]), nat.ptr(index["postings"]), nat.ptr(index["rnorm"]),
+                                           n_img, index["n_ref"], nat.ptr(off), nat.ptr(qs["node"][b:]), nat.ptr(q_val[b:]),
+                                           c1 - c0, topk, nat.ptr(seed), np_, nat.ptr(shard_key), nat.ptr(shard_id),
+                                           nat.ptr(all_key[c0:]) if want_all else None, s), "vt_score_topk_seeded")
+        m = merge_topk(shard_key.view(c1 - c0, -1), shard_id.view(c1 - c0, -1), c1 - c0, topk, nat.SCORE_TF_L2,
+                       q["sumsq"][c0:c1].contiguous(), index["sumsq"])
+        key[c0:c1], ids[c0:c1], sc[c0:c1] = m["key"], m["id"], m["score"]
+    return dict(key=key[:nq], id=ids[:nq], score=sc[:nq], all_key=all_key, topk=topk)
+
+
+def _dense_query_overflow(q: dict, layout: dict, block: torch.Tensor):
+    """Rare: a query has more than 255 descriptors under one dense node.  The scattered row holds min(count, 255);
+    the remainder is added to the seed column by column (dot products are linear in the query counts)."""
+    col = layout["col_of_ref"][q["node"].long()]
+    big = torch.nonzero((col >= 0) & (q["count"] > 255)).flatten()
+    rows = (torch.searchsorted(q["row_off"], big, right=True) - 1).tolist()
+    cols, rest = col[big].tolist(), (q["count"][big] - 255).tolist()
+
+    def add(seed, c0, c1):
+        for r, c, v in zip(rows, cols, rest):
+            if c0 <= r < c1:
+                seed[r - c0] += int(v) * block[:, c].to(torch.int32)
+    return add
+
+
 # --------------------------------------------------------------------------------------- score
 @_device_scoped
 def score(index: dict, q: dict, topk: int, mode: int = nat.SCORE_TF_L2, q_val: torch.Tensor = None,

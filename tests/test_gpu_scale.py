@@ -229,3 +229,69 @@ def test_tensors_on_a_non_current_device_are_served(vt, cuda):
     assert torch.cuda.current_device() == 0
     assert np.array_equal(v0.flat.centroids, v1.flat.centroids)
     assert np.array_equal(v0.quantize(x), v1.quantize(x))
+
+
+# ------------------------------------------------------------------------------------------ dense top of all-nodes indexes
+def _full_tree(vt, cuda, k, depth, d, seed):
+    torch = _torch()
+    cent = vt.synth.hierarchical_tree(k, depth, d, seed=seed, device=cuda)
+    nh = vt.tree.heap_size(k, depth)
+    internal = torch.zeros(nh, dtype=torch.uint8, device=cuda)
+    internal[:vt.tree.level_offset(k, depth)] = 1
+    pad = torch.zeros((nh, vt.tree.pad_dim(d)), dtype=torch.float32, device=cuda)
+    pad[:, :d] = cent
+    return vt.FlatTree.from_device(k, depth, d, pad, torch.ones(nh, dtype=torch.uint8, device=cuda), internal, byte_built=True), cent
+
+
+@pytest.mark.parametrize("k,depth", [(4, 6), (10, 3), (3, 2), (16, 3)])
+def test_dense_top_equals_plain_postings(vt, cuda, k, depth):
+    """All-nodes tf retrieval with the dense top (levels 0..1 int32, levels 2..4 uint8 block scored by the tcgen05 GEMM,
+    deeper levels postings) must give the ids, scores and rank keys of the plain all-postings index, bit for bit --
+    including images without descriptors, database sizes that are no multiple of the tile, several shards, and a
+    query with more than 255 descriptors under one dense node."""
+    torch = _torch()
+    rng = np.random.default_rng(k * 10 + depth)
+    ft, cent = _full_tree(vt, cuda, k, depth, 32, seed=3)
+    voc = vt.encoders.VocabularyTree(k, depth, descriptor=lambda im: im, all_nodes=True, device=cuda).set_tree(ft)
+    n_img = 9000 if k == 4 else 700                                  # 9000 images: two shards of 8192
+    sizes = rng.integers(5, 60, n_img)
+    sizes[13] = 0
+    sizes[n_img - 1] = 0
+    x = vt.synth.descriptors_from_tree(cent, k, depth, int(sizes.sum()), seed=8).cpu().numpy()[:, :32]
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    images = [x[offs[i]:offs[i + 1]] for i in range(n_img)]
+    csr = voc.encode_batch(images)
+    tdev = ft.device(cuda)
+    plain = vt.engine.build_index(csr, ft.n_ref)
+    dense = vt.engine.DenseTopBuilder(tdev, depth, ft.n_ref, n_img).add(csr, 0).finish()
+    assert dense is not None and dense["layout"]["n_top"] == 1 + k
+    heavy = np.repeat(x[:3], 300, axis=0)                            # 300 copies of 3 descriptors: counts of 300 on their paths
+    q_images = [images[0], images[13], images[4321 % n_img], heavy, x[100:140], images[n_img - 2]]
+    q = voc.encode_batch(q_images)
+    a = vt.engine.score(plain, q, 10, want_all=True)
+    b = vt.engine.score_dense(dense, q, 10, want_all=True)
+    assert torch.equal(a["id"], b["id"])
+    assert torch.equal(a["score"], b["score"]) and torch.equal(a["key"], b["key"])
+    assert torch.equal(a["all_key"], b["all_key"])
+    assert int(b["id"][0, 0]) == 0 and float(b["score"][0, 0]) == 0.0
+    assert (b["score"][1] == 1e6).all()                              # query without descriptors (database.py:70)
+    # small query budget: several GEMM chunks
+    c = vt.engine.score_dense(dense, q, 10, want_all=True, d_budget_bytes=1)
+    assert torch.equal(a["id"], c["id"]) and torch.equal(a["all_key"], c["all_key"])
+
+
+def test_dense_top_falls_back_when_a_database_count_overflows(vt, cuda):
+    rng = np.random.default_rng(0)
+    ft, cent = _full_tree(vt, cuda, 4, 5, 32, seed=3)
+    voc = vt.encoders.VocabularyTree(4, 5, descriptor=lambda im: im, all_nodes=True, device=cuda).set_tree(ft)
+    x = vt.synth.descriptors_from_tree(cent, 4, 5, 4000, seed=8).cpu().numpy()[:, :32]
+    images = [x[i * 40:(i + 1) * 40] for i in range(99)] + [np.repeat(x[:1], 400, axis=0)]
+    ds = vt.ArrayDataset(images)
+    db = vt.Database(ds, voc)
+    db.index()
+    assert db._dense_index is None                                   # a count of 400 does not fit the byte block
+    ids, sc = db.retrieve_batch(ds.image_paths, k=3)
+    assert (ids[:, 0] == np.arange(100)).all() and (sc[:, 0] == 0).all()
+    ok = vt.Database(vt.ArrayDataset(images[:99]), voc)
+    ok.index()
+    assert ok._dense_index is not None
