@@ -204,32 +204,23 @@ int vt_csr_compact(const int64_t *d_in_off, const int32_t *d_nnz, const int64_t 
                    int32_t *d_node_out, int32_t *d_count_out, void *stream);
 
 /* ---- inverted file: the dict-per-node postings of vocabulary.py:96-100 as CSR, sharded by image
- * range (vt_score_shard_size() images per shard).  Row key = node * n_shards + img / shard_size, so a
+ * range (vt_score_shard_size() = 8192 images per shard).  Row key = node * n_shards + img / shard_size, so a
  * node's posting list is one contiguous image-ordered run and shards are consecutive ranges of it.
- * vt_posting_keys writes, for every forward-CSR entry e, its key, e itself and its image;
- * sort (key, e) with vt_sort_pairs (stable => postings stay in image order); vt_posting_fill then
- * gathers the postings (uint32 local image id, uint32 payload = tf count, or float weight bits
- * when d_weight is given) and derives the row pointers d_post_off [n_keys + 1] (uint32). */
-int vt_posting_keys(const int64_t *d_row_off, const int32_t *d_node, int64_t n_img,
-                    int32_t shard_size, int64_t n_ref, uint32_t *d_keys, uint32_t *d_entry,
-                    int32_t *d_entry_img, void *stream);
-int vt_posting_fill(const uint32_t *d_sorted_keys, const uint32_t *d_sorted_entry, int64_t nnz,
-                    const int32_t *d_entry_img, const int32_t *d_count, const float *d_weight,
-                    int32_t shard_size, int64_t n_keys, uint32_t *d_post_off, void *d_postings,
-                    void *stream);
-/* tf-mode variant without the gather: vt_posting_pack writes the key and, as the value to sort with it,
- * the posting itself -- (count << log2(shard_size)) | local image id (shard_size a power of two; counts
- * fit: an image has at most vt_encode_max_words() descriptors); vt_posting_unpack turns the sorted pairs
- * into d_postings / d_post_off (nnz > 0).  Same result as vt_posting_keys + vt_posting_fill with counts. */
+ * A posting is ONE uint32: (tf << 13) | local image id inside its shard (an image has at most
+ * vt_encode_max_words() = 8192 descriptors, so tf fits the upper 19 bits).  vt_posting_pack writes, for every
+ * forward-CSR entry, its key and that posting as the value to sort with it; vt_sort_pairs (stable => postings
+ * stay in image order) leaves the sorted values = the posting array; vt_posting_offsets derives the row
+ * pointers d_post_off [n_keys + 1] (uint32) from the sorted keys.  tf-idf / L1 scoring uses the same tf
+ * postings (weights enter on the query side, vt_score_topk_weighted). */
 int vt_posting_pack(const int64_t *d_row_off, const int32_t *d_node, const int32_t *d_count,
                     int64_t n_img, int32_t shard_size, int64_t n_ref, uint32_t *d_keys,
                     uint32_t *d_packed, void *stream);
-int vt_posting_unpack(const uint32_t *d_sorted_keys, const uint32_t *d_sorted_packed, int64_t nnz,
-                      int32_t shard_size, int64_t n_keys, uint32_t *d_post_off, void *d_postings,
-                      void *stream);
+int vt_posting_offsets(const uint32_t *d_sorted_keys, int64_t nnz, int64_t n_keys, uint32_t *d_post_off,
+                       void *stream);
 
 /* ---- scoring + top-k: Database.score / Database.retrieve, database.py:59-81 -----------------
- * Queries are a CSR batch (d_q_off [n_query+1], d_q_node, d_q_val = tf as float or weight).
+ * Queries are a CSR batch (d_q_off [n_query+1], d_q_node, d_q_val = tf as float); mode VT_SCORE_TF_L2 only
+ * (the weighted modes: vt_score_topk_weighted).
  * vt_score_topk writes, per (query, shard), the topk best (rank key, global image id) pairs:
  * d_shard_key / d_shard_id [n_query, n_shards, topk] (id -1 = no candidate); optionally every
  * image's rank key in d_all_key [n_query, n_img].  vt_topk_merge merges n_cand candidates per
@@ -283,6 +274,15 @@ int vt_score_topk_seeded(const uint32_t *d_post_off, const void *d_postings, con
                          const float *d_q_val, int64_t n_query, int topk, const int32_t *d_seed,
                          int64_t seed_stride, double *d_shard_key, int32_t *d_shard_id, double *d_all_key,
                          void *stream);
+
+/* ---- dense encoders: any object with embedding(image) (the reference's plugin protocol; its AlexNet encoder,
+ * encoders/alexnet.py:15-19) goes through Database.retrieve with dense embeddings.  vt_dense_scores evaluates
+ * || d/|d| - q/|q| ||_2 (database.py:66-69) for already normalised binary64 rows, NaN -> 1e6; vt_topk_rows selects the
+ * topk smallest per (query, shard) as lists for vt_topk_merge_scored. */
+int vt_dense_scores(const double *d_db_unit, int64_t n, int64_t dim, const double *d_q_unit, int64_t n_query,
+                    double *d_out, void *stream);
+int vt_topk_rows(const double *d_score, int64_t n, int64_t n_query, int topk, double *d_shard_key,
+                 int32_t *d_shard_id, double *d_shard_score, void *stream);
 
 /* ---- TF-IDF weighting + L1/L2 normalisation (what vocabulary.py:131,137 leaves commented out; opt-in) ----
  * Everything in binary64; the inverted file stays the exact integer tf index, the weights enter on the query

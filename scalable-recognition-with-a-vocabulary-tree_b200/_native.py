@@ -49,10 +49,8 @@ SIGNATURES = {
     "vt_encode": (_int, [_vp, _vp, _i64, _i32, _int, _vp, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vt_encode_max_words": (_int, []),
     "vt_csr_compact": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
-    "vt_posting_keys": (_int, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp]),
-    "vt_posting_fill": (_int, [_vp, _vp, _i64, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp]),
     "vt_posting_pack": (_int, [_vp, _vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp]),
-    "vt_posting_unpack": (_int, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp]),
+    "vt_posting_offsets": (_int, [_vp, _i64, _i64, _vp, _vp]),
     "vt_score_shard_size": (_int, []),
     "vt_score_max_topk": (_int, []),
     "vt_rnorm": (_int, [_vp, _i64, _vp, _vp]),
@@ -61,6 +59,8 @@ SIGNATURES = {
     "vt_dense_scatter": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _int, _vp, _vp]),
     "vt_dense_dots": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp, _i64, _vp]),
     "vt_score_topk_seeded": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _int, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "vt_dense_scores": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp]),
+    "vt_topk_rows": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp, _vp]),
     "vt_idf": (_int, [_vp, _i64, _i64, _vp, _vp]),
     "vt_weighted_rnorm": (_int, [_vp, _vp, _vp, _i64, _vp, _int, _vp, _vp]),
     "vt_query_weights": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _int, _vp, _vp, _vp]),

@@ -173,42 +173,6 @@ encode_kernel(const int32_t *__restrict__ word, const int64_t *__restrict__ img_
 }
 
 // ---- inverted file ------------------------------------------------------------------------------
-__global__ void posting_keys_kernel(const int64_t *__restrict__ row_off, const int32_t *__restrict__ node, int64_t n_img,
-                                    int32_t shard_size, int64_t n_ref, uint32_t *__restrict__ keys,
-                                    uint32_t *__restrict__ entry, int32_t *__restrict__ entry_img)
-{
-    const uint32_t n_shards = (uint32_t)((n_img + shard_size - 1) / shard_size);
-    for (int64_t img = blockIdx.x; img < n_img; img += gridDim.x) {
-        const int64_t b = row_off[img], e = row_off[img + 1];
-        const uint32_t shard = (uint32_t)(img / shard_size);
-        for (int64_t t = b + threadIdx.x; t < e; t += blockDim.x) {
-            // node-major rows: the posting list of a node is one contiguous, image-ordered run and the
-            // shards are consecutive ranges of it (row pointers of one node for all shards are adjacent)
-            keys[t] = (uint32_t)node[t] * n_shards + shard;
-            entry[t] = (uint32_t)t;
-            entry_img[t] = (int32_t)img;
-        }
-    }
-}
-
-__global__ void posting_fill_kernel(const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ sentry, int64_t nnz,
-                                    const int32_t *__restrict__ entry_img, const int32_t *__restrict__ count,
-                                    const float *__restrict__ weight, int32_t shard_size, int64_t n_keys,
-                                    uint32_t *__restrict__ post_off, uint2 *__restrict__ postings)
-{
-    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t key = skeys[p];
-        const uint32_t e = sentry[p];
-        const uint32_t local = (uint32_t)(entry_img[e] % shard_size);
-        postings[p] = make_uint2(local, weight ? __float_as_uint(weight[e]) : (uint32_t)count[e]);
-        // row pointers: every key in (previous key, key] starts at p
-        const int64_t prev = p == 0 ? -1 : (int64_t)skeys[p - 1];
-        for (int64_t kk = prev + 1; kk <= (int64_t)key; ++kk) post_off[kk] = (uint32_t)p;
-        if (p == nnz - 1)
-            for (int64_t kk = (int64_t)key + 1; kk <= n_keys; ++kk) post_off[kk] = (uint32_t)nnz;
-    }
-}
-
 // tf postings without a gather: the sort value carries the posting itself, (count << shard_bits) | local image
 __global__ void posting_pack_kernel(const int64_t *__restrict__ row_off, const int32_t *__restrict__ node,
                                     const int32_t *__restrict__ count, int64_t n_img, int shard_bits, int64_t n_ref,
@@ -226,16 +190,13 @@ __global__ void posting_pack_kernel(const int64_t *__restrict__ row_off, const i
     }
 }
 
-__global__ void posting_unpack_kernel(const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ spacked, int64_t nnz,
-                                      int shard_bits, int64_t n_keys, uint32_t *__restrict__ post_off,
-                                      uint2 *__restrict__ postings)
+// row pointers of the sorted keys: every key in (previous key, key] starts at p.  The sorted packed values are the
+// postings themselves.
+__global__ void posting_offsets_kernel(const uint32_t *__restrict__ skeys, int64_t nnz, int64_t n_keys,
+                                       uint32_t *__restrict__ post_off)
 {
-    const uint32_t lmask = (1u << shard_bits) - 1u;
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t key = skeys[p];
-        const uint32_t v = spacked[p];
-        postings[p] = make_uint2(v & lmask, v >> shard_bits);
-        // row pointers: every key in (previous key, key] starts at p
         const int64_t prev = p == 0 ? -1 : (int64_t)skeys[p - 1];
         for (int64_t kk = prev + 1; kk <= (int64_t)key; ++kk) post_off[kk] = (uint32_t)p;
         if (p == nnz - 1)
@@ -307,45 +268,10 @@ extern "C" int vt_encode(const int32_t *d_word, const int64_t *d_img_off, int64_
 #undef VT_E
 }
 
-extern "C" int vt_posting_keys(const int64_t *d_row_off, const int32_t *d_node, int64_t n_img, int32_t shard_size,
-                               int64_t n_ref, uint32_t *d_keys, uint32_t *d_entry, int32_t *d_entry_img, void *stream)
-{
-    VT_CHECK_ARG(n_img >= 0 && shard_size > 0 && n_ref > 0, "bad sizes");
-    const int64_t n_shards = (n_img + shard_size - 1) / shard_size;
-    VT_CHECK_ARG(n_shards * n_ref < ((int64_t)1 << 32), "shards * nodes must fit 32 bits");
-    if (n_img == 0) return VT_OK;
-    const int64_t cap = (int64_t)vt_sm_count() * 16;
-    posting_keys_kernel<<<(int)(n_img < cap ? n_img : cap), 128, 0, (cudaStream_t)stream>>>(
-        d_row_off, d_node, n_img, shard_size, n_ref, d_keys, d_entry, d_entry_img);
-    VT_LAUNCH_CHECK();
-    return VT_OK;
-}
-
-extern "C" int vt_posting_fill(const uint32_t *d_sorted_keys, const uint32_t *d_sorted_entry, int64_t nnz,
-                               const int32_t *d_entry_img, const int32_t *d_count, const float *d_weight,
-                               int32_t shard_size, int64_t n_keys, uint32_t *d_post_off, void *d_postings, void *stream)
-{
-    VT_CHECK_ARG(nnz >= 0 && nnz < ((int64_t)1 << 32) && n_keys >= 0 && shard_size > 0, "bad sizes");
-    VT_CHECK_ARG(d_count || d_weight, "need counts or weights");
-    cudaStream_t s = (cudaStream_t)stream;
-    if (nnz == 0) {
-        const int64_t cap = (int64_t)vt_sm_count() * 16, want = (n_keys + 1 + 255) / 256;
-        fill_u32_kernel<<<(int)(want < cap ? want : cap), 256, 0, s>>>(d_post_off, n_keys + 1, 0u);
-        VT_LAUNCH_CHECK();
-        return VT_OK;
-    }
-    const int64_t cap = (int64_t)vt_sm_count() * 16, want = (nnz + 255) / 256;
-    posting_fill_kernel<<<(int)(want < cap ? want : cap), 256, 0, s>>>(d_sorted_keys, d_sorted_entry, nnz, d_entry_img,
-                                                                       d_count, d_weight, shard_size, n_keys, d_post_off,
-                                                                       (uint2 *)d_postings);
-    VT_LAUNCH_CHECK();
-    return VT_OK;
-}
-
-// tf-mode variant of vt_posting_keys / vt_posting_fill: the value sorted along with the key IS the posting,
-// (count << log2(shard_size)) | local image id, so building the inverted file needs no gather through entry
-// indices (the two random 4-byte reads per posting of vt_posting_fill).  shard_size must be a power of two and
-// counts must fit the remaining bits (vt_encode_max_words() = 8192 descriptors per image do).
+// The inverted file: node-major, sharded by image range.  The value sorted along with the key (node * n_shards + shard)
+// IS the posting, (count << log2(shard_size)) | local image id, so building the inverted file needs no gather through
+// entry indices and a posting is 4 bytes.  shard_size must be a power of two and counts must fit the remaining bits
+// (vt_encode_max_words() = 8192 descriptors per image do).
 extern "C" int vt_posting_pack(const int64_t *d_row_off, const int32_t *d_node, const int32_t *d_count, int64_t n_img,
                                int32_t shard_size, int64_t n_ref, uint32_t *d_keys, uint32_t *d_packed, void *stream)
 {
@@ -364,17 +290,21 @@ extern "C" int vt_posting_pack(const int64_t *d_row_off, const int32_t *d_node, 
     return VT_OK;
 }
 
-extern "C" int vt_posting_unpack(const uint32_t *d_sorted_keys, const uint32_t *d_sorted_packed, int64_t nnz,
-                                 int32_t shard_size, int64_t n_keys, uint32_t *d_post_off, void *d_postings, void *stream)
+// row pointers d_post_off [n_keys + 1] of the sorted keys; the sorted packed values are the posting array as they are
+extern "C" int vt_posting_offsets(const uint32_t *d_sorted_keys, int64_t nnz, int64_t n_keys, uint32_t *d_post_off,
+                                  void *stream)
 {
-    VT_CHECK_ARG(nnz > 0 && nnz < ((int64_t)1 << 32) && n_keys >= 0, "bad sizes");
-    VT_CHECK_ARG(shard_size > 0 && (shard_size & (shard_size - 1)) == 0, "shard_size must be a power of two");
-    VT_CHECK_ARG(d_sorted_keys && d_sorted_packed && d_post_off && d_postings, "null buffer");
-    int shard_bits = 0;
-    while ((1 << shard_bits) < shard_size) ++shard_bits;
+    VT_CHECK_ARG(nnz >= 0 && nnz < ((int64_t)1 << 32) && n_keys >= 0 && d_post_off, "bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (nnz == 0) {
+        const int64_t cap = (int64_t)vt_sm_count() * 16, want = (n_keys + 1 + 255) / 256;
+        fill_u32_kernel<<<(int)(want < cap ? want : cap), 256, 0, s>>>(d_post_off, n_keys + 1, 0u);
+        VT_LAUNCH_CHECK();
+        return VT_OK;
+    }
+    VT_CHECK_ARG(d_sorted_keys, "null buffer");
     const int64_t cap = (int64_t)vt_sm_count() * 16, want = (nnz + 255) / 256;
-    posting_unpack_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
-        d_sorted_keys, d_sorted_packed, nnz, shard_bits, n_keys, d_post_off, (uint2 *)d_postings);
+    posting_offsets_kernel<<<(int)(want < cap ? want : cap), 256, 0, s>>>(d_sorted_keys, nnz, n_keys, d_post_off);
     VT_LAUNCH_CHECK();
     return VT_OK;
 }

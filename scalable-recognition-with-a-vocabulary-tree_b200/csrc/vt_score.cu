@@ -3,7 +3,7 @@
 //
 // The database is sharded by image range (shard_size images, the same rule that shards it across
 // GPUs).  One CTA scores one (query, shard) pair: its lanes walk the posting lists of the query's
-// words inside that shard (node-major CSR, 8 B per posting: local image id + tf or weight) with
+// words inside that shard (node-major CSR, 4 B per posting: tf << 13 | local image id) with
 // several words and postings in flight per lane, accumulate the sparse dot products of all shard
 // images in shared memory, and select the shard's top-k -- in tf mode (the reference's semantics,
 // score_shard_tf_kernel) through an exact integer bound so that only a few dozen survivors need a
@@ -60,29 +60,28 @@ constexpr uint32_t SC_LONG = 24;
 constexpr int SC_UNROLL = 4;
 constexpr int SC_FETCH = 8;         // postings fetched together by one lane
 
+// A posting is ONE 32-bit word: (tf << 13) | local image index inside its shard of 8192 images -- exactly the value the
+// index build sorts (vt_posting_pack), so the sorted array IS the posting array (4 B per posting instead of 8).
+constexpr uint32_t SC_LOCAL_MASK = 8191u;
+constexpr int SC_LOCAL_BITS = 13;
+
 template <int MODE>
-__device__ __forceinline__ void accumulate(int *s_acci, float *s_accf, const uint2 pe, const float qv)
+__device__ __forceinline__ void accumulate(int *s_acci, float *, const uint32_t pe, const float qv)
 {
-    if (MODE == VT_SCORE_TF_L2) {
-        atomicAdd(&s_acci[pe.x], (int)qv * (int)pe.y);
-    } else if (MODE == VT_SCORE_W_L2) {
-        atomicAdd(&s_accf[pe.x], qv * __uint_as_float(pe.y));
-    } else {
-        const float dv = __uint_as_float(pe.y);
-        atomicAdd(&s_accf[pe.x], qv + dv - fabsf(qv - dv));
-    }
+    static_assert(MODE == VT_SCORE_TF_L2, "weighted modes run in vt_weight.cu");
+    atomicAdd(&s_acci[pe & SC_LOCAL_MASK], (int)qv * (int)(pe >> SC_LOCAL_BITS));
 }
 
 // one lane walks a short posting list: SC_FETCH postings are fetched before any is accumulated, so the
 // DRAM round trips of a list overlap instead of serialising behind the shared-memory atomics
 template <int MODE>
-__device__ __forceinline__ void walk_short(int *s_acci, float *s_accf, const uint2 *__restrict__ postings, uint32_t b,
+__device__ __forceinline__ void walk_short(int *s_acci, float *s_accf, const uint32_t *__restrict__ postings, uint32_t b,
                                            uint32_t e, float qv)
 {
     for (uint32_t p = b; p < e; p += SC_FETCH) {
-        uint2 pe[SC_FETCH];
+        uint32_t pe[SC_FETCH];
 #pragma unroll
-        for (int i = 0; i < SC_FETCH; ++i) pe[i] = p + i < e ? __ldg(postings + p + i) : make_uint2(0u, 0u);
+        for (int i = 0; i < SC_FETCH; ++i) pe[i] = p + i < e ? __ldg(postings + p + i) : 0u;
 #pragma unroll
         for (int i = 0; i < SC_FETCH; ++i)
             if (p + i < e) accumulate<MODE>(s_acci, s_accf, pe[i], qv);
@@ -92,7 +91,7 @@ __device__ __forceinline__ void walk_short(int *s_acci, float *s_accf, const uin
 // MODE: VT_SCORE_*.  R: images per shard.
 template <int MODE, int R>
 __global__ void __launch_bounds__(SC_THREADS)
-score_shard_kernel(const uint32_t *__restrict__ post_off, const uint2 *__restrict__ postings,
+score_shard_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__restrict__ postings,
                    const double *__restrict__ img_rnorm, int64_t n_img, int64_t n_ref, int n_shards,
                    const int64_t *__restrict__ q_off, const int32_t *__restrict__ q_node,
                    const float *__restrict__ q_val, int64_t n_query, int topk, double *__restrict__ out_key,
@@ -221,7 +220,7 @@ constexpr int SC_CAND = 256;
 // postings in registers; 6: long lists are walked by whole warps and want occupancy instead)
 template <int R, int MINB>
 __global__ void __launch_bounds__(SC_THREADS, MINB)
-score_shard_tf_kernel(const uint32_t *__restrict__ post_off, const uint2 *__restrict__ postings,
+score_shard_tf_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__restrict__ postings,
                       const double *__restrict__ img_rnorm, int64_t n_img, int64_t n_ref, int n_shards,
                       const int64_t *__restrict__ q_off, const int32_t *__restrict__ q_node,
                       const float *__restrict__ q_val, int64_t n_query, int topk, double *__restrict__ out_key,
@@ -512,6 +511,105 @@ topk_merge_scored_kernel(const double *__restrict__ in_key, const int32_t *__res
     }
 }
 
+// ---- dense encoders (any object with embedding(image), e.g. the reference's AlexNet, encoders/alexnet.py:15-19) -------
+// score(d, q) = || d/|d| - q/|q| ||_2 exactly as Database.score evaluates it (database.py:66-69), for unit rows that are
+// already normalised: one warp per database row, 8 queries at a time from shared memory, binary64, fixed summation
+// order (lane-strided partial sums, then an xor butterfly).  NaN (a zero embedding) -> 1e6 (database.py:70).
+constexpr int DS_Q = 8, DS_TILE = 512;
+__global__ void __launch_bounds__(256)
+dense_score_kernel(const double *__restrict__ db, int64_t n, int64_t d, const double *__restrict__ q, int64_t nq,
+                   double *__restrict__ out)
+{
+    __shared__ double s_q[DS_Q][DS_TILE];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t q0 = (int64_t)blockIdx.y * DS_Q;
+    const int nqh = (int)((nq - q0) < DS_Q ? (nq - q0) : DS_Q);
+    for (int64_t row0 = (int64_t)blockIdx.x * 8; row0 < n; row0 += (int64_t)gridDim.x * 8) {
+        const int64_t row = row0 + warp;
+        double acc[DS_Q];
+#pragma unroll
+        for (int j = 0; j < DS_Q; ++j) acc[j] = 0.0;
+        for (int64_t t0 = 0; t0 < d; t0 += DS_TILE) {
+            const int tl = (int)((d - t0) < DS_TILE ? (d - t0) : DS_TILE);
+            __syncthreads();
+            for (int i = threadIdx.x; i < DS_Q * DS_TILE; i += 256) {
+                const int j = i / DS_TILE, e = i - j * DS_TILE;
+                s_q[j][e] = (j < nqh && e < tl) ? q[(q0 + j) * d + t0 + e] : 0.0;
+            }
+            __syncthreads();
+            if (row < n) {
+                for (int e = lane; e < tl; e += 32) {
+                    const double x = db[row * d + t0 + e];
+#pragma unroll
+                    for (int j = 0; j < DS_Q; ++j) {
+                        const double df = x - s_q[j][e];
+                        acc[j] += df * df;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < DS_Q; ++j) {
+            double s = acc[j];
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(VT_FULL, s, o);
+            if (lane == 0 && row < n && j < nqh) {
+                const double r = sqrt(s);
+                out[(q0 + j) * n + row] = (r == r) ? r : 1e6;
+            }
+        }
+    }
+}
+
+// per (query, shard of R rows): the topk smallest scores, ties by smaller index (the reference's stable ascending sort,
+// database.py:79-80), as (key = -score, id, score) lists for vt_topk_merge_scored
+template <int R>
+__global__ void __launch_bounds__(SC_THREADS)
+topk_rows_kernel(const double *__restrict__ score, int64_t n, int64_t nq, int n_shards, int topk, double *__restrict__ out_key,
+                 int32_t *__restrict__ out_id, double *__restrict__ out_score)
+{
+    constexpr int PER = R / SC_THREADS;
+    extern __shared__ unsigned char s_raw[];
+    double *s_keys = reinterpret_cast<double *>(s_raw);
+    __shared__ double r_key[SC_WARPS];
+    __shared__ int32_t r_id[SC_WARPS];
+    __shared__ int r_owner[SC_WARPS];
+    for (int64_t pair = blockIdx.x; pair < nq * n_shards; pair += gridDim.x) {
+        const int64_t q = pair / n_shards;
+        const int shard = (int)(pair - q * n_shards);
+        const int64_t i0 = (int64_t)shard * R;
+        double bkey = -1e300; int32_t bid = 0x7fffffff;
+        for (int u = 0; u < PER; ++u) {
+            const int t = u * SC_THREADS + threadIdx.x;
+            const double key = i0 + t < n ? -score[q * n + i0 + t] : -1e300;     // padding never wins
+            s_keys[t] = key;
+            if (better(key, (int32_t)(i0 + t), bkey, bid)) { bkey = key; bid = (int32_t)(i0 + t); }
+        }
+        __syncthreads();
+        for (int r = 0; r < topk; ++r) {
+            double key = bkey; int32_t id = bid; int owner;
+            block_best(key, id, owner, r_key, r_id, r_owner);
+            const bool ok = key > -1e300;
+            if (threadIdx.x == 0) {
+                const size_t o = ((size_t)q * n_shards + shard) * topk + r;
+                out_key[o] = key;
+                out_id[o] = ok ? id : -1;
+                out_score[o] = ok ? -key : 1e6;
+            }
+            if (threadIdx.x == owner) {
+                if (ok) s_keys[id - i0] = -1e300;
+                bkey = -1e300; bid = 0x7fffffff;
+                for (int u = 0; u < PER; ++u) {
+                    const int t = u * SC_THREADS + threadIdx.x;
+                    const double k2 = s_keys[t];
+                    if (better(k2, (int32_t)(i0 + t), bkey, bid)) { bkey = k2; bid = (int32_t)(i0 + t); }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void rnorm_kernel(const unsigned long long *__restrict__ sumsq, int64_t n, double *__restrict__ rnorm)
 {
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
@@ -546,7 +644,7 @@ static int launch_score(const uint32_t *post_off, const void *postings, const do
     VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t pairs = n_query * n_shards;
     const int64_t cap = (int64_t)vt_sm_count() * 2 * 8;
-    kern<<<(int)(pairs < cap ? pairs : cap), SC_THREADS, smem, s>>>(post_off, (const uint2 *)postings, img_rnorm, n_img, n_ref,
+    kern<<<(int)(pairs < cap ? pairs : cap), SC_THREADS, smem, s>>>(post_off, (const uint32_t *)postings, img_rnorm, n_img, n_ref,
                                                                     n_shards, q_off, q_node, q_val, n_query, topk, out_key,
                                                                     out_id, all_key, shard_empty, nullptr, 0);
     VT_LAUNCH_CHECK();
@@ -567,12 +665,12 @@ static int launch_score_tf(const uint32_t *post_off, const void *postings, const
     if (long_lists) {
         auto kern = score_shard_tf_kernel<R, 6>;
         VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<blocks, SC_THREADS, smem, s>>>(post_off, (const uint2 *)postings, img_rnorm, n_img, n_ref, n_shards, q_off,
+        kern<<<blocks, SC_THREADS, smem, s>>>(post_off, (const uint32_t *)postings, img_rnorm, n_img, n_ref, n_shards, q_off,
                                               q_node, q_val, n_query, topk, out_key, out_id, shard_rho);
     } else {
         auto kern = score_shard_tf_kernel<R, 4>;
         VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<blocks, SC_THREADS, smem, s>>>(post_off, (const uint2 *)postings, img_rnorm, n_img, n_ref, n_shards, q_off,
+        kern<<<blocks, SC_THREADS, smem, s>>>(post_off, (const uint32_t *)postings, img_rnorm, n_img, n_ref, n_shards, q_off,
                                               q_node, q_val, n_query, topk, out_key, out_id, shard_rho);
     }
     VT_LAUNCH_CHECK();
@@ -595,8 +693,10 @@ extern "C" int vt_score_topk(const uint32_t *d_post_off, const void *d_postings,
                                d_shard_key, d_shard_id, d_shard_rho, long_lists, s);
     switch (mode) {
     case VT_SCORE_TF_L2: return launch_score<VT_SCORE_TF_L2>(d_post_off, d_postings, d_img_rnorm, n_img, n_ref, d_q_off, d_q_node, d_q_val, n_query, topk, d_shard_key, d_shard_id, d_all_key, d_shard_empty, s);
-    case VT_SCORE_W_L2: return launch_score<VT_SCORE_W_L2>(d_post_off, d_postings, d_img_rnorm, n_img, n_ref, d_q_off, d_q_node, d_q_val, n_query, topk, d_shard_key, d_shard_id, d_all_key, d_shard_empty, s);
-    case VT_SCORE_W_L1: return launch_score<VT_SCORE_W_L1>(d_post_off, d_postings, d_img_rnorm, n_img, n_ref, d_q_off, d_q_node, d_q_val, n_query, topk, d_shard_key, d_shard_id, d_all_key, d_shard_empty, s);
+    case VT_SCORE_W_L2:
+    case VT_SCORE_W_L1:
+        vt_set_error("vt_score_topk: the weighted modes run over the tf index in binary64: vt_score_topk_weighted");
+        return VT_EINVAL;
     }
     vt_set_error("vt_score_topk: unknown mode %d", mode);
     return VT_EINVAL;
@@ -673,8 +773,41 @@ extern "C" int vt_score_topk_seeded(const uint32_t *d_post_off, const void *d_po
     VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t pairs = n_query * n_shards, cap = (int64_t)vt_sm_count() * 2 * 8;
     kern<<<(int)(pairs < cap ? pairs : cap), SC_THREADS, smem, (cudaStream_t)stream>>>(
-        d_post_off, (const uint2 *)d_postings, d_img_rnorm, n_img, n_ref, n_shards, d_q_off, d_q_node, d_q_val, n_query, topk,
+        d_post_off, (const uint32_t *)d_postings, d_img_rnorm, n_img, n_ref, n_shards, d_q_off, d_q_node, d_q_val, n_query, topk,
         d_shard_key, d_shard_id, d_all_key, nullptr, d_seed, seed_stride);
+    VT_LAUNCH_CHECK();
+    return VT_OK;
+}
+
+// Dense-encoder path: scores of unit embedding rows, binary64 (d_out [n_query, n]).
+extern "C" int vt_dense_scores(const double *d_db_unit, int64_t n, int64_t dim, const double *d_q_unit, int64_t n_query,
+                               double *d_out, void *stream)
+{
+    VT_CHECK_ARG(d_db_unit && d_q_unit && d_out && n >= 0 && dim >= 1 && n_query >= 0, "bad arguments");
+    if (n == 0 || n_query == 0) return VT_OK;
+    const int64_t want = (n + 7) / 8, cap = (int64_t)vt_sm_count() * 8;
+    dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)((n_query + DS_Q - 1) / DS_Q));
+    dense_score_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_db_unit, n, dim, d_q_unit, n_query, d_out);
+    VT_LAUNCH_CHECK();
+    return VT_OK;
+}
+
+// top-k smallest scores per (query, shard of vt_score_shard_size() rows): lists [n_query, n_shards, topk] for
+// vt_topk_merge_scored (key = -score, ties by smaller index)
+extern "C" int vt_topk_rows(const double *d_score, int64_t n, int64_t n_query, int topk, double *d_shard_key,
+                            int32_t *d_shard_id, double *d_shard_score, void *stream)
+{
+    VT_CHECK_ARG(d_score && d_shard_key && d_shard_id && d_shard_score && n > 0 && n_query >= 0, "bad arguments");
+    VT_CHECK_ARG(topk >= 1 && topk <= SC_MAXK, "topk out of range");
+    if (n_query == 0) return VT_OK;
+    constexpr int R = 8192;
+    const int n_shards = (int)((n + R - 1) / R);
+    auto kern = topk_rows_kernel<R>;
+    const size_t smem = (size_t)R * 8;
+    VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t pairs = n_query * n_shards, cap = (int64_t)vt_sm_count() * 8;
+    kern<<<(int)(pairs < cap ? pairs : cap), SC_THREADS, smem, (cudaStream_t)stream>>>(d_score, n, n_query, n_shards, topk,
+                                                                                       d_shard_key, d_shard_id, d_shard_score);
     VT_LAUNCH_CHECK();
     return VT_OK;
 }

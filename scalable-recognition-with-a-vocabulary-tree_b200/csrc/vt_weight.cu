@@ -71,21 +71,24 @@ __device__ __forceinline__ bool better(double ka, int32_t ia, double kb, int32_t
     return ka > kb || (ka == kb && ia < ib);
 }
 
+// posting = (tf << 13) | local image index (the packed tf postings of vt_score.cu)
 template <int L1>
-__device__ __forceinline__ void accumulate(double *s_acc, const double *s_rn, const uint2 pe, double qv, double qi)
+__device__ __forceinline__ void accumulate(double *s_acc, const double *s_rn, const uint32_t pe, double qv, double qi)
 {
+    const uint32_t img = pe & 8191u;
+    const double tf = (double)(pe >> 13);
     if (L1) {
-        const double d = qi * (double)pe.y * s_rn[pe.x];
-        atomicAdd(&s_acc[pe.x], qv + d - fabs(qv - d));
+        const double d = qi * tf * s_rn[img];
+        atomicAdd(&s_acc[img], qv + d - fabs(qv - d));
     } else {
-        atomicAdd(&s_acc[pe.x], qv * (double)pe.y);
+        atomicAdd(&s_acc[img], qv * tf);
     }
 }
 
 // CTA per (query, shard of R images); lanes own query words, long posting runs go to the whole warp
 template <int L1, int R>
 __global__ void __launch_bounds__(WS_THREADS)
-score_shard_w_kernel(const uint32_t *__restrict__ post_off, const uint2 *__restrict__ postings,
+score_shard_w_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__restrict__ postings,
                      const double *__restrict__ img_rnorm, int64_t n_img, int n_shards,
                      const int64_t *__restrict__ q_off, const int32_t *__restrict__ q_node, const double *__restrict__ qv,
                      const double *__restrict__ qi, const double *__restrict__ q_rnorm, int64_t n_query, int topk,
@@ -222,7 +225,7 @@ extern "C" int vt_query_weights(const int64_t *d_row_off, const int32_t *d_node,
     return VT_OK;
 }
 
-// weighted scoring over the TF inverted file (d_postings: (local image, tf) as vt_posting_unpack writes them);
+// weighted scoring over the TF inverted file (d_postings: the packed 4-byte tf postings, (tf << 13) | local image);
 // per-shard top-k lists like vt_score_topk, merged by vt_topk_merge with mode VT_SCORE_W_L2 / VT_SCORE_W_L1
 extern "C" int vt_score_topk_weighted(const uint32_t *d_post_off, const void *d_postings, const double *d_img_rnorm,
                                       int64_t n_img, int64_t n_ref, const int64_t *d_q_off, const int32_t *d_q_node,
@@ -244,13 +247,13 @@ extern "C" int vt_score_topk_weighted(const uint32_t *d_post_off, const void *d_
         auto kern = score_shard_w_kernel<1, R>;
         const size_t smem = (size_t)R * 16;
         VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<blocks, WS_THREADS, smem, s>>>(d_post_off, (const uint2 *)d_postings, d_img_rnorm, n_img, n_shards, d_q_off,
+        kern<<<blocks, WS_THREADS, smem, s>>>(d_post_off, (const uint32_t *)d_postings, d_img_rnorm, n_img, n_shards, d_q_off,
                                               d_q_node, d_qv, d_qi, d_q_rnorm, n_query, topk, d_shard_key, d_shard_id, d_all_key);
     } else {
         auto kern = score_shard_w_kernel<0, R>;
         const size_t smem = (size_t)R * 8;
         VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<blocks, WS_THREADS, smem, s>>>(d_post_off, (const uint2 *)d_postings, d_img_rnorm, n_img, n_shards, d_q_off,
+        kern<<<blocks, WS_THREADS, smem, s>>>(d_post_off, (const uint32_t *)d_postings, d_img_rnorm, n_img, n_shards, d_q_off,
                                               d_q_node, d_qv, d_qi, d_q_rnorm, n_query, topk, d_shard_key, d_shard_id, d_all_key);
     }
     VT_LAUNCH_CHECK();

@@ -191,12 +191,15 @@ class Database(object):
 
     def _dense_scores(self, q_unit):
         """reference score of every indexed image against unit query rows [Q, D] -> [Q, N] float64:
-        ||d/|d| - q/|q|||_2 evaluated directly (exactly 0 for identical vectors), NaN -> 1e6."""
+        ||d/|d| - q/|q|||_2 evaluated directly (exactly 0 for identical vectors), NaN -> 1e6 (``vt_dense_scores``)."""
         import torch
-        out = torch.empty((q_unit.shape[0], self._dense_unit.shape[0]), dtype=torch.float64, device=q_unit.device)
-        for i in range(q_unit.shape[0]):
-            out[i] = (self._dense_unit - q_unit[i]).norm(dim=1)
-        return torch.nan_to_num(out, nan=1e6)
+        lib = nat.load()
+        n, dim = self._dense_unit.shape
+        out = torch.empty((q_unit.shape[0], n), dtype=torch.float64, device=q_unit.device)
+        with torch.cuda.device(q_unit.device):
+            nat.check(lib.vt_dense_scores(nat.ptr(self._dense_unit), n, dim, nat.ptr(q_unit.contiguous()), q_unit.shape[0],
+                                          nat.ptr(out), nat.stream_ptr()), "vt_dense_scores")
+        return out
 
     def _dense_query_rows(self, query_paths):
         import torch
@@ -204,27 +207,33 @@ class Database(object):
         return self._unit_rows(torch.from_numpy(q).to(self._device()))
 
     def _retrieve_batch_dense(self, query_paths, k, return_all):
+        """brute force over the dense embeddings: scores by ``vt_dense_scores``, per-shard selection by
+        ``vt_topk_rows``, merge by ``vt_topk_merge_scored`` (ascending score, ties keep ``image_paths`` order like the
+        reference's stable sort, database.py:79-80)."""
         import torch
         if self._dense_unit is None:
             self.index()
+        lib = nat.load()
         q = self._dense_query_rows(list(query_paths))
         n = self._dense_unit.shape[0]
         k = min(k, n)
-        if return_all or n <= 4 * k + 64:
-            scores = self._dense_scores(q)
-        else:
-            # one matrix product ranks everything; the best 4k + 64 are re-scored exactly
-            cos = torch.nan_to_num(q, nan=0.0) @ torch.nan_to_num(self._dense_unit, nan=0.0).T
-            bad = torch.isnan(self._dense_unit).any(dim=1)
-            cos[:, bad] = -2.0
-            cand = torch.topk(cos, 4 * k + 64, dim=1).indices.sort(dim=1).values
-            scores = torch.full((q.shape[0], n), float("inf"), dtype=torch.float64, device=q.device)
-            for i in range(q.shape[0]):
-                d = (self._dense_unit[cand[i]] - q[i]).norm(dim=1)
-                scores[i, cand[i]] = torch.nan_to_num(d, nan=1e6)
-        order = torch.sort(scores, dim=1, stable=True)          # ties keep image_paths order (database.py:79-80)
-        ids = order.indices[:, :k].to(torch.int32).cpu().numpy()
-        sc = order.values[:, :k].cpu().numpy()
+        if k > lib.vt_score_max_topk():
+            raise ValueError("top-%d requested; at most %d per query" % (k, lib.vt_score_max_topk()))
+        scores = self._dense_scores(q)
+        nq, dev = q.shape[0], q.device
+        n_shards = (n + lib.vt_score_shard_size() - 1) // lib.vt_score_shard_size()
+        skey = torch.empty((nq, n_shards, k), dtype=torch.float64, device=dev)
+        sid = torch.empty((nq, n_shards, k), dtype=torch.int32, device=dev)
+        ssc = torch.empty((nq, n_shards, k), dtype=torch.float64, device=dev)
+        okey = torch.empty((nq, k), dtype=torch.float64, device=dev)
+        oid = torch.empty((nq, k), dtype=torch.int32, device=dev)
+        osc = torch.empty((nq, k), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            s = nat.stream_ptr()
+            nat.check(lib.vt_topk_rows(nat.ptr(scores), n, nq, k, nat.ptr(skey), nat.ptr(sid), nat.ptr(ssc), s), "vt_topk_rows")
+            nat.check(lib.vt_topk_merge_scored(nat.ptr(skey), nat.ptr(sid), nat.ptr(ssc), nq, n_shards * k, k, nat.ptr(okey),
+                                               nat.ptr(oid), nat.ptr(osc), s), "vt_topk_merge_scored")
+        ids, sc = oid.cpu().numpy(), osc.cpu().numpy()
         if return_all:
             return ids, sc, scores.cpu().numpy()
         return ids, sc

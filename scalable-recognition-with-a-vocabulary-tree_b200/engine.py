@@ -295,6 +295,37 @@ class CudaLevelOps:
         return sort_pairs(keys[:n_active], perm, int(n_rows).bit_length())
 
 
+class _ChangedProbes:
+    """Asynchronous reads of the device-side `changed` counter of the Lloyd passes: ``add`` copies the counter into a
+    pinned slot and records an event right behind the copy; ``get(i)`` waits for pass i only.  One pinned buffer per
+    build.  CPU tensors (gloo protocol tests) are read directly."""
+
+    def __init__(self, slots: int, cuda: bool):
+        self.host = torch.empty(slots, dtype=torch.int64)
+        if cuda:
+            self.host = self.host.pin_memory()
+        self.cuda, self.events, self.base = cuda, [], 0
+
+    def reset(self):
+        self.events = []
+
+    def add(self, changed: torch.Tensor):
+        i = len(self.events)
+        if not self.cuda:
+            self.host[i] = int(changed.item())
+            self.events.append(None)
+            return
+        self.host[i:i + 1].copy_(changed, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events.append(ev)
+
+    def get(self, i: int) -> int:
+        if self.events[i] is not None:
+            self.events[i].synchronize()
+        return int(self.host[i])
+
+
 @_device_scoped
 def build_tree(desc: torch.Tensor, d: int, k: int, depth: int, n_iter: int = 10, comm=None,
                stats: torch.Tensor = None, log=None, ops=None) -> FlatTree:
@@ -331,6 +362,7 @@ def build_tree(desc: torch.Tensor, d: int, k: int, depth: int, n_iter: int = 10,
     seg_local = torch.tensor([n], dtype=torch.int64, device=dev)
     seg_global = torch.tensor([n_total], dtype=torch.int64, device=dev)
 
+    probes = _ChangedProbes(n_iter + 1, dev.type == "cuda")
     split = subtree_split_level(k, depth, comm.world) if comm.world > 1 else None
     publish, published_from = None, None
     for level in range(depth):
@@ -394,15 +426,22 @@ def build_tree(desc: torch.Tensor, d: int, k: int, depth: int, n_iter: int = 10,
             else:
                 local_counts = counts
 
-        converged = False
-        iters = 0
+        # Lloyd passes.  "labels repeat" (changed == 0) is a fixed point: one more update + assign reproduces the same
+        # sums, centres and labels bit for bit.  So the counter of pass `it` is read one pass LATE, from a pinned copy
+        # whose event was recorded right behind the pass: the device never idles for the host round trip, and
+        # stopping one pass after the fixed point leaves exactly the state of stopping at it.
+        converged, iters = False, 0
+        probes.reset()
         for it in range(n_iter):
             assign()
-            if it > 0 and int(changed.item()) == 0:
-                converged = True                                          # labels repeat: fixed point
+            probes.add(changed)
+            if it > 1 and probes.get(it - 1) == 0:
+                converged, iters = True, it - 1                           # fixed point reached at pass it - 1
                 break
             ops.kmeans_update(sums, counts, n_rows, dp, child_cent)
-            iters += 1
+            iters = it + 1
+        if not converged and n_iter > 1 and probes.get(n_iter - 1) == 0:
+            converged, iters = True, n_iter - 1                           # ... at the last pass: the labels are current
         if not converged:
             assign()                                                      # labels_ against the final centres
         if log is not None:
@@ -563,38 +602,29 @@ def query_weights(q: dict, idf: torch.Tensor, norm: str = "l2") -> dict:
 
 # --------------------------------------------------------------------------------------- index
 @_device_scoped
-def build_index(csr: dict, n_ref: int, weight: torch.Tensor = None) -> dict:
-    """Forward CSR -> inverted file sharded by image range (postings in image order)."""
+def build_index(csr: dict, n_ref: int) -> dict:
+    """Forward CSR -> inverted file sharded by image range (postings in image order, 4 bytes each:
+    (tf << 13) | local image index).  The same index serves tf, tf-idf/L2 and tf-idf/L1 scoring."""
     lib = _lib()
-    dev = csr["row_off"].device
+    dev = csr["sumsq"].device
     s = nat.stream_ptr()
     n_img, nnz = csr["n_img"], csr["nnz"]
     shard = lib.vt_score_shard_size()
     n_shards = max(1, (n_img + shard - 1) // shard)
     n_keys = n_shards * n_ref
-    keys = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
-    entry = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
-    postings = torch.empty((max(nnz, 1), 2), dtype=torch.int32, device=dev)
     n_bits = int(n_keys).bit_length()
+    post_off = torch.empty(n_keys + 1, dtype=torch.int32, device=dev)
     if nnz == 0:                 # no image has a descriptor (or there is no image): every posting list is empty
-        post_off = torch.zeros(n_keys + 1, dtype=torch.int32, device=dev)
-    elif weight is None:
-        # tf postings: the value sorted with the key is the posting itself (count | local image), no gather
-        post_off = torch.empty(n_keys + 1, dtype=torch.int32, device=dev)
-        nat.check(lib.vt_posting_pack(nat.ptr(csr["row_off"]), nat.ptr(csr["node"]), nat.ptr(csr["count"]), n_img, shard,
-                                      n_ref, nat.ptr(keys), nat.ptr(entry), s), "vt_posting_pack")
-        skeys, spacked = sort_pairs(keys[:nnz], entry[:nnz], n_bits)
-        nat.check(lib.vt_posting_unpack(nat.ptr(skeys), nat.ptr(spacked), nnz, shard, n_keys, nat.ptr(post_off),
-                                        nat.ptr(postings), s), "vt_posting_unpack")
+        postings = torch.empty(1, dtype=torch.int32, device=dev)
+        nat.check(lib.vt_posting_offsets(None, 0, n_keys, nat.ptr(post_off), s), "vt_posting_offsets")
     else:
-        post_off = torch.empty(n_keys + 1, dtype=torch.int32, device=dev)
-        entry_img = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
-        nat.check(lib.vt_posting_keys(nat.ptr(csr["row_off"]), nat.ptr(csr["node"]), n_img, shard, n_ref, nat.ptr(keys),
-                                      nat.ptr(entry), nat.ptr(entry_img), s), "vt_posting_keys")
-        skeys, sentry = sort_pairs(keys[:nnz], entry[:nnz], n_bits)
-        nat.check(lib.vt_posting_fill(nat.ptr(skeys), nat.ptr(sentry), nnz, nat.ptr(entry_img), nat.ptr(csr["count"]),
-                                      nat.ptr(weight), shard, n_keys, nat.ptr(post_off), nat.ptr(postings), s),
-                  "vt_posting_fill")
+        keys = torch.empty(nnz, dtype=torch.int32, device=dev)
+        packed = torch.empty(nnz, dtype=torch.int32, device=dev)
+        nat.check(lib.vt_posting_pack(nat.ptr(csr["row_off"]), nat.ptr(csr["node"]), nat.ptr(csr["count"]), n_img, shard,
+                                      n_ref, nat.ptr(keys), nat.ptr(packed), s), "vt_posting_pack")
+        skeys, postings = sort_pairs(keys, packed, n_bits)        # the sorted values ARE the postings
+        nat.check(lib.vt_posting_offsets(nat.ptr(skeys), nnz, n_keys, nat.ptr(post_off), s), "vt_posting_offsets")
+        del keys, packed, skeys
     rnorm = torch.empty(max(n_img, 1), dtype=torch.float64, device=dev)
     nat.check(lib.vt_rnorm(nat.ptr(csr["sumsq"]), n_img, nat.ptr(rnorm), s), "vt_rnorm")
     shard_empty = torch.zeros(n_shards, dtype=torch.uint8, device=dev)
@@ -614,7 +644,7 @@ def build_index(csr: dict, n_ref: int, weight: torch.Tensor = None) -> dict:
     long_lists = bool(nnz > 0 and float((lens * lens).sum().item()) / float(nnz) > 64.0)
     return dict(post_off=post_off, postings=postings[:nnz], rnorm=rnorm[:n_img], sumsq=csr["sumsq"], n_img=n_img,
                 shard_empty=shard_empty, shard_rho=shard_rho, long_lists=long_lists,
-                n_ref=n_ref, shard=shard, n_shards=n_shards, nnz=nnz, weighted=weight is not None)
+                n_ref=n_ref, shard=shard, n_shards=n_shards, nnz=nnz)
 
 
 # --------------------------------------------------------------------------------------- dense top (all-nodes indexes)
@@ -776,7 +806,7 @@ def score(index: dict, q: dict, topk: int, mode: int = nat.SCORE_TF_L2, q_val: t
     shard_key = torch.empty((max(nq, 1), n_shards, topk), dtype=torch.float64, device=dev)
     shard_id = torch.empty((max(nq, 1), n_shards, topk), dtype=torch.int32, device=dev)
     all_key = torch.empty((max(nq, 1), n_img), dtype=torch.float64, device=dev) if want_all else None
-    if mode != nat.SCORE_TF_L2 and not index.get("weighted", False):
+    if mode != nat.SCORE_TF_L2:
         # tf-idf modes over the integer tf index: binary64 weights on the query side, per-image weighted norms
         if weights is None or "img_rnorm" not in weights:
             raise ValueError("weighted scoring needs weights=dict(idf=..., img_rnorm=..., norm=...)")

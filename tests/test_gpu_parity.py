@@ -389,7 +389,8 @@ def test_postings_and_topk_match_reference(vt, cuda, name):
     index = vt.engine.build_index(csr, ft.n_ref)
     # posting lists: per node the (image, count) pairs, in image order
     off = index["post_off"].cpu().numpy().astype(np.int64)
-    post = index["postings"].cpu().numpy()
+    packed = index["postings"].cpu().numpy().view(np.uint32)          # (tf << 13) | local image index
+    post = np.stack([packed & 8191, packed >> 13], axis=1).astype(np.int64)
     counts = g["counts"]
     assert off[-1] == (counts > 0).sum() and index["n_shards"] == 1
     for node in range(ft.n_ref):
