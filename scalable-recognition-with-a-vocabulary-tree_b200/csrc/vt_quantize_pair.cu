@@ -50,7 +50,6 @@ template <int KP>
 struct LpCfg {
     using P = PlaneCfg<KP>;
     static constexpr int STAGES = KP <= 10 ? 8 : 6;             // even: stage parity == epilogue group
-    static constexpr int LAG = STAGES - 2;                      // cp.async groups a producer keeps in flight
     static constexpr int TMEM_ALLOC = KP <= 10 ? 256 : 512;     // >= STAGES x P::TMEM_COLS, power of two
     static constexpr int OFF_B = STAGES * MM_A_BYTES;
     static constexpr int OFF_CN = OFF_B + STAGES * P::B_BYTES;
@@ -176,7 +175,7 @@ level_pair_kernel(const LpArgs a)
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 0) {
-        for (int s = 0; s < S; ++s) { mbar_init(&bar_full[s], LP_PRODUCERS); mbar_init(&bar_acc[s], 1); mbar_init(&bar_empty[s], 4); }
+        for (int s = 0; s < S; ++s) { mbar_init(&bar_full[s], 32); mbar_init(&bar_acc[s], 1); mbar_init(&bar_empty[s], 4); }
         s_done[0] = 0; s_done[1] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
@@ -280,27 +279,15 @@ level_pair_kernel(const LpArgs a)
         // Order of work per CTA:  P1(c0)  P1(c1)  sort(c0) P2(c0)  P1(c2)  sort(c1) P2(c1) ...  -- phase 1 of the NEXT chunk is
         // in the pipeline while the child indices of the current chunk are collected, so the ring never drains.
         const int ptid = tid - 256, pw = warp - 8;
-        uint32_t g = 0;
-        int pending = 0;                                        // committed gathers whose full barrier is still to be arrived on
+        uint32_t g = 0;                                         // pipeline slots handed out so far (the same in every producer warp)
         int issued[2] = {0, 0};                                 // tiles handed to each epilogue group so far
         int snap_a[2] = {0, 0}, snap_b[2] = {0, 0};             // per list buffer: `issued` when its phase 1 had been issued
-        uint32_t snap_g[2] = {0, 0};
         const int newbits = bits * a.phases;
         const uint32_t newmask = (1u << newbits) - 1u;
         const long long my_chunks = n_chunks > blockIdx.x ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-        auto arrive_oldest = [&]() {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy smem writes -> tensor core
-            mbar_arrive(&bar_full[(g - (uint32_t)pending) % S]);
-            --pending;
-        };
-        auto flush = [&]() {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            while (pending > 0) arrive_oldest();
-        };
         // every tile issued before the snapshot has left the epilogue (both groups work in order)
         auto wait_done = [&](int buf) {
-            if (g - (uint32_t)pending < snap_g[buf]) flush();   // (only when little was issued since: last / sparse chunks)
             const volatile int *d = s_done;
             long long t0 = 0;
             for (uint32_t spins = 0; d[0] < 4 * snap_a[buf] || d[1] < 4 * snap_b[buf]; ++spins) {
@@ -314,9 +301,10 @@ level_pair_kernel(const LpArgs a)
             __threadfence_block();
         };
         // rows that take no part in the final phase (stopped earlier, or at phase 1): their slot of the output
-        auto none_outputs = [&](const uint32_t *lrow, const uint32_t *lkey, int start, int len, long long base) {
+        auto none_outputs = [&](const uint32_t *lrow, const uint32_t *lkey, int start, int len, long long base, int me,
+                                int stride) {
             if (a.mode == 1) return;
-            for (int i = ptid; i < len; i += LP_PRODUCERS) {
+            for (int i = me; i < len; i += stride) {
                 const long long pos = base + start + i;
                 if (a.mode == 2) {
                     a.keys_out[pos] = 0xffffffffu;
@@ -326,6 +314,9 @@ level_pair_kernel(const LpArgs a)
                 }
             }
         };
+        // Tiles are issued by ONE warp each (warp = slot index mod 8), so eight gathers are being set up concurrently; the
+        // copies complete asynchronously: every lane hands its cp.async operations to the stage's full barrier
+        // (cp.async.mbarrier.arrive.noinc), nobody waits for data here.
         auto issue_phase = [&](const uint32_t *lrow, const uint32_t *lkey, const uint32_t *lnode, int phase_flag,
                                bool final_phase, long long base, int buf) {
             const int nt = s_ntiles;
@@ -335,50 +326,49 @@ level_pair_kernel(const LpArgs a)
                 len = (int)tl_len[t] + 1;
                 const uint32_t node = lnode[start];
                 if (node == LP_NONE) {
-                    if (final_phase) none_outputs(lrow, lkey, start, len, base);
+                    if (final_phase && (t & 7) == pw) none_outputs(lrow, lkey, start, len, base, lane, 32);
                     continue;
                 }
-                const int st = (int)(g % S);
-                mbar_wait(&bar_empty[st], ((g / S) & 1u) ^ 1u);
-                {   // A tile: 8 lanes copy one 128 B row, 32 rows per pass, swizzled destination (as level_mma_kernel)
-                    const int r0 = ptid >> 3, j = ptid & 7;
-                    const uint32_t dst0 = smem_u32(sA + (size_t)st * MM_A_BYTES) +
-                                          (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128 + ((j ^ (r0 & 7)) << 4));
+                const uint32_t slot = g;
+                ++issued[g & 1u];
+                ++g;
+                if ((int)(slot & 7u) != pw) continue;
+                const int st = (int)(slot % S);
+                mbar_wait(&bar_empty[st], ((slot / S) & 1u) ^ 1u);
+                {   // A tile: 8 lanes copy one 128 B row, 4 rows per pass, swizzled destination (as level_mma_kernel)
+                    const int rq = lane >> 3, j = lane & 7;
+                    const uint32_t abase = smem_u32(sA + (size_t)st * MM_A_BYTES);
                     const uint8_t *col = a.desc + j * 16;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int r = r0 + 32 * i;
+#pragma unroll 8
+                    for (int i = 0; i < 32; ++i) {
+                        const int r = 4 * i + rq;
                         const bool ok = r < len;
                         const uint32_t rr = ok ? lrow[start + r] : 0u;
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + 4096u * i),
-                                     "l"(col + (size_t)rr * 128), "r"(ok ? 16 : 0));
+                        const uint32_t dst = abase + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(col + (size_t)rr * 128),
+                                     "r"(ok ? 16 : 0));
                     }
                 }
                 {
                     const uint8_t *bsrc = a.bimg + (size_t)node * P::B_BYTES;
                     const uint32_t bdst = smem_u32(sB + (size_t)st * P::B_BYTES);
-                    for (int c = ptid; c < P::B_BYTES / 16; c += LP_PRODUCERS)
+#pragma unroll
+                    for (int c = lane; c < P::B_BYTES / 16; c += 32)
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(bdst + c * 16), "l"(bsrc + c * 16));
-                    if (ptid < 4)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_cn + st * 16) + ptid * 16),
-                                     "l"(a.cn32 + (size_t)node * 16 + ptid * 4));
-                    if (ptid == 4)
+                    if (lane < 4)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_cn + st * 16) + lane * 16),
+                                     "l"(a.cn32 + (size_t)node * 16 + lane * 4));
+                    if (lane == 4)
                         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(s_flag + st)), "l"(a.cmask + node));
                 }
-                if (ptid == 0) {
+                if (lane == 0) {
                     LpTile ti;
                     ti.start = start; ti.len = len; ti.node = node; ti.pos0 = (int)(base + start);
                     ti.flags = phase_flag; ti.buf = buf;
                     tinfo[st] = ti;
                 }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                ++issued[g & 1u];
-                ++g;
-                ++pending;
-                if (pending > Cfg::LAG) {
-                    asm volatile("cp.async.wait_group %0;" ::"n"(Cfg::LAG) : "memory");
-                    arrive_oldest();
-                }
+                // the barrier completes when the copies of all 32 lanes have landed (and lane 0 has written tinfo)
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bar_full[st])) : "memory");
             }
         };
 
@@ -448,7 +438,7 @@ level_pair_kernel(const LpArgs a)
             const int buf = (int)(i & 1);
             const Lists L = lists(buf);
             issue_phase(L.c_row, L.c_key, L.c_node, 0, a.phases == 1, chunk_base(i), buf);
-            snap_a[buf] = issued[0]; snap_b[buf] = issued[1]; snap_g[buf] = g;
+            snap_a[buf] = issued[0]; snap_b[buf] = issued[1];
         };
 
         bool uni[2] = {false, false};
@@ -478,7 +468,7 @@ level_pair_kernel(const LpArgs a)
                 const long long base = chunk_base(i);
                 producers_sync();
                 if (nreal1[buf] == 0) {
-                    none_outputs(L.c_row, L.c_key, 0, clen, base);    // nothing alive in this chunk
+                    none_outputs(L.c_row, L.c_key, 0, clen, base, ptid, LP_PRODUCERS);    // nothing alive in this chunk
                 } else {
                     wait_done(buf);                              // the epilogue has left every child index in c_cls
                     // ---- stable counting sort of the chunk by child index (LP_STOP = stopped) ----
@@ -554,12 +544,13 @@ level_pair_kernel(const LpArgs a)
                 }
             }
         }
-        flush();
-        for (int e = 0; e < 2; ++e) {   // end markers through the same pipeline, one per epilogue group
+        for (int e = 0; e < 2; ++e) {   // end markers through the same pipeline, one per epilogue group (warp 8 issues them)
             const int st = (int)(g % S);
-            mbar_wait(&bar_empty[st], ((g / S) & 1u) ^ 1u);
-            if (ptid == 0) { LpTile ti; ti.start = 0; ti.len = 0; ti.node = 0; ti.flags = LPF_END; ti.pos0 = 0; ti.buf = 0; tinfo[st] = ti; }
-            mbar_arrive(&bar_full[st]);
+            if (pw == 0) {
+                mbar_wait(&bar_empty[st], ((g / S) & 1u) ^ 1u);
+                if (lane == 0) { LpTile ti; ti.start = 0; ti.len = 0; ti.node = 0; ti.flags = LPF_END; ti.pos0 = 0; ti.buf = 0; tinfo[st] = ti; }
+                mbar_arrive(&bar_full[st]);
+            }
             ++g;
         }
     } else {
@@ -568,6 +559,7 @@ level_pair_kernel(const LpArgs a)
         for (uint32_t g = 0; ends < 2; ++g) {
             const int st = (int)(g % S);
             mbar_wait(&bar_full[st], (g / S) & 1u);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // cp.async (generic proxy) writes -> tensor core reads
             asm volatile("tcgen05.fence::after_thread_sync;");
             const int flags = tinfo[st].flags;
             if (flags & LPF_END) {
