@@ -3,21 +3,26 @@
 // re-evaluation as level_mma_kernel in vt_quantize_mma.cu, hence the same ids).
 //
 // Why: one level per launch reads every 128-byte descriptor row from DRAM once per level (6 x 12.8 GB for 100 M rows
-// at k=10, L=6 against 13.2 GB of algorithmic traffic).  Here a persistent CTA takes a CHUNK of 1024 consecutive rows of
-// the node-grouped batch through two levels before anything goes back to DRAM:
+// at k=10, L=6 against 13.2 GB of algorithmic traffic).  Here a persistent CTA (one per SM) takes a CHUNK of 1024
+// consecutive rows of the node-grouped batch through two levels before anything goes back to DRAM:
 //   phase 1  the chunk's rows are gathered tile by tile (DRAM -> shared memory), one MMA per tile against the
 //            children of the tile's node, the epilogue leaves each row's child index in shared memory;
 //   sort     a stable counting sort of the chunk by child index (shared memory only) -- rows of one child become
 //            contiguous, so phase-2 tiles again meet a single node;
-//   phase 2  the same rows are gathered a second time, microseconds after the first read: 148 SMs x 2 CTAs x 128 KB of
-//            rows = 38 MB in flight, so this read is served by the 126 MB L2, not by DRAM;
+//   phase 2  the same rows are gathered a second time, microseconds after the first read: 148 SMs x 2 chunks x 128 KB of
+//            rows = 38 MB in flight, so this read is served by the 126 MB L2, not by DRAM (ncu: DRAM reads of a launch =
+//            one pass over the rows, L2 hit rate 47 %);
 //   output   packed paths with TWO new digits (one 8-bit radix pass regroups the batch instead of two split passes).
 // DRAM row traffic: 3 reads per descent at L=6 instead of 6.
 //
-// Roles inside a CTA (288 threads, 2 CTAs per SM): warps 0-3 epilogue (thread = TMEM lane = tile row), warps 4-7
-// producers (chunk bookkeeping, tile building, cp.async gathers into a 4-stage ring), warp 8 issues the MMAs.  Three
-// mbarrier arrays connect them (full: producers -> MMA, acc: tcgen05.commit -> epilogue, empty: epilogue ->
-// producers); a fourth barrier tells the producers that the epilogue has finished phase 1 of the chunk.
+// Roles inside a CTA (544 threads): warps 0-7 are two epilogue groups (group = tile parity; thread = TMEM lane = tile
+// row), warps 8-15 producers (chunk bookkeeping together; tiles are gathered by ONE warp each, warp = slot mod 8, with
+// cp.async), warp 16 issues the MMAs.  Two rings: 8 shared-memory stages (16 KB row tile + 4 KB planes), freed by
+// tcgen05.commit as soon as the MMA has read them, and 16 accumulator slots (32 TMEM columns + the node's norms, flags
+// and the tile record), freed by the epilogue.  mbarriers: full (producer warp -> MMA), sfree (commit -> producers),
+// acc (commit -> epilogue), afree (epilogue -> producers); per-group completion counters tell the producers when the
+// child indices of a chunk are complete.  Phase 1 of chunk i+1 is issued BEFORE phase 2 of chunk i, so the ring does
+// not drain while a chunk is being sorted.
 #include "vt_mma_common.cuh"
 #include <stdlib.h>
 
@@ -49,11 +54,15 @@ struct LpArgs {
 template <int KP>
 struct LpCfg {
     using P = PlaneCfg<KP>;
-    static constexpr int STAGES = KP <= 10 ? 8 : 6;             // even: stage parity == epilogue group
-    static constexpr int TMEM_ALLOC = KP <= 10 ? 256 : 512;     // >= STAGES x P::TMEM_COLS, power of two
+    // Two rings.  Shared-memory stages (row tile + planes) are released as soon as the MMA has read them
+    // (tcgen05.commit); accumulator slots (TMEM columns + the node's norms, flags and the tile record) live until the
+    // epilogue is through with the tile.  So a row tile occupies shared memory for gather + MMA only.
+    static constexpr int STAGES = KP <= 10 ? 8 : 6;
+    static constexpr int ACC = 512 / P::TMEM_COLS;              // 16 (k <= 10) or 8 accumulator slots; even: slot parity == epilogue group
+    static constexpr int TMEM_ALLOC = 512;
     static constexpr int OFF_B = STAGES * MM_A_BYTES;
     static constexpr int OFF_CN = OFF_B + STAGES * P::B_BYTES;
-    static constexpr int OFF_FLAG = OFF_CN + STAGES * 64;
+    static constexpr int OFF_FLAG = OFF_CN + ACC * 64;
     static constexpr int OFF_LIST = OFF_FLAG + 64;
     // per chunk buffer: six u32 lists (c_row c_key c_node s_row s_key s_node) and two u8 lists (c_cls s_d1); two buffers
     static constexpr int LIST_BYTES = 6 * LP_CHUNK * 4 + 2 * LP_CHUNK;
@@ -147,14 +156,17 @@ level_pair_kernel(const LpArgs a)
     uint8_t *sA = smem;
     uint8_t *sB = smem + Cfg::OFF_B;
     int *s_cn = reinterpret_cast<int *>(smem + Cfg::OFF_CN);
-    uint32_t *s_flag = reinterpret_cast<uint32_t *>(smem + Cfg::OFF_FLAG);   // [S] child-internal bitmask of the stage's node
+    uint32_t *s_flag = reinterpret_cast<uint32_t *>(smem + Cfg::OFF_FLAG);   // [ACC] child-internal bitmask of the slot's node
     uint8_t *tl_len = smem + Cfg::OFF_TL;
-    __shared__ __align__(8) unsigned long long bar_full[S], bar_acc[S], bar_empty[S];
-    __shared__ LpTile tinfo[S];
+    constexpr int AS = Cfg::ACC;
+    // full: gather landed (producers -> MMA);  sfree: MMA has read the stage (commit -> producers);
+    // acc: accumulator complete (commit -> epilogue);  afree: epilogue done with the slot (epilogue -> producers)
+    __shared__ __align__(8) unsigned long long bar_full[S], bar_sfree[S], bar_acc[AS], bar_afree[AS];
+    __shared__ LpTile tinfo[AS];
     __shared__ uint32_t s_tmem;
     __shared__ int s_ntiles, s_nreal;
     __shared__ int s_wcnt[8][32], s_run[8][32];
-    __shared__ int s_done[2];                                   // warp-tiles each epilogue group has completed (4 per tile)
+    __shared__ int s_done[8];                                   // tiles each epilogue WARP has completed (its group's tiles, in order)
 
     struct Lists { uint32_t *c_row, *c_key, *c_node, *s_row, *s_key, *s_node; uint8_t *c_cls, *s_d1; };
     auto lists = [&](int buf) {
@@ -175,8 +187,9 @@ level_pair_kernel(const LpArgs a)
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 0) {
-        for (int s = 0; s < S; ++s) { mbar_init(&bar_full[s], 32); mbar_init(&bar_acc[s], 1); mbar_init(&bar_empty[s], 4); }
-        s_done[0] = 0; s_done[1] = 0;
+        for (int s = 0; s < S; ++s) { mbar_init(&bar_full[s], 32); mbar_init(&bar_sfree[s], 1); }
+        for (int s = 0; s < AS; ++s) { mbar_init(&bar_acc[s], 1); mbar_init(&bar_afree[s], 4); }
+        for (int w = 0; w < 8; ++w) s_done[w] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -190,10 +203,11 @@ level_pair_kernel(const LpArgs a)
         // thread = TMEM lane = row of the tile
         const int grp = warp >> 2, qw = warp & 3, etid = tid & 127;
         unsigned int rechecks = 0;
+        int tiles_done = 0;
         const int none = 0x7fffffff;
         for (uint32_t g = (uint32_t)grp;; g += 2) {
-            const int st = (int)(g % S);
-            mbar_wait(&bar_acc[st], (g / S) & 1u);
+            const int st = (int)(g % AS);                       // accumulator slot
+            mbar_wait(&bar_acc[st], (g / AS) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;");
             const LpTile ti = tinfo[st];
             if (ti.flags & LPF_END) break;
@@ -218,11 +232,22 @@ level_pair_kernel(const LpArgs a)
             const uint32_t row = active ? lrow[idx] : 0u;
             int best = none, second = none, arg = 0;
             if (active) score_children_tree<KP, P::N>(v, s_cn + st * 16, best, second, arg);
-            const uint8_t *tileA = sA + (size_t)st * MM_A_BYTES;
-            // (second - 15: the tournament ranks scores coarsened to 16 units, see score_children_tree)
-            const bool contested = contested_row(active && k > 1, best, second - 15, tileA, etid);
-            unsigned int m = __ballot_sync(VT_FULL, contested);
             const uint8_t *xrow = a.desc + (size_t)row * 128;
+            // (second - 15: the tournament ranks scores coarsened to 16 units, see score_children_tree).  The row tile
+            // has left shared memory by now: the rare warps that still hold a candidate read |x|^2 from the row itself.
+            bool contested = active && k > 1 && contest_test(best, second - 15, 8323200.f);
+            if (__any_sync(VT_FULL, contested)) {
+                unsigned int xn = 0;
+                if (contested) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint4 qv = __ldg(reinterpret_cast<const uint4 *>(xrow) + j);
+                        xn = __dp4a(qv.x, qv.x, xn); xn = __dp4a(qv.y, qv.y, xn); xn = __dp4a(qv.z, qv.z, xn); xn = __dp4a(qv.w, qv.w, xn);
+                    }
+                }
+                contested = contested && contest_test(best, second - 15, (float)xn * 1.0000002f);
+            }
+            unsigned int m = __ballot_sync(VT_FULL, contested);
             while (m) {
                 const int src = __ffs(m) - 1;
                 m &= m - 1;
@@ -265,10 +290,11 @@ level_pair_kernel(const LpArgs a)
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncwarp();
+            ++tiles_done;
             if (lane == 0) {
-                mbar_arrive(&bar_empty[st]);
+                mbar_arrive(&bar_afree[st]);
                 __threadfence_block();                          // c_cls of this tile before the completion count
-                atomicAdd(&s_done[grp], 1);
+                *(volatile int *)&s_done[warp] = tiles_done;    // per warp: a warp that runs ahead must not stand in for a slow one
             }
         }
 #pragma unroll
@@ -286,11 +312,13 @@ level_pair_kernel(const LpArgs a)
         const uint32_t newmask = (1u << newbits) - 1u;
         const long long my_chunks = n_chunks > blockIdx.x ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-        // every tile issued before the snapshot has left the epilogue (both groups work in order)
+        // every tile issued before the snapshot has left the epilogue: EVERY warp of both groups (each works in order)
         auto wait_done = [&](int buf) {
             const volatile int *d = s_done;
             long long t0 = 0;
-            for (uint32_t spins = 0; d[0] < 4 * snap_a[buf] || d[1] < 4 * snap_b[buf]; ++spins) {
+            const int na = snap_a[buf], nb2 = snap_b[buf];
+            for (uint32_t spins = 0; d[0] < na || d[1] < na || d[2] < na || d[3] < na || d[4] < nb2 || d[5] < nb2 || d[6] < nb2 || d[7] < nb2;
+                 ++spins) {
                 __nanosleep(40);
                 if ((spins & 1023u) == 1023u) {
                     const long long t = clock64();
@@ -314,9 +342,18 @@ level_pair_kernel(const LpArgs a)
                 }
             }
         };
-        // Tiles are issued by ONE warp each (warp = slot index mod 8), so eight gathers are being set up concurrently; the
-        // copies complete asynchronously: every lane hands its cp.async operations to the stage's full barrier
-        // (cp.async.mbarrier.arrive.noinc), nobody waits for data here.
+        // Tiles are issued by ONE warp each (warp = slot index mod 8), so eight gathers are set up and in flight
+        // concurrently.  A warp publishes its tile when it comes back for its next one (or at the end of the phase): every
+        // lane waits for its own copies, orders them against the tensor core's proxy and arrives on the stage's barrier.
+        bool outstanding = false;
+        int out_st = 0;
+        auto publish = [&]() {
+            if (!outstanding) return;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy smem writes -> tensor core
+            mbar_arrive(&bar_full[out_st]);
+            outstanding = false;
+        };
         auto issue_phase = [&](const uint32_t *lrow, const uint32_t *lkey, const uint32_t *lnode, int phase_flag,
                                bool final_phase, long long base, int buf) {
             const int nt = s_ntiles;
@@ -333,8 +370,10 @@ level_pair_kernel(const LpArgs a)
                 ++issued[g & 1u];
                 ++g;
                 if ((int)(slot & 7u) != pw) continue;
-                const int st = (int)(slot % S);
-                mbar_wait(&bar_empty[st], ((slot / S) & 1u) ^ 1u);
+                const int st = (int)(slot % S), as = (int)(slot % AS);
+                publish();                                            // this warp's previous tile (issued eight slots ago)
+                mbar_wait(&bar_afree[as], ((slot / AS) & 1u) ^ 1u);   // the slot's norms / flags / tile record may be rewritten
+                mbar_wait(&bar_sfree[st], ((slot / S) & 1u) ^ 1u);    // the MMA of the stage's previous tile has read it
                 {   // A tile: 8 lanes copy one 128 B row, 4 rows per pass, swizzled destination (as level_mma_kernel)
                     const int rq = lane >> 3, j = lane & 7;
                     const uint32_t abase = smem_u32(sA + (size_t)st * MM_A_BYTES);
@@ -356,20 +395,22 @@ level_pair_kernel(const LpArgs a)
                     for (int c = lane; c < P::B_BYTES / 16; c += 32)
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(bdst + c * 16), "l"(bsrc + c * 16));
                     if (lane < 4)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_cn + st * 16) + lane * 16),
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_cn + as * 16) + lane * 16),
                                      "l"(a.cn32 + (size_t)node * 16 + lane * 4));
                     if (lane == 4)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(s_flag + st)), "l"(a.cmask + node));
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(s_flag + as)), "l"(a.cmask + node));
                 }
                 if (lane == 0) {
                     LpTile ti;
                     ti.start = start; ti.len = len; ti.node = node; ti.pos0 = (int)(base + start);
                     ti.flags = phase_flag; ti.buf = buf;
-                    tinfo[st] = ti;
+                    tinfo[as] = ti;
                 }
-                // the barrier completes when the copies of all 32 lanes have landed (and lane 0 has written tinfo)
-                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bar_full[st])) : "memory");
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                outstanding = true;
+                out_st = st;
             }
+            publish();                                           // nothing stays unpublished across the bookkeeping between phases
         };
 
         // chunk rows are fetched one chunk ahead: the global loads of chunk i+1 are in flight while chunk i is issued
@@ -545,10 +586,11 @@ level_pair_kernel(const LpArgs a)
             }
         }
         for (int e = 0; e < 2; ++e) {   // end markers through the same pipeline, one per epilogue group (warp 8 issues them)
-            const int st = (int)(g % S);
+            const int st = (int)(g % S), as = (int)(g % AS);
             if (pw == 0) {
-                mbar_wait(&bar_empty[st], ((g / S) & 1u) ^ 1u);
-                if (lane == 0) { LpTile ti; ti.start = 0; ti.len = 0; ti.node = 0; ti.flags = LPF_END; ti.pos0 = 0; ti.buf = 0; tinfo[st] = ti; }
+                mbar_wait(&bar_afree[as], ((g / AS) & 1u) ^ 1u);
+                mbar_wait(&bar_sfree[st], ((g / S) & 1u) ^ 1u);
+                if (lane == 0) { LpTile ti; ti.start = 0; ti.len = 0; ti.node = 0; ti.flags = LPF_END; ti.pos0 = 0; ti.buf = 0; tinfo[as] = ti; }
                 mbar_arrive(&bar_full[st]);
             }
             ++g;
@@ -557,20 +599,19 @@ level_pair_kernel(const LpArgs a)
         // ================================ MMA issuer ================================
         int ends = 0;
         for (uint32_t g = 0; ends < 2; ++g) {
-            const int st = (int)(g % S);
+            const int st = (int)(g % S), as = (int)(g % AS);
             mbar_wait(&bar_full[st], (g / S) & 1u);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // cp.async (generic proxy) writes -> tensor core reads
             asm volatile("tcgen05.fence::after_thread_sync;");
-            const int flags = tinfo[st].flags;
+            const int flags = tinfo[as].flags;
             if (flags & LPF_END) {
-                if (lane == 0) mbar_arrive(&bar_acc[st]);
+                if (lane == 0) { mbar_arrive(&bar_acc[as]); mbar_arrive(&bar_sfree[st]); }
                 ++ends;
                 continue;
             }
             if (lane == 0) {
                 const uint64_t a_desc = make_desc(smem_u32(sA + (size_t)st * MM_A_BYTES));
                 const uint64_t b_desc = make_desc(smem_u32(sB + (size_t)st * P::B_BYTES));
-                const uint32_t d_tmem = tmem + (uint32_t)(st * P::TMEM_COLS);
+                const uint32_t d_tmem = tmem + (uint32_t)(as * P::TMEM_COLS);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {                // K = 4 x 32 bytes
                     const uint32_t acc = ks > 0 ? 1u : 0u;
@@ -579,7 +620,9 @@ level_pair_kernel(const LpArgs a)
                         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
                         ::"r"(d_tmem), "l"(a_desc + 2 * ks), "l"(b_desc + 2 * ks), "r"(P::IDESC), "r"(acc), "r"(0u));
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_acc[st])) : "memory");
+                // one commit per consumer: the stage goes back to the producers, the accumulator to the epilogue
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_sfree[st])) : "memory");
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_acc[as])) : "memory");
             }
             __syncwarp();
         }
