@@ -41,9 +41,12 @@ __device__ __forceinline__ void dg_mbar_wait(unsigned long long *bar, uint32_t p
     uint32_t done;
     long long t0 = 0;
     for (uint32_t spins = 0;; ++spins) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        // (suspend-time hint: a waiting warp sleeps in the barrier unit instead of spinning through the issue slots the
+        // working warps need -- the first version of this kernel spent half of its instructions in this loop)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity), "r"(20000u) : "memory");
         if (done) return;
+        __nanosleep(64);
         if ((spins & 1023u) == 1023u) {                          // watchdog: trap instead of hanging the device
             const long long t = clock64();
             if (t0 == 0) t0 = t;
