@@ -671,7 +671,7 @@ extern "C" int vt_kmeans_assign_mma(const void *d_desc, int dtype, int dp, const
 int64_t vt_mma_prepared_bytes(int k, int depth);
 int vt_mma_levels_paired(const void *d_desc, int64_t n, const float *cent, const uint8_t *internal, const int32_t *ref_id,
                          int k, int depth, int32_t *leaf, int32_t *word, uint64_t *stats, const uint8_t *bimg,
-                         const int *cn32, uint32_t *cmask, void *sortwork, bool defer, cudaStream_t s, cudaEvent_t *ev,
+                         const int *cn32, int *cninfo, void *sortwork, bool defer, cudaStream_t s, cudaEvent_t *ev,
                          int *n_ev_io);
 
 // ids of (row, child) pairs that were bucketed by row range (the deferred output of the last level)
@@ -731,7 +731,7 @@ int64_t vt_mma_prepared_bytes(int k, int depth)
     for (int l = 0; l <= depth; ++l) { n_heap += p; p *= k; }
     return ((mma_int_nodes(k, depth) * mma_plane_bytes(k) + 255) / 256) * 256 + ((n_heap * 8 + 255) / 256) * 256 +
            ((mma_int_nodes(k, depth) * 64 + 255) / 256) * 256 +  // planes, 64-bit norms, 32-bit norms (16 per node)
-           mma_int_nodes(k, depth) * 4;                          // child-internal masks (vt_quantize_pair.cu)
+           mma_int_nodes(k, depth) * 80;                         // 80-byte node records (vt_quantize_pair.cu)
 }
 
 // the level loop; `prepared` from vt_mma_prepare, `sortwork` = 16 n + vt_sort_scratch_bytes(n) bytes
@@ -772,10 +772,10 @@ int vt_mma_levels(const void *d_desc, int64_t n, const float *cent, const uint8_
     }
     if (n >= pair_min && depth >= 2) {
         // two levels per launch (vt_quantize_pair.cu): every row is read from DRAM once per PAIR of levels
-        // (the child masks live behind the 32-bit norms of the prepared buffer; they are rewritten on every call, so the
+        // (the per-node records live behind the 32-bit norms of the prepared buffer; they are rewritten on every call, so the
         // buffer only has to be large enough -- vt_mma_prepared_bytes)
-        uint32_t *cmask = (uint32_t *)((uint8_t *)const_cast<int *>(cn) + ((n_int * 64 + 255) / 256) * 256);
-        const int rc = vt_mma_levels_paired(d_desc, n, cent, internal, ref_id, k, depth, leaf, word, stats, bimg, cn, cmask,
+        int *cninfo = (int *)((uint8_t *)const_cast<int *>(cn) + ((n_int * 64 + 255) / 256) * 256);
+        const int rc = vt_mma_levels_paired(d_desc, n, cent, internal, ref_id, k, depth, leaf, word, stats, bimg, cn, cninfo,
                                             sortwork, n >= defer_min, s, ev, &n_ev);
         if (n_ev_io) *n_ev_io = n_ev;
         return rc;

@@ -24,6 +24,7 @@
 // child indices of a chunk are complete.  Phase 1 of chunk i+1 is issued BEFORE phase 2 of chunk i, so the ring does
 // not drain while a chunk is being sorted.
 #include "vt_mma_common.cuh"
+#include <cuda.h>
 #include <stdlib.h>
 
 int vt_sort_pass_impl(const uint32_t *kin, const uint32_t *vin, uint32_t *kout, uint32_t *vout, int64_t n, int shift,
@@ -47,7 +48,8 @@ struct LpArgs {
     int level, phases, bits, k, mode;           // mode of the final phase: 0 = paths for the next launch, 1 = ids, 2 = (row, child) pairs
     long long n_heap;
     const float *cent; const uint8_t *internal; const int32_t *ref_id; const uint8_t *bimg; const int *cn32;
-    const uint32_t *cmask;                      // per node: bit c set <=> child c is internal (has children of its own)
+    const int *cninfo;                          // per node 20 ints (80 B, one bulk copy): the 16 squared norms of cn32, then the
+                                                // child mask (bit c set <=> child c is internal), then padding
     uint32_t *keys_out, *perm_out; int32_t *leaf_out, *word_out; unsigned long long *stats;
 };
 
@@ -62,8 +64,8 @@ struct LpCfg {
     static constexpr int TMEM_ALLOC = 512;
     static constexpr int OFF_B = STAGES * MM_A_BYTES;
     static constexpr int OFF_CN = OFF_B + STAGES * P::B_BYTES;
-    static constexpr int OFF_FLAG = OFF_CN + ACC * 64;
-    static constexpr int OFF_LIST = OFF_FLAG + 64;
+    static constexpr int OFF_LIST = OFF_CN + ACC * 80;
+    static constexpr uint32_t TX_BYTES = MM_A_BYTES + P::B_BYTES + 80;   // bytes one tile brings into shared memory
     // per chunk buffer: six u32 lists (c_row c_key c_node s_row s_key s_node) and two u8 lists (c_cls s_d1); two buffers
     static constexpr int LIST_BYTES = 6 * LP_CHUNK * 4 + 2 * LP_CHUNK;
     static constexpr int OFF_TL = OFF_LIST + 2 * LIST_BYTES;    // tile lengths of the phase being issued (u8)
@@ -149,7 +151,7 @@ __device__ __forceinline__ void build_tiles(const uint32_t *nodes, int len, uint
 
 template <int KP>
 __global__ void __launch_bounds__(LP_THREADS, 1)
-level_pair_kernel(const LpArgs a)
+level_pair_kernel(const LpArgs a, const __grid_constant__ CUtensorMap tmap)
 {
     using Cfg = LpCfg<KP>;
     using P = PlaneCfg<KP>;
@@ -159,7 +161,6 @@ level_pair_kernel(const LpArgs a)
     uint8_t *sA = smem;
     uint8_t *sB = smem + Cfg::OFF_B;
     int *s_cn = reinterpret_cast<int *>(smem + Cfg::OFF_CN);
-    uint32_t *s_flag = reinterpret_cast<uint32_t *>(smem + Cfg::OFF_FLAG);   // [ACC] child-internal bitmask of the slot's node
     uint8_t *tl_len = smem + Cfg::OFF_TL;
     constexpr int AS = Cfg::ACC;
     // full: gather landed (producers -> MMA);  sfree: MMA has read the stage (commit -> producers);
@@ -190,7 +191,7 @@ level_pair_kernel(const LpArgs a)
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 0) {
-        for (int s = 0; s < S; ++s) { mbar_init(&bar_full[s], 32); mbar_init(&bar_sfree[s], 1); }
+        for (int s = 0; s < S; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_sfree[s], 1); }
         for (int s = 0; s < AS; ++s) { mbar_init(&bar_acc[s], 1); mbar_init(&bar_afree[s], 4); }
         for (int w = 0; w < 8; ++w) s_done[w] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;");
@@ -234,7 +235,7 @@ level_pair_kernel(const LpArgs a)
             const int idx = ti.start + etid;
             const uint32_t row = active ? lrow[idx] : 0u;
             int best = none, second = none, arg = 0;
-            if (active) score_children_tree<KP, P::N>(v, s_cn + st * 16, best, second, arg);
+            if (active) score_children_tree<KP, P::N>(v, s_cn + st * 20, best, second, arg);
             const uint8_t *xrow = a.desc + (size_t)row * 128;
             // (second - 15: the tournament ranks scores coarsened to 16 units, see score_children_tree).  The row tile
             // has left shared memory by now: the rare warps that still hold a candidate read |x|^2 from the row itself.
@@ -261,7 +262,7 @@ level_pair_kernel(const LpArgs a)
             }
             if (active) {
                 const long long child = (long long)ti.node * k + 1 + arg;
-                const bool cont = ((s_flag[st] >> arg) & 1u) != 0;   // the child has children of its own
+                const bool cont = (((uint32_t)s_cn[st * 20 + 16] >> arg) & 1u) != 0;   // the child has children of its own
                 const bool final_phase = p2 || a.phases == 1;
                 if (!final_phase) {
                     // phase 1 of 2: the child index stays in shared memory; a row whose child is a leaf stops here
@@ -345,18 +346,10 @@ level_pair_kernel(const LpArgs a)
                 }
             }
         };
-        // Tiles are issued by ONE warp each (warp = slot index mod 8), so eight gathers are set up and in flight
-        // concurrently.  A warp publishes its tile when it comes back for its next one (or at the end of the phase): every
-        // lane waits for its own copies, orders them against the tensor core's proxy and arrives on the stage's barrier.
-        bool outstanding = false;
-        int out_st = 0;
-        auto publish = [&]() {
-            if (!outstanding) return;
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy smem writes -> tensor core
-            mbar_arrive(&bar_full[out_st]);
-            outstanding = false;
-        };
+        // Tiles are issued by ONE warp each (warp = slot index mod 8) with the TMA: lane g fetches rows 4g .. 4g+3 of the tile
+        // with one tile::gather4 (arbitrary row indices, 128B-swizzled destination = exactly the K-major tile the MMA reads,
+        // rows past the tile's length are out of range and arrive as zeros), lanes 0 and 1 bulk-copy the node's planes
+        // and its 80-byte record.  Everything completes on the stage's full barrier (expect_tx); nobody waits for data.
         auto issue_phase = [&](const uint32_t *lrow, const uint32_t *lkey, const uint32_t *lnode, int phase_flag,
                                bool final_phase, long long base, int buf) {
             const int nt = s_ntiles;
@@ -374,46 +367,36 @@ level_pair_kernel(const LpArgs a)
                 ++g;
                 if ((int)(slot & 7u) != pw) continue;
                 const int st = (int)(slot % S), as = (int)(slot % AS);
-                publish();                                            // this warp's previous tile (issued eight slots ago)
-                mbar_wait(&bar_afree[as], ((slot / AS) & 1u) ^ 1u);   // the slot's norms / flags / tile record may be rewritten
+                mbar_wait(&bar_afree[as], ((slot / AS) & 1u) ^ 1u);   // the slot's record / tile info may be rewritten
                 mbar_wait(&bar_sfree[st], ((slot / S) & 1u) ^ 1u);    // the MMA of the stage's previous tile has read it
-                {   // A tile: 8 lanes copy one 128 B row, 4 rows per pass, swizzled destination (as level_mma_kernel)
-                    const int rq = lane >> 3, j = lane & 7;
-                    const uint32_t abase = smem_u32(sA + (size_t)st * MM_A_BYTES);
-                    const uint8_t *col = a.desc + j * 16;
-#pragma unroll 8
-                    for (int i = 0; i < 32; ++i) {
-                        const int r = 4 * i + rq;
-                        const bool ok = r < len;
-                        const uint32_t rr = ok ? lrow[start + r] : 0u;
-                        const uint32_t dst = abase + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(col + (size_t)rr * 128),
-                                     "r"(ok ? 16 : 0));
-                    }
-                }
-                {
-                    const uint8_t *bsrc = a.bimg + (size_t)node * P::B_BYTES;
-                    const uint32_t bdst = smem_u32(sB + (size_t)st * P::B_BYTES);
-#pragma unroll
-                    for (int c = lane; c < P::B_BYTES / 16; c += 32)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(bdst + c * 16), "l"(bsrc + c * 16));
-                    if (lane < 4)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_cn + as * 16) + lane * 16),
-                                     "l"(a.cn32 + (size_t)node * 16 + lane * 4));
-                    if (lane == 4)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(s_flag + as)), "l"(a.cmask + node));
-                }
+                const uint32_t fullb = smem_u32(&bar_full[st]);
                 if (lane == 0) {
                     LpTile ti;
                     ti.start = start; ti.len = len; ti.node = node; ti.pos0 = (int)(base + start);
                     ti.flags = phase_flag; ti.buf = buf;
                     tinfo[as] = ti;
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fullb), "r"(Cfg::TX_BYTES) : "memory");
                 }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                outstanding = true;
-                out_st = st;
+                __syncwarp();
+                {
+                    int r4[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = 4 * lane + u;
+                        r4[u] = r < len ? (int)lrow[start + r] : -1;      // -1: out of range -> zero fill
+                    }
+                    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                                 ::"r"(smem_u32(sA + (size_t)st * MM_A_BYTES) + lane * 512), "l"(&tmap), "r"(0), "r"(r4[0]), "r"(r4[1]),
+                                   "r"(r4[2]), "r"(r4[3]), "r"(fullb) : "memory");
+                }
+                if (lane == 0)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(smem_u32(sB + (size_t)st * P::B_BYTES)), "l"(a.bimg + (size_t)node * P::B_BYTES),
+                                   "r"((uint32_t)P::B_BYTES), "r"(fullb) : "memory");
+                if (lane == 1)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(smem_u32(s_cn + as * 20)), "l"(a.cninfo + (size_t)node * 20), "r"(80u), "r"(fullb) : "memory");
             }
-            publish();                                           // nothing stays unpublished across the bookkeeping between phases
         };
 
         // chunk rows are fetched one chunk ahead: the global loads of chunk i+1 are in flight while chunk i is issued
@@ -593,8 +576,10 @@ level_pair_kernel(const LpArgs a)
             if (pw == 0) {
                 mbar_wait(&bar_afree[as], ((g / AS) & 1u) ^ 1u);
                 mbar_wait(&bar_sfree[st], ((g / S) & 1u) ^ 1u);
-                if (lane == 0) { LpTile ti; ti.start = 0; ti.len = 0; ti.node = 0; ti.flags = LPF_END; ti.pos0 = 0; ti.buf = 0; tinfo[as] = ti; }
-                mbar_arrive(&bar_full[st]);
+                if (lane == 0) {
+                    LpTile ti; ti.start = 0; ti.len = 0; ti.node = 0; ti.flags = LPF_END; ti.pos0 = 0; ti.buf = 0; tinfo[as] = ti;
+                    mbar_arrive(&bar_full[st]);
+                }
             }
             ++g;
         }
@@ -635,18 +620,53 @@ level_pair_kernel(const LpArgs a)
     if (warp == 16) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(Cfg::TMEM_ALLOC));
 }
 
-// per node: bit c set <=> child c exists as an internal node (the descent continues below it)
-__global__ void child_mask_kernel(const uint8_t *__restrict__ internal, long long n_int, int k, uint32_t *__restrict__ cmask)
+// per internal node one 80-byte record: its 16 fixed-point squared norms (cn32) and the child mask (bit c set <=> child c
+// is an internal node, the descent continues below it)
+__global__ void node_record_kernel(const uint8_t *__restrict__ internal, const int *__restrict__ cn32, long long n_int, int k,
+                                   int *__restrict__ cninfo)
 {
     for (long long h = blockIdx.x * (long long)blockDim.x + threadIdx.x; h < n_int; h += (long long)gridDim.x * blockDim.x) {
         uint32_t m = 0;
         for (int c = 0; c < k; ++c) m |= (uint32_t)(internal[h * k + 1 + c] != 0) << c;
-        cmask[h] = m;
+        for (int c = 0; c < 16; ++c) cninfo[h * 20 + c] = cn32[h * 16 + c];
+        cninfo[h * 20 + 16] = (int)m;
+        cninfo[h * 20 + 17] = 0; cninfo[h * 20 + 18] = 0; cninfo[h * 20 + 19] = 0;
     }
 }
 
+typedef CUresult (*LpEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// tensor map of the descriptor matrix [n, 128] bytes for tile::gather4: box = one 128-byte row, 128B swizzle
+int make_row_map(const void *desc, long long n, CUtensorMap *out)
+{
+    static LpEncodeFn encode = nullptr;
+    if (!encode) {
+        cudaDriverEntryPointQueryResult q;
+        void *fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+            vt_set_error("vt_quantize_mma: cuTensorMapEncodeTiled is not available");
+            return VT_EUNSUPPORTED;
+        }
+        encode = (LpEncodeFn)fn;
+    }
+    cuuint64_t gdim[2] = {128, (cuuint64_t)n};
+    cuuint64_t gstride[1] = {128};
+    cuuint32_t box[2] = {128, 1};
+    cuuint32_t estride[2] = {1, 1};
+    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(desc), gdim, gstride, box, estride,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        vt_set_error("vt_quantize_mma: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return VT_ECUDA;
+    }
+    return VT_OK;
+}
+
 template <int KP>
-int launch_pair(const LpArgs &a, cudaStream_t s)
+int launch_pair(const LpArgs &a, const CUtensorMap &tmap, cudaStream_t s)
 {
     static bool attr_set = false;
     auto kern = level_pair_kernel<KP>;
@@ -655,7 +675,7 @@ int launch_pair(const LpArgs &a, cudaStream_t s)
         attr_set = true;
     }
     const long long n_chunks = (a.n + LP_CHUNK - 1) / LP_CHUNK, cap = (long long)vt_sm_count();
-    kern<<<(int)(n_chunks < cap ? n_chunks : cap), LP_THREADS, LpCfg<KP>::SMEM, s>>>(a);
+    kern<<<(int)(n_chunks < cap ? n_chunks : cap), LP_THREADS, LpCfg<KP>::SMEM, s>>>(a, tmap);
     VT_LAUNCH_CHECK();
     return VT_OK;
 }
@@ -665,7 +685,7 @@ int launch_pair(const LpArgs &a, cudaStream_t s)
 // receives one event before and one after every launch-pair stage, for the profile variant.
 int vt_mma_levels_paired(const void *d_desc, int64_t n, const float *cent, const uint8_t *internal, const int32_t *ref_id,
                          int k, int depth, int32_t *leaf, int32_t *word, uint64_t *stats, const uint8_t *bimg,
-                         const int *cn32, uint32_t *cmask, void *sortwork, bool defer, cudaStream_t s, cudaEvent_t *ev,
+                         const int *cn32, int *cninfo, void *sortwork, bool defer, cudaStream_t s, cudaEvent_t *ev,
                          int *n_ev_io)
 {
     int n_ev = n_ev_io ? *n_ev_io : 0;
@@ -677,12 +697,15 @@ int vt_mma_levels_paired(const void *d_desc, int64_t n, const float *cent, const
     const int bits = path_bits(k);
     uint32_t *keys = kA, *perm = pA, *tkeys = kB, *tperm = pB;
     const uint32_t *cur_perm = nullptr, *cur_parent = nullptr;
-    {   // which children of every internal node continue the descent (4 B per node, next to the prepared planes)
+    CUtensorMap tmap;
+    {   // per-node records (norms + which children continue the descent), next to the prepared planes; the row map
         int64_t n_int = 0, p = 1;
         for (int l = 0; l < depth; ++l) { n_int += p; p *= k; }
         const int64_t want = (n_int + 255) / 256, cap = (int64_t)vt_sm_count() * 8;
-        child_mask_kernel<<<(int)(want < cap ? want : cap), 256, 0, s>>>(internal, n_int, k, cmask);
+        node_record_kernel<<<(int)(want < cap ? want : cap), 256, 0, s>>>(internal, cn32, n_int, k, cninfo);
         VT_LAUNCH_CHECK();
+        const int rc = make_row_map(d_desc, n, &tmap);
+        if (rc != VT_OK) return rc;
     }
     for (int level = 0; level < depth;) {
         const int phases = depth - level >= 2 ? 2 : 1;
@@ -690,11 +713,11 @@ int vt_mma_levels_paired(const void *d_desc, int64_t n, const float *cent, const
         LpArgs a;
         a.desc = (const uint8_t *)d_desc; a.perm = cur_perm; a.parent = cur_parent; a.n = n;
         a.level = level; a.phases = phases; a.bits = bits; a.k = k; a.mode = last ? (defer ? 2 : 1) : 0;
-        a.n_heap = n_heap; a.cent = cent; a.internal = internal; a.ref_id = ref_id; a.bimg = bimg; a.cn32 = cn32; a.cmask = cmask;
+        a.n_heap = n_heap; a.cent = cent; a.internal = internal; a.ref_id = ref_id; a.bimg = bimg; a.cn32 = cn32; a.cninfo = cninfo;
         a.keys_out = last && !defer ? nullptr : tkeys; a.perm_out = last && !defer ? nullptr : tperm;
         a.leaf_out = leaf; a.word_out = word; a.stats = (unsigned long long *)stats;
         if (level > 0) VT_MARK();                                 // (the caller recorded the first event)
-        int rc = k <= 10 ? launch_pair<10>(a, s) : launch_pair<16>(a, s);
+        int rc = k <= 10 ? launch_pair<10>(a, tmap, s) : launch_pair<16>(a, tmap, s);
         if (rc != VT_OK) return rc;
         if (last) {
             if (defer) {
