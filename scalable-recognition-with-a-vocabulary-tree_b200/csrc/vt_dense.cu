@@ -12,10 +12,11 @@
 // deep levels and ranks.  Database.retrieve (database.py:72-81) semantics are unchanged: exact integer dots.
 //
 // dense_gemm_kernel: persistent, one CTA per SM, tile = 256 queries x 256 images, K blocks of 128 bytes through a 3-stage
-// cp.async ring (A 32 KB + B 32 KB per stage, 128B-swizzled K-major like the descent kernels), two M=128 x N=256 x K=32
-// kind::i8 MMAs per K step into the two halves of TMEM (512 columns), warps 0-3 epilogue (tcgen05.ld, top-level
-// correction with integer FMAs, int32 stores), warps 4-7 producers, warp 8 issues.
+// TMA ring (two 2-D tile loads per K block: A 32 KB + B 32 KB, 128B-swizzled K-major like the descent kernels), two
+// M=128 x N=256 x K=32 kind::i8 MMAs per K step into the two halves of TMEM (512 columns), warps 0-3 epilogue
+// (tcgen05.ld, top-level correction with integer FMAs, int32 stores), warp 4 issues the TMA loads, warp 8 the MMAs.
 #include "vt_mma_common.cuh"
+#include <cuda.h>
 
 namespace {
 constexpr int DG_TM = 256, DG_TN = 256, DG_KB = 128;
@@ -82,9 +83,9 @@ __global__ void dense_scatter_kernel(const int64_t *__restrict__ row_off, const 
 }
 
 __global__ void __launch_bounds__(DG_THREADS, 1)
-dense_gemm_kernel(const uint8_t *__restrict__ A, const int32_t *__restrict__ QT, const uint8_t *__restrict__ B,
-                  const int32_t *__restrict__ T, int64_t qp, int64_t np, int64_t kd, int n_top, int32_t *__restrict__ D,
-                  int64_t ldd)
+dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  const int32_t *__restrict__ QT, const int32_t *__restrict__ T, int64_t qp, int64_t np, int64_t kd, int n_top,
+                  int32_t *__restrict__ D, int64_t ldd)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -98,7 +99,7 @@ dense_gemm_kernel(const uint8_t *__restrict__ A, const int32_t *__restrict__ QT,
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 0) {
-        for (int s = 0; s < DG_STAGES; ++s) { dg_mbar_init(&bar_full[s], 128); dg_mbar_init(&bar_empty[s], 1); }
+        for (int s = 0; s < DG_STAGES; ++s) { dg_mbar_init(&bar_full[s], 1); dg_mbar_init(&bar_empty[s], 1); }
         dg_mbar_init(&bar_tfull, 1);
         dg_mbar_init(&bar_tempty, 4);
         asm volatile("fence.mbarrier_init.release.cluster;");
@@ -158,40 +159,23 @@ dense_gemm_kernel(const uint8_t *__restrict__ A, const int32_t *__restrict__ QT,
             if (lane == 0) dg_mbar_arrive(&bar_tempty);
         }
     } else if (warp < 8) {
-        // ---------------- producers: cp.async of the A and B K-blocks into the swizzled ring ----------------
-        const int ptid = tid - 128;
-        uint32_t g = 0;
-        int pending = 0;
-        auto arrive_oldest = [&]() {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            dg_mbar_arrive(&bar_full[(g - (uint32_t)pending) % DG_STAGES]);
-            --pending;
-        };
-        for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-            const int64_t n0 = (t / m_tiles) * DG_TN, m0 = (t % m_tiles) * DG_TM;
-            for (int kb = 0; kb < kblocks; ++kb) {
-                const int st = (int)(g % DG_STAGES);
-                dg_mbar_wait(&bar_empty[st], ((g / DG_STAGES) & 1u) ^ 1u);
-                const uint32_t sa = smem_u32(smem + (size_t)st * DG_STAGE_BYTES), sb = sa + DG_A_BYTES;
-                const uint8_t *ga = A + (size_t)m0 * kd + (size_t)kb * DG_KB, *gb = B + (size_t)n0 * kd + (size_t)kb * DG_KB;
-#pragma unroll 4
-                for (int i = 0; i < DG_TM * 8 / 128; ++i) {
-                    const int c = ptid + 128 * i, r = c >> 3, j = c & 7;
-                    const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + off), "l"(ga + (size_t)r * kd + j * 16));
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sb + off), "l"(gb + (size_t)r * kd + j * 16));
-                }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                ++g;
-                ++pending;
-                if (pending > DG_LAG) {
-                    asm volatile("cp.async.wait_group %0;" ::"n"(DG_LAG) : "memory");
-                    arrive_oldest();
+        // ---------------- producer: one thread, two TMA tile loads per K block ----------------
+        if (warp == 4 && lane == 0) {
+            uint32_t g = 0;
+            for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+                const int n0 = (int)((t / m_tiles) * DG_TN), m0 = (int)((t % m_tiles) * DG_TM);
+                for (int kb = 0; kb < kblocks; ++kb, ++g) {
+                    const int st = (int)(g % DG_STAGES);
+                    dg_mbar_wait(&bar_empty[st], ((g / DG_STAGES) & 1u) ^ 1u);
+                    const uint32_t sa = smem_u32(smem + (size_t)st * DG_STAGE_BYTES), sb = sa + DG_A_BYTES, fb = smem_u32(&bar_full[st]);
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"((uint32_t)DG_STAGE_BYTES) : "memory");
+                    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                                 ::"r"(sa), "l"(&map_a), "r"(kb * DG_KB), "r"(m0), "r"(fb) : "memory");
+                    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                                 ::"r"(sb), "l"(&map_b), "r"(kb * DG_KB), "r"(n0), "r"(fb) : "memory");
                 }
             }
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        while (pending > 0) arrive_oldest();
     } else {
         // ---------------- MMA issuer ----------------
         uint32_t g = 0, use = 0;
@@ -248,22 +232,62 @@ extern "C" int vt_dense_scatter(const int64_t *d_row_off, const int32_t *d_node,
 
 // D[q][img] (int32, row stride ldd) = A[q] . B[img] over the kd dense columns + QT[q] . T[img] over the n_top top
 // nodes.  qp and np (padded row counts of A / QT and B / T) are multiples of 256, kd a multiple of 128.
+typedef CUresult (*DgEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D byte matrix [rows, kd], box = 256 rows x 128 bytes, 128B swizzle: the K-major tile the MMA descriptors expect
+static int dg_make_map(const void *base, int64_t rows, int64_t kd, CUtensorMap *out)
+{
+    static DgEncodeFn encode = nullptr;
+    if (!encode) {
+        cudaDriverEntryPointQueryResult q;
+        void *fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+            vt_set_error("vt_dense_dots: cuTensorMapEncodeTiled is not available");
+            return VT_EUNSUPPORTED;
+        }
+        encode = (DgEncodeFn)fn;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)kd, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)kd};
+    cuuint32_t box[2] = {DG_KB, 256};
+    cuuint32_t estride[2] = {1, 1};
+    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), gdim, gstride, box, estride,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        vt_set_error("vt_dense_dots: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return VT_ECUDA;
+    }
+    return VT_OK;
+}
+
+// D[q][img] (int32, row stride ldd) = A[q] . B[img] over the kd dense columns + QT[q] . T[img] over the n_top top
+// nodes.  qp and np (padded row counts of A / QT and B / T) are multiples of 256, kd a multiple of 128.
 extern "C" int vt_dense_dots(const uint8_t *d_a, const int32_t *d_qt, const uint8_t *d_b, const int32_t *d_t, int64_t qp,
                              int64_t np, int64_t kd, int n_top, int32_t *d_out, int64_t ldd, void *stream)
 {
     VT_CHECK_ARG(d_a && d_qt && d_b && d_t && d_out, "null buffer");
     VT_CHECK_ARG(qp > 0 && np > 0 && qp % DG_TM == 0 && np % DG_TN == 0 && kd > 0 && kd % DG_KB == 0 && ldd >= np &&
                  ldd % 4 == 0, "rows must be padded to 256, columns to 128");
+    VT_CHECK_ARG(qp < ((int64_t)1 << 31) && np < ((int64_t)1 << 31) && kd < ((int64_t)1 << 31), "matrix too large");
     VT_CHECK_ARG(n_top >= 1 && n_top <= DG_MAX_TOP, "n_top out of range");
+    VT_CHECK_ARG((((uintptr_t)d_a | (uintptr_t)d_b) & 15) == 0, "matrices must be 16-byte aligned");
     const int smem = DG_STAGES * DG_STAGE_BYTES + DG_TN * DG_MAX_TOP * 4 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         VT_CUDA(cudaFuncSetAttribute(dense_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
+    CUtensorMap map_a, map_b;
+    int rc = dg_make_map(d_a, qp, kd, &map_a);
+    if (rc != VT_OK) return rc;
+    rc = dg_make_map(d_b, np, kd, &map_b);
+    if (rc != VT_OK) return rc;
     const int64_t tiles = (qp / DG_TM) * (np / DG_TN), cap = vt_sm_count();
     dense_gemm_kernel<<<(int)(tiles < cap ? tiles : cap), DG_THREADS, smem, (cudaStream_t)stream>>>(
-        d_a, d_qt, d_b, d_t, qp, np, kd, n_top, d_out, ldd);
+        map_a, map_b, d_qt, d_t, qp, np, kd, n_top, d_out, ldd);
     VT_LAUNCH_CHECK();
     return VT_OK;
 }

@@ -881,7 +881,13 @@ extern "C" int vt_quantize_mma_profile(const void *d_desc, int dtype, int64_t n,
     int rc = vt_quantize_mma_impl(d_desc, n, d_centroids, d_internal, d_ref_id, k, depth, d_leaf_heap, d_word, d_stats,
                                   d_work, (cudaStream_t)stream, ev, &n_used);
     // (the two-levels-per-launch path records one stage per launch: entries beyond its stages stay 0)
-    if (rc == VT_OK && cudaDeviceSynchronize() != cudaSuccess) rc = VT_ECUDA;
+    if (rc == VT_OK) {
+        const cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+            vt_set_error("vt_quantize_mma_profile: %s", cudaGetErrorString(e));
+            rc = VT_ECUDA;
+        }
+    }
     for (int l = 0; l < depth && rc == VT_OK; ++l) {
         h_level_ms[l] = 0.f;
         h_sort_ms[l] = 0.f;

@@ -23,6 +23,7 @@
 // acc (commit -> epilogue), afree (epilogue -> producers); per-group completion counters tell the producers when the
 // child indices of a chunk are complete.  Phase 1 of chunk i+1 is issued BEFORE phase 2 of chunk i, so the ring does
 // not drain while a chunk is being sorted.
+// #define LP_DEBUG 1    (bounds checks with printf + trap on the tiles the producers issue and the rows the epilogue writes)
 #include "vt_mma_common.cuh"
 #include <cuda.h>
 #include <stdlib.h>
@@ -169,6 +170,7 @@ level_pair_kernel(const LpArgs a, const __grid_constant__ CUtensorMap tmap)
     __shared__ LpTile tinfo[AS];
     __shared__ uint32_t s_tmem;
     __shared__ int s_ntiles, s_nreal;
+    __shared__ uint16_t s_tstart[64];                           // phase-2 tile starts of a regular chunk (<= 8 + 31 tiles)
     __shared__ int s_wcnt[8][32], s_run[8][32];
     __shared__ int s_done[8];                                   // tiles each epilogue WARP has completed (its group's tiles, in order)
 
@@ -234,6 +236,12 @@ level_pair_kernel(const LpArgs a, const __grid_constant__ CUtensorMap tmap)
             const bool active = etid < ti.len;
             const int idx = ti.start + etid;
             const uint32_t row = active ? lrow[idx] : 0u;
+#ifdef LP_DEBUG
+            if (active && (long long)row >= a.n) {
+                printf("LP_DEBUG bad row: block %d warp %d slot %u idx %d row %u start %d len %d flags %d buf %d\n", (int)blockIdx.x, warp, g, idx, row, ti.start, ti.len, ti.flags, ti.buf);
+                __trap();
+            }
+#endif
             int best = none, second = none, arg = 0;
             if (active) score_children_tree<KP, P::N>(v, s_cn + st * 20, best, second, arg);
             const uint8_t *xrow = a.desc + (size_t)row * 128;
@@ -350,6 +358,53 @@ level_pair_kernel(const LpArgs a, const __grid_constant__ CUtensorMap tmap)
         // with one tile::gather4 (arbitrary row indices, 128B-swizzled destination = exactly the K-major tile the MMA reads,
         // rows past the tile's length are out of range and arrive as zeros), lanes 0 and 1 bulk-copy the node's planes
         // and its 80-byte record.  Everything completes on the stage's full barrier (expect_tx); nobody waits for data.
+        auto issue_tile = [&](uint32_t slot, int start, int len, uint32_t node, const uint32_t *lrow, int phase_flag,
+                              long long base, int buf) {
+            const int st = (int)(slot % S), as = (int)(slot % AS);
+#ifdef LP_DEBUG
+            if (!((long long)node * k + k < a.n_heap) || start < 0 || len < 1 || len > MM_TILE || start + len > LP_CHUNK) {
+                if (lane == 0) printf("LP_DEBUG bad tile: block %d warp %d slot %u start %d len %d node %u flag %d buf %d\n", (int)blockIdx.x, pw, slot, start, len, node, phase_flag, buf);
+                __trap();
+            }
+#endif
+            mbar_wait(&bar_afree[as], ((slot / AS) & 1u) ^ 1u);   // the slot's record / tile info may be rewritten
+            mbar_wait(&bar_sfree[st], ((slot / S) & 1u) ^ 1u);    // the MMA of the stage's previous tile has read it
+            const uint32_t fullb = smem_u32(&bar_full[st]);
+            if (lane == 0) {
+                LpTile ti;
+                ti.start = start; ti.len = len; ti.node = node; ti.pos0 = (int)(base + start);
+                ti.flags = phase_flag; ti.buf = buf;
+                tinfo[as] = ti;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fullb), "r"(Cfg::TX_BYTES) : "memory");
+            }
+            __syncwarp();
+            {
+                int r4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = 4 * lane + u;
+                    r4[u] = r < len ? (int)lrow[start + r] : -1;      // -1: out of range -> zero fill
+                }
+                asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                             ::"r"(smem_u32(sA + (size_t)st * MM_A_BYTES) + lane * 512), "l"(&tmap), "r"(0), "r"(r4[0]), "r"(r4[1]),
+                               "r"(r4[2]), "r"(r4[3]), "r"(fullb) : "memory");
+            }
+            if (lane == 0)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32(sB + (size_t)st * P::B_BYTES)), "l"(a.bimg + (size_t)node * P::B_BYTES),
+                               "r"((uint32_t)P::B_BYTES), "r"(fullb) : "memory");
+            if (lane == 1)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32(s_cn + as * 20)), "l"(a.cninfo + (size_t)node * 20), "r"(80u), "r"(fullb) : "memory");
+        };
+        // slots [g, g + nt) have been handed out: per-group tile counts and the slot counter
+        auto take_slots = [&](int nt) {
+            const int even = (nt + ((g & 1u) ? 0 : 1)) / 2;
+            issued[0] += even;
+            issued[1] += nt - even;
+            g += (uint32_t)nt;
+        };
+        // irregular chunks (several nodes, stopped rows): every warp walks the tile list and issues the tiles whose slot it owns
         auto issue_phase = [&](const uint32_t *lrow, const uint32_t *lkey, const uint32_t *lnode, int phase_flag,
                                bool final_phase, long long base, int buf) {
             const int nt = s_ntiles;
@@ -363,40 +418,35 @@ level_pair_kernel(const LpArgs a, const __grid_constant__ CUtensorMap tmap)
                     continue;
                 }
                 const uint32_t slot = g;
-                ++issued[g & 1u];
-                ++g;
-                if ((int)(slot & 7u) != pw) continue;
-                const int st = (int)(slot % S), as = (int)(slot % AS);
-                mbar_wait(&bar_afree[as], ((slot / AS) & 1u) ^ 1u);   // the slot's record / tile info may be rewritten
-                mbar_wait(&bar_sfree[st], ((slot / S) & 1u) ^ 1u);    // the MMA of the stage's previous tile has read it
-                const uint32_t fullb = smem_u32(&bar_full[st]);
-                if (lane == 0) {
-                    LpTile ti;
-                    ti.start = start; ti.len = len; ti.node = node; ti.pos0 = (int)(base + start);
-                    ti.flags = phase_flag; ti.buf = buf;
-                    tinfo[as] = ti;
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fullb), "r"(Cfg::TX_BYTES) : "memory");
-                }
-                __syncwarp();
-                {
-                    int r4[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int r = 4 * lane + u;
-                        r4[u] = r < len ? (int)lrow[start + r] : -1;      // -1: out of range -> zero fill
-                    }
-                    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-                                 ::"r"(smem_u32(sA + (size_t)st * MM_A_BYTES) + lane * 512), "l"(&tmap), "r"(0), "r"(r4[0]), "r"(r4[1]),
-                                   "r"(r4[2]), "r"(r4[3]), "r"(fullb) : "memory");
-                }
-                if (lane == 0)
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(smem_u32(sB + (size_t)st * P::B_BYTES)), "l"(a.bimg + (size_t)node * P::B_BYTES),
-                                   "r"((uint32_t)P::B_BYTES), "r"(fullb) : "memory");
-                if (lane == 1)
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(smem_u32(s_cn + as * 20)), "l"(a.cninfo + (size_t)node * 20), "r"(80u), "r"(fullb) : "memory");
+                take_slots(1);
+                if ((int)(slot & 7u) == pw) issue_tile(slot, start, len, node, lrow, phase_flag, base, buf);
             }
+        };
+        // regular chunks (one node for every row -- the usual case): tile t of phase 1 is rows [128 t, 128 t + 128); the
+        // tiles of phase 2 come from the table the sort leaves in s_tstart / tl_len.  A warp goes straight to its tiles.
+        auto issue_regular_p1 = [&](const Lists &L, int clen, long long base, int buf) {
+            const int nt = (clen + MM_TILE - 1) / MM_TILE;
+            const uint32_t node0 = L.c_node[0];
+            for (int t = (int)((uint32_t)(pw - (int)(g & 7u)) & 7u); t < nt; t += 8)
+                issue_tile(g + (uint32_t)t, t * MM_TILE, clen - t * MM_TILE < MM_TILE ? clen - t * MM_TILE : MM_TILE, node0, L.c_row, 0,
+                           base, buf);
+            take_slots(nt);
+        };
+        auto issue_regular_p2 = [&](const Lists &L, int clen, long long base, int buf) {
+            const int nt = s_ntiles, stop_off = s_nreal;          // (s_nreal carries the offset of the stopped rows here)
+            for (int t = (int)((uint32_t)(pw - (int)(g & 7u)) & 7u); t < nt; t += 8) {
+                const int start = s_tstart[t];
+#ifdef LP_DEBUG
+                if (!((long long)L.s_node[start] * k + k < a.n_heap)) {
+                    if (lane == 0) printf("LP_DEBUG p2: level %d block %d warp %d t %d nt %d stop %d clen %d start %d len %d s_node %u s_row %u s_key %u c_node0 %u c_cls0 %d wcnt %d %d %d %d\n",
+                                          a.level, (int)blockIdx.x, pw, t, nt, stop_off, clen, start, (int)tl_len[t] + 1, L.s_node[start], L.s_row[start], L.s_key[start], L.c_node[0], (int)L.c_cls[0],
+                                          s_wcnt[0][0], s_wcnt[0][1], s_wcnt[0][2], s_wcnt[0][31]);
+                }
+#endif
+                issue_tile(g + (uint32_t)t, start, (int)tl_len[t] + 1, L.s_node[start], L.s_row, LPF_PHASE2, base, buf);
+            }
+            take_slots(nt);
+            none_outputs(L.s_row, L.s_key, stop_off, clen - stop_off, base, ptid, LP_PRODUCERS);
         };
 
         // chunk rows are fetched one chunk ahead: the global loads of chunk i+1 are in flight while chunk i is issued
@@ -414,6 +464,31 @@ level_pair_kernel(const LpArgs a, const __grid_constant__ CUtensorMap tmap)
         // registers -> lists of buffer `buf` + the tile list of phase 1; returns with s_ntiles / s_nreal valid
         auto commit_load = [&](int clen, int buf) {
             const Lists L = lists(buf);
+            // regular chunk: every row carries the same live path -> one node, no per-row tree lookups (below level 0 a
+            // live path always ends at an internal node: the launch before only extends paths into internal children)
+            if (ptid == 0) s_run[0][0] = (int)rkey[0];
+            producers_sync();
+            const uint32_t key0 = (uint32_t)s_run[0][0];
+            bool same = true;
+#pragma unroll
+            for (int u = 0; u < LP_PER; ++u)
+                if (ptid + u * LP_PRODUCERS < clen) same = same && rkey[u] == key0;
+            bool regular = producers_all(same) && (a.level == 0 || (key0 & dmask) != dmask);
+            uint32_t node0 = LP_NONE;
+            if (regular) {
+                node0 = path_to_heap32(key0, a.level, bits, (uint32_t)k);
+                if (a.level == 0 && !(((long long)node0 * k + k < a.n_heap) && a.internal[node0])) regular = false;   // a root-only tree
+            }
+            if (regular) {
+#pragma unroll
+                for (int u = 0; u < LP_PER; ++u) {
+                    const int i = ptid + u * LP_PRODUCERS;
+                    if (i < clen) { L.c_row[i] = rrow[u]; L.c_key[i] = key0; L.c_node[i] = node0; L.c_cls[i] = LP_STOP; }
+                }
+                if (ptid == 0) { s_ntiles = (clen + MM_TILE - 1) / MM_TILE; s_nreal = s_ntiles; }
+                producers_sync();
+                return true;
+            }
             uint32_t rh[LP_PER];
             uint8_t rint[LP_PER];
 #pragma unroll
@@ -423,8 +498,6 @@ level_pair_kernel(const LpArgs a, const __grid_constant__ CUtensorMap tmap)
                 rh[u] = alive ? path_to_heap32(rkey[u], a.level, bits, (uint32_t)k) : LP_NONE;
                 rint[u] = (alive && ((long long)rh[u] * k + k < a.n_heap)) ? a.internal[rh[u]] : (uint8_t)0;
             }
-            uint32_t first = LP_NONE;
-            bool same = true;
 #pragma unroll
             for (int u = 0; u < LP_PER; ++u) {
                 const int i = ptid + u * LP_PRODUCERS;
@@ -439,37 +512,27 @@ level_pair_kernel(const LpArgs a, const __grid_constant__ CUtensorMap tmap)
                     }
                 }
                 L.c_row[i] = rrow[u]; L.c_key[i] = rkey[u]; L.c_node[i] = node; L.c_cls[i] = LP_STOP;
-                if (u == 0) first = node; else same = same && node == first;
-            }
-            // one node for the whole chunk (the usual case): the tile list is arithmetic
-            if (ptid == 0) s_run[0][0] = (int)first;
-            producers_sync();
-            const uint32_t node0 = (uint32_t)s_run[0][0];
-            const bool uniform = producers_all(same && (ptid >= clen || first == node0) && node0 != LP_NONE);
-            if (uniform) {
-                const int nt = (clen + MM_TILE - 1) / MM_TILE;
-                if (ptid < nt) tl_len[ptid] = (uint8_t)((clen - ptid * MM_TILE < MM_TILE ? clen - ptid * MM_TILE : MM_TILE) - 1);
-                if (ptid == 0) { s_ntiles = nt; s_nreal = nt; }
-            } else if (pw == 0) {
-                build_tiles(L.c_node, clen, tl_len, &s_ntiles, &s_nreal, lane);
             }
             producers_sync();
-            return uniform;
+            if (pw == 0) build_tiles(L.c_node, clen, tl_len, &s_ntiles, &s_nreal, lane);
+            producers_sync();
+            return false;
         };
         auto chunk_len = [&](long long i) {
             const long long base = (blockIdx.x + i * (long long)gridDim.x) * LP_CHUNK;
             return (int)((a.n - base) < LP_CHUNK ? (a.n - base) : LP_CHUNK);
         };
         auto chunk_base = [&](long long i) { return (blockIdx.x + i * (long long)gridDim.x) * LP_CHUNK; };
+        bool uni[2] = {false, false};                          // per list buffer: its chunk is regular (one node)
+        int nreal1[2] = {0, 0};
         auto issue_p1 = [&](long long i) {
             const int buf = (int)(i & 1);
             const Lists L = lists(buf);
-            issue_phase(L.c_row, L.c_key, L.c_node, 0, a.phases == 1, chunk_base(i), buf);
+            if (uni[buf]) issue_regular_p1(L, chunk_len(i), chunk_base(i), buf);
+            else issue_phase(L.c_row, L.c_key, L.c_node, 0, a.phases == 1, chunk_base(i), buf);
             snap_a[buf] = issued[0]; snap_b[buf] = issued[1];
         };
 
-        bool uni[2] = {false, false};
-        int nreal1[2] = {0, 0};
         if (my_chunks > 0) {
             fetch(0);
             uni[0] = commit_load(chunk_len(0), 0);
@@ -498,6 +561,61 @@ level_pair_kernel(const LpArgs a, const __grid_constant__ CUtensorMap tmap)
                     none_outputs(L.c_row, L.c_key, 0, clen, base, ptid, LP_PRODUCERS);    // nothing alive in this chunk
                 } else {
                     wait_done(buf);                              // the epilogue has left every child index in c_cls
+                    if (uni[buf]) {
+                        // ---- regular chunk: counting sort by child index with shared-memory atomics (the order inside a
+                        // class is free: all its rows go to the same child node), tile table from the class counts ----
+                        if (ptid < 32) s_wcnt[0][ptid] = 0;
+                        producers_sync();
+                        int cls[LP_PER], rank[LP_PER];
+#pragma unroll
+                        for (int u = 0; u < LP_PER; ++u) {
+                            const int e = ptid + u * LP_PRODUCERS;
+                            cls[u] = e < clen ? (int)L.c_cls[e] : -1;
+                            rank[u] = cls[u] >= 0 ? atomicAdd(&s_wcnt[0][cls[u]], 1) : 0;
+                        }
+                        producers_sync();
+                        const int total_c = s_wcnt[0][lane];        // lane = class
+                        int incl = total_c;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int t = __shfl_up_sync(VT_FULL, incl, o);
+                            if (lane >= o) incl += t;
+                        }
+                        const int cbase = incl - total_c;           // first sorted position of class `lane`
+                        const uint32_t node1 = L.c_node[0], key1 = L.c_key[0];
+#pragma unroll
+                        for (int u = 0; u < LP_PER; ++u) {
+                            const int e = ptid + u * LP_PRODUCERS;
+                            const int off = __shfl_sync(VT_FULL, cbase, cls[u] >= 0 ? cls[u] : 0);
+                            if (cls[u] >= 0) {
+                                const int dst = off + rank[u];
+                                L.s_row[dst] = L.c_row[e];
+                                L.s_key[dst] = key1;
+                                L.s_node[dst] = cls[u] == LP_STOP ? LP_NONE : node1 * (uint32_t)k + 1u + (uint32_t)cls[u];
+                                L.s_d1[dst] = cls[u] == LP_STOP ? (uint8_t)dmask : (uint8_t)cls[u];
+                            }
+                        }
+                        if (pw == 0) {
+                            const int ntile = lane == LP_STOP ? 0 : (total_c + MM_TILE - 1) / MM_TILE;
+                            int ti = ntile;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const int t = __shfl_up_sync(VT_FULL, ti, o);
+                                if (lane >= o) ti += t;
+                            }
+                            int at = ti - ntile, pos = cbase;
+                            for (int r = lane == LP_STOP ? 0 : total_c; r > 0; r -= MM_TILE, pos += MM_TILE) {
+                                s_tstart[at] = (uint16_t)pos;
+                                tl_len[at++] = (uint8_t)((r < MM_TILE ? r : MM_TILE) - 1);
+                            }
+                            const int all = __shfl_sync(VT_FULL, ti, 31);
+                            if (lane == LP_STOP) { s_ntiles = all; s_nreal = cbase; }     // s_nreal: where the stopped rows start
+                        }
+                        producers_sync();
+                        issue_regular_p2(L, clen, base, buf);
+                        continue;
+                    }
+                    // ---- irregular chunk (several parent nodes): the order inside a class matters ----
                     // ---- stable counting sort of the chunk by child index (LP_STOP = stopped) ----
                     s_wcnt[pw][lane] = 0;
                     __syncwarp();
