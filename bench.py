@@ -289,15 +289,31 @@ def main():
         return lvl_acc / reps, srt_acc / reps
 
     level_ms, sort_ms = stage_profile(lib.vt_quantize_mma_profile if method == "mma" else lib.vt_quantize_sorted_profile)
+    # the two-levels-per-launch variant of the tcgen05 descent (vt_quantize_pair.cu; off by default): same ids, 3 DRAM
+    # reads of every row instead of 6
+    pair = None
+    if method == "mma":
+        prev = lib.vt_quantize_mma_pair_min(1 << 20)
+        w2 = engine.quantize(tree_dev, K_BRANCH, DEPTH, desc, method="mma", work=work)
+        pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pa.record()
+        for _ in range(3):
+            w2 = engine.quantize(tree_dev, K_BRANCH, DEPTH, desc, method="mma", work=work)
+        pb.record()
+        torch.cuda.synchronize()
+        p_lvl, p_srt = stage_profile(lib.vt_quantize_mma_profile, reps=2)
+        lib.vt_quantize_mma_pair_min(prev if prev < (1 << 62) else -1)
+        pair = {"kernel": "level_pair_kernel<10> (vt_quantize_pair.cu): two tree levels per launch, TMA tile::gather4, the second "
+                          "level re-gathers from L2", "ms_per_step": pa.elapsed_time(pb) / 3, "value": n / (pa.elapsed_time(pb) / 3 * 1e-3),
+                "unit": "descriptors/s", "level_kernel_ms": [round(float(v), 3) for v in p_lvl if v > 0],
+                "resort_ms": [round(float(v), 3) for v in p_srt if v > 0], "same_words": bool(torch.equal(w2, words)),
+                "dram_row_reads_per_descent": (DEPTH + 1) // 2, "default": False}
+        del w2
     other_ms, _ = stage_profile(lib.vt_quantize_sorted_profile if method == "mma" else lib.vt_quantize_mma_profile, reps=1)
-    # kernels per step.  tcgen05 engine, batches >= 2^20 rows: ceil(L/2) two-level launches, one radix pass (hist, scan,
-    # scatter) between consecutive launches, and from 2^22 rows on the deferred output (one more pass + the id write);
-    # the byte planes are prepared once per tree, outside the steps.  SIMT engine: one launch and one pass per level.
-    if method == "mma" and n >= (1 << 20):
-        n_launch = (DEPTH + 1) // 2
-        launches_per_step = n_launch + 3 * (n_launch - 1) + (4 if n >= (1 << 22) else 0)
-    else:
-        launches_per_step = DEPTH + 3 * (DEPTH - 1) + (4 if method == "mma" and n >= (1 << 22) else 0)
+    # kernels per step: one level launch and one regrouping pass (hist, scan, scatter) per level transition; the tcgen05
+    # engine adds, from 2^22 rows on, the deferred output of the last level (one more pass + the id write); the byte
+    # planes are prepared once per tree, outside the steps.
+    launches_per_step = DEPTH + 3 * (DEPTH - 1) + (4 if method == "mma" and n >= (1 << 22) else 0)
 
     # float32 input (the primary feed is fp32 [N, 128]; bytes are its lossless compressed form): the staging
     # pass vt_stage_f32_to_u8 (512 B read + 128 B written per descriptor) is part of the step
@@ -405,7 +421,7 @@ def main():
         simt = {"bound": "fp32", "kernel": "level_kernel<128,R> (vt_quantize_sorted.cu)", "unit": "TFLOP/s",
                 "peak": peak_tf.value, "peak_source": "FFMA microbenchmark on this device (vt_measure_fp32_peak)",
                 "flop_per_descriptor": flop_per_desc}
-        mma = {"bound": "hbm", "kernel": "level_pair_kernel<10> (vt_quantize_pair.cu, tcgen05.mma kind::i8, two tree levels per launch)",
+        mma = {"bound": "hbm", "kernel": "level_mma_kernel<8,10> (vt_quantize_mma.cu, tcgen05.mma kind::i8, one tree level per launch)",
                "unit": "GB/s", "peak": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                "bytes_per_descriptor": alg_bytes}
         def fill(d, total_ms):
@@ -433,10 +449,11 @@ def main():
                            "hbm_bound_descriptors_per_s": hbm_peak * 1e9 / alg_bytes},
             "traffic": traffic,
             "traffic_source": traffic_src,
-            "level_kernel_ms_note": "one entry per launch (two tree levels each); entry 0 includes the per-call plane preparation of the profile variant, the last entry the deferred output (bucket pass + id write)",
+            "level_kernel_ms_note": "one entry per level; entry 0 includes the per-call plane preparation of the profile variant, the last entry the deferred output (bucket pass + id write)",
             "other_engine": dict(fill(other_r, other_total_ms), level_kernel_ms=[round(float(v), 3) for v in other_ms]),
             "fused_single_launch_descent": {"value": fused_rate, "unit": "descriptors/s", "rows": n_f},
             "fp32_input": fp32_in,
+            "two_levels_per_launch": pair,
         })
         line = {
             "metric": METRIC, "value": value, "unit": "descriptors/s", "n_gpus": world, "steps": args.steps,

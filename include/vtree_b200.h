@@ -203,6 +203,12 @@ int vt_csr_compact(const int64_t *d_in_off, const int32_t *d_nnz, const int64_t 
                    int64_t n_img, const int32_t *d_node_in, const int32_t *d_count_in,
                    int32_t *d_node_out, int32_t *d_count_out, void *stream);
 
+/* The tcgen05 descent has a second level loop that takes TWO tree levels per launch (csrc/vt_quantize_pair.cu:
+ * persistent CTAs, TMA gathers, the second level re-reads the rows from L2: 3 DRAM reads of every row per descent
+ * at L=6 instead of 6).  vt_quantize_mma_pair_min(rows) makes batches of at least `rows` rows use it (rows < 0:
+ * never, the default; rows == 0: query only) and returns the previous threshold.  Ids are identical either way. */
+int64_t vt_quantize_mma_pair_min(int64_t min_rows);
+
 /* ---- inverted file: the dict-per-node postings of vocabulary.py:96-100 as CSR, sharded by image
  * range (vt_score_shard_size() = 8192 images per shard).  Row key = node * n_shards + img / shard_size, so a
  * node's posting list is one contiguous image-ordered run and shards are consecutive ranges of it.

@@ -34,6 +34,7 @@ SIGNATURES = {
     "vt_quantize_mma_prepare": (_int, [_vp, _int, _int, _vp, _vp, _vp]),
     "vt_quantize_mma_prepared": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "vt_quantize_mma_profile": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _int, _int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "vt_quantize_mma_pair_min": (_i64, [_i64]),
     "vt_quantize_host": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _int, _int, _vp, _i64]),
     "vt_host_release": (_int, []),
     "vt_kmeans_init": (_int, [_vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp, _vp]),

@@ -669,6 +669,17 @@ extern "C" int vt_kmeans_assign_mma(const void *d_desc, int dtype, int dp, const
 }
 
 int64_t vt_mma_prepared_bytes(int k, int depth);
+// Batches of at least this many rows take TWO tree levels per launch (vt_quantize_pair.cu).  Off by default: the
+// kernel halves the DRAM traffic of the descent (3 row reads instead of 6) but its per-chunk bookkeeping is latency
+// bound and on one B200 it is still behind the one-level kernel at 100 M rows.  VT_MMA_PAIR_MIN
+// in the environment or vt_quantize_mma_pair_min() switch it on.
+static int64_t g_pair_min = (int64_t)1 << 62;
+extern "C" int64_t vt_quantize_mma_pair_min(int64_t min_rows)
+{
+    const int64_t old = g_pair_min;
+    if (min_rows != 0) g_pair_min = min_rows > 0 ? min_rows : ((int64_t)1 << 62);
+    return old;
+}
 int vt_mma_levels_paired(const void *d_desc, int64_t n, const float *cent, const uint8_t *internal, const int32_t *ref_id,
                          int k, int depth, int32_t *leaf, int32_t *word, uint64_t *stats, const uint8_t *bimg,
                          const int *cn32, int *cninfo, void *sortwork, bool defer, cudaStream_t s, cudaEvent_t *ev,
@@ -754,7 +765,6 @@ int vt_mma_levels(const void *d_desc, int64_t n, const float *cent, const uint8_
     static bool attr_set = false;
     static int ctas10 = 8, ctas16 = 7;                           // resident CTAs per SM the grid is sized for (k <= 10 / k <= 16)
     static int64_t defer_min = (int64_t)1 << 22;                 // batches from this size on defer the last level's output
-    static int64_t pair_min = (int64_t)1 << 20;                  // batches from this size on take two levels per launch
     const bool narrow = mma_slots(k) == 10;
     const int smem = MM_A_BYTES + (int)mma_plane_bytes(k) + 1024;
     if (!attr_set) {
@@ -763,14 +773,14 @@ int vt_mma_levels(const void *d_desc, int64_t n, const float *cent, const uint8_
         e = getenv("VT_MMA_DEFER_MIN");
         if (e) defer_min = atoll(e);
         e = getenv("VT_MMA_PAIR_MIN");                            // <= 0 switches the two-level kernel off
-        if (e) pair_min = atoll(e) > 0 ? atoll(e) : ((int64_t)1 << 62);
+        if (e) g_pair_min = atoll(e) > 0 ? atoll(e) : ((int64_t)1 << 62);
         VT_CUDA(cudaFuncSetAttribute(level_mma_kernel<7, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      MM_A_BYTES + PlaneCfg<16>::B_BYTES + 1024));
         VT_CUDA(cudaFuncSetAttribute(level_mma_kernel<8, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      MM_A_BYTES + PlaneCfg<10>::B_BYTES + 1024));
         attr_set = true;
     }
-    if (n >= pair_min && depth >= 2) {
+    if (n >= g_pair_min && depth >= 2) {
         // two levels per launch (vt_quantize_pair.cu): every row is read from DRAM once per PAIR of levels
         // (the per-node records live behind the 32-bit norms of the prepared buffer; they are rewritten on every call, so the
         // buffer only has to be large enough -- vt_mma_prepared_bytes)

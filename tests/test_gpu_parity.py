@@ -196,9 +196,9 @@ def test_tensor_core_deferred_output_on_small_batches(cuda):
 
 @pytest.mark.parametrize("defer", ["0", "1"])
 def test_two_levels_per_launch_on_small_batches(cuda, defer):
-    """Batches >= 2^20 rows take TWO tree levels per launch (vt_quantize_pair.cu: chunked, warp-specialised, the second
-    level re-gathers from L2).  A child process lowers that threshold to 1 row (VT_MMA_PAIR_MIN, read once by the
-    library) and repeats the tensor-core parity cases -- ragged trees, exact ties, k = 16, odd and even depths, near-tie
+    """The tcgen05 descent can take TWO tree levels per launch (vt_quantize_pair.cu: persistent warp-specialised CTAs, TMA
+    gathers, the second level re-gathers from L2; opt-in).  A child process sets the threshold to 1 row (VT_MMA_PAIR_MIN,
+    read once by the library) and repeats the tensor-core parity cases -- ragged trees, exact ties, k = 16, odd and even depths, near-tie
     margins -- with the ids written directly (defer=0) and through the deferred (row, child) pairs (defer=1)."""
     import os
     import subprocess

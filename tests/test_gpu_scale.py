@@ -295,3 +295,22 @@ def test_dense_top_falls_back_when_a_database_count_overflows(vt, cuda):
     ok = vt.Database(vt.ArrayDataset(images[:99]), voc)
     ok.index()
     assert ok._dense_index is not None
+
+
+def test_two_levels_per_launch_at_scale_equals_one_level_per_launch(vt, cuda):
+    """16 M descriptors through the k=10, L=6 tree: the two-levels-per-launch kernel (3 DRAM reads of every row) and the
+    default one-level kernel (6 reads) must return the same ids -- regular chunks, chunk pipelining over ~100 chunks per CTA,
+    node boundaries inside chunks, the deferred output."""
+    torch = _torch()
+    lib = vt._native.load()
+    ft, cent = _full_tree(vt, cuda, 10, 6, 128, seed=7)
+    x = vt.synth.descriptors_from_tree(cent, 10, 6, 16_000_000, seed=21)
+    td = ft.device(cuda)
+    a = vt.engine.quantize(td, 10, 6, x, method="mma")
+    prev = lib.vt_quantize_mma_pair_min(1 << 20)
+    try:
+        b = vt.engine.quantize(td, 10, 6, x, method="mma")
+        c = vt.engine.quantize(td, 10, 6, x[:3_000_001], method="mma")      # below the deferred-output threshold, ragged last chunk
+    finally:
+        lib.vt_quantize_mma_pair_min(prev if prev < (1 << 62) else -1)
+    assert torch.equal(a, b) and torch.equal(a[:3_000_001], c)
