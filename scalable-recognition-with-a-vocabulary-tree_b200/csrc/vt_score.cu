@@ -224,7 +224,8 @@ score_shard_tf_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__r
                       const double *__restrict__ img_rnorm, int64_t n_img, int64_t n_ref, int n_shards,
                       const int64_t *__restrict__ q_off, const int32_t *__restrict__ q_node,
                       const float *__restrict__ q_val, int64_t n_query, int topk, double *__restrict__ out_key,
-                      int32_t *__restrict__ out_id, const double *__restrict__ shard_rho)
+                      int32_t *__restrict__ out_id, const double *__restrict__ shard_rho,
+                      const int32_t *__restrict__ seed, int64_t seed_stride, double *__restrict__ all_key)
 {
     constexpr int PER = R / SC_THREADS;
     extern __shared__ unsigned char s_raw[];
@@ -244,7 +245,9 @@ score_shard_tf_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__r
         const int shard = (int)(pair - q * n_shards);
         const int64_t img0 = (int64_t)shard * R;
         const int n_here = (int)((n_img - img0) < R ? (n_img - img0) : R);
-        for (int t = threadIdx.x; t < R; t += SC_THREADS) s_acc[t] = 0;
+        // seeded (all-nodes indexes): the accumulators start from the int32 dots over the dense top levels (vt_dense_dots)
+        for (int t = threadIdx.x; t < R; t += SC_THREADS)
+            s_acc[t] = (seed && t < n_here) ? seed[(size_t)q * seed_stride + img0 + t] : 0;
         if (threadIdx.x == 0) s_ncand = 0;
         if (threadIdx.x < 64) s_hist[threadIdx.x] = 0;
         __syncthreads();
@@ -289,7 +292,7 @@ score_shard_tf_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__r
         for (int u = 0; u < PER; ++u) {
             const int a = s_acc[u * SC_THREADS + threadIdx.x];
             mine_acc[u] = a;
-            if (a >= 2) atomicAdd(&s_hist[a < 63 ? a : 63], 1);
+            if (a >= 2 && !seed) atomicAdd(&s_hist[a < 63 ? a : 63], 1);      // (seeded dots all land in the last bin: skip)
         }
         __syncthreads();
         if (warp == 0) {
@@ -313,7 +316,9 @@ score_shard_tf_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__r
         }
         __syncthreads();
         const int d_lo = s_thr;
-        bool fast = d_lo > 0;
+        // (seeded: every image shares the top levels with the query, the dots are ~1e6 and the 64-bin bound says nothing:
+        // straight to the exhaustive selection, which recomputes keys on demand and keeps the shared memory at 4 B per image)
+        bool fast = d_lo > 0 && !seed;
         if (fast) {
 #pragma unroll
             for (int u = 0; u < PER; ++u) {
@@ -377,6 +382,7 @@ score_shard_tf_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__r
             for (int u = 0; u < PER; ++u) {
                 const int t = u * SC_THREADS + threadIdx.x;
                 const double key = key_of(t);
+                if (all_key && t < n_here) all_key[q * n_img + img0 + t] = key;
                 if (better(key, (int32_t)(img0 + t), bkey, bid)) { bkey = key; bid = (int32_t)(img0 + t); }
             }
             for (int r = 0; r < topk; ++r) {
@@ -666,12 +672,12 @@ static int launch_score_tf(const uint32_t *post_off, const void *postings, const
         auto kern = score_shard_tf_kernel<R, 6>;
         VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<blocks, SC_THREADS, smem, s>>>(post_off, (const uint32_t *)postings, img_rnorm, n_img, n_ref, n_shards, q_off,
-                                              q_node, q_val, n_query, topk, out_key, out_id, shard_rho);
+                                              q_node, q_val, n_query, topk, out_key, out_id, shard_rho, nullptr, 0, nullptr);
     } else {
         auto kern = score_shard_tf_kernel<R, 4>;
         VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<blocks, SC_THREADS, smem, s>>>(post_off, (const uint32_t *)postings, img_rnorm, n_img, n_ref, n_shards, q_off,
-                                              q_node, q_val, n_query, topk, out_key, out_id, shard_rho);
+                                              q_node, q_val, n_query, topk, out_key, out_id, shard_rho, nullptr, 0, nullptr);
     }
     VT_LAUNCH_CHECK();
     return VT_OK;
@@ -768,13 +774,15 @@ extern "C" int vt_score_topk_seeded(const uint32_t *d_post_off, const void *d_po
     if (n_query == 0) return VT_OK;
     constexpr int R = 8192;
     const int n_shards = (int)((n_img + R - 1) / R);
-    auto kern = score_shard_kernel<VT_SCORE_TF_L2, R>;
-    const size_t smem = (size_t)R * 12;
+    // the tf kernel in its long-list configuration (whole warps walk the runs, 6 CTAs per SM): 4 B of shared memory per
+    // image, keys recomputed on demand by the exhaustive selection
+    auto kern = score_shard_tf_kernel<R, 6>;
+    const size_t smem = (size_t)R * 4 + SC_CAND * 12;
     VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t pairs = n_query * n_shards, cap = (int64_t)vt_sm_count() * 2 * 8;
+    const int64_t pairs = n_query * n_shards, cap = (int64_t)vt_sm_count() * 6 * 4;
     kern<<<(int)(pairs < cap ? pairs : cap), SC_THREADS, smem, (cudaStream_t)stream>>>(
         d_post_off, (const uint32_t *)d_postings, d_img_rnorm, n_img, n_ref, n_shards, d_q_off, d_q_node, d_q_val, n_query, topk,
-        d_shard_key, d_shard_id, d_all_key, nullptr, d_seed, seed_stride);
+        d_shard_key, d_shard_id, nullptr, d_seed, seed_stride, d_all_key);
     VT_LAUNCH_CHECK();
     return VT_OK;
 }
