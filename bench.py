@@ -57,7 +57,27 @@ def parse():
     ap.add_argument("--build-iters", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--profile-range", default="", choices=["", "quantize", "retrieval", "retrieval_all_nodes"],
+                    help="cudaProfilerStart/Stop around this timed region (for `ncu --profile-from-start off` launch lists)")
     return ap.parse_args()
+
+
+class ProfileRange:
+    """cudaProfilerStart/Stop around a timed region when --profile-range names it: `ncu --profile-from-start off` then lists
+    exactly the launches bench.py times (a no-op without a profiler attached)."""
+
+    def __init__(self, torch, on: bool):
+        self.torch, self.on = torch, on
+
+    def __enter__(self):
+        if self.on:
+            self.torch.cuda.synchronize()
+            self.torch.cuda.profiler.start()
+
+    def __exit__(self, *a):
+        if self.on:
+            self.torch.cuda.synchronize()
+            self.torch.cuda.profiler.stop()
 
 
 # ----------------------------------------------------------------------------------- clocks
@@ -262,7 +282,7 @@ def main():
     stats.zero_()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local) as clocks, ProfileRange(torch, args.profile_range == "quantize"):
         t0 = time.perf_counter()
         for a, b in ev:
             a.record()
@@ -582,11 +602,12 @@ def bench_retrieval(args, torch, vt, engine, nat, dev, rank, world, comm, cent, 
         ids, sc = resident_pass()
     steps = 3
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        ids, sc = resident_pass()
-    barrier()
-    ms = max_over_ranks((time.perf_counter() - t0) / steps * 1e3)
+    with ProfileRange(torch, args.profile_range == ("retrieval_all_nodes" if all_nodes else "retrieval")):
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ids, sc = resident_pass()
+        barrier()
+        ms = max_over_ranks((time.perf_counter() - t0) / steps * 1e3)
     back_t = torch.from_numpy(back).to(dev)
     ids_q, sc_q = ids[back_t], sc[back_t]
     ok = bool((ids_q[:n_member, 0].to(torch.int64) == member).all().item() and (sc_q[:n_member, 0] == 0).all().item())
@@ -638,7 +659,7 @@ def bench_retrieval(args, torch, vt, engine, nat, dev, rank, world, comm, cent, 
                       "algorithmic_GBps": csr["nnz"] * (12.0 + 20.0 * -(-int(index["n_shards"] * flat.n_ref).bit_length() // 8) + 16.0)
                                           / t_invert / 1e9}}
     if not all_nodes:
-        alg = 8.0 * wpi * (db_images * wpi / n_leaf)
+        alg = 4.0 * wpi * (db_images * wpi / n_leaf)          # 4-byte postings of the query's words
         hbm = {"algorithmic_bytes_per_query": alg, "achieved_GBps": alg * q / (ms * 1e-3) / 1e9}
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "r02_scorer_traffic.json")))

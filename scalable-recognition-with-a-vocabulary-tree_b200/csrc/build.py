@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 LIB = os.path.join(PKG, "libvtree_b200.so")
-SOURCES = ["vt_abi.cu", "vt_quantize.cu", "vt_quantize_sorted.cu", "vt_quantize_mma.cu", "vt_quantize_pair.cu", "vt_kmeans.cu", "vt_sort.cu", "vt_encode.cu", "vt_score.cu", "vt_weight.cu", "vt_dense.cu", "vt_bench.cu"]
+SOURCES = ["vt_abi.cu", "vt_quantize.cu", "vt_quantize_sorted.cu", "vt_quantize_mma.cu", "vt_quantize_pair.cu", "vt_kmeans.cu", "vt_sort.cu", "vt_encode.cu", "vt_score.cu", "vt_score_query.cu", "vt_weight.cu", "vt_dense.cu", "vt_bench.cu"]
 HEADERS = ["vt_common.cuh", "vt_mma_common.cuh", os.path.join(ROOT, "include", "vtree_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]

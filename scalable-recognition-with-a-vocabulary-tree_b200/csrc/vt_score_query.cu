@@ -1,0 +1,459 @@
+// vt_score_query.cu -- tf / L2 inverted-file scoring (database.py:55-87) with the top-k CARRIED from shard to shard.
+//
+// vt_score.cu gives every (query, shard) pair its own CTA and its own top-k: a histogram pass (or, for all-nodes indexes
+// whose dots are ~1e6, ten block-wide arg-max rounds) per pair, one list per pair in HBM.  ncu (profiles/r02_*scorer*):
+// that selection is half of the instructions of a pair in leaf-words mode and a third in all-nodes mode, the lane-per-word
+// walk issues ~1.35 warp instructions per posting with 32 separate sectors per load instruction, and the warp-per-run walk
+// of long lists has ONE load in flight per warp.  Here a CTA takes a query through a GROUP of consecutive shards:
+//   * the k best (key, id) pairs seen so far stay in shared memory; their worst key T is an exact lower bound of the final
+//     k-th key, so in every further shard only images that can beat T are looked at: `dot >= ceil(T / max 1/|d|)` (integer
+//     test, leaf-words indexes) or `dot / |d| >= T` (all-nodes indexes: every image shares the top levels with the
+//     query, the integer bound says nothing) -- typically 0-3 candidates, inserted into the list by one warp.  Only the
+//     first shard of a group (no T yet), or a shard where nothing can be pruned (T <= 0), runs the exhaustive selection;
+//   * the row pointers of a query word are fetched ONCE per 8 shards (the 9 pointers sit in one or two sectors) and kept
+//     on chip as run lengths -- not one 32-byte sector per (word, shard) -- and the word's node is not looked up again;
+//   * the walk is FLAT: the posting runs of 32 query words are concatenated (prefix sum of their lengths); lane l of the
+//     warp takes position 32 c + l of chunk c, finds its word from a head-bit mask with one popc, and 4 chunks are loaded
+//     before the first is accumulated -- coalesced requests with every lane busy, whatever the run length; runs longer
+//     than 64 postings are walked by the whole warp with 4 x 32 postings in flight.  (Measured alternative: 2^n lanes per
+//     run, 32 / 2^n runs per round, 8 rounds in flight, no shared-memory bookkeeping -- 7 % slower at the best n.)
+// Shared-memory atomics are not the limit: tools/atoms_probe.cu measures 12 random 32-bit atomicAdd lanes per clock and
+// SM (3.4 T/s), the scorer uses ~0.8.  The kernel is latency bound (8 warps per scheduler, dependent LDS -> LDG -> ATOMS
+// chains; ncu: issue slots 35 % busy, long scoreboard 34 %, short scoreboard 19 %, barrier 18 % of the stall samples).
+// Results are the same (key, id) sets as vt_score.cu's kernels: dots are exact integers, keys binary64, order =
+// (key descending, id ascending) like the reference's stable ascending sort of the scores (database.py:79-80).
+#include "vt_common.cuh"
+#include <limits.h>
+
+namespace {
+constexpr int SQ_THREADS = 256;
+constexpr int SQ_WARPS = SQ_THREADS / 32;
+constexpr int SQ_MAXK = 64;
+constexpr int SQ_R = 8192;                 // images per shard (vt_score_shard_size)
+constexpr int SQ_PER = SQ_R / SQ_THREADS;
+constexpr int SQ_CAND = 128;               // candidates per shard before the exhaustive selection takes over
+constexpr int SQ_SUB = 8;                  // shards whose run lengths are fetched together (one pointer sector per word)
+constexpr int SQ_WCACHE = 1024;            // query words whose runs are tracked on chip (the rest re-read their pointers)
+constexpr uint32_t SQ_LONG = 64;           // longer runs leave the flat walk
+constexpr int SQ_HEADS = 64;               // 32 words x 64 postings = 2048 flat positions
+constexpr int SQ_U = 4;                    // chunks (posting loads per lane) in flight
+constexpr uint32_t SQ_LOCAL_MASK = 8191u;  // posting = (tf << 13) | local image index (vt_posting_pack)
+constexpr int SQ_LOCAL_BITS = 13;
+constexpr int SQ_TAKEN = INT_MIN;
+
+struct SqScratch {                         // per warp
+    uint32_t base[32];                     // compacted non-empty words: posting index of flat position 0 of the word
+    int tf[32];                            //   ... and the query's count of the word
+    uint32_t head[SQ_HEADS];               // bit j of head[c]: flat position 32 c + j starts a word's run
+};
+
+struct SqShared {
+    int acc[SQ_R];
+    double ckey[SQ_CAND];
+    int cslot[SQ_CAND];
+    double lkey[SQ_MAXK], nkey[SQ_MAXK];   // the carried list (best first) and the one the exhaustive selection builds
+    int32_t lid[SQ_MAXK], nid[SQ_MAXK];
+    SqScratch ws[SQ_WARPS];
+    // thread-private slots (word i of the query belongs to thread i % 256): where the word's run starts in the current
+    // shard, its query count, and the lengths of its runs in the SQ_SUB shards of the current sub-group (255 = longer)
+    uint32_t w_run[SQ_WCACHE];
+    uint16_t w_tf[SQ_WCACHE];
+    uint8_t w_len[SQ_SUB][SQ_WCACHE];
+    double r_key[SQ_WARPS];
+    int32_t r_id[SQ_WARPS];
+    int r_owner[SQ_WARPS];
+    int ncand, ln;
+};
+
+__device__ __forceinline__ bool sq_better(double ka, int32_t ia, double kb, int32_t ib)
+{
+    return ka > kb || (ka == kb && ia < ib);
+}
+
+__device__ __forceinline__ void sq_block_best(double &key, int32_t &id, int &owner, SqShared &sh)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    owner = threadIdx.x;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const double k2 = __shfl_xor_sync(VT_FULL, key, o);
+        const int32_t i2 = __shfl_xor_sync(VT_FULL, id, o);
+        const int o2 = __shfl_xor_sync(VT_FULL, owner, o);
+        if (sq_better(k2, i2, key, id)) { key = k2; id = i2; owner = o2; }
+    }
+    if (lane == 0) { sh.r_key[warp] = key; sh.r_id[warp] = id; sh.r_owner[warp] = owner; }
+    __syncthreads();
+    key = sh.r_key[0]; id = sh.r_id[0]; owner = sh.r_owner[0];
+#pragma unroll
+    for (int w = 1; w < SQ_WARPS; ++w)
+        if (sq_better(sh.r_key[w], sh.r_id[w], key, id)) { key = sh.r_key[w]; id = sh.r_id[w]; owner = sh.r_owner[w]; }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void sq_add(int *acc, uint32_t pe, int tf)
+{
+    atomicAdd(&acc[pe & SQ_LOCAL_MASK], tf * (int)(pe >> SQ_LOCAL_BITS));
+}
+
+// SEEDED: accumulators start from the int32 dots over the dense top levels (vt_dense_dots) and candidates are filtered by
+// their exact key; otherwise they start from zero and the filter is the integer bound through shard_rmax.
+template <bool SEEDED, int MINB>
+__global__ void __launch_bounds__(SQ_THREADS, MINB)
+score_query_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__restrict__ postings,
+                   const double *__restrict__ img_rnorm, int64_t n_img, int n_shards, const int64_t *__restrict__ q_off,
+                   const int32_t *__restrict__ q_node, const float *__restrict__ q_val, int64_t n_query, int topk,
+                   const double *__restrict__ shard_rmax, const int32_t *__restrict__ seed, int64_t seed_stride,
+                   int n_groups, int per_group, double *__restrict__ out_key, int32_t *__restrict__ out_id)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    SqShared &sh = *reinterpret_cast<SqShared *>(s_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t le_mask = (2u << lane) - 1u, lt_mask = (1u << lane) - 1u;
+    SqScratch &ws = sh.ws[warp];
+
+    for (int64_t item = blockIdx.x; item < n_query * n_groups; item += gridDim.x) {
+        const int64_t q = item / n_groups;
+        const int g = (int)(item - q * n_groups);
+        const int s0 = g * per_group, s1 = s0 + per_group < n_shards ? s0 + per_group : n_shards;
+        const int64_t qb = q_off[q], qe = q_off[q + 1];
+
+        auto fill = [&](int shard) {
+            if (SEEDED) {
+                const int64_t img0 = (int64_t)shard * SQ_R;
+                const int n_here = (int)((n_img - img0) < SQ_R ? (n_img - img0) : SQ_R);
+                const int32_t *row = seed + (size_t)q * seed_stride + img0;
+                for (int t = tid; t < SQ_R; t += SQ_THREADS) sh.acc[t] = t < n_here ? __ldg(row + t) : 0;
+            } else {
+                int4 *a4 = reinterpret_cast<int4 *>(sh.acc);
+                for (int t = tid; t < SQ_R / 4; t += SQ_THREADS) a4[t] = make_int4(0, 0, 0, 0);
+            }
+        };
+        if (s0 < s1) fill(s0);
+        if (tid == 0) { sh.ln = 0; sh.ncand = 0; }
+        __syncthreads();
+
+        for (int shard = s0; shard < s1; ++shard) {
+            const int64_t img0 = (int64_t)shard * SQ_R;
+            const int n_here = (int)((n_img - img0) < SQ_R ? (n_img - img0) : SQ_R);
+            const uint32_t *off = post_off + shard;                // row of (node, shard) = node * n_shards + shard
+
+            // ---- walk ------------------------------------------------------------------------------------------------
+            // one call = the runs of 32 query words (lane l: run [b, b + len) of a word with query count tf)
+            auto walk32 = [&](uint32_t b, uint32_t len, int tf) {
+                const bool is_long = len > SQ_LONG;
+                unsigned int m = __ballot_sync(VT_FULL, is_long);
+                while (m) {                                        // long runs: the whole warp, SQ_U x 32 postings in flight
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t lb = __shfl_sync(VT_FULL, b, src), lend = lb + __shfl_sync(VT_FULL, len, src);
+                    const int ltf = __shfl_sync(VT_FULL, tf, src);
+                    for (uint32_t p = lb + lane; p < lend; p += 32 * SQ_U) {
+                        uint32_t pe[SQ_U];
+#pragma unroll
+                        for (int u = 0; u < SQ_U; ++u) pe[u] = p + 32 * u < lend ? __ldg(postings + p + 32 * u) : 0u;
+#pragma unroll
+                        for (int u = 0; u < SQ_U; ++u)
+                            if (p + 32 * u < lend) sq_add(sh.acc, pe[u], ltf);
+                    }
+                }
+                if (is_long) len = 0;
+                // flat walk over the concatenated short runs of the 32 words
+                uint32_t incl = len;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(VT_FULL, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const uint32_t total = __shfl_sync(VT_FULL, incl, 31);
+                if (total == 0) return;                            // (warp uniform)
+                const uint32_t excl = incl - len;
+                ws.head[lane] = 0;
+                ws.head[lane + 32] = 0;
+                __syncwarp();
+                const bool ne = len > 0;
+                const unsigned int nem = __ballot_sync(VT_FULL, ne);
+                if (ne) {
+                    const int rank = __popc(nem & lt_mask);
+                    ws.base[rank] = b - excl;
+                    ws.tf[rank] = tf;
+                    atomicOr(&ws.head[excl >> 5], 1u << (excl & 31));
+                }
+                __syncwarp();
+                int before = 0;                                    // words that start before the current chunk
+                for (uint32_t c0 = 0; c0 * 32 < total; c0 += SQ_U) {
+                    uint32_t pe[SQ_U];
+                    int tv[SQ_U];
+#pragma unroll
+                    for (int u = 0; u < SQ_U; ++u) {
+                        const uint32_t c = c0 + u, j = c * 32 + lane;
+                        const uint32_t h = c * 32 < total ? ws.head[c] : 0u;
+                        const int idx = before + __popc(h & le_mask) - 1;
+                        before += __popc(h);
+                        pe[u] = 0u;
+                        tv[u] = 0;                                 // (tf > 0 for every real word: 0 marks an idle slot)
+                        if (j < total) {
+                            tv[u] = ws.tf[idx];
+                            pe[u] = __ldg(postings + (ws.base[idx] + j));
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < SQ_U; ++u)
+                        if (tv[u]) sq_add(sh.acc, pe[u], tv[u]);
+                }
+                __syncwarp();                                      // the scratch is rewritten by the next 32 words
+            };
+            const int sub = (shard - s0) % SQ_SUB;
+            if (sub == 0) {
+                // run lengths of the next SQ_SUB shards: the 9 row pointers of a word sit in one or two sectors and are read
+                // ONCE here -- not one sector per (word, shard) -- and the word's node is not looked up again
+                const int last = n_shards - shard;                 // pointer index of the row's end
+                for (int i = tid; i < SQ_WCACHE; i += SQ_THREADS) {
+                    const int64_t w = qb + i;
+                    uint32_t p[SQ_SUB + 1];
+                    int tf = 0;
+                    if (w < qe) {
+                        const uint32_t *r = off + (size_t)__ldg(q_node + w) * n_shards;
+                        tf = (int)__ldg(q_val + w);
+#pragma unroll
+                        for (int j = 0; j <= SQ_SUB; ++j) p[j] = __ldg(r + (j < last ? j : last));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j <= SQ_SUB; ++j) p[j] = 0u;
+                    }
+                    sh.w_run[i] = p[0];
+                    sh.w_tf[i] = (uint16_t)(tf < 65535 ? tf : 65535);
+#pragma unroll
+                    for (int j = 0; j < SQ_SUB; ++j) {
+                        const uint32_t len = p[j + 1] - p[j];
+                        sh.w_len[j][i] = (uint8_t)(len < 255u && tf < 65535 ? len : 255u);
+                    }
+                }
+                // (thread-private slots: no barrier)
+            }
+#pragma unroll 1
+            for (int i = tid; i < SQ_WCACHE && qb + (i - lane) < qe; i += SQ_THREADS) {
+                uint32_t len = sh.w_len[sub][i], b = sh.w_run[i];
+                int tf = sh.w_tf[i];
+                if (len == 255u) {                                 // a long run (or a huge query count): read it again
+                    const int64_t w = qb + i;
+                    const uint32_t *r = off + (size_t)__ldg(q_node + w) * n_shards;
+                    b = __ldg(r);
+                    len = __ldg(r + 1) - b;
+                    tf = (int)__ldg(q_val + w);
+                }
+                sh.w_run[i] = b + len;
+                walk32(b, len, tf);
+            }
+            for (int64_t w0 = qb + SQ_WCACHE + (int64_t)warp * 32; w0 < qe; w0 += SQ_THREADS) {
+                const int64_t w = w0 + lane;
+                uint32_t b = 0, len = 0;
+                int tf = 0;
+                if (w < qe) {
+                    const uint32_t *r = off + (size_t)__ldg(q_node + w) * n_shards;
+                    b = __ldg(r);
+                    len = __ldg(r + 1) - b;
+                    tf = (int)__ldg(q_val + w);
+                }
+                walk32(b, len, tf);
+            }
+            __syncthreads();
+
+            // ---- selection against the carried list ------------------------------------------------------------------
+            const int ln = sh.ln;
+            const double T = ln == topk ? sh.lkey[topk - 1] : -1.0;
+            bool exhaustive = !(T > 0.0);                          // nothing can be pruned: untouched images reach T
+            if (!exhaustive) {
+                if (SEEDED) {
+#pragma unroll 4
+                    for (int u = 0; u < SQ_PER; ++u) {
+                        const int t = u * SQ_THREADS + tid;
+                        const int a = sh.acc[t];
+                        if (a > 0 && t < n_here) {
+                            const double key = (double)a * __ldg(img_rnorm + img0 + t);   // (empty images: a == 0)
+                            if (key >= T) {
+                                const int pos = atomicAdd(&sh.ncand, 1);
+                                if (pos < SQ_CAND) { sh.cslot[pos] = t; sh.ckey[pos] = key; }
+                            }
+                        }
+                    }
+                } else {
+                    // smallest integer dot whose key can reach T: key = dot / |d| <= dot * rmax
+                    const double rmax = __ldg(shard_rmax + shard);
+                    int d_lo = INT_MAX;
+                    if (rmax > 0.0) {
+                        const double x = ceil(T / rmax);
+                        d_lo = x >= 2147483647.0 ? INT_MAX : (int)x;
+                        while (d_lo > 1 && (double)(d_lo - 1) * rmax >= T) --d_lo;
+                        while (d_lo < INT_MAX && (double)d_lo * rmax < T) ++d_lo;
+                        if (d_lo < 1) d_lo = 1;
+                    }
+                    const int4 *a4 = reinterpret_cast<const int4 *>(sh.acc);
+#pragma unroll 2
+                    for (int u = 0; u < SQ_PER / 4; ++u) {
+                        const int t4 = u * SQ_THREADS + tid;
+                        const int4 a = a4[t4];
+                        const int mx = max(max(a.x, a.y), max(a.z, a.w));
+                        if (mx >= d_lo) {
+                            const int av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                if (av[i] >= d_lo) {
+                                    const int pos = atomicAdd(&sh.ncand, 1);
+                                    if (pos < SQ_CAND) sh.cslot[pos] = t4 * 4 + i;
+                                }
+                        }
+                    }
+                }
+                __syncthreads();
+                const int nc = sh.ncand;
+                if (nc > SQ_CAND) {
+                    exhaustive = true;                             // (block uniform)
+                } else if (nc > 0) {
+                    if (!SEEDED) {
+                        for (int i = tid; i < nc; i += SQ_THREADS) {
+                            const int t = sh.cslot[i];
+                            sh.ckey[i] = (double)sh.acc[t] * __ldg(img_rnorm + img0 + t);
+                        }
+                        __syncthreads();
+                    }
+                    if (warp == 0) {
+                        // insert the candidates that beat the current worst entry, one at a time (the list stays sorted)
+                        for (int i0 = 0; i0 < nc; i0 += 32) {
+                            const int i = i0 + lane;
+                            const double ck = i < nc ? sh.ckey[i] : -2.0;
+                            const int32_t cid = i < nc ? (int32_t)(img0 + sh.cslot[i]) : 0x7fffffff;
+                            unsigned int live = __ballot_sync(VT_FULL, i < nc);
+                            while (live) {
+                                const int src = __ffs(live) - 1;
+                                live &= live - 1;
+                                const double k = __shfl_sync(VT_FULL, ck, src);
+                                const int32_t id = __shfl_sync(VT_FULL, cid, src);
+                                const bool h0 = lane < topk, h1 = lane + 32 < topk;
+                                const double k0 = h0 ? sh.lkey[lane] : 0.0, k1 = h1 ? sh.lkey[lane + 32] : 0.0;
+                                const int32_t d0 = h0 ? sh.lid[lane] : 0, d1 = h1 ? sh.lid[lane + 32] : 0;
+                                const bool b0 = h0 && sq_better(k0, d0, k, id), b1 = h1 && sq_better(k1, d1, k, id);
+                                const int pos = __popc(__ballot_sync(VT_FULL, b0)) + __popc(__ballot_sync(VT_FULL, b1));
+                                if (pos < topk) {                  // entries from pos on move down by one, the last one drops
+                                    __syncwarp();
+                                    if (h0 && !b0 && lane + 1 < topk) { sh.lkey[lane + 1] = k0; sh.lid[lane + 1] = d0; }
+                                    if (h1 && !b1 && lane + 33 < topk) { sh.lkey[lane + 33] = k1; sh.lid[lane + 33] = d1; }
+                                    __syncwarp();
+                                    if (lane == 0) { sh.lkey[pos] = k; sh.lid[pos] = id; }
+                                    __syncwarp();
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            if (exhaustive) {
+                // ---- k rounds of block arg-max over (this shard's images) U (the carried list) -------------------------
+                auto key_of = [&](int t) -> double {
+                    if (t >= n_here) return -2.0;
+                    const int a = sh.acc[t];
+                    if (a == SQ_TAKEN) return -2.0;
+                    const double rn = __ldg(img_rnorm + img0 + t);
+                    return rn < 0.0 ? -1.0 : (double)a * rn;
+                };
+                double lk = tid < ln ? sh.lkey[tid] : -2.0;        // thread t owns list entry t
+                const int32_t li = tid < ln ? sh.lid[tid] : 0x7fffffff;
+                double bkey = -2.0; int32_t bid = 0x7fffffff;
+                for (int u = 0; u < SQ_PER; ++u) {
+                    const int t = u * SQ_THREADS + tid;
+                    const double key = key_of(t);
+                    if (sq_better(key, (int32_t)(img0 + t), bkey, bid)) { bkey = key; bid = (int32_t)(img0 + t); }
+                }
+                int n_new = 0;
+                for (int r = 0; r < topk; ++r) {
+                    double key = bkey; int32_t id = bid; int owner;
+                    if (sq_better(lk, li, key, id)) { key = lk; id = li; }
+                    sq_block_best(key, id, owner, sh);
+                    if (key > -2.0) n_new = r + 1;
+                    if (tid == 0) { sh.nkey[r] = key; sh.nid[r] = key > -2.0 ? id : -1; }
+                    if (tid == owner && key > -2.0) {
+                        if ((int64_t)id >= img0) {                 // one of this shard's images (list ids are smaller)
+                            sh.acc[id - img0] = SQ_TAKEN;
+                            bkey = -2.0; bid = 0x7fffffff;
+                            for (int u = 0; u < SQ_PER; ++u) {
+                                const int t = u * SQ_THREADS + tid;
+                                const double k2 = key_of(t);
+                                if (sq_better(k2, (int32_t)(img0 + t), bkey, bid)) { bkey = k2; bid = (int32_t)(img0 + t); }
+                            }
+                        } else {
+                            lk = -2.0;
+                        }
+                    }
+                }
+                if (tid < topk) { sh.lkey[tid] = sh.nkey[tid]; sh.lid[tid] = sh.nid[tid]; }
+                if (tid == 0) sh.ln = n_new;
+            }
+            __syncthreads();
+            if (shard + 1 < s1) fill(shard + 1);
+            if (tid == 0) sh.ncand = 0;
+            __syncthreads();
+        }
+
+        if (tid < topk) {
+            const size_t o = ((size_t)q * n_groups + g) * topk + tid;
+            const bool have = tid < sh.ln;
+            out_key[o] = have ? sh.lkey[tid] : -2.0;
+            out_id[o] = have ? sh.lid[tid] : -1;
+        }
+        __syncthreads();
+    }
+}
+}  // namespace
+
+// lists per query vt_score_topk_carried should write: enough (query, group) items to fill the device about four times over,
+// groups as long as possible (the exhaustive first shard of a group is paid once per group)
+extern "C" int vt_score_group_count(int64_t n_query, int64_t n_img)
+{
+    if (n_query <= 0 || n_img <= 0) return 1;
+    const int64_t n_shards = (n_img + SQ_R - 1) / SQ_R;
+    const int64_t want = (int64_t)vt_sm_count() * 4 * 4;
+    int64_t n_groups = (want + n_query - 1) / n_query;
+    if (n_groups < 1) n_groups = 1;
+    if (n_groups > n_shards) n_groups = n_shards;
+    const int64_t per = (n_shards + n_groups - 1) / n_groups;
+    return (int)((n_shards + per - 1) / per);
+}
+
+template <bool SEEDED>
+static int launch_query(const uint32_t *post_off, const uint32_t *postings, const double *img_rnorm, int64_t n_img, int n_shards,
+                        const int64_t *q_off, const int32_t *q_node, const float *q_val, int64_t n_query, int topk,
+                        const double *shard_rmax, const int32_t *seed, int64_t seed_stride, int n_groups, double *out_key,
+                        int32_t *out_id, cudaStream_t s)
+{
+    auto kern = score_query_kernel<SEEDED, 4>;
+    const size_t smem = sizeof(SqShared);
+    VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int per_group = (n_shards + n_groups - 1) / n_groups;
+    const int64_t items = n_query * n_groups, cap = (int64_t)vt_sm_count() * 4;
+    kern<<<(int)(items < cap ? items : cap), SQ_THREADS, smem, s>>>(post_off, postings, img_rnorm, n_img, n_shards, q_off, q_node,
+                                                                    q_val, n_query, topk, shard_rmax, seed, seed_stride, n_groups,
+                                                                    per_group, out_key, out_id);
+    VT_LAUNCH_CHECK();
+    return VT_OK;
+}
+
+extern "C" int vt_score_topk_carried(const uint32_t *d_post_off, const void *d_postings, const double *d_img_rnorm,
+                                     int64_t n_img, int64_t n_ref, const int64_t *d_q_off, const int32_t *d_q_node,
+                                     const float *d_q_val, int64_t n_query, int topk, const double *d_shard_rmax,
+                                     const int32_t *d_seed, int64_t seed_stride, int n_groups, double *d_group_key,
+                                     int32_t *d_group_id, void *stream)
+{
+    VT_CHECK_ARG(n_img > 0 && n_ref > 0 && n_query >= 0 && d_img_rnorm, "bad arguments");
+    VT_CHECK_ARG(topk >= 1 && topk <= SQ_MAXK, "topk out of range");
+    VT_CHECK_ARG((d_seed != nullptr) != (d_shard_rmax != nullptr), "pass either the seed rows (all-nodes) or the shard bounds (leaf words)");
+    VT_CHECK_ARG(d_seed == nullptr || seed_stride >= n_img, "seed rows shorter than the image count");
+    const int n_shards = (int)((n_img + SQ_R - 1) / SQ_R);
+    VT_CHECK_ARG(n_groups >= 1 && n_groups <= n_shards, "n_groups out of range");
+    if (n_query == 0) return VT_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint32_t *po = (const uint32_t *)d_postings;
+    if (d_seed)
+        return launch_query<true>(d_post_off, po, d_img_rnorm, n_img, n_shards, d_q_off, d_q_node, d_q_val, n_query, topk, nullptr,
+                                  d_seed, seed_stride, n_groups, d_group_key, d_group_id, s);
+    return launch_query<false>(d_post_off, po, d_img_rnorm, n_img, n_shards, d_q_off, d_q_node, d_q_val, n_query, topk, d_shard_rmax,
+                               nullptr, 0, n_groups, d_group_key, d_group_id, s);
+}

@@ -643,7 +643,8 @@ def build_index(csr: dict, n_ref: int) -> dict:
     lens = (post_off[1:] - post_off[:-1]).to(torch.float64)
     long_lists = bool(nnz > 0 and float((lens * lens).sum().item()) / float(nnz) > 64.0)
     return dict(post_off=post_off, postings=postings[:nnz], rnorm=rnorm[:n_img], sumsq=csr["sumsq"], n_img=n_img,
-                shard_empty=shard_empty, shard_rho=shard_rho, long_lists=long_lists,
+                shard_empty=shard_empty, shard_rho=shard_rho, shard_rmax=hi.clamp(min=0.0).contiguous(),
+                long_lists=long_lists,
                 n_ref=n_ref, shard=shard, n_shards=n_shards, nnz=nnz)
 
 
@@ -719,7 +720,8 @@ class DenseTopBuilder:
 
 
 @_device_scoped
-def score_dense(dense: dict, q: dict, topk: int, want_all: bool = False, d_budget_bytes: int = 4 << 30) -> dict:
+def score_dense(dense: dict, q: dict, topk: int, want_all: bool = False, d_budget_bytes: int = 4 << 30,
+                groups: int = None) -> dict:
     """All-nodes tf scoring with the dense top: per chunk of queries ONE tcgen05 INT8 GEMM gives the int32 dots over
     levels 0..Ld (``vt_dense_dots``), the posting scorer starts its accumulators from them and adds the deep levels
     (``vt_score_topk_seeded``).  Same outputs as ``score`` (exact integer dots, binary64 keys)."""
@@ -759,6 +761,19 @@ def score_dense(dense: dict, q: dict, topk: int, want_all: bool = False, d_budge
             extra(seed, c0, c1)
         off = (qs["row_off"][c0:c1 + 1] - qs["row_off"][c0]).contiguous()
         b = int(qs["row_off"][c0].item())
+        if not want_all:
+            # the top-k carried from shard to shard (vt_score_query.cu): a few lists per query instead of one per shard
+            n_groups = int(groups or lib.vt_score_group_count(c1 - c0, n_img))
+            shard_key = torch.empty((c1 - c0, n_groups, topk), dtype=torch.float64, device=dev)
+            shard_id = torch.empty((c1 - c0, n_groups, topk), dtype=torch.int32, device=dev)
+            nat.check(lib.vt_score_topk_carried(nat.ptr(index["post_off"]), nat.ptr(index["postings"]), nat.ptr(index["rnorm"]),
+                                                n_img, index["n_ref"], nat.ptr(off), nat.ptr(qs["node"][b:]), nat.ptr(q_val[b:]),
+                                                c1 - c0, topk, None, nat.ptr(seed), np_, n_groups, nat.ptr(shard_key),
+                                                nat.ptr(shard_id), s), "vt_score_topk_carried")
+            m = merge_topk(shard_key.view(c1 - c0, -1), shard_id.view(c1 - c0, -1), c1 - c0, topk, nat.SCORE_TF_L2,
+                           q["sumsq"][c0:c1].contiguous(), index["sumsq"])
+            key[c0:c1], ids[c0:c1], sc[c0:c1] = m["key"], m["id"], m["score"]
+            continue
         shard_key = torch.empty((c1 - c0, n_shards, topk), dtype=torch.float64, device=dev)
         shard_id = torch.empty((c1 - c0, n_shards, topk), dtype=torch.int32, device=dev)
         nat.check(lib.vt_score_topk_seeded(nat.ptr(index["post_off"]), nat.ptr(index["postings"]), nat.ptr(index["rnorm"]),
@@ -789,11 +804,12 @@ def _dense_query_overflow(q: dict, layout: dict, block: torch.Tensor):
 # --------------------------------------------------------------------------------------- score
 @_device_scoped
 def score(index: dict, q: dict, topk: int, mode: int = nat.SCORE_TF_L2, q_val: torch.Tensor = None,
-          want_all: bool = False, merge: bool = True, weights: dict = None) -> dict:
+          want_all: bool = False, merge: bool = True, weights: dict = None, groups: int = None) -> dict:
     """Score a CSR batch of queries against the inverted file and select the top-k per query.
 
     Returns dict(key [Q, topk] f64, id [Q, topk] i32, score [Q, topk] f64, all_key [Q, n_img] | None,
-    shard_key/shard_id when ``merge`` is False)."""
+    shard_key/shard_id when ``merge`` is False).  ``groups``: lists per query of the carried-top-k scorer (default: what
+    ``vt_score_group_count`` proposes for the batch; 1 = one CTA takes a query through every shard)."""
     lib = _lib()
     dev = index["post_off"].device
     s = nat.stream_ptr()
@@ -823,6 +839,19 @@ def score(index: dict, q: dict, topk: int, mode: int = nat.SCORE_TF_L2, q_val: t
         return out
     if q_val is None:
         q_val = q["count"].to(torch.float32)
+    if not want_all and nq > 0 and index.get("shard_rmax") is not None:
+        # the top-k carried from shard to shard (vt_score_query.cu): ``shard_key`` / ``shard_id`` are then per GROUP of shards
+        n_groups = int(groups or lib.vt_score_group_count(nq, n_img))
+        shard_key = torch.empty((nq, n_groups, topk), dtype=torch.float64, device=dev)
+        shard_id = torch.empty((nq, n_groups, topk), dtype=torch.int32, device=dev)
+        nat.check(lib.vt_score_topk_carried(nat.ptr(index["post_off"]), nat.ptr(index["postings"]), nat.ptr(index["rnorm"]),
+                                            n_img, index["n_ref"], nat.ptr(q["row_off"]), nat.ptr(q["node"]), nat.ptr(q_val),
+                                            nq, topk, nat.ptr(index["shard_rmax"]), None, 0, n_groups, nat.ptr(shard_key),
+                                            nat.ptr(shard_id), s), "vt_score_topk_carried")
+        out = dict(all_key=None, shard_key=shard_key, shard_id=shard_id, topk=topk)
+        if merge:
+            out.update(merge_topk(shard_key.view(nq, -1), shard_id.view(nq, -1), nq, topk, mode, q["sumsq"], index["sumsq"]))
+        return out
     nat.check(lib.vt_score_topk(nat.ptr(index["post_off"]), nat.ptr(index["postings"]), nat.ptr(index["rnorm"]),
                                 n_img, index["n_ref"], nat.ptr(q["row_off"]), nat.ptr(q["node"]), nat.ptr(q_val),
                                 nq, mode, topk, nat.ptr(shard_key), nat.ptr(shard_id), nat.ptr(all_key),

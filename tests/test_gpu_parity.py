@@ -461,6 +461,58 @@ def test_score_multi_shard_random_csr(vt, cuda):
         assert ids[qi][0] == qr and sc[qi][0] == 0.0            # self match first, exactly zero
 
 
+@pytest.mark.parametrize("groups", [1, 2, 5])
+def test_carried_topk_equals_exhaustive_selection(vt, cuda, groups):
+    """vt_score_query.cu: a CTA carries the k best of a query from shard to shard and prunes with their worst key.  40 k
+    images (5 shards) with planted duplicates (exact key ties across shards, broken by the smaller image index like
+    database.py:79-80), images without words, queries with no match at all, long and short posting runs; every grouping
+    of the shards must return the order the full key dump gives."""
+    torch = _torch()
+    import scipy.sparse as sp
+    rng = np.random.default_rng(21 + groups)
+    n_img, n_ref, nnz_per = 40_000, 3000, 30
+    rows = np.repeat(np.arange(n_img), nnz_per)
+    cols = rng.integers(0, n_ref, n_img * nnz_per)
+    cols[rng.random(len(cols)) < 0.2] = 7                       # one very frequent word: runs of thousands of postings
+    m = sp.coo_matrix((rng.integers(1, 4, len(rows)).astype(np.int64), (rows, cols)), shape=(n_img, n_ref)).tolil()
+    dup_src = [11, 9000, 17000, 30000]
+    for j, src in enumerate(dup_src):                           # copies of an image in other shards: equal keys
+        for dst in ((src + 8192 * (1 + j % 2) + 3) % n_img, (src + 20011) % n_img):
+            m[dst] = m[src]
+    for e in (17, 8192, 39999):
+        m[e] = 0
+    m = m.tocsr()
+    m.eliminate_zeros()
+    m.sort_indices()
+
+    def to_csr(mat):
+        return dict(row_off=torch.from_numpy(mat.indptr.astype(np.int64)).to(cuda),
+                    node=torch.from_numpy(mat.indices.astype(np.int32)).to(cuda),
+                    count=torch.from_numpy(mat.data.astype(np.int32)).to(cuda),
+                    sumsq=torch.from_numpy(np.asarray(mat.multiply(mat).sum(1)).ravel().astype(np.int64)).to(cuda),
+                    n_img=mat.shape[0], nnz=mat.nnz)
+    index = vt.engine.build_index(to_csr(m), n_ref)
+    assert index["n_shards"] == 5
+    q_rows = np.concatenate([dup_src, [0, 17, 8191, 8193, 25000, 39998], rng.integers(0, n_img, 54)])
+    mq = m[q_rows].tolil()
+    mq[5] = 0
+    mq[5, n_ref - 1] = 2                                        # a query whose only word is (almost surely) rare
+    mq = mq.tocsr()
+    q = to_csr(mq)
+    k = 12
+    full = vt.engine.score(index, q, k, want_all=True)
+    allk = full["all_key"].cpu().numpy()
+    got = vt.engine.score(index, q, k, groups=groups)
+    ids, key, sc = got["id"].cpu().numpy(), got["key"].cpu().numpy(), got["score"].cpu().numpy()
+    for qi in range(len(q_rows)):
+        order = np.lexsort((np.arange(n_img), -allk[qi]))[:k]
+        assert np.array_equal(ids[qi], order), (groups, qi, ids[qi], order)
+        assert np.array_equal(key[qi], allk[qi][order])
+    assert np.array_equal(ids, full["id"].cpu().numpy()) and np.array_equal(sc, full["score"].cpu().numpy())
+    for j, src in enumerate(dup_src):                           # the copies tie with the original, smaller index first
+        assert sc[j][0] == 0.0 and sc[j][1] == 0.0 and sc[j][2] == 0.0 and list(ids[j][:3]) == sorted(ids[j][:3])
+
+
 @pytest.mark.parametrize("norm", ["l2", "l1"])
 def test_tfidf_modes_against_dense_oracle(vt, cuda, norm):
     ft, g, meta, images = _flat_from_golden(vt, "orb")

@@ -253,7 +253,7 @@ def test_dense_top_equals_plain_postings(vt, cuda, k, depth):
     rng = np.random.default_rng(k * 10 + depth)
     ft, cent = _full_tree(vt, cuda, k, depth, 32, seed=3)
     voc = vt.encoders.VocabularyTree(k, depth, descriptor=lambda im: im, all_nodes=True, device=cuda).set_tree(ft)
-    n_img = 9000 if k == 4 else 700                                  # 9000 images: two shards of 8192
+    n_img = 17000 if k == 4 else 700                                 # 17000 images: three shards of 8192
     sizes = rng.integers(5, 60, n_img)
     sizes[13] = 0
     sizes[n_img - 1] = 0
@@ -278,6 +278,11 @@ def test_dense_top_equals_plain_postings(vt, cuda, k, depth):
     # small query budget: several GEMM chunks
     c = vt.engine.score_dense(dense, q, 10, want_all=True, d_budget_bytes=1)
     assert torch.equal(a["id"], c["id"]) and torch.equal(a["all_key"], c["all_key"])
+    # the top-k carried from shard to shard (vt_score_query.cu), seeded with the GEMM dots or over the plain postings:
+    # one CTA per query over all shards, one list per shard, and the default grouping
+    for groups in (1, None, plain["n_shards"]):
+        for got in (vt.engine.score_dense(dense, q, 10, groups=groups), vt.engine.score(plain, q, 10, groups=groups)):
+            assert torch.equal(a["id"], got["id"]) and torch.equal(a["key"], got["key"]) and torch.equal(a["score"], got["score"])
 
 
 def test_dense_top_falls_back_when_a_database_count_overflows(vt, cuda):
