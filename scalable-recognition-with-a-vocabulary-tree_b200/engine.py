@@ -492,8 +492,10 @@ def encode(words: torch.Tensor, img_off: torch.Tensor, tree_dev: dict, depth: in
     sizes = img_off[1:] - img_off[:-1]
     max_words = int(sizes.max().item()) if n_img > 0 else 0
     if max_words > lib.vt_encode_max_words():
-        raise ValueError("an image has %d descriptors; vt_encode handles at most %d per image"
-                         % (max_words, lib.vt_encode_max_words()))
+        # the reference has no limit (vocabulary.py:78-102); one CTA sorts at most vt_encode_max_words() words in shared
+        # memory, so larger images are encoded in pieces whose rows are then merged (counts are additive)
+        return _encode_in_pieces(words, img_off, tree_dev, depth, n_ref, all_nodes, want_df, min_level,
+                                 int(lib.vt_encode_max_words()))
     nnz = torch.zeros(max(n_img, 1), dtype=torch.int32, device=dev)
     if not 0 <= min_level <= depth:
         raise ValueError("min_level must lie in [0, depth]")
@@ -527,6 +529,46 @@ def encode(words: torch.Tensor, img_off: torch.Tensor, tree_dev: dict, depth: in
                                 nat.ptr(df), s), "vt_encode(fill)")
     return dict(row_off=row_off, node=node[:total], count=count[:total], sumsq=sumsq[:n_img], df=df,
                 n_img=n_img, nnz=total)
+
+
+def _encode_in_pieces(words, img_off, tree_dev, depth, n_ref, all_nodes, want_df, min_level, limit) -> dict:
+    """``encode`` for batches holding images with more than ``limit`` descriptors: every image is cut into pieces of at most
+    ``limit`` words, the pieces are encoded as rows of their own and the rows of an image are merged on the device (sort by
+    (image, emission order, node), add the counts of equal nodes).  Rows come out in the order ``vt_encode`` emits them."""
+    dev = words.device
+    n_img = img_off.numel() - 1
+    off = img_off.cpu().numpy()
+    piece_off, piece_img = [0], []
+    for i in range(n_img):
+        b, e = int(off[i]), int(off[i + 1])
+        for c in range(b, e, limit):
+            piece_off.append(min(c + limit, e))
+            piece_img.append(i)
+        if e == b:
+            piece_off.append(e)
+            piece_img.append(i)
+    sub = encode(words, torch.tensor(piece_off, dtype=torch.int64, device=dev), tree_dev, depth, n_ref, all_nodes=all_nodes,
+                 want_df=False, min_level=min_level)
+    p_img = torch.tensor(piece_img, dtype=torch.int64, device=dev)
+    lens = sub["row_off"][1:] - sub["row_off"][:-1]
+    img = torch.repeat_interleave(p_img, lens)
+    node = sub["node"].to(torch.int64)
+    if all_nodes:       # vt_encode emits the deepest level first, ids ascending inside a level
+        rank = depth - tree_dev["level_ref"].to(torch.int64)[node]
+        key = (img * (depth + 1) + rank) * n_ref + node
+    else:
+        key = img * n_ref + node
+    key, order = torch.sort(key, stable=True)
+    uniq, inverse = torch.unique_consecutive(key, return_inverse=True)
+    count = torch.zeros(uniq.numel(), dtype=torch.int64, device=dev).index_add_(0, inverse, sub["count"].to(torch.int64)[order])
+    out_node = (uniq % n_ref).to(torch.int32)
+    out_img = uniq // (n_ref * (depth + 1)) if all_nodes else uniq // n_ref
+    row_off = torch.zeros(n_img + 1, dtype=torch.int64, device=dev)
+    row_off[1:] = torch.cumsum(torch.bincount(out_img, minlength=n_img)[:n_img], 0)
+    sumsq = torch.zeros(max(n_img, 1), dtype=torch.int64, device=dev).index_add_(0, out_img, count * count)
+    df = torch.bincount(out_node.to(torch.int64), minlength=n_ref)[:n_ref].to(torch.int32) if want_df else None
+    total = int(uniq.numel())
+    return dict(row_off=row_off, node=out_node, count=count.to(torch.int32), sumsq=sumsq[:n_img], df=df, n_img=n_img, nnz=total)
 
 
 def concat_csr(parts: list) -> dict:

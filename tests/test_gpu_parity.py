@@ -358,8 +358,12 @@ def test_encode_large_images(vt, cuda):
         dense = csr_to_dense(*(csr[k_].cpu().numpy() for k_ in ("row_off", "node", "count")), ft.n_ref)
         want = np.stack([vo.path_counts(ot, im, all_nodes=all_nodes) for im in imgs])
         assert np.array_equal(dense, want)
-    with pytest.raises(ValueError):
-        voc.encode_batch([pool[rng.integers(0, len(pool), 8193)]])
+    # beyond the per-CTA capacity: encoded in pieces and merged (the reference has no limit, vocabulary.py:78-102)
+    big = [pool[rng.integers(0, len(pool), n)] for n in (8193, 7, 30000)]
+    for all_nodes in (True, False):
+        csr = voc.encode_batch(big, all_nodes=all_nodes)
+        dense = csr_to_dense(*(csr[k_].cpu().numpy() for k_ in ("row_off", "node", "count")), ft.n_ref)
+        assert np.array_equal(dense, np.stack([vo.path_counts(ot, im, all_nodes=all_nodes) for im in big]))
 
 
 # ------------------------------------------------------------------------------------------ index + score

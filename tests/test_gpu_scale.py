@@ -319,3 +319,47 @@ def test_two_levels_per_launch_at_scale_equals_one_level_per_launch(vt, cuda):
     finally:
         lib.vt_quantize_mma_pair_min(prev if prev < (1 << 62) else -1)
     assert torch.equal(a, b) and torch.equal(a[:3_000_001], c)
+
+
+@pytest.mark.parametrize("all_nodes", [False, True])
+def test_images_with_more_descriptors_than_one_cta_sorts(vt, cuda, all_nodes):
+    """The reference puts no limit on the descriptors of an image (vocabulary.py:78-102); vt_encode sorts at most 8192
+    words per CTA, larger images are encoded in pieces and merged.  20,000- and 8,193-descriptor images between ordinary
+    and empty ones: counts against a numpy restatement (every node on the path counts once per descriptor), rows in
+    vt_encode's order, and the big image retrieves itself with score 0."""
+    torch = _torch()
+    k, depth = 4, 5
+    ft, cent = _full_tree(vt, cuda, k, depth, 32, seed=5)
+    voc = vt.encoders.VocabularyTree(k, depth, descriptor=lambda im: im, all_nodes=all_nodes, device=cuda).set_tree(ft)
+    sizes = [30, 20000, 0, 8193, 55, 8192]
+    x = vt.synth.descriptors_from_tree(cent, k, depth, sum(sizes), seed=11).cpu().numpy()[:, :32]
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    images = [x[offs[i]:offs[i + 1]] for i in range(len(sizes))]
+    csr = voc.encode_batch(images, want_df=True)
+    tdev = ft.device(cuda)
+    words = vt.engine.quantize(tdev, k, depth, torch.from_numpy(x).to(cuda)).cpu().numpy()
+    parent, level = tdev["parent_ref"].cpu().numpy(), tdev["level_ref"].cpu().numpy()
+    ro, node, cnt = csr["row_off"].cpu().numpy(), csr["node"].cpu().numpy(), csr["count"].cpu().numpy()
+    df = np.zeros(ft.n_ref, np.int64)
+    for i in range(len(sizes)):
+        want = np.zeros(ft.n_ref, np.int64)
+        w = words[offs[i]:offs[i + 1]].copy()
+        np.add.at(want, w, 1)
+        while all_nodes and len(w) and (level[w] > 0).any():
+            w = parent[w[level[w] > 0]]
+            np.add.at(want, w, 1)
+        got = np.zeros(ft.n_ref, np.int64)
+        got[node[ro[i]:ro[i + 1]]] = cnt[ro[i]:ro[i + 1]]
+        assert np.array_equal(got, want), i
+        assert len(np.unique(node[ro[i]:ro[i + 1]])) == ro[i + 1] - ro[i]                  # one entry per node
+        assert int(csr["sumsq"][i]) == int((want * want).sum())
+        df += want > 0
+        small = voc.encode_batch([images[i]])                                              # the row order vt_encode emits
+        if sizes[i] <= 8192:
+            assert np.array_equal(small["node"].cpu().numpy(), node[ro[i]:ro[i + 1]])
+    assert np.array_equal(csr["df"].cpu().numpy(), df)
+    ds = vt.ArrayDataset(images)
+    db = vt.Database(ds, voc)
+    db.index()
+    ids, sc = db.retrieve_batch([ds.image_paths[1], ds.image_paths[3]], k=2)
+    assert ids[0][0] == 1 and sc[0][0] == 0.0 and ids[1][0] == 3 and sc[1][0] == 0.0

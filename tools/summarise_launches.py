@@ -49,7 +49,7 @@ def main():
             lvl_ms += ms
         g = by_name.setdefault(name[:60], [0, 0.0, 0.0])
         g[0], g[1], g[2] = g[0] + 1, g[1] + ms, g[2] + rd + wr
-        if "score_shard" in name:
+        if "score_shard" in name or "score_query" in name:
             sc_bytes += rd + wr
             sc_ms += ms
         out.append("%3d %-40s %8.3f ms  DRAM read %8.3f GB  write %7.3f GB  (%.2f TB/s)"
@@ -67,7 +67,7 @@ def main():
         out.append("scorer launches: %.3f ms, %.2f GB of DRAM traffic over %d queries = %.2f MB per query"
                    % (sc_ms, sc_bytes / 1e9, queries, sc_bytes / queries / 1e6))
         j = {"dram_bytes_per_query": sc_bytes / queries, "queries": queries,
-             "source": "ncu launch list %s (dram__bytes_read.sum + dram__bytes_write.sum of the score_shard* launches, %d queries)"
+             "source": "ncu launch list %s (dram__bytes_read.sum + dram__bytes_write.sum of the scorer launches, %d queries)"
                        % (os.path.basename(dst), queries)}
         json.dump(j, open(os.path.join(os.path.dirname(dst), "r02_scorer_traffic.json"), "w"), indent=1)
     open(dst, "w").write("\n".join(out) + "\n")
