@@ -469,7 +469,12 @@ def main():
                            "hbm_bound_descriptors_per_s": hbm_peak * 1e9 / alg_bytes},
             "traffic": traffic,
             "traffic_source": traffic_src,
-            "level_kernel_ms_note": "one entry per level; entry 0 includes the per-call plane preparation of the profile variant, the last entry the deferred output (bucket pass + id write)",
+            # the same launches against what ONE level has to move (128 B row gather + 8 B key/permutation in + 8 B out,
+            # 136 / 144 / 140 B on the first / middle / last level): how close a single launch is to HBM speed
+            "per_level_launch": {"bytes_per_descriptor_level": 140.0,
+                                 "achieved": 140.0 * per_launch * n_stages / (lvl_total_ms * 1e-3) / 1e9,
+                                 "frac": 140.0 * per_launch * n_stages / (lvl_total_ms * 1e-3) / 1e9 / hbm_peak},
+            "level_kernel_ms_note": "CUDA events around each level_mma_kernel launch alone; resort_ms = the regrouping pass after each level, its last entry the deferred output of the last level (bucket pass + id write); the per-call plane preparation is in step_ms only",
             "other_engine": dict(fill(other_r, other_total_ms), level_kernel_ms=[round(float(v), 3) for v in other_ms]),
             "fused_single_launch_descent": {"value": fused_rate, "unit": "descriptors/s", "rows": n_f},
             "fp32_input": fp32_in,

@@ -813,6 +813,7 @@ int vt_mma_levels(const void *d_desc, int64_t n, const float *cent, const uint8_
                                                                   perm_out, leaf, word, (unsigned long long *)stats);
         VT_LAUNCH_CHECK();
         if (last && defer) {
+            VT_MARK();                                           // (the deferred output is timed as the last "regrouping" stage)
             // (row, child) pairs -> 256 buckets of consecutive rows -> ids written bucket by bucket
             uint32_t *ok = level == 0 ? tkeys : keys, *op = level == 0 ? tperm : perm;
             int nb = 0;
@@ -847,9 +848,9 @@ int vt_quantize_mma_impl(const void *d_desc, int64_t n, const float *cent, const
                          cudaEvent_t *ev, int *n_ev_out = nullptr)
 {
     int n_ev = 0;
-    if (ev) VT_CUDA(cudaEventRecord(ev[n_ev++], s));           // the first stage includes the plane preparation
     int rc = vt_mma_prepare(cent, k, depth, work, stats, s);
     if (rc != VT_OK) return rc;
+    if (ev) VT_CUDA(cudaEventRecord(ev[n_ev++], s));           // stages start after the plane preparation
     rc = vt_mma_levels(d_desc, n, cent, internal, ref_id, k, depth, leaf, word, stats, work,
                        (uint8_t *)work + vt_mma_prepared_bytes(k, depth), s, ev, &n_ev);
     if (n_ev_out) *n_ev_out = n_ev;
@@ -874,7 +875,7 @@ extern "C" int vt_quantize_mma(const void *d_desc, int dtype, int64_t n, int dp,
                                 (cudaStream_t)stream, nullptr);
 }
 
-// measurement variant: h_level_ms[depth] (level kernels; entry 0 includes the plane preparation),
+// measurement variant: h_level_ms[depth] (the level kernel launches alone; the per-call plane preparation is not timed),
 // h_sort_ms[depth] (re-sorts)
 extern "C" int vt_quantize_mma_profile(const void *d_desc, int dtype, int64_t n, int dp, const float *d_centroids,
                                        const uint8_t *d_internal, const int32_t *d_ref_id, int k, int depth,
@@ -885,7 +886,7 @@ extern "C" int vt_quantize_mma_profile(const void *d_desc, int dtype, int64_t n,
     VT_CHECK_ARG(d_work && work_bytes >= vt_quantize_mma_work_bytes(n, k, depth), "workspace too small");
     VT_CHECK_ARG(h_level_ms && h_sort_ms, "null output");
     cudaEvent_t ev[40];
-    const int n_ev = 2 * depth;
+    const int n_ev = 2 * depth + 1;
     for (int i = 0; i < n_ev; ++i) VT_CUDA(cudaEventCreate(&ev[i]));
     int n_used = 0;
     int rc = vt_quantize_mma_impl(d_desc, n, d_centroids, d_internal, d_ref_id, k, depth, d_leaf_heap, d_word, d_stats,

@@ -126,14 +126,29 @@ class VocabularyTree(object):
 
     def fit(self, features, node=0, root=None, current_depth=0):
         """Hierarchical k-means over ``features`` [N, D] (vocabulary.py:36-76), all nodes of a
-        level per launch.  Only whole-tree builds (node=0) are offered."""
-        if node != 0 or root is not None or current_depth != 0:
-            raise NotImplementedError("only whole-tree builds (node=0) are supported")
+        level per launch.  The reference's recursion arguments are honoured where they make sense for a call from
+        outside: ``root`` replaces the stored value of node 0 (vocabulary.py:48-51; the descent never compares with
+        it) and ``current_depth`` = c builds the ``depth - c`` levels the reference's recursion would still add below a
+        node at that depth (vocabulary.py:55).  ``node != 0`` would graft a subtree into the reference's running
+        ``_current_index`` numbering of a half-built tree -- state the level-synchronous build does not have."""
+        if node != 0:
+            raise NotImplementedError("fit(node != 0): grafting below an existing node needs the reference's recursive "
+                                      "numbering state; build the whole tree with node=0")
+        levels = self.depth - int(current_depth)
+        if current_depth < 0 or levels < 1:
+            raise NotImplementedError("fit(current_depth >= depth) leaves a one-node tree; nothing to build")
         features = np.asarray(features) if not hasattr(features, "device") else features
         desc, d = engine.stage(features, self.device, prefer_bytes=True)
         self.build_log = []
-        self._flat = engine.build_tree(desc, d, self.n_branches, self.depth, n_iter=self.n_iter, comm=self.comm,
+        self._flat = engine.build_tree(desc, d, self.n_branches, levels, n_iter=self.n_iter, comm=self.comm,
                                        log=lambda **kw: self.build_log.append(kw))
+        if root is not None:
+            import torch
+            r = torch.as_tensor(np.asarray(root, dtype=np.float32).reshape(-1)[:d])
+            cent = self._flat.device(self.device)["centroids"]
+            cent[0, :d] = r.to(cent.device)
+            if getattr(self._flat, "_centroids", None) is not None:
+                self._flat._centroids[0, :d] = r.numpy()
         self._views = {}
         self._propagated = {}
         return self

@@ -924,3 +924,23 @@ def test_notebook_cells_78_to_91_with_real_images(vt, cuda, tmp_path):
     assert db2.load(str(store))
     for name in dataset.image_paths[:4]:
         assert [p for p in db2.retrieve(name)] == order[name]
+
+
+def test_fit_recursion_arguments(vt, cuda):
+    """vocabulary.py:36: fit(features, node, root, current_depth).  root replaces the stored value of node 0, current_depth
+    = c builds the depth - c levels the recursion would still add; node != 0 is refused with an explanation."""
+    rng = np.random.default_rng(4)
+    x = rng.integers(0, 256, (6000, 128), dtype=np.uint8)
+    full = vt.encoders.VocabularyTree(3, 2, descriptor=lambda im: im).fit(x)
+    root = np.full(128, 7.5, np.float32)
+    part = vt.encoders.VocabularyTree(3, 3, descriptor=lambda im: im).fit(x, node=0, root=root, current_depth=1)
+    assert part.flat.depth == 2 and part.flat.n_ref == full.flat.n_ref
+    a, b = full.flat.nodes_dict(), part.flat.nodes_dict()
+    assert np.array_equal(b[0], root) and not np.array_equal(a[0], root)
+    assert all(np.array_equal(a[i], b[i]) for i in range(1, full.flat.n_ref))
+    img = x[:500]
+    assert np.array_equal(full.embedding(img), part.embedding(img))
+    with pytest.raises(NotImplementedError):
+        vt.encoders.VocabularyTree(3, 2, descriptor=lambda im: im).fit(x, node=4)
+    with pytest.raises(NotImplementedError):
+        vt.encoders.VocabularyTree(3, 2, descriptor=lambda im: im).fit(x, current_depth=2)
