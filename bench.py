@@ -624,6 +624,14 @@ def bench_retrieval(args, torch, vt, engine, nat, dev, rank, world, comm, cent, 
 
     for _ in range(2):
         h_ids, h_sc = e2e_pass()
+    if os.environ.get("VT_BENCH_PROFILE_E2E"):             # developer switch: where the host time of one pass goes
+        import cProfile
+        import pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        e2e_pass()
+        pr.disable()
+        pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(28)
     barrier()
     t0 = time.perf_counter()
     for _ in range(steps):

@@ -47,6 +47,11 @@ const char *vt_last_error(void);
 /* sm_count, cc_major, cc_minor of the current device; fails when no sm_100 device is present */
 int vt_device_info(int *sm_count, int *cc_major, int *cc_minor);
 
+/* ---- host staging (Database.index / retrieve_batch: the descriptor arrays of a batch of images, database.py:36-44,
+ * are separate host arrays; the upload wants them back to back in pinned memory).  Copies h_src[i] (h_bytes[i] bytes)
+ * one after another into h_dst with n_threads memcpy threads.  Host pointers only; no device is touched. */
+int vt_host_pack(const void *const *h_src, const int64_t *h_bytes, int64_t n, void *h_dst, int n_threads);
+
 /* ---- descriptor staging (input side of vocabulary.py:29-34 extract_features) ------------- */
 /* float32 [n, d] -> bytes [n, dp] zero padded.  *d_flag (device int, caller zeroes it) is set
  * to 1 when some value is not an integer in 0..255 (the conversion would be lossy). */

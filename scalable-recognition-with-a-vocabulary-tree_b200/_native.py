@@ -22,6 +22,7 @@ SIGNATURES = {
     "vt_abi_version": (_int, []),
     "vt_last_error": (C.c_char_p, []),
     "vt_device_info": (_int, [C.POINTER(_int)] * 3),
+    "vt_host_pack": (_int, [_vp, _vp, _i64, _vp, _int]),
     "vt_stage_f32_to_u8": (_int, [_vp, _i64, _int, _vp, _int, _vp, _vp]),
     "vt_stage_pad": (_int, [_vp, _i64, _int, _vp, _int, _int, _vp]),
     "vt_quantize": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _int, _int, _i32, _vp, _vp, _vp, _vp]),

@@ -267,7 +267,7 @@ class Database(object):
         return score if not np.isnan(score) else 1e6
 
     # ------------------------------------------------------------------ retrieval
-    def _query_csr(self, query_paths):
+    def _query_csr(self, query_paths, prestaged=None):
         """CSR batch (device) for a list of image paths, plus the permutation that puts the rows back into query
         order.  Images indexed on this rank reuse their rows (gathered on the device); all others are encoded in
         ONE batch (pinned staging, like ``index``)."""
@@ -284,6 +284,13 @@ class Database(object):
             for qi, p in fresh:
                 uniq.setdefault(p, []).append(qi)
             missing = [p for p in uniq if p not in self._extra_csr]
+            if prestaged is not None and prestaged[0]:
+                # packed by the loader thread of ``_retrieve_batch_pipelined`` (a superset of what is still missing)
+                staged_paths, staged = prestaged
+                csr = self.encoder.encode_batch(None, staged=staged)
+                for j, p in enumerate(staged_paths):
+                    self._extra_csr[p] = (csr, j)
+                missing = [p for p in uniq if p not in self._extra_csr]
             if missing:
                 staged = self._load_batch(missing, 0)
                 csr = self.encoder.encode_batch(None, staged=staged)
@@ -348,18 +355,61 @@ class Database(object):
         if self._csr is None:
             self.index()
         query_paths = list(query_paths)
+        if not return_all and len(query_paths) > 2 * self.query_chunk:
+            return self._retrieve_batch_pipelined(query_paths, k)
         q, back = self._query_csr(query_paths)
-        if self.comm is None:
-            out = self._score_local(q, k, return_all)
-            ids_t, sc_t = out["id"], out["score"]
-        else:
-            from . import dist as vdist
-            out = self._score_local(q, k, return_all)
-            ids_t, sc_t, _ = vdist.retrieve_sharded(lambda: out, self._img_base, k, self.comm)
+        ids_t, sc_t, out = self._score_global(q, k, return_all)
         ids, sc = ids_t.cpu().numpy()[back], sc_t.cpu().numpy()[back]
         if return_all:
             return ids, sc, self._all_keys_global(out["all_key"]).cpu().numpy()[back]
         return ids, sc
+
+    def _score_global(self, q, k, return_all=False):
+        out = self._score_local(q, k, return_all)
+        if self.comm is None:
+            return out["id"], out["score"], out
+        from . import dist as vdist
+        ids_t, sc_t, _ = vdist.retrieve_sharded(lambda: out, self._img_base, k, self.comm)
+        return ids_t, sc_t, out
+
+    query_chunk = 2048      # queries per pipeline stage of a large ``retrieve_batch``
+
+    def _retrieve_batch_pipelined(self, query_paths, k):
+        """Large query batches go through in chunks: a loader thread reads, describes and packs the images of chunk c+1
+        into pinned memory (``_load_batch``, alternating staging slots) while the device uploads, quantises, encodes and
+        scores chunk c -- the host packing, not the device, is what a one-shot batch waits for.  Same results, chunk by
+        chunk; the ids and scores stay on the device until the end."""
+        import torch
+        from concurrent.futures import ThreadPoolExecutor
+        step = int(self.query_chunk)
+        chunks = [query_paths[c0:c0 + step] for c0 in range(0, len(query_paths), step)]
+
+        def stage(ci):
+            missing = self._missing(chunks[ci])
+            return missing, (self._load_batch(missing, "q%d" % (ci % 2)) if missing else None)
+
+        ids_parts, sc_parts = [], []
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            pending = pool.submit(stage, 0)
+            for ci in range(len(chunks)):
+                prestaged = pending.result()
+                if ci + 1 < len(chunks):
+                    pending = pool.submit(stage, ci + 1)
+                q, back = self._query_csr(chunks[ci], prestaged=prestaged)
+                ids_t, sc_t, _ = self._score_global(q, k)
+                back_t = torch.from_numpy(back).to(ids_t.device)
+                ids_parts.append(ids_t[back_t])
+                sc_parts.append(sc_t[back_t])
+        return torch.cat(ids_parts).cpu().numpy(), torch.cat(sc_parts).cpu().numpy()
+
+    def _missing(self, query_paths):
+        """query images that are neither indexed on this rank nor encoded before (in first-seen order)"""
+        seen, out = set(), []
+        for p in query_paths:
+            if p not in self._rows and p not in self._extra_csr and p not in seen:
+                seen.add(p)
+                out.append(p)
+        return out
 
     def _scores_from_keys(self, keys, q_sumsq):
         """rank keys of every image -> reference scores (host, float64)."""

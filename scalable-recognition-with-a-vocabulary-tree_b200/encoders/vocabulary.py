@@ -22,10 +22,8 @@ import numpy as np
 
 from .. import utils
 from .. import engine
+from .. import _native as nat
 from ..tree import FlatTree
-
-
-_POOL = None
 
 
 def _pack_threads() -> int:
@@ -35,15 +33,6 @@ def _pack_threads() -> int:
     except AttributeError:
         n = os.cpu_count() or 1
     return max(1, min(8, n))
-
-
-def _pack_pool():
-    """threads that pack descriptor arrays into the pinned staging buffer (``VocabularyTree.stage_host``)"""
-    global _POOL
-    if _POOL is None:
-        from concurrent.futures import ThreadPoolExecutor
-        _POOL = ThreadPoolExecutor(max_workers=_pack_threads(), thread_name_prefix="vt-pack")
-    return _POOL
 
 
 class VocabularyTree(object):
@@ -208,15 +197,20 @@ class VocabularyTree(object):
                 if sizes[i]:
                     np.copyto(view[offs[i]:offs[i + 1]], arrs[i].reshape(sizes[i], d), casting="unsafe")
 
-        n_thr = _pack_threads() if total * d * buf.element_size() >= (8 << 20) else 1
-        if n_thr <= 1:
-            pack(0, len(arrs))
+        want = np.uint8 if as_bytes else np.float32
+        plain = all(a.dtype == want and a.flags.c_contiguous and (a.ndim == 2 and a.shape[1] == d or a.shape[0] == 0)
+                    for a in arrs)
+        if plain and total * d * buf.element_size() >= (8 << 20):
+            # one memcpy thread moves ~10 GB/s, the upload that follows 55 GB/s: vt_host_pack spreads the copy over native
+            # threads (the call releases the GIL, so a loader thread packing here never stalls the thread driving the GPU)
+            import ctypes as C
+            lib = nat.load()
+            n_arr = len(arrs)
+            src = (C.c_void_p * n_arr)(*[a.__array_interface__["data"][0] for a in arrs])
+            nbytes = (C.c_int64 * n_arr)(*[a.nbytes for a in arrs])
+            nat.check(lib.vt_host_pack(src, nbytes, n_arr, C.c_void_p(buf.data_ptr()), _pack_threads()), "vt_host_pack")
         else:
-            # one memcpy thread moves ~10 GB/s, the upload that follows 55 GB/s: pack with several (numpy releases the GIL
-            # inside the copy); image ranges of about equal bytes
-            cuts = np.searchsorted(offs, np.linspace(0, total, n_thr + 1)[1:-1]).tolist()
-            bounds = [0] + cuts + [len(arrs)]
-            list(_pack_pool().map(lambda ab: pack(*ab), zip(bounds[:-1], bounds[1:])))
+            pack(0, len(arrs))
         return dict(rows=buf[:total], sizes=sizes, slot=slot)
 
     def encode_batch(self, images, want_df=False, all_nodes=None, staged=None):

@@ -944,3 +944,27 @@ def test_fit_recursion_arguments(vt, cuda):
         vt.encoders.VocabularyTree(3, 2, descriptor=lambda im: im).fit(x, node=4)
     with pytest.raises(NotImplementedError):
         vt.encoders.VocabularyTree(3, 2, descriptor=lambda im: im).fit(x, current_depth=2)
+
+
+def test_pipelined_retrieve_batch_equals_one_shot(vt, cuda):
+    """Large query batches are staged chunk by chunk on a loader thread while the device works on the previous chunk
+    (Database._retrieve_batch_pipelined): same ids and scores as the one-shot path, for indexed images, images that are
+    not in the database, repeated queries and an image without descriptors."""
+    ft, g, meta, images = _flat_from_golden(vt, "orb")
+    voc = vt.encoders.VocabularyTree(ft.k, ft.depth, descriptor=lambda im: im).set_tree(ft)
+    rng = np.random.default_rng(2)
+    pool = np.concatenate(images)
+    extra = [pool[rng.integers(0, len(pool), int(n))] for n in rng.integers(1, 300, 25)] + [pool[:0]]
+    ds = vt.ArrayDataset(list(images) + extra)
+    n_db = len(images)
+    db = vt.Database(vt.ArrayDataset(list(images)), voc)
+    db.index()
+    db.dataset = ds                                              # queries may name images beyond the indexed ones
+    order = rng.permutation(len(ds.image_paths)).tolist() + [3, 3, n_db + 1, n_db + 1]
+    paths = [ds.image_paths[i] for i in order]
+    one_ids, one_sc = db.retrieve_batch(paths, k=5)
+    db._extra_csr.clear()
+    db.query_chunk = 7
+    ids, sc = db.retrieve_batch(paths, k=5)
+    assert np.array_equal(ids, one_ids) and np.array_equal(sc, one_sc)
+    assert all(sc[j][0] == 0.0 for j, i in enumerate(order) if i < n_db and len(images[i]))
