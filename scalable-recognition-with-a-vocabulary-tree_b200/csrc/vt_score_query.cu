@@ -37,6 +37,7 @@ constexpr int SQ_WCACHE = 1024;            // query words whose runs are tracked
 constexpr uint32_t SQ_LONG = 64;           // longer runs leave the flat walk
 constexpr int SQ_HEADS = 64;               // 32 words x 64 postings = 2048 flat positions
 constexpr int SQ_U = 4;                    // chunks (posting loads per lane) in flight
+constexpr int SQ_G = 3;                    // long runs walked together
 constexpr uint32_t SQ_LOCAL_MASK = 8191u;  // posting = (tf << 13) | local image index (vt_posting_pack)
 constexpr int SQ_LOCAL_BITS = 13;
 constexpr int SQ_TAKEN = INT_MIN;
@@ -90,9 +91,15 @@ __device__ __forceinline__ void sq_block_best(double &key, int32_t &id, int &own
     __syncthreads();
 }
 
-__device__ __forceinline__ void sq_add(int *acc, uint32_t pe, int tf)
+// acc[local image of the posting] += (tf of the posting) * (tf of the query word), predicated: one `red.shared` under a
+// predicate instead of a branch around an atomic (the compiler wraps every `if (ok) atomicAdd` in BSSY / BRA / BSYNC --
+// a third of the instructions of the walk).  acc_s = shared-window address of the accumulators.
+__device__ __forceinline__ void sq_add(uint32_t acc_s, uint32_t pe, int tf, bool ok)
 {
-    atomicAdd(&acc[pe & SQ_LOCAL_MASK], tf * (int)(pe >> SQ_LOCAL_BITS));
+    const uint32_t addr = (pe & SQ_LOCAL_MASK) * 4u + acc_s;
+    const int val = tf * (int)(pe >> SQ_LOCAL_BITS);
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}"
+                 :: "r"(addr), "r"(val), "r"((uint32_t)ok) : "memory");
 }
 
 // SEEDED: accumulators start from the int32 dots over the dense top levels (vt_dense_dots) and candidates are filtered by
@@ -110,6 +117,7 @@ score_query_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__rest
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t le_mask = (2u << lane) - 1u, lt_mask = (1u << lane) - 1u;
     SqScratch &ws = sh.ws[warp];
+    const uint32_t acc_s = (uint32_t)__cvta_generic_to_shared(sh.acc);
 
     for (int64_t item = blockIdx.x; item < n_query * n_groups; item += gridDim.x) {
         const int64_t q = item / n_groups;
@@ -142,19 +150,43 @@ score_query_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__rest
             auto walk32 = [&](uint32_t b, uint32_t len, int tf) {
                 const bool is_long = len > SQ_LONG;
                 unsigned int m = __ballot_sync(VT_FULL, is_long);
-                while (m) {                                        // long runs: the whole warp, SQ_U x 32 postings in flight
-                    const int src = __ffs(m) - 1;
-                    m &= m - 1;
-                    const uint32_t lb = __shfl_sync(VT_FULL, b, src), lend = lb + __shfl_sync(VT_FULL, len, src);
-                    const int ltf = __shfl_sync(VT_FULL, tf, src);
-                    for (uint32_t p = lb + lane; p < lend; p += 32 * SQ_U) {
-                        uint32_t pe[SQ_U];
+                while (m) {
+                    // long runs: the whole warp walks SQ_G runs together, the first SQ_U x 32 postings of each are loaded
+                    // before any is accumulated (one DRAM round trip per SQ_G runs instead of one per run)
+                    uint32_t lb[SQ_G], lend[SQ_G];
+                    int ltf[SQ_G];
 #pragma unroll
-                        for (int u = 0; u < SQ_U; ++u) pe[u] = p + 32 * u < lend ? __ldg(postings + p + 32 * u) : 0u;
+                    for (int g = 0; g < SQ_G; ++g) {
+                        const int src = m ? __ffs(m) - 1 : 0;
+                        const bool have = m != 0;
+                        m &= m - 1;
+                        lb[g] = __shfl_sync(VT_FULL, b, src);
+                        lend[g] = have ? lb[g] + __shfl_sync(VT_FULL, len, src) : lb[g];
+                        ltf[g] = __shfl_sync(VT_FULL, tf, src);
+                    }
+                    uint32_t pe[SQ_G][SQ_U];
+#pragma unroll
+                    for (int g = 0; g < SQ_G; ++g)
+#pragma unroll
+                        for (int u = 0; u < SQ_U; ++u) {
+                            const uint32_t p = lb[g] + lane + 32 * u;
+                            pe[g][u] = p < lend[g] ? __ldg(postings + p) : 0u;
+                        }
+#pragma unroll
+                    for (int g = 0; g < SQ_G; ++g)
 #pragma unroll
                         for (int u = 0; u < SQ_U; ++u)
-                            if (p + 32 * u < lend) sq_add(sh.acc, pe[u], ltf);
-                    }
+                            sq_add(acc_s, pe[g][u], ltf[g], lb[g] + lane + 32 * u < lend[g]);
+#pragma unroll
+                    for (int g = 0; g < SQ_G; ++g)                 // what is left of runs beyond SQ_U x 32 postings
+                        for (uint32_t p = lb[g] + 32 * SQ_U + lane; p < lend[g]; p += 32 * SQ_U) {
+                            uint32_t pt[SQ_U];
+#pragma unroll
+                            for (int u = 0; u < SQ_U; ++u) pt[u] = p + 32 * u < lend[g] ? __ldg(postings + p + 32 * u) : 0u;
+#pragma unroll
+                            for (int u = 0; u < SQ_U; ++u)
+                                sq_add(acc_s, pt[u], ltf[g], p + 32 * u < lend[g]);
+                        }
                 }
                 if (is_long) len = 0;
                 // flat walk over the concatenated short runs of the 32 words
@@ -198,7 +230,7 @@ score_query_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__rest
                     }
 #pragma unroll
                     for (int u = 0; u < SQ_U; ++u)
-                        if (tv[u]) sq_add(sh.acc, pe[u], tv[u]);
+                        sq_add(acc_s, pe[u], tv[u], tv[u] != 0);
                 }
                 __syncwarp();                                      // the scratch is rewritten by the next 32 words
             };
