@@ -71,7 +71,8 @@ __device__ __forceinline__ bool sq_better(double ka, int32_t ia, double kb, int3
     return ka > kb || (ka == kb && ia < ib);
 }
 
-__device__ __forceinline__ void sq_block_best(double &key, int32_t &id, int &owner, SqShared &sh)
+template <class Shared>
+__device__ __forceinline__ void sq_block_best(double &key, int32_t &id, int &owner, Shared &sh)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     owner = threadIdx.x;
@@ -434,6 +435,357 @@ score_query_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__rest
         __syncthreads();
     }
 }
+
+// ---- NS shards per step, 16-bit accumulators -------------------------------------------------------------------------
+// The kernel above is latency bound: per (query, shard) every warp walks a fixed chain of dependent loads and the CTA
+// passes five barriers.  When every dot of the batch is known to stay below 65535 (Cauchy-Schwarz on the stored squared
+// norms: the caller checks sqrt(max |q|^2 * max |d|^2) < 65535) two accumulators share a 32-bit word, so the SAME shared
+// memory holds NS = 2 (or, at half the occupancy, 4) shards at once: a word's runs in consecutive shards are contiguous
+// in the posting array, so a step walks ONE run of NS times the length per word (fewer, longer requests: 3 sectors per
+// 16 postings instead of 2 x 2), and the barriers, the list maintenance and the pointer bookkeeping are paid once per NS
+// shards.  A posting's shard inside the step follows from its position against the word's run boundaries.
+template <int NS>
+struct Sq16Shared {
+    uint32_t acc[NS * SQ_R / 2];           // image x of the step: half (x & 1) of word x >> 1
+    double ckey[SQ_CAND];
+    int cslot[SQ_CAND];
+    double lkey[SQ_MAXK], nkey[SQ_MAXK];
+    int32_t lid[SQ_MAXK], nid[SQ_MAXK];
+    SqScratch ws[SQ_WARPS];
+    uint32_t wb[SQ_WARPS][NS - 1][32];     // flat positions where the runs of shards 1 .. NS-1 of a word start
+    uint32_t w_run[SQ_WCACHE];
+    uint16_t w_tf[SQ_WCACHE];
+    uint8_t w_len[SQ_SUB][SQ_WCACHE];
+    double r_key[SQ_WARPS];
+    int32_t r_id[SQ_WARPS];
+    int r_owner[SQ_WARPS];
+    int ncand, ln;
+};
+
+// acc16[x] += val (x = image of the step, val < 65536 and the sum stays below 65536): one 32-bit reduction on the word
+__device__ __forceinline__ void sq_add16(uint32_t acc_s, uint32_t x, uint32_t val, bool ok)
+{
+    const uint32_t addr = (x >> 1) * 4u + acc_s;
+    const uint32_t v = val << ((x & 1u) * 16u);
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}"
+                 :: "r"(addr), "r"(v), "r"((uint32_t)ok) : "memory");
+}
+
+template <int NS, int MINB>
+__global__ void __launch_bounds__(SQ_THREADS, MINB)
+score_query16_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__restrict__ postings,
+                     const double *__restrict__ img_rnorm, int64_t n_img, int n_shards, const int64_t *__restrict__ q_off,
+                     const int32_t *__restrict__ q_node, const float *__restrict__ q_val, int64_t n_query, int topk,
+                     const double *__restrict__ shard_rmax, int n_groups, int per_group, double *__restrict__ out_key,
+                     int32_t *__restrict__ out_id)
+{
+    static_assert(NS == 2 || NS == 4, "shards per step");
+    static_assert(SQ_SUB % NS == 0, "a step must not straddle two pointer sub-groups");
+    constexpr int IM = NS * SQ_R, PER = IM / SQ_THREADS;
+    constexpr uint32_t TAKEN16 = 0xffffu;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    Sq16Shared<NS> &sh = *reinterpret_cast<Sq16Shared<NS> *>(s_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t le_mask = (2u << lane) - 1u, lt_mask = (1u << lane) - 1u;
+    SqScratch &ws = sh.ws[warp];
+    const uint32_t acc_s = (uint32_t)__cvta_generic_to_shared(sh.acc);
+    auto half_of = [&](int x) -> uint32_t { return (sh.acc[x >> 1] >> ((x & 1) * 16)) & 0xffffu; };
+
+    for (int64_t item = blockIdx.x; item < n_query * n_groups; item += gridDim.x) {
+        const int64_t q = item / n_groups;
+        const int g = (int)(item - q * n_groups);
+        const int s0 = g * per_group, s1 = s0 + per_group < n_shards ? s0 + per_group : n_shards;
+        const int64_t qb = q_off[q], qe = q_off[q + 1];
+        auto fill = [&]() {
+            uint4 *a4 = reinterpret_cast<uint4 *>(sh.acc);
+            for (int t = tid; t < IM / 8; t += SQ_THREADS) a4[t] = make_uint4(0u, 0u, 0u, 0u);
+        };
+        fill();
+        if (tid == 0) { sh.ln = 0; sh.ncand = 0; }
+        __syncthreads();
+
+        for (int shard = s0; shard < s1; shard += NS) {
+            const int ns_here = s1 - shard < NS ? s1 - shard : NS;
+            const int64_t img0 = (int64_t)shard * SQ_R;
+            const int n_here = (int)((n_img - img0) < (int64_t)ns_here * SQ_R ? (n_img - img0) : (int64_t)ns_here * SQ_R);
+            const uint32_t *off = post_off + shard;
+            const int last = n_shards - shard;                     // pointer index of the row's end
+
+            // one call = 32 query words; lane l: runs of lengths l[0..NS) starting at b, one after the other
+            auto walk32 = [&](uint32_t b, const uint32_t (&l)[NS], int tf) {
+                uint32_t cum[NS];                                  // cum[j] = postings of the word before shard j + 1
+                cum[0] = l[0];
+#pragma unroll
+                for (int j = 1; j < NS; ++j) cum[j] = cum[j - 1] + l[j];
+                uint32_t len = cum[NS - 1];
+                const bool is_long = len > SQ_LONG;
+                unsigned int m = __ballot_sync(VT_FULL, is_long);
+                while (m) {                                        // (rare for leaf-word indexes) one run, the whole warp
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t lb = __shfl_sync(VT_FULL, b, src);
+                    uint32_t bnd[NS];
+#pragma unroll
+                    for (int j = 0; j < NS; ++j) bnd[j] = lb + __shfl_sync(VT_FULL, cum[j], src);
+                    const uint32_t ltf = (uint32_t)__shfl_sync(VT_FULL, tf, src);
+                    for (uint32_t p = lb + lane; p < bnd[NS - 1]; p += 32) {
+                        const uint32_t pe = __ldg(postings + p);
+                        uint32_t so = 0;
+#pragma unroll
+                        for (int j = 0; j + 1 < NS; ++j) so += p >= bnd[j];
+                        sq_add16(acc_s, (so << SQ_LOCAL_BITS) | (pe & SQ_LOCAL_MASK), ltf * (pe >> SQ_LOCAL_BITS), true);
+                    }
+                }
+                if (is_long) len = 0;
+                uint32_t incl = len;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(VT_FULL, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const uint32_t total = __shfl_sync(VT_FULL, incl, 31);
+                if (total == 0) return;
+                const uint32_t excl = incl - len;
+                ws.head[lane] = 0;
+                ws.head[lane + 32] = 0;
+                __syncwarp();
+                const bool ne = len > 0;
+                const unsigned int nem = __ballot_sync(VT_FULL, ne);
+                if (ne) {
+                    const int rank = __popc(nem & lt_mask);
+                    ws.base[rank] = b - excl;
+                    ws.tf[rank] = tf;
+#pragma unroll
+                    for (int j = 0; j + 1 < NS; ++j) sh.wb[warp][j][rank] = excl + cum[j];
+                    atomicOr(&ws.head[excl >> 5], 1u << (excl & 31));
+                }
+                __syncwarp();
+                int before = 0;
+                for (uint32_t c0 = 0; c0 * 32 < total; c0 += SQ_U) {
+                    uint32_t pe[SQ_U], so[SQ_U];
+                    int tv[SQ_U];
+#pragma unroll
+                    for (int u = 0; u < SQ_U; ++u) {
+                        const uint32_t c = c0 + u, j = c * 32 + lane;
+                        const uint32_t h = c * 32 < total ? ws.head[c] : 0u;
+                        const int idx = before + __popc(h & le_mask) - 1;
+                        before += __popc(h);
+                        pe[u] = 0u;
+                        so[u] = 0u;
+                        tv[u] = 0;
+                        if (j < total) {
+                            tv[u] = ws.tf[idx];
+                            pe[u] = __ldg(postings + (ws.base[idx] + j));
+#pragma unroll
+                            for (int jj = 0; jj + 1 < NS; ++jj) so[u] += j >= sh.wb[warp][jj][idx];
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < SQ_U; ++u)
+                        sq_add16(acc_s, (so[u] << SQ_LOCAL_BITS) | (pe[u] & SQ_LOCAL_MASK),
+                                 (uint32_t)tv[u] * (pe[u] >> SQ_LOCAL_BITS), tv[u] != 0);
+                }
+                __syncwarp();
+            };
+            // run lengths straight from the row pointers (words beyond the cache, runs of 255 and more)
+            auto from_pointers = [&](int64_t w, uint32_t &b, uint32_t (&l)[NS], int &tf) {
+                const uint32_t *r = off + (size_t)__ldg(q_node + w) * n_shards;
+                tf = (int)__ldg(q_val + w);
+                uint32_t prev = __ldg(r);
+                b = prev;
+#pragma unroll
+                for (int j = 0; j < NS; ++j) {
+                    const uint32_t nxt = __ldg(r + (j + 1 < last ? j + 1 : last));
+                    l[j] = j < ns_here ? nxt - prev : 0u;
+                    prev = nxt;
+                }
+            };
+
+            const int sub = (shard - s0) % SQ_SUB;
+            if (sub == 0) {
+                for (int i = tid; i < SQ_WCACHE; i += SQ_THREADS) {
+                    const int64_t w = qb + i;
+                    uint32_t p[SQ_SUB + 1];
+                    int tf = 0;
+                    if (w < qe) {
+                        const uint32_t *r = off + (size_t)__ldg(q_node + w) * n_shards;
+                        tf = (int)__ldg(q_val + w);
+#pragma unroll
+                        for (int j = 0; j <= SQ_SUB; ++j) p[j] = __ldg(r + (j < last ? j : last));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j <= SQ_SUB; ++j) p[j] = 0u;
+                    }
+                    sh.w_run[i] = p[0];
+                    sh.w_tf[i] = (uint16_t)(tf < 65535 ? tf : 65535);
+#pragma unroll
+                    for (int j = 0; j < SQ_SUB; ++j) {
+                        const uint32_t len = p[j + 1] - p[j];
+                        sh.w_len[j][i] = (uint8_t)(len < 255u && tf < 65535 ? len : 255u);
+                    }
+                }
+            }
+#pragma unroll 1
+            for (int i = tid; i < SQ_WCACHE && qb + (i - lane) < qe; i += SQ_THREADS) {
+                uint32_t l[NS], b = sh.w_run[i];
+                int tf = sh.w_tf[i];
+                bool esc = false;
+                uint32_t adv = 0;
+#pragma unroll
+                for (int j = 0; j < NS; ++j) {
+                    const uint32_t lj = sh.w_len[sub + j][i];
+                    esc |= lj == 255u;
+                    adv += lj;
+                    l[j] = j < ns_here ? lj : 0u;
+                }
+                if (esc) {
+                    from_pointers(qb + i, b, l, tf);
+                    adv = 0;
+#pragma unroll
+                    for (int j = 0; j < NS; ++j) adv += l[j];       // (a group's last step may stop early: nothing follows it)
+                }
+                sh.w_run[i] = b + adv;
+                walk32(b, l, tf);
+            }
+            for (int64_t w0 = qb + SQ_WCACHE + (int64_t)warp * 32; w0 < qe; w0 += SQ_THREADS) {
+                const int64_t w = w0 + lane;
+                uint32_t l[NS], b = 0;
+                int tf = 0;
+#pragma unroll
+                for (int j = 0; j < NS; ++j) l[j] = 0u;
+                if (w < qe) from_pointers(w, b, l, tf);
+                walk32(b, l, tf);
+            }
+            __syncthreads();
+
+            // ---- selection against the carried list ------------------------------------------------------------------
+            const int ln = sh.ln;
+            const double T = ln == topk ? sh.lkey[topk - 1] : -1.0;
+            bool exhaustive = !(T > 0.0);
+            if (!exhaustive) {
+                double rmax = 0.0;
+                for (int j = 0; j < ns_here; ++j) rmax = fmax(rmax, __ldg(shard_rmax + shard + j));
+                uint32_t d_lo = 0xffffffffu;                        // (no 16-bit dot reaches it)
+                if (rmax > 0.0) {
+                    const double x = ceil(T / rmax);
+                    if (x < 65536.0) {
+                        int d = (int)x;
+                        while (d > 1 && (double)(d - 1) * rmax >= T) --d;
+                        while ((double)d * rmax < T) ++d;
+                        d_lo = (uint32_t)(d < 1 ? 1 : d);
+                    }
+                }
+                const uint4 *a4 = reinterpret_cast<const uint4 *>(sh.acc);
+#pragma unroll 2
+                for (int u = 0; u < PER / 8; ++u) {
+                    const int t8 = u * SQ_THREADS + tid;
+                    const uint4 a = a4[t8];
+                    const uint32_t mx = __vmaxu2(__vmaxu2(a.x, a.y), __vmaxu2(a.z, a.w));
+                    if (max(mx & 0xffffu, mx >> 16) >= d_lo) {
+                        const uint32_t av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (((av[i >> 1] >> ((i & 1) * 16)) & 0xffffu) >= d_lo) {
+                                const int pos = atomicAdd(&sh.ncand, 1);
+                                if (pos < SQ_CAND) sh.cslot[pos] = t8 * 8 + i;
+                            }
+                    }
+                }
+                __syncthreads();
+                const int nc = sh.ncand;
+                if (nc > SQ_CAND) {
+                    exhaustive = true;
+                } else if (nc > 0) {
+                    for (int i = tid; i < nc; i += SQ_THREADS) {
+                        const int x = sh.cslot[i];
+                        sh.ckey[i] = (double)half_of(x) * __ldg(img_rnorm + img0 + x);
+                    }
+                    __syncthreads();
+                    if (warp == 0) {
+                        for (int i0 = 0; i0 < nc; i0 += 32) {
+                            const int i = i0 + lane;
+                            const double ck = i < nc ? sh.ckey[i] : -2.0;
+                            const int32_t cid = i < nc ? (int32_t)(img0 + sh.cslot[i]) : 0x7fffffff;
+                            unsigned int live = __ballot_sync(VT_FULL, i < nc);
+                            while (live) {
+                                const int src = __ffs(live) - 1;
+                                live &= live - 1;
+                                const double k = __shfl_sync(VT_FULL, ck, src);
+                                const int32_t id = __shfl_sync(VT_FULL, cid, src);
+                                const bool h0 = lane < topk, h1 = lane + 32 < topk;
+                                const double k0 = h0 ? sh.lkey[lane] : 0.0, k1 = h1 ? sh.lkey[lane + 32] : 0.0;
+                                const int32_t d0 = h0 ? sh.lid[lane] : 0, d1 = h1 ? sh.lid[lane + 32] : 0;
+                                const bool b0 = h0 && sq_better(k0, d0, k, id), b1 = h1 && sq_better(k1, d1, k, id);
+                                const int pos = __popc(__ballot_sync(VT_FULL, b0)) + __popc(__ballot_sync(VT_FULL, b1));
+                                if (pos < topk) {
+                                    __syncwarp();
+                                    if (h0 && !b0 && lane + 1 < topk) { sh.lkey[lane + 1] = k0; sh.lid[lane + 1] = d0; }
+                                    if (h1 && !b1 && lane + 33 < topk) { sh.lkey[lane + 33] = k1; sh.lid[lane + 33] = d1; }
+                                    __syncwarp();
+                                    if (lane == 0) { sh.lkey[pos] = k; sh.lid[pos] = id; }
+                                    __syncwarp();
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            if (exhaustive) {
+                auto key_of = [&](int x) -> double {
+                    if (x >= n_here) return -2.0;
+                    const uint32_t a = half_of(x);
+                    if (a == TAKEN16) return -2.0;
+                    const double rn = __ldg(img_rnorm + img0 + x);
+                    return rn < 0.0 ? -1.0 : (double)a * rn;
+                };
+                double lk = tid < ln ? sh.lkey[tid] : -2.0;
+                const int32_t li = tid < ln ? sh.lid[tid] : 0x7fffffff;
+                double bkey = -2.0; int32_t bid = 0x7fffffff;
+                for (int u = 0; u < PER; ++u) {
+                    const int x = u * SQ_THREADS + tid;
+                    const double key = key_of(x);
+                    if (sq_better(key, (int32_t)(img0 + x), bkey, bid)) { bkey = key; bid = (int32_t)(img0 + x); }
+                }
+                int n_new = 0;
+                for (int r = 0; r < topk; ++r) {
+                    double key = bkey; int32_t id = bid; int owner;
+                    if (sq_better(lk, li, key, id)) { key = lk; id = li; }
+                    sq_block_best(key, id, owner, sh);
+                    if (key > -2.0) n_new = r + 1;
+                    if (tid == 0) { sh.nkey[r] = key; sh.nid[r] = key > -2.0 ? id : -1; }
+                    if (tid == owner && key > -2.0) {
+                        if ((int64_t)id >= img0) {
+                            const int x = (int)(id - img0);
+                            sh.acc[x >> 1] |= TAKEN16 << ((x & 1) * 16);   // (only the owner writes between two barriers)
+                            bkey = -2.0; bid = 0x7fffffff;
+                            for (int u = 0; u < PER; ++u) {
+                                const int x2 = u * SQ_THREADS + tid;
+                                const double k2 = key_of(x2);
+                                if (sq_better(k2, (int32_t)(img0 + x2), bkey, bid)) { bkey = k2; bid = (int32_t)(img0 + x2); }
+                            }
+                        } else {
+                            lk = -2.0;
+                        }
+                    }
+                }
+                if (tid < topk) { sh.lkey[tid] = sh.nkey[tid]; sh.lid[tid] = sh.nid[tid]; }
+                if (tid == 0) sh.ln = n_new;
+            }
+            __syncthreads();
+            if (shard + NS < s1) fill();
+            if (tid == 0) sh.ncand = 0;
+            __syncthreads();
+        }
+
+        if (tid < topk) {
+            const size_t o = ((size_t)q * n_groups + g) * topk + tid;
+            const bool have = tid < sh.ln;
+            out_key[o] = have ? sh.lkey[tid] : -2.0;
+            out_id[o] = have ? sh.lid[tid] : -1;
+        }
+        __syncthreads();
+    }
+}
 }  // namespace
 
 // lists per query vt_score_topk_carried should write: enough (query, group) items to fill the device about four times over,
@@ -468,12 +820,31 @@ static int launch_query(const uint32_t *post_off, const uint32_t *postings, cons
     return VT_OK;
 }
 
+template <int NS, int MINB>
+static int launch_query16(const uint32_t *post_off, const uint32_t *postings, const double *img_rnorm, int64_t n_img,
+                          int n_shards, const int64_t *q_off, const int32_t *q_node, const float *q_val, int64_t n_query,
+                          int topk, const double *shard_rmax, int n_groups, double *out_key, int32_t *out_id, cudaStream_t s)
+{
+    auto kern = score_query16_kernel<NS, MINB>;
+    const size_t smem = sizeof(Sq16Shared<NS>);
+    VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int per_group = (n_shards + n_groups - 1) / n_groups;
+    const int64_t items = n_query * n_groups, cap = (int64_t)vt_sm_count() * MINB;
+    kern<<<(int)(items < cap ? items : cap), SQ_THREADS, smem, s>>>(post_off, postings, img_rnorm, n_img, n_shards, q_off, q_node,
+                                                                    q_val, n_query, topk, shard_rmax, n_groups, per_group,
+                                                                    out_key, out_id);
+    VT_LAUNCH_CHECK();
+    return VT_OK;
+}
+
 extern "C" int vt_score_topk_carried(const uint32_t *d_post_off, const void *d_postings, const double *d_img_rnorm,
                                      int64_t n_img, int64_t n_ref, const int64_t *d_q_off, const int32_t *d_q_node,
                                      const float *d_q_val, int64_t n_query, int topk, const double *d_shard_rmax,
-                                     const int32_t *d_seed, int64_t seed_stride, int n_groups, double *d_group_key,
-                                     int32_t *d_group_id, void *stream)
+                                     const int32_t *d_seed, int64_t seed_stride, int n_groups, int shards_per_step,
+                                     double *d_group_key, int32_t *d_group_id, void *stream)
 {
+    VT_CHECK_ARG(shards_per_step == 1 || ((shards_per_step == 2 || shards_per_step == 4) && d_seed == nullptr),
+                 "shards_per_step is 1, or 2 / 4 (16-bit accumulators: leaf-word indexes whose dots stay below 65535)");
     VT_CHECK_ARG(n_img > 0 && n_ref > 0 && n_query >= 0 && d_img_rnorm, "bad arguments");
     VT_CHECK_ARG(topk >= 1 && topk <= SQ_MAXK, "topk out of range");
     VT_CHECK_ARG((d_seed != nullptr) != (d_shard_rmax != nullptr), "pass either the seed rows (all-nodes) or the shard bounds (leaf words)");
@@ -483,6 +854,12 @@ extern "C" int vt_score_topk_carried(const uint32_t *d_post_off, const void *d_p
     if (n_query == 0) return VT_OK;
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t *po = (const uint32_t *)d_postings;
+    if (shards_per_step == 2)
+        return launch_query16<2, 4>(d_post_off, po, d_img_rnorm, n_img, n_shards, d_q_off, d_q_node, d_q_val, n_query, topk,
+                                    d_shard_rmax, n_groups, d_group_key, d_group_id, s);
+    if (shards_per_step == 4)
+        return launch_query16<4, 2>(d_post_off, po, d_img_rnorm, n_img, n_shards, d_q_off, d_q_node, d_q_val, n_query, topk,
+                                    d_shard_rmax, n_groups, d_group_key, d_group_id, s);
     if (d_seed)
         return launch_query<true>(d_post_off, po, d_img_rnorm, n_img, n_shards, d_q_off, d_q_node, d_q_val, n_query, topk, nullptr,
                                   d_seed, seed_stride, n_groups, d_group_key, d_group_id, s);

@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import functools
+import os
 
 import numpy as np
 import torch
@@ -686,6 +687,7 @@ def build_index(csr: dict, n_ref: int) -> dict:
     long_lists = bool(nnz > 0 and float((lens * lens).sum().item()) / float(nnz) > 64.0)
     return dict(post_off=post_off, postings=postings[:nnz], rnorm=rnorm[:n_img], sumsq=csr["sumsq"], n_img=n_img,
                 shard_empty=shard_empty, shard_rho=shard_rho, shard_rmax=hi.clamp(min=0.0).contiguous(),
+                max_sumsq=int(csr["sumsq"][:n_img].max().item()) if n_img > 0 else 0,
                 long_lists=long_lists,
                 n_ref=n_ref, shard=shard, n_shards=n_shards, nnz=nnz)
 
@@ -810,7 +812,7 @@ def score_dense(dense: dict, q: dict, topk: int, want_all: bool = False, d_budge
             shard_id = torch.empty((c1 - c0, n_groups, topk), dtype=torch.int32, device=dev)
             nat.check(lib.vt_score_topk_carried(nat.ptr(index["post_off"]), nat.ptr(index["postings"]), nat.ptr(index["rnorm"]),
                                                 n_img, index["n_ref"], nat.ptr(off), nat.ptr(qs["node"][b:]), nat.ptr(q_val[b:]),
-                                                c1 - c0, topk, None, nat.ptr(seed), np_, n_groups, nat.ptr(shard_key),
+                                                c1 - c0, topk, None, nat.ptr(seed), np_, n_groups, 1, nat.ptr(shard_key),
                                                 nat.ptr(shard_id), s), "vt_score_topk_carried")
             m = merge_topk(shard_key.view(c1 - c0, -1), shard_id.view(c1 - c0, -1), c1 - c0, topk, nat.SCORE_TF_L2,
                            q["sumsq"][c0:c1].contiguous(), index["sumsq"])
@@ -846,12 +848,15 @@ def _dense_query_overflow(q: dict, layout: dict, block: torch.Tensor):
 # --------------------------------------------------------------------------------------- score
 @_device_scoped
 def score(index: dict, q: dict, topk: int, mode: int = nat.SCORE_TF_L2, q_val: torch.Tensor = None,
-          want_all: bool = False, merge: bool = True, weights: dict = None, groups: int = None) -> dict:
+          want_all: bool = False, merge: bool = True, weights: dict = None, groups: int = None,
+          shards_per_step: int = None) -> dict:
     """Score a CSR batch of queries against the inverted file and select the top-k per query.
 
     Returns dict(key [Q, topk] f64, id [Q, topk] i32, score [Q, topk] f64, all_key [Q, n_img] | None,
     shard_key/shard_id when ``merge`` is False).  ``groups``: lists per query of the carried-top-k scorer (default: what
-    ``vt_score_group_count`` proposes for the batch; 1 = one CTA takes a query through every shard)."""
+    ``vt_score_group_count`` proposes for the batch; 1 = one CTA takes a query through every shard).
+    ``shards_per_step``: 1 (32-bit accumulators), 2 or 4 (16-bit accumulators, several shards per step; only valid when
+    every dot stays below 65535); default: 2 when the Cauchy-Schwarz bound of the batch allows it."""
     lib = _lib()
     dev = index["post_off"].device
     s = nat.stream_ptr()
@@ -884,12 +889,18 @@ def score(index: dict, q: dict, topk: int, mode: int = nat.SCORE_TF_L2, q_val: t
     if not want_all and nq > 0 and index.get("shard_rmax") is not None:
         # the top-k carried from shard to shard (vt_score_query.cu): ``shard_key`` / ``shard_id`` are then per GROUP of shards
         n_groups = int(groups or lib.vt_score_group_count(nq, n_img))
+        # 16-bit accumulators (two shards per step) when no dot of the batch can reach 65535: |q . d| <= |q| |d|
+        if shards_per_step is None:
+            bound = float(q["sumsq"].max().item()) * float(index.get("max_sumsq", 1 << 62))
+            shards_per_step = 2 if bound < 65535.0 ** 2 and n_shards > 1 else 1
+            if shards_per_step > 1 and os.environ.get("VT_SCORE_SHARDS_PER_STEP"):     # (experiments: 1, 2 or 4)
+                shards_per_step = int(os.environ["VT_SCORE_SHARDS_PER_STEP"])
         shard_key = torch.empty((nq, n_groups, topk), dtype=torch.float64, device=dev)
         shard_id = torch.empty((nq, n_groups, topk), dtype=torch.int32, device=dev)
         nat.check(lib.vt_score_topk_carried(nat.ptr(index["post_off"]), nat.ptr(index["postings"]), nat.ptr(index["rnorm"]),
                                             n_img, index["n_ref"], nat.ptr(q["row_off"]), nat.ptr(q["node"]), nat.ptr(q_val),
-                                            nq, topk, nat.ptr(index["shard_rmax"]), None, 0, n_groups, nat.ptr(shard_key),
-                                            nat.ptr(shard_id), s), "vt_score_topk_carried")
+                                            nq, topk, nat.ptr(index["shard_rmax"]), None, 0, n_groups, int(shards_per_step),
+                                            nat.ptr(shard_key), nat.ptr(shard_id), s), "vt_score_topk_carried")
         out = dict(all_key=None, shard_key=shard_key, shard_id=shard_id, topk=topk)
         if merge:
             out.update(merge_topk(shard_key.view(nq, -1), shard_id.view(nq, -1), nq, topk, mode, q["sumsq"], index["sumsq"]))

@@ -465,12 +465,14 @@ def test_score_multi_shard_random_csr(vt, cuda):
         assert ids[qi][0] == qr and sc[qi][0] == 0.0            # self match first, exactly zero
 
 
+@pytest.mark.parametrize("shards_per_step", [1, 2, 4])
 @pytest.mark.parametrize("groups", [1, 2, 5])
-def test_carried_topk_equals_exhaustive_selection(vt, cuda, groups):
+def test_carried_topk_equals_exhaustive_selection(vt, cuda, groups, shards_per_step):
     """vt_score_query.cu: a CTA carries the k best of a query from shard to shard and prunes with their worst key.  40 k
     images (5 shards) with planted duplicates (exact key ties across shards, broken by the smaller image index like
     database.py:79-80), images without words, queries with no match at all, long and short posting runs; every grouping
-    of the shards must return the order the full key dump gives."""
+    of the shards must return the order the full key dump gives -- with 32-bit accumulators (one shard per step) and with
+    16-bit accumulators (2 or 4 shards per step, groups that end inside a step)."""
     torch = _torch()
     import scipy.sparse as sp
     rng = np.random.default_rng(21 + groups)
@@ -506,7 +508,9 @@ def test_carried_topk_equals_exhaustive_selection(vt, cuda, groups):
     k = 12
     full = vt.engine.score(index, q, k, want_all=True)
     allk = full["all_key"].cpu().numpy()
-    got = vt.engine.score(index, q, k, groups=groups)
+    got = vt.engine.score(index, q, k, groups=groups, shards_per_step=shards_per_step)
+    auto = vt.engine.score(index, q, k)
+    assert torch.equal(auto["id"], got["id"]) and torch.equal(auto["key"], got["key"])
     ids, key, sc = got["id"].cpu().numpy(), got["key"].cpu().numpy(), got["score"].cpu().numpy()
     for qi in range(len(q_rows)):
         order = np.lexsort((np.arange(n_img), -allk[qi]))[:k]
