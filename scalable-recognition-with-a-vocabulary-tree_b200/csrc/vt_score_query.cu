@@ -105,7 +105,7 @@ __device__ __forceinline__ void sq_add(uint32_t acc_s, uint32_t pe, int tf, bool
 
 // SEEDED: accumulators start from the int32 dots over the dense top levels (vt_dense_dots) and candidates are filtered by
 // their exact key; otherwise they start from zero and the filter is the integer bound through shard_rmax.
-template <bool SEEDED, int MINB>
+template <bool SEEDED, int MINB, int U, int G>
 __global__ void __launch_bounds__(SQ_THREADS, MINB)
 score_query_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__restrict__ postings,
                    const double *__restrict__ img_rnorm, int64_t n_img, int n_shards, const int64_t *__restrict__ q_off,
@@ -152,12 +152,12 @@ score_query_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__rest
                 const bool is_long = len > SQ_LONG;
                 unsigned int m = __ballot_sync(VT_FULL, is_long);
                 while (m) {
-                    // long runs: the whole warp walks SQ_G runs together, the first SQ_U x 32 postings of each are loaded
-                    // before any is accumulated (one DRAM round trip per SQ_G runs instead of one per run)
-                    uint32_t lb[SQ_G], lend[SQ_G];
-                    int ltf[SQ_G];
+                    // long runs: the whole warp walks G runs together, the first U x 32 postings of each are loaded
+                    // before any is accumulated (one DRAM round trip per G runs instead of one per run)
+                    uint32_t lb[G], lend[G];
+                    int ltf[G];
 #pragma unroll
-                    for (int g = 0; g < SQ_G; ++g) {
+                    for (int g = 0; g < G; ++g) {
                         const int src = m ? __ffs(m) - 1 : 0;
                         const bool have = m != 0;
                         m &= m - 1;
@@ -165,27 +165,27 @@ score_query_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__rest
                         lend[g] = have ? lb[g] + __shfl_sync(VT_FULL, len, src) : lb[g];
                         ltf[g] = __shfl_sync(VT_FULL, tf, src);
                     }
-                    uint32_t pe[SQ_G][SQ_U];
+                    uint32_t pe[G][U];
 #pragma unroll
-                    for (int g = 0; g < SQ_G; ++g)
+                    for (int g = 0; g < G; ++g)
 #pragma unroll
-                        for (int u = 0; u < SQ_U; ++u) {
+                        for (int u = 0; u < U; ++u) {
                             const uint32_t p = lb[g] + lane + 32 * u;
                             pe[g][u] = p < lend[g] ? __ldg(postings + p) : 0u;
                         }
 #pragma unroll
-                    for (int g = 0; g < SQ_G; ++g)
+                    for (int g = 0; g < G; ++g)
 #pragma unroll
-                        for (int u = 0; u < SQ_U; ++u)
+                        for (int u = 0; u < U; ++u)
                             sq_add(acc_s, pe[g][u], ltf[g], lb[g] + lane + 32 * u < lend[g]);
 #pragma unroll
-                    for (int g = 0; g < SQ_G; ++g)                 // what is left of runs beyond SQ_U x 32 postings
-                        for (uint32_t p = lb[g] + 32 * SQ_U + lane; p < lend[g]; p += 32 * SQ_U) {
-                            uint32_t pt[SQ_U];
+                    for (int g = 0; g < G; ++g)                 // what is left of runs beyond U x 32 postings
+                        for (uint32_t p = lb[g] + 32 * U + lane; p < lend[g]; p += 32 * U) {
+                            uint32_t pt[U];
 #pragma unroll
-                            for (int u = 0; u < SQ_U; ++u) pt[u] = p + 32 * u < lend[g] ? __ldg(postings + p + 32 * u) : 0u;
+                            for (int u = 0; u < U; ++u) pt[u] = p + 32 * u < lend[g] ? __ldg(postings + p + 32 * u) : 0u;
 #pragma unroll
-                            for (int u = 0; u < SQ_U; ++u)
+                            for (int u = 0; u < U; ++u)
                                 sq_add(acc_s, pt[u], ltf[g], p + 32 * u < lend[g]);
                         }
                 }
@@ -213,11 +213,11 @@ score_query_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__rest
                 }
                 __syncwarp();
                 int before = 0;                                    // words that start before the current chunk
-                for (uint32_t c0 = 0; c0 * 32 < total; c0 += SQ_U) {
-                    uint32_t pe[SQ_U];
-                    int tv[SQ_U];
+                for (uint32_t c0 = 0; c0 * 32 < total; c0 += U) {
+                    uint32_t pe[U];
+                    int tv[U];
 #pragma unroll
-                    for (int u = 0; u < SQ_U; ++u) {
+                    for (int u = 0; u < U; ++u) {
                         const uint32_t c = c0 + u, j = c * 32 + lane;
                         const uint32_t h = c * 32 < total ? ws.head[c] : 0u;
                         const int idx = before + __popc(h & le_mask) - 1;
@@ -230,7 +230,7 @@ score_query_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__rest
                         }
                     }
 #pragma unroll
-                    for (int u = 0; u < SQ_U; ++u)
+                    for (int u = 0; u < U; ++u)
                         sq_add(acc_s, pe[u], tv[u], tv[u] != 0);
                 }
                 __syncwarp();                                      // the scratch is rewritten by the next 32 words
@@ -471,7 +471,7 @@ __device__ __forceinline__ void sq_add16(uint32_t acc_s, uint32_t x, uint32_t va
                  :: "r"(addr), "r"(v), "r"((uint32_t)ok) : "memory");
 }
 
-template <int NS, int MINB>
+template <int NS, int MINB, int U>
 __global__ void __launch_bounds__(SQ_THREADS, MINB)
 score_query16_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__restrict__ postings,
                      const double *__restrict__ img_rnorm, int64_t n_img, int n_shards, const int64_t *__restrict__ q_off,
@@ -561,29 +561,30 @@ score_query16_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__re
                 }
                 __syncwarp();
                 int before = 0;
-                for (uint32_t c0 = 0; c0 * 32 < total; c0 += SQ_U) {
-                    uint32_t pe[SQ_U], so[SQ_U];
-                    int tv[SQ_U];
+                for (uint32_t c0 = 0; c0 * 32 < total; c0 += U) {
+                    // per slot two registers: the posting, and (shard of the step << 16 | query count) -- a posting's tf
+                    // and the query count are below 65536 here, or some dot would not be
+                    uint32_t pe[U], ts[U];
 #pragma unroll
-                    for (int u = 0; u < SQ_U; ++u) {
+                    for (int u = 0; u < U; ++u) {
                         const uint32_t c = c0 + u, j = c * 32 + lane;
                         const uint32_t h = c * 32 < total ? ws.head[c] : 0u;
                         const int idx = before + __popc(h & le_mask) - 1;
                         before += __popc(h);
                         pe[u] = 0u;
-                        so[u] = 0u;
-                        tv[u] = 0;
+                        ts[u] = 0u;
                         if (j < total) {
-                            tv[u] = ws.tf[idx];
-                            pe[u] = __ldg(postings + (ws.base[idx] + j));
+                            uint32_t so = 0;
 #pragma unroll
-                            for (int jj = 0; jj + 1 < NS; ++jj) so[u] += j >= sh.wb[warp][jj][idx];
+                            for (int jj = 0; jj + 1 < NS; ++jj) so += j >= sh.wb[warp][jj][idx];
+                            ts[u] = (so << 16) | (uint32_t)ws.tf[idx];
+                            pe[u] = __ldg(postings + (ws.base[idx] + j));
                         }
                     }
 #pragma unroll
-                    for (int u = 0; u < SQ_U; ++u)
-                        sq_add16(acc_s, (so[u] << SQ_LOCAL_BITS) | (pe[u] & SQ_LOCAL_MASK),
-                                 (uint32_t)tv[u] * (pe[u] >> SQ_LOCAL_BITS), tv[u] != 0);
+                    for (int u = 0; u < U; ++u)
+                        sq_add16(acc_s, ((ts[u] >> 16) << SQ_LOCAL_BITS) | (pe[u] & SQ_LOCAL_MASK),
+                                 (ts[u] & 0xffffu) * (pe[u] >> SQ_LOCAL_BITS), ts[u] != 0);
                 }
                 __syncwarp();
             };
@@ -802,17 +803,17 @@ extern "C" int vt_score_group_count(int64_t n_query, int64_t n_img)
     return (int)((n_shards + per - 1) / per);
 }
 
-template <bool SEEDED>
+template <bool SEEDED, int MINB = 4, int U = SQ_U, int G = SQ_G>
 static int launch_query(const uint32_t *post_off, const uint32_t *postings, const double *img_rnorm, int64_t n_img, int n_shards,
                         const int64_t *q_off, const int32_t *q_node, const float *q_val, int64_t n_query, int topk,
                         const double *shard_rmax, const int32_t *seed, int64_t seed_stride, int n_groups, double *out_key,
                         int32_t *out_id, cudaStream_t s)
 {
-    auto kern = score_query_kernel<SEEDED, 4>;
+    auto kern = score_query_kernel<SEEDED, MINB, U, G>;
     const size_t smem = sizeof(SqShared);
     VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int per_group = (n_shards + n_groups - 1) / n_groups;
-    const int64_t items = n_query * n_groups, cap = (int64_t)vt_sm_count() * 4;
+    const int64_t items = n_query * n_groups, cap = (int64_t)vt_sm_count() * MINB;
     kern<<<(int)(items < cap ? items : cap), SQ_THREADS, smem, s>>>(post_off, postings, img_rnorm, n_img, n_shards, q_off, q_node,
                                                                     q_val, n_query, topk, shard_rmax, seed, seed_stride, n_groups,
                                                                     per_group, out_key, out_id);
@@ -820,12 +821,12 @@ static int launch_query(const uint32_t *post_off, const uint32_t *postings, cons
     return VT_OK;
 }
 
-template <int NS, int MINB>
+template <int NS, int MINB, int U = SQ_U>
 static int launch_query16(const uint32_t *post_off, const uint32_t *postings, const double *img_rnorm, int64_t n_img,
                           int n_shards, const int64_t *q_off, const int32_t *q_node, const float *q_val, int64_t n_query,
                           int topk, const double *shard_rmax, int n_groups, double *out_key, int32_t *out_id, cudaStream_t s)
 {
-    auto kern = score_query16_kernel<NS, MINB>;
+    auto kern = score_query16_kernel<NS, MINB, U>;
     const size_t smem = sizeof(Sq16Shared<NS>);
     VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int per_group = (n_shards + n_groups - 1) / n_groups;
@@ -854,12 +855,15 @@ extern "C" int vt_score_topk_carried(const uint32_t *d_post_off, const void *d_p
     if (n_query == 0) return VT_OK;
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t *po = (const uint32_t *)d_postings;
+    // chunks in flight and CTAs per SM as measured on the 1 M-image leaf-word bench: <NS 2, 4 CTAs, U 4> 240 k q/s, <2, 3, 8>
+    // 268 k, <2, 3, 12> 300-310 k, <2, 3, 16> 270 k, <2, 2, 16> 206 k, <4, 2, 8> 201 k: instruction-level parallelism beats warps
     if (shards_per_step == 2)
-        return launch_query16<2, 4>(d_post_off, po, d_img_rnorm, n_img, n_shards, d_q_off, d_q_node, d_q_val, n_query, topk,
+        return launch_query16<2, 3, 12>(d_post_off, po, d_img_rnorm, n_img, n_shards, d_q_off, d_q_node, d_q_val, n_query, topk,
                                     d_shard_rmax, n_groups, d_group_key, d_group_id, s);
     if (shards_per_step == 4)
         return launch_query16<4, 2>(d_post_off, po, d_img_rnorm, n_img, n_shards, d_q_off, d_q_node, d_q_val, n_query, topk,
                                     d_shard_rmax, n_groups, d_group_key, d_group_id, s);
+    // (all-nodes indexes: 3 CTAs with 8 or 12 chunks in flight, or 6 long runs at a time, measured within 2 % or slower)
     if (d_seed)
         return launch_query<true>(d_post_off, po, d_img_rnorm, n_img, n_shards, d_q_off, d_q_node, d_q_val, n_query, topk, nullptr,
                                   d_seed, seed_stride, n_groups, d_group_key, d_group_id, s);
