@@ -41,3 +41,22 @@ def test_argument_validation_without_gpu(vt):
     rc = lib.vt_sort_pairs(None, None, None, None, 1 << 40, 8, None, ctypes.byref(flip), None)
     assert rc == -1
     assert lib.vt_encode_max_words() == 8192 and lib.vt_score_shard_size() == 8192
+
+
+def test_host_pack_is_pure_host_code(vt):
+    """vt_host_pack (the native multi-threaded packing of a batch's descriptor arrays into one staging buffer) touches no
+    device: many arrays of ragged sizes, empty ones included, land back to back, with one thread and with eight."""
+    import numpy as np
+    lib = vt._native.load()
+    rng = np.random.default_rng(0)
+    arrs = [rng.integers(0, 256, (int(n), 128), dtype=np.uint8) for n in rng.integers(0, 900, 400)] + [np.zeros((0, 128), np.uint8)]
+    want = np.concatenate(arrs)
+    assert want.nbytes > (8 << 20)                                  # large enough for the threaded path
+    n = len(arrs)
+    src = (ctypes.c_void_p * n)(*[a.__array_interface__["data"][0] for a in arrs])
+    nbytes = (ctypes.c_int64 * n)(*[a.nbytes for a in arrs])
+    for threads in (1, 8):
+        dst = np.full(want.shape, 7, np.uint8)
+        assert lib.vt_host_pack(src, nbytes, n, ctypes.c_void_p(dst.ctypes.data), threads) == 0
+        assert np.array_equal(dst, want)
+    assert lib.vt_host_pack(src, nbytes, n, None, 4) == -1 and b"bad arguments" in lib.vt_last_error()
