@@ -330,6 +330,12 @@ int vt_score_topk_weighted(const uint32_t *d_post_off, const void *d_postings, c
                            const double *d_qv, const double *d_qi, const double *d_q_rnorm, int64_t n_query,
                            int mode, int topk, double *d_shard_key, int32_t *d_shard_id, double *d_all_key,
                            void *stream);
+/* VT_SCORE_W_L2 with the top-k carried from shard to shard (csrc/vt_score_query.cu, binary64 accumulators): n_groups lists
+ * per query like vt_score_topk_carried; d_qv from vt_query_weights, d_q_rnorm its per-query norms (<= 0: no weight). */
+int vt_score_topk_weighted_carried(const uint32_t *d_post_off, const void *d_postings, const double *d_img_rnorm,
+                                   int64_t n_img, int64_t n_ref, const int64_t *d_q_off, const int32_t *d_q_node,
+                                   const double *d_qv, const double *d_q_rnorm, int64_t n_query, int topk, int n_groups,
+                                   double *d_group_key, int32_t *d_group_id, void *stream);
 
 /* ---- measurement helper (bench.py): best-of-reps FP32 FFMA throughput of the current device in
  * TFLOP/s; d_scratch holds at least sm_count*8*256 floats. */

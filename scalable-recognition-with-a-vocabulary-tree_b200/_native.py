@@ -68,6 +68,7 @@ SIGNATURES = {
     "vt_idf": (_int, [_vp, _i64, _i64, _vp, _vp]),
     "vt_weighted_rnorm": (_int, [_vp, _vp, _vp, _i64, _vp, _int, _vp, _vp]),
     "vt_query_weights": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _int, _vp, _vp, _vp]),
+    "vt_score_topk_weighted_carried": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _int, _int, _vp, _vp, _vp]),
     "vt_score_topk_weighted": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _vp, _vp, _vp, _vp]),
     "vt_measure_fp32_peak": (_int, [_vp, _int, _int, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp]),
     "vt_topk_merge": (_int, [_vp, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

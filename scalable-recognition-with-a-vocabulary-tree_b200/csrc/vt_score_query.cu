@@ -42,29 +42,36 @@ constexpr uint32_t SQ_LOCAL_MASK = 8191u;  // posting = (tf << 13) | local image
 constexpr int SQ_LOCAL_BITS = 13;
 constexpr int SQ_TAKEN = INT_MIN;
 
-struct SqScratch {                         // per warp
+template <class W>
+struct SqScratchT {                        // per warp
     uint32_t base[32];                     // compacted non-empty words: posting index of flat position 0 of the word
-    int tf[32];                            //   ... and the query's count of the word
+    W tf[32];                              //   ... and the query's count (tf modes) or binary64 weight (tf-idf) of the word
     uint32_t head[SQ_HEADS];               // bit j of head[c]: flat position 32 c + j starts a word's run
 };
+using SqScratch = SqScratchT<int>;
 
-struct SqShared {
-    int acc[SQ_R];
+template <class W> struct SqWordStore { typedef uint16_t type; };          // cached per-word query factor
+template <> struct SqWordStore<double> { typedef double type; };
+
+template <class A, class W>
+struct SqSharedT {
+    A acc[SQ_R];
     double ckey[SQ_CAND];
     int cslot[SQ_CAND];
     double lkey[SQ_MAXK], nkey[SQ_MAXK];   // the carried list (best first) and the one the exhaustive selection builds
     int32_t lid[SQ_MAXK], nid[SQ_MAXK];
-    SqScratch ws[SQ_WARPS];
+    SqScratchT<W> ws[SQ_WARPS];
     // thread-private slots (word i of the query belongs to thread i % 256): where the word's run starts in the current
     // shard, its query count, and the lengths of its runs in the SQ_SUB shards of the current sub-group (255 = longer)
     uint32_t w_run[SQ_WCACHE];
-    uint16_t w_tf[SQ_WCACHE];
+    typename SqWordStore<W>::type w_tf[SQ_WCACHE];
     uint8_t w_len[SQ_SUB][SQ_WCACHE];
     double r_key[SQ_WARPS];
     int32_t r_id[SQ_WARPS];
     int r_owner[SQ_WARPS];
     int ncand, ln;
 };
+using SqShared = SqSharedT<int, int>;
 
 __device__ __forceinline__ bool sq_better(double ka, int32_t ia, double kb, int32_t ib)
 {
@@ -103,31 +110,56 @@ __device__ __forceinline__ void sq_add(uint32_t acc_s, uint32_t pe, int tf, bool
                  :: "r"(addr), "r"(val), "r"((uint32_t)ok) : "memory");
 }
 
+// tf-idf: acc[local image] += (binary64 query weight of the word) * (tf of the posting)
+__device__ __forceinline__ void sq_add(double *acc, uint32_t pe, double w, bool ok)
+{
+    if (ok) atomicAdd(acc + (pe & SQ_LOCAL_MASK), w * (double)(pe >> SQ_LOCAL_BITS));
+}
+
 // SEEDED: accumulators start from the int32 dots over the dense top levels (vt_dense_dots) and candidates are filtered by
 // their exact key; otherwise they start from zero and the filter is the integer bound through shard_rmax.
-template <bool SEEDED, int MINB, int U, int G>
+// MODE: SQ_TF (integer accumulators from zero, integer pruning bound), SQ_TF_SEEDED (integer accumulators from the dense-top
+// dots, exact-key filter), SQ_TFIDF_L2 (binary64 accumulators: q_val_ are the binary64 query weights of vt_query_weights,
+// img_rnorm the weighted norms, q_rnorm <= 0 marks a query without weight; exact-key filter).
+enum { SQ_TF = 0, SQ_TF_SEEDED = 1, SQ_TFIDF_L2 = 2 };
+template <int MODE> struct SqTypes { typedef int A; typedef int W; typedef float Q; };
+template <> struct SqTypes<SQ_TFIDF_L2> { typedef double A; typedef double W; typedef double Q; };
+
+template <int MODE, int MINB, int U, int G>
 __global__ void __launch_bounds__(SQ_THREADS, MINB)
 score_query_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__restrict__ postings,
                    const double *__restrict__ img_rnorm, int64_t n_img, int n_shards, const int64_t *__restrict__ q_off,
-                   const int32_t *__restrict__ q_node, const float *__restrict__ q_val, int64_t n_query, int topk,
-                   const double *__restrict__ shard_rmax, const int32_t *__restrict__ seed, int64_t seed_stride,
-                   int n_groups, int per_group, double *__restrict__ out_key, int32_t *__restrict__ out_id)
+                   const int32_t *__restrict__ q_node, const void *__restrict__ q_val_, const double *__restrict__ q_rnorm,
+                   int64_t n_query, int topk, const double *__restrict__ shard_rmax, const int32_t *__restrict__ seed,
+                   int64_t seed_stride, int n_groups, int per_group, double *__restrict__ out_key, int32_t *__restrict__ out_id)
 {
+    typedef typename SqTypes<MODE>::A A;                   // accumulator
+    typedef typename SqTypes<MODE>::W W;                   // per-word query factor
+    constexpr bool SEEDED = MODE == SQ_TF_SEEDED, WEIGHTED = MODE == SQ_TFIDF_L2, EXACT_FILTER = MODE != SQ_TF;
+    const typename SqTypes<MODE>::Q *__restrict__ q_val = static_cast<const typename SqTypes<MODE>::Q *>(q_val_);
     extern __shared__ __align__(16) unsigned char s_raw[];
-    SqShared &sh = *reinterpret_cast<SqShared *>(s_raw);
+    SqSharedT<A, W> &sh = *reinterpret_cast<SqSharedT<A, W> *>(s_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t le_mask = (2u << lane) - 1u, lt_mask = (1u << lane) - 1u;
-    SqScratch &ws = sh.ws[warp];
+    SqScratchT<W> &ws = sh.ws[warp];
     const uint32_t acc_s = (uint32_t)__cvta_generic_to_shared(sh.acc);
+    auto add = [&](uint32_t pe, W w, bool ok) {
+        if constexpr (WEIGHTED) sq_add(sh.acc, pe, w, ok);
+        else sq_add(acc_s, pe, w, ok);
+    };
+    const A TAKEN = WEIGHTED ? (A)-1 : (A)SQ_TAKEN;         // (dots and weighted sums are never negative)
 
     for (int64_t item = blockIdx.x; item < n_query * n_groups; item += gridDim.x) {
         const int64_t q = item / n_groups;
         const int g = (int)(item - q * n_groups);
         const int s0 = g * per_group, s1 = s0 + per_group < n_shards ? s0 + per_group : n_shards;
         const int64_t qb = q_off[q], qe = q_off[q + 1];
+        const bool q_ok = !WEIGHTED || __ldg(q_rnorm + q) > 0.0;
 
         auto fill = [&](int shard) {
-            if (SEEDED) {
+            if constexpr (WEIGHTED) {
+                for (int t = tid; t < SQ_R; t += SQ_THREADS) sh.acc[t] = 0.0;
+            } else if constexpr (SEEDED) {
                 const int64_t img0 = (int64_t)shard * SQ_R;
                 const int n_here = (int)((n_img - img0) < SQ_R ? (n_img - img0) : SQ_R);
                 const int32_t *row = seed + (size_t)q * seed_stride + img0;
@@ -148,14 +180,14 @@ score_query_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__rest
 
             // ---- walk ------------------------------------------------------------------------------------------------
             // one call = the runs of 32 query words (lane l: run [b, b + len) of a word with query count tf)
-            auto walk32 = [&](uint32_t b, uint32_t len, int tf) {
+            auto walk32 = [&](uint32_t b, uint32_t len, W tf) {
                 const bool is_long = len > SQ_LONG;
                 unsigned int m = __ballot_sync(VT_FULL, is_long);
                 while (m) {
                     // long runs: the whole warp walks G runs together, the first U x 32 postings of each are loaded
                     // before any is accumulated (one DRAM round trip per G runs instead of one per run)
                     uint32_t lb[G], lend[G];
-                    int ltf[G];
+                    W ltf[G];
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
                         const int src = m ? __ffs(m) - 1 : 0;
@@ -177,7 +209,7 @@ score_query_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__rest
                     for (int g = 0; g < G; ++g)
 #pragma unroll
                         for (int u = 0; u < U; ++u)
-                            sq_add(acc_s, pe[g][u], ltf[g], lb[g] + lane + 32 * u < lend[g]);
+                            add(pe[g][u], ltf[g], lb[g] + lane + 32 * u < lend[g]);
 #pragma unroll
                     for (int g = 0; g < G; ++g)                 // what is left of runs beyond U x 32 postings
                         for (uint32_t p = lb[g] + 32 * U + lane; p < lend[g]; p += 32 * U) {
@@ -186,7 +218,7 @@ score_query_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__rest
                             for (int u = 0; u < U; ++u) pt[u] = p + 32 * u < lend[g] ? __ldg(postings + p + 32 * u) : 0u;
 #pragma unroll
                             for (int u = 0; u < U; ++u)
-                                sq_add(acc_s, pt[u], ltf[g], p + 32 * u < lend[g]);
+                                add(pt[u], ltf[g], p + 32 * u < lend[g]);
                         }
                 }
                 if (is_long) len = 0;
@@ -215,7 +247,7 @@ score_query_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__rest
                 int before = 0;                                    // words that start before the current chunk
                 for (uint32_t c0 = 0; c0 * 32 < total; c0 += U) {
                     uint32_t pe[U];
-                    int tv[U];
+                    W tv[U];
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         const uint32_t c = c0 + u, j = c * 32 + lane;
@@ -231,7 +263,7 @@ score_query_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__rest
                     }
 #pragma unroll
                     for (int u = 0; u < U; ++u)
-                        sq_add(acc_s, pe[u], tv[u], tv[u] != 0);
+                        add(pe[u], tv[u], tv[u] != 0);
                 }
                 __syncwarp();                                      // the scratch is rewritten by the next 32 words
             };
@@ -243,10 +275,10 @@ score_query_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__rest
                 for (int i = tid; i < SQ_WCACHE; i += SQ_THREADS) {
                     const int64_t w = qb + i;
                     uint32_t p[SQ_SUB + 1];
-                    int tf = 0;
+                    W tf = 0;
                     if (w < qe) {
                         const uint32_t *r = off + (size_t)__ldg(q_node + w) * n_shards;
-                        tf = (int)__ldg(q_val + w);
+                        tf = (W)__ldg(q_val + w);
 #pragma unroll
                         for (int j = 0; j <= SQ_SUB; ++j) p[j] = __ldg(r + (j < last ? j : last));
                     } else {
@@ -254,11 +286,12 @@ score_query_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__rest
                         for (int j = 0; j <= SQ_SUB; ++j) p[j] = 0u;
                     }
                     sh.w_run[i] = p[0];
-                    sh.w_tf[i] = (uint16_t)(tf < 65535 ? tf : 65535);
+                    const bool wide = !WEIGHTED && tf >= (W)65535;      // (a count that does not fit the 16-bit slot)
+                    sh.w_tf[i] = (typename SqWordStore<W>::type)(wide ? (W)65535 : tf);
 #pragma unroll
                     for (int j = 0; j < SQ_SUB; ++j) {
                         const uint32_t len = p[j + 1] - p[j];
-                        sh.w_len[j][i] = (uint8_t)(len < 255u && tf < 65535 ? len : 255u);
+                        sh.w_len[j][i] = (uint8_t)(len < 255u && !wide ? len : 255u);
                     }
                 }
                 // (thread-private slots: no barrier)
@@ -266,13 +299,13 @@ score_query_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__rest
 #pragma unroll 1
             for (int i = tid; i < SQ_WCACHE && qb + (i - lane) < qe; i += SQ_THREADS) {
                 uint32_t len = sh.w_len[sub][i], b = sh.w_run[i];
-                int tf = sh.w_tf[i];
+                W tf = (W)sh.w_tf[i];
                 if (len == 255u) {                                 // a long run (or a huge query count): read it again
                     const int64_t w = qb + i;
                     const uint32_t *r = off + (size_t)__ldg(q_node + w) * n_shards;
                     b = __ldg(r);
                     len = __ldg(r + 1) - b;
-                    tf = (int)__ldg(q_val + w);
+                    tf = (W)__ldg(q_val + w);
                 }
                 sh.w_run[i] = b + len;
                 walk32(b, len, tf);
@@ -280,12 +313,12 @@ score_query_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__rest
             for (int64_t w0 = qb + SQ_WCACHE + (int64_t)warp * 32; w0 < qe; w0 += SQ_THREADS) {
                 const int64_t w = w0 + lane;
                 uint32_t b = 0, len = 0;
-                int tf = 0;
+                W tf = 0;
                 if (w < qe) {
                     const uint32_t *r = off + (size_t)__ldg(q_node + w) * n_shards;
                     b = __ldg(r);
                     len = __ldg(r + 1) - b;
-                    tf = (int)__ldg(q_val + w);
+                    tf = (W)__ldg(q_val + w);
                 }
                 walk32(b, len, tf);
             }
@@ -296,12 +329,12 @@ score_query_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__rest
             const double T = ln == topk ? sh.lkey[topk - 1] : -1.0;
             bool exhaustive = !(T > 0.0);                          // nothing can be pruned: untouched images reach T
             if (!exhaustive) {
-                if (SEEDED) {
+                if constexpr (EXACT_FILTER) {
 #pragma unroll 4
                     for (int u = 0; u < SQ_PER; ++u) {
                         const int t = u * SQ_THREADS + tid;
-                        const int a = sh.acc[t];
-                        if (a > 0 && t < n_here) {
+                        const A a = sh.acc[t];
+                        if (a > (A)0 && t < n_here) {
                             const double key = (double)a * __ldg(img_rnorm + img0 + t);   // (empty images: a == 0)
                             if (key >= T) {
                                 const int pos = atomicAdd(&sh.ncand, 1);
@@ -342,7 +375,7 @@ score_query_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__rest
                 if (nc > SQ_CAND) {
                     exhaustive = true;                             // (block uniform)
                 } else if (nc > 0) {
-                    if (!SEEDED) {
+                    if constexpr (!EXACT_FILTER) {
                         for (int i = tid; i < nc; i += SQ_THREADS) {
                             const int t = sh.cslot[i];
                             sh.ckey[i] = (double)sh.acc[t] * __ldg(img_rnorm + img0 + t);
@@ -383,10 +416,10 @@ score_query_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__rest
                 // ---- k rounds of block arg-max over (this shard's images) U (the carried list) -------------------------
                 auto key_of = [&](int t) -> double {
                     if (t >= n_here) return -2.0;
-                    const int a = sh.acc[t];
-                    if (a == SQ_TAKEN) return -2.0;
+                    const A a = sh.acc[t];
+                    if (a == TAKEN) return -2.0;
                     const double rn = __ldg(img_rnorm + img0 + t);
-                    return rn < 0.0 ? -1.0 : (double)a * rn;
+                    return (rn < 0.0 || !q_ok) ? -1.0 : (double)a * rn;
                 };
                 double lk = tid < ln ? sh.lkey[tid] : -2.0;        // thread t owns list entry t
                 const int32_t li = tid < ln ? sh.lid[tid] : 0x7fffffff;
@@ -405,7 +438,7 @@ score_query_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__rest
                     if (tid == 0) { sh.nkey[r] = key; sh.nid[r] = key > -2.0 ? id : -1; }
                     if (tid == owner && key > -2.0) {
                         if ((int64_t)id >= img0) {                 // one of this shard's images (list ids are smaller)
-                            sh.acc[id - img0] = SQ_TAKEN;
+                            sh.acc[id - img0] = TAKEN;
                             bkey = -2.0; bid = 0x7fffffff;
                             for (int u = 0; u < SQ_PER; ++u) {
                                 const int t = u * SQ_THREADS + tid;
@@ -803,20 +836,20 @@ extern "C" int vt_score_group_count(int64_t n_query, int64_t n_img)
     return (int)((n_shards + per - 1) / per);
 }
 
-template <bool SEEDED, int MINB = 4, int U = SQ_U, int G = SQ_G>
+template <int MODE, int MINB = 4, int U = SQ_U, int G = SQ_G>
 static int launch_query(const uint32_t *post_off, const uint32_t *postings, const double *img_rnorm, int64_t n_img, int n_shards,
-                        const int64_t *q_off, const int32_t *q_node, const float *q_val, int64_t n_query, int topk,
-                        const double *shard_rmax, const int32_t *seed, int64_t seed_stride, int n_groups, double *out_key,
-                        int32_t *out_id, cudaStream_t s)
+                        const int64_t *q_off, const int32_t *q_node, const void *q_val, const double *q_rnorm, int64_t n_query,
+                        int topk, const double *shard_rmax, const int32_t *seed, int64_t seed_stride, int n_groups,
+                        double *out_key, int32_t *out_id, cudaStream_t s)
 {
-    auto kern = score_query_kernel<SEEDED, MINB, U, G>;
-    const size_t smem = sizeof(SqShared);
+    auto kern = score_query_kernel<MODE, MINB, U, G>;
+    const size_t smem = sizeof(SqSharedT<typename SqTypes<MODE>::A, typename SqTypes<MODE>::W>);
     VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int per_group = (n_shards + n_groups - 1) / n_groups;
     const int64_t items = n_query * n_groups, cap = (int64_t)vt_sm_count() * MINB;
     kern<<<(int)(items < cap ? items : cap), SQ_THREADS, smem, s>>>(post_off, postings, img_rnorm, n_img, n_shards, q_off, q_node,
-                                                                    q_val, n_query, topk, shard_rmax, seed, seed_stride, n_groups,
-                                                                    per_group, out_key, out_id);
+                                                                    q_val, q_rnorm, n_query, topk, shard_rmax, seed, seed_stride,
+                                                                    n_groups, per_group, out_key, out_id);
     VT_LAUNCH_CHECK();
     return VT_OK;
 }
@@ -865,8 +898,27 @@ extern "C" int vt_score_topk_carried(const uint32_t *d_post_off, const void *d_p
                                     d_shard_rmax, n_groups, d_group_key, d_group_id, s);
     // (all-nodes indexes: 3 CTAs with 8 or 12 chunks in flight, or 6 long runs at a time, measured within 2 % or slower)
     if (d_seed)
-        return launch_query<true>(d_post_off, po, d_img_rnorm, n_img, n_shards, d_q_off, d_q_node, d_q_val, n_query, topk, nullptr,
-                                  d_seed, seed_stride, n_groups, d_group_key, d_group_id, s);
-    return launch_query<false>(d_post_off, po, d_img_rnorm, n_img, n_shards, d_q_off, d_q_node, d_q_val, n_query, topk, d_shard_rmax,
-                               nullptr, 0, n_groups, d_group_key, d_group_id, s);
+        return launch_query<SQ_TF_SEEDED>(d_post_off, po, d_img_rnorm, n_img, n_shards, d_q_off, d_q_node, d_q_val, nullptr, n_query,
+                                          topk, nullptr, d_seed, seed_stride, n_groups, d_group_key, d_group_id, s);
+    return launch_query<SQ_TF>(d_post_off, po, d_img_rnorm, n_img, n_shards, d_q_off, d_q_node, d_q_val, nullptr, n_query, topk,
+                               d_shard_rmax, nullptr, 0, n_groups, d_group_key, d_group_id, s);
+}
+
+// tf-idf / L2 (VT_SCORE_W_L2) with the carried top-k: binary64 accumulators (64 KB per shard: 2 CTAs per SM, 8 chunks in
+// flight per lane), candidates filtered by their exact key.  Same keys as vt_score_topk_weighted up to the order of the
+// binary64 additions (shared-memory atomics), lists per group like vt_score_topk_carried.
+extern "C" int vt_score_topk_weighted_carried(const uint32_t *d_post_off, const void *d_postings, const double *d_img_rnorm,
+                                              int64_t n_img, int64_t n_ref, const int64_t *d_q_off, const int32_t *d_q_node,
+                                              const double *d_qv, const double *d_q_rnorm, int64_t n_query, int topk,
+                                              int n_groups, double *d_group_key, int32_t *d_group_id, void *stream)
+{
+    VT_CHECK_ARG(n_img > 0 && n_ref > 0 && n_query >= 0 && d_img_rnorm && d_q_rnorm, "bad arguments");
+    VT_CHECK_ARG(topk >= 1 && topk <= SQ_MAXK, "topk out of range");
+    const int n_shards = (int)((n_img + SQ_R - 1) / SQ_R);
+    VT_CHECK_ARG(n_groups >= 1 && n_groups <= n_shards, "n_groups out of range");
+    if (n_query == 0) return VT_OK;
+    // (4, 8, 12 or 16 chunks in flight per lane: 86 k / 91 k / 92 k / 90 k queries/s on the 1 M-image bench)
+    return launch_query<SQ_TFIDF_L2, 2, 8, 3>(d_post_off, (const uint32_t *)d_postings, d_img_rnorm, n_img, n_shards, d_q_off,
+                                              d_q_node, d_qv, d_q_rnorm, n_query, topk, nullptr, nullptr, 0, n_groups,
+                                              d_group_key, d_group_id, (cudaStream_t)stream);
 }

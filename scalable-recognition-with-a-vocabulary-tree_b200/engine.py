@@ -874,6 +874,20 @@ def score(index: dict, q: dict, topk: int, mode: int = nat.SCORE_TF_L2, q_val: t
         if weights is None or "img_rnorm" not in weights:
             raise ValueError("weighted scoring needs weights=dict(idf=..., img_rnorm=..., norm=...)")
         qw = query_weights(q, weights["idf"], weights["norm"])
+        if mode == nat.SCORE_W_L2 and not want_all and nq > 0:
+            # tf-idf / L2 with the top-k carried from shard to shard (binary64 accumulators, vt_score_query.cu)
+            n_groups = int(groups or lib.vt_score_group_count(nq, n_img))
+            shard_key = torch.empty((nq, n_groups, topk), dtype=torch.float64, device=dev)
+            shard_id = torch.empty((nq, n_groups, topk), dtype=torch.int32, device=dev)
+            nat.check(lib.vt_score_topk_weighted_carried(nat.ptr(index["post_off"]), nat.ptr(index["postings"]),
+                                                         nat.ptr(weights["img_rnorm"]), n_img, index["n_ref"],
+                                                         nat.ptr(q["row_off"]), nat.ptr(q["node"]), nat.ptr(qw["qv"]),
+                                                         nat.ptr(qw["rnorm"]), nq, topk, n_groups, nat.ptr(shard_key),
+                                                         nat.ptr(shard_id), s), "vt_score_topk_weighted_carried")
+            out = dict(all_key=None, shard_key=shard_key, shard_id=shard_id, topk=topk)
+            if merge:
+                out.update(merge_topk(shard_key.view(nq, -1), shard_id.view(nq, -1), nq, topk, mode, q["sumsq"], index["sumsq"]))
+            return out
         nat.check(lib.vt_score_topk_weighted(nat.ptr(index["post_off"]), nat.ptr(index["postings"]),
                                              nat.ptr(weights["img_rnorm"]), n_img, index["n_ref"], nat.ptr(q["row_off"]),
                                              nat.ptr(q["node"]), nat.ptr(qw["qv"]), nat.ptr(qw["qi"]), nat.ptr(qw["rnorm"]),

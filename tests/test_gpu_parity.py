@@ -519,6 +519,24 @@ def test_carried_topk_equals_exhaustive_selection(vt, cuda, groups, shards_per_s
     assert np.array_equal(ids, full["id"].cpu().numpy()) and np.array_equal(sc, full["score"].cpu().numpy())
     for j, src in enumerate(dup_src):                           # the copies tie with the original, smaller index first
         assert sc[j][0] == 0.0 and sc[j][1] == 0.0 and sc[j][2] == 0.0 and list(ids[j][:3]) == sorted(ids[j][:3])
+    if shards_per_step != 1:
+        return
+    # tf-idf / L2 through the same carried kernel with binary64 accumulators: the keys of the full dump (per-shard kernel),
+    # up to the order of the binary64 additions
+    csr = to_csr(m)
+    df = torch.bincount(csr["node"].long(), minlength=n_ref).to(torch.int32)
+    idf = vt.engine.idf_from_df(df, n_img)
+    weights = dict(idf=idf, norm="l2", img_rnorm=vt.engine.weighted_rnorm(csr, idf, "l2"))
+    mode = vt._native.SCORE_W_L2
+    fullw = vt.engine.score(index, q, k, mode=mode, weights=weights, want_all=True)
+    gotw = vt.engine.score(index, q, k, mode=mode, weights=weights, groups=groups)
+    wk, wid, wkey = fullw["all_key"].cpu().numpy(), gotw["id"].cpu().numpy(), gotw["key"].cpu().numpy()
+    for qi in range(len(q_rows)):
+        best = np.sort(wk[qi])[::-1][:k]
+        np.testing.assert_allclose(wkey[qi], best, rtol=1e-12, atol=1e-15)
+        assert len(set(wid[qi].tolist())) == k
+        np.testing.assert_allclose(wk[qi][wid[qi]], wkey[qi], rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(gotw["score"].cpu().numpy(), fullw["score"].cpu().numpy(), rtol=1e-9, atol=1e-12)
 
 
 @pytest.mark.parametrize("norm", ["l2", "l1"])
