@@ -667,7 +667,13 @@ def bench_retrieval(args, torch, vt, engine, nat, dev, rank, world, comm, cent, 
         db1 = vt.Database(qds, voc, weighting=weighting, norm="l2")
         db1._adopt(csr1, {}, db_images, 0)
         ids1, sc1 = db1.retrieve_batch(names[:n_chk], k=topk)
-        same_as_single = bool(np.array_equal(ids1, h_ids[:n_chk]) and np.array_equal(sc1, h_sc[:n_chk]))
+        if weighting == "tf":
+            same_as_single = bool(np.array_equal(ids1, h_ids[:n_chk]) and np.array_equal(sc1, h_sc[:n_chk]))
+        else:
+            # binary64 sums accumulated with shared-memory atomics: equal up to the order of the additions (see e2e above)
+            d_sc = np.abs(sc1 - h_sc[:n_chk])
+            same_as_single = bool((d_sc <= 1e-9 * np.maximum(1.0, np.abs(sc1))).all()
+                                  and ((ids1 == h_ids[:n_chk]) | (d_sc <= 1e-9)).all())
         del db1, csr1
 
     out = {"metric": "queries/s top-10 @%s images" % ("1M" if db_images == 1_000_000 else db_images),
