@@ -685,10 +685,11 @@ def build_index(csr: dict, n_ref: int) -> dict:
     # for leaf-word indexes, thousands once the top tree levels (which list every image) are indexed
     lens = (post_off[1:] - post_off[:-1]).to(torch.float64)
     long_lists = bool(nnz > 0 and float((lens * lens).sum().item()) / float(nnz) > 64.0)
+    run_mean = float(nnz) / max(int((lens > 0).sum().item()), 1)               # postings per non-empty (word, shard) run
     return dict(post_off=post_off, postings=postings[:nnz], rnorm=rnorm[:n_img], sumsq=csr["sumsq"], n_img=n_img,
                 shard_empty=shard_empty, shard_rho=shard_rho, shard_rmax=hi.clamp(min=0.0).contiguous(),
                 max_sumsq=int(csr["sumsq"][:n_img].max().item()) if n_img > 0 else 0,
-                long_lists=long_lists,
+                long_lists=long_lists, run_mean=run_mean,
                 n_ref=n_ref, shard=shard, n_shards=n_shards, nnz=nnz)
 
 
@@ -906,7 +907,9 @@ def score(index: dict, q: dict, topk: int, mode: int = nat.SCORE_TF_L2, q_val: t
         # 16-bit accumulators (two shards per step) when no dot of the batch can reach 65535: |q . d| <= |q| |d|
         if shards_per_step is None:
             bound = float(q["sumsq"].max().item()) * float(index.get("max_sumsq", 1 << 62))
-            shards_per_step = 2 if bound < 65535.0 ** 2 and n_shards > 1 else 1
+            # ... and when the runs are long enough for the longer two-shard runs to pay (measured: runs of ~8 postings 207 k
+            # -> 296 k queries/s; runs of ~1 posting 1.36 M -> 1.24 M, where the one-shard kernel's 4 CTAs per SM win)
+            shards_per_step = 2 if bound < 65535.0 ** 2 and n_shards > 1 and index.get("run_mean", 0.0) >= 3.0 else 1
             if shards_per_step > 1 and os.environ.get("VT_SCORE_SHARDS_PER_STEP"):     # (experiments: 1, 2 or 4)
                 shards_per_step = int(os.environ["VT_SCORE_SHARDS_PER_STEP"])
         shard_key = torch.empty((nq, n_groups, topk), dtype=torch.float64, device=dev)

@@ -465,18 +465,20 @@ def test_score_multi_shard_random_csr(vt, cuda):
         assert ids[qi][0] == qr and sc[qi][0] == 0.0            # self match first, exactly zero
 
 
+@pytest.mark.parametrize("n_ref", [3000, 400_000])
 @pytest.mark.parametrize("shards_per_step", [1, 2, 4])
 @pytest.mark.parametrize("groups", [1, 2, 5])
-def test_carried_topk_equals_exhaustive_selection(vt, cuda, groups, shards_per_step):
+def test_carried_topk_equals_exhaustive_selection(vt, cuda, groups, shards_per_step, n_ref):
     """vt_score_query.cu: a CTA carries the k best of a query from shard to shard and prunes with their worst key.  40 k
     images (5 shards) with planted duplicates (exact key ties across shards, broken by the smaller image index like
     database.py:79-80), images without words, queries with no match at all, long and short posting runs; every grouping
     of the shards must return the order the full key dump gives -- with 32-bit accumulators (one shard per step) and with
-    16-bit accumulators (2 or 4 shards per step, groups that end inside a step)."""
+    16-bit accumulators (2 or 4 shards per step, groups that end inside a step), on an index with runs of ~80 postings and
+    on a sparse one (~0.6 postings per run)."""
     torch = _torch()
     import scipy.sparse as sp
     rng = np.random.default_rng(21 + groups)
-    n_img, n_ref, nnz_per = 40_000, 3000, 30
+    n_img, nnz_per = 40_000, 30                                 # n_ref 3000: runs of ~80 postings per (word, shard); 400 k: ~0.6
     rows = np.repeat(np.arange(n_img), nnz_per)
     cols = rng.integers(0, n_ref, n_img * nnz_per)
     cols[rng.random(len(cols)) < 0.2] = 7                       # one very frequent word: runs of thousands of postings
