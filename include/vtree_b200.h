@@ -291,7 +291,9 @@ int vt_score_topk_seeded(const uint32_t *d_post_off, const void *d_postings, con
  * consecutive shards and keeps the k best (key, id) pairs, whose worst key prunes every later shard.  Output: n_groups
  * lists per query, [n_query, n_groups, topk] (id -1 = empty slot), to be merged by vt_topk_merge with n_cand =
  * n_groups * topk.  vt_score_group_count proposes n_groups for a batch (any value in 1..number of shards is valid).
- * Leaf-word indexes pass d_shard_rmax [n_shards] = max over the shard's images of 1/|d| (0 when all are empty) and
+ * Leaf-word indexes pass d_shard_rmax [n_shards] = max over the shard's images of 1/|d| (0 when all are empty), optionally
+ * d_shard_rmin [n_shards] = the min over its described images (0 when there is none; NULL: a group's first step selects
+ * exhaustively instead of bounding the k-th key from the histogram of its dots) and
  * d_seed = NULL; all-nodes indexes pass d_seed (vt_dense_dots rows, stride seed_stride) and d_shard_rmax = NULL.
  * shards_per_step: 1 = 32-bit accumulators, one shard at a time (always valid); 2 or 4 = that many consecutive shards
  * per step with 16-bit accumulators -- only without seeds and only when the caller knows every dot of the batch stays
@@ -299,9 +301,9 @@ int vt_score_topk_seeded(const uint32_t *d_post_off, const void *d_postings, con
 int vt_score_group_count(int64_t n_query, int64_t n_img);
 int vt_score_topk_carried(const uint32_t *d_post_off, const void *d_postings, const double *d_img_rnorm, int64_t n_img,
                           int64_t n_ref, const int64_t *d_q_off, const int32_t *d_q_node, const float *d_q_val,
-                          int64_t n_query, int topk, const double *d_shard_rmax, const int32_t *d_seed,
-                          int64_t seed_stride, int n_groups, int shards_per_step, double *d_group_key,
-                          int32_t *d_group_id, void *stream);
+                          int64_t n_query, int topk, const double *d_shard_rmax, const double *d_shard_rmin,
+                          const int32_t *d_seed, int64_t seed_stride, int n_groups, int shards_per_step,
+                          double *d_group_key, int32_t *d_group_id, void *stream);
 
 /* ---- dense encoders: any object with embedding(image) (the reference's plugin protocol; its AlexNet encoder,
  * encoders/alexnet.py:15-19) goes through Database.retrieve with dense embeddings.  vt_dense_scores evaluates

@@ -61,7 +61,7 @@ SIGNATURES = {
     "vt_dense_scatter": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _int, _vp, _vp]),
     "vt_dense_dots": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp, _i64, _vp]),
     "vt_score_group_count": (_int, [_i64, _i64]),
-    "vt_score_topk_carried": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _int, _vp, _vp, _i64, _int, _int, _vp, _vp, _vp]),
+    "vt_score_topk_carried": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _i64, _int, _int, _vp, _vp, _vp]),
     "vt_score_topk_seeded": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _int, _vp, _i64, _vp, _vp, _vp, _vp]),
     "vt_dense_scores": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp]),
     "vt_topk_rows": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp, _vp]),

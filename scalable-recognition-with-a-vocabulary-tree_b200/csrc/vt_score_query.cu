@@ -69,7 +69,8 @@ struct SqSharedT {
     double r_key[SQ_WARPS];
     int32_t r_id[SQ_WARPS];
     int r_owner[SQ_WARPS];
-    int ncand, ln;
+    int hist[64];                          // dots of a group's first step (threshold bootstrap)
+    int ncand, ln, boot;
 };
 using SqShared = SqSharedT<int, int>;
 
@@ -97,6 +98,59 @@ __device__ __forceinline__ void sq_block_best(double &key, int32_t &id, int &own
     for (int w = 1; w < SQ_WARPS; ++w)
         if (sq_better(sh.r_key[w], sh.r_id[w], key, id)) { key = sh.r_key[w]; id = sh.r_id[w]; owner = sh.r_owner[w]; }
     __syncthreads();
+}
+
+// Warp 0: insert the nc candidates (sh.cslot / sh.ckey, images img0 + slot) into the carried list (best first, sh.ln entries,
+// at most topk), one at a time; the list stays sorted and (key, id) is a strict total order, so the result does not depend on
+// the order in which the candidates were found.
+template <class Shared>
+__device__ __forceinline__ void sq_insert_candidates(Shared &sh, int nc, int64_t img0, int topk, int lane)
+{
+    int ln = sh.ln;                                            // (warp uniform)
+    for (int i0 = 0; i0 < nc; i0 += 32) {
+        const int i = i0 + lane;
+        const double ck = i < nc ? sh.ckey[i] : -2.0;
+        const int32_t cid = i < nc ? (int32_t)(img0 + sh.cslot[i]) : 0x7fffffff;
+        unsigned int live = __ballot_sync(VT_FULL, i < nc);
+        while (live) {
+            const int src = __ffs(live) - 1;
+            live &= live - 1;
+            const double k = __shfl_sync(VT_FULL, ck, src);
+            const int32_t id = __shfl_sync(VT_FULL, cid, src);
+            const bool h0 = lane < ln, h1 = lane + 32 < ln;
+            const double k0 = h0 ? sh.lkey[lane] : 0.0, k1 = h1 ? sh.lkey[lane + 32] : 0.0;
+            const int32_t d0 = h0 ? sh.lid[lane] : 0, d1 = h1 ? sh.lid[lane + 32] : 0;
+            const bool b0 = h0 && sq_better(k0, d0, k, id), b1 = h1 && sq_better(k1, d1, k, id);
+            const int pos = __popc(__ballot_sync(VT_FULL, b0)) + __popc(__ballot_sync(VT_FULL, b1));
+            if (pos < topk) {                                  // entries from pos on move down by one, a full list drops its last
+                __syncwarp();
+                if (h0 && !b0 && lane + 1 < topk) { sh.lkey[lane + 1] = k0; sh.lid[lane + 1] = d0; }
+                if (h1 && !b1 && lane + 33 < topk) { sh.lkey[lane + 33] = k1; sh.lid[lane + 33] = d1; }
+                __syncwarp();
+                if (lane == 0) { sh.lkey[pos] = k; sh.lid[pos] = id; }
+                __syncwarp();
+                if (ln < topk) ++ln;
+            }
+        }
+    }
+    if (lane == 0) sh.ln = ln;
+}
+
+// Warp 0, after sh.hist holds the histogram of the step's dots >= 1 (clamped at 63): the largest b >= 1 such that at least
+// topk images of the step have a dot >= b (0 if there is none).  Those images have keys >= b * (smallest 1/|d| of the step),
+// a valid lower bound of the final k-th key: a group's first step can prune with it instead of selecting exhaustively.
+template <class Shared>
+__device__ __forceinline__ void sq_bootstrap_bin(Shared &sh, int topk, int lane)
+{
+    int hi = sh.hist[63 - lane], lo = lane < 31 ? sh.hist[31 - lane] : 0;     // (bin 0 is not a bound)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t1 = __shfl_up_sync(VT_FULL, hi, o), t2 = __shfl_up_sync(VT_FULL, lo, o);
+        if (lane >= o) { hi += t1; lo += t2; }
+    }
+    lo += __shfl_sync(VT_FULL, hi, 31);
+    const unsigned int mh = __ballot_sync(VT_FULL, hi >= topk), ml = __ballot_sync(VT_FULL, lo >= topk);
+    if (lane == 0) sh.boot = mh ? 63 - (__ffs(mh) - 1) : (ml ? 31 - (__ffs(ml) - 1) : 0);
 }
 
 // acc[local image of the posting] += (tf of the posting) * (tf of the query word), predicated: one `red.shared` under a
@@ -130,8 +184,9 @@ __global__ void __launch_bounds__(SQ_THREADS, MINB)
 score_query_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__restrict__ postings,
                    const double *__restrict__ img_rnorm, int64_t n_img, int n_shards, const int64_t *__restrict__ q_off,
                    const int32_t *__restrict__ q_node, const void *__restrict__ q_val_, const double *__restrict__ q_rnorm,
-                   int64_t n_query, int topk, const double *__restrict__ shard_rmax, const int32_t *__restrict__ seed,
-                   int64_t seed_stride, int n_groups, int per_group, double *__restrict__ out_key, int32_t *__restrict__ out_id)
+                   int64_t n_query, int topk, const double *__restrict__ shard_rmax, const double *__restrict__ shard_rmin,
+                   const int32_t *__restrict__ seed, int64_t seed_stride, int n_groups, int per_group,
+                   double *__restrict__ out_key, int32_t *__restrict__ out_id)
 {
     typedef typename SqTypes<MODE>::A A;                   // accumulator
     typedef typename SqTypes<MODE>::W W;                   // per-word query factor
@@ -326,7 +381,27 @@ score_query_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__rest
 
             // ---- selection against the carried list ------------------------------------------------------------------
             const int ln = sh.ln;
-            const double T = ln == topk ? sh.lkey[topk - 1] : -1.0;
+            double T = ln == topk ? sh.lkey[topk - 1] : -1.0;
+            if constexpr (MODE == SQ_TF) {
+                // first step of a group (empty list): bound the k-th key from the histogram of the step's dots
+                const double rmin = (ln == 0 && shard_rmin) ? __ldg(shard_rmin + shard) : 0.0;
+                if (rmin > 0.0) {                                  // (block uniform)
+                    if (tid < 64) sh.hist[tid] = 0;
+                    __syncthreads();
+                    const int4 *h4 = reinterpret_cast<const int4 *>(sh.acc);
+                    for (int u = 0; u < SQ_PER / 4; ++u) {
+                        const int4 a = h4[u * SQ_THREADS + tid];
+                        const int av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (av[i] >= 1) atomicAdd(&sh.hist[av[i] < 63 ? av[i] : 63], 1);
+                    }
+                    __syncthreads();
+                    if (warp == 0) sq_bootstrap_bin(sh, topk, lane);
+                    __syncthreads();
+                    if (sh.boot >= 1) T = (double)sh.boot * rmin;
+                }
+            }
             bool exhaustive = !(T > 0.0);                          // nothing can be pruned: untouched images reach T
             if (!exhaustive) {
                 if constexpr (EXACT_FILTER) {
@@ -382,34 +457,7 @@ score_query_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__rest
                         }
                         __syncthreads();
                     }
-                    if (warp == 0) {
-                        // insert the candidates that beat the current worst entry, one at a time (the list stays sorted)
-                        for (int i0 = 0; i0 < nc; i0 += 32) {
-                            const int i = i0 + lane;
-                            const double ck = i < nc ? sh.ckey[i] : -2.0;
-                            const int32_t cid = i < nc ? (int32_t)(img0 + sh.cslot[i]) : 0x7fffffff;
-                            unsigned int live = __ballot_sync(VT_FULL, i < nc);
-                            while (live) {
-                                const int src = __ffs(live) - 1;
-                                live &= live - 1;
-                                const double k = __shfl_sync(VT_FULL, ck, src);
-                                const int32_t id = __shfl_sync(VT_FULL, cid, src);
-                                const bool h0 = lane < topk, h1 = lane + 32 < topk;
-                                const double k0 = h0 ? sh.lkey[lane] : 0.0, k1 = h1 ? sh.lkey[lane + 32] : 0.0;
-                                const int32_t d0 = h0 ? sh.lid[lane] : 0, d1 = h1 ? sh.lid[lane + 32] : 0;
-                                const bool b0 = h0 && sq_better(k0, d0, k, id), b1 = h1 && sq_better(k1, d1, k, id);
-                                const int pos = __popc(__ballot_sync(VT_FULL, b0)) + __popc(__ballot_sync(VT_FULL, b1));
-                                if (pos < topk) {                  // entries from pos on move down by one, the last one drops
-                                    __syncwarp();
-                                    if (h0 && !b0 && lane + 1 < topk) { sh.lkey[lane + 1] = k0; sh.lid[lane + 1] = d0; }
-                                    if (h1 && !b1 && lane + 33 < topk) { sh.lkey[lane + 33] = k1; sh.lid[lane + 33] = d1; }
-                                    __syncwarp();
-                                    if (lane == 0) { sh.lkey[pos] = k; sh.lid[pos] = id; }
-                                    __syncwarp();
-                                }
-                            }
-                        }
-                    }
+                    if (warp == 0) sq_insert_candidates(sh, nc, img0, topk, lane);
                 }
             }
             if (exhaustive) {
@@ -492,7 +540,8 @@ struct Sq16Shared {
     double r_key[SQ_WARPS];
     int32_t r_id[SQ_WARPS];
     int r_owner[SQ_WARPS];
-    int ncand, ln;
+    int hist[64];                          // dots of a group's first step (threshold bootstrap)
+    int ncand, ln, boot;
 };
 
 // acc16[x] += val (x = image of the step, val < 65536 and the sum stays below 65536): one 32-bit reduction on the word
@@ -509,8 +558,8 @@ __global__ void __launch_bounds__(SQ_THREADS, MINB)
 score_query16_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__restrict__ postings,
                      const double *__restrict__ img_rnorm, int64_t n_img, int n_shards, const int64_t *__restrict__ q_off,
                      const int32_t *__restrict__ q_node, const float *__restrict__ q_val, int64_t n_query, int topk,
-                     const double *__restrict__ shard_rmax, int n_groups, int per_group, double *__restrict__ out_key,
-                     int32_t *__restrict__ out_id)
+                     const double *__restrict__ shard_rmax, const double *__restrict__ shard_rmin, int n_groups, int per_group,
+                     double *__restrict__ out_key, int32_t *__restrict__ out_id)
 {
     static_assert(NS == 2 || NS == 4, "shards per step");
     static_assert(SQ_SUB % NS == 0, "a step must not straddle two pointer sub-groups");
@@ -694,7 +743,37 @@ score_query16_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__re
 
             // ---- selection against the carried list ------------------------------------------------------------------
             const int ln = sh.ln;
-            const double T = ln == topk ? sh.lkey[topk - 1] : -1.0;
+            double T = ln == topk ? sh.lkey[topk - 1] : -1.0;
+            {
+                // first step of a group (empty list): bound the k-th key from the histogram of the step's dots
+                double rmin = 0.0;
+                if (ln == 0 && shard_rmin) {
+                    rmin = 1e300;
+                    for (int j = 0; j < ns_here; ++j) {
+                        const double r = __ldg(shard_rmin + shard + j);
+                        if (r > 0.0) rmin = fmin(rmin, r);         // (a shard without any described image bounds nothing)
+                    }
+                    if (rmin == 1e300) rmin = 0.0;
+                }
+                if (rmin > 0.0) {                                  // (block uniform)
+                    if (tid < 64) sh.hist[tid] = 0;
+                    __syncthreads();
+                    const uint4 *h4 = reinterpret_cast<const uint4 *>(sh.acc);
+                    for (int u = 0; u < PER / 8; ++u) {
+                        const uint4 a = h4[u * SQ_THREADS + tid];
+                        const uint32_t av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const uint32_t d = (av[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
+                            if (d >= 1u) atomicAdd(&sh.hist[d < 63u ? d : 63u], 1);
+                        }
+                    }
+                    __syncthreads();
+                    if (warp == 0) sq_bootstrap_bin(sh, topk, lane);
+                    __syncthreads();
+                    if (sh.boot >= 1) T = (double)sh.boot * rmin;
+                }
+            }
             bool exhaustive = !(T > 0.0);
             if (!exhaustive) {
                 double rmax = 0.0;
@@ -735,33 +814,7 @@ score_query16_kernel(const uint32_t *__restrict__ post_off, const uint32_t *__re
                         sh.ckey[i] = (double)half_of(x) * __ldg(img_rnorm + img0 + x);
                     }
                     __syncthreads();
-                    if (warp == 0) {
-                        for (int i0 = 0; i0 < nc; i0 += 32) {
-                            const int i = i0 + lane;
-                            const double ck = i < nc ? sh.ckey[i] : -2.0;
-                            const int32_t cid = i < nc ? (int32_t)(img0 + sh.cslot[i]) : 0x7fffffff;
-                            unsigned int live = __ballot_sync(VT_FULL, i < nc);
-                            while (live) {
-                                const int src = __ffs(live) - 1;
-                                live &= live - 1;
-                                const double k = __shfl_sync(VT_FULL, ck, src);
-                                const int32_t id = __shfl_sync(VT_FULL, cid, src);
-                                const bool h0 = lane < topk, h1 = lane + 32 < topk;
-                                const double k0 = h0 ? sh.lkey[lane] : 0.0, k1 = h1 ? sh.lkey[lane + 32] : 0.0;
-                                const int32_t d0 = h0 ? sh.lid[lane] : 0, d1 = h1 ? sh.lid[lane + 32] : 0;
-                                const bool b0 = h0 && sq_better(k0, d0, k, id), b1 = h1 && sq_better(k1, d1, k, id);
-                                const int pos = __popc(__ballot_sync(VT_FULL, b0)) + __popc(__ballot_sync(VT_FULL, b1));
-                                if (pos < topk) {
-                                    __syncwarp();
-                                    if (h0 && !b0 && lane + 1 < topk) { sh.lkey[lane + 1] = k0; sh.lid[lane + 1] = d0; }
-                                    if (h1 && !b1 && lane + 33 < topk) { sh.lkey[lane + 33] = k1; sh.lid[lane + 33] = d1; }
-                                    __syncwarp();
-                                    if (lane == 0) { sh.lkey[pos] = k; sh.lid[pos] = id; }
-                                    __syncwarp();
-                                }
-                            }
-                        }
-                    }
+                    if (warp == 0) sq_insert_candidates(sh, nc, img0, topk, lane);
                 }
             }
             if (exhaustive) {
@@ -839,8 +892,8 @@ extern "C" int vt_score_group_count(int64_t n_query, int64_t n_img)
 template <int MODE, int MINB = 4, int U = SQ_U, int G = SQ_G>
 static int launch_query(const uint32_t *post_off, const uint32_t *postings, const double *img_rnorm, int64_t n_img, int n_shards,
                         const int64_t *q_off, const int32_t *q_node, const void *q_val, const double *q_rnorm, int64_t n_query,
-                        int topk, const double *shard_rmax, const int32_t *seed, int64_t seed_stride, int n_groups,
-                        double *out_key, int32_t *out_id, cudaStream_t s)
+                        int topk, const double *shard_rmax, const double *shard_rmin, const int32_t *seed, int64_t seed_stride,
+                        int n_groups, double *out_key, int32_t *out_id, cudaStream_t s)
 {
     auto kern = score_query_kernel<MODE, MINB, U, G>;
     const size_t smem = sizeof(SqSharedT<typename SqTypes<MODE>::A, typename SqTypes<MODE>::W>);
@@ -848,8 +901,8 @@ static int launch_query(const uint32_t *post_off, const uint32_t *postings, cons
     const int per_group = (n_shards + n_groups - 1) / n_groups;
     const int64_t items = n_query * n_groups, cap = (int64_t)vt_sm_count() * MINB;
     kern<<<(int)(items < cap ? items : cap), SQ_THREADS, smem, s>>>(post_off, postings, img_rnorm, n_img, n_shards, q_off, q_node,
-                                                                    q_val, q_rnorm, n_query, topk, shard_rmax, seed, seed_stride,
-                                                                    n_groups, per_group, out_key, out_id);
+                                                                    q_val, q_rnorm, n_query, topk, shard_rmax, shard_rmin, seed,
+                                                                    seed_stride, n_groups, per_group, out_key, out_id);
     VT_LAUNCH_CHECK();
     return VT_OK;
 }
@@ -857,7 +910,8 @@ static int launch_query(const uint32_t *post_off, const uint32_t *postings, cons
 template <int NS, int MINB, int U = SQ_U>
 static int launch_query16(const uint32_t *post_off, const uint32_t *postings, const double *img_rnorm, int64_t n_img,
                           int n_shards, const int64_t *q_off, const int32_t *q_node, const float *q_val, int64_t n_query,
-                          int topk, const double *shard_rmax, int n_groups, double *out_key, int32_t *out_id, cudaStream_t s)
+                          int topk, const double *shard_rmax, const double *shard_rmin, int n_groups, double *out_key,
+                          int32_t *out_id, cudaStream_t s)
 {
     auto kern = score_query16_kernel<NS, MINB, U>;
     const size_t smem = sizeof(Sq16Shared<NS>);
@@ -865,8 +919,8 @@ static int launch_query16(const uint32_t *post_off, const uint32_t *postings, co
     const int per_group = (n_shards + n_groups - 1) / n_groups;
     const int64_t items = n_query * n_groups, cap = (int64_t)vt_sm_count() * MINB;
     kern<<<(int)(items < cap ? items : cap), SQ_THREADS, smem, s>>>(post_off, postings, img_rnorm, n_img, n_shards, q_off, q_node,
-                                                                    q_val, n_query, topk, shard_rmax, n_groups, per_group,
-                                                                    out_key, out_id);
+                                                                    q_val, n_query, topk, shard_rmax, shard_rmin, n_groups,
+                                                                    per_group, out_key, out_id);
     VT_LAUNCH_CHECK();
     return VT_OK;
 }
@@ -874,8 +928,8 @@ static int launch_query16(const uint32_t *post_off, const uint32_t *postings, co
 extern "C" int vt_score_topk_carried(const uint32_t *d_post_off, const void *d_postings, const double *d_img_rnorm,
                                      int64_t n_img, int64_t n_ref, const int64_t *d_q_off, const int32_t *d_q_node,
                                      const float *d_q_val, int64_t n_query, int topk, const double *d_shard_rmax,
-                                     const int32_t *d_seed, int64_t seed_stride, int n_groups, int shards_per_step,
-                                     double *d_group_key, int32_t *d_group_id, void *stream)
+                                     const double *d_shard_rmin, const int32_t *d_seed, int64_t seed_stride, int n_groups,
+                                     int shards_per_step, double *d_group_key, int32_t *d_group_id, void *stream)
 {
     VT_CHECK_ARG(shards_per_step == 1 || ((shards_per_step == 2 || shards_per_step == 4) && d_seed == nullptr),
                  "shards_per_step is 1, or 2 / 4 (16-bit accumulators: leaf-word indexes whose dots stay below 65535)");
@@ -892,16 +946,16 @@ extern "C" int vt_score_topk_carried(const uint32_t *d_post_off, const void *d_p
     // 268 k, <2, 3, 12> 300-310 k, <2, 3, 16> 270 k, <2, 2, 16> 206 k, <4, 2, 8> 201 k: instruction-level parallelism beats warps
     if (shards_per_step == 2)
         return launch_query16<2, 3, 12>(d_post_off, po, d_img_rnorm, n_img, n_shards, d_q_off, d_q_node, d_q_val, n_query, topk,
-                                    d_shard_rmax, n_groups, d_group_key, d_group_id, s);
+                                        d_shard_rmax, d_shard_rmin, n_groups, d_group_key, d_group_id, s);
     if (shards_per_step == 4)
         return launch_query16<4, 2>(d_post_off, po, d_img_rnorm, n_img, n_shards, d_q_off, d_q_node, d_q_val, n_query, topk,
-                                    d_shard_rmax, n_groups, d_group_key, d_group_id, s);
+                                    d_shard_rmax, d_shard_rmin, n_groups, d_group_key, d_group_id, s);
     // (all-nodes indexes: 3 CTAs with 8 or 12 chunks in flight, or 6 long runs at a time, measured within 2 % or slower)
     if (d_seed)
         return launch_query<SQ_TF_SEEDED>(d_post_off, po, d_img_rnorm, n_img, n_shards, d_q_off, d_q_node, d_q_val, nullptr, n_query,
-                                          topk, nullptr, d_seed, seed_stride, n_groups, d_group_key, d_group_id, s);
+                                          topk, nullptr, nullptr, d_seed, seed_stride, n_groups, d_group_key, d_group_id, s);
     return launch_query<SQ_TF>(d_post_off, po, d_img_rnorm, n_img, n_shards, d_q_off, d_q_node, d_q_val, nullptr, n_query, topk,
-                               d_shard_rmax, nullptr, 0, n_groups, d_group_key, d_group_id, s);
+                               d_shard_rmax, d_shard_rmin, nullptr, 0, n_groups, d_group_key, d_group_id, s);
 }
 
 // tf-idf / L2 (VT_SCORE_W_L2) with the carried top-k: binary64 accumulators (64 KB per shard: 2 CTAs per SM, 8 chunks in
@@ -919,6 +973,6 @@ extern "C" int vt_score_topk_weighted_carried(const uint32_t *d_post_off, const 
     if (n_query == 0) return VT_OK;
     // (4, 8, 12 or 16 chunks in flight per lane: 86 k / 91 k / 92 k / 90 k queries/s on the 1 M-image bench)
     return launch_query<SQ_TFIDF_L2, 2, 8, 3>(d_post_off, (const uint32_t *)d_postings, d_img_rnorm, n_img, n_shards, d_q_off,
-                                              d_q_node, d_qv, d_q_rnorm, n_query, topk, nullptr, nullptr, 0, n_groups,
+                                              d_q_node, d_qv, d_q_rnorm, n_query, topk, nullptr, nullptr, nullptr, 0, n_groups,
                                               d_group_key, d_group_id, (cudaStream_t)stream);
 }

@@ -679,6 +679,9 @@ def build_index(csr: dict, n_ref: int) -> dict:
     rn = rnorm[:n_img]
     lo = torch.cat([rn, rn.new_full((pad,), float("inf"))]).view(n_shards, shard).min(1).values
     hi = torch.cat([rn, rn.new_full((pad,), 0.0)]).view(n_shards, shard).max(1).values
+    pos = torch.where(rn > 0, rn, rn.new_full((), float("inf")))             # described images only
+    rmin = torch.cat([pos, pos.new_full((pad,), float("inf"))]).view(n_shards, shard).min(1).values
+    rmin = torch.where(torch.isinf(rmin), torch.zeros_like(rmin), rmin * (1.0 - 1e-12)).contiguous()
     shard_rho = torch.where((shard_empty == 0) & (hi > 0), lo / hi.clamp(min=1e-300) * (1.0 - 1e-9),
                             torch.full_like(lo, -1.0)).contiguous()
     # size-biased mean length of a (node, shard) posting run = the run a random posting sits in: a few postings
@@ -687,7 +690,7 @@ def build_index(csr: dict, n_ref: int) -> dict:
     long_lists = bool(nnz > 0 and float((lens * lens).sum().item()) / float(nnz) > 64.0)
     run_mean = float(nnz) / max(int((lens > 0).sum().item()), 1)               # postings per non-empty (word, shard) run
     return dict(post_off=post_off, postings=postings[:nnz], rnorm=rnorm[:n_img], sumsq=csr["sumsq"], n_img=n_img,
-                shard_empty=shard_empty, shard_rho=shard_rho, shard_rmax=hi.clamp(min=0.0).contiguous(),
+                shard_empty=shard_empty, shard_rho=shard_rho, shard_rmax=hi.clamp(min=0.0).contiguous(), shard_rmin=rmin,
                 max_sumsq=int(csr["sumsq"][:n_img].max().item()) if n_img > 0 else 0,
                 long_lists=long_lists, run_mean=run_mean,
                 n_ref=n_ref, shard=shard, n_shards=n_shards, nnz=nnz)
@@ -813,7 +816,7 @@ def score_dense(dense: dict, q: dict, topk: int, want_all: bool = False, d_budge
             shard_id = torch.empty((c1 - c0, n_groups, topk), dtype=torch.int32, device=dev)
             nat.check(lib.vt_score_topk_carried(nat.ptr(index["post_off"]), nat.ptr(index["postings"]), nat.ptr(index["rnorm"]),
                                                 n_img, index["n_ref"], nat.ptr(off), nat.ptr(qs["node"][b:]), nat.ptr(q_val[b:]),
-                                                c1 - c0, topk, None, nat.ptr(seed), np_, n_groups, 1, nat.ptr(shard_key),
+                                                c1 - c0, topk, None, None, nat.ptr(seed), np_, n_groups, 1, nat.ptr(shard_key),
                                                 nat.ptr(shard_id), s), "vt_score_topk_carried")
             m = merge_topk(shard_key.view(c1 - c0, -1), shard_id.view(c1 - c0, -1), c1 - c0, topk, nat.SCORE_TF_L2,
                            q["sumsq"][c0:c1].contiguous(), index["sumsq"])
@@ -916,7 +919,8 @@ def score(index: dict, q: dict, topk: int, mode: int = nat.SCORE_TF_L2, q_val: t
         shard_id = torch.empty((nq, n_groups, topk), dtype=torch.int32, device=dev)
         nat.check(lib.vt_score_topk_carried(nat.ptr(index["post_off"]), nat.ptr(index["postings"]), nat.ptr(index["rnorm"]),
                                             n_img, index["n_ref"], nat.ptr(q["row_off"]), nat.ptr(q["node"]), nat.ptr(q_val),
-                                            nq, topk, nat.ptr(index["shard_rmax"]), None, 0, n_groups, int(shards_per_step),
+                                            nq, topk, nat.ptr(index["shard_rmax"]), nat.ptr(index.get("shard_rmin")), None, 0,
+                                            n_groups, int(shards_per_step),
                                             nat.ptr(shard_key), nat.ptr(shard_id), s), "vt_score_topk_carried")
         out = dict(all_key=None, shard_key=shard_key, shard_id=shard_id, topk=topk)
         if merge:
