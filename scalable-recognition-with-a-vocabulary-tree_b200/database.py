@@ -375,26 +375,28 @@ class Database(object):
     query_chunk = 2048      # queries per pipeline stage of a large ``retrieve_batch``
 
     def _retrieve_batch_pipelined(self, query_paths, k):
-        """Large query batches go through in chunks: a loader thread reads, describes and packs the images of chunk c+1
-        into pinned memory (``_load_batch``, alternating staging slots) while the device uploads, quantises, encodes and
-        scores chunk c -- the host packing, not the device, is what a one-shot batch waits for.  Same results, chunk by
-        chunk; the ids and scores stay on the device until the end."""
+        """Large query batches go through in chunks: two loader threads read, describe and pack the images of chunks c+1
+        and c+2 into pinned memory (``_load_batch``, three rotating staging slots) while the device uploads, quantises,
+        encodes and scores chunk c -- the host packing, not the device, is what a one-shot batch waits for.  Same results,
+        chunk by chunk; the ids and scores stay on the device until the end."""
         import torch
         from concurrent.futures import ThreadPoolExecutor
         step = int(self.query_chunk)
         chunks = [query_paths[c0:c0 + step] for c0 in range(0, len(query_paths), step)]
 
+        depth = 2                                            # chunks being packed ahead of the one on the device
+
         def stage(ci):
             missing = self._missing(chunks[ci])
-            return missing, (self._load_batch(missing, "q%d" % (ci % 2)) if missing else None)
+            return missing, (self._load_batch(missing, "q%d" % (ci % (depth + 1))) if missing else None)
 
         ids_parts, sc_parts = [], []
-        with ThreadPoolExecutor(max_workers=1) as pool:
-            pending = pool.submit(stage, 0)
+        with ThreadPoolExecutor(max_workers=depth) as pool:
+            pending = [pool.submit(stage, ci) for ci in range(min(depth, len(chunks)))]
             for ci in range(len(chunks)):
-                prestaged = pending.result()
-                if ci + 1 < len(chunks):
-                    pending = pool.submit(stage, ci + 1)
+                prestaged = pending.pop(0).result()
+                if ci + depth < len(chunks):
+                    pending.append(pool.submit(stage, ci + depth))
                 q, back = self._query_csr(chunks[ci], prestaged=prestaged)
                 ids_t, sc_t, _ = self._score_global(q, k)
                 back_t = torch.from_numpy(back).to(ids_t.device)

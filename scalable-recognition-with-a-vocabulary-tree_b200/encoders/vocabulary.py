@@ -32,7 +32,7 @@ def _pack_threads() -> int:
         n = len(os.sched_getaffinity(0))
     except AttributeError:
         n = os.cpu_count() or 1
-    return max(1, min(8, n))
+    return max(1, min(16, n))
 
 
 class VocabularyTree(object):
