@@ -23,11 +23,12 @@ import numpy as np
 
 from . import _native as nat
 from . import engine
+from . import utils
 from .dataset import Dataset
 
 
 class Database(object):
-    def __init__(self, dataset, encoder, *, weighting="tf", norm="l2", comm=None, dense_top=True):
+    def __init__(self, dataset, encoder, *, weighting="tf", norm="l2", comm=None, dense_top=True, record_postings=False):
         # public:
         if isinstance(dataset, Dataset):
             self.dataset = dataset
@@ -48,6 +49,12 @@ class Database(object):
         # by one tcgen05 GEMM per query batch, only the deep levels are posting lists (csrc/vt_dense.cu)
         self.dense_top = bool(dense_top)
         self._dense_index = None
+        # strict parity with the reference's side effects (opt-in, host work per image): its ``Database.embedding`` calls
+        # ``encoder.embedding(image)``, which PROPAGATES the image -- indexed images and queries alike -- into the tree's
+        # per-node ``{image sha1: count}`` postings (vocabulary.py:126-127, :96-100).  With ``record_postings`` the same
+        # entries appear in ``encoder.postings()`` / ``encoder.graph`` (and in what ``encoder.save`` writes).  Retrieval
+        # results never depend on it, here or in the reference.
+        self.record_postings = bool(record_postings)
 
         # private:
         self._rows = {}           # image path -> row in this rank's indexed CSR
@@ -114,7 +121,19 @@ class Database(object):
                     pending = pool.submit(self._load_batch, batches[bi + 1], (bi + 1) & 1)
                 parts.append(self.encoder.encode_batch(None, want_df=True, staged=staged))
         self._adopt(engine.concat_csr(parts), {p: i for i, p in enumerate(local)}, len(paths), lo)
+        self._record(local)
         return
+
+    def _record(self, image_paths):
+        """``record_postings``: the visit counts of these images under their content hash, as ``VocabularyTree.propagate``
+        leaves them (idempotent per image content)."""
+        if not self.record_postings or self._dense or not hasattr(self.encoder, "_propagated"):
+            return
+        for p in image_paths:
+            image_id = utils.get_image_id(self.dataset.read_image(p))
+            if image_id not in self.encoder._propagated:
+                nodes, counts = self._sparse(p)
+                self.encoder._propagated[image_id] = (np.asarray(nodes, np.int32), np.asarray(counts, np.int32))
 
     def _adopt(self, csr, rows, n_images, img_base, df=None):
         """device forward CSR of this rank's images -> inverted file, weights, bookkeeping."""
@@ -358,6 +377,7 @@ class Database(object):
         if not return_all and len(query_paths) > 2 * self.query_chunk:
             return self._retrieve_batch_pipelined(query_paths, k)
         q, back = self._query_csr(query_paths)
+        self._record(query_paths)
         ids_t, sc_t, out = self._score_global(q, k, return_all)
         ids, sc = ids_t.cpu().numpy()[back], sc_t.cpu().numpy()[back]
         if return_all:
@@ -398,6 +418,7 @@ class Database(object):
                 if ci + depth < len(chunks):
                     pending.append(pool.submit(stage, ci + depth))
                 q, back = self._query_csr(chunks[ci], prestaged=prestaged)
+                self._record(chunks[ci])
                 ids_t, sc_t, _ = self._score_global(q, k)
                 back_t = torch.from_numpy(back).to(ids_t.device)
                 ids_parts.append(ids_t[back_t])
@@ -451,6 +472,7 @@ class Database(object):
         if self._csr is None:
             self.index()
         q, _ = self._query_csr([query_image_path])
+        self._record([query_image_path])
         out = self._score_local(q, 1, True)
         keys = self._all_keys_global(out["all_key"])[0].cpu().numpy()
         scores = self._scores_from_keys(keys, int(q["sumsq"][0].item()))

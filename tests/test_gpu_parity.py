@@ -992,3 +992,42 @@ def test_pipelined_retrieve_batch_equals_one_shot(vt, cuda):
     ids, sc = db.retrieve_batch(paths, k=5)
     assert np.array_equal(ids, one_ids) and np.array_equal(sc, one_sc)
     assert all(sc[j][0] == 0.0 for j, i in enumerate(order) if i < n_db and len(images[i]))
+
+
+def test_record_postings_reproduces_the_reference_side_effect(vt, cuda):
+    """vocabulary.py:126-127: the reference's embedding() propagates every image it sees -- database images and queries --
+    into the tree's per-node {image sha1: count} postings (vocabulary.py:96-100).  Opt-in here (Database(record_postings=
+    True)); the postings then equal the golden visit counts image by image, a query that is not in the database appears
+    after it was retrieved, and without the flag nothing is recorded.  Retrieval results are the same either way."""
+    ft, g, meta, images = _flat_from_golden(vt, "small")
+    counts = g["counts"].astype(np.int64)
+    extra = np.concatenate([images[0][:7], images[1][:5]])
+    ds = vt.ArrayDataset(list(images) + [extra])
+    plain_voc = vt.encoders.VocabularyTree(ft.k, ft.depth, descriptor=lambda im: im).set_tree(ft)
+    plain = vt.Database(vt.ArrayDataset(list(images)), plain_voc)
+    plain.index()
+    plain.dataset = ds
+    want_ids, want_sc = plain.retrieve_batch(ds.image_paths, k=4)
+    assert plain_voc.postings() == {}
+    voc = vt.encoders.VocabularyTree(ft.k, ft.depth, descriptor=lambda im: im).set_tree(ft)
+    db = vt.Database(vt.ArrayDataset(list(images)), voc, record_postings=True)
+    db.index()
+    post = voc.postings()
+    for i, im in enumerate(images):
+        key = vt.utils.get_image_id(im)
+        got = np.zeros(ft.n_ref, np.int64)
+        for node, by_image in post.items():
+            if key in by_image:
+                got[node] = by_image[key]
+        assert np.array_equal(got, counts[i]), i
+    q_key = vt.utils.get_image_id(extra)
+    assert not any(q_key in by_image for by_image in post.values())
+    db.dataset = ds
+    ids, sc = db.retrieve_batch(ds.image_paths, k=4)
+    assert np.array_equal(ids, want_ids) and np.array_equal(sc, want_sc)
+    ot = oracle_tree_from_flat(ft)
+    got = np.zeros(ft.n_ref, np.int64)
+    for node, by_image in voc.postings().items():
+        if q_key in by_image:
+            got[node] = by_image[q_key]
+    assert np.array_equal(got, vo.path_counts(ot, extra, all_nodes=True))
