@@ -226,8 +226,11 @@ encode_kernel(const int32_t *__restrict__ word, const int64_t *__restrict__ img_
             __syncthreads();
             m = m2;
         }
-        // per-image statistics
-        atomicAdd(&s_sq, sq);
+        // per-image statistics: warp sums first -- a 64-bit shared-memory atomicAdd is a compare-and-swap loop, and 256
+        // threads spinning on one word were 25 % of the kernel's instructions (ncu)
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) sq += __shfl_xor_sync(VT_FULL, sq, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&s_sq, sq);
         __syncthreads();
         if (threadIdx.x == 0) {
             if (nnz_out) nnz_out[img] = (int32_t)emitted;
