@@ -2,20 +2,18 @@
 // cbir/database.py:59-81), batched over queries.
 //
 // The database is sharded by image range (shard_size images, the same rule that shards it across
-// GPUs).  One CTA scores one (query, shard) pair: its lanes walk the posting lists of the query's
-// words inside that shard (node-major CSR, 4 B per posting: tf << 13 | local image id) with
-// several words and postings in flight per lane, accumulate the sparse dot products of all shard
-// images in shared memory, and select the shard's top-k -- in tf mode (the reference's semantics,
-// score_shard_tf_kernel) through an exact integer bound so that only a few dozen survivors need a
-// binary64 rank key; the float tf-idf / L1 modes and the full score dump use the exhaustive
-// score_shard_kernel.  A second kernel merges the per-shard lists of a query and turns keys into the
-// reference's score (database.py:66-70: L2 distance of the L2-normalised vectors, NaN -> 1e6).
-// Algorithmic HBM traffic per query: 8 B x (sum of the posting lengths of its words) + 8 B per (word, shard)
-// row-pointer pair.  Measured (ncu, 1 M images, leaf words): 2.7x that -- a (word, shard) run is ~8 postings, so
-// 32 B sectors around 64 B runs and 8 B pointer pairs dominate -- at 3.2 TB/s, issue slots 27 % busy: the
-// kernel is bound by the two dependent DRAM round trips per word at ~1 warp instruction per posting, not by
-// the shared-memory atomics (9 % of their peak).  Long runs (all-nodes indexes) are walked by whole warps
-// and move 460 G postings/s.
+// GPUs).  The kernels of THIS file give every (query, shard) pair a CTA of its own and write one top-k list per pair:
+// lanes walk the posting lists of the query's words inside that shard (node-major CSR, 4 B per posting: tf << 13 | local
+// image id), accumulate the sparse dot products of all shard images in shared memory, and select the shard's top-k --
+// score_shard_tf_kernel through an exact integer bound from a histogram of the dots, score_shard_kernel exhaustively
+// (and with the full key dump `retrieve()` needs).  Since round 2 the DEFAULT scorer is vt_score_query.cu (a CTA carries a
+// query's top-k from shard to shard); these kernels remain for the full key dump, for indexes built without the shard
+// bounds, and as the per-shard reference the carried kernels are tested against.  topk_merge_kernel merges the lists of a
+// query (per shard or per group) and turns keys into the reference's score (database.py:66-70: L2 distance of the
+// L2-normalised vectors, NaN -> 1e6).
+// Measured on the round-1 version (8-byte postings; ncu, 1 M images, leaf words): 2.7x the algorithmic traffic -- a
+// (word, shard) run is ~8 postings, so 32 B sectors around the runs and 8 B pointer pairs dominate -- at 3.2 TB/s, issue
+// slots 27 % busy: bound by the dependent DRAM round trips per word, not by the shared-memory atomics.
 //
 // Rank key (larger is better), ties broken by smaller image index like the reference's stable
 // ascending sort (database.py:79-80):
